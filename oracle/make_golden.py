@@ -1,0 +1,161 @@
+"""Generate tests/golden/ from the UNMODIFIED reference (build container only).
+
+    python oracle/make_golden.py            # needs /root/reference
+
+Produces
+  tests/golden/ckpt/<name>.pt     the 7 shipped checkpoints re-saved as plain
+                                  dict / fp32 tensors (no EasyDict pickle), so the
+                                  GPU box -- which has no /root/reference -- can load them
+  tests/golden/kat_<name>.npz     raw ScoreNetworkX*/ScoreNetworkA outputs of the reference
+                                  modules on the deterministic SURVEY section-8c input recipe
+  tests/golden/traj_<case>.npz    final (x, adj) of the reference's get_pc_sampler / S4_solver
+                                  closures, with every torch.randn / randn_like call served by
+                                  numpy's frozen RandomState(seed) stream so the same raw draws
+                                  can be replayed through the oracle and injected into the
+                                  CUDA path
+  tests/golden/MANIFEST.json      what was generated, from which torch version
+
+The reference code is imported and called, never copied.
+"""
+import contextlib
+import io
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, ROOT)
+
+from oracle import gdss_oracle as O          # noqa: E402
+from oracle import refimport                 # noqa: E402
+from oracle.cases import CKPTS, SHORT_CASES, FULL_CASES, NumpyDraws, plain   # noqa: E402
+
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+def convert_ckpts():
+    os.makedirs(os.path.join(GOLD, "ckpt"), exist_ok=True)
+    out = {}
+    for name, rel in CKPTS.items():
+        ck = refimport.load_ckpt(rel)
+        use_ema = bool(ck["model_config"].get("sample", {}).get("use_ema", False))
+        d = {
+            "model_config": plain(ck["model_config"]),
+            "params_x": plain(ck["params_x"]),
+            "params_adj": plain(ck["params_adj"]),
+            "x_state_dict": {k: v.detach().float().clone() for k, v in ck["x_state_dict"].items()},
+            "adj_state_dict": {k: v.detach().float().clone() for k, v in ck["adj_state_dict"].items()},
+        }
+        if use_ema:     # only ENZYMES / grid sample with EMA weights (sampler.py:47-52)
+            for key in ("ema_x", "ema_adj"):
+                e = ck[key]
+                d[key] = {"decay": float(e["decay"]), "num_updates": int(e["num_updates"]),
+                          "shadow_params": [p.detach().float().clone() for p in e["shadow_params"]]}
+        path = os.path.join(GOLD, "ckpt", f"{name}.pt")
+        torch.save(d, path)
+        out[name] = {"source": f"checkpoints/{rel}.pth", "bytes": os.path.getsize(path), "ema": use_ema}
+    return out
+
+
+def ref_models(name, ema=False):
+    from utils.loader import load_model
+    ck = refimport.load_ckpt(CKPTS[name])
+    px, pa = dict(ck["params_x"]), dict(ck["params_adj"])
+    mx, ma = load_model(px), load_model(pa)
+    mx.load_state_dict(ck["x_state_dict"])
+    ma.load_state_dict(ck["adj_state_dict"])
+    if ema:
+        from utils.ema import ExponentialMovingAverage
+        for m, key in ((mx, "ema_x"), (ma, "ema_adj")):
+            e = ExponentialMovingAverage(m.parameters(), decay=0.999)
+            e.load_state_dict(ck[key])
+            e.copy_to(m.parameters())
+    return mx.eval(), ma.eval(), px, pa
+
+
+def make_kat():
+    out = {}
+    for name in CKPTS:
+        mx, ma, px, pa = ref_models(name)
+        N, F = pa["max_node_num"], pa["max_feat_num"]
+        B = 4 if N < 200 else 2
+        x, adj, flags = O.kat_inputs(N, F, B)
+        with torch.no_grad():
+            sx, sa = mx(x, adj, flags), ma(x, adj, flags)
+        np.savez_compressed(os.path.join(GOLD, f"kat_{name}.npz"), score_x=sx.numpy(), score_adj=sa.numpy(),
+                            B=B, N=N, F=F)
+        out[name] = {"B": B, "abs_sum_x": float(sx.double().abs().sum()), "abs_sum_adj": float(sa.double().abs().sum())}
+        print("kat", name, out[name], flush=True)
+    return out
+
+
+@contextlib.contextmanager
+def numpy_randn(seed):
+    """Serve torch.randn / torch.randn_like from RandomState(seed) while the reference runs."""
+    draws = NumpyDraws(seed)
+    orig_randn, orig_like = torch.randn, torch.randn_like
+
+    def randn(*shape, **kw):
+        if len(shape) == 1 and isinstance(shape[0], (tuple, list, torch.Size)):
+            shape = tuple(shape[0])
+        return draws(shape)
+
+    def randn_like(t, **kw):
+        return draws(tuple(t.shape))
+
+    torch.randn, torch.randn_like = randn, randn_like
+    try:
+        yield draws
+    finally:
+        torch.randn, torch.randn_like = orig_randn, orig_like
+
+
+def run_reference_case(case):
+    import sde as RSDE
+    import solver as RS
+    mx, ma, px, pa = ref_models(case["ckpt"], ema=case.get("ema", False))
+    N, F, B = pa["max_node_num"], pa["max_feat_num"], case["B"]
+    _, _, flags = O.kat_inputs(N, F, B)
+    cls = {"VP": RSDE.VPSDE, "VE": RSDE.VESDE, "subVP": RSDE.subVPSDE}
+    sx = cls[case["sde_x"][0]](case["sde_x"][1], case["sde_x"][2], case["scales"])
+    sa = cls[case["sde_adj"][0]](case["sde_adj"][1], case["sde_adj"][2], case["scales"])
+    get = RS.S4_solver if case["predictor"] == "S4" else RS.get_pc_sampler
+    fn = get(sx, sa, (B, N, F), (B, N, N), predictor=case["predictor"], corrector=case["corrector"],
+             snr=case["snr"], scale_eps=case["scale_eps"], n_steps=1, probability_flow=False, continuous=True,
+             denoise=case.get("denoise", True), eps=1e-4, device="cpu")
+    with numpy_randn(case["seed"]), contextlib.redirect_stdout(io.StringIO()), \
+            contextlib.redirect_stderr(io.StringIO()):
+        x, adj, n_evals = fn(mx, ma, flags)
+    return flags, x, adj, n_evals
+
+
+def make_traj():
+    out = {}
+    for case in SHORT_CASES + FULL_CASES:
+        flags, x, adj, n_evals = run_reference_case(case)
+        assert torch.isfinite(x).all() and torch.isfinite(adj).all()
+        np.savez_compressed(os.path.join(GOLD, f"traj_{case['name']}.npz"), flags=flags.numpy(), x=x.numpy(),
+                            adj=adj.numpy(), n_evals=n_evals, case=json.dumps(case))
+        out[case["name"]] = {"n_evals": int(n_evals), "adj_gt_half": float((adj > 0.5).float().mean())}
+        print("traj", case["name"], out[case["name"]], flush=True)
+    return out
+
+
+def main():
+    refimport.activate()
+    torch.set_num_threads(os.cpu_count())
+    os.makedirs(GOLD, exist_ok=True)
+    manifest = {"torch": torch.__version__, "numpy": np.__version__, "reference": refimport.REF}
+    manifest["ckpt"] = convert_ckpts()
+    manifest["kat"] = make_kat()
+    manifest["traj"] = make_traj()
+    with open(os.path.join(GOLD, "MANIFEST.json"), "w") as f:
+        json.dump(manifest, f, indent=1, sort_keys=True)
+
+
+if __name__ == "__main__":
+    main()
