@@ -1,0 +1,191 @@
+/*
+ * gdss_b200.h -- C ABI of the B200-native GDSS reverse-diffusion sampling hot path.
+ *
+ * One shared library (gdss_b200/csrc/libgdss_b200.so, CUDA, sm_100a only).  Plain pointers
+ * and sizes; no torch / C++ types.  The reference (harryjo97/GDSS) is pure Python/PyTorch
+ * and has no FFI of its own: each entry point below names the reference interface it
+ * replaces (file:line relative to the upstream repository).  INTEGRATION.md shows the
+ * ctypes stub a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - every device buffer (weights blob, workspace, state, outputs) is owned by the caller;
+ *     the library never allocates device memory and never synchronises the device except
+ *     where stated; all work is enqueued on the `stream` argument (a cudaStream_t passed as
+ *     void*), so the functions are re-entrant per (ctx, workspace, stream);
+ *   - tensors are contiguous row-major fp32 exactly as the reference lays them out:
+ *     x [B,N,F], adj [B,N,N], flags [B,N] (0/1 floats);
+ *   - return value: 0 = ok, <0 = GDSS_E_* below, >0 = a cudaError_t from the launch;
+ *   - there is no CPU fallback: without a CUDA device every compute call returns an error.
+ */
+#ifndef GDSS_B200_H
+#define GDSS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GDSS_ABI_VERSION 1
+
+enum {
+  GDSS_OK = 0,
+  GDSS_E_BADARG = -1,       /* null pointer / negative size / shape mismatch            */
+  GDSS_E_UNSUPPORTED = -2,  /* configuration outside what the kernels are built for     */
+  GDSS_E_WORKSPACE = -3,    /* workspace too small                                      */
+  GDSS_E_NCCL = -4          /* NCCL not loadable / collective failed                    */
+};
+
+/* utils/loader.py:37-48 model_type strings */
+enum { GDSS_NET_X = 0 /* ScoreNetworkX */, GDSS_NET_X_GMH = 1 /* ScoreNetworkX_GMH */, GDSS_NET_A = 2 /* ScoreNetworkA */ };
+/* utils/loader.py:94-108 sde.type strings */
+enum { GDSS_SDE_VP = 0, GDSS_SDE_VE = 1, GDSS_SDE_SUBVP = 2 };
+/* solver.py:163-164, utils/loader.py:128-131 */
+enum { GDSS_PRED_EULER = 0, GDSS_PRED_REVERSE = 1, GDSS_PRED_S4 = 2 };
+enum { GDSS_CORR_NONE = 0, GDSS_CORR_LANGEVIN = 1 };
+
+/* Constructor kwargs of the score networks (the `params_x` / `params_adj` dicts stored in
+ * every checkpoint, utils/loader.py:150-165).  Unused fields are ignored per model_type. */
+typedef struct gdss_net_desc {
+  int32_t model_type;    /* GDSS_NET_*                                                    */
+  int32_t max_feat_num;  /* F                                                             */
+  int32_t max_node_num;  /* N (ScoreNetworkA only; X nets take N from the call)           */
+  int32_t nhid;
+  int32_t depth;         /* X nets: depth; ScoreNetworkA: num_layers                      */
+  int32_t num_linears;
+  int32_t c_init, c_hid, c_final;
+  int32_t adim;
+  int32_t num_heads;
+  int32_t reserved;
+} gdss_net_desc;
+
+/* Sampler configuration = the arguments of get_pc_sampler / S4_solver (solver.py:153-156,
+ * :200-203) plus the two SDEs built by load_sde (utils/loader.py:94-108). */
+typedef struct gdss_sde_desc {
+  int32_t type;          /* GDSS_SDE_*                                                    */
+  int32_t num_scales;    /* N of the SDE (1000 in every shipped config)                   */
+  double lo, hi;         /* beta_min,beta_max (VP/subVP) or sigma_min,sigma_max (VE)      */
+} gdss_sde_desc;
+
+typedef struct gdss_sampler_desc {
+  gdss_sde_desc sde_x, sde_adj;
+  int32_t predictor;     /* GDSS_PRED_*                                                   */
+  int32_t corrector;     /* GDSS_CORR_* (ignored by S4, which always corrects)            */
+  double snr, scale_eps, eps;
+  int32_t n_steps;       /* Langevin inner steps (1 in every shipped config; only 1 is built) */
+  int32_t probability_flow;  /* only 0 is built (every shipped config)                     */
+  int32_t denoise;       /* return *_mean (noise_removal)                                 */
+  int32_t reserved;
+} gdss_sampler_desc;
+
+/* One row of the per-step coefficient table (host-computed once per sampler, fp32, in the
+ * reference's own expression order; sde.py / solver.py line numbers in gdss_b200/schedule.py).
+ * Index 0 = node features x, index 1 = adjacency. */
+typedef struct gdss_step_coef {
+  float cs[2];      /* score scale: -1/std(t) (VP, subVP) or 1 (VE)       losses.py:13-29  */
+  float lang[2];    /* 2*alpha_k*snr^2 ; 0 when no corrector              solver.py:132    */
+  float pa[2], pb[2], pc[2];  /* predictor: y_mean = pa*y + pb*raw ; y = y_mean + pc*z     */
+  float mu1[2], sig1[2], drift[2], mu2[2], sig2[2];   /* S4 two half transitions           */
+  float seps;       /* scale_eps                                                          */
+  float t;          /* the time of this step (diagnostic)                                 */
+} gdss_step_coef;
+
+typedef struct gdss_ctx gdss_ctx;   /* opaque: two packed networks + launch plan */
+
+/* ---- library ------------------------------------------------------------------------ */
+int gdss_abi_version(void);
+/* number of CUDA devices visible (0 on a CPU box); never fails */
+int gdss_device_count(void);
+const char* gdss_error_string(int code);
+
+/* ---- weights ------------------------------------------------------------------------
+ * Replaces: nn.Module construction + load_state_dict (utils/loader.py:37-48, :186-196).
+ * `tensors[i]` = i-th tensor of the reference state_dict in state_dict order (host, fp32,
+ * contiguous, 'module.' prefix irrelevant); `numel[i]` its element count (validated).
+ * gdss_packed_floats returns the blob size in floats (<0 on error).  gdss_pack_weights
+ * fills a HOST blob of that size; the caller uploads it to the device unchanged. */
+int64_t gdss_packed_floats(const gdss_net_desc* desc, int32_t n_nodes);
+int32_t gdss_num_state_tensors(const gdss_net_desc* desc);
+int gdss_pack_weights(const gdss_net_desc* desc, int32_t n_nodes, const float* const* tensors,
+                      const int64_t* numel, int32_t n_tensors, float* host_blob, int64_t blob_floats);
+
+/* ---- context ------------------------------------------------------------------------
+ * A context binds up to two packed networks (node-feature net, adjacency net; either may
+ * be NULL) for graphs of N nodes and F features.  Host memory only. */
+gdss_ctx* gdss_ctx_create(int32_t N, int32_t F, const gdss_net_desc* net_x, const float* dev_blob_x,
+                          const gdss_net_desc* net_a, const float* dev_blob_a);
+void gdss_ctx_destroy(gdss_ctx* ctx);
+/* bytes of device workspace the calls below need for a batch of B graphs */
+int64_t gdss_workspace_bytes(const gdss_ctx* ctx, int32_t B);
+
+/* ---- score networks -----------------------------------------------------------------
+ * Replaces: ScoreNetworkX.forward / ScoreNetworkX_GMH.forward (models/ScoreNetwork_X.py:32-46,
+ * :75-89) and ScoreNetworkA.forward (models/ScoreNetwork_A.py:131-150): raw network outputs
+ * (before the -1/std scaling of losses.py:13-21).  score_x / score_adj may be NULL to skip a
+ * network.  `inputs_masked` != 0 promises x, adj are already zero on flag==0 rows/cols (true
+ * inside the sampler) and lets the kernels skip padded nodes; 0 evaluates all N nodes.
+ * adj must be symmetric (it always is in GDSS). */
+int gdss_score_forward(gdss_ctx* ctx, const float* x, const float* adj, const float* flags,
+                       float* score_x, float* score_adj, int32_t B, int32_t inputs_masked,
+                       void* workspace, int64_t workspace_bytes, void* stream);
+
+/* ---- solver -------------------------------------------------------------------------
+ * gdss_build_schedule: host-only; fills `table[num_scales]` for a sampler configuration
+ * (replaces the per-step scalar algebra of sde.py:127-168, :189-230 and solver.py:45-89,
+ * :113-149, :231-277).  The Python host mirror computes the same table with torch fp32
+ * expressions (gdss_b200/schedule.py) and passes it to gdss_sample. */
+int gdss_build_schedule(const gdss_sampler_desc* s, gdss_step_coef* table, int32_t n_rows);
+
+/* gdss_sample: replaces the closure returned by get_pc_sampler / S4_solver
+ * (solver.py:158-195, :205-279): runs `n_iters` (<= num_scales) reverse-diffusion steps on
+ * the B graphs of this rank.
+ *   x, adj        in/out state.  If init_prior != 0 they are overwritten with the masked
+ *                 N(0,1) prior (solver.py:174-178) from the Philox stream, else used as given.
+ *   x_mean, adj_mean  out: the predictor means of the last step (what denoise=True returns)
+ *   inj_x, inj_adj    optional injected raw N(0,1) draws, layouts [n_iters][dx][B][N][F] and
+ *                 [n_iters][da][B][N][N] in the reference's draw order (dx=da= 2 PC+Langevin,
+ *                 1 PC without corrector, 3 S4); NULL -> counter-based Philox4x32-10 keyed by
+ *                 (seed, global graph id = graph_offset + b, step, draw), so results do not
+ *                 depend on how the batch is sharded.
+ *   trace         optional [n_iters][8] floats: per step the Langevin step sizes
+ *                 (eps_x, eps_adj) and the four batch-mean norms, for parity tests.
+ *   global_B, nccl_comm   batch-mean coupling of the Langevin step size (solver.py:130-132):
+ *                 with nccl_comm != NULL the four per-step norm sums are all-reduced over
+ *                 the communicator and divided by global_B; with NULL the local batch is
+ *                 the whole batch (global_B must equal B). */
+int gdss_sample(gdss_ctx* ctx, const gdss_sampler_desc* s, const gdss_step_coef* table, int32_t n_iters,
+                float* x, float* adj, const float* flags, float* x_mean, float* adj_mean, int32_t B,
+                int32_t init_prior, uint64_t seed, int64_t graph_offset, int64_t global_B,
+                const float* inj_x, const float* inj_adj, float* trace, void* nccl_comm, int32_t use_graph,
+                void* workspace, int64_t workspace_bytes, void* stream);
+
+/* ---- NCCL plumbing (dlopen'ed; the library loads without NCCL) ------------------------- */
+int gdss_nccl_unique_id(void* id128);                         /* rank 0: 128-byte id       */
+int gdss_nccl_comm_create(const void* id128, int32_t world, int32_t rank, void** comm_out);
+int gdss_nccl_comm_destroy(void* comm);
+int gdss_nccl_allgather(void* comm, const float* send, float* recv, int64_t count_per_rank, void* stream);
+
+/* ---- tensor helpers -----------------------------------------------------------------
+ * Replace utils/graph_utils.py: mask_x :8-12, mask_adjs :16-29 (3-D or 4-D via C channels),
+ * gen_noise :78-86 (raw draw supplied or Philox), pow_tensor :133-142, quantize :90-92,
+ * quantize_mol :97-106 (int64 out). */
+int gdss_mask_x(float* x, const float* flags, int32_t B, int32_t N, int32_t F, void* stream);
+int gdss_mask_adjs(float* adjs, const float* flags, int32_t B, int32_t C, int32_t N, void* stream);
+int gdss_gen_noise(float* out, const float* raw_or_null, const float* flags, int32_t B, int32_t N, int32_t F_or_0,
+                   int32_t sym, uint64_t seed, uint64_t draw_id, int64_t graph_offset, void* stream);
+int gdss_pow_tensor(const float* adj, float* out /* [B,cnum,N,N] */, int32_t B, int32_t N, int32_t cnum, void* stream);
+int gdss_quantize(const float* adj, float* out, float thr, int64_t numel, void* stream);
+int gdss_quantize_mol(const float* adj, int64_t* out, int64_t numel, void* stream);
+
+/* ---- introspection for tests / profiling ---------------------------------------------- */
+/* number of kernel launches the library has enqueued since process start (all contexts) */
+int64_t gdss_launch_count(void);
+/* workspace layout of the last plan: byte offsets of named regions (for parity tests that look
+ * at intermediates).  Returns <0 if name unknown. */
+int64_t gdss_workspace_offset(const gdss_ctx* ctx, int32_t B, const char* region);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GDSS_B200_H */
