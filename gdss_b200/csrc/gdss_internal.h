@@ -1,0 +1,78 @@
+// Internal (non-ABI) definitions shared by the translation units of libgdss_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+
+#include "../../include/gdss_b200.h"
+
+#define GDSS_MAX_LAYERS 16
+#define GDSS_MAX_LIN 4
+#define GDSS_MAX_STEPS 8192
+#define GDSS_MAX_CH 8        // c_init / c_hid / c_final upper bound the edge kernels are built for
+
+namespace gdss {
+
+// One AttentionLayer (models/attention.py:75-116) in the packed blob.  All Linear weights
+// are stored transposed, [in][out] row-major, so that consecutive threads (consecutive
+// output units) read consecutive floats.
+struct LayerPlan {
+  int c_in, c_out, f_in, attn, nhid, hid, nlin, qkvw;
+  int64_t wqkv;                 // [c_in][f_in][qkvw]   columns = Q | K | V
+  int64_t bqkv;                 // [c_in][qkvw]
+  int64_t ew[GDSS_MAX_LIN];     // edge MLP `mlp`: (2 c_in -> hid), (hid -> hid)*, (hid -> c_out)
+  int64_t eb[GDSS_MAX_LIN];
+  int64_t nw[2], nb[2];         // node MLP `multi_channel`: (c_in*nhid -> hid), (hid -> nhid)
+};
+
+struct NetPlan {
+  int type;                     // GDSS_NET_*
+  int F, N, nhid, depth, nlin, c_init, c_hid, c_final, adim, heads;
+  int fdim;                     // input width of `final`
+  int fout;                     // output width of `final` (F for X nets, 1 for A)
+  int n_tensors;                // number of state_dict tensors
+  LayerPlan layers[GDSS_MAX_LAYERS];
+  int64_t gw[GDSS_MAX_LAYERS], gb[GDSS_MAX_LAYERS];   // ScoreNetworkX: DenseGCNConv weight [in][out], bias
+  int64_t fw[3], fb[3];         // final MLP (3 linears), [in][out]
+  int64_t total;                // floats
+};
+
+int plan_net(const gdss_net_desc* d, int N, NetPlan* p);
+
+// named workspace regions (byte offsets, 256-aligned)
+enum Region {
+  R_NEFF = 0, R_STEP, R_TABLE, R_MEANS, R_NORMS, R_STACK_A, R_STACK_X, R_DIS, R_QKV, R_XA0, R_XA1, R_XS, R_RAW_X, R_RAW_ADJ,
+  R_COUNT
+};
+
+struct Workspace {
+  int64_t off[R_COUNT + 1];
+};
+
+}  // namespace gdss
+
+struct gdss_ctx {
+  int N, F;
+  bool has_x, has_a;
+  gdss::NetPlan px, pa;
+  const float* blob_x;
+  const float* blob_a;
+  int smem_optin;               // max dynamic shared memory per block
+  int num_sms;
+};
+
+namespace gdss {
+
+void layout_workspace(const gdss_ctx* ctx, int B, Workspace* w);
+
+// Enqueue one joint evaluation of the bound networks (raw outputs).  neff = device int[B].
+int launch_eval(const gdss_ctx* ctx, const float* x, const float* adj, const float* flags, const int* neff,
+                float* score_x, float* score_adj, int B, char* ws, const Workspace& w, cudaStream_t st);
+int launch_neff(const float* flags, int* neff, int B, int N, int inputs_masked, cudaStream_t st);
+
+void count_launch(int n = 1);
+
+// NCCL (dlopen'ed)
+int nccl_allreduce_sum(void* comm, float* buf, int count, cudaStream_t st);
+
+}  // namespace gdss

@@ -1,0 +1,973 @@
+// Score-network kernels (general-N path): ScoreNetworkX / ScoreNetworkX_GMH / ScoreNetworkA.
+//
+// HBM layout (all fp32, row-major, one slab per graph b):
+//   edge-channel stack  S[b][c][i][j]   full N x N planes, plane c of layer l's input/output
+//                                       (models/ScoreNetwork_A.py:133-141 keeps the same list)
+//   node features       x[b][i][f]
+//   dis[b][c][i]        D^-1/2 of plane c with self loops (models/layers.py:72-78)
+//   qkv[b][c][i][Q|K|V] DenseGCNConv outputs of the c_in attentions of one layer
+// Everything is bounded by neff[b] = number of leading nodes that can be non-zero, so padded
+// nodes cost nothing.  Only the strict upper triangle of every edge plane is computed and
+// mirrored (all per-edge inputs are symmetric in (i,j), models/attention.py:49, :113); diagonal
+// pixels are never produced nor read (DenseGCNConv overwrites them with 1, the final score
+// zeroes them, ScoreNetwork_A.py:145).
+#include <stdio.h>
+
+#include "gdss_common.cuh"
+#include "gdss_internal.h"
+
+namespace gdss {
+
+static int64_t g_launches = 0;
+void count_launch(int n) { g_launches += n; }
+
+#define LAUNCH_CHECK()                          \
+  do {                                          \
+    cudaError_t e__ = cudaGetLastError();       \
+    if (e__ != cudaSuccess) return (int)e__;    \
+  } while (0)
+
+// ---------------------------------------------------------------------------------------
+// neff[b] = 1 + index of the last node whose flag is set (N when the inputs are not masked)
+// ---------------------------------------------------------------------------------------
+__global__ void neff_kernel(const float* __restrict__ flags, int* __restrict__ neff, int B, int N, int masked) {
+  int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  int lane = threadIdx.x & 31;
+  if (b >= B) return;
+  int m = 0;
+  if (masked) {
+    for (int i = lane; i < N; i += 32)
+      if (flags[(int64_t)b * N + i] != 0.f) m = i + 1;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+  } else {
+    m = N;
+  }
+  if (lane == 0) neff[b] = m;
+}
+
+int launch_neff(const float* flags, int* neff, int B, int N, int inputs_masked, cudaStream_t st) {
+  neff_kernel<<<(B + 7) / 8, 256, 0, st>>>(flags, neff, B, N, inputs_masked);
+  count_launch();
+  LAUNCH_CHECK();
+  return 0;
+}
+
+// strict upper triangle of an m x m block: p in [0, m(m-1)/2) -> (i, j), i < j, row-major
+DEVINL void tri_decode(int p, int m, int& i, int& j) {
+  float fm = (float)(2 * m - 1);
+  int r = (int)((fm - sqrtf(fm * fm - 8.f * (float)p)) * 0.5f);
+  r = max(0, min(r, m - 2));
+  while (r > 0 && r * (2 * m - r - 1) / 2 > p) --r;
+  while ((r + 1) * (2 * m - r - 2) / 2 <= p) ++r;
+  i = r;
+  j = p - r * (2 * m - r - 1) / 2 + r + 1;
+}
+
+// ---------------------------------------------------------------------------------------
+// pow_kernel: out = L @ A on the leading neff x neff block (utils/graph_utils.py:133-142).
+// 32x32 output tile per CTA, upper-triangular tiles only, result mirrored.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) pow_kernel(const float* __restrict__ Lp, int64_t l_bs,
+                                                  const float* __restrict__ Ap, int64_t a_bs, float* __restrict__ out,
+                                                  int64_t o_bs, const int* __restrict__ neff, int N) {
+  const int b = blockIdx.z, n = neff[b];
+  const int ti = blockIdx.y, tj = blockIdx.x;
+  if (ti > tj || tj * 32 >= n) return;
+  __shared__ float Ls[32][33], Rs[32][33];
+  const float* L = Lp + b * l_bs;
+  const float* A = Ap + b * a_bs;
+  float* O = out + b * o_bs;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int k0 = 0; k0 < n; k0 += 32) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      int r = ty + 8 * q;
+      int gi = ti * 32 + r, gk = k0 + tx;
+      Ls[r][tx] = (gi < n && gk < n) ? L[(int64_t)gi * N + gk] : 0.f;
+      int gr = k0 + r, gj = tj * 32 + tx;
+      Rs[r][tx] = (gr < n && gj < n) ? A[(int64_t)gr * N + gj] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 32; ++k) {
+      float rv = Rs[k][tx];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) acc[q] = fmaf(Ls[ty + 8 * q][k], rv, acc[q]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    int i = ti * 32 + ty + 8 * q, j = tj * 32 + tx;
+    if (i < n && j < n && i <= j) {
+      O[(int64_t)i * N + j] = acc[q];
+      O[(int64_t)j * N + i] = acc[q];
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// deg_kernel: dis[b][c][i] = clamp(1 + sum_{j != i} P_c[i][j], min=1)^-1/2  (layers.py:72-78)
+// one warp per row, lanes along j (coalesced).
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) deg_kernel(const float* __restrict__ planes, int64_t p_bs, float* __restrict__ dis,
+                                                  int64_t d_bs, const int* __restrict__ neff, int N) {
+  const int b = blockIdx.y, c = blockIdx.x, n = neff[b];
+  const float* P = planes + b * p_bs + (int64_t)c * N * N;
+  float* D = dis + b * d_bs + (int64_t)c * N;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  for (int i = w; i < n; i += 8) {
+    float s = 0.f;
+    for (int j = lane; j < n; j += 32) s += (j == i) ? 1.f : P[(int64_t)i * N + j];
+    s = warp_sum(s);
+    if (lane == 0) D[i] = 1.0f / sqrtf(fmaxf(s, 1.0f));
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// gcn_kernel: DenseGCNConv (layers.py:49-88) for a tile of TI rows of channel c of graph b,
+// evaluated as  out = dis_i * ((A~ diag(dis)) x) W + bias   (A~ = plane with unit diagonal).
+// ---------------------------------------------------------------------------------------
+struct GcnArgs {
+  const float* planes; int64_t p_bs;
+  const float* x; int64_t x_bs; int ldx; int f_in;
+  const float* dis; int64_t d_bs;
+  const float* W; int64_t w_cs; int w_ld; int col0; int ow;
+  const float* bias; int b_cs;
+  float* out; int64_t o_bs; int64_t o_cs; int ldo;
+  const int* neff;
+  int act; int N; int TI;
+};
+
+#define GCN_JC 64
+#define GCN_MAXIT 6
+
+__global__ void __launch_bounds__(256) gcn_kernel(GcnArgs a) {
+  extern __shared__ float sm[];
+  const int b = blockIdx.z, c = blockIdx.y, n = a.neff[b];
+  const int i0 = blockIdx.x * a.TI;
+  if (i0 >= n) return;
+  const int ti = min(a.TI, n - i0);
+  const int F = a.f_in, N = a.N;
+  float* xs = sm;                         // [JC][F]
+  float* As = xs + GCN_JC * F;            // [TI][JC+1]
+  float* AX = As + a.TI * (GCN_JC + 1);   // [TI][F+1]
+  const float* P = a.planes + b * a.p_bs + (int64_t)c * N * N;
+  const float* X = a.x + b * a.x_bs;
+  const float* D = a.dis + b * a.d_bs + (int64_t)c * N;
+  const int tid = threadIdx.x;
+  const int items = ti * F;
+  float acc[GCN_MAXIT];
+#pragma unroll
+  for (int q = 0; q < GCN_MAXIT; ++q) acc[q] = 0.f;
+  for (int j0 = 0; j0 < n; j0 += GCN_JC) {
+    const int jc = min(GCN_JC, n - j0);
+    for (int idx = tid; idx < jc * F; idx += 256) {
+      int j = idx / F, f = idx - j * F;
+      xs[idx] = X[(int64_t)(j0 + j) * a.ldx + f];
+    }
+    for (int idx = tid; idx < ti * jc; idx += 256) {
+      int i = idx / jc, j = idx - i * jc;
+      int gi = i0 + i, gj = j0 + j;
+      float v = (gi == gj) ? 1.f : P[(int64_t)gi * N + gj];
+      As[i * (GCN_JC + 1) + j] = v * D[gj];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < GCN_MAXIT; ++q) {
+      int idx = tid + q * 256;
+      if (idx < items) {
+        int i = idx / F, f = idx - i * F;
+        const float* ar = As + i * (GCN_JC + 1);
+        float s = acc[q];
+        for (int j = 0; j < jc; ++j) s = fmaf(ar[j], xs[j * F + f], s);
+        acc[q] = s;
+      }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int q = 0; q < GCN_MAXIT; ++q) {
+    int idx = tid + q * 256;
+    if (idx < items) {
+      int i = idx / F, f = idx - i * F;
+      AX[i * (F + 1) + f] = acc[q] * D[i0 + i];
+    }
+  }
+  __syncthreads();
+  const float* W = a.W + (int64_t)c * a.w_cs;
+  const float* Bv = a.bias + (int64_t)c * a.b_cs;
+  float* O = a.out + b * a.o_bs + (int64_t)c * a.o_cs;
+  for (int idx = tid; idx < ti * a.ow; idx += 256) {
+    int i = idx / a.ow, o = idx - i * a.ow + a.col0;
+    float s = Bv[o];
+    const float* axr = AX + i * (F + 1);
+    for (int f = 0; f < F; ++f) s = fmaf(axr[f], __ldg(W + (int64_t)f * a.w_ld + o), s);
+    if (a.act == 1) s = tanh_f(s);
+    O[(int64_t)(i0 + i) * a.ldo + o] = s;
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// edge_kernel: per-pixel part of one AttentionLayer (attention.py:35-49, :109-114):
+//   M_c(i,j)  = sym( mean_h tanh(Q_c,i,h . K_c,j,h / sqrt(nhid)) )
+//   out(i,j)  = 2 * MLP([M_0..M_{C-1}, P_0(i,j)..P_{C-1}(i,j)]) * flag_i * flag_j, mirrored.
+// One CTA per (upper-triangular) T x T pixel tile; Q|K rows of both node sets live in smem.
+// ---------------------------------------------------------------------------------------
+struct EdgeArgs {
+  const float* qkv; int64_t q_bs; int64_t q_cs; int qkvw; int attn; int heads; float scale;
+  const float* pin; int64_t pin_bs;
+  float* pout; int64_t pout_bs;
+  const float* w[GDSS_MAX_LIN]; const float* bias[GDSS_MAX_LIN];
+  const float* flags; const int* neff;
+  int N; int T; int ntile; int cin, hid, cout;
+};
+
+// y[OUTP] = bias + x[IN] . W[IN][OUTP], weights in shared memory read as broadcast float4
+template <int IN, int OUTP>
+DEVINL void dense_smem(const float* __restrict__ W, const float* __restrict__ Bs, const float* x, float* y) {
+#pragma unroll
+  for (int o = 0; o < OUTP; o += 4) {
+    const float4 bv = *reinterpret_cast<const float4*>(Bs + o);
+    y[o] = bv.x; y[o + 1] = bv.y; y[o + 2] = bv.z; y[o + 3] = bv.w;
+  }
+#pragma unroll
+  for (int k = 0; k < IN; ++k) {
+#pragma unroll
+    for (int o = 0; o < OUTP; o += 4) {
+      const float4 w = *reinterpret_cast<const float4*>(W + k * OUTP + o);
+      y[o] = fmaf(x[k], w.x, y[o]);
+      y[o + 1] = fmaf(x[k], w.y, y[o + 1]);
+      y[o + 2] = fmaf(x[k], w.z, y[o + 2]);
+      y[o + 3] = fmaf(x[k], w.w, y[o + 3]);
+    }
+  }
+}
+
+template <int CIN, int HID, int COUT, int NLIN>
+__global__ void __launch_bounds__(256) edge_kernel(EdgeArgs a) {
+  extern __shared__ __align__(16) float sm[];
+  const int b = blockIdx.y, n = a.neff[b];
+  // decode the tile pair (ti <= tj)
+  int t = blockIdx.x, ti = 0;
+  while (t >= a.ntile - ti) { t -= a.ntile - ti; ++ti; }
+  const int tj = ti + t;
+  const int T = a.T, N = a.N;
+  const int i0 = ti * T, j0 = tj * T;
+  if (j0 >= n) return;                      // (i0 <= j0)
+  const int mi = min(T, n - i0), mj = min(T, n - j0);
+  const int npix = (ti == tj) ? mi * (mi - 1) / 2 : mi * mj;
+  if (npix <= 0) return;
+  const int qk = 2 * a.attn;                // floats per (row, channel)
+  const int RS = a.cin * qk + 4;            // padded row stride: == 4 (mod 32) -> conflict-free float4 reads
+  float* SI = sm;                           // [T][RS]
+  float* SJ = SI + T * RS;                  // [T][RS]
+  float* Wsm = SJ + T * RS;
+  const int tid = threadIdx.x;
+  // ---- stage Q|K rows of both node sets
+  const float* Q = a.qkv + b * a.q_bs;
+  for (int idx = tid; idx < (mi + mj) * a.cin * (qk >> 2); idx += 256) {
+    int v = idx % (qk >> 2);
+    int rc = idx / (qk >> 2);
+    int c = rc % a.cin, r = rc / a.cin;
+    int node = r < mi ? i0 + r : j0 + (r - mi);
+    float4 val = *reinterpret_cast<const float4*>(Q + (int64_t)c * a.q_cs + (int64_t)node * a.qkvw + 4 * v);
+    float* dst = (r < mi ? SI + r * RS : SJ + (r - mi) * RS) + c * qk + 4 * v;
+    *reinterpret_cast<float4*>(dst) = val;
+  }
+  // ---- stage the MLP weights: per linear W[INP][OUTP] zero padded to the template shape, bias[OUTP].
+  // The kernel may be instantiated larger than the layer (cin <= CIN, hid <= HID, cout <= COUT):
+  // padded inputs / units carry zero weights, so the result is unchanged.
+  int woff[NLIN], boff[NLIN];
+  {
+    int cur = 0;
+#pragma unroll
+    for (int l = 0; l < NLIN; ++l) {
+      const int inp = l == 0 ? 2 * CIN : HID, outp = ((l == NLIN - 1 ? COUT : HID) + 3) & ~3;
+      const int in = l == 0 ? 2 * a.cin : a.hid, out = l == NLIN - 1 ? a.cout : a.hid;
+      woff[l] = cur;
+      cur += inp * outp;
+      boff[l] = cur;
+      cur += outp;
+      for (int idx = tid; idx < inp * outp; idx += 256) {
+        int k = idx / outp, o = idx - k * outp;
+        int kr = k;                               // real input row of padded row k
+        if (l == 0) kr = k < CIN ? (k < a.cin ? k : -1) : (k - CIN < a.cin ? a.cin + (k - CIN) : -1);
+        else if (k >= in) kr = -1;
+        Wsm[woff[l] + idx] = (kr >= 0 && o < out) ? a.w[l][kr * out + o] : 0.f;
+      }
+      for (int idx = tid; idx < outp; idx += 256) Wsm[boff[l] + idx] = idx < out ? a.bias[l][idx] : 0.f;
+    }
+  }
+  __syncthreads();
+  const float* Pin = a.pin + b * a.pin_bs;
+  float* Pout = a.pout + b * a.pout_bs;
+  const float* fl = a.flags + (int64_t)b * N;
+  const int hd = a.attn / a.heads;
+  const float mscale = 0.5f / (float)a.heads;
+  for (int p = tid; p < npix; p += 256) {
+    int li, lj;
+    if (ti == tj) tri_decode(p, mi, li, lj);
+    else { li = p / mj; lj = p - li * mj; }
+    const int gi = i0 + li, gj = j0 + lj;
+    const float* ri = SI + li * RS;
+    const float* rj = (ti == tj ? SI : SJ) + lj * RS;
+    float in[2 * CIN];
+#pragma unroll
+    for (int c = 0; c < CIN; ++c) {
+      if (c >= a.cin) {
+        in[c] = 0.f;
+        in[CIN + c] = 0.f;
+        continue;
+      }
+      const float* qi = ri + c * qk;
+      const float* ki = qi + a.attn;
+      const float* qj = rj + c * qk;
+      const float* kj = qj + a.attn;
+      float m = 0.f;
+      for (int h = 0; h < a.heads; ++h) {
+        float s1 = 0.f, s2 = 0.f;
+        for (int d = 0; d < hd; d += 4) {
+          const float4 a1 = *reinterpret_cast<const float4*>(qi + h * hd + d);
+          const float4 b1 = *reinterpret_cast<const float4*>(kj + h * hd + d);
+          const float4 a2 = *reinterpret_cast<const float4*>(qj + h * hd + d);
+          const float4 b2 = *reinterpret_cast<const float4*>(ki + h * hd + d);
+          s1 = fmaf(a1.x, b1.x, s1); s1 = fmaf(a1.y, b1.y, s1); s1 = fmaf(a1.z, b1.z, s1); s1 = fmaf(a1.w, b1.w, s1);
+          s2 = fmaf(a2.x, b2.x, s2); s2 = fmaf(a2.y, b2.y, s2); s2 = fmaf(a2.z, b2.z, s2); s2 = fmaf(a2.w, b2.w, s2);
+        }
+        m += tanh_f(s1 * a.scale) + tanh_f(s2 * a.scale);
+      }
+      in[c] = m * mscale;
+      in[CIN + c] = Pin[(int64_t)c * N * N + (int64_t)gi * N + gj];
+    }
+    // ---- MLP (layers.py:135-153): Linear, ELU, ..., Linear
+    constexpr int HIDP = (HID + 3) & ~3, COUTP = (COUT + 3) & ~3;
+    float h0[HIDP];
+    dense_smem<2 * CIN, HIDP>(Wsm + woff[0], Wsm + boff[0], in, h0);
+#pragma unroll
+    for (int o = 0; o < HIDP; ++o) h0[o] = elu_f(h0[o]);
+#pragma unroll
+    for (int l = 1; l < NLIN - 1; ++l) {
+      float h1[HIDP];
+      dense_smem<HID, HIDP>(Wsm + woff[l], Wsm + boff[l], h0, h1);
+#pragma unroll
+      for (int o = 0; o < HIDP; ++o) h0[o] = elu_f(h1[o]);
+    }
+    float outv[COUTP];
+    dense_smem<HID, COUTP>(Wsm + woff[NLIN - 1], Wsm + boff[NLIN - 1], h0, outv);
+    const float fm = 2.f * fl[gi] * fl[gj];      // (S + S^T) then mask_adjs
+#pragma unroll
+    for (int o = 0; o < COUT; ++o) {
+      if (o >= a.cout) continue;
+      float v = outv[o] * fm;
+      Pout[(int64_t)o * N * N + (int64_t)gi * N + gj] = v;
+      Pout[(int64_t)o * N * N + (int64_t)gj * N + gi] = v;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// node_kernel: x_out = tanh(mask_x(multi_channel(cat_c V_c)))  (attention.py:106-107),
+// optionally tanh'd once more (ScoreNetwork_X.py:81).
+// ---------------------------------------------------------------------------------------
+struct NodeArgs {
+  const float* qkv; int64_t q_bs; int64_t q_cs; int qkvw; int vcol;
+  const float* w1; const float* b1; const float* w2; const float* b2;
+  float* out; int64_t o_bs; int ldo;
+  const float* flags; const int* neff;
+  int N, cin, nhid, hid, extra_tanh;
+};
+
+#define NODE_ROWS 64
+
+__global__ void __launch_bounds__(256) node_kernel(NodeArgs a) {
+  extern __shared__ float sm[];
+  const int b = blockIdx.y, n = a.neff[b];
+  const int i0 = blockIdx.x * NODE_ROWS;
+  if (i0 >= n) return;
+  const int rows = min(NODE_ROWS, n - i0);
+  const int K1 = a.cin * a.nhid, H = a.hid, NH = a.nhid;
+  float* W1 = sm;                 // [K1][H]
+  float* W2 = W1 + K1 * H;        // [H][NH]
+  float* Hs = W2 + H * NH;        // [rows][H]
+  const int tid = threadIdx.x;
+  for (int idx = tid; idx < K1 * H; idx += 256) W1[idx] = a.w1[idx];
+  for (int idx = tid; idx < H * NH; idx += 256) W2[idx] = a.w2[idx];
+  __syncthreads();
+  const float* Q = a.qkv + b * a.q_bs;
+  for (int idx = tid; idx < rows * H; idx += 256) {
+    int r = idx / H, u = idx - r * H;
+    float s = a.b1[u];
+    for (int c = 0; c < a.cin; ++c) {
+      const float* v = Q + (int64_t)c * a.q_cs + (int64_t)(i0 + r) * a.qkvw + a.vcol;
+      const float* w = W1 + (c * NH) * H + u;
+      for (int k = 0; k < NH; ++k) s = fmaf(v[k], w[k * H], s);
+    }
+    Hs[idx] = elu_f(s);
+  }
+  __syncthreads();
+  float* O = a.out + b * a.o_bs;
+  const float* fl = a.flags + (int64_t)b * a.N;
+  for (int idx = tid; idx < rows * NH; idx += 256) {
+    int r = idx / NH, o = idx - r * NH;
+    float s = a.b2[o];
+    for (int u = 0; u < H; ++u) s = fmaf(Hs[r * H + u], W2[u * NH + o], s);
+    s = tanh_f(s * fl[i0 + r]);
+    if (a.extra_tanh) s = tanh_f(s);
+    O[(int64_t)(i0 + r) * a.ldo + o] = s;
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// final_edge_kernel: ScoreNetworkA.final (ScoreNetwork_A.py:141-148): per pixel
+// fdim -> 2 fdim -> 2 fdim -> 1 with ELU, zero diagonal, flag mask.  128 upper-triangle pixels
+// per CTA; both hidden layers are register-blocked SGEMMs out of shared memory
+// (8 pixels x OPT hidden units per thread), the 1-wide output layer is a dot product.
+// ---------------------------------------------------------------------------------------
+struct FinalEdgeArgs {
+  const float* stack; int64_t s_bs;
+  const float* w1; const float* b1; const float* w2; const float* b2; const float* w3; const float* b3;
+  float* out;       // [B][N][N]
+  const float* flags; const int* neff;
+  int N, fdim, H;
+};
+
+template <int OPT>
+__global__ void __launch_bounds__(256) final_edge_kernel(FinalEdgeArgs a) {
+  extern __shared__ __align__(16) float sm[];
+  constexpr int HP = 16 * OPT;
+  const int b = blockIdx.y, n = a.neff[b];
+  const int P = n * (n - 1) / 2;
+  const int p0 = blockIdx.x * 128;
+  if (p0 >= P) return;
+  const int K1 = a.fdim, H = a.H, N = a.N;
+  const int sizeA = max(K1 * 128 + K1 * HP, H * HP);
+  float* Xs = sm;                   // [K1][128]
+  float* W1s = Xs + K1 * 128;       // [K1][HP]
+  float* W2s = sm;                  // [H][HP]   (aliases Xs/W1s after layer 1)
+  float* H1s = sm + sizeA;          // [HP][128]
+  float* b1s = H1s + HP * 128;      // [HP]
+  float* b2s = b1s + HP;
+  float* w3s = b2s + HP;
+  int* pij = reinterpret_cast<int*>(w3s + HP);   // [128] packed (i << 16 | j), -1 if invalid
+  const int tid = threadIdx.x;
+  if (tid < 128) {
+    int p = p0 + tid, v = -1;
+    if (p < P) {
+      int i, j;
+      tri_decode(p, n, i, j);
+      v = (i << 16) | j;
+    }
+    pij[tid] = v;
+  }
+  for (int idx = tid; idx < HP; idx += 256) {
+    b1s[idx] = idx < H ? a.b1[idx] : 0.f;
+    b2s[idx] = idx < H ? a.b2[idx] : 0.f;
+    w3s[idx] = idx < H ? a.w3[idx] : 0.f;
+  }
+  for (int idx = tid; idx < K1 * HP; idx += 256) {
+    int k = idx / HP, o = idx - k * HP;
+    W1s[idx] = o < H ? a.w1[k * H + o] : 0.f;
+  }
+  __syncthreads();
+  const float* S = a.stack + b * a.s_bs;
+  for (int idx = tid; idx < K1 * 128; idx += 256) {
+    int k = idx >> 7, m = idx & 127;
+    int v = pij[m];
+    float val = 0.f;
+    if (v >= 0) val = S[(int64_t)k * N * N + (int64_t)(v >> 16) * N + (v & 0xffff)];
+    Xs[idx] = val;
+  }
+  __syncthreads();
+  const int tx = tid & 15, ty = tid >> 4;
+  float acc[8][OPT];
+  // ---- layer 1
+#pragma unroll
+  for (int q = 0; q < OPT; ++q) {
+    float bb = b1s[ty * OPT + q];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) acc[r][q] = bb;
+  }
+  for (int k = 0; k < K1; ++k) {
+    const float4 xa = *reinterpret_cast<const float4*>(Xs + k * 128 + 4 * tx);
+    const float4 xb = *reinterpret_cast<const float4*>(Xs + k * 128 + 64 + 4 * tx);
+    const float xv[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
+    float wv[OPT];
+#pragma unroll
+    for (int q = 0; q < OPT; ++q) wv[q] = W1s[k * HP + ty * OPT + q];
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+#pragma unroll
+      for (int q = 0; q < OPT; ++q) acc[r][q] = fmaf(xv[r], wv[q], acc[r][q]);
+  }
+#pragma unroll
+  for (int q = 0; q < OPT; ++q) {
+    float4 ha = make_float4(elu_f(acc[0][q]), elu_f(acc[1][q]), elu_f(acc[2][q]), elu_f(acc[3][q]));
+    float4 hb = make_float4(elu_f(acc[4][q]), elu_f(acc[5][q]), elu_f(acc[6][q]), elu_f(acc[7][q]));
+    *reinterpret_cast<float4*>(H1s + (ty * OPT + q) * 128 + 4 * tx) = ha;
+    *reinterpret_cast<float4*>(H1s + (ty * OPT + q) * 128 + 64 + 4 * tx) = hb;
+  }
+  __syncthreads();              // everyone is done with Xs / W1s
+  for (int idx = tid; idx < H * HP; idx += 256) {
+    int k = idx / HP, o = idx - k * HP;
+    W2s[idx] = o < H ? a.w2[k * H + o] : 0.f;
+  }
+  __syncthreads();
+  // ---- layer 2
+#pragma unroll
+  for (int q = 0; q < OPT; ++q) {
+    float bb = b2s[ty * OPT + q];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) acc[r][q] = bb;
+  }
+  for (int k = 0; k < H; ++k) {
+    const float4 xa = *reinterpret_cast<const float4*>(H1s + k * 128 + 4 * tx);
+    const float4 xb = *reinterpret_cast<const float4*>(H1s + k * 128 + 64 + 4 * tx);
+    const float xv[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
+    float wv[OPT];
+#pragma unroll
+    for (int q = 0; q < OPT; ++q) wv[q] = W2s[k * HP + ty * OPT + q];
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+#pragma unroll
+      for (int q = 0; q < OPT; ++q) acc[r][q] = fmaf(xv[r], wv[q], acc[r][q]);
+  }
+  // ---- layer 3: dot with w3, reduced over the 16 ty groups through shared memory
+  float part[8];
+#pragma unroll
+  for (int r = 0; r < 8; ++r) part[r] = 0.f;
+#pragma unroll
+  for (int q = 0; q < OPT; ++q) {
+    float w = w3s[ty * OPT + q];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) part[r] = fmaf(elu_f(acc[r][q]), w, part[r]);
+  }
+  __syncthreads();              // H1s no longer needed -> reuse as red[16][128]
+  float* red = H1s;
+  *reinterpret_cast<float4*>(red + ty * 128 + 4 * tx) = make_float4(part[0], part[1], part[2], part[3]);
+  *reinterpret_cast<float4*>(red + ty * 128 + 64 + 4 * tx) = make_float4(part[4], part[5], part[6], part[7]);
+  __syncthreads();
+  if (tid < 128) {
+    int v = pij[tid];
+    if (v >= 0) {
+      float s = a.b3[0];
+#pragma unroll
+      for (int g = 0; g < 16; ++g) s += red[g * 128 + tid];
+      int i = v >> 16, j = v & 0xffff;
+      const float* fl = a.flags + (int64_t)b * N;
+      s *= fl[i] * fl[j];
+      float* O = a.out + (int64_t)b * N * N;
+      O[(int64_t)i * N + j] = s;
+      O[(int64_t)j * N + i] = s;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// final_node_kernel: `final` MLP of the X networks (ScoreNetwork_X.py:40-44, :84-87):
+// rows of the node feature stack [x, x_1 .. x_d] -> 2f -> 2f -> F, ELU, mask_x.
+// ---------------------------------------------------------------------------------------
+struct FinalNodeArgs {
+  const float* xs; int64_t xs_bs; int fdim; int H; int fout;
+  const float* w1; const float* b1; const float* w2; const float* b2; const float* w3; const float* b3;
+  float* out; const float* flags; const int* neff; int N;
+};
+
+#define FN_ROWS 32
+
+__global__ void __launch_bounds__(256) final_node_kernel(FinalNodeArgs a) {
+  extern __shared__ float sm[];
+  const int b = blockIdx.y, n = a.neff[b];
+  const int i0 = blockIdx.x * FN_ROWS;
+  if (i0 >= n) return;
+  const int rows = min(FN_ROWS, n - i0);
+  const int K = a.fdim, H = a.H;
+  float* X0 = sm;                    // [rows][K]
+  float* H1 = X0 + FN_ROWS * K;      // [rows][H]
+  float* H2 = H1 + FN_ROWS * H;      // [rows][H]
+  const int tid = threadIdx.x;
+  const float* XS = a.xs + b * a.xs_bs;
+  for (int idx = tid; idx < rows * K; idx += 256) {
+    int r = idx / K, k = idx - r * K;
+    X0[idx] = XS[(int64_t)(i0 + r) * K + k];
+  }
+  __syncthreads();
+  for (int idx = tid; idx < rows * H; idx += 256) {
+    int r = idx / H, o = idx - r * H;
+    float s = a.b1[o];
+    for (int k = 0; k < K; ++k) s = fmaf(X0[r * K + k], __ldg(a.w1 + k * H + o), s);
+    H1[idx] = elu_f(s);
+  }
+  __syncthreads();
+  for (int idx = tid; idx < rows * H; idx += 256) {
+    int r = idx / H, o = idx - r * H;
+    float s = a.b2[o];
+    for (int k = 0; k < H; ++k) s = fmaf(H1[r * H + k], __ldg(a.w2 + k * H + o), s);
+    H2[idx] = elu_f(s);
+  }
+  __syncthreads();
+  const float* fl = a.flags + (int64_t)b * a.N;
+  float* O = a.out + (int64_t)b * a.N * a.fout;
+  for (int idx = tid; idx < rows * a.fout; idx += 256) {
+    int r = idx / a.fout, o = idx - r * a.fout;
+    float s = a.b3[o];
+    for (int k = 0; k < H; ++k) s = fmaf(H2[r * H + k], __ldg(a.w3 + k * a.fout + o), s);
+    O[(int64_t)(i0 + r) * a.fout + o] = s * fl[i0 + r];
+  }
+}
+
+// x rows -> first F columns of the node feature stack
+__global__ void copy_x_kernel(const float* __restrict__ x, float* __restrict__ xs, int N, int F, int ld,
+                              const int* __restrict__ neff) {
+  const int b = blockIdx.y, n = neff[b];
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n * F; idx += gridDim.x * blockDim.x) {
+    int i = idx / F, f = idx - i * F;
+    xs[(int64_t)b * N * ld + (int64_t)i * ld + f] = x[(int64_t)b * N * F + idx];
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// host-side launch plan
+// ---------------------------------------------------------------------------------------
+static inline int64_t align_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
+
+static int node_tile(int N) {            // balanced row tiles of at most 48 rows
+  int nt = (N + 47) / 48;
+  return (N + nt - 1) / nt;
+}
+
+static int gcn_tile(int N, int f_in) {
+  int ti = node_tile(N);
+  while (ti > 1 && ti * f_in > 256 * GCN_MAXIT) --ti;
+  return ti;
+}
+
+// pixel-tile edge for the edge kernel: whole graph when its Q|K rows fit, else 2 node sets of T rows
+static int edge_tile(int N, int cin, int attn, int smem_budget) {
+  const int row_bytes = (cin * 2 * attn + 4) * 4;
+  if (2 * N * row_bytes <= smem_budget && N <= 64) return N;
+  int T = smem_budget / (2 * row_bytes);
+  if (T > 32) T = 32;
+  if (T < 4) T = 4;
+  return T;
+}
+
+void layout_workspace(const gdss_ctx* ctx, int B, Workspace* w) {
+  const int64_t N = ctx->N, F = ctx->F;
+  int64_t sz[R_COUNT];
+  for (int i = 0; i < R_COUNT; ++i) sz[i] = 0;
+  sz[R_NEFF] = 4 * (int64_t)B;
+  sz[R_STEP] = 256;
+  sz[R_TABLE] = (int64_t)sizeof(gdss_step_coef) * GDSS_MAX_STEPS;
+  sz[R_MEANS] = 256;
+  sz[R_NORMS] = 4 * 4 * (int64_t)B;
+  int64_t maxc = 1, qkv = 0, nh = 1;
+  const NetPlan* nets[2] = {ctx->has_a ? &ctx->pa : nullptr, ctx->has_x ? &ctx->px : nullptr};
+  for (int k = 0; k < 2; ++k) {
+    const NetPlan* p = nets[k];
+    if (!p) continue;
+    nh = nh > p->nhid ? nh : p->nhid;
+    if (p->type == GDSS_NET_X) {
+      sz[R_XS] = 4 * (int64_t)B * N * p->fdim;
+      continue;
+    }
+    int64_t planes = p->c_init;
+    for (int l = 0; l < p->depth; ++l) {
+      const LayerPlan& L = p->layers[l];
+      maxc = maxc > L.c_in ? maxc : L.c_in;
+      int64_t q = (int64_t)L.c_in * N * L.qkvw;
+      qkv = qkv > q ? qkv : q;
+      bool writes = p->type == GDSS_NET_A || l < p->depth - 1;
+      if (writes) planes += L.c_out;
+    }
+    if (p->type == GDSS_NET_A) sz[R_STACK_A] = 4 * (int64_t)B * planes * N * N;
+    else {
+      sz[R_STACK_X] = 4 * (int64_t)B * planes * N * N;
+      sz[R_XS] = 4 * (int64_t)B * N * p->fdim;
+    }
+  }
+  sz[R_DIS] = 4 * (int64_t)B * maxc * N;
+  sz[R_QKV] = 4 * (int64_t)B * qkv;
+  sz[R_XA0] = 4 * (int64_t)B * N * nh;
+  sz[R_XA1] = 4 * (int64_t)B * N * nh;
+  sz[R_RAW_X] = 4 * (int64_t)B * N * F;
+  sz[R_RAW_ADJ] = 4 * (int64_t)B * N * N;
+  int64_t cur = 0;
+  for (int i = 0; i < R_COUNT; ++i) {
+    w->off[i] = cur;
+    cur += align_up(sz[i], 256);
+  }
+  w->off[R_COUNT] = cur;
+}
+
+template <typename K>
+static int set_smem(K kernel, size_t bytes) {
+  if (bytes > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e != cudaSuccess) return (int)e;
+  }
+  return 0;
+}
+
+typedef void (*edge_fn)(EdgeArgs);
+// Instantiated shapes: the three (c_in, c_out) pairs of the shipped checkpoints (c_init=2, c_hid=8,
+// c_final=4); (8,16,8) doubles as the zero-padded fallback for every other shape up to GDSS_MAX_CH.
+template <int NLIN>
+static edge_fn pick_edge_shape(int cin, int cout, int hid, int* pcin, int* phid, int* pcout) {
+  if (cin <= 2 && cout <= 8 && hid <= 16 && cin == 2) { *pcin = 2; *phid = 16; *pcout = 8; return edge_kernel<2, 16, 8, NLIN>; }
+  if (cin <= 8 && cout <= 4 && hid <= 16) { *pcin = 8; *phid = 16; *pcout = 4; return edge_kernel<8, 16, 4, NLIN>; }
+  if (cin <= 8 && cout <= 8 && hid <= 16) { *pcin = 8; *phid = 16; *pcout = 8; return edge_kernel<8, 16, 8, NLIN>; }
+  return nullptr;
+}
+static edge_fn pick_edge(int cin, int cout, int hid, int nlin, int* pcin, int* phid, int* pcout) {
+  switch (nlin) {
+    case 2: return pick_edge_shape<2>(cin, cout, hid, pcin, phid, pcout);
+    case 3: return pick_edge_shape<3>(cin, cout, hid, pcin, phid, pcout);
+    case 4: return pick_edge_shape<4>(cin, cout, hid, pcin, phid, pcout);
+  }
+  return nullptr;
+}
+
+typedef void (*final_fn)(FinalEdgeArgs);
+static final_fn pick_final(int H, int* hp) {
+  int opt = (H + 15) / 16;
+  *hp = 16 * opt;
+  switch (opt) {
+    case 1: return final_edge_kernel<1>;
+    case 2: return final_edge_kernel<2>;
+    case 3: return final_edge_kernel<3>;
+    case 4: return final_edge_kernel<4>;
+    case 5: return final_edge_kernel<5>;
+    case 6: return final_edge_kernel<6>;
+    case 7: return final_edge_kernel<7>;
+    case 8: return final_edge_kernel<8>;
+  }
+  return nullptr;
+}
+
+static int launch_gcn(const GcnArgs& g, int C, int B, cudaStream_t st) {
+  size_t smem = sizeof(float) * ((size_t)GCN_JC * g.f_in + (size_t)g.TI * (GCN_JC + 1) + (size_t)g.TI * (g.f_in + 1));
+  int rc = set_smem(gcn_kernel, smem);
+  if (rc) return rc;
+  dim3 grid((g.N + g.TI - 1) / g.TI, C, B);
+  gcn_kernel<<<grid, 256, smem, st>>>(g);
+  count_launch();
+  LAUNCH_CHECK();
+  return 0;
+}
+
+// AttentionLayer stack shared by ScoreNetworkA and ScoreNetworkX_GMH.
+static int run_attn_net(const gdss_ctx* ctx, const NetPlan& p, const float* blob, const float* x, const float* adj,
+                        const float* flags, const int* neff, float* score, int B, char* ws, const Workspace& w,
+                        cudaStream_t st) {
+  const int N = p.N, F = p.F;
+  const int64_t NN = (int64_t)N * N;
+  const bool isA = p.type == GDSS_NET_A;
+  float* stack = reinterpret_cast<float*>(ws + w.off[isA ? R_STACK_A : R_STACK_X]);
+  int planes = p.c_init;
+  for (int l = 0; l < p.depth; ++l)
+    if (isA || l < p.depth - 1) planes += p.layers[l].c_out;
+  const int64_t s_bs = (int64_t)planes * NN;
+  float* dis = reinterpret_cast<float*>(ws + w.off[R_DIS]);
+  float* qkv = reinterpret_cast<float*>(ws + w.off[R_QKV]);
+  float* xa[2] = {reinterpret_cast<float*>(ws + w.off[R_XA0]), reinterpret_cast<float*>(ws + w.off[R_XA1])};
+  float* xs = reinterpret_cast<float*>(ws + w.off[R_XS]);
+  int64_t maxc = 1;
+  for (int l = 0; l < p.depth; ++l) maxc = maxc > p.layers[l].c_in ? maxc : p.layers[l].c_in;
+  const int64_t d_bs = maxc * N;
+  const int ntile32 = (N + 31) / 32;
+
+  // ---- power stack: plane 0 = adj, plane k = plane k-1 @ adj
+  cudaError_t e = cudaMemcpy2DAsync(stack, s_bs * 4, adj, NN * 4, NN * 4, B, cudaMemcpyDeviceToDevice, st);
+  if (e != cudaSuccess) return (int)e;
+  for (int k = 1; k < p.c_init; ++k) {
+    pow_kernel<<<dim3(ntile32, ntile32, B), 256, 0, st>>>(stack + (k - 1) * NN, s_bs, adj, NN, stack + k * NN, s_bs,
+                                                         neff, N);
+    count_launch();
+    LAUNCH_CHECK();
+  }
+  if (!isA) {
+    copy_x_kernel<<<dim3((N * F + 255) / 256, B), 256, 0, st>>>(x, xs, N, F, p.fdim, neff);
+    count_launch();
+    LAUNCH_CHECK();
+  }
+  const float* xin = x;
+  int64_t x_bs = (int64_t)N * F;
+  int ldx = F;
+  int cur = 0;      // first input plane of the current layer
+  for (int l = 0; l < p.depth; ++l) {
+    const LayerPlan& L = p.layers[l];
+    const bool last = l == p.depth - 1;
+    const bool need_edge = isA || !last;   // X_GMH: the last layer's adj_out (hence Q, K) is dead
+    const bool need_node = !isA || !last;  // A: the last layer's x_out (hence V) is dead
+    const float* pin = stack + (int64_t)cur * NN;
+    deg_kernel<<<dim3(L.c_in, B), 256, 0, st>>>(pin, s_bs, dis, d_bs, neff, N);
+    count_launch();
+    LAUNCH_CHECK();
+    GcnArgs g;
+    g.planes = pin; g.p_bs = s_bs;
+    g.x = xin; g.x_bs = x_bs; g.ldx = ldx; g.f_in = L.f_in;
+    g.dis = dis; g.d_bs = d_bs;
+    g.W = blob + L.wqkv; g.w_cs = (int64_t)L.f_in * L.qkvw; g.w_ld = L.qkvw;
+    g.col0 = need_edge ? 0 : 2 * L.attn;
+    g.ow = (need_edge ? 2 * L.attn : 0) + (need_node ? L.nhid : 0);
+    g.bias = blob + L.bqkv; g.b_cs = L.qkvw;
+    g.out = qkv; g.o_bs = (int64_t)L.c_in * N * L.qkvw; g.o_cs = (int64_t)N * L.qkvw; g.ldo = L.qkvw;
+    g.neff = neff; g.act = 0; g.N = N; g.TI = gcn_tile(N, L.f_in);
+    int rc = launch_gcn(g, L.c_in, B, st);
+    if (rc) return rc;
+    if (need_edge) {
+      EdgeArgs ea;
+      ea.qkv = qkv; ea.q_bs = g.o_bs; ea.q_cs = g.o_cs; ea.qkvw = L.qkvw; ea.attn = L.attn; ea.heads = p.heads;
+      ea.scale = 1.0f / sqrtf((float)L.nhid);
+      ea.pin = pin; ea.pin_bs = s_bs;
+      ea.pout = stack + (int64_t)(cur + L.c_in) * NN; ea.pout_bs = s_bs;
+      for (int i = 0; i < L.nlin; ++i) {
+        ea.w[i] = blob + L.ew[i];
+        ea.bias[i] = blob + L.eb[i];
+      }
+      ea.flags = flags; ea.neff = neff; ea.N = N;
+      if ((L.attn / p.heads) % 4) return GDSS_E_UNSUPPORTED;
+      const int budget = 96 * 1024;
+      ea.T = edge_tile(N, L.c_in, L.attn, budget);
+      ea.ntile = (N + ea.T - 1) / ea.T;
+      ea.cin = L.c_in; ea.hid = L.hid; ea.cout = L.c_out;
+      int tc, th, to;
+      edge_fn fn = pick_edge(L.c_in, L.c_out, L.hid, L.nlin, &tc, &th, &to);
+      if (!fn) return GDSS_E_UNSUPPORTED;
+      size_t wfl = 0;
+      for (int i = 0; i < L.nlin; ++i) {
+        int inp = i == 0 ? 2 * tc : th, outp = ((i == L.nlin - 1 ? to : th) + 3) & ~3;
+        wfl += (size_t)(inp + 1) * outp;
+      }
+      size_t smem = sizeof(float) * (2 * (size_t)ea.T * (L.c_in * 2 * L.attn + 4) + wfl);
+      rc = set_smem(fn, smem);
+      if (rc) return rc;
+      fn<<<dim3(ea.ntile * (ea.ntile + 1) / 2, B), 256, smem, st>>>(ea);
+      count_launch();
+      LAUNCH_CHECK();
+    }
+    if (need_node) {
+      NodeArgs na;
+      na.qkv = qkv; na.q_bs = g.o_bs; na.q_cs = g.o_cs; na.qkvw = L.qkvw; na.vcol = 2 * L.attn;
+      na.w1 = blob + L.nw[0]; na.b1 = blob + L.nb[0]; na.w2 = blob + L.nw[1]; na.b2 = blob + L.nb[1];
+      if (isA) { na.out = xa[l & 1]; na.o_bs = (int64_t)N * L.nhid; na.ldo = L.nhid; }
+      else { na.out = xs + F + l * p.nhid; na.o_bs = (int64_t)N * p.fdim; na.ldo = p.fdim; }
+      na.flags = flags; na.neff = neff; na.N = N; na.cin = L.c_in; na.nhid = L.nhid; na.hid = L.hid;
+      na.extra_tanh = isA ? 0 : 1;
+      size_t smem = sizeof(float) * ((size_t)L.c_in * L.nhid * L.hid + (size_t)L.hid * L.nhid + (size_t)NODE_ROWS * L.hid);
+      rc = set_smem(node_kernel, smem);
+      if (rc) return rc;
+      node_kernel<<<dim3((N + NODE_ROWS - 1) / NODE_ROWS, B), 256, smem, st>>>(na);
+      count_launch();
+      LAUNCH_CHECK();
+      xin = na.out; x_bs = na.o_bs; ldx = na.ldo;
+    }
+    cur += L.c_in;
+  }
+  if (isA) {
+    FinalEdgeArgs fa;
+    fa.stack = stack; fa.s_bs = s_bs;
+    fa.w1 = blob + p.fw[0]; fa.b1 = blob + p.fb[0]; fa.w2 = blob + p.fw[1]; fa.b2 = blob + p.fb[1];
+    fa.w3 = blob + p.fw[2]; fa.b3 = blob + p.fb[2];
+    fa.out = score; fa.flags = flags; fa.neff = neff; fa.N = N; fa.fdim = p.fdim; fa.H = 2 * p.fdim;
+    int HP;
+    final_fn fn = pick_final(fa.H, &HP);
+    if (!fn) return GDSS_E_UNSUPPORTED;
+    int64_t sizeA = (int64_t)p.fdim * 128 + (int64_t)p.fdim * HP;
+    if (sizeA < (int64_t)fa.H * HP) sizeA = (int64_t)fa.H * HP;
+    size_t smem = sizeof(float) * (sizeA + (size_t)HP * 128 + 3 * HP + 128);
+    if ((int)smem > ctx->smem_optin) return GDSS_E_UNSUPPORTED;
+    int rc = set_smem(fn, smem);
+    if (rc) return rc;
+    int P = N * (N - 1) / 2;
+    if (P > 0) {
+      fn<<<dim3((P + 127) / 128, B), 256, smem, st>>>(fa);
+      count_launch();
+      LAUNCH_CHECK();
+    }
+  } else {
+    FinalNodeArgs fa;
+    fa.xs = xs; fa.xs_bs = (int64_t)N * p.fdim; fa.fdim = p.fdim; fa.H = 2 * p.fdim; fa.fout = p.fout;
+    fa.w1 = blob + p.fw[0]; fa.b1 = blob + p.fb[0]; fa.w2 = blob + p.fw[1]; fa.b2 = blob + p.fb[1];
+    fa.w3 = blob + p.fw[2]; fa.b3 = blob + p.fb[2];
+    fa.out = score; fa.flags = flags; fa.neff = neff; fa.N = N;
+    size_t smem = sizeof(float) * FN_ROWS * ((size_t)fa.fdim + 2 * fa.H);
+    int rc = set_smem(final_node_kernel, smem);
+    if (rc) return rc;
+    final_node_kernel<<<dim3((N + FN_ROWS - 1) / FN_ROWS, B), 256, smem, st>>>(fa);
+    count_launch();
+    LAUNCH_CHECK();
+  }
+  return 0;
+}
+
+// ScoreNetworkX (ScoreNetwork_X.py:32-46): depth x tanh(DenseGCNConv(x, adj)) on the raw adjacency.
+static int run_gcn_net(const gdss_ctx* ctx, const NetPlan& p, const float* blob, const float* x, const float* adj,
+                       const float* flags, const int* neff, float* score, int B, char* ws, const Workspace& w,
+                       cudaStream_t st) {
+  const int N = p.N, F = p.F;
+  const int64_t NN = (int64_t)N * N;
+  float* dis = reinterpret_cast<float*>(ws + w.off[R_DIS]);
+  float* xs = reinterpret_cast<float*>(ws + w.off[R_XS]);
+  copy_x_kernel<<<dim3((N * F + 255) / 256, B), 256, 0, st>>>(x, xs, N, F, p.fdim, neff);
+  count_launch();
+  LAUNCH_CHECK();
+  deg_kernel<<<dim3(1, B), 256, 0, st>>>(adj, NN, dis, N, neff, N);
+  count_launch();
+  LAUNCH_CHECK();
+  for (int l = 0; l < p.depth; ++l) {
+    GcnArgs g;
+    g.planes = adj; g.p_bs = NN;
+    g.x = l == 0 ? xs : xs + F + (l - 1) * p.nhid; g.x_bs = (int64_t)N * p.fdim; g.ldx = p.fdim;
+    g.f_in = l == 0 ? F : p.nhid;
+    g.dis = dis; g.d_bs = N;
+    g.W = blob + p.gw[l]; g.w_cs = 0; g.w_ld = p.nhid; g.col0 = 0; g.ow = p.nhid;
+    g.bias = blob + p.gb[l]; g.b_cs = 0;
+    g.out = xs + F + l * p.nhid; g.o_bs = (int64_t)N * p.fdim; g.o_cs = 0; g.ldo = p.fdim;
+    g.neff = neff; g.act = 1; g.N = N; g.TI = gcn_tile(N, g.f_in);
+    int rc = launch_gcn(g, 1, B, st);
+    if (rc) return rc;
+  }
+  FinalNodeArgs fa;
+  fa.xs = xs; fa.xs_bs = (int64_t)N * p.fdim; fa.fdim = p.fdim; fa.H = 2 * p.fdim; fa.fout = p.fout;
+  fa.w1 = blob + p.fw[0]; fa.b1 = blob + p.fb[0]; fa.w2 = blob + p.fw[1]; fa.b2 = blob + p.fb[1];
+  fa.w3 = blob + p.fw[2]; fa.b3 = blob + p.fb[2];
+  fa.out = score; fa.flags = flags; fa.neff = neff; fa.N = N;
+  size_t smem = sizeof(float) * FN_ROWS * ((size_t)fa.fdim + 2 * fa.H);
+  int rc = set_smem(final_node_kernel, smem);
+  if (rc) return rc;
+  final_node_kernel<<<dim3((N + FN_ROWS - 1) / FN_ROWS, B), 256, smem, st>>>(fa);
+  count_launch();
+  LAUNCH_CHECK();
+  return 0;
+}
+
+int launch_eval(const gdss_ctx* ctx, const float* x, const float* adj, const float* flags, const int* neff,
+                float* score_x, float* score_adj, int B, char* ws, const Workspace& w, cudaStream_t st) {
+  const int N = ctx->N, F = ctx->F;
+  cudaError_t e;
+  if (score_adj && ctx->has_a) {
+    e = cudaMemsetAsync(score_adj, 0, sizeof(float) * (size_t)B * N * N, st);
+    if (e != cudaSuccess) return (int)e;
+    int rc = run_attn_net(ctx, ctx->pa, ctx->blob_a, x, adj, flags, neff, score_adj, B, ws, w, st);
+    if (rc) return rc;
+  }
+  if (score_x && ctx->has_x) {
+    e = cudaMemsetAsync(score_x, 0, sizeof(float) * (size_t)B * N * F, st);
+    if (e != cudaSuccess) return (int)e;
+    int rc;
+    if (ctx->px.type == GDSS_NET_X)
+      rc = run_gcn_net(ctx, ctx->px, ctx->blob_x, x, adj, flags, neff, score_x, B, ws, w, st);
+    else
+      rc = run_attn_net(ctx, ctx->px, ctx->blob_x, x, adj, flags, neff, score_x, B, ws, w, st);
+    if (rc) return rc;
+  }
+  return 0;
+}
+
+}  // namespace gdss
+
+extern "C" int64_t gdss_launch_count(void) { return gdss::g_launches; }

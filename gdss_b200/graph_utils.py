@@ -1,0 +1,96 @@
+"""CUDA versions of the tensor helpers the sampling path uses (utils/graph_utils.py): same names,
+same argument meaning, CUDA tensors only."""
+import numpy as np
+import torch
+
+from ._lib import check, lib, require_cuda
+
+
+def _prep(t):
+    if not t.is_cuda:
+        raise RuntimeError("gdss_b200.graph_utils works on CUDA tensors only (no CPU fallback)")
+    return t.to(torch.float32).contiguous()
+
+
+def _stream(t):
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def mask_x(x, flags):
+    """utils/graph_utils.py:8-12."""
+    if flags is None:
+        return x
+    require_cuda()
+    out, flags = _prep(x).clone(), _prep(flags)
+    B, N, F = out.shape
+    with torch.cuda.device(out.device):
+        check(lib().gdss_mask_x(out.data_ptr(), flags.data_ptr(), B, N, F, _stream(out)), "gdss_mask_x")
+    return out
+
+
+def mask_adjs(adjs, flags):
+    """utils/graph_utils.py:16-29 ([B,N,N] or [B,C,N,N])."""
+    if flags is None:
+        return adjs
+    require_cuda()
+    out, flags = _prep(adjs).clone(), _prep(flags)
+    B, N = out.shape[0], out.shape[-1]
+    Cn = out.shape[1] if out.dim() == 4 else 1
+    with torch.cuda.device(out.device):
+        check(lib().gdss_mask_adjs(out.data_ptr(), flags.data_ptr(), B, Cn, N, _stream(out)), "gdss_mask_adjs")
+    return out
+
+
+def gen_noise(x, flags, sym=True, raw=None, seed=None, draw_id=0, graph_offset=0):
+    """utils/graph_utils.py:78-86.  ``raw`` (same shape as x) injects the N(0,1) draw; otherwise
+    the library's Philox stream keyed by (seed, graph id, draw_id) is used."""
+    require_cuda()
+    x, flags = _prep(x), _prep(flags)
+    out = torch.empty_like(x)
+    B, N = x.shape[0], x.shape[1]
+    F = 0 if sym else x.shape[2]
+    seed = torch.initial_seed() if seed is None else seed
+    rawp = _prep(raw).data_ptr() if raw is not None else None
+    with torch.cuda.device(x.device):
+        check(lib().gdss_gen_noise(out.data_ptr(), rawp, flags.data_ptr(), B, N, F, int(bool(sym)),
+                                   int(seed) & (2 ** 64 - 1), int(draw_id), int(graph_offset), _stream(x)), "gdss_gen_noise")
+    return out
+
+
+def pow_tensor(x, cnum):
+    """utils/graph_utils.py:133-142 -> [B, cnum, N, N]."""
+    require_cuda()
+    x = _prep(x)
+    B, N = x.shape[0], x.shape[-1]
+    out = torch.empty(B, cnum, N, N, device=x.device)
+    with torch.cuda.device(x.device):
+        check(lib().gdss_pow_tensor(x.data_ptr(), out.data_ptr(), B, N, cnum, _stream(x)), "gdss_pow_tensor")
+    return out
+
+
+def quantize(adjs, thr=0.5):
+    """utils/graph_utils.py:90-92."""
+    require_cuda()
+    a = _prep(adjs)
+    out = torch.empty_like(a)
+    with torch.cuda.device(a.device):
+        check(lib().gdss_quantize(a.data_ptr(), out.data_ptr(), float(thr), a.numel(), _stream(a)), "gdss_quantize")
+    return out
+
+
+def quantize_mol(adjs):
+    """utils/graph_utils.py:97-106 -> int64 numpy array with bond orders {0,1,2,3}."""
+    require_cuda()
+    a = _prep(adjs if torch.is_tensor(adjs) else torch.as_tensor(np.asarray(adjs)).cuda())
+    out = torch.empty(a.shape, dtype=torch.int64, device=a.device)
+    with torch.cuda.device(a.device):
+        check(lib().gdss_quantize_mol(a.data_ptr(), out.data_ptr(), a.numel(), _stream(a)), "gdss_quantize_mol")
+    return out.cpu().numpy()
+
+
+def node_flags(adj, eps=1e-5):
+    """utils/graph_utils.py:33-39 (host-side glue, torch)."""
+    flags = torch.abs(adj).sum(-1).gt(eps).to(dtype=torch.float32)
+    if len(flags.shape) == 3:
+        flags = flags[:, 0, :]
+    return flags

@@ -79,16 +79,19 @@ typedef struct gdss_sampler_desc {
   int32_t reserved;
 } gdss_sampler_desc;
 
-/* One row of the per-step coefficient table (host-computed once per sampler, fp32, in the
- * reference's own expression order; sde.py / solver.py line numbers in gdss_b200/schedule.py).
- * Index 0 = node features x, index 1 = adjacency. */
+/* One row of the per-step coefficient table (24 floats).  Host-computed once per sampler in the
+ * reference's own fp32 expressions (gdss_b200/schedule.py cites the sde.py / solver.py lines) and
+ * handed to gdss_sample.  Index 0 = node features x, index 1 = adjacency.  `raw` is the raw
+ * network output, the score is s = cs * raw (losses.py:13-29). */
 typedef struct gdss_step_coef {
-  float cs[2];      /* score scale: -1/std(t) (VP, subVP) or 1 (VE)       losses.py:13-29  */
-  float lang[2];    /* 2*alpha_k*snr^2 ; 0 when no corrector              solver.py:132    */
-  float pa[2], pb[2], pc[2];  /* predictor: y_mean = pa*y + pb*raw ; y = y_mean + pc*z     */
-  float mu1[2], sig1[2], drift[2], mu2[2], sig2[2];   /* S4 two half transitions           */
-  float seps;       /* scale_eps                                                          */
-  float t;          /* the time of this step (diagnostic)                                 */
+  float cs[2];      /* -1/std(t) (VP, subVP) or 1 (VE)                                      */
+  float alpha[2];   /* Langevin alpha_k (solver.py:120-124, :240-243); 1 where not used     */
+  float pa[2], pb[2], pc[2];  /* predictor: y_mean = pa*y + pb*raw ; y = y_mean + pc*z       */
+  float mu1[2], sig1[2], drift[2], mu2[2], sig2[2];
+                    /* S4: y = mu1*y + sig1*z2 ; y += drift*raw ; y_mean = mu2*y ; y = y_mean + sig2*z3 */
+  float snr, seps;  /* Langevin signal-to-noise ratio and scale_eps                         */
+  float t;          /* time of this step (diagnostic)                                       */
+  float reserved;
 } gdss_step_coef;
 
 typedef struct gdss_ctx gdss_ctx;   /* opaque: two packed networks + launch plan */
@@ -130,16 +133,12 @@ int gdss_score_forward(gdss_ctx* ctx, const float* x, const float* adj, const fl
                        float* score_x, float* score_adj, int32_t B, int32_t inputs_masked,
                        void* workspace, int64_t workspace_bytes, void* stream);
 
-/* ---- solver -------------------------------------------------------------------------
- * gdss_build_schedule: host-only; fills `table[num_scales]` for a sampler configuration
- * (replaces the per-step scalar algebra of sde.py:127-168, :189-230 and solver.py:45-89,
- * :113-149, :231-277).  The Python host mirror computes the same table with torch fp32
- * expressions (gdss_b200/schedule.py) and passes it to gdss_sample. */
-int gdss_build_schedule(const gdss_sampler_desc* s, gdss_step_coef* table, int32_t n_rows);
-
+/* ---- solver ------------------------------------------------------------------------- */
 /* gdss_sample: replaces the closure returned by get_pc_sampler / S4_solver
- * (solver.py:158-195, :205-279): runs `n_iters` (<= num_scales) reverse-diffusion steps on
- * the B graphs of this rank.
+ * (solver.py:158-195, :205-279): runs reverse-diffusion steps first_step .. first_step+n_iters-1
+ * (rows of `table`, which holds first_step+n_iters rows at least) on the B graphs of this rank.
+ * With use_graph != 0 the step is captured into a CUDA graph and the call synchronises `stream`
+ * before it returns; otherwise it only enqueues work.
  *   x, adj        in/out state.  If init_prior != 0 they are overwritten with the masked
  *                 N(0,1) prior (solver.py:174-178) from the Philox stream, else used as given.
  *   x_mean, adj_mean  out: the predictor means of the last step (what denoise=True returns)
@@ -154,8 +153,8 @@ int gdss_build_schedule(const gdss_sampler_desc* s, gdss_step_coef* table, int32
  *                 with nccl_comm != NULL the four per-step norm sums are all-reduced over
  *                 the communicator and divided by global_B; with NULL the local batch is
  *                 the whole batch (global_B must equal B). */
-int gdss_sample(gdss_ctx* ctx, const gdss_sampler_desc* s, const gdss_step_coef* table, int32_t n_iters,
-                float* x, float* adj, const float* flags, float* x_mean, float* adj_mean, int32_t B,
+int gdss_sample(gdss_ctx* ctx, const gdss_sampler_desc* s, const gdss_step_coef* table, int32_t first_step,
+                int32_t n_iters, float* x, float* adj, const float* flags, float* x_mean, float* adj_mean, int32_t B,
                 int32_t init_prior, uint64_t seed, int64_t graph_offset, int64_t global_B,
                 const float* inj_x, const float* inj_adj, float* trace, void* nccl_comm, int32_t use_graph,
                 void* workspace, int64_t workspace_bytes, void* stream);

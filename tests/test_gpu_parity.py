@@ -1,0 +1,191 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the golden fixtures generated from the
+unmodified reference and against the CPU oracle on the same injected noise.
+
+Tolerances (fp32 path): per-evaluation raw scores and teacher-forced per-step state rel-L2 <= 1e-4
+(BASELINE.json north_star); thresholded final adjacency of the 1000-step runs bit-exact."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import gdss_oracle as O
+from oracle.cases import CKPTS, SHORT_CASES, FULL_CASES, load_golden_ckpt, load_kat
+from tests.gpu_common import rel, injected_noise, case_setup, oracle_trace
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+
+@pytest.mark.parametrize("name", list(CKPTS))
+@pytest.mark.parametrize("masked", [False, True])
+def test_score_networks_match_reference(name, masked):
+    from gdss_b200.engine import Engine
+    ck = load_golden_ckpt(name)
+    kat = load_kat(name)
+    B, N, F = int(kat["B"]), int(kat["N"]), int(kat["F"])
+    x, adj, flags = O.kat_inputs(N, F, B)
+    eng = Engine(ck["x_state_dict"], ck["adj_state_dict"], N, "cuda")
+    sx, sa = eng.score(x.cuda(), adj.cuda(), flags.cuda(), inputs_masked=masked)
+    torch.cuda.synchronize()
+    gx, ga = torch.from_numpy(kat["score_x"]), torch.from_numpy(kat["score_adj"])
+    assert torch.isfinite(sx).all() and torch.isfinite(sa).all()
+    assert rel(sx, gx) <= TOL, ("score_x", rel(sx, gx))
+    assert rel(sa, ga) <= TOL, ("score_adj", rel(sa, ga))
+    sa_c = sa.cpu()
+    assert float(sa_c.diagonal(dim1=-2, dim2=-1).abs().max()) == 0.0
+    assert float((sa_c - sa_c.transpose(-1, -2)).abs().max()) == 0.0          # mirrored by construction
+    assert float((sa_c * (1 - flags[:, :, None] * flags[:, None, :])).abs().max()) == 0.0
+    assert float((sx.cpu() * (1 - flags[:, :, None])).abs().max()) == 0.0
+
+
+def test_unmasked_inputs_follow_the_reference_modules():
+    """model(x, adj, flags) called with non-zero data on padded nodes (the reference masks only where it masks)."""
+    from gdss_b200.engine import Engine
+    ck = load_golden_ckpt("community_small")
+    N, F, B = 20, 10, 3
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(B, N, F, generator=g)
+    a = torch.randn(B, N, N, generator=g).triu(1)
+    adj = a + a.transpose(-1, -2)
+    flags = torch.ones(B, N)
+    flags[0, 15:] = 0
+    flags[1, 3] = 0          # a hole: non-prefix flags
+    with torch.no_grad():
+        ox = O.run_model(ck["x_state_dict"], ck["params_x"], x, adj, flags)
+        oa = O.run_model(ck["adj_state_dict"], ck["params_adj"], x, adj, flags)
+    eng = Engine(ck["x_state_dict"], ck["adj_state_dict"], N, "cuda")
+    sx, sa = eng.score(x.cuda(), adj.cuda(), flags.cuda(), inputs_masked=False)
+    assert rel(sx, ox) <= TOL and rel(sa, oa) <= TOL, (rel(sx, ox), rel(sa, oa))
+
+
+@pytest.mark.parametrize("name", [c["name"] for c in SHORT_CASES])
+def test_sampler_steps_match_oracle_and_reference(name):
+    case, z, weights, (N, F, B), flags, table, sdesc, eng = case_setup(name)
+    iters = case["scales"]
+    px, pa, ix, ia = injected_noise(case, B, N, F, iters)
+    x0, a0 = O.prior((B, N, F), (B, N, N), flags, _tape([px, pa]))
+    trace = oracle_trace(case, weights, (N, F, B), flags, iters)
+    # --- teacher-forced single steps: start every step from the oracle's previous state
+    xs, as_ = x0, a0
+    worst = 0.0
+    for i in range(iters):
+        x, adj, xm, am, tr = eng.sample(sdesc, table, flags, x=xs, adj=as_, first_step=i, n_iters=1,
+                                        inj_x=ix[i:i + 1], inj_adj=ia[i:i + 1], trace=True, use_graph=False)
+        rec = trace[i]
+        errs = dict(x=rel(x, rec["x"]), adj=rel(adj, rec["adj"]), x_mean=rel(xm, rec["x_mean"]),
+                    adj_mean=rel(am, rec["adj_mean"]))
+        key_x = "c_eps_x" if "c_eps_x" in rec else ("eps_x" if "eps_x" in rec else None)
+        if key_x:
+            key_a = key_x.replace("_x", "_adj")
+            t = tr.cpu()[0]
+            errs["eps_x"] = abs(float(t[0]) - float(rec[key_x])) / abs(float(rec[key_x]))
+            errs["eps_adj"] = abs(float(t[1]) - float(rec[key_a])) / abs(float(rec[key_a]))
+        worst = max(worst, max(errs.values()))
+        assert max(errs.values()) <= TOL, (name, i, errs)
+        xs, as_ = rec["x"], rec["adj"]
+    # --- free-running, one captured CUDA graph per step, against the reference's final state
+    x, adj, xm, am = eng.sample(sdesc, table, flags, x=x0, adj=a0, n_iters=iters, inj_x=ix, inj_adj=ia, use_graph=True)
+    outx, outa = (xm, am) if case.get("denoise", True) else (x, adj)
+    ex, ea = rel(outx, torch.from_numpy(z["x"])), rel(outa, torch.from_numpy(z["adj"]))
+    assert ex <= 10 * TOL and ea <= 10 * TOL, (name, ex, ea, worst)
+    # graph replay == eager launches, bit for bit
+    x2, adj2, xm2, am2 = eng.sample(sdesc, table, flags, x=x0, adj=a0, n_iters=iters, inj_x=ix, inj_adj=ia, use_graph=False)
+    assert torch.equal(x, x2) and torch.equal(adj, adj2) and torch.equal(am, am2)
+
+
+def _tape(ts):
+    it = iter(ts)
+    return lambda shape: next(it)
+
+
+@pytest.mark.parametrize("name", [c["name"] for c in FULL_CASES])
+def test_full_1000_step_runs_match_reference(name):
+    """BASELINE configurations at a small batch, full 1000 steps, injected noise: final state within
+    tolerance and the thresholded adjacency / atom types bit-exact (graph_utils.py:90-106)."""
+    case, z, weights, (N, F, B), flags, table, sdesc, eng = case_setup(name)
+    iters = case["scales"]
+    px, pa, ix, ia = injected_noise(case, B, N, F, iters)
+    x0, a0 = O.prior((B, N, F), (B, N, N), flags, _tape([px, pa]))
+    x, adj, xm, am = eng.sample(sdesc, table, flags, x=x0, adj=a0, n_iters=iters, inj_x=ix, inj_adj=ia, use_graph=True)
+    gx, ga = torch.from_numpy(z["x"]), torch.from_numpy(z["adj"])
+    ex, ea = rel(xm, gx), rel(am, ga)
+    assert ex <= 5e-3 and ea <= 5e-3, (name, ex, ea)
+    from gdss_b200.graph_utils import quantize_mol, quantize
+    assert np.array_equal(quantize_mol(am), O.quantize_mol(ga)), name
+    assert torch.equal(quantize(am).cpu(), O.quantize(ga)), name
+    assert torch.equal((xm > 0.5).cpu(), gx > 0.5), name
+
+
+def test_tensor_helpers_match_oracle():
+    from gdss_b200 import graph_utils as G
+    g = torch.Generator().manual_seed(3)
+    B, N, F = 5, 13, 7
+    x = torch.randn(B, N, F, generator=g)
+    raw = torch.randn(B, N, N, generator=g)
+    a = raw.triu(1)
+    adj = a + a.transpose(-1, -2)
+    flags = (torch.rand(B, N, generator=g) > 0.3).float()
+    assert torch.equal(G.mask_x(x.cuda(), flags.cuda()).cpu(), O.mask_x(x, flags))
+    assert torch.equal(G.mask_adjs(adj.cuda(), flags.cuda()).cpu(), O.mask_adjs(adj, flags))
+    a4 = torch.randn(B, 3, N, N, generator=g)
+    assert torch.equal(G.mask_adjs(a4.cuda(), flags.cuda()).cpu(), O.mask_adjs(a4, flags))
+    assert torch.equal(G.gen_noise(adj.cuda(), flags.cuda(), sym=True, raw=raw.cuda()).cpu(), O.sym_noise_from_raw(raw, flags))
+    assert torch.equal(G.gen_noise(x.cuda(), flags.cuda(), sym=False, raw=x.cuda()).cpu(), O.mask_x(x, flags))
+    assert rel(G.pow_tensor(adj.cuda(), 3), O.pow_stack(adj, 3)) <= 1e-6
+    q = torch.tensor([[-0.2, 0.49999, 0.5, 1.49, 1.5, 2.49999, 2.5, 7.0]])
+    assert G.quantize_mol(q.cuda()).tolist() == O.quantize_mol(q).tolist()
+    assert torch.equal(G.quantize(q.cuda()).cpu(), O.quantize(q))
+
+
+def test_philox_noise_statistics_and_shard_invariance():
+    from gdss_b200 import graph_utils as G
+    B, N, F = 256, 38, 9
+    flags = torch.ones(B, N).cuda()
+    zx = G.gen_noise(torch.empty(B, N, F).cuda(), flags, sym=False, seed=7, draw_id=5)
+    za = G.gen_noise(torch.empty(B, N, N).cuda(), flags, sym=True, seed=7, draw_id=5)
+    assert abs(float(zx.mean())) < 0.02 and abs(float(zx.std()) - 1) < 0.02
+    iu = torch.triu_indices(N, N, 1)
+    up = za[:, iu[0], iu[1]]
+    assert abs(float(up.mean())) < 0.01 and abs(float(up.std()) - 1) < 0.01
+    assert abs(float((up ** 4).mean()) - 3.0) < 0.1                              # Gaussian kurtosis
+    assert torch.equal(za, za.transpose(-1, -2)) and float(za.diagonal(dim1=-2, dim2=-1).abs().max()) == 0
+    # the stream depends on the global graph id only
+    lo = G.gen_noise(torch.empty(100, N, N).cuda(), flags[:100], sym=True, seed=7, draw_id=5, graph_offset=156)
+    assert torch.equal(lo, za[156:])
+    other = G.gen_noise(torch.empty(B, N, N).cuda(), flags, sym=True, seed=8, draw_id=5)
+    assert not torch.equal(other, za)
+
+
+def test_public_sampler_api_runs_and_is_deterministic():
+    """get_pc_sampler / S4_solver closures with the library's own Philox noise (no injected draws)."""
+    from gdss_b200.solver import get_pc_sampler, S4_solver
+    from gdss_b200.sde import VPSDE, VESDE
+    from gdss_b200.models import load_model
+    ck = load_golden_ckpt("qm9")
+    mx, ma = load_model(ck["params_x"]), load_model(ck["params_adj"])
+    mx.load_state_dict(ck["x_state_dict"])
+    ma.load_state_dict(ck["adj_state_dict"])
+    B, N, F = 64, 9, 4
+    flags = torch.ones(B, N)
+    flags[::3, 7:] = 0
+    for get, pred, corr in ((S4_solver, "S4", "None"), (get_pc_sampler, "Reverse", "Langevin"), (get_pc_sampler, "Euler", "None")):
+        fn = get(VESDE(0.1, 1.0, 50), VESDE(0.1, 1.0, 50), (B, N, F), (B, N, N), predictor=pred, corrector=corr,
+                 snr=0.2, scale_eps=0.7, n_steps=1, probability_flow=False, continuous=True, denoise=True, eps=1e-4,
+                 device="cuda")
+        torch.manual_seed(11)
+        x1, a1, n1 = fn(mx, ma, flags)
+        torch.manual_seed(11)
+        x2, a2, _ = fn(mx, ma, flags)
+        torch.manual_seed(12)
+        x3, a3, _ = fn(mx, ma, flags)
+        assert n1 == (0 if pred == "S4" else 100)
+        assert torch.isfinite(x1).all() and torch.isfinite(a1).all()
+        assert torch.equal(x1, x2) and torch.equal(a1, a2) and not torch.equal(a1, a3)
+        assert torch.equal(a1, a1.transpose(-1, -2))
+        fl = flags.cuda()
+        assert float((a1 * (1 - fl[:, :, None] * fl[:, None, :])).abs().max()) == 0
+        assert float((x1 * (1 - fl[:, :, None])).abs().max()) == 0
+    # model.forward drop-in (raw scores) == engine path
+    x, adj, fl = O.kat_inputs(N, F, 4)
+    with torch.no_grad():
+        ref = O.run_model(ck["adj_state_dict"], ck["params_adj"], x, adj, fl)
+    assert rel(ma.cuda()(x.cuda(), adj.cuda(), fl.cuda()), ref) <= TOL

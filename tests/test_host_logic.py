@@ -1,0 +1,218 @@
+"""CPU tests (-m "not gpu"): the C-ABI library loads and exports every symbol the header declares,
+host-side packing / schedule / sharding logic, and loud failure without a CUDA device."""
+import ctypes as C
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import gdss_oracle as O
+from oracle.cases import CKPTS, SHORT_CASES, load_golden_ckpt
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HAS_CUDA = torch.cuda.is_available()
+
+
+def test_library_exports_every_symbol_of_the_header():
+    from gdss_b200 import _lib
+    L = _lib.lib()
+    hdr = open(os.path.join(ROOT, "include", "gdss_b200.h")).read()
+    names = set(re.findall(r"\b(gdss_[a-z0-9_]+)\s*\(", hdr))
+    assert len(names) >= 20
+    for n in sorted(names):
+        assert hasattr(L, n), f"{n} declared in include/gdss_b200.h but not exported"
+    assert set(L._gdss_symbols) == names, set(L._gdss_symbols) ^ names
+    assert L.gdss_abi_version() == 1
+    assert L.gdss_device_count() >= 0
+    assert b"workspace" in L.gdss_error_string(-3)
+
+
+def test_struct_sizes_match_the_header():
+    from gdss_b200 import _lib
+    assert C.sizeof(_lib.NetDesc) == 48
+    assert C.sizeof(_lib.SdeDesc) == 24
+    assert C.sizeof(_lib.SamplerDesc) == 24 * 2 + 8 + 24 + 16
+    assert _lib.STEP_COEF_FLOATS == 24 and max(_lib.COL.values()) < 24
+
+
+@pytest.mark.parametrize("name", list(CKPTS))
+def test_describe_and_pack_every_checkpoint(name):
+    from gdss_b200 import _lib
+    from gdss_b200.engine import describe_network, pack_network
+    ck = load_golden_ckpt(name)
+    N = ck["params_adj"]["max_node_num"]
+    for sd, params in ((ck["x_state_dict"], ck["params_x"]), (ck["adj_state_dict"], ck["params_adj"])):
+        d = describe_network(sd, N)
+        kind = {"ScoreNetworkX": _lib.NET_X, "ScoreNetworkX_GMH": _lib.NET_X_GMH, "ScoreNetworkA": _lib.NET_A}[params["model_type"]]
+        assert d.model_type == kind
+        assert d.max_feat_num == params["max_feat_num"] and d.nhid == params["nhid"]
+        assert d.depth == params.get("depth", params.get("num_layers"))
+        if kind != _lib.NET_X:
+            for k in ("num_linears", "c_init", "c_hid", "c_final", "adim"):
+                assert getattr(d, k) == params[k], k
+        desc, blob = pack_network(sd, N)
+        n_param = sum(v.numel() for v in sd.values())
+        assert n_param <= blob.numel() <= n_param + 4 * len(sd)
+        # every parameter value survives packing (multiset of values, transposition aside)
+        src = torch.cat([v.reshape(-1) for v in sd.values()]).double()
+        assert abs(float(blob.double().sum()) - float(src.sum())) <= 1e-6 * float(src.abs().sum())
+        assert abs(float((blob.double() ** 2).sum()) - float((src ** 2).sum())) <= 1e-9 * float((src ** 2).sum())
+        # wrong tensor count / wrong shape are rejected
+        bad = dict(list(sd.items())[:-1])
+        with pytest.raises(Exception):
+            pack_network(bad, N, desc)
+
+
+def test_linear_weights_are_stored_transposed():
+    from gdss_b200.engine import pack_network
+    ck = load_golden_ckpt("qm9")
+    sd = ck["x_state_dict"]             # ScoreNetworkX: gcn weights first, then final.linears
+    _, blob = pack_network(sd, 9)
+    w0 = sd["layers.0.weight"]          # [in, out] stays as is at offset 0
+    assert torch.equal(blob[: w0.numel()].view_as(w0), w0)
+    wl = sd["final.linears.2.weight"]   # [out, in] -> [in, out]
+    tail = blob[-(wl.numel() + 4 + 0):]
+    flat = wl.t().contiguous().view(-1)
+    s = blob.unfold(0, flat.numel(), 1)
+    assert any(torch.equal(row, flat) for row in s[-64:])
+
+
+def test_models_load_reference_checkpoints_unchanged():
+    from gdss_b200.models import load_model
+    for name in CKPTS:
+        ck = load_golden_ckpt(name)
+        for params, sd in ((ck["params_x"], ck["x_state_dict"]), (ck["params_adj"], ck["adj_state_dict"])):
+            m = load_model(params)
+            assert list(m.state_dict().keys()) == list(sd.keys())
+            m.load_state_dict(sd, strict=True)
+    with pytest.raises(ValueError, match="Unknown"):
+        load_model({"model_type": "Nope"})
+
+
+def _oracle_coeffs(case, i):
+    sx = O.SDESpec(*case["sde_x"], case["scales"])
+    sa = O.SDESpec(*case["sde_adj"], case["scales"])
+    t = torch.linspace(1, 1e-4, case["scales"])[i]
+    return sx, sa, t
+
+
+@pytest.mark.parametrize("case", SHORT_CASES, ids=[c["name"] for c in SHORT_CASES])
+def test_schedule_table_matches_oracle_scalars(case):
+    """Apply the folded affine coefficients to random scalars and compare with the oracle's own
+    step algebra evaluated on the same numbers."""
+    from gdss_b200._lib import COL
+    from gdss_b200.schedule import build_table
+    from tests.gpu_common import sde_from
+    sdx, sda = sde_from(case["sde_x"], case["scales"]), sde_from(case["sde_adj"], case["scales"])
+    tab = build_table(sdx, sda, case["predictor"], case["corrector"], case["snr"], case["scale_eps"], 1e-4)
+    assert tab.shape == (case["scales"], 24) and tab.dtype == np.float32
+    rs = np.random.RandomState(0)
+    for i in (0, case["scales"] // 2, case["scales"] - 1):
+        sx, sa, t = _oracle_coeffs(case, i)
+        for d, sd in enumerate((sx, sa)):
+            y, raw, z = [torch.tensor(float(v)) for v in rs.standard_normal(3)]
+            row = tab[i]
+            cs = -1.0 / sd.marginal_std(t) if sd.kind != "VE" else torch.ones(())
+            assert np.isclose(row[COL["cs"] + d], float(cs), rtol=1e-6)
+            s = cs * raw
+            if case["predictor"] == "S4":
+                hdt = torch.ones(()) * (-0.5 / case["scales"])
+                m1, s1 = sd.transition(t, hdt)
+                m2, s2 = sd.transition(t + hdt, hdt)
+                want = m1 * y + s1 * z
+                want = want + (-sd.diffusion(t) ** 2 * s) * (-1.0 / case["scales"])
+                want = m2 * want
+                got = row[COL["mu1"] + d] * y + row[COL["sig1"] + d] * z
+                got = got + row[COL["drift"] + d] * raw
+                got = row[COL["mu2"] + d] * got
+                assert np.isclose(row[COL["sig2"] + d], float(s2), rtol=1e-6, equal_nan=True)
+            elif case["predictor"] == "Reverse":
+                f, G = sd.discretize(y, t)
+                want = y - (f - G ** 2 * s) + G * z
+                got = row[COL["pa"] + d] * y + row[COL["pb"] + d] * raw + row[COL["pc"] + d] * z
+            else:
+                dt = -1.0 / sd.N
+                g = sd.diffusion(t)
+                want = y + (sd.drift_coeff(t) * y - g ** 2 * s) * dt + g * np.sqrt(-dt) * z
+                got = row[COL["pa"] + d] * y + row[COL["pb"] + d] * raw + row[COL["pc"] + d] * z
+            assert abs(float(got) - float(want)) <= 2e-6 * max(1.0, abs(float(want))), (i, d, float(got), float(want))
+            if case["corrector"] == "Langevin":
+                assert np.isclose(row[COL["alpha"] + d], float(sd.langevin_alpha(t, False)), rtol=0, atol=0)
+
+
+def test_unknown_sde_and_predictor_behave_like_the_reference():
+    from gdss_b200.sde import load_sde, VPSDE
+    from gdss_b200.schedule import build_table
+    with pytest.raises(NotImplementedError, match="not yet supported"):
+        load_sde(dict(type="XX", beta_min=.1, beta_max=1., num_scales=10))
+    sde = VPSDE(.1, 1., 10)
+    a = build_table(sde, sde, "Bogus", "Bogus", .1, 1., 1e-3)      # silently Euler / None (solver.py:163-164)
+    b = build_table(sde, sde, "Euler", "None", .1, 1., 1e-3)
+    assert np.array_equal(a, b)
+
+
+def test_shard_bounds_cover_the_batch():
+    from gdss_b200.dist import shard_bounds
+    for total in (1, 7, 8, 10000, 10001):
+        for world in (1, 2, 3, 8):
+            spans = [shard_bounds(total, world, r) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == total
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
+            sizes = [hi - lo for lo, hi in spans]
+            assert max(sizes) - min(sizes) <= 1
+
+
+@pytest.mark.skipif(HAS_CUDA, reason="CPU-only behaviour")
+def test_compute_calls_fail_loudly_without_cuda():
+    from gdss_b200 import _lib
+    from gdss_b200.engine import Engine
+    from gdss_b200.solver import get_pc_sampler
+    from gdss_b200.sde import VPSDE
+    from gdss_b200.models import load_model
+    from gdss_b200 import graph_utils as G
+    ck = load_golden_ckpt("qm9")
+    with pytest.raises(_lib.GdssError, match="no CPU fallback"):
+        Engine(ck["x_state_dict"], ck["adj_state_dict"], 9, "cuda")
+    fn = get_pc_sampler(VPSDE(.1, 1., 10), VPSDE(.1, 1., 10), (2, 9, 4), (2, 9, 9), device="cpu")
+    with pytest.raises(Exception):
+        fn(ck["x_state_dict"], ck["adj_state_dict"], torch.ones(2, 9))
+    m = load_model(ck["params_adj"])
+    with pytest.raises(RuntimeError, match="CUDA"):
+        m(torch.zeros(1, 9, 4), torch.zeros(1, 9, 9), torch.ones(1, 9))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        G.mask_x(torch.zeros(1, 9, 4), torch.ones(1, 9))
+    # the C entry points themselves refuse, they do not silently compute on the host
+    L = _lib.lib()
+    assert L.gdss_quantize(C.c_void_p(8), C.c_void_p(8), 0.5, 4, None) == -2
+
+
+WORKER = r"""
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, os.environ["GDSS_ROOT"])
+from gdss_b200.dist import ShardInfo, shard_bounds
+dist.init_process_group("gloo")
+s = ShardInfo(create_comm=False)
+ident = s.exchange_id(lambda: bytes(range(128)))
+assert ident == bytes(range(128)), ident[:8]
+lo, hi = s.bounds(11)
+# the 4-float Langevin exchange: every rank contributes its shard's norm sums
+local = torch.tensor([float(hi - lo), 1.0, 2.0 * s.rank, 3.0])
+dist.all_reduce(local)
+assert local.tolist() == [11.0, 2.0, 2.0, 6.0], local
+open(os.path.join(os.environ["GDSS_OUT"], f"rank{s.rank}.txt"), "w").write(f"ok {lo} {hi}")
+"""
+
+
+def test_two_rank_gloo_sharding_and_id_exchange(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER)
+    env = dict(os.environ, GDSS_ROOT=ROOT, GDSS_OUT=str(tmp_path), MASTER_ADDR="127.0.0.1")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29613", str(script)],
+                         env=env, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    assert (tmp_path / "rank0.txt").read_text() == "ok 0 6" and (tmp_path / "rank1.txt").read_text() == "ok 6 11"
