@@ -1,0 +1,362 @@
+#!/usr/bin/env python
+"""Headline benchmark: sampled graphs/sec of the 1000-step reverse-diffusion sampler (BASELINE.json).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload zinc250k_v2|qm9_s4|...] [--impl reference]
+
+A "step" is ONE reverse-diffusion solver step (for Reverse+Langevin: corrector + predictor = two joint
+evaluations of both score networks, noise, norms, updates) over the whole batch; 1000 of them make one
+sample, so   value [graphs/s] = batch / (1000 * seconds_per_step).
+Every step costs the same (the work is data independent), so K steps measure the full run's rate.
+
+  value     inputs resident in HBM, K steps replayed from one captured CUDA graph, CUDA-event timed.
+  e2e       the public sampler API (get_pc_sampler / S4_solver closure) called with HOST flags; the timed
+            region holds the H2D copy, the on-device prior, K steps and the D2H copy of (x, adj).
+  roofline  the dominant kernel (per-kernel CUDA-event timing of eager launches, gdss_prof_*).
+  cpu_baseline  the CPU oracle port of the reference algorithm on the host cores (bounded sample).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+# per-graph FLOPs of one joint evaluation as the reference computes them
+WORKLOADS = {
+    "zinc250k_v2": dict(ckpt="zinc250k_v2", N=38, F=9, B=10000, sde_x=("VP", .1, 1.), sde_adj=("VE", .2, 1.),
+                        predictor="Reverse", corrector="Langevin", snr=.2, scale_eps=.8, evals=2,
+                        flop_eval=6.504e6 + 5.849e7, flop_final=2 * 1444 * (46 * 92 + 92 * 92 + 92), cpu_B=32, cpu_steps=4,
+                        desc="C3 ZINC250k v2 (N=38, F=9, ScoreNetworkX_GMH + ScoreNetworkA) Reverse+Langevin snr .2 scale_eps .8"),
+    "qm9_s4": dict(ckpt="qm9", N=9, F=4, B=10000, sde_x=("VE", .1, 1.), sde_adj=("VE", .1, 1.), predictor="S4",
+                   corrector="None", snr=.2, scale_eps=.7, evals=1, flop_eval=1.561e5 + 1.260e6,
+                   flop_final=2 * 81 * (22 * 44 + 44 * 44 + 44), cpu_B=1000, cpu_steps=8,
+                   desc="C2 QM9 (N=9, F=4, ScoreNetworkX + ScoreNetworkA) S4 snr .2 scale_eps .7"),
+    "community_small": dict(ckpt="community_small", N=20, F=10, B=100, sde_x=("VP", .1, 1.), sde_adj=("VP", .1, 1.),
+                            predictor="Euler", corrector="Langevin", snr=.05, scale_eps=.7, evals=2,
+                            flop_eval=2.953e6 + 1.663e7, flop_final=2 * 400 * (38 * 76 + 76 * 76 + 76), cpu_B=100,
+                            cpu_steps=8, desc="C1 community_small (N=20) Euler+Langevin"),
+    "enzymes": dict(ckpt="enzymes", N=125, F=10, B=64, sde_x=("VP", .1, 1.), sde_adj=("VE", .2, 1.), predictor="S4",
+                    corrector="None", snr=.15, scale_eps=.7, evals=1, flop_eval=5.030e7 + 8.747e8,
+                    flop_final=2 * 15625 * (54 * 108 + 108 * 108 + 108), cpu_B=8, cpu_steps=3, ema=True,
+                    desc="C4 ENZYMES (N=125) S4"),
+    "grid": dict(ckpt="grid", N=361, F=5, B=8, sde_x=("VP", .1, 1.), sde_adj=("VP", .2, .8), predictor="Reverse",
+                 corrector="Langevin", snr=.1, scale_eps=.7, evals=2, flop_eval=1.639e8 + 7.113e9,
+                 flop_final=2 * 130321 * (54 * 108 + 108 * 108 + 108), cpu_B=1, cpu_steps=2, ema=True,
+                 desc="C4 grid (N=361) Reverse+Langevin"),
+}
+
+
+def make_flags(wl, B, mode):
+    """SURVEY.md 8d synthetic node-count histograms (RandomState(42)); 'full' = flags == 1 (worst case)."""
+    N = wl["N"]
+    rs = np.random.RandomState(42)
+    if mode == "full":
+        counts = np.full(B, N)
+    elif wl["ckpt"].startswith("zinc"):
+        counts = np.clip(np.round(rs.normal(23.2, 4.5, B)), 6, 38).astype(int)
+    elif wl["ckpt"] == "qm9":
+        counts = rs.choice([9, 8, 7, 6, 5], size=B, p=[.83, .14, .025, .004, .001])
+    else:
+        counts = rs.randint(max(2, N // 2), N + 1, size=B)
+    flags = torch.zeros(B, N)
+    for b, c in enumerate(counts):
+        flags[b, :c] = 1.0
+    return flags, counts
+
+
+def load_weights(wl):
+    from oracle.cases import load_golden_ckpt     # fixture loader only (plain torch.load of tests/golden/ckpt)
+    ck = load_golden_ckpt(wl["ckpt"])
+    sdx, sda = ck["x_state_dict"], ck["adj_state_dict"]
+    if wl.get("ema"):
+        sdx = {k: s for k, s in zip(sdx.keys(), ck["ema_x"]["shadow_params"])}
+        sda = {k: s for k, s in zip(sda.keys(), ck["ema_adj"]["shadow_params"])}
+    return sdx, ck["params_x"], sda, ck["params_adj"]
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        pw = [float(r[2]) for r in self.rows if len(r) >= 7 and r[2].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for k, n in enumerate(names) if any(len(r) >= 7 and r[3 + k].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": reasons}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        d = json.load(open(p))
+        return d, "measured (MEASURED_PEAKS.json)"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "sm_max_mhz": 1965.0}, "fallback"
+
+
+class TimedTrace(list):
+    def __init__(self, sync=False):
+        super().__init__()
+        self.times, self.sync = [], sync
+
+    def append(self, rec):
+        if self.sync:
+            torch.cuda.synchronize()
+        self.times.append(time.perf_counter())
+
+
+def cpu_oracle_rate(wl, weights, B, warm, steps, flag_mode, device="cpu"):
+    """graphs/s of the oracle port (reference algorithm as plain PyTorch fp32 ops) on a bounded sample:
+    `steps` timed solver steps (after `warm`) on B graphs -- on the host cores (device='cpu', all threads)
+    or as PyTorch eager CUDA ops on the same GPU (device='cuda', TF32 off = the reference's default)."""
+    from oracle import gdss_oracle as O
+    sdx, px, sda, pa = weights
+    N, F = wl["N"], wl["F"]
+    torch.set_num_threads(os.cpu_count() or 1)
+    flags, _ = make_flags(wl, B, flag_mode)
+    draw = O.global_rng_draw
+    if device != "cpu":
+        torch.backends.cuda.matmul.allow_tf32 = False
+        torch.backends.cudnn.allow_tf32 = False
+        sdx = {k: v.to(device) for k, v in sdx.items()}
+        sda = {k: v.to(device) for k, v in sda.items()}
+        flags = flags.to(device)
+        draw = O.device_rng_draw(device)
+    sx, sa = O.SDESpec(*wl["sde_x"], 1000), O.SDESpec(*wl["sde_adj"], 1000)
+    tr = TimedTrace(sync=device != "cpu")
+    torch.manual_seed(0)
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        if wl["predictor"] == "S4":
+            O.s4_sample(sx, sa, sdx, px, sda, pa, (B, N, F), (B, N, N), flags, draw, snr=wl["snr"],
+                        scale_eps=wl["scale_eps"], eps=1e-4, trace=tr, max_iters=warm + steps)
+        else:
+            O.pc_sample(sx, sa, sdx, px, sda, pa, (B, N, F), (B, N, N), flags, draw,
+                        predictor=wl["predictor"], corrector=wl["corrector"], snr=wl["snr"], scale_eps=wl["scale_eps"],
+                        eps=1e-4, trace=tr, max_iters=warm + steps)
+    start = tr.times[warm - 1] if warm > 0 else t0
+    sec_per_step = (tr.times[-1] - start) / steps
+    return B / (1000.0 * sec_per_step), sec_per_step, torch.get_num_threads()
+
+
+def run_reference_arm(args, wl, weights):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    B = args.cpu_batch or wl["cpu_B"]
+    val, sps, cores = cpu_oracle_rate(wl, weights, B, args.warmup, args.steps, args.flags)
+    sample = f"{args.steps} timed solver steps (after {args.warmup}) of 1000 on B={B} graphs, shipped checkpoint weights"
+    line = {"impl": "reference", "metric": "sampled graphs/sec (1000-step reverse SDE)", "value": val, "unit": "graphs/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sps * 1e3,
+            "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic flags",
+            "config": workload_config(args, wl, B),
+            "cpu_baseline": {"value": val, "unit": "graphs/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": "graphs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "note": "the reference is pure Python/PyTorch and /root/reference is absent on the GPU box: this arm times the "
+                    "CPU oracle (oracle/gdss_oracle.py, pinned bit-close to the unmodified reference) on the host cores"}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, wl, B):
+    return {"workload": wl["desc"], "batch": B, "flags": args.flags, "solver_steps_per_sample": 1000,
+            "step": "one reverse-diffusion solver step over the whole batch", "l2": "inputs larger than L2 (per-step working "
+            "set = edge-channel stacks >> 126 MB at B=10000)" if B * wl["N"] ** 2 * 46 * 4 > 126e6 else "working set fits L2",
+            "weights": "shipped checkpoint (tests/golden/ckpt)", "noise": "in-kernel Philox4x32-10, seed 42"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="zinc250k_v2", choices=list(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=0)
+    ap.add_argument("--cpu-batch", type=int, default=0)
+    ap.add_argument("--flags", default="ragged", choices=["ragged", "full"])
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-profile", action="store_true")
+    ap.add_argument("--no-torch-baseline", action="store_true")
+    ap.add_argument("--torch-batch", type=int, default=10000)
+    args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
+    weights = load_weights(wl)
+    if args.impl == "reference":
+        return run_reference_arm(args, wl, weights)
+
+    from gdss_b200 import _lib
+    from gdss_b200.dist import init_from_env
+    from gdss_b200.engine import Engine, make_sampler_desc
+    from gdss_b200.schedule import build_table
+    from gdss_b200.solver import get_pc_sampler, S4_solver
+    from tests.gpu_common import sde_from
+    import torch.distributed as dist
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py (impl ours) needs a CUDA device: the GDSS kernels have no CPU fallback")
+    shard, dev = init_from_env()
+    world, rank = shard.world, shard.rank
+    sdx, px, sda, pa = weights
+    N, F = wl["N"], wl["F"]
+    B = args.batch or wl["B"]
+    if args.scaling == "weak":
+        B = B * world
+    flags, counts = make_flags(wl, B, args.flags)
+    lo, hi = shard.bounds(B)
+    K, W = args.steps, max(args.warmup, 0)
+    sx, sa = sde_from(wl["sde_x"], 1000), sde_from(wl["sde_adj"], 1000)
+    table = build_table(sx, sa, wl["predictor"], wl["corrector"], wl["snr"], wl["scale_eps"], 1e-4)
+    while table.shape[0] < W + K:                       # K beyond one sample: keep stepping with the same rows
+        table = np.concatenate([table, table[-1000:]])
+    sdesc = make_sampler_desc(sx, sa, wl["predictor"], wl["corrector"], wl["snr"], wl["scale_eps"], 1e-4, 1, False, True)
+    eng = Engine(sdx, sda, N, dev)
+    L = _lib.lib()
+    fl_local = flags[lo:hi].to(dev)
+    kw = dict(seed=42, graph_offset=lo, global_B=B, comm=shard.comm, use_graph=True)
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # ---- warm-up: W untimed steps from the prior
+    x, adj, xm, am = eng.sample(sdesc, table, fl_local, n_iters=max(W, 1), **kw)
+    barrier()
+    clocks = ClockSampler(dev.index if dev.index is not None else 0)
+    before = L.gdss_launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    x, adj, xm, am = eng.sample(sdesc, table, fl_local, x=x, adj=adj, first_step=max(W, 1), n_iters=K, **kw)
+    ev1.record()
+    barrier()
+    launches = L.gdss_launch_count() - before
+    ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = float(ms)
+    clk = clocks.stop()
+    ms_per_step = ms_total / K
+    value = B / (1000.0 * ms_per_step * 1e-3)
+    finite = bool(torch.isfinite(am).all())
+
+    # ---- e2e: public API with host buffers
+    get = S4_solver if wl["predictor"] == "S4" else get_pc_sampler
+    fn = get(sx, sa, (B, N, F), (B, N, N), predictor=wl["predictor"], corrector=wl["corrector"], snr=wl["snr"],
+             scale_eps=wl["scale_eps"], n_steps=1, probability_flow=False, continuous=True, denoise=True, eps=1e-4,
+             device=str(dev), shard=shard if world > 1 else None, max_iters=K)
+    host_flags = flags.pin_memory()
+    out_x = torch.empty(B, N, F).pin_memory()
+    out_a = torch.empty(B, N, N).pin_memory()
+    torch.manual_seed(42)
+    fn(sdx, sda, host_flags)                            # warm (engine cache, allocator)
+    barrier()
+    t0 = time.perf_counter()
+    ex, ea, _ = fn(sdx, sda, host_flags)
+    out_x.copy_(ex, non_blocking=True)
+    out_a.copy_(ea, non_blocking=True)
+    torch.cuda.synchronize(dev)
+    t_e2e = torch.tensor([time.perf_counter() - t0], device=dev)
+    if world > 1:
+        dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
+    e2e_val = B * K / (1000.0 * float(t_e2e))
+    e2e = {"value": e2e_val, "unit": "graphs/s", "h2d_bytes_per_step": host_flags.numel() * 4 / K,
+           "d2h_bytes_per_step": (out_x.numel() + out_a.numel()) * 4 / K,
+           "call": f"sampler(model_x, model_adj, host_flags) for {K} solver steps + D2H of (x, adj); bytes are per call / {K}"}
+
+    if rank != 0:
+        return
+    peaks, peak_src = measured_peaks()
+    # ---- per-kernel timing of eager launches (1 GPU view) -> roofline of the dominant kernel
+    roofline, kernel_ms = None, None
+    if not args.no_profile:
+        nb = hi - lo
+        L.gdss_prof_begin(torch.cuda.current_stream(dev).cuda_stream)
+        eng.sample(sdesc, table, fl_local, x=x, adj=adj, first_step=1, n_iters=2, seed=42, graph_offset=lo, global_B=B,
+                   comm=None if world == 1 else shard.comm, use_graph=False)
+        import ctypes as C
+        msb = (C.c_float * 16)()
+        cnt = (C.c_int64 * 16)()
+        _lib.check(L.gdss_prof_end(msb, cnt, 16), "gdss_prof_end")
+        kernel_ms = {L.gdss_prof_name(i).decode(): {"ms_per_step": msb[i] / 2, "launches_per_step": cnt[i] / 2}
+                     for i in range(14) if cnt[i]}
+        tot = sum(v["ms_per_step"] for v in kernel_ms.values())
+        for v in kernel_ms.values():
+            v["share"] = v["ms_per_step"] / tot
+        fin = kernel_ms.get("final_edge_kernel")
+        if fin:
+            per_launch_ms = fin["ms_per_step"] / fin["launches_per_step"]
+            ach = nb * wl["flop_final"] / (per_launch_ms * 1e-3) / 1e12
+            peak = peaks["bf16_tflops_sustained"]
+            fp32_peak = 148 * 128 * 2 * (clk["sm_mhz"] or peaks["sm_max_mhz"]) * 1e6 / 1e12
+            roofline = {"bound": "tensor", "kernel": "final_edge_kernel", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
+                        "frac": ach / peak, "traffic": None, "peak_source": peak_src + ", sustained bf16 (kernel timed inside a long step)",
+                        "kernel_ms": per_launch_ms, "share_of_step": fin["share"],
+                        "fp32_ffma_peak_tflops_at_observed_clock": fp32_peak, "frac_of_fp32_ffma_peak": ach / fp32_peak,
+                        "note": "round-1 kernel computes on the FP32 FFMA pipe (strict fp32 parity); algorithmic FLOPs = the "
+                                "reference's dense count for ScoreNetworkA.final over all N^2 pixels (no symmetry/flag credit)"}
+    cpu = None
+    if not args.no_cpu_baseline and world == 1:
+        cb, cs = args.cpu_batch or wl["cpu_B"], wl["cpu_steps"]
+        v, sps, cores = cpu_oracle_rate(wl, weights, cb, 1, cs, args.flags)
+        cpu = {"value": v, "unit": "graphs/s", "cores": cores, "kind": "port",
+               "sample": f"{cs} timed solver steps (after 1) of 1000 on B={cb} graphs, {sps:.2f} s/step, same weights/flags recipe"}
+    torch_gpu = None
+    if not args.no_torch_baseline and world == 1:
+        try:
+            del eng, x, adj, xm, am, ex, ea
+            torch.cuda.empty_cache()
+            tb = min(B, args.torch_batch)
+            v, sps, _ = cpu_oracle_rate(wl, weights, tb, 1, 2, args.flags, device=str(dev))
+            torch_gpu = {"value": v, "unit": "graphs/s", "kind": "port (oracle as PyTorch eager CUDA fp32 ops, TF32 off)",
+                         "sample": f"2 timed solver steps (after 1) of 1000 on B={tb} graphs on the same B200, {sps * 1e3:.1f} ms/step"}
+        except Exception as exc:                                  # e.g. out of memory: reported, not fatal
+            torch_gpu = {"unavailable": repr(exc)[:200]}
+    path_tflops = value * 1000 * wl["evals"] * wl["flop_eval"] / 1e12
+    line = {"metric": "sampled graphs/sec (1000-step reverse SDE)", "value": value, "unit": "graphs/s", "n_gpus": world,
+            "steps": K, "warmup": W, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": args.scaling,
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic flags (SURVEY 8d node-count recipe), shipped checkpoint weights",
+            "config": workload_config(args, wl, B), "clocks": clk, "e2e": e2e, "gpu_launches": int(launches) * world,
+            "roofline": roofline, "cpu_baseline": cpu, "torch_eager_same_gpu": torch_gpu,
+            "path_algorithmic_tflops": path_tflops,
+            "mean_nodes": float(np.mean(counts)), "finite": finite, "kernel_ms": kernel_ms}
+    print(json.dumps(line), flush=True)
+    shard.close()
+
+
+if __name__ == "__main__":
+    main()

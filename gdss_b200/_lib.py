@@ -79,6 +79,9 @@ def lib():
         "gdss_quantize": (C.c_int, [fp, fp, C.c_float, i64, vp]),
         "gdss_quantize_mol": (C.c_int, [fp, vp, i64, vp]),
         "gdss_launch_count": (i64, []),
+        "gdss_prof_begin": (C.c_int, [vp]),
+        "gdss_prof_end": (C.c_int, [fp, vp, i32]),
+        "gdss_prof_name": (C.c_char_p, [i32]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)          # AttributeError here = header / library mismatch

@@ -72,6 +72,13 @@ int launch_neff(const float* flags, int* neff, int B, int N, int inputs_masked, 
 
 void count_launch(int n = 1);
 
+// optional per-kernel-class timing (gdss_prof_begin / gdss_prof_end): when enabled every launch site
+// records a CUDA event right after its launch on the launching stream.
+enum KernelId { K_NEFF = 0, K_POW, K_DEG, K_GCN, K_EDGE, K_NODE, K_FINAL_EDGE, K_FINAL_NODE, K_COPY, K_NORMS, K_SUMS,
+                K_UPDATE, K_MISC, K_MEMOPS, K_COUNT };
+void prof_tick(int kid, cudaStream_t st);
+inline void launched(int kid, cudaStream_t st) { count_launch(); prof_tick(kid, st); }
+
 // NCCL (dlopen'ed)
 int nccl_allreduce_sum(void* comm, float* buf, int count, cudaStream_t st);
 

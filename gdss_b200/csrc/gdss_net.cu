@@ -13,6 +13,8 @@
 // zeroes them, ScoreNetwork_A.py:145).
 #include <stdio.h>
 
+#include <vector>
+
 #include "gdss_common.cuh"
 #include "gdss_internal.h"
 
@@ -20,6 +22,25 @@ namespace gdss {
 
 static int64_t g_launches = 0;
 void count_launch(int n) { g_launches += n; }
+
+// ---- per-kernel-class timing -------------------------------------------------------------
+struct ProfState {
+  bool on = false;
+  std::vector<cudaEvent_t> ev;
+  std::vector<int> kid;
+};
+static ProfState g_prof;
+
+void prof_tick(int kid, cudaStream_t st) {
+  if (!g_prof.on) return;
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(st, &cap) != cudaSuccess || cap != cudaStreamCaptureStatusNone) return;
+  cudaEvent_t e;
+  if (cudaEventCreate(&e) != cudaSuccess) return;
+  cudaEventRecord(e, st);
+  g_prof.ev.push_back(e);
+  g_prof.kid.push_back(kid);
+}
 
 #define LAUNCH_CHECK()                          \
   do {                                          \
@@ -48,7 +69,7 @@ __global__ void neff_kernel(const float* __restrict__ flags, int* __restrict__ n
 
 int launch_neff(const float* flags, int* neff, int B, int N, int inputs_masked, cudaStream_t st) {
   neff_kernel<<<(B + 7) / 8, 256, 0, st>>>(flags, neff, B, N, inputs_masked);
-  count_launch();
+  launched(K_NEFF, st);
   LAUNCH_CHECK();
   return 0;
 }
@@ -753,7 +774,7 @@ static int launch_gcn(const GcnArgs& g, int C, int B, cudaStream_t st) {
   if (rc) return rc;
   dim3 grid((g.N + g.TI - 1) / g.TI, C, B);
   gcn_kernel<<<grid, 256, smem, st>>>(g);
-  count_launch();
+  launched(K_GCN, st);
   LAUNCH_CHECK();
   return 0;
 }
@@ -782,15 +803,16 @@ static int run_attn_net(const gdss_ctx* ctx, const NetPlan& p, const float* blob
   // ---- power stack: plane 0 = adj, plane k = plane k-1 @ adj
   cudaError_t e = cudaMemcpy2DAsync(stack, s_bs * 4, adj, NN * 4, NN * 4, B, cudaMemcpyDeviceToDevice, st);
   if (e != cudaSuccess) return (int)e;
+  prof_tick(K_MEMOPS, st);
   for (int k = 1; k < p.c_init; ++k) {
     pow_kernel<<<dim3(ntile32, ntile32, B), 256, 0, st>>>(stack + (k - 1) * NN, s_bs, adj, NN, stack + k * NN, s_bs,
                                                          neff, N);
-    count_launch();
+    launched(K_POW, st);
     LAUNCH_CHECK();
   }
   if (!isA) {
     copy_x_kernel<<<dim3((N * F + 255) / 256, B), 256, 0, st>>>(x, xs, N, F, p.fdim, neff);
-    count_launch();
+    launched(K_COPY, st);
     LAUNCH_CHECK();
   }
   const float* xin = x;
@@ -804,7 +826,7 @@ static int run_attn_net(const gdss_ctx* ctx, const NetPlan& p, const float* blob
     const bool need_node = !isA || !last;  // A: the last layer's x_out (hence V) is dead
     const float* pin = stack + (int64_t)cur * NN;
     deg_kernel<<<dim3(L.c_in, B), 256, 0, st>>>(pin, s_bs, dis, d_bs, neff, N);
-    count_launch();
+    launched(K_DEG, st);
     LAUNCH_CHECK();
     GcnArgs g;
     g.planes = pin; g.p_bs = s_bs;
@@ -846,7 +868,7 @@ static int run_attn_net(const gdss_ctx* ctx, const NetPlan& p, const float* blob
       rc = set_smem(fn, smem);
       if (rc) return rc;
       fn<<<dim3(ea.ntile * (ea.ntile + 1) / 2, B), 256, smem, st>>>(ea);
-      count_launch();
+      launched(K_EDGE, st);
       LAUNCH_CHECK();
     }
     if (need_node) {
@@ -861,7 +883,7 @@ static int run_attn_net(const gdss_ctx* ctx, const NetPlan& p, const float* blob
       rc = set_smem(node_kernel, smem);
       if (rc) return rc;
       node_kernel<<<dim3((N + NODE_ROWS - 1) / NODE_ROWS, B), 256, smem, st>>>(na);
-      count_launch();
+      launched(K_NODE, st);
       LAUNCH_CHECK();
       xin = na.out; x_bs = na.o_bs; ldx = na.ldo;
     }
@@ -885,7 +907,7 @@ static int run_attn_net(const gdss_ctx* ctx, const NetPlan& p, const float* blob
     int P = N * (N - 1) / 2;
     if (P > 0) {
       fn<<<dim3((P + 127) / 128, B), 256, smem, st>>>(fa);
-      count_launch();
+      launched(K_FINAL_EDGE, st);
       LAUNCH_CHECK();
     }
   } else {
@@ -898,7 +920,7 @@ static int run_attn_net(const gdss_ctx* ctx, const NetPlan& p, const float* blob
     int rc = set_smem(final_node_kernel, smem);
     if (rc) return rc;
     final_node_kernel<<<dim3((N + FN_ROWS - 1) / FN_ROWS, B), 256, smem, st>>>(fa);
-    count_launch();
+    launched(K_FINAL_NODE, st);
     LAUNCH_CHECK();
   }
   return 0;
@@ -913,10 +935,10 @@ static int run_gcn_net(const gdss_ctx* ctx, const NetPlan& p, const float* blob,
   float* dis = reinterpret_cast<float*>(ws + w.off[R_DIS]);
   float* xs = reinterpret_cast<float*>(ws + w.off[R_XS]);
   copy_x_kernel<<<dim3((N * F + 255) / 256, B), 256, 0, st>>>(x, xs, N, F, p.fdim, neff);
-  count_launch();
+  launched(K_COPY, st);
   LAUNCH_CHECK();
   deg_kernel<<<dim3(1, B), 256, 0, st>>>(adj, NN, dis, N, neff, N);
-  count_launch();
+  launched(K_DEG, st);
   LAUNCH_CHECK();
   for (int l = 0; l < p.depth; ++l) {
     GcnArgs g;
@@ -940,7 +962,7 @@ static int run_gcn_net(const gdss_ctx* ctx, const NetPlan& p, const float* blob,
   int rc = set_smem(final_node_kernel, smem);
   if (rc) return rc;
   final_node_kernel<<<dim3((N + FN_ROWS - 1) / FN_ROWS, B), 256, smem, st>>>(fa);
-  count_launch();
+  launched(K_FINAL_NODE, st);
   LAUNCH_CHECK();
   return 0;
 }
@@ -952,12 +974,14 @@ int launch_eval(const gdss_ctx* ctx, const float* x, const float* adj, const flo
   if (score_adj && ctx->has_a) {
     e = cudaMemsetAsync(score_adj, 0, sizeof(float) * (size_t)B * N * N, st);
     if (e != cudaSuccess) return (int)e;
+    prof_tick(K_MEMOPS, st);
     int rc = run_attn_net(ctx, ctx->pa, ctx->blob_a, x, adj, flags, neff, score_adj, B, ws, w, st);
     if (rc) return rc;
   }
   if (score_x && ctx->has_x) {
     e = cudaMemsetAsync(score_x, 0, sizeof(float) * (size_t)B * N * F, st);
     if (e != cudaSuccess) return (int)e;
+    prof_tick(K_MEMOPS, st);
     int rc;
     if (ctx->px.type == GDSS_NET_X)
       rc = run_gcn_net(ctx, ctx->px, ctx->blob_x, x, adj, flags, neff, score_x, B, ws, w, st);
@@ -971,3 +995,40 @@ int launch_eval(const gdss_ctx* ctx, const float* x, const float* adj, const flo
 }  // namespace gdss
 
 extern "C" int64_t gdss_launch_count(void) { return gdss::g_launches; }
+
+extern "C" int gdss_prof_begin(void* stream) {
+  using namespace gdss;
+  for (cudaEvent_t e : g_prof.ev) cudaEventDestroy(e);
+  g_prof.ev.clear();
+  g_prof.kid.clear();
+  g_prof.on = true;
+  prof_tick(K_MISC, (cudaStream_t)stream);      // time origin
+  return 0;
+}
+
+extern "C" int gdss_prof_end(float* ms, int64_t* counts, int32_t n) {
+  using namespace gdss;
+  g_prof.on = false;
+  if (!ms || !counts || n < K_COUNT) return GDSS_E_BADARG;
+  for (int i = 0; i < n; ++i) { ms[i] = 0.f; counts[i] = 0; }
+  if (g_prof.ev.empty()) return 0;
+  cudaError_t e = cudaEventSynchronize(g_prof.ev.back());
+  if (e != cudaSuccess) return (int)e;
+  for (size_t i = 1; i < g_prof.ev.size(); ++i) {
+    float t = 0.f;
+    cudaEventElapsedTime(&t, g_prof.ev[i - 1], g_prof.ev[i]);
+    ms[g_prof.kid[i]] += t;
+    counts[g_prof.kid[i]] += 1;
+  }
+  for (cudaEvent_t ev : g_prof.ev) cudaEventDestroy(ev);
+  g_prof.ev.clear();
+  g_prof.kid.clear();
+  return 0;
+}
+
+extern "C" const char* gdss_prof_name(int32_t kid) {
+  static const char* names[gdss::K_COUNT] = {"neff_kernel", "pow_kernel", "deg_kernel", "gcn_kernel", "edge_kernel", "node_kernel",
+                                             "final_edge_kernel", "final_node_kernel", "copy_x_kernel", "norms_kernel",
+                                             "sums_kernel", "update_kernel", "misc", "memset/memcpy"};
+  return kid >= 0 && kid < gdss::K_COUNT ? names[kid] : "?";
+}

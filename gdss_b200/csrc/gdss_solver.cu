@@ -329,10 +329,10 @@ static int enqueue_step(const StepPlan& p, cudaStream_t st) {
   if (rc) return rc;
   if (p.s4 || p.langevin) {
     norms_kernel<<<B, 256, 0, st>>>(u.ns, raw_x, raw_a, u.flags, u.neff, u.table, u.step_ptr, p.norms);
-    count_launch();
+    launched(K_NORMS, st);
     LAUNCH_CHECK();
     sums_kernel<<<1, 1024, 0, st>>>(p.norms, B, p.sums);
-    count_launch();
+    launched(K_SUMS, st);
     LAUNCH_CHECK();
     if (p.comm) {
       rc = nccl_allreduce_sum(p.comm, p.sums, 4, st);
@@ -341,22 +341,22 @@ static int enqueue_step(const StepPlan& p, cudaStream_t st) {
   }
   if (p.s4) {
     update_kernel<MODE_S4><<<ugrid, 256, 0, st>>>(u);
-    count_launch();
+    launched(K_UPDATE, st);
     LAUNCH_CHECK();
   } else {
     if (p.langevin) {
       update_kernel<MODE_CORR><<<ugrid, 256, 0, st>>>(u);
-      count_launch();
+      launched(K_UPDATE, st);
       LAUNCH_CHECK();
       rc = launch_eval(p.ctx, u.x, u.adj, u.flags, u.neff, raw_x, raw_a, B, p.ws, p.w, st);
       if (rc) return rc;
     }
     update_kernel<MODE_PRED><<<ugrid, 256, 0, st>>>(u);
-    count_launch();
+    launched(K_UPDATE, st);
     LAUNCH_CHECK();
   }
   advance_kernel<<<1, 1, 0, st>>>(p.step_ptr);
-  count_launch();
+  launched(K_MISC, st);
   LAUNCH_CHECK();
   return 0;
 }
@@ -424,13 +424,13 @@ extern "C" int gdss_sample(gdss_ctx* ctx, const gdss_sampler_desc* s, const gdss
   e = cudaMemcpyAsync(dtable, table, sizeof(gdss_step_coef) * (size_t)(first_step + n_iters), cudaMemcpyHostToDevice, st);
   if (e != cudaSuccess) return (int)e;
   set_step_kernel<<<1, 1, 0, st>>>(p.step_ptr, first_step);
-  count_launch();
+  launched(K_MISC, st);
   LAUNCH_CHECK();
   int rc = launch_neff(flags, neff, B, N, 1, st);
   if (rc) return rc;
   if (init_prior) {
     prior_kernel<<<B, 256, 0, st>>>(u.ns, x, adj, flags);
-    count_launch();
+    launched(K_MISC, st);
     LAUNCH_CHECK();
   }
   if (first_step == 0 || init_prior) {

@@ -180,6 +180,12 @@ int gdss_quantize_mol(const float* adj, int64_t* out, int64_t numel, void* strea
 /* ---- introspection for tests / profiling ---------------------------------------------- */
 /* number of kernel launches the library has enqueued since process start (all contexts) */
 int64_t gdss_launch_count(void);
+/* per-kernel-class device time of everything enqueued (eagerly, i.e. use_graph == 0) between
+ * gdss_prof_begin and gdss_prof_end: CUDA events recorded after every launch on its own stream.
+ * ms / counts have n >= 16 entries indexed by kernel class; gdss_prof_name names a class. */
+int gdss_prof_begin(void* stream);
+int gdss_prof_end(float* ms, int64_t* counts, int32_t n);
+const char* gdss_prof_name(int32_t kernel_class);
 /* workspace layout of the last plan: byte offsets of named regions (for parity tests that look
  * at intermediates).  Returns <0 if name unknown. */
 int64_t gdss_workspace_offset(const gdss_ctx* ctx, int32_t B, const char* region);

@@ -122,7 +122,7 @@ def dense_gcn(x: Tensor, adj: Tensor, weight: Tensor, bias: Tensor) -> Tensor:
     normalisation, out = A_hat @ (x @ W) + b.  ``weight`` is [in, out]."""
     n = adj.shape[-1]
     a = adj.clone()
-    ii = torch.arange(n)
+    ii = torch.arange(n, device=adj.device)
     a[:, ii, ii] = 1.0
     xw = torch.matmul(x, weight)
     dis = a.sum(dim=-1).clamp(min=1).pow(-0.5)
@@ -226,7 +226,7 @@ def score_network_a(sd: StateDict, p: dict, x: Tensor, adj: Tensor, flags: Tenso
     cat = torch.cat(stacks, dim=1).permute(0, 2, 3, 1)         # [B,N,N,fdim]
     score = mlp(sd, "final", cat, 3).squeeze(-1)
     n = adj.shape[-1]
-    score = score * (1.0 - torch.eye(n)).unsqueeze(0)
+    score = score * (1.0 - torch.eye(n, device=score.device)).unsqueeze(0)
     return mask_adjs(score, flags)
 
 
@@ -518,6 +518,16 @@ def s4_sample(sde_x: SDESpec, sde_adj: SDESpec, sd_x: StateDict, p_x: dict, sd_a
 def global_rng_draw(shape):
     """Draw from the global torch CPU generator, exactly like the reference."""
     return torch.randn(*shape)
+
+
+def device_rng_draw(device):
+    """Draws on `device` (the reference draws its in-loop noise on the state's device, graph_utils.py:79).
+    With tensors on a CUDA device every function of this module runs as plain PyTorch eager CUDA ops --
+    the same ops the unmodified reference issues -- which bench.py times as the 'torch eager on the same
+    GPU' baseline.  Still test/bench infrastructure only."""
+    def draw(shape):
+        return torch.randn(*shape, device=device)
+    return draw
 
 
 class RecordedDraws:
