@@ -1014,7 +1014,8 @@ extern "C" int gdss_prof_end(float* ms, int64_t* counts, int32_t n) {
   if (g_prof.ev.empty()) return 0;
   cudaError_t e = cudaEventSynchronize(g_prof.ev.back());
   if (e != cudaSuccess) return (int)e;
-  for (size_t i = 1; i < g_prof.ev.size(); ++i) {
+  // interval 1 (origin tick -> first launch) is host-side set-up with an idle GPU: not attributed
+  for (size_t i = 2; i < g_prof.ev.size(); ++i) {
     float t = 0.f;
     cudaEventElapsedTime(&t, g_prof.ev[i - 1], g_prof.ev[i]);
     ms[g_prof.kid[i]] += t;

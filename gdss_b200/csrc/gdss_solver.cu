@@ -194,9 +194,19 @@ struct UpdateArgs {
 template <int MODE>
 __global__ void __launch_bounds__(256) update_kernel(UpdateArgs a) {
   const NoiseSrc& ns = a.ns;
-  const int b = blockIdx.y, N = ns.N, F = ns.F, n = a.neff[b];
+  const int b = blockIdx.y, N = ns.N, F = ns.F;
   const int step = *a.step_ptr;
   const gdss_step_coef c = a.table[step];
+  // The reference updates every element, padded nodes and the diagonal included (0 * coef + 0 * z): they
+  // stay exactly 0 unless a coefficient is non-finite (e.g. the last S4 half-transition of a VP SDE with
+  // few scales takes sqrt of a negative variance, sde.py:163-168) and then turn NaN everywhere.  Only in
+  // that case is the full N x N range (diagonal included) walked; otherwise only the live n x n block.
+  bool finite = true;
+  {
+    const float* cf = reinterpret_cast<const float*>(&c);
+#pragma unroll
+    for (int q = 0; q < 20; ++q) finite = finite && (fabsf(cf[q]) <= 3.0e38f);
+  }
   float eps_x = 0.f, eps_a = 0.f;
   if (MODE != MODE_PRED) {
     const float gx = a.sums[0] * a.inv_gb, nx = a.sums[1] * a.inv_gb, ga = a.sums[2] * a.inv_gb, na = a.sums[3] * a.inv_gb;
@@ -207,6 +217,9 @@ __global__ void __launch_bounds__(256) update_kernel(UpdateArgs a) {
       tr[0] = eps_x; tr[1] = eps_a; tr[2] = gx; tr[3] = nx; tr[4] = ga; tr[5] = na; tr[6] = c.t; tr[7] = (float)step;
     }
   }
+  if (MODE != MODE_PRED) finite = finite && (fabsf(eps_x) <= 3.0e38f) && (fabsf(eps_a) <= 3.0e38f);
+  const int n = finite ? a.neff[b] : N;
+  const int dg = finite ? 1 : 0;           // first column offset: strict upper triangle, or diagonal included
   const float nzx = sqrtf(eps_x * 2.f) * c.seps, nza = sqrtf(eps_a * 2.f) * c.seps;
   const float* fl = a.flags + (int64_t)b * N;
   const int gwx = (F + 3) >> 2, gwa = (N + 3) >> 2;
@@ -256,7 +269,7 @@ __global__ void __launch_bounds__(256) update_kernel(UpdateArgs a) {
     const float* RA = a.raw_adj + (int64_t)b * N * N;
     for (int idx = t0; idx < n * gwa; idx += stride) {
       int i = idx / gwa, g = idx - i * gwa;
-      if (4 * g + 3 <= i || 4 * g >= n) continue;
+      if (4 * g + 3 < i + dg || 4 * g >= n) continue;
       const float fi = fl[i];
       float4 z0, z1, z2;
       if (MODE == MODE_CORR) z0 = noise_a4(ns, b, step, 0, i, g);
@@ -269,8 +282,8 @@ __global__ void __launch_bounds__(256) update_kernel(UpdateArgs a) {
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         const int j = 4 * g + q;
-        if (j <= i || j >= n) continue;
-        const float f = fi * fl[j];
+        if (j < i + dg || j >= n) continue;
+        const float f = j == i ? 0.f : fi * fl[j];      // the symmetric noise has a zero diagonal (triu(1))
         const int e = i * N + j, et = j * N + i;
         float y = A[e];
         const float r = RA[e];

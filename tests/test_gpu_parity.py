@@ -89,7 +89,10 @@ def test_sampler_steps_match_oracle_and_reference(name):
     assert ex <= 10 * TOL and ea <= 10 * TOL, (name, ex, ea, worst)
     # graph replay == eager launches, bit for bit
     x2, adj2, xm2, am2 = eng.sample(sdesc, table, flags, x=x0, adj=a0, n_iters=iters, inj_x=ix, inj_adj=ia, use_graph=False)
-    assert torch.equal(x, x2) and torch.equal(adj, adj2) and torch.equal(am, am2)
+    def bits(t):                      # NaNs (enzymes_s4: the reference's own last-step NaN) compare equal bitwise
+        return t.contiguous().view(torch.int32)
+
+    assert torch.equal(bits(x), bits(x2)) and torch.equal(bits(adj), bits(adj2)) and torch.equal(bits(am), bits(am2))
 
 
 def _tape(ts):
