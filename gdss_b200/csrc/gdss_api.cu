@@ -69,6 +69,9 @@ extern "C" gdss_ctx* gdss_ctx_create(int32_t N, int32_t F, const gdss_net_desc* 
     cudaDeviceGetAttribute(&c->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
     cudaDeviceGetAttribute(&c->num_sms, cudaDevAttrMultiProcessorCount, dev);
   }
+  c->fused = false;
+  const char* nf = getenv("GDSS_NO_FUSED");
+  if (!(nf && nf[0] == '1')) c->fused = fused_supported(c);
   return c;
 }
 
@@ -83,7 +86,7 @@ extern "C" int64_t gdss_workspace_bytes(const gdss_ctx* ctx, int32_t B) {
 
 extern "C" int64_t gdss_workspace_offset(const gdss_ctx* ctx, int32_t B, const char* region) {
   static const char* names[R_COUNT] = {"neff", "step", "table", "means", "norms", "stack_a", "stack_x", "dis",
-                                       "qkv", "xa0", "xa1", "xs", "raw_x", "raw_adj"};
+                                       "qkv", "xa0", "xa1", "xs", "raw_x", "raw_adj", "poff", "meta", "gmap", "stackT"};
   if (!ctx || B <= 0 || !region) return GDSS_E_BADARG;
   Workspace w;
   layout_workspace(ctx, B, &w);
@@ -104,7 +107,8 @@ extern "C" int gdss_score_forward(gdss_ctx* ctx, const float* x, const float* ad
   cudaStream_t st = (cudaStream_t)stream;
   char* ws = (char*)workspace;
   int* neff = reinterpret_cast<int*>(ws + w.off[R_NEFF]);
-  int rc = launch_neff(flags, neff, B, ctx->N, inputs_masked, st);
+  if ((int64_t)B * (ctx->N * (ctx->N - 1) / 2) >= (int64_t)1 << 30 || B >= (1 << 19)) return GDSS_E_UNSUPPORTED;
+  int rc = launch_setup(ctx, flags, B, inputs_masked, ws, w, st);
   if (rc) return rc;
   return launch_eval(ctx, x, adj, flags, neff, score_x, score_adj, B, ws, w, st);
 }

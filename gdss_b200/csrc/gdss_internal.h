@@ -42,11 +42,13 @@ int plan_net(const gdss_net_desc* d, int N, NetPlan* p);
 // named workspace regions (byte offsets, 256-aligned)
 enum Region {
   R_NEFF = 0, R_STEP, R_TABLE, R_MEANS, R_NORMS, R_STACK_A, R_STACK_X, R_DIS, R_QKV, R_XA0, R_XA1, R_XS, R_RAW_X, R_RAW_ADJ,
+  R_POFF, R_META, R_GMAP, R_STACKT,
   R_COUNT
 };
 
 struct Workspace {
   int64_t off[R_COUNT + 1];
+  int64_t pstride;              // fused path: floats per channel plane of the pixel-major stack
 };
 
 }  // namespace gdss
@@ -59,6 +61,7 @@ struct gdss_ctx {
   const float* blob_a;
   int smem_optin;               // max dynamic shared memory per block
   int num_sms;
+  bool fused;                   // small-graph path: one CTA per graph (gdss_fused.cu)
 };
 
 namespace gdss {
@@ -75,9 +78,18 @@ void count_launch(int n = 1);
 // optional per-kernel-class timing (gdss_prof_begin / gdss_prof_end): when enabled every launch site
 // records a CUDA event right after its launch on the launching stream.
 enum KernelId { K_NEFF = 0, K_POW, K_DEG, K_GCN, K_EDGE, K_NODE, K_FINAL_EDGE, K_FINAL_NODE, K_COPY, K_NORMS, K_SUMS,
-                K_UPDATE, K_MISC, K_MEMOPS, K_COUNT };
+                K_UPDATE, K_MISC, K_MEMOPS, K_FUSED, K_COUNT };
 void prof_tick(int kid, cudaStream_t st);
 inline void launched(int kid, cudaStream_t st) { count_launch(); prof_tick(kid, st); }
+
+// fused small-graph path (gdss_fused.cu)
+bool fused_supported(const gdss_ctx* ctx);
+int launch_tri_setup(const gdss_ctx* ctx, const int* neff, int B, char* ws, const Workspace& w, cudaStream_t st);
+int launch_eval_fused(const gdss_ctx* ctx, const float* x, const float* adj, const float* flags, const int* neff,
+                      float* score_x, float* score_adj, int B, char* ws, const Workspace& w, cudaStream_t st);
+// flags -> neff (+ the pixel bookkeeping of the fused path); call once per flags tensor
+int launch_setup(const gdss_ctx* ctx, const float* flags, int B, int inputs_masked, char* ws, const Workspace& w,
+                 cudaStream_t st);
 
 // NCCL (dlopen'ed)
 int nccl_allreduce_sum(void* comm, float* buf, int count, cudaStream_t st);

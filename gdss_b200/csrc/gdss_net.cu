@@ -713,6 +713,17 @@ void layout_workspace(const gdss_ctx* ctx, int B, Workspace* w) {
   sz[R_QKV] = 4 * (int64_t)B * qkv;
   sz[R_XA0] = 4 * (int64_t)B * N * nh;
   sz[R_XA1] = 4 * (int64_t)B * N * nh;
+  w->pstride = 0;
+  if (ctx->fused) {
+    // the per-graph kernel keeps everything but the A-network's channel stack on chip
+    sz[R_STACK_A] = sz[R_STACK_X] = sz[R_DIS] = sz[R_QKV] = sz[R_XA0] = sz[R_XA1] = sz[R_XS] = 0;
+    const int64_t pmax = (int64_t)B * (N * (N - 1) / 2);
+    w->pstride = (pmax + 127) / 128 * 128 + 128;
+    sz[R_POFF] = 4 * ((int64_t)B + 1);
+    sz[R_META] = 256;
+    sz[R_GMAP] = 4 * w->pstride;
+    sz[R_STACKT] = ctx->has_a ? 4 * w->pstride * ctx->pa.fdim : 0;
+  }
   sz[R_RAW_X] = 4 * (int64_t)B * N * F;
   sz[R_RAW_ADJ] = 4 * (int64_t)B * N * N;
   int64_t cur = 0;
@@ -967,10 +978,32 @@ static int run_gcn_net(const gdss_ctx* ctx, const NetPlan& p, const float* blob,
   return 0;
 }
 
+int launch_setup(const gdss_ctx* ctx, const float* flags, int B, int inputs_masked, char* ws, const Workspace& w,
+                 cudaStream_t st) {
+  int* neff = reinterpret_cast<int*>(ws + w.off[R_NEFF]);
+  int rc = launch_neff(flags, neff, B, ctx->N, inputs_masked, st);
+  if (rc) return rc;
+  if (ctx->fused) rc = launch_tri_setup(ctx, neff, B, ws, w, st);
+  return rc;
+}
+
 int launch_eval(const gdss_ctx* ctx, const float* x, const float* adj, const float* flags, const int* neff,
                 float* score_x, float* score_adj, int B, char* ws, const Workspace& w, cudaStream_t st) {
   const int N = ctx->N, F = ctx->F;
   cudaError_t e;
+  if (ctx->fused) {
+    if (score_adj && ctx->has_a) {
+      e = cudaMemsetAsync(score_adj, 0, sizeof(float) * (size_t)B * N * N, st);
+      if (e != cudaSuccess) return (int)e;
+      prof_tick(K_MEMOPS, st);
+    }
+    if (score_x && ctx->has_x) {
+      e = cudaMemsetAsync(score_x, 0, sizeof(float) * (size_t)B * N * F, st);
+      if (e != cudaSuccess) return (int)e;
+      prof_tick(K_MEMOPS, st);
+    }
+    return launch_eval_fused(ctx, x, adj, flags, neff, score_x, score_adj, B, ws, w, st);
+  }
   if (score_adj && ctx->has_a) {
     e = cudaMemsetAsync(score_adj, 0, sizeof(float) * (size_t)B * N * N, st);
     if (e != cudaSuccess) return (int)e;
@@ -1030,6 +1063,6 @@ extern "C" int gdss_prof_end(float* ms, int64_t* counts, int32_t n) {
 extern "C" const char* gdss_prof_name(int32_t kid) {
   static const char* names[gdss::K_COUNT] = {"neff_kernel", "pow_kernel", "deg_kernel", "gcn_kernel", "edge_kernel", "node_kernel",
                                              "final_edge_kernel", "final_node_kernel", "copy_x_kernel", "norms_kernel",
-                                             "sums_kernel", "update_kernel", "misc", "memset/memcpy"};
+                                             "sums_kernel", "update_kernel", "misc", "memset/memcpy", "fused_layers_kernel"};
   return kid >= 0 && kid < gdss::K_COUNT ? names[kid] : "?";
 }

@@ -439,15 +439,17 @@ extern "C" int gdss_sample(gdss_ctx* ctx, const gdss_sampler_desc* s, const gdss
   set_step_kernel<<<1, 1, 0, st>>>(p.step_ptr, first_step);
   launched(K_MISC, st);
   LAUNCH_CHECK();
-  int rc = launch_neff(flags, neff, B, N, 1, st);
+  if ((int64_t)B * (N * (N - 1) / 2) >= (int64_t)1 << 30 || B >= (1 << 19)) return GDSS_E_UNSUPPORTED;
+  int rc = launch_setup(ctx, flags, B, 1, ws, w, st);
   if (rc) return rc;
   if (init_prior) {
     prior_kernel<<<B, 256, 0, st>>>(u.ns, x, adj, flags);
     launched(K_MISC, st);
     LAUNCH_CHECK();
   }
-  if (first_step == 0 || init_prior) {
-    // the means start as the state (solver.py returns x_mean of the last step; defined even for 0 steps)
+  {
+    // the means start as the state (solver.py returns x_mean of the last step; defined even for 0 steps),
+    // which also defines the rows / columns of padded nodes that the update kernels never touch
     e = cudaMemcpyAsync(x_mean, x, sizeof(float) * (size_t)B * N * F, cudaMemcpyDeviceToDevice, st);
     if (e != cudaSuccess) return (int)e;
     e = cudaMemcpyAsync(adj_mean, adj, sizeof(float) * (size_t)B * N * N, cudaMemcpyDeviceToDevice, st);
