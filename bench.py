@@ -313,7 +313,7 @@ def main():
         cnt = (C.c_int64 * 16)()
         _lib.check(L.gdss_prof_end(msb, cnt, 16), "gdss_prof_end")
         kernel_ms = {L.gdss_prof_name(i).decode(): {"ms_per_step": msb[i] / 2, "launches_per_step": cnt[i] / 2}
-                     for i in range(14) if cnt[i]}
+                     for i in range(15) if cnt[i]}
         tot = sum(v["ms_per_step"] for v in kernel_ms.values())
         for v in kernel_ms.values():
             v["share"] = v["ms_per_step"] / tot

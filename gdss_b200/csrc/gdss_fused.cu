@@ -31,36 +31,54 @@ DEVINL float tanh_fast(float v) {      // no clamp needed: ex2 -> inf gives 1, -
 // ---------------------------------------------------------------------------------------
 // pixel bookkeeping (depends on the flags only: once per sampler call)
 // ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024) tri_scan_kernel(const int* __restrict__ neff, int B, int* __restrict__ poff,
-                                                        int* __restrict__ meta, int* __restrict__ gmap) {
+// meta: [0] total pixels, [1] 128-pixel tiles, [2..4] graphs per size bucket, [5..7] first slot of each bucket in order[]
+__global__ void __launch_bounds__(1024) tri_scan_kernel(const int* __restrict__ neff, int B, int nb0, int nb1,
+                                                        int* __restrict__ poff, int* __restrict__ meta,
+                                                        int* __restrict__ gmap, int* __restrict__ order) {
   __shared__ int part[1024];
+  __shared__ int tot_s[4];
   const int t = threadIdx.x;
   const int chunk = (B + 1023) / 1024;
   const int lo = min(B, t * chunk), hi = min(B, lo + chunk);
-  int s = 0;
+  int s = 0, cnt[3] = {0, 0, 0};
   for (int b = lo; b < hi; ++b) {
-    int n = neff[b];
+    const int n = neff[b];
     s += n * (n - 1) / 2;
+    cnt[n <= nb0 ? 0 : (n <= nb1 ? 1 : 2)]++;
   }
-  part[t] = s;
-  __syncthreads();
-  for (int off = 1; off < 1024; off <<= 1) {
-    int v = t >= off ? part[t - off] : 0;
+  int excl[4];
+  for (int q = 0; q < 4; ++q) {
+    const int v0 = q == 0 ? s : cnt[q - 1];
+    part[t] = v0;
     __syncthreads();
-    part[t] += v;
+    for (int off = 1; off < 1024; off <<= 1) {
+      int v = t >= off ? part[t - off] : 0;
+      __syncthreads();
+      part[t] += v;
+      __syncthreads();
+    }
+    excl[q] = part[t] - v0;
+    if (t == 1023) tot_s[q] = part[1023];
     __syncthreads();
   }
-  int base = part[t] - s;
+  const int start[3] = {0, tot_s[1], tot_s[1] + tot_s[2]};
+  int base = excl[0];
+  int pos[3] = {start[0] + excl[1], start[1] + excl[2], start[2] + excl[3]};
   for (int b = lo; b < hi; ++b) {
     poff[b] = base;
-    int n = neff[b];
+    const int n = neff[b];
     base += n * (n - 1) / 2;
+    order[pos[n <= nb0 ? 0 : (n <= nb1 ? 1 : 2)]++] = b;
   }
   if (t == 1023) {
-    const int tot = part[1023];
+    const int tot = tot_s[0];
     poff[B] = tot;
     meta[0] = tot;
     meta[1] = (tot + 127) / 128;
+    for (int q = 0; q < 3; ++q) {
+      meta[2 + q] = tot_s[1 + q];
+      meta[5 + q] = start[q];
+    }
     for (int k = tot; k < ((tot + 127) / 128) * 128; ++k) gmap[k] = -1;
   }
 }
@@ -81,12 +99,12 @@ __global__ void __launch_bounds__(64) tri_map_kernel(const int* __restrict__ nef
 #define RMAX 8                 // rows per register-blocked item
 
 struct FLayer {
-  int c_in, c_out, f_in, attn, nlin, qkvw, need_edge, need_node;
+  int c_in, c_out, f_in, f_in_p, attn, nlin, qkvw, need_edge, need_node;
   const float *wqkv, *bqkv, *ew[3], *eb[3], *nw0, *nb0, *nw1, *nb1;
 };
 
 struct FNet {
-  int type, depth, F, nhid, heads, fdim, fout, c_init;
+  int type, depth, F, nhid, heads, fdim, fout, c_init, Hp, foutp;
   FLayer L[FUSED_MAX_LAYERS];
   const float* gw[FUSED_MAX_LAYERS];
   const float* gb[FUSED_MAX_LAYERS];
@@ -95,7 +113,7 @@ struct FNet {
 
 // float offsets into dynamic shared memory
 struct FSmem {
-  int fl, dinv, pix, x0, xb, xc, xs, h1, wts, p0, pa, r1, qk, r2, total;
+  int fl, dinv, pix, x0, xb, xs, h1, wts, p0, pa, r1, qk, r2, total;
   int LD, XS, QKS, PM, NBP, XSS;
 };
 
@@ -107,157 +125,182 @@ struct FusedArgs {
   float* raw_x;
   float* stackT;
   const int* poff;
+  const int* order;        // graph ids sorted by size bucket
+  const int* meta;
+  int bucket;
   int64_t pstride;
   int N, F;
   FSmem sl;
 };
 
 // ---------------------------------------------------------------------------------------
-// mm_rows: out[c][i][o] = act( (bias[c][o] + sum_k in[c][i][k] * W[c][k][o]) * rowscale[i] )
-// Register-blocked: one item = 4 consecutive output columns x up to RMAX rows; the 4x4 weight block of a
-// k-chunk is loaded once (global, L2-resident) and reused over the rows, the input rows come from shared
-// memory as float4.  `in` rows must be readable (and finite) up to K rounded up to 4.
-// Output columns < split go to out0, the others to out1 (column index minus split).
+// small helpers
 // ---------------------------------------------------------------------------------------
+// exact x / d for 0 <= x < 2^16, 1 <= d < 2^16 (one IMAD.HI instead of an integer division)
+struct FastDiv {
+  unsigned m;
+  int d;
+  DEVINL explicit FastDiv(int dd) : m(dd > 1 ? (0xFFFFFFFFu / (unsigned)dd + 1u) : 0u), d(dd) {}
+  DEVINL int div(int x) const { return d > 1 ? (int)__umulhi((unsigned)x, m) : x; }
+};
+
 enum { ACT_NONE = 0, ACT_ELU = 1, ACT_TANH = 2, ACT_TANH2 = 3 };
 
-template <int ACT>
-DEVINL void mm_rows(const float* in, int in_cs, int ldin, int K, const float* __restrict__ W, int w_cs, int ldw,
-                    const float* __restrict__ bias, int b_cs, int C, int n, int o_lo, int o_hi, int OUTN, float* out0,
-                    int o0_cs, int ld0, int split, float* out1, int o1_cs, int ld1, const float* rowscale) {
+// ---------------------------------------------------------------------------------------
+// mm_rows: out[c][i][o] = act( (bias[c][o] + sum_k in[c][i][k] * W[c][k][o]) * rowscale[i] )
+// Register-blocked: one item = 4 consecutive output columns x up to RMAX rows; the 4x4 weight block of a
+// k-chunk is loaded once (global; L1/L2-resident, shared by every CTA) and reused over the rows, the input
+// rows come from shared memory as float4.  `in` rows must be readable (and finite) up to K rounded up to 4.
+// Output columns < split go to out0, the others to out1 (column index minus split).  One out-of-line
+// instance (instruction-cache footprint), the activation is a run-time switch in the epilogue.
+// ---------------------------------------------------------------------------------------
+struct MM {
+  const float* in; int in_cs, ldin, K;       // K rounded up to 4 by the caller: W rows [K_true, K) are zero in the blob
+  const float* W; int w_cs, ldw;
+  const float* bias; int b_cs;
+  int C, n, o_lo, o_hi;
+  float* out0; int o0_cs, ld0, split;
+  float* out1; int o1_cs, ld1;
+  const float* rowscale;
+  int act, vec_out;
+};
+
+__device__ __noinline__ void mm_rows(const MM& m) {
   const int tid = threadIdx.x, nt = blockDim.x;
-  const int ogn = (o_hi - o_lo + 3) >> 2;
-  const int pairs = C * ogn;
+  const int n = m.n, K4 = m.K, ldw = m.ldw, ldin = m.ldin;
+  const int ogn = (m.o_hi - m.o_lo + 3) >> 2;
+  const int pairs = m.C * ogn;
   if (pairs <= 0 || n <= 0) return;
-  // rows are dealt round-robin to IP row-partitions; pick IP to minimise (rounds x rows per item)
-  int IP = (n + RMAX - 1) / RMAX, best = 1 << 30;
-  for (int rows = RMAX; rows >= 1; --rows) {
-    const int ip = (n + rows - 1) / rows;
-    const int rounds = (pairs * ip + nt - 1) / nt;
-    const int cost = rounds * (rows * 5 + 4);      // ~ weight loads + rows * (lds + 16 fma)
-    if (cost < best) { best = cost; IP = ip; }
+  // rows are dealt round-robin to IP row-partitions: RMAX rows per item when that already fills the CTA,
+  // otherwise as many partitions as fit in one round
+  int IP = (n + RMAX - 1) / RMAX;
+  if (pairs * IP < nt) {
+    int ip = nt / pairs;
+    if (ip > n) ip = n;
+    if (ip > IP) IP = ip;
   }
-  const int K4 = (K + 3) & ~3;
-  const bool vecw = ((ldw & 3) == 0);
+  const FastDiv dpairs(pairs), dogn(ogn);
   for (int item = tid; item < pairs * IP; item += nt) {
-    const int ip = item / pairs, pr = item - ip * pairs;
-    const int c = pr / ogn, og = pr - c * ogn;
-    const int o = o_lo + 4 * og;
-    const float* Wc = W + (int64_t)c * w_cs;
-    const float* inc = in + c * in_cs;
+    const int ip = dpairs.div(item), pr = item - ip * pairs;
+    const int c = dogn.div(pr), og = pr - c * ogn;
+    const int o = m.o_lo + 4 * og;
+    const float* Wc = m.W + (int64_t)c * m.w_cs + o;
+    const float* inc = m.in + c * m.in_cs + ip * ldin;
     const int rcnt = (n - ip + IP - 1) / IP;       // rows of this item: ip, ip + IP, ...
+    const int rstep = IP * ldin;
     float acc[RMAX][4];
     {
-      float bv[4];
+      const float4 bv = __ldg(reinterpret_cast<const float4*>(m.bias + c * m.b_cs + o));
 #pragma unroll
-      for (int q = 0; q < 4; ++q) bv[q] = (o + q < OUTN) ? __ldg(bias + c * b_cs + o + q) : 0.f;
-#pragma unroll
-      for (int r = 0; r < RMAX; ++r)
-#pragma unroll
-        for (int q = 0; q < 4; ++q) acc[r][q] = bv[q];
+      for (int r = 0; r < RMAX; ++r) { acc[r][0] = bv.x; acc[r][1] = bv.y; acc[r][2] = bv.z; acc[r][3] = bv.w; }
     }
+    float4 wn[4];
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) wn[kk] = __ldg(reinterpret_cast<const float4*>(Wc + (int64_t)kk * ldw));
     for (int k0 = 0; k0 < K4; k0 += 4) {
-      float w[4][4];
+      const float4 w0 = wn[0], w1 = wn[1], w2 = wn[2], w3 = wn[3];
+      if (k0 + 4 < K4) {                             // prefetch the next weight block (L2 latency)
 #pragma unroll
-      for (int kk = 0; kk < 4; ++kk) {
-        const int k = k0 + kk;
-        if (k < K) {
-          if (vecw && o + 3 < OUTN) {
-            const float4 t = __ldg(reinterpret_cast<const float4*>(Wc + (int64_t)k * ldw + o));
-            w[kk][0] = t.x; w[kk][1] = t.y; w[kk][2] = t.z; w[kk][3] = t.w;
-          } else {
-#pragma unroll
-            for (int q = 0; q < 4; ++q) w[kk][q] = (o + q < OUTN) ? __ldg(Wc + (int64_t)k * ldw + o + q) : 0.f;
-          }
-        } else {
-#pragma unroll
-          for (int q = 0; q < 4; ++q) w[kk][q] = 0.f;
-        }
+        for (int kk = 0; kk < 4; ++kk) wn[kk] = __ldg(reinterpret_cast<const float4*>(Wc + (int64_t)(k0 + 4 + kk) * ldw));
       }
 #pragma unroll
       for (int r = 0; r < RMAX; ++r) {
         if (r >= rcnt) break;
-        const int i = ip + r * IP;
-        const float4 a = *reinterpret_cast<const float4*>(inc + i * ldin + k0);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          acc[r][q] = fmaf(a.x, w[0][q], acc[r][q]);
-          acc[r][q] = fmaf(a.y, w[1][q], acc[r][q]);
-          acc[r][q] = fmaf(a.z, w[2][q], acc[r][q]);
-          acc[r][q] = fmaf(a.w, w[3][q], acc[r][q]);
-        }
+        const float4 a = *reinterpret_cast<const float4*>(inc + r * rstep + k0);
+        acc[r][0] = fmaf(a.x, w0.x, acc[r][0]); acc[r][1] = fmaf(a.x, w0.y, acc[r][1]); acc[r][2] = fmaf(a.x, w0.z, acc[r][2]); acc[r][3] = fmaf(a.x, w0.w, acc[r][3]);
+        acc[r][0] = fmaf(a.y, w1.x, acc[r][0]); acc[r][1] = fmaf(a.y, w1.y, acc[r][1]); acc[r][2] = fmaf(a.y, w1.z, acc[r][2]); acc[r][3] = fmaf(a.y, w1.w, acc[r][3]);
+        acc[r][0] = fmaf(a.z, w2.x, acc[r][0]); acc[r][1] = fmaf(a.z, w2.y, acc[r][1]); acc[r][2] = fmaf(a.z, w2.z, acc[r][2]); acc[r][3] = fmaf(a.z, w2.w, acc[r][3]);
+        acc[r][0] = fmaf(a.w, w3.x, acc[r][0]); acc[r][1] = fmaf(a.w, w3.y, acc[r][1]); acc[r][2] = fmaf(a.w, w3.z, acc[r][2]); acc[r][3] = fmaf(a.w, w3.w, acc[r][3]);
       }
     }
+    const int act = m.act;
+    const bool to0 = o < m.split;
+    float* ob = to0 ? m.out0 + c * m.o0_cs + o : m.out1 + c * m.o1_cs + (o - m.split);
+    const int ldo = to0 ? m.ld0 : m.ld1;
+    const bool vec = m.vec_out && (o + 3 < m.o_hi);
 #pragma unroll
     for (int r = 0; r < RMAX; ++r) {
+      if (r >= rcnt) break;
       const int i = ip + r * IP;
-      if (i >= n) continue;
-      const float rs = rowscale ? rowscale[i] : 1.f;
+      const float rs = m.rowscale ? m.rowscale[i] : 1.f;
+      float v[4];
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
-        const int oc = o + q;
-        if (oc >= o_hi) continue;                 // columns in [OUTN, o_hi) are padding: exactly act(0) = 0
-        float v = acc[r][q] * rs;
-        if (ACT == ACT_ELU) v = elu_f(v);
-        if (ACT == ACT_TANH) v = tanh_fast(v);
-        if (ACT == ACT_TANH2) v = tanh_fast(tanh_fast(v));
-        if (oc < split) out0[c * o0_cs + i * ld0 + oc] = v;
-        else out1[c * o1_cs + i * ld1 + (oc - split)] = v;
+        v[q] = acc[r][q] * rs;
+        if (act == ACT_ELU) v[q] = elu_f(v[q]);
+        else if (act >= ACT_TANH) {
+          v[q] = tanh_fast(v[q]);
+          if (act == ACT_TANH2) v[q] = tanh_fast(v[q]);
+        }
+      }
+      if (vec) {
+        *reinterpret_cast<float4*>(ob + i * ldo) = make_float4(v[0], v[1], v[2], v[3]);
+      } else {
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          if (o + q < m.o_hi) ob[i * ldo + q] = v[q];
       }
     }
   }
 }
 
-DEVINL int tri_index(int i, int j, int n) {      // i != j
-  const int lo = min(i, j), hi = max(i, j);
-  return lo * (2 * n - lo - 1) / 2 + hi - lo - 1;
-}
-
-// dense normalised adjacency of C tri planes: D^-1/2 (P with unit diagonal) D^-1/2   (layers.py:72-79)
-DEVINL void build_norm_adj(const float* pin, int PM, int C, int n, int LD, int NBP, float* dense, float* dinv) {
+// ---------------------------------------------------------------------------------------
+// DenseGCNConv pieces (layers.py:49-88) straight from the strict-upper-triangle planes.
+// Row i of plane c is walked in increasing j: entries (j, i) for j < i (index step n-j-2), then the
+// contiguous run (i, j) for j > i.  The self loop (diagonal := 1) is added explicitly.
+// ---------------------------------------------------------------------------------------
+DEVINL void gcn_degrees(const float* pin, int PM, int C, int n, int NBP, float* dinv, const FastDiv& dn) {
   const int tid = threadIdx.x, nt = blockDim.x;
-  const int nn = n * n;
-  for (int idx = tid; idx < C * nn; idx += nt) {
-    const int c = idx / nn, r = idx - c * nn;
-    const int i = r / n, j = r - i * n;
-    dense[c * n * LD + i * LD + j] = (i == j) ? 1.f : pin[c * PM + tri_index(i, j, n)];
-  }
-  __syncthreads();
-  for (int idx = tid; idx < C * n; idx += nt) {
-    const int c = idx / n, i = idx - c * n;
-    const float* row = dense + c * n * LD + i * LD;
-    float s = 0.f;
-    for (int j = 0; j < n; ++j) s += row[j];
+  for (int item = tid; item < C * n; item += nt) {
+    const int c = dn.div(item), i = item - c * n;
+    const float* pl = pin + c * PM;
+    float s = 1.f;
+    int idx = i - 1;
+    for (int j = 0; j < i; ++j) {
+      s += pl[idx];
+      idx += n - j - 2;
+    }
+    idx = i * (2 * n - i - 1) / 2;
+    for (int j = i + 1; j < n; ++j) s += pl[idx++];
     dinv[c * NBP + i] = 1.0f / sqrtf(fmaxf(s, 1.0f));
   }
-  __syncthreads();
-  for (int idx = tid; idx < C * nn; idx += nt) {
-    const int c = idx / nn, r = idx - c * nn;
-    const int i = r / n, j = r - i * n;
-    float* e = dense + c * n * LD + i * LD + j;
-    *e = (dinv[c * NBP + i] * *e) * dinv[c * NBP + j];
-  }
-  __syncthreads();
 }
 
-// AX[c][i][0..fp) = sum_j dense[c][i][j] * x[j][0..fp)     (x rows zero-padded to fp = f rounded up to 4)
-DEVINL void adj_times_x(const float* dense, int LD, const float* x, int ldx, int C, int n, int fp, float* ax) {
+// ax[c][i][8g..8g+7] = d_i * sum_j A~_c(i,j) d_j x[j][8g..8g+7]
+DEVINL void gcn_ax(const float* pin, int PM, const float* dinv, int NBP, const float* x, int ldx, int C, int n, int f8,
+                   int ldax, float* ax, const FastDiv& dn) {
   const int tid = threadIdx.x, nt = blockDim.x;
-  const int fg = fp >> 2;
-  for (int item = tid; item < C * n * fg; item += nt) {
-    const int g = item % fg, ci = item / fg;
-    const int c = ci / n, i = ci - c * n;
-    const float* row = dense + c * n * LD + i * LD;
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int j = 0; j < n; ++j) {
-      const float a = row[j];
-      const float4 xv = *reinterpret_cast<const float4*>(x + j * ldx + 4 * g);
-      acc.x = fmaf(a, xv.x, acc.x);
-      acc.y = fmaf(a, xv.y, acc.y);
-      acc.z = fmaf(a, xv.z, acc.z);
-      acc.w = fmaf(a, xv.w, acc.w);
+  const FastDiv df(f8);
+  for (int item = tid; item < C * n * f8; item += nt) {
+    const int ci = df.div(item), g = item - ci * f8;
+    const int c = dn.div(ci), i = ci - c * n;
+    const float* pl = pin + c * PM;
+    const float* dv = dinv + c * NBP;
+    const float* xg = x + 8 * g;
+    const float di = dv[i];
+    float acc[8];
+    {
+      const float4 a = *reinterpret_cast<const float4*>(xg + i * ldx);
+      const float4 b = *reinterpret_cast<const float4*>(xg + i * ldx + 4);
+      acc[0] = di * a.x; acc[1] = di * a.y; acc[2] = di * a.z; acc[3] = di * a.w;
+      acc[4] = di * b.x; acc[5] = di * b.y; acc[6] = di * b.z; acc[7] = di * b.w;
     }
-    *reinterpret_cast<float4*>(ax + (c * n + i) * fp + 4 * g) = acc;
+    int idx = i - 1;
+    for (int j = 0; j < n; ++j) {
+      if (j == i) {
+        idx = i * (2 * n - i - 1) / 2;
+        continue;
+      }
+      const float w = pl[idx] * dv[j];
+      idx += j < i ? n - j - 2 : 1;
+      const float4 a = *reinterpret_cast<const float4*>(xg + j * ldx);
+      const float4 b = *reinterpret_cast<const float4*>(xg + j * ldx + 4);
+      acc[0] = fmaf(w, a.x, acc[0]); acc[1] = fmaf(w, a.y, acc[1]); acc[2] = fmaf(w, a.z, acc[2]); acc[3] = fmaf(w, a.w, acc[3]);
+      acc[4] = fmaf(w, b.x, acc[4]); acc[5] = fmaf(w, b.y, acc[5]); acc[6] = fmaf(w, b.z, acc[6]); acc[7] = fmaf(w, b.w, acc[7]);
+    }
+    float* o = ax + (c * n + i) * ldax + 8 * g;
+    *reinterpret_cast<float4*>(o) = make_float4(acc[0] * di, acc[1] * di, acc[2] * di, acc[3] * di);
+    *reinterpret_cast<float4*>(o + 4) = make_float4(acc[4] * di, acc[5] * di, acc[6] * di, acc[7] * di);
   }
 }
 
@@ -287,35 +330,73 @@ DEVINL void stage_edge_weights(const FLayer& L, float* w) {
   for (int idx = tid; idx < 8; idx += nt) w[cur + idx] = idx < L.c_out ? __ldg(bl + idx) : 0.f;
 }
 
-// attention maps (attention.py:35-49): M[c][p] = mean over heads and over the two orientations of
-// tanh(Q_h . K_h / sqrt(out_dim))
-DEVINL void attention_maps(const float* qk, int QKS, const unsigned* pix, int C, int n, int P, int PM, int attn,
-                           int heads, float scale, float* M) {
+// first linear of `multi_channel` (attention.py:90, :106): h1[i][0..16) = elu(b + cat_c V_c[i] . W), the K
+// range split over 4 adjacent lanes and reduced with shuffles (the layer has only n x 4 column groups)
+DEVINL void node_l1(const float* V, int K, const float* __restrict__ W, const float* __restrict__ b, int n, float* h1) {
+  const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31;
+  const int total = n * 16, kq = K >> 2;
+  for (int base = tid - lane; base < total; base += nt) {
+    const int idx = base + lane;
+    const bool valid = idx < total;
+    const int id2 = valid ? idx : total - 1;
+    const int i = id2 >> 4, og = (id2 >> 2) & 3, kp = id2 & 3;
+    const float* vr = V + i * K + kp * kq;
+    const float* wr = W + (int64_t)(kp * kq) * 16 + 4 * og;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int k = 0; k < kq; k += 4) {
+      const float4 v = *reinterpret_cast<const float4*>(vr + k);
+      const float4 w0 = __ldg(reinterpret_cast<const float4*>(wr + (k + 0) * 16));
+      const float4 w1 = __ldg(reinterpret_cast<const float4*>(wr + (k + 1) * 16));
+      const float4 w2 = __ldg(reinterpret_cast<const float4*>(wr + (k + 2) * 16));
+      const float4 w3 = __ldg(reinterpret_cast<const float4*>(wr + (k + 3) * 16));
+      acc.x = fmaf(v.x, w0.x, acc.x); acc.y = fmaf(v.x, w0.y, acc.y); acc.z = fmaf(v.x, w0.z, acc.z); acc.w = fmaf(v.x, w0.w, acc.w);
+      acc.x = fmaf(v.y, w1.x, acc.x); acc.y = fmaf(v.y, w1.y, acc.y); acc.z = fmaf(v.y, w1.z, acc.z); acc.w = fmaf(v.y, w1.w, acc.w);
+      acc.x = fmaf(v.z, w2.x, acc.x); acc.y = fmaf(v.z, w2.y, acc.y); acc.z = fmaf(v.z, w2.z, acc.z); acc.w = fmaf(v.z, w2.w, acc.w);
+      acc.x = fmaf(v.w, w3.x, acc.x); acc.y = fmaf(v.w, w3.y, acc.y); acc.z = fmaf(v.w, w3.z, acc.z); acc.w = fmaf(v.w, w3.w, acc.w);
+    }
+#pragma unroll
+    for (int o = 1; o <= 2; o <<= 1) {
+      acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o);
+      acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
+      acc.z += __shfl_xor_sync(0xffffffffu, acc.z, o);
+      acc.w += __shfl_xor_sync(0xffffffffu, acc.w, o);
+    }
+    if (valid && kp == 0) {
+      const float4 bv = __ldg(reinterpret_cast<const float4*>(b + 4 * og));
+      *reinterpret_cast<float4*>(h1 + i * 16 + 4 * og) =
+          make_float4(elu_f(acc.x + bv.x), elu_f(acc.y + bv.y), elu_f(acc.z + bv.z), elu_f(acc.w + bv.w));
+    }
+  }
+}
+
+// attention maps (attention.py:35-49): M[c][p] = mean over the 4 heads and over the two orientations of
+// tanh(Q_h . K_h / sqrt(out_dim)); HD = head width (attn_dim / 4)
+template <int HD>
+DEVINL void attention_maps(const float* qk, int QKS, const unsigned* pix, int C, int n, int P, int PM, float scale, float* M, const FastDiv& dP) {
   const int tid = threadIdx.x, nt = blockDim.x;
-  const int hd = attn / heads;
-  const float ms = 0.5f / (float)heads;
+  constexpr int AT = 4 * HD;
   for (int item = tid; item < C * P; item += nt) {
-    const int c = item / P, p = item - c * P;
+    const int c = dP.div(item), p = item - c * P;
     const unsigned ij = pix[p];
     const int i = ij >> 8, j = ij & 255;
     const float* qi = qk + (c * n + i) * QKS;
     const float* qj = qk + (c * n + j) * QKS;
-    const float* ki = qi + attn;
-    const float* kj = qj + attn;
     float m = 0.f;
-    for (int h = 0; h < heads; ++h) {
+#pragma unroll
+    for (int h = 0; h < 4; ++h) {
       float s1 = 0.f, s2 = 0.f;
-      for (int d = 0; d < hd; d += 4) {
-        const float4 a1 = *reinterpret_cast<const float4*>(qi + h * hd + d);
-        const float4 b1 = *reinterpret_cast<const float4*>(kj + h * hd + d);
-        const float4 a2 = *reinterpret_cast<const float4*>(qj + h * hd + d);
-        const float4 b2 = *reinterpret_cast<const float4*>(ki + h * hd + d);
+#pragma unroll
+      for (int d = 0; d < HD; d += 4) {
+        const float4 a1 = *reinterpret_cast<const float4*>(qi + h * HD + d);
+        const float4 b1 = *reinterpret_cast<const float4*>(qj + AT + h * HD + d);
+        const float4 a2 = *reinterpret_cast<const float4*>(qj + h * HD + d);
+        const float4 b2 = *reinterpret_cast<const float4*>(qi + AT + h * HD + d);
         s1 = fmaf(a1.x, b1.x, s1); s1 = fmaf(a1.y, b1.y, s1); s1 = fmaf(a1.z, b1.z, s1); s1 = fmaf(a1.w, b1.w, s1);
         s2 = fmaf(a2.x, b2.x, s2); s2 = fmaf(a2.y, b2.y, s2); s2 = fmaf(a2.z, b2.z, s2); s2 = fmaf(a2.w, b2.w, s2);
       }
       m += tanh_fast(s1 * scale) + tanh_fast(s2 * scale);
     }
-    M[c * PM + p] = m * ms;
+    M[c * PM + p] = m * 0.125f;
   }
 }
 
@@ -328,12 +409,12 @@ DEVINL void edge_mlp(const float* M, const float* pin, int PM, const unsigned* p
   const int tid = threadIdx.x, nt = blockDim.x;
   const int sub = tid & 1;
   const int in1 = 2 * C;
-  const float* W1 = w;
-  const float* b1 = W1 + in1 * 16;
-  const float* W2 = b1 + 16;
-  const float* b2 = W2 + 256;
-  const float* W3 = NLIN == 3 ? b2 + 16 : b1 + 16;
-  const float* b3 = W3 + 128;
+  const float* W1 = w + 8 * sub;
+  const float* b1 = w + in1 * 16;
+  const float* W2 = b1 + 16 + 8 * sub;
+  const float* b2 = b1 + 16 + 256;
+  const float* W3 = (NLIN == 3 ? b2 + 16 : b1 + 16) + 4 * sub;
+  const float* b3 = (NLIN == 3 ? b2 + 16 : b1 + 16) + 128;
   const int total = 2 * P;
   for (int base = tid - (tid & 31); base < total; base += nt) {       // warp-uniform trip count
     const int idx = base + (tid & 31);
@@ -345,10 +426,17 @@ DEVINL void edge_mlp(const float* M, const float* pin, int PM, const unsigned* p
       const float4 bb = *reinterpret_cast<const float4*>(b1 + 8 * sub + 4);
       h[0] = ba.x; h[1] = ba.y; h[2] = ba.z; h[3] = ba.w; h[4] = bb.x; h[5] = bb.y; h[6] = bb.z; h[7] = bb.w;
     }
-    for (int k = 0; k < in1; ++k) {
-      const float v = k < C ? M[k * PM + p] : pin[(k - C) * PM + p];
-      const float4 wa = *reinterpret_cast<const float4*>(W1 + k * 16 + 8 * sub);
-      const float4 wb = *reinterpret_cast<const float4*>(W1 + k * 16 + 8 * sub + 4);
+    for (int k = 0; k < C; ++k) {
+      const float v = M[k * PM + p];
+      const float4 wa = *reinterpret_cast<const float4*>(W1 + k * 16);
+      const float4 wb = *reinterpret_cast<const float4*>(W1 + k * 16 + 4);
+      h[0] = fmaf(v, wa.x, h[0]); h[1] = fmaf(v, wa.y, h[1]); h[2] = fmaf(v, wa.z, h[2]); h[3] = fmaf(v, wa.w, h[3]);
+      h[4] = fmaf(v, wb.x, h[4]); h[5] = fmaf(v, wb.y, h[5]); h[6] = fmaf(v, wb.z, h[6]); h[7] = fmaf(v, wb.w, h[7]);
+    }
+    for (int k = 0; k < C; ++k) {
+      const float v = pin[k * PM + p];
+      const float4 wa = *reinterpret_cast<const float4*>(W1 + (C + k) * 16);
+      const float4 wb = *reinterpret_cast<const float4*>(W1 + (C + k) * 16 + 4);
       h[0] = fmaf(v, wa.x, h[0]); h[1] = fmaf(v, wa.y, h[1]); h[2] = fmaf(v, wa.z, h[2]); h[3] = fmaf(v, wa.w, h[3]);
       h[4] = fmaf(v, wb.x, h[4]); h[5] = fmaf(v, wb.y, h[5]); h[6] = fmaf(v, wb.z, h[6]); h[7] = fmaf(v, wb.w, h[7]);
     }
@@ -368,8 +456,8 @@ DEVINL void edge_mlp(const float* M, const float* pin, int PM, const unsigned* p
 #pragma unroll
       for (int u = 0; u < 16; ++u) {
         const float v = hf[u];
-        const float4 wa = *reinterpret_cast<const float4*>(W2 + u * 16 + 8 * sub);
-        const float4 wb = *reinterpret_cast<const float4*>(W2 + u * 16 + 8 * sub + 4);
+        const float4 wa = *reinterpret_cast<const float4*>(W2 + u * 16);
+        const float4 wb = *reinterpret_cast<const float4*>(W2 + u * 16 + 4);
         h[0] = fmaf(v, wa.x, h[0]); h[1] = fmaf(v, wa.y, h[1]); h[2] = fmaf(v, wa.z, h[2]); h[3] = fmaf(v, wa.w, h[3]);
         h[4] = fmaf(v, wb.x, h[4]); h[5] = fmaf(v, wb.y, h[5]); h[6] = fmaf(v, wb.z, h[6]); h[7] = fmaf(v, wb.w, h[7]);
       }
@@ -385,7 +473,7 @@ DEVINL void edge_mlp(const float* M, const float* pin, int PM, const unsigned* p
 #pragma unroll
     for (int u = 0; u < 16; ++u) {
       const float v = hf[u];
-      const float4 wv = *reinterpret_cast<const float4*>(W3 + u * 8 + 4 * sub);
+      const float4 wv = *reinterpret_cast<const float4*>(W3 + u * 8);
       o4.x = fmaf(v, wv.x, o4.x); o4.y = fmaf(v, wv.y, o4.y); o4.z = fmaf(v, wv.z, o4.z); o4.w = fmaf(v, wv.w, o4.w);
     }
     if (valid) {
@@ -404,26 +492,37 @@ DEVINL void edge_mlp(const float* M, const float* pin, int PM, const unsigned* p
   }
 }
 
+DEVINL MM mm_make(const float* in, int in_cs, int ldin, int K, const float* W, int w_cs, int ldw, const float* bias, int b_cs,
+                  int C, int n, int o_lo, int o_hi, float* out0, int o0_cs, int ld0, int split, float* out1, int o1_cs,
+                  int ld1, const float* rowscale, int act, int vec_out = 1) {
+  MM m;
+  m.in = in; m.in_cs = in_cs; m.ldin = ldin; m.K = (K + 3) & ~3; m.W = W; m.w_cs = w_cs; m.ldw = ldw; m.bias = bias; m.b_cs = b_cs;
+  m.C = C; m.n = n; m.o_lo = o_lo; m.o_hi = o_hi; m.out0 = out0; m.o0_cs = o0_cs; m.ld0 = ld0; m.split = split;
+  m.out1 = out1; m.o1_cs = o1_cs; m.ld1 = ld1; m.rowscale = rowscale; m.act = act; m.vec_out = vec_out;
+  return m;
+}
+
 // final node MLP of the X networks (ScoreNetwork_X.py:40-44, :84-87): xs [n][fdim] -> 2f -> 2f -> F, ELU, mask_x
 DEVINL void final_node_mlp(const FNet& net, const float* xs, int XSS, int n, const float* fl, float* hA, float* hB,
                            float* out_g, int F) {
-  const int H = 2 * net.fdim, HP = (H + 3) & ~3;
-  mm_rows<ACT_ELU>(xs, 0, XSS, net.fdim, net.fw[0], 0, H, net.fb[0], 0, 1, n, 0, HP, H, hA, 0, HP, HP, nullptr, 0, 0, nullptr);
+  const int HP = net.Hp;
+  mm_rows(mm_make(xs, 0, XSS, net.fdim, net.fw[0], 0, HP, net.fb[0], 0, 1, n, 0, HP, hA, 0, HP, HP, nullptr, 0, 0, nullptr, ACT_ELU));
   __syncthreads();
-  mm_rows<ACT_ELU>(hA, 0, HP, H, net.fw[1], 0, H, net.fb[1], 0, 1, n, 0, HP, H, hB, 0, HP, HP, nullptr, 0, 0, nullptr);
+  mm_rows(mm_make(hA, 0, HP, HP, net.fw[1], 0, HP, net.fb[1], 0, 1, n, 0, HP, hB, 0, HP, HP, nullptr, 0, 0, nullptr, ACT_ELU));
   __syncthreads();
-  // the F-wide result goes straight to global memory (row stride F)
-  mm_rows<ACT_NONE>(hB, 0, HP, H, net.fw[2], 0, net.fout, net.fb[2], 0, 1, n, 0, net.fout, net.fout, out_g, 0, F, net.fout,
-                    nullptr, 0, 0, fl);
+  // the F-wide result goes straight to global memory (row stride F: scalar stores)
+  mm_rows(mm_make(hB, 0, HP, HP, net.fw[2], 0, net.foutp, net.fb[2], 0, 1, n, 0, net.fout, out_g, 0, F, net.fout, nullptr, 0, 0, fl,
+                  ACT_NONE, 0));
   __syncthreads();
 }
 
 // ---------------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) fused_layers_kernel(const __grid_constant__ FusedArgs A) {
+__global__ void __launch_bounds__(256, 2) fused_layers_kernel(const __grid_constant__ FusedArgs A) {
   extern __shared__ __align__(16) float sm[];
-  const int b = blockIdx.x;
+  if ((int)blockIdx.x >= A.meta[2 + A.bucket]) return;
+  const int b = A.order[A.meta[5 + A.bucket] + blockIdx.x];
   const int n = A.neff[b];
   if (n <= 0) return;
   const int tid = threadIdx.x, nt = blockDim.x;
@@ -436,17 +535,16 @@ __global__ void __launch_bounds__(256) fused_layers_kernel(const __grid_constant
   unsigned* pix = reinterpret_cast<unsigned*>(sm + S.pix);
   float* x0 = sm + S.x0;
   float* xb = sm + S.xb;
-  float* xc = sm + S.xc;
   float* xs = sm + S.xs;
   float* h1 = sm + S.h1;
   float* wts = sm + S.wts;
   float* P0 = sm + S.p0;
   float* PA = sm + S.pa;
-  float* R1 = sm + S.r1;           // A.x products, then attention maps
-  float* QK = sm + S.qk;           // Q|K rows; [QK | R2] also hosts the dense normalised adjacency
-  float* R2 = sm + S.r2;           // V rows
-  float* dense = QK;
-  const int64_t gp0 = A.poff ? A.poff[b] : 0;
+  float* R1 = sm + S.r1;           // dense A (power stack), then A.x products, then attention maps
+  float* QK = sm + S.qk;           // Q|K rows [c][i][2 attn + 4]   ([R1 | QK] also hosts the final node MLP's hidden rows)
+  float* R2 = sm + S.r2;           // V rows [i][c][nhid]
+  const int64_t gp0 = A.poff[b];
+  const FastDiv dn(n), dP(P);
 
   // ---- stage the graph
   for (int i = tid; i < N; i += nt) fl[i] = A.flags[(int64_t)b * N + i];
@@ -454,15 +552,16 @@ __global__ void __launch_bounds__(256) fused_layers_kernel(const __grid_constant
     const int rs = i * (2 * n - i - 1) / 2;
     for (int j = i + 1; j < n; ++j) pix[rs + j - i - 1] = (unsigned)((i << 8) | j);
   }
-  for (int idx = tid; idx < n * XS; idx += nt) {
-    const int i = idx / XS, k = idx - i * XS;
-    x0[idx] = k < F ? A.x_in[((int64_t)b * N + i) * F + k] : 0.f;
-  }
   {
+    const FastDiv dx(XS);
+    for (int idx = tid; idx < n * XS; idx += nt) {
+      const int i = dx.div(idx), k = idx - i * XS;
+      x0[idx] = k < F ? A.x_in[((int64_t)b * N + i) * F + k] : 0.f;
+    }
     const float* Ag = A.adj + (int64_t)b * N * N;
     for (int idx = tid; idx < n * n; idx += nt) {
-      const int i = idx / n, j = idx - i * n;
-      dense[i * LD + j] = Ag[i * N + j];
+      const int i = dn.div(idx), j = idx - i * n;
+      R1[i * LD + j] = Ag[i * N + j];
     }
   }
   __syncthreads();
@@ -473,11 +572,11 @@ __global__ void __launch_bounds__(256) fused_layers_kernel(const __grid_constant
   for (int p = tid; p < P; p += nt) {
     const unsigned ij = pix[p];
     const int i = ij >> 8, j = ij & 255;
-    const float a = dense[i * LD + j];
+    const float a = R1[i * LD + j];
     P0[p] = a;
     float a2 = 0.f;
     if (c_init > 1) {
-      for (int m = 0; m < n; ++m) a2 = fmaf(dense[i * LD + m], dense[m * LD + j], a2);
+      for (int m = 0; m < n; ++m) a2 = fmaf(R1[i * LD + m], R1[m * LD + j], a2);
       P0[PM + p] = a2;
     }
     if (A.has_a) {
@@ -494,62 +593,64 @@ __global__ void __launch_bounds__(256) fused_layers_kernel(const __grid_constant
     const FNet& net = isA ? A.a : A.x;
     if (!isA) {
       // node feature stack [x, x_1 .. x_depth] (ScoreNetwork_X.py:40, :84), padded columns zero
+      const FastDiv dq(XSS);
       for (int idx = tid; idx < n * XSS; idx += nt) {
-        const int i = idx / XSS, k = idx - i * XSS;
+        const int i = dq.div(idx), k = idx - i * XSS;
         xs[idx] = k < F ? x0[i * XS + k] : 0.f;
       }
     }
+    const int h = net.nhid;
+    const FastDiv dh(h);
+    float* hA = R1;
+    float* hB = R1 + n * net.Hp;
     if (net.type == GDSS_NET_X) {
       // ScoreNetworkX (ScoreNetwork_X.py:32-46): x_l = tanh(DenseGCNConv_l(x_{l-1}, adj)), raw adjacency only
-      build_norm_adj(P0, PM, 1, n, LD, NBP, dense, dinv);
+      gcn_degrees(P0, PM, 1, n, NBP, dinv, dn);
+      __syncthreads();
       const float* xin = x0;
       for (int l = 0; l < net.depth; ++l) {
-        const int f = l == 0 ? F : net.nhid, fp = (f + 3) & ~3;
-        adj_times_x(dense, LD, xin, XS, 1, n, fp, R1);
+        const int f = l == 0 ? F : h, f8 = (f + 7) >> 3;
+        gcn_ax(P0, PM, dinv, NBP, xin, XS, 1, n, f8, 8 * f8, R1, dn);
         __syncthreads();
-        float* xo = (l & 1) ? xc : xb;
-        mm_rows<ACT_TANH>(R1, 0, fp, f, net.gw[l], 0, net.nhid, net.gb[l], 0, 1, n, 0, net.nhid, net.nhid, xo, 0, XS, net.nhid,
-                          nullptr, 0, 0, nullptr);
+        mm_rows(mm_make(R1, 0, 8 * f8, f, net.gw[l], 0, h, net.gb[l], 0, 1, n, 0, h, xb, 0, XS, h, nullptr, 0, 0, nullptr, ACT_TANH));
         __syncthreads();
-        for (int idx = tid; idx < n * net.nhid; idx += nt) {
-          const int i = idx / net.nhid, o = idx - i * net.nhid;
-          xs[i * XSS + F + l * net.nhid + o] = xo[i * XS + o];
+        for (int idx = tid; idx < n * h; idx += nt) {
+          const int i = dh.div(idx), o = idx - i * h;
+          xs[i * XSS + F + l * h + o] = xb[i * XS + o];
         }
-        xin = xo;
-        __syncthreads();
+        xin = xb;
       }
-      final_node_mlp(net, xs, XSS, n, fl, PA, PA + n * ((2 * net.fdim + 3) & ~3), A.raw_x + (int64_t)b * N * F, F);
+      __syncthreads();
+      final_node_mlp(net, xs, XSS, n, fl, hA, hB, A.raw_x + (int64_t)b * N * F, F);
       continue;
     }
     // AttentionLayer stack (ScoreNetwork_A.py:131-141, ScoreNetwork_X.py:75-84)
     const float* pin = P0;
     const float* xin = x0;
     int cbase = net.c_init;
-    const float scale = 1.0f / sqrtf((float)net.nhid);
+    const float scale = 1.0f / sqrtf((float)h);
     for (int l = 0; l < net.depth; ++l) {
       const FLayer& L = net.L[l];
-      const int C = L.c_in, f = L.f_in, fp = (f + 3) & ~3, attn = L.attn, h = net.nhid;
+      const int C = L.c_in, f = L.f_in, f8 = (f + 7) >> 3, attn = L.attn;
       if (L.need_edge) stage_edge_weights(L, wts);
-      build_norm_adj(pin, PM, C, n, LD, NBP, dense, dinv);
-      adj_times_x(dense, LD, xin, XS, C, n, fp, R1);
+      gcn_degrees(pin, PM, C, n, NBP, dinv, dn);
+      __syncthreads();
+      gcn_ax(pin, PM, dinv, NBP, xin, XS, C, n, f8, 8 * f8, R1, dn);
       __syncthreads();
       // Q | K | V = (A^ x) W + b for every channel (attention.py:32-34); V rows are stored [i][c][h]
-      mm_rows<ACT_NONE>(R1, n * fp, fp, f, L.wqkv, f * L.qkvw, L.qkvw, L.bqkv, L.qkvw, C, n, L.need_edge ? 0 : 2 * attn,
-                        L.need_node ? L.qkvw : 2 * attn, L.qkvw, QK, n * QKS, QKS, 2 * attn, R2, h, C * h, nullptr);
+      mm_rows(mm_make(R1, n * 8 * f8, 8 * f8, f, L.wqkv, L.f_in_p * L.qkvw, L.qkvw, L.bqkv, L.qkvw, C, n, L.need_edge ? 0 : 2 * attn,
+                      L.need_node ? L.qkvw : 2 * attn, QK, n * QKS, QKS, 2 * attn, R2, h, C * h, nullptr, ACT_NONE));
       __syncthreads();
-      float* xo = (l & 1) ? xc : xb;
-      if (L.need_node) {
-        // x_out = tanh(mask_x(multi_channel(cat_c V_c)))  (attention.py:106-107), tanh'd twice in X_GMH (:81)
-        mm_rows<ACT_ELU>(R2, 0, C * h, C * h, L.nw0, 0, 16, L.nb0, 0, 1, n, 0, 16, 16, h1, 0, 16, 16, nullptr, 0, 0, nullptr);
+      // x_out = tanh(mask_x(multi_channel(cat_c V_c)))  (attention.py:106-107), tanh'd twice in X_GMH (:81).
+      // x_in is dead by now: layers >= 1 update xb in place (layer 0 reads x0, which the X network needs again)
+      if (L.need_node) node_l1(R2, C * h, L.nw0, L.nb0, n, h1);
+      if (L.need_edge) {
+        if (attn == 16) attention_maps<4>(QK, QKS, pix, C, n, P, PM, scale, R1, dP);
+        else attention_maps<8>(QK, QKS, pix, C, n, P, PM, scale, R1, dP);
       }
-      if (L.need_edge) attention_maps(QK, QKS, pix, C, n, P, PM, attn, net.heads, scale, R1);
       __syncthreads();
-      if (L.need_node) {
-        if (isA)
-          mm_rows<ACT_TANH>(h1, 0, 16, 16, L.nw1, 0, h, L.nb1, 0, 1, n, 0, h, h, xo, 0, XS, h, nullptr, 0, 0, fl);
-        else
-          mm_rows<ACT_TANH2>(h1, 0, 16, 16, L.nw1, 0, h, L.nb1, 0, 1, n, 0, h, h, xo, 0, XS, h, nullptr, 0, 0, fl);
-      }
+      if (L.need_node)
+        mm_rows(mm_make(h1, 0, 16, 16, L.nw1, 0, h, L.nb1, 0, 1, n, 0, h, xb, 0, XS, h, nullptr, 0, 0, fl, isA ? ACT_TANH : ACT_TANH2));
       if (L.need_edge) {
         const bool keep = l + 1 < net.depth;                    // a later layer reads the planes
         float* gout = isA ? A.stackT + (int64_t)cbase * A.pstride + gp0 : nullptr;
@@ -560,17 +661,19 @@ __global__ void __launch_bounds__(256) fused_layers_kernel(const __grid_constant
       if (L.need_node) {
         if (!isA) {
           for (int idx = tid; idx < n * h; idx += nt) {
-            const int i = idx / h, o = idx - i * h;
-            xs[i * XSS + F + l * h + o] = xo[i * XS + o];
+            const int i = dh.div(idx), o = idx - i * h;
+            xs[i * XSS + F + l * h + o] = xb[i * XS + o];
           }
         }
-        xin = xo;
+        xin = xb;
       }
       pin = PA;
       cbase += L.c_out;
-      __syncthreads();
     }
-    if (!isA) final_node_mlp(net, xs, XSS, n, fl, PA, PA + n * ((2 * net.fdim + 3) & ~3), A.raw_x + (int64_t)b * N * F, F);
+    if (!isA) {
+      __syncthreads();
+      final_node_mlp(net, xs, XSS, n, fl, hA, hB, A.raw_x + (int64_t)b * N * F, F);
+    }
   }
 }
 
@@ -583,7 +686,7 @@ struct FinalTriArgs {
   const int* gmap; const int* meta;
   const float* w1; const float* b1; const float* w2; const float* b2; const float* w3; const float* b3;
   float* out; const float* flags;
-  int N, fdim, H;
+  int N, fdim, H, Hs;
 };
 
 template <int OPT>
@@ -606,11 +709,11 @@ __global__ void __launch_bounds__(256) final_edge_tri_kernel(FinalTriArgs a) {
   for (int idx = tid; idx < HP; idx += 256) {
     b1s[idx] = idx < H ? a.b1[idx] : 0.f;
     b2s[idx] = idx < H ? a.b2[idx] : 0.f;
-    w3s[idx] = idx < H ? a.w3[idx] : 0.f;
+    w3s[idx] = idx < H ? a.w3[idx * 4] : 0.f;      // [Hp][foutp = 4]: the single output column
   }
   for (int idx = tid; idx < K1 * HP; idx += 256) {
     int k = idx / HP, o = idx - k * HP;
-    W1s[idx] = o < H ? a.w1[k * H + o] : 0.f;
+    W1s[idx] = o < H ? a.w1[k * a.Hs + o] : 0.f;
   }
   for (int idx = tid; idx < K1 * 128; idx += 256) {
     int k = idx >> 7, m = idx & 127;
@@ -647,7 +750,7 @@ __global__ void __launch_bounds__(256) final_edge_tri_kernel(FinalTriArgs a) {
   __syncthreads();
   for (int idx = tid; idx < H * HP; idx += 256) {
     int k = idx / HP, o = idx - k * HP;
-    W2s[idx] = o < H ? a.w2[k * H + o] : 0.f;
+    W2s[idx] = o < H ? a.w2[k * a.Hs + o] : 0.f;
   }
   __syncthreads();
 #pragma unroll
@@ -733,7 +836,7 @@ static bool net_fusable(const NetPlan& p) {
 static void fill_net(const NetPlan& p, const float* blob, FNet* f) {
   memset(f, 0, sizeof(*f));
   f->type = p.type; f->depth = p.depth; f->F = p.F; f->nhid = p.nhid; f->heads = p.heads;
-  f->fdim = p.fdim; f->fout = p.fout; f->c_init = p.c_init;
+  f->fdim = p.fdim; f->fout = p.fout; f->c_init = p.c_init; f->Hp = p.Hp; f->foutp = p.foutp;
   for (int l = 0; l < p.depth && l < FUSED_MAX_LAYERS; ++l) {
     if (p.type == GDSS_NET_X) {
       f->gw[l] = blob + p.gw[l];
@@ -743,7 +846,7 @@ static void fill_net(const NetPlan& p, const float* blob, FNet* f) {
     const LayerPlan& L = p.layers[l];
     FLayer& o = f->L[l];
     const bool last = l == p.depth - 1;
-    o.c_in = L.c_in; o.c_out = L.c_out; o.f_in = L.f_in; o.attn = L.attn; o.nlin = L.nlin; o.qkvw = L.qkvw;
+    o.c_in = L.c_in; o.c_out = L.c_out; o.f_in = L.f_in; o.f_in_p = L.f_in_p; o.attn = L.attn; o.nlin = L.nlin; o.qkvw = L.qkvw;
     o.need_edge = (p.type == GDSS_NET_A || !last) ? 1 : 0;   // X_GMH: the last layer's adj_out is never read
     o.need_node = (p.type != GDSS_NET_A || !last) ? 1 : 0;   // A: the last layer's x_out is never read
     o.wqkv = blob + L.wqkv; o.bqkv = blob + L.bqkv;
@@ -757,7 +860,7 @@ static void fill_net(const NetPlan& p, const float* blob, FNet* f) {
 // dense adjacency alias)
 static int64_t plan_smem(const gdss_ctx* ctx, int NB, FSmem* s) {
   const NetPlan* nets[2] = {ctx->has_a ? &ctx->pa : nullptr, ctx->has_x ? &ctx->px : nullptr};
-  int Cmax = 1, hmax = 4, amax = 0, fmax = (ctx->F + 3) & ~3, fdx = 4, Hx = 0, cinit = 1;
+  int Cmax = 1, hmax = 8, amax = 0, fmax = (ctx->F + 7) & ~7, fdx = 4, Hx = 0, cinit = 1;
   for (int k = 0; k < 2; ++k) {
     const NetPlan* p = nets[k];
     if (!p) continue;
@@ -772,7 +875,7 @@ static int64_t plan_smem(const gdss_ctx* ctx, int NB, FSmem* s) {
       amax = amax > L.attn ? amax : L.attn;
     }
   }
-  if (fmax < hmax) fmax = hmax;
+  if (fmax < ((hmax + 7) & ~7)) fmax = (hmax + 7) & ~7;
   const int NBP = (NB + 3) & ~3;
   const int PM = ((NB * (NB - 1) / 2) + 3) & ~3;
   s->NBP = NBP; s->PM = PM > 4 ? PM : 4;
@@ -787,25 +890,31 @@ static int64_t plan_smem(const gdss_ctx* ctx, int NB, FSmem* s) {
   s->pix = take(s->PM);
   s->x0 = take(NB * s->XS);
   s->xb = take(NB * s->XS);
-  s->xc = take(NB * s->XS);
   s->xs = take(NB * s->XSS);
   s->h1 = take(NB * 16);
   s->wts = take(2 * Cmax * 16 + 16 + 256 + 16 + 128 + 8);
   s->p0 = take(cinit * s->PM);
-  int pa = Cmax * s->PM;
-  if (pa < 2 * NB * Hx) pa = 2 * NB * Hx;            // hosts the two hidden buffers of the final node MLP
-  s->pa = take(pa);
-  int r1 = Cmax * NB * fmax;                         // A.x products [C][n][fp]
+  s->pa = take(Cmax * s->PM);
+  int r1 = Cmax * NB * fmax;                         // A.x products [C][n][f rounded up to 8]
   if (r1 < Cmax * s->PM) r1 = Cmax * s->PM;          // attention maps [C][P]
-  s->r1 = take(r1);
-  const int dense = Cmax * NB * s->LD;
+  if (r1 < NB * s->LD) r1 = NB * s->LD;              // dense A while the power stack is built
   int qk = Cmax * NB * s->QKS;
-  int r2 = Cmax * NB * hmax;
-  if (qk + r2 < dense) r2 = dense - qk;
+  if (r1 + qk < 2 * NB * Hx) qk = 2 * NB * Hx - r1;  // [R1 | QK] hosts the two hidden buffers of the final node MLP
+  s->r1 = take(r1);
   s->qk = take(qk);
-  s->r2 = take(r2);
+  s->r2 = take(Cmax * NB * hmax);
   s->total = cur;
   return (int64_t)cur * 4;
+}
+
+// size buckets of the per-graph kernel (its shared memory is sized by the largest graph of a launch):
+// graphs of at most 24 / 32 / N nodes; returns the number of buckets and their upper bounds
+static int size_buckets(int N, int nb[3]) {
+  int k = 0;
+  if (N > 24) nb[k++] = 24;
+  if (N > 32) nb[k++] = 32;
+  nb[k++] = N;
+  return k;
 }
 
 bool fused_supported(const gdss_ctx* ctx) {
@@ -821,7 +930,12 @@ int launch_tri_setup(const gdss_ctx* ctx, const int* neff, int B, char* ws, cons
   int* poff = reinterpret_cast<int*>(ws + w.off[R_POFF]);
   int* meta = reinterpret_cast<int*>(ws + w.off[R_META]);
   int* gmap = reinterpret_cast<int*>(ws + w.off[R_GMAP]);
-  tri_scan_kernel<<<1, 1024, 0, st>>>(neff, B, poff, meta, gmap);
+  int* order = reinterpret_cast<int*>(ws + w.off[R_ORDER]);
+  int nb[3];
+  const int k = size_buckets(ctx->N, nb);
+  // scan kernel buckets: n <= nb0 -> 0, n <= nb1 -> 1, else 2 (unused buckets get bounds that never match)
+  const int b0 = nb[0], b1 = k > 1 ? nb[1] : nb[0];
+  tri_scan_kernel<<<1, 1024, 0, st>>>(neff, B, b0, b1, poff, meta, gmap, order);
   launched(K_MISC, st);
   LAUNCH_CHECK();
   tri_map_kernel<<<B, 64, 0, st>>>(neff, poff, gmap);
@@ -847,14 +961,24 @@ int launch_eval_fused(const gdss_ctx* ctx, const float* x, const float* adj, con
   fa.poff = reinterpret_cast<const int*>(ws + w.off[R_POFF]);
   fa.pstride = w.pstride;
   fa.N = N; fa.F = ctx->F;
-  const int64_t smem = plan_smem(ctx, N, &fa.sl);
-  if (smem <= 0 || smem > ctx->smem_optin) return GDSS_E_UNSUPPORTED;
-  cudaError_t e = cudaFuncSetAttribute(fused_layers_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return (int)e;
-  const int threads = N <= 12 ? 64 : (N <= 24 ? 128 : 256);
-  fused_layers_kernel<<<B, threads, smem, st>>>(fa);
-  launched(K_FUSED, st);
-  LAUNCH_CHECK();
+  fa.order = reinterpret_cast<const int*>(ws + w.off[R_ORDER]);
+  fa.meta = reinterpret_cast<const int*>(ws + w.off[R_META]);
+  int nb[3];
+  const int nbk = size_buckets(N, nb);
+  for (int k = 0; k < nbk; ++k) {
+    // one launch per size bucket: B CTAs, those beyond the bucket's population exit at once (the counts live
+    // on the device; no host synchronisation)
+    fa.bucket = k;
+    const int64_t smem = plan_smem(ctx, nb[k], &fa.sl);
+    if (smem <= 0 || smem > ctx->smem_optin) return GDSS_E_UNSUPPORTED;
+    cudaError_t e = cudaFuncSetAttribute(fused_layers_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    const int threads = nb[k] <= 12 ? 128 : 256;
+    fused_layers_kernel<<<B, threads, smem, st>>>(fa);
+    launched(K_FUSED, st);
+    LAUNCH_CHECK();
+  }
+  cudaError_t e;
   if (want_a) {
     const NetPlan& p = ctx->pa;
     FinalTriArgs ta;
@@ -863,7 +987,7 @@ int launch_eval_fused(const gdss_ctx* ctx, const float* x, const float* adj, con
     ta.meta = reinterpret_cast<const int*>(ws + w.off[R_META]);
     ta.w1 = ctx->blob_a + p.fw[0]; ta.b1 = ctx->blob_a + p.fb[0]; ta.w2 = ctx->blob_a + p.fw[1]; ta.b2 = ctx->blob_a + p.fb[1];
     ta.w3 = ctx->blob_a + p.fw[2]; ta.b3 = ctx->blob_a + p.fb[2];
-    ta.out = score_adj; ta.flags = flags; ta.N = N; ta.fdim = p.fdim; ta.H = 2 * p.fdim;
+    ta.out = score_adj; ta.flags = flags; ta.N = N; ta.fdim = p.fdim; ta.H = 2 * p.fdim; ta.Hs = p.Hp;
     int HP;
     final_tri_fn fn = pick_final_tri(ta.H, &HP);
     if (!fn) return GDSS_E_UNSUPPORTED;

@@ -18,7 +18,8 @@ namespace gdss {
 // output units) read consecutive floats.
 struct LayerPlan {
   int c_in, c_out, f_in, attn, nhid, hid, nlin, qkvw;
-  int64_t wqkv;                 // [c_in][f_in][qkvw]   columns = Q | K | V
+  int f_in_p;                   // f_in rounded up to 4 (zero rows): row count of every wqkv channel block
+  int64_t wqkv;                 // [c_in][f_in_p][qkvw]   columns = Q | K | V
   int64_t bqkv;                 // [c_in][qkvw]
   int64_t ew[GDSS_MAX_LIN];     // edge MLP `mlp`: (2 c_in -> hid), (hid -> hid)*, (hid -> c_out)
   int64_t eb[GDSS_MAX_LIN];
@@ -30,10 +31,11 @@ struct NetPlan {
   int F, N, nhid, depth, nlin, c_init, c_hid, c_final, adim, heads;
   int fdim;                     // input width of `final`
   int fout;                     // output width of `final` (F for X nets, 1 for A)
+  int fdp, Hp, foutp;           // fdim, 2 fdim, fout rounded up to 4: padded (zero) rows / row strides of `final`
   int n_tensors;                // number of state_dict tensors
   LayerPlan layers[GDSS_MAX_LAYERS];
-  int64_t gw[GDSS_MAX_LAYERS], gb[GDSS_MAX_LAYERS];   // ScoreNetworkX: DenseGCNConv weight [in][out], bias
-  int64_t fw[3], fb[3];         // final MLP (3 linears), [in][out]
+  int64_t gw[GDSS_MAX_LAYERS], gb[GDSS_MAX_LAYERS];   // ScoreNetworkX: DenseGCNConv weight [in rounded up to 4][out], bias
+  int64_t fw[3], fb[3];         // final MLP (3 linears): [fdp][Hp], [Hp][Hp], [Hp][foutp]; biases [Hp],[Hp],[foutp]
   int64_t total;                // floats
 };
 
@@ -42,7 +44,7 @@ int plan_net(const gdss_net_desc* d, int N, NetPlan* p);
 // named workspace regions (byte offsets, 256-aligned)
 enum Region {
   R_NEFF = 0, R_STEP, R_TABLE, R_MEANS, R_NORMS, R_STACK_A, R_STACK_X, R_DIS, R_QKV, R_XA0, R_XA1, R_XS, R_RAW_X, R_RAW_ADJ,
-  R_POFF, R_META, R_GMAP, R_STACKT,
+  R_POFF, R_META, R_GMAP, R_ORDER, R_STACKT,
   R_COUNT
 };
 

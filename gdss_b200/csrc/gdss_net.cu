@@ -452,7 +452,7 @@ struct FinalEdgeArgs {
   const float* w1; const float* b1; const float* w2; const float* b2; const float* w3; const float* b3;
   float* out;       // [B][N][N]
   const float* flags; const int* neff;
-  int N, fdim, H;
+  int N, fdim, H, Hs;
 };
 
 template <int OPT>
@@ -486,11 +486,11 @@ __global__ void __launch_bounds__(256) final_edge_kernel(FinalEdgeArgs a) {
   for (int idx = tid; idx < HP; idx += 256) {
     b1s[idx] = idx < H ? a.b1[idx] : 0.f;
     b2s[idx] = idx < H ? a.b2[idx] : 0.f;
-    w3s[idx] = idx < H ? a.w3[idx] : 0.f;
+    w3s[idx] = idx < H ? a.w3[idx * 4] : 0.f;      // [Hp][foutp = 4]: the single output column
   }
   for (int idx = tid; idx < K1 * HP; idx += 256) {
     int k = idx / HP, o = idx - k * HP;
-    W1s[idx] = o < H ? a.w1[k * H + o] : 0.f;
+    W1s[idx] = o < H ? a.w1[k * a.Hs + o] : 0.f;
   }
   __syncthreads();
   const float* S = a.stack + b * a.s_bs;
@@ -533,7 +533,7 @@ __global__ void __launch_bounds__(256) final_edge_kernel(FinalEdgeArgs a) {
   __syncthreads();              // everyone is done with Xs / W1s
   for (int idx = tid; idx < H * HP; idx += 256) {
     int k = idx / HP, o = idx - k * HP;
-    W2s[idx] = o < H ? a.w2[k * H + o] : 0.f;
+    W2s[idx] = o < H ? a.w2[k * a.Hs + o] : 0.f;
   }
   __syncthreads();
   // ---- layer 2
@@ -591,7 +591,7 @@ __global__ void __launch_bounds__(256) final_edge_kernel(FinalEdgeArgs a) {
 // rows of the node feature stack [x, x_1 .. x_d] -> 2f -> 2f -> F, ELU, mask_x.
 // ---------------------------------------------------------------------------------------
 struct FinalNodeArgs {
-  const float* xs; int64_t xs_bs; int fdim; int H; int fout;
+  const float* xs; int64_t xs_bs; int fdim; int H; int fout; int Hs; int fouts;
   const float* w1; const float* b1; const float* w2; const float* b2; const float* w3; const float* b3;
   float* out; const float* flags; const int* neff; int N;
 };
@@ -618,14 +618,14 @@ __global__ void __launch_bounds__(256) final_node_kernel(FinalNodeArgs a) {
   for (int idx = tid; idx < rows * H; idx += 256) {
     int r = idx / H, o = idx - r * H;
     float s = a.b1[o];
-    for (int k = 0; k < K; ++k) s = fmaf(X0[r * K + k], __ldg(a.w1 + k * H + o), s);
+    for (int k = 0; k < K; ++k) s = fmaf(X0[r * K + k], __ldg(a.w1 + k * a.Hs + o), s);
     H1[idx] = elu_f(s);
   }
   __syncthreads();
   for (int idx = tid; idx < rows * H; idx += 256) {
     int r = idx / H, o = idx - r * H;
     float s = a.b2[o];
-    for (int k = 0; k < H; ++k) s = fmaf(H1[r * H + k], __ldg(a.w2 + k * H + o), s);
+    for (int k = 0; k < H; ++k) s = fmaf(H1[r * H + k], __ldg(a.w2 + k * a.Hs + o), s);
     H2[idx] = elu_f(s);
   }
   __syncthreads();
@@ -634,7 +634,7 @@ __global__ void __launch_bounds__(256) final_node_kernel(FinalNodeArgs a) {
   for (int idx = tid; idx < rows * a.fout; idx += 256) {
     int r = idx / a.fout, o = idx - r * a.fout;
     float s = a.b3[o];
-    for (int k = 0; k < H; ++k) s = fmaf(H2[r * H + k], __ldg(a.w3 + k * a.fout + o), s);
+    for (int k = 0; k < H; ++k) s = fmaf(H2[r * H + k], __ldg(a.w3 + k * a.fouts + o), s);
     O[(int64_t)(i0 + r) * a.fout + o] = s * fl[i0 + r];
   }
 }
@@ -722,6 +722,7 @@ void layout_workspace(const gdss_ctx* ctx, int B, Workspace* w) {
     sz[R_POFF] = 4 * ((int64_t)B + 1);
     sz[R_META] = 256;
     sz[R_GMAP] = 4 * w->pstride;
+    sz[R_ORDER] = 4 * (int64_t)B;
     sz[R_STACKT] = ctx->has_a ? 4 * w->pstride * ctx->pa.fdim : 0;
   }
   sz[R_RAW_X] = 4 * (int64_t)B * N * F;
@@ -843,7 +844,7 @@ static int run_attn_net(const gdss_ctx* ctx, const NetPlan& p, const float* blob
     g.planes = pin; g.p_bs = s_bs;
     g.x = xin; g.x_bs = x_bs; g.ldx = ldx; g.f_in = L.f_in;
     g.dis = dis; g.d_bs = d_bs;
-    g.W = blob + L.wqkv; g.w_cs = (int64_t)L.f_in * L.qkvw; g.w_ld = L.qkvw;
+    g.W = blob + L.wqkv; g.w_cs = (int64_t)L.f_in_p * L.qkvw; g.w_ld = L.qkvw;
     g.col0 = need_edge ? 0 : 2 * L.attn;
     g.ow = (need_edge ? 2 * L.attn : 0) + (need_node ? L.nhid : 0);
     g.bias = blob + L.bqkv; g.b_cs = L.qkvw;
@@ -905,7 +906,7 @@ static int run_attn_net(const gdss_ctx* ctx, const NetPlan& p, const float* blob
     fa.stack = stack; fa.s_bs = s_bs;
     fa.w1 = blob + p.fw[0]; fa.b1 = blob + p.fb[0]; fa.w2 = blob + p.fw[1]; fa.b2 = blob + p.fb[1];
     fa.w3 = blob + p.fw[2]; fa.b3 = blob + p.fb[2];
-    fa.out = score; fa.flags = flags; fa.neff = neff; fa.N = N; fa.fdim = p.fdim; fa.H = 2 * p.fdim;
+    fa.out = score; fa.flags = flags; fa.neff = neff; fa.N = N; fa.fdim = p.fdim; fa.H = 2 * p.fdim; fa.Hs = p.Hp;
     int HP;
     final_fn fn = pick_final(fa.H, &HP);
     if (!fn) return GDSS_E_UNSUPPORTED;
@@ -923,7 +924,7 @@ static int run_attn_net(const gdss_ctx* ctx, const NetPlan& p, const float* blob
     }
   } else {
     FinalNodeArgs fa;
-    fa.xs = xs; fa.xs_bs = (int64_t)N * p.fdim; fa.fdim = p.fdim; fa.H = 2 * p.fdim; fa.fout = p.fout;
+    fa.xs = xs; fa.xs_bs = (int64_t)N * p.fdim; fa.fdim = p.fdim; fa.H = 2 * p.fdim; fa.fout = p.fout; fa.Hs = p.Hp; fa.fouts = p.foutp;
     fa.w1 = blob + p.fw[0]; fa.b1 = blob + p.fb[0]; fa.w2 = blob + p.fw[1]; fa.b2 = blob + p.fb[1];
     fa.w3 = blob + p.fw[2]; fa.b3 = blob + p.fb[2];
     fa.out = score; fa.flags = flags; fa.neff = neff; fa.N = N;
@@ -965,7 +966,7 @@ static int run_gcn_net(const gdss_ctx* ctx, const NetPlan& p, const float* blob,
     if (rc) return rc;
   }
   FinalNodeArgs fa;
-  fa.xs = xs; fa.xs_bs = (int64_t)N * p.fdim; fa.fdim = p.fdim; fa.H = 2 * p.fdim; fa.fout = p.fout;
+  fa.xs = xs; fa.xs_bs = (int64_t)N * p.fdim; fa.fdim = p.fdim; fa.H = 2 * p.fdim; fa.fout = p.fout; fa.Hs = p.Hp; fa.fouts = p.foutp;
   fa.w1 = blob + p.fw[0]; fa.b1 = blob + p.fb[0]; fa.w2 = blob + p.fw[1]; fa.b2 = blob + p.fb[1];
   fa.w3 = blob + p.fw[2]; fa.b3 = blob + p.fb[2];
   fa.out = score; fa.flags = flags; fa.neff = neff; fa.N = N;

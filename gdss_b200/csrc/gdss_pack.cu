@@ -34,7 +34,7 @@ int plan_net(const gdss_net_desc* d, int N, NetPlan* p) {
   if (p->type == GDSS_NET_X) {
     for (int l = 0; l < p->depth; ++l) {
       int fin = l == 0 ? p->F : p->nhid;
-      p->gw[l] = take(cur, (int64_t)fin * p->nhid);
+      p->gw[l] = take(cur, (int64_t)((fin + 3) & ~3) * p->nhid);
       p->gb[l] = take(cur, p->nhid);
       nt += 2;
     }
@@ -56,7 +56,8 @@ int plan_net(const gdss_net_desc* d, int N, NetPlan* p) {
       L.hid = 2 * (L.c_in > L.c_out ? L.c_in : L.c_out);
       L.nlin = p->nlin;
       L.qkvw = 2 * L.attn + L.nhid;
-      L.wqkv = take(cur, (int64_t)L.c_in * L.f_in * L.qkvw);
+      L.f_in_p = (L.f_in + 3) & ~3;
+      L.wqkv = take(cur, (int64_t)L.c_in * L.f_in_p * L.qkvw);
       L.bqkv = take(cur, (int64_t)L.c_in * L.qkvw);
       nt += 6 * L.c_in;
       for (int i = 0; i < L.nlin; ++i) {
@@ -83,7 +84,10 @@ int plan_net(const gdss_net_desc* d, int N, NetPlan* p) {
   } else {
     return GDSS_E_UNSUPPORTED;
   }
-  int dims[4] = {p->fdim, 2 * p->fdim, 2 * p->fdim, p->fout};
+  p->fdp = (p->fdim + 3) & ~3;
+  p->Hp = (2 * p->fdim + 3) & ~3;
+  p->foutp = (p->fout + 3) & ~3;
+  int dims[4] = {p->fdp, p->Hp, p->Hp, p->foutp};
   for (int i = 0; i < 3; ++i) {
     p->fw[i] = take(cur, (int64_t)dims[i] * dims[i + 1]);
     p->fb[i] = take(cur, dims[i + 1]);
@@ -94,10 +98,11 @@ int plan_net(const gdss_net_desc* d, int N, NetPlan* p) {
   return GDSS_OK;
 }
 
-// nn.Linear weight [out][in] -> [in][out]
-static void put_linear_t(float* dst, const float* src, int in, int out) {
+// nn.Linear weight [out][in] -> [in][out] with row stride ld (>= out; the padding stays zero)
+static void put_linear_t(float* dst, const float* src, int in, int out, int ld = 0) {
+  if (ld <= 0) ld = out;
   for (int o = 0; o < out; ++o)
-    for (int i = 0; i < in; ++i) dst[(int64_t)i * out + o] = src[(int64_t)o * in + i];
+    for (int i = 0; i < in; ++i) dst[(int64_t)i * ld + o] = src[(int64_t)o * in + i];
 }
 
 struct Cursor {
@@ -158,7 +163,7 @@ extern "C" int gdss_pack_weights(const gdss_net_desc* desc, int32_t n_nodes, con
           const float* w = c.next((int64_t)L.f_in * widths[m]);
           const float* b = c.next(widths[m]);
           if (c.bad) return GDSS_E_BADARG;
-          float* W = blob + L.wqkv + (int64_t)ch * L.f_in * L.qkvw;
+          float* W = blob + L.wqkv + (int64_t)ch * L.f_in_p * L.qkvw;
           for (int f = 0; f < L.f_in; ++f)
             for (int o = 0; o < widths[m]; ++o) W[(int64_t)f * L.qkvw + col + o] = w[(int64_t)f * widths[m] + o];
           float* Bv = blob + L.bqkv + (int64_t)ch * L.qkvw;
@@ -185,11 +190,12 @@ extern "C" int gdss_pack_weights(const gdss_net_desc* desc, int32_t n_nodes, con
     }
   }
   int dims[4] = {p.fdim, 2 * p.fdim, 2 * p.fdim, p.fout};
+  int lds[3] = {p.Hp, p.Hp, p.foutp};
   for (int i = 0; i < 3; ++i) {
     const float* w = c.next((int64_t)dims[i] * dims[i + 1]);
     const float* b = c.next(dims[i + 1]);
     if (c.bad) return GDSS_E_BADARG;
-    put_linear_t(blob + p.fw[i], w, dims[i], dims[i + 1]);
+    put_linear_t(blob + p.fw[i], w, dims[i], dims[i + 1], lds[i]);
     memcpy(blob + p.fb[i], b, sizeof(float) * dims[i + 1]);
   }
   if (c.pos != n_tensors) return GDSS_E_BADARG;

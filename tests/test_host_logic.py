@@ -56,7 +56,7 @@ def test_describe_and_pack_every_checkpoint(name):
                 assert getattr(d, k) == params[k], k
         desc, blob = pack_network(sd, N)
         n_param = sum(v.numel() for v in sd.values())
-        assert n_param <= blob.numel() <= n_param + 4 * len(sd)
+        assert n_param <= blob.numel() <= 1.35 * n_param + 64 * len(sd)      # rows / strides are padded to 4
         # every parameter value survives packing (multiset of values, transposition aside)
         src = torch.cat([v.reshape(-1) for v in sd.values()]).double()
         assert abs(float(blob.double().sum()) - float(src.sum())) <= 1e-6 * float(src.abs().sum())
