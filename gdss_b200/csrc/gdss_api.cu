@@ -72,6 +72,8 @@ extern "C" gdss_ctx* gdss_ctx_create(int32_t N, int32_t F, const gdss_net_desc* 
   c->fused = false;
   const char* nf = getenv("GDSS_NO_FUSED");
   if (!(nf && nf[0] == '1')) c->fused = fused_supported(c);
+  const char* ntc = getenv("GDSS_NO_TC");
+  c->use_tc = !(ntc && ntc[0] == '1');
   return c;
 }
 

@@ -75,6 +75,7 @@ __global__ void __launch_bounds__(1024) tri_scan_kernel(const int* __restrict__ 
     poff[B] = tot;
     meta[0] = tot;
     meta[1] = (tot + 127) / 128;
+    meta[16] = 0;                          // error flag of the tensor-core kernel (lost mbarrier arrival)
     for (int q = 0; q < 3; ++q) {
       meta[2 + q] = tot_s[1 + q];
       meta[5 + q] = start[q];
@@ -801,6 +802,270 @@ __global__ void __launch_bounds__(256) final_edge_tri_kernel(FinalTriArgs a) {
   }
 }
 
+// ---------------------------------------------------------------------------------------
+// final_edge_tc_kernel: the same final MLP on the 5th-generation tensor cores (tcgen05), fp32-faithful through
+// the 3xTF32 split  x*w ~= hi(x)hi(w) + lo(x)hi(w) + hi(x)lo(w)  (hi = round-to-nearest TF32, lo = TF32 of the
+// remainder; accumulation in fp32 in tensor memory).  Persistent: one CTA per SM loops over 128-pixel tiles.
+//
+//   tensor memory (columns):  [0, NP)  A-operand hi      [NP, 2NP)  A-operand lo      [2NP, 3NP)  accumulator D
+//     layer 1: A = the K1P channel values of the tile's 128 pixels (hi in columns [0,K1P), lo in [K1P, 2 K1P)),
+//              written by tcgen05.st straight from registers (thread = pixel = TMEM lane);
+//     layer 2: A = ELU(D + b1), split again and stored over the dead layer-1 operand.
+//   shared memory: W1^T, W2^T as B operands, K-major without swizzle ([k/4][n][k%4], hi and lo copies),
+//              staged once per CTA; biases and the last layer's weight vector.
+//   256 threads: warp w works on TMEM lanes 32 (w % 4) .. +31 and on column half w / 4.
+// ---------------------------------------------------------------------------------------
+DEVINL uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+DEVINL float tf32_rna(float v) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+  return __uint_as_float(r);
+}
+
+DEVINL uint64_t umma_bdesc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;                 // descriptor version of sm_100; layout type 0 = no swizzle
+  return d;
+}
+
+DEVINL void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+DEVINL void tmem_st4(uint32_t taddr, float a, float b, float c, float d) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};\n" ::"r"(taddr), "r"(__float_as_uint(a)),
+               "r"(__float_as_uint(b)), "r"(__float_as_uint(c)), "r"(__float_as_uint(d))
+               : "memory");
+}
+
+DEVINL void tmem_st8(uint32_t taddr, const float* v) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};\n" ::"r"(taddr),
+               "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+               "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7]))
+               : "memory");
+}
+
+DEVINL void tmem_ld8(uint32_t taddr, float* v) {
+  uint32_t r[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// bounded wait (a lost arrival must not hang the GPU): returns false after ~1 s
+DEVINL bool mbar_wait(uint32_t mbar, uint32_t parity) {
+  for (int it = 0; it < (1 << 24); ++it) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}\n"
+        : "=r"(ok)
+        : "r"(mbar), "r"(parity)
+        : "memory");
+    if (ok) return true;
+  }
+  return false;
+}
+
+DEVINL void tc_sync_before_mma() {         // tcgen05.st / ld of every thread ordered before the next MMA
+  asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+}
+
+template <int NP, int K1P>
+__global__ void __launch_bounds__(256, 1) final_edge_tc_kernel(FinalTriArgs a, int* __restrict__ err) {
+  extern __shared__ __align__(128) float sm[];
+  constexpr int KH = K1P / 2;             // layer-1 operand columns per column half
+  constexpr int CH = NP / 2;              // hidden columns per column half
+  static_assert(NP % 16 == 0 && K1P % 8 == 0 && K1P <= NP && 3 * NP <= 512 && CH % 8 == 0 && KH % 4 == 0, "shape");
+  float* W1hi = sm;                       // [K1P/4][NP][4]
+  float* W1lo = W1hi + K1P * NP;
+  float* W2hi = W1lo + K1P * NP;          // [NP/4][NP][4]
+  float* W2lo = W2hi + NP * NP;
+  float* b1s = W2lo + NP * NP;            // [NP]
+  float* b2s = b1s + NP;
+  float* w3s = b2s + NP;
+  float* part = w3s + NP;                 // [128] partial dot products of column half 1
+  __shared__ uint32_t tmem_base_s;
+  __shared__ __align__(8) uint64_t mbar;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int half = warp >> 2;
+  const int row = 32 * (warp & 3) + lane;
+  const int K1 = a.fdim, H = a.H, N = a.N;
+  // ---- one-time set-up: B operands (hi / lo), biases, tensor memory, mbarrier
+  for (int idx = tid; idx < K1P * NP; idx += 256) {
+    const int k = idx / NP, n = idx - k * NP;
+    const float w = (k < K1 && n < H) ? a.w1[k * a.Hs + n] : 0.f;
+    const float hi = tf32_rna(w);
+    const int o = (k >> 2) * (NP * 4) + n * 4 + (k & 3);
+    W1hi[o] = hi;
+    W1lo[o] = tf32_rna(w - hi);
+  }
+  for (int idx = tid; idx < NP * NP; idx += 256) {
+    const int k = idx / NP, n = idx - k * NP;
+    const float w = (k < H && n < H) ? a.w2[k * a.Hs + n] : 0.f;
+    const float hi = tf32_rna(w);
+    const int o = (k >> 2) * (NP * 4) + n * 4 + (k & 3);
+    W2hi[o] = hi;
+    W2lo[o] = tf32_rna(w - hi);
+  }
+  for (int idx = tid; idx < NP; idx += 256) {
+    b1s[idx] = idx < H ? a.b1[idx] : 0.f;
+    b2s[idx] = idx < H ? a.b2[idx] : 0.f;
+    w3s[idx] = idx < H ? a.w3[idx * 4] : 0.f;
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;\n" ::"r"(smem_u32(&tmem_base_s)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+  }
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(smem_u32(&mbar)) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");     // generic-proxy writes of W -> async proxy (UMMA)
+  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+  const uint32_t tb = tmem_base_s;
+  const uint32_t tlane = tb + ((uint32_t)(32 * (warp & 3)) << 16);
+  constexpr uint32_t colAhi = 0, colAlo = NP, colD = 2 * NP;
+  constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NP >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  constexpr uint32_t LBO = NP * 16, SBO = 128;
+  const uint32_t mb = smem_u32(&mbar);
+  const float b3 = a.b3[0];
+  uint32_t phase = 0;
+  bool ok = true;
+  const int ntiles = a.meta[1];
+  for (int tile = blockIdx.x; tile < ntiles && ok; tile += gridDim.x) {
+    const int64_t gp = (int64_t)tile * 128 + row;
+    // ---- layer-1 operand: channel values of this pixel -> hi / lo -> tensor memory
+    {
+      float v[KH];
+#pragma unroll
+      for (int kk = 0; kk < KH; ++kk) {
+        const int c = half * KH + kk;
+        v[kk] = c < K1 ? __ldg(a.stackT + (int64_t)c * a.pstride + gp) : 0.f;
+      }
+#pragma unroll
+      for (int kk = 0; kk < KH; kk += 4) {
+        float h[4], l[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          h[q] = tf32_rna(v[kk + q]);
+          l[q] = tf32_rna(v[kk + q] - h[q]);
+        }
+        tmem_st4(tlane + colAhi + half * KH + kk, h[0], h[1], h[2], h[3]);
+        tmem_st4(tlane + colAhi + K1P + half * KH + kk, l[0], l[1], l[2], l[3]);
+      }
+    }
+    tc_sync_before_mma();
+    if (tid == 0) {
+      uint32_t acc = 0;
+#pragma unroll
+      for (int ps = 0; ps < 3; ++ps) {
+        const uint32_t acol = tb + colAhi + (ps == 1 ? K1P : 0);
+        const uint32_t bbase = smem_u32(ps == 2 ? W1lo : W1hi);
+#pragma unroll
+        for (int s = 0; s < K1P / 8; ++s) {
+          umma_tf32_ts(tb + colD, acol + s * 8, umma_bdesc(bbase + s * 2 * LBO, LBO, SBO), idesc, acc);
+          acc = 1;
+        }
+      }
+      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(mb) : "memory");
+    }
+    ok = mbar_wait(mb, phase);
+    phase ^= 1;
+    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+    // ---- epilogue 1: ELU(D + b1) -> hi / lo -> layer-2 operand
+#pragma unroll
+    for (int c0 = 0; c0 < CH; c0 += 8) {
+      const int col = half * CH + c0;
+      float d[8], h[8], l[8];
+      tmem_ld8(tlane + colD + col, d);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const float e = elu_f(d[q] + b1s[col + q]);
+        h[q] = tf32_rna(e);
+        l[q] = tf32_rna(e - h[q]);
+      }
+      tmem_st8(tlane + colAhi + col, h);
+      tmem_st8(tlane + colAlo + col, l);
+    }
+    tc_sync_before_mma();
+    if (tid == 0) {
+      uint32_t acc = 0;
+#pragma unroll
+      for (int ps = 0; ps < 3; ++ps) {
+        const uint32_t acol = tb + (ps == 1 ? colAlo : colAhi);
+        const uint32_t bbase = smem_u32(ps == 2 ? W2lo : W2hi);
+#pragma unroll
+        for (int s = 0; s < NP / 8; ++s) {
+          umma_tf32_ts(tb + colD, acol + s * 8, umma_bdesc(bbase + s * 2 * LBO, LBO, SBO), idesc, acc);
+          acc = 1;
+        }
+      }
+      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(mb) : "memory");
+    }
+    ok = ok && mbar_wait(mb, phase);
+    phase ^= 1;
+    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+    // ---- epilogue 2: ELU(D + b2) . w3 + b3, zero diagonal / flag mask (ScoreNetwork_A.py:143-148), mirrored store
+    float dot = 0.f;
+#pragma unroll
+    for (int c0 = 0; c0 < CH; c0 += 8) {
+      const int col = half * CH + c0;
+      float d[8];
+      tmem_ld8(tlane + colD + col, d);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) dot = fmaf(elu_f(d[q] + b2s[col + q]), w3s[col + q], dot);
+    }
+    if (half == 1) part[row] = dot;
+    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+    __syncthreads();                        // also: every thread is done reading D before the next tile's MMA
+    if (half == 0) {
+      const int v = a.gmap[gp];
+      if (v >= 0) {
+        const int b = v >> 12, i = (v >> 6) & 63, j = v & 63;
+        const float* fl = a.flags + (int64_t)b * N;
+        const float s = (dot + part[row] + b3) * (fl[i] * fl[j]);
+        float* O = a.out + (int64_t)b * N * N;
+        O[i * N + j] = s;
+        O[j * N + i] = s;
+      }
+    }
+    ok = __syncthreads_and(ok);             // part[] is reused by the next tile; uniform loop exit
+  }
+  if (!ok && tid == 0) atomicExch(err, 1);
+  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;\n" ::"r"(tb) : "memory");
+}
+
+typedef void (*final_tc_fn)(FinalTriArgs, int*);
+static final_tc_fn pick_final_tc(int fdim, int* np, int* k1p) {
+  const int H = 2 * fdim, NP = (H + 15) & ~15, K1P = (fdim + 7) & ~7;
+  *np = NP;
+  *k1p = K1P;
+  if (NP == 96 && K1P == 48) return final_edge_tc_kernel<96, 48>;     // fdim 46 (ZINC250k: 2 + 8*5 + 4)
+  if (NP == 80 && K1P == 40) return final_edge_tc_kernel<80, 40>;     // fdim 38 (community_small, ego_small)
+  if (NP == 48 && K1P == 24) return final_edge_tc_kernel<48, 24>;     // fdim 22 (QM9)
+  if (NP == 112 && K1P == 56) return final_edge_tc_kernel<112, 56>;   // fdim 54 (ENZYMES, grid)
+  return nullptr;
+}
+
 typedef void (*final_tri_fn)(FinalTriArgs);
 static final_tri_fn pick_final_tri(int H, int* hp) {
   int opt = (H + 15) / 16;
@@ -988,6 +1253,23 @@ int launch_eval_fused(const gdss_ctx* ctx, const float* x, const float* adj, con
     ta.w1 = ctx->blob_a + p.fw[0]; ta.b1 = ctx->blob_a + p.fb[0]; ta.w2 = ctx->blob_a + p.fw[1]; ta.b2 = ctx->blob_a + p.fb[1];
     ta.w3 = ctx->blob_a + p.fw[2]; ta.b3 = ctx->blob_a + p.fb[2];
     ta.out = score_adj; ta.flags = flags; ta.N = N; ta.fdim = p.fdim; ta.H = 2 * p.fdim; ta.Hs = p.Hp;
+    const int64_t max_tiles = ((int64_t)B * (N * (N - 1) / 2) + 127) / 128;
+    int np = 0, k1p = 0;
+    final_tc_fn tfn = ctx->use_tc ? pick_final_tc(p.fdim, &np, &k1p) : nullptr;
+    if (tfn && max_tiles > 0) {
+      const size_t tsm = sizeof(float) * (2 * (size_t)(k1p * np + np * np) + 3 * np + 128) + 256;
+      if ((int)tsm <= ctx->smem_optin) {
+        e = cudaFuncSetAttribute(tfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsm);
+        if (e != cudaSuccess) return (int)e;
+        int grid = ctx->num_sms > 0 ? ctx->num_sms : 148;
+        if ((int64_t)grid > max_tiles) grid = (int)max_tiles;
+        int* errflag = reinterpret_cast<int*>(ws + w.off[R_META]) + 16;
+        tfn<<<grid, 256, tsm, st>>>(ta, errflag);
+        launched(K_FINAL_EDGE, st);
+        LAUNCH_CHECK();
+        return 0;
+      }
+    }
     int HP;
     final_tri_fn fn = pick_final_tri(ta.H, &HP);
     if (!fn) return GDSS_E_UNSUPPORTED;
@@ -999,7 +1281,6 @@ int launch_eval_fused(const gdss_ctx* ctx, const float* x, const float* adj, con
       e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsm);
       if (e != cudaSuccess) return (int)e;
     }
-    const int64_t max_tiles = ((int64_t)B * (N * (N - 1) / 2) + 127) / 128;
     if (max_tiles > 0) {
       fn<<<(unsigned)max_tiles, 256, fsm, st>>>(ta);
       launched(K_FINAL_EDGE, st);
