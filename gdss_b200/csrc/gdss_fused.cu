@@ -10,6 +10,7 @@
 //   global pixel index gp = poff[b] + p;   stackT[c][gp]  (c = channel of the concatenated stack)
 //   gmap[gp] = b << 12 | i << 6 | j        (-1 on the padding of the last 128-pixel tile)
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "gdss_common.cuh"
@@ -99,9 +100,13 @@ __global__ void __launch_bounds__(64) tri_map_kernel(const int* __restrict__ nef
 #define FUSED_MAX_LAYERS 8
 #define RMAX 8                 // rows per register-blocked item
 
+// The weights of one AttentionLayer are two contiguous runs of the blob (gdss_pack.cu lays a layer out as
+// wqkv, bqkv | mlp linears, multi_channel linears); each run is copied to shared memory by one bulk async copy
+// (TMA, cp.async.bulk) one phase group ahead of its use.  *_o = float offsets inside the run.
 struct FLayer {
   int c_in, c_out, f_in, f_in_p, attn, nlin, qkvw, need_edge, need_node;
-  const float *wqkv, *bqkv, *ew[3], *eb[3], *nw0, *nb0, *nw1, *nb1;
+  const float* blk_q; int q_floats, bq_o;                 // [c_in][f_in_p][qkvw] then biases [c_in][qkvw]
+  const float* blk_m; int m_floats, ew_o[3], eb_o[3], nw0_o, nb0_o, nw1_o, nb1_o;
 };
 
 struct FNet {
@@ -114,7 +119,7 @@ struct FNet {
 
 // float offsets into dynamic shared memory
 struct FSmem {
-  int fl, dinv, pix, x0, xb, xs, h1, wts, p0, pa, r1, qk, r2, total;
+  int fl, dinv, pix, x0, xb, xs, h1, wq, wm, p0, pa, r1, qk, r2, total;
   int LD, XS, QKS, PM, NBP, XSS;
 };
 
@@ -129,6 +134,7 @@ struct FusedArgs {
   const int* order;        // graph ids sorted by size bucket
   const int* meta;
   int bucket;
+  unsigned long long* prof;   // optional [16] per-phase clock cycles (thread 0 of every CTA, summed), else null
   int64_t pstride;
   int N, F;
   FSmem sl;
@@ -146,6 +152,30 @@ struct FastDiv {
 };
 
 enum { ACT_NONE = 0, ACT_ELU = 1, ACT_TANH = 2, ACT_TANH2 = 3 };
+
+DEVINL uint32_t sm_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// one elected thread: arm the mbarrier with the byte count and start the bulk global -> shared copy (TMA)
+DEVINL void tma_fetch(float* dst, const float* src, int floats, uint64_t* mbar) {
+  const uint32_t bytes = (uint32_t)floats * 4u;
+  asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");      // earlier generic reads of dst are done (after the CTA barrier)
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(sm_addr(mbar)), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(sm_addr(dst)),
+               "l"(src), "r"(bytes), "r"(sm_addr(mbar))
+               : "memory");
+}
+
+DEVINL void mbar_wait_parity(uint64_t* mbar, uint32_t parity) {
+  const uint32_t a = sm_addr(mbar);
+  uint32_t ok = 0;
+  while (!ok) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}\n"
+        : "=r"(ok)
+        : "r"(a), "r"(parity)
+        : "memory");
+  }
+}
 
 // ---------------------------------------------------------------------------------------
 // mm_rows: out[c][i][o] = act( (bias[c][o] + sum_k in[c][i][k] * W[c][k][o]) * rowscale[i] )
@@ -166,19 +196,29 @@ struct MM {
   int act, vec_out;
 };
 
-__device__ __noinline__ void mm_rows(const MM& m) {
+template <bool WS>          // WS: weights / biases in shared memory (staged by TMA), else global (read-only path)
+DEVINL float4 ldw4(const float* p) {
+  if (WS) return *reinterpret_cast<const float4*>(p);
+  return __ldg(reinterpret_cast<const float4*>(p));
+}
+
+template <bool WS>
+DEVINL void mm_rows_t(const MM& m) {
   const int tid = threadIdx.x, nt = blockDim.x;
   const int n = m.n, K4 = m.K, ldw = m.ldw, ldin = m.ldin;
   const int ogn = (m.o_hi - m.o_lo + 3) >> 2;
   const int pairs = m.C * ogn;
   if (pairs <= 0 || n <= 0) return;
-  // rows are dealt round-robin to IP row-partitions: RMAX rows per item when that already fills the CTA,
-  // otherwise as many partitions as fit in one round
-  int IP = (n + RMAX - 1) / RMAX;
-  if (pairs * IP < nt) {
-    int ip = nt / pairs;
-    if (ip > n) ip = n;
-    if (ip > IP) IP = ip;
+  // rows are dealt round-robin to IP row-partitions; pick the rows-per-item that minimises
+  // (rounds of the CTA) x (cost of one item); nt is a power of two
+  int IP = n, best = 1 << 30;
+  const int sh = 31 - __clz(nt);
+#pragma unroll
+  for (int rows = 1; rows <= RMAX; ++rows) {
+    const int ip = (n + rows - 1) / rows;
+    const int rounds = (pairs * ip + nt - 1) >> sh;
+    const int cost = rounds * (rows * 17 + 6);
+    if (cost < best) { best = cost; IP = ip; }
   }
   const FastDiv dpairs(pairs), dogn(ogn);
   for (int item = tid; item < pairs * IP; item += nt) {
@@ -191,18 +231,18 @@ __device__ __noinline__ void mm_rows(const MM& m) {
     const int rstep = IP * ldin;
     float acc[RMAX][4];
     {
-      const float4 bv = __ldg(reinterpret_cast<const float4*>(m.bias + c * m.b_cs + o));
+      const float4 bv = ldw4<WS>(m.bias + c * m.b_cs + o);
 #pragma unroll
       for (int r = 0; r < RMAX; ++r) { acc[r][0] = bv.x; acc[r][1] = bv.y; acc[r][2] = bv.z; acc[r][3] = bv.w; }
     }
     float4 wn[4];
 #pragma unroll
-    for (int kk = 0; kk < 4; ++kk) wn[kk] = __ldg(reinterpret_cast<const float4*>(Wc + (int64_t)kk * ldw));
+    for (int kk = 0; kk < 4; ++kk) wn[kk] = ldw4<WS>(Wc + (int64_t)kk * ldw);
     for (int k0 = 0; k0 < K4; k0 += 4) {
       const float4 w0 = wn[0], w1 = wn[1], w2 = wn[2], w3 = wn[3];
       if (k0 + 4 < K4) {                             // prefetch the next weight block (L2 latency)
 #pragma unroll
-        for (int kk = 0; kk < 4; ++kk) wn[kk] = __ldg(reinterpret_cast<const float4*>(Wc + (int64_t)(k0 + 4 + kk) * ldw));
+        for (int kk = 0; kk < 4; ++kk) wn[kk] = ldw4<WS>(Wc + (int64_t)(k0 + 4 + kk) * ldw);
       }
 #pragma unroll
       for (int r = 0; r < RMAX; ++r) {
@@ -244,6 +284,9 @@ __device__ __noinline__ void mm_rows(const MM& m) {
     }
   }
 }
+
+// out-of-line instance for the cold call sites (final node MLP, plain GCN layers): instruction-cache footprint
+__device__ __noinline__ void mm_rows(const MM& m) { mm_rows_t<false>(m); }
 
 // ---------------------------------------------------------------------------------------
 // DenseGCNConv pieces (layers.py:49-88) straight from the strict-upper-triangle planes.
@@ -305,35 +348,9 @@ DEVINL void gcn_ax(const float* pin, int PM, const float* dinv, int NBP, const f
   }
 }
 
-// stage the per-edge MLP of one AttentionLayer (attention.py:89, layers.py:96-153) into shared memory:
-//   W1 [2C][16] b1[16] | (W2 [16][16] b2[16]) | W3 [16][8] b3[8]      (hidden width 16, outputs padded to 8)
-DEVINL void stage_edge_weights(const FLayer& L, float* w) {
-  const int tid = threadIdx.x, nt = blockDim.x;
-  const int in1 = 2 * L.c_in;
-  int cur = 0;
-  for (int idx = tid; idx < in1 * 16; idx += nt) w[cur + idx] = __ldg(L.ew[0] + idx);
-  cur += in1 * 16;
-  for (int idx = tid; idx < 16; idx += nt) w[cur + idx] = __ldg(L.eb[0] + idx);
-  cur += 16;
-  if (L.nlin == 3) {
-    for (int idx = tid; idx < 256; idx += nt) w[cur + idx] = __ldg(L.ew[1] + idx);
-    cur += 256;
-    for (int idx = tid; idx < 16; idx += nt) w[cur + idx] = __ldg(L.eb[1] + idx);
-    cur += 16;
-  }
-  const float* wl = L.ew[L.nlin - 1];
-  const float* bl = L.eb[L.nlin - 1];
-  for (int idx = tid; idx < 128; idx += nt) {
-    const int u = idx >> 3, o = idx & 7;
-    w[cur + idx] = o < L.c_out ? __ldg(wl + u * L.c_out + o) : 0.f;
-  }
-  cur += 128;
-  for (int idx = tid; idx < 8; idx += nt) w[cur + idx] = idx < L.c_out ? __ldg(bl + idx) : 0.f;
-}
-
 // first linear of `multi_channel` (attention.py:90, :106): h1[i][0..16) = elu(b + cat_c V_c[i] . W), the K
 // range split over 4 adjacent lanes and reduced with shuffles (the layer has only n x 4 column groups)
-DEVINL void node_l1(const float* V, int K, const float* __restrict__ W, const float* __restrict__ b, int n, float* h1) {
+DEVINL void node_l1(const float* V, int K, const float* W, const float* b, int n, float* h1) {
   const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31;
   const int total = n * 16, kq = K >> 2;
   for (int base = tid - lane; base < total; base += nt) {
@@ -346,10 +363,10 @@ DEVINL void node_l1(const float* V, int K, const float* __restrict__ W, const fl
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int k = 0; k < kq; k += 4) {
       const float4 v = *reinterpret_cast<const float4*>(vr + k);
-      const float4 w0 = __ldg(reinterpret_cast<const float4*>(wr + (k + 0) * 16));
-      const float4 w1 = __ldg(reinterpret_cast<const float4*>(wr + (k + 1) * 16));
-      const float4 w2 = __ldg(reinterpret_cast<const float4*>(wr + (k + 2) * 16));
-      const float4 w3 = __ldg(reinterpret_cast<const float4*>(wr + (k + 3) * 16));
+      const float4 w0 = *reinterpret_cast<const float4*>(wr + (k + 0) * 16);
+      const float4 w1 = *reinterpret_cast<const float4*>(wr + (k + 1) * 16);
+      const float4 w2 = *reinterpret_cast<const float4*>(wr + (k + 2) * 16);
+      const float4 w3 = *reinterpret_cast<const float4*>(wr + (k + 3) * 16);
       acc.x = fmaf(v.x, w0.x, acc.x); acc.y = fmaf(v.x, w0.y, acc.y); acc.z = fmaf(v.x, w0.z, acc.z); acc.w = fmaf(v.x, w0.w, acc.w);
       acc.x = fmaf(v.y, w1.x, acc.x); acc.y = fmaf(v.y, w1.y, acc.y); acc.z = fmaf(v.y, w1.z, acc.z); acc.w = fmaf(v.y, w1.w, acc.w);
       acc.x = fmaf(v.z, w2.x, acc.x); acc.y = fmaf(v.z, w2.y, acc.y); acc.z = fmaf(v.z, w2.z, acc.z); acc.w = fmaf(v.z, w2.w, acc.w);
@@ -363,7 +380,7 @@ DEVINL void node_l1(const float* V, int K, const float* __restrict__ W, const fl
       acc.w += __shfl_xor_sync(0xffffffffu, acc.w, o);
     }
     if (valid && kp == 0) {
-      const float4 bv = __ldg(reinterpret_cast<const float4*>(b + 4 * og));
+      const float4 bv = *reinterpret_cast<const float4*>(b + 4 * og);
       *reinterpret_cast<float4*>(h1 + i * 16 + 4 * og) =
           make_float4(elu_f(acc.x + bv.x), elu_f(acc.y + bv.y), elu_f(acc.z + bv.z), elu_f(acc.w + bv.w));
     }
@@ -405,17 +422,18 @@ DEVINL void attention_maps(const float* qk, int QKS, const unsigned* pix, int C,
 //   in = [M_0..M_{C-1}, P_0..P_{C-1}] -> 16 -> (16) -> c_out ; out = 2 * mlp * flag_i * flag_j
 // pout may alias pin (each pixel is read completely before it is written).
 template <int NLIN>
-DEVINL void edge_mlp(const float* M, const float* pin, int PM, const unsigned* pix, const float* fl, const float* w,
-                     int C, int P, int c_out, float* pout, float* gout, int64_t gstride) {
+DEVINL void edge_mlp(const float* M, const float* pin, int PM, const unsigned* pix, const float* fl, const float* wm,
+                     const FLayer& L, int P, float* pout, float* gout, int64_t gstride) {
   const int tid = threadIdx.x, nt = blockDim.x;
   const int sub = tid & 1;
-  const int in1 = 2 * C;
-  const float* W1 = w + 8 * sub;
-  const float* b1 = w + in1 * 16;
-  const float* W2 = b1 + 16 + 8 * sub;
-  const float* b2 = b1 + 16 + 256;
-  const float* W3 = (NLIN == 3 ? b2 + 16 : b1 + 16) + 4 * sub;
-  const float* b3 = (NLIN == 3 ? b2 + 16 : b1 + 16) + 128;
+  const int C = L.c_in, c_out = L.c_out;
+  const float* W1 = wm + L.ew_o[0] + 8 * sub;                 // [2C][16]
+  const float* b1 = wm + L.eb_o[0];
+  const float* W2 = wm + L.ew_o[1] + 8 * sub;                 // [16][16] (NLIN == 3)
+  const float* b2 = wm + L.eb_o[1];
+  const float* W3 = wm + L.ew_o[NLIN - 1];                    // [16][c_out]
+  const float* b3 = wm + L.eb_o[NLIN - 1];
+  const bool act3 = 4 * sub < c_out;                          // this lane's 4 output columns exist
   const int total = 2 * P;
   for (int base = tid - (tid & 31); base < total; base += nt) {       // warp-uniform trip count
     const int idx = base + (tid & 31);
@@ -470,12 +488,15 @@ DEVINL void edge_mlp(const float* M, const float* pin, int PM, const unsigned* p
         hf[8 + u] = sub ? own : oth;
       }
     }
-    float4 o4 = *reinterpret_cast<const float4*>(b3 + 4 * sub);
+    float4 o4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (act3) {
+      o4 = *reinterpret_cast<const float4*>(b3 + 4 * sub);
 #pragma unroll
-    for (int u = 0; u < 16; ++u) {
-      const float v = hf[u];
-      const float4 wv = *reinterpret_cast<const float4*>(W3 + u * 8);
-      o4.x = fmaf(v, wv.x, o4.x); o4.y = fmaf(v, wv.y, o4.y); o4.z = fmaf(v, wv.z, o4.z); o4.w = fmaf(v, wv.w, o4.w);
+      for (int u = 0; u < 16; ++u) {
+        const float v = hf[u];
+        const float4 wv = *reinterpret_cast<const float4*>(W3 + u * c_out + 4 * sub);
+        o4.x = fmaf(v, wv.x, o4.x); o4.y = fmaf(v, wv.y, o4.y); o4.z = fmaf(v, wv.z, o4.z); o4.w = fmaf(v, wv.w, o4.w);
+      }
     }
     if (valid) {
       const unsigned ij = pix[p];
@@ -520,8 +541,20 @@ DEVINL void final_node_mlp(const FNet& net, const float* xs, int XSS, int n, con
 // ---------------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256, 2) fused_layers_kernel(const __grid_constant__ FusedArgs A) {
+#define PHASE(id)                                                      \
+  do {                                                                 \
+    if (A.prof && threadIdx.x == 0) {                                  \
+      const long long t__ = clock64();                                 \
+      atomicAdd(A.prof + (id), (unsigned long long)(t__ - tprev));     \
+      tprev = t__;                                                     \
+    }                                                                  \
+  } while (0)
+
+template <int NT, bool WSM>      // WSM: layer weights staged in shared memory by TMA (else read from global / L2)
+__global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1) fused_layers_kernel(const __grid_constant__ FusedArgs A) {
   extern __shared__ __align__(16) float sm[];
+  __shared__ __align__(8) uint64_t mbar_q, mbar_m;
+  long long tprev = A.prof ? clock64() : 0;
   if ((int)blockIdx.x >= A.meta[2 + A.bucket]) return;
   const int b = A.order[A.meta[5 + A.bucket] + blockIdx.x];
   const int n = A.neff[b];
@@ -538,7 +571,8 @@ __global__ void __launch_bounds__(256, 2) fused_layers_kernel(const __grid_const
   float* xb = sm + S.xb;
   float* xs = sm + S.xs;
   float* h1 = sm + S.h1;
-  float* wts = sm + S.wts;
+  float* wq = sm + S.wq;           // TMA-staged weights of the current layer: Q|K|V convolutions
+  float* wm = sm + S.wm;           //                                        : per-edge MLP + multi_channel MLP
   float* P0 = sm + S.p0;
   float* PA = sm + S.pa;
   float* R1 = sm + S.r1;           // dense A (power stack), then A.x products, then attention maps
@@ -547,6 +581,12 @@ __global__ void __launch_bounds__(256, 2) fused_layers_kernel(const __grid_const
   const int64_t gp0 = A.poff[b];
   const FastDiv dn(n), dP(P);
 
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(sm_addr(&mbar_q)) : "memory");
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(sm_addr(&mbar_m)) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  uint32_t ph_q = 0, ph_m = 0;      // mbarrier phase parities (one completion per fetched run)
   // ---- stage the graph
   for (int i = tid; i < N; i += nt) fl[i] = A.flags[(int64_t)b * N + i];
   for (int i = tid; i < n; i += nt) {
@@ -586,6 +626,7 @@ __global__ void __launch_bounds__(256, 2) fused_layers_kernel(const __grid_const
     }
   }
   __syncthreads();
+  PHASE(0);
 
   // ---- the two networks
   for (int which = 0; which < 2; ++which) {
@@ -630,35 +671,58 @@ __global__ void __launch_bounds__(256, 2) fused_layers_kernel(const __grid_const
     const float* xin = x0;
     int cbase = net.c_init;
     const float scale = 1.0f / sqrtf((float)h);
+    __syncthreads();                 // the previous network is done with wq / wm
+    if (WSM && tid == 0) {
+      tma_fetch(wq, net.L[0].blk_q, net.L[0].q_floats, &mbar_q);
+      tma_fetch(wm, net.L[0].blk_m, net.L[0].m_floats, &mbar_m);
+    }
     for (int l = 0; l < net.depth; ++l) {
       const FLayer& L = net.L[l];
       const int C = L.c_in, f = L.f_in, f8 = (f + 7) >> 3, attn = L.attn;
-      if (L.need_edge) stage_edge_weights(L, wts);
+      const bool more = l + 1 < net.depth;
       gcn_degrees(pin, PM, C, n, NBP, dinv, dn);
       __syncthreads();
+      PHASE(1);
       gcn_ax(pin, PM, dinv, NBP, xin, XS, C, n, f8, 8 * f8, R1, dn);
       __syncthreads();
+      PHASE(2);
       // Q | K | V = (A^ x) W + b for every channel (attention.py:32-34); V rows are stored [i][c][h]
-      mm_rows(mm_make(R1, n * 8 * f8, 8 * f8, f, L.wqkv, L.f_in_p * L.qkvw, L.qkvw, L.bqkv, L.qkvw, C, n, L.need_edge ? 0 : 2 * attn,
-                      L.need_node ? L.qkvw : 2 * attn, QK, n * QKS, QKS, 2 * attn, R2, h, C * h, nullptr, ACT_NONE));
+      if (WSM) {
+        mbar_wait_parity(&mbar_q, ph_q);
+        ph_q ^= 1;
+      }
+      const float* wqp = WSM ? wq : L.blk_q;
+      mm_rows_t<WSM>(mm_make(R1, n * 8 * f8, 8 * f8, f, wqp, L.f_in_p * L.qkvw, L.qkvw, wqp + L.bq_o, L.qkvw, C, n,
+                             L.need_edge ? 0 : 2 * attn, L.need_node ? L.qkvw : 2 * attn, QK, n * QKS, QKS, 2 * attn, R2, h, C * h,
+                             nullptr, ACT_NONE));
       __syncthreads();
+      if (WSM && more && tid == 0) tma_fetch(wq, net.L[l + 1].blk_q, net.L[l + 1].q_floats, &mbar_q);
+      PHASE(3);
       // x_out = tanh(mask_x(multi_channel(cat_c V_c)))  (attention.py:106-107), tanh'd twice in X_GMH (:81).
       // x_in is dead by now: layers >= 1 update xb in place (layer 0 reads x0, which the X network needs again)
-      if (L.need_node) node_l1(R2, C * h, L.nw0, L.nb0, n, h1);
+      if (WSM) {
+        mbar_wait_parity(&mbar_m, ph_m);
+        ph_m ^= 1;
+      }
+      const float* wmp = WSM ? wm : L.blk_m;
+      if (L.need_node) node_l1(R2, C * h, wmp + L.nw0_o, wmp + L.nb0_o, n, h1);
       if (L.need_edge) {
         if (attn == 16) attention_maps<4>(QK, QKS, pix, C, n, P, PM, scale, R1, dP);
         else attention_maps<8>(QK, QKS, pix, C, n, P, PM, scale, R1, dP);
       }
       __syncthreads();
+      PHASE(4);
       if (L.need_node)
-        mm_rows(mm_make(h1, 0, 16, 16, L.nw1, 0, h, L.nb1, 0, 1, n, 0, h, xb, 0, XS, h, nullptr, 0, 0, fl, isA ? ACT_TANH : ACT_TANH2));
+        mm_rows_t<WSM>(mm_make(h1, 0, 16, 16, wmp + L.nw1_o, 0, h, wmp + L.nb1_o, 0, 1, n, 0, h, xb, 0, XS, h, nullptr, 0, 0, fl,
+                               isA ? ACT_TANH : ACT_TANH2));
       if (L.need_edge) {
-        const bool keep = l + 1 < net.depth;                    // a later layer reads the planes
         float* gout = isA ? A.stackT + (int64_t)cbase * A.pstride + gp0 : nullptr;
-        if (L.nlin == 3) edge_mlp<3>(R1, pin, PM, pix, fl, wts, C, P, L.c_out, keep ? PA : nullptr, gout, A.pstride);
-        else edge_mlp<2>(R1, pin, PM, pix, fl, wts, C, P, L.c_out, keep ? PA : nullptr, gout, A.pstride);
+        if (L.nlin == 3) edge_mlp<3>(R1, pin, PM, pix, fl, wmp, L, P, more ? PA : nullptr, gout, A.pstride);
+        else edge_mlp<2>(R1, pin, PM, pix, fl, wmp, L, P, more ? PA : nullptr, gout, A.pstride);
       }
       __syncthreads();
+      if (WSM && more && tid == 0) tma_fetch(wm, net.L[l + 1].blk_m, net.L[l + 1].m_floats, &mbar_m);
+      PHASE(5);
       if (L.need_node) {
         if (!isA) {
           for (int idx = tid; idx < n * h; idx += nt) {
@@ -674,6 +738,7 @@ __global__ void __launch_bounds__(256, 2) fused_layers_kernel(const __grid_const
     if (!isA) {
       __syncthreads();
       final_node_mlp(net, xs, XSS, n, fl, hA, hB, A.raw_x + (int64_t)b * N * F, F);
+      PHASE(6);
     }
   }
 }
@@ -1093,7 +1158,7 @@ static bool net_fusable(const NetPlan& p) {
   if (p.nlin < 2 || p.nlin > 3) return false;
   for (int l = 0; l < p.depth; ++l) {
     const LayerPlan& L = p.layers[l];
-    if (L.hid != 16 || L.c_in > 8 || L.c_out > 8) return false;
+    if (L.hid != 16 || L.c_in > 8 || L.c_out > 8 || (L.c_out & 3)) return false;
   }
   return true;
 }
@@ -1114,16 +1179,21 @@ static void fill_net(const NetPlan& p, const float* blob, FNet* f) {
     o.c_in = L.c_in; o.c_out = L.c_out; o.f_in = L.f_in; o.f_in_p = L.f_in_p; o.attn = L.attn; o.nlin = L.nlin; o.qkvw = L.qkvw;
     o.need_edge = (p.type == GDSS_NET_A || !last) ? 1 : 0;   // X_GMH: the last layer's adj_out is never read
     o.need_node = (p.type != GDSS_NET_A || !last) ? 1 : 0;   // A: the last layer's x_out is never read
-    o.wqkv = blob + L.wqkv; o.bqkv = blob + L.bqkv;
-    for (int i = 0; i < L.nlin && i < 3; ++i) { o.ew[i] = blob + L.ew[i]; o.eb[i] = blob + L.eb[i]; }
-    o.nw0 = blob + L.nw[0]; o.nb0 = blob + L.nb[0]; o.nw1 = blob + L.nw[1]; o.nb1 = blob + L.nb[1];
+    o.blk_q = blob + L.wqkv;
+    o.bq_o = (int)(L.bqkv - L.wqkv);
+    o.q_floats = (int)(L.ew[0] - L.wqkv);                        // wqkv + bqkv (both padded to 4 floats)
+    o.blk_m = blob + L.ew[0];
+    for (int i = 0; i < L.nlin && i < 3; ++i) { o.ew_o[i] = (int)(L.ew[i] - L.ew[0]); o.eb_o[i] = (int)(L.eb[i] - L.ew[0]); }
+    o.nw0_o = (int)(L.nw[0] - L.ew[0]); o.nb0_o = (int)(L.nb[0] - L.ew[0]);
+    o.nw1_o = (int)(L.nw[1] - L.ew[0]); o.nb1_o = (int)(L.nb[1] - L.ew[0]);
+    o.m_floats = (int)(L.nb[1] - L.ew[0]) + ((L.nhid + 3) & ~3);
   }
   for (int i = 0; i < 3; ++i) { f->fw[i] = blob + p.fw[i]; f->fb[i] = blob + p.fb[i]; }
 }
 
 // shared-memory plan for graphs of at most NB nodes; returns bytes (or -1 when the regions cannot host the
 // dense adjacency alias)
-static int64_t plan_smem(const gdss_ctx* ctx, int NB, FSmem* s) {
+static int64_t plan_smem(const gdss_ctx* ctx, int NB, FSmem* s, bool wsm = true) {
   const NetPlan* nets[2] = {ctx->has_a ? &ctx->pa : nullptr, ctx->has_x ? &ctx->px : nullptr};
   int Cmax = 1, hmax = 8, amax = 0, fmax = (ctx->F + 7) & ~7, fdx = 4, Hx = 0, cinit = 1;
   for (int k = 0; k < 2; ++k) {
@@ -1157,7 +1227,19 @@ static int64_t plan_smem(const gdss_ctx* ctx, int NB, FSmem* s) {
   s->xb = take(NB * s->XS);
   s->xs = take(NB * s->XSS);
   s->h1 = take(NB * 16);
-  s->wts = take(2 * Cmax * 16 + 16 + 256 + 16 + 128 + 8);
+  int wqf = 4, wmf = 4;
+  for (int k = 0; k < 2; ++k) {
+    const NetPlan* p = nets[k];
+    if (!p || p->type == GDSS_NET_X) continue;
+    for (int l = 0; l < p->depth; ++l) {
+      const LayerPlan& L = p->layers[l];
+      const int q = (int)(L.ew[0] - L.wqkv), m = (int)(L.nb[1] - L.ew[0]) + ((L.nhid + 3) & ~3);
+      wqf = wqf > q ? wqf : q;
+      wmf = wmf > m ? wmf : m;
+    }
+  }
+  s->wq = take(wsm ? wqf : 4);
+  s->wm = take(wsm ? wmf : 4);
   s->p0 = take(cinit * s->PM);
   s->pa = take(Cmax * s->PM);
   int r1 = Cmax * NB * fmax;                         // A.x products [C][n][f rounded up to 8]
@@ -1173,10 +1255,10 @@ static int64_t plan_smem(const gdss_ctx* ctx, int NB, FSmem* s) {
 }
 
 // size buckets of the per-graph kernel (its shared memory is sized by the largest graph of a launch):
-// graphs of at most 24 / 32 / N nodes; returns the number of buckets and their upper bounds
+// graphs of at most 23 / 32 / N nodes; returns the number of buckets and their upper bounds
 static int size_buckets(int N, int nb[3]) {
   int k = 0;
-  if (N > 24) nb[k++] = 24;
+  if (N > 23) nb[k++] = 23;
   if (N > 32) nb[k++] = 32;
   nb[k++] = N;
   return k;
@@ -1226,6 +1308,7 @@ int launch_eval_fused(const gdss_ctx* ctx, const float* x, const float* adj, con
   fa.poff = reinterpret_cast<const int*>(ws + w.off[R_POFF]);
   fa.pstride = w.pstride;
   fa.N = N; fa.F = ctx->F;
+  fa.prof = getenv("GDSS_PHASE_PROF") ? reinterpret_cast<unsigned long long*>(ws + w.off[R_META] + 128) : nullptr;
   fa.order = reinterpret_cast<const int*>(ws + w.off[R_ORDER]);
   fa.meta = reinterpret_cast<const int*>(ws + w.off[R_META]);
   int nb[3];
@@ -1234,12 +1317,27 @@ int launch_eval_fused(const gdss_ctx* ctx, const float* x, const float* adj, con
     // one launch per size bucket: B CTAs, those beyond the bucket's population exit at once (the counts live
     // on the device; no host synchronisation)
     fa.bucket = k;
-    const int64_t smem = plan_smem(ctx, nb[k], &fa.sl);
-    if (smem <= 0 || smem > ctx->smem_optin) return GDSS_E_UNSUPPORTED;
-    cudaError_t e = cudaFuncSetAttribute(fused_layers_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
-    const int threads = nb[k] <= 12 ? 128 : 256;
-    fused_layers_kernel<<<B, threads, smem, st>>>(fa);
+    // Preferred: layer weights staged in shared memory by TMA with two CTAs of 256 threads per SM; if only the
+    // weight-less plan fits twice, read the weights through L2 instead; the largest graphs run one CTA of 512.
+    const int limit2 = (227 * 1024) / 2 - 1024;
+    int64_t smem = plan_smem(ctx, nb[k], &fa.sl, true);
+    cudaError_t e;
+    if (smem <= limit2) {
+      e = cudaFuncSetAttribute(fused_layers_kernel<256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return (int)e;
+      fused_layers_kernel<256, true><<<B, nb[k] <= 12 ? 128 : 256, smem, st>>>(fa);
+    } else if (plan_smem(ctx, nb[k], &fa.sl, false) <= limit2) {
+      smem = plan_smem(ctx, nb[k], &fa.sl, false);
+      e = cudaFuncSetAttribute(fused_layers_kernel<256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return (int)e;
+      fused_layers_kernel<256, false><<<B, 256, smem, st>>>(fa);
+    } else {
+      smem = plan_smem(ctx, nb[k], &fa.sl, true);
+      if (smem <= 0 || smem > ctx->smem_optin) return GDSS_E_UNSUPPORTED;
+      e = cudaFuncSetAttribute(fused_layers_kernel<512, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return (int)e;
+      fused_layers_kernel<512, true><<<B, 512, smem, st>>>(fa);
+    }
     launched(K_FUSED, st);
     LAUNCH_CHECK();
   }
