@@ -120,7 +120,7 @@ struct FNet {
 // float offsets into dynamic shared memory
 struct FSmem {
   int fl, dinv, pix, x0, xb, xs, h1, wq, wm, p0, pa, r1, qk, r2, total;
-  int LD, XS, QKS, PM, NBP, XSS;
+  int LD, XS, QKS, PM, NBP, XSS, RS;     // RS: per-channel stride of R1 (A.x rows / attention maps of one channel)
 };
 
 struct FusedArgs {
@@ -152,6 +152,12 @@ struct FastDiv {
 };
 
 enum { ACT_NONE = 0, ACT_ELU = 1, ACT_TANH = 2, ACT_TANH2 = 3 };
+
+// Blackwell packed FP32: one FFMA2 issues two independent IEEE fp32 FMAs (same results as two scalar FMAs)
+DEVINL float2 fma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+DEVINL float2 dup2(float v) { return make_float2(v, v); }
+DEVINL float2 lo2(const float4& v) { return make_float2(v.x, v.y); }
+DEVINL float2 hi2(const float4& v) { return make_float2(v.z, v.w); }
 
 DEVINL uint32_t sm_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -229,18 +235,18 @@ DEVINL void mm_rows_t(const MM& m) {
     const float* inc = m.in + c * m.in_cs + ip * ldin;
     const int rcnt = (n - ip + IP - 1) / IP;       // rows of this item: ip, ip + IP, ...
     const int rstep = IP * ldin;
-    float acc[RMAX][4];
+    float2 acc[RMAX][2];
     {
       const float4 bv = ldw4<WS>(m.bias + c * m.b_cs + o);
 #pragma unroll
-      for (int r = 0; r < RMAX; ++r) { acc[r][0] = bv.x; acc[r][1] = bv.y; acc[r][2] = bv.z; acc[r][3] = bv.w; }
+      for (int r = 0; r < RMAX; ++r) { acc[r][0] = lo2(bv); acc[r][1] = hi2(bv); }
     }
     float4 wn[4];
 #pragma unroll
     for (int kk = 0; kk < 4; ++kk) wn[kk] = ldw4<WS>(Wc + (int64_t)kk * ldw);
     for (int k0 = 0; k0 < K4; k0 += 4) {
       const float4 w0 = wn[0], w1 = wn[1], w2 = wn[2], w3 = wn[3];
-      if (k0 + 4 < K4) {                             // prefetch the next weight block (L2 latency)
+      if (k0 + 4 < K4) {                             // prefetch the next weight block
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk) wn[kk] = ldw4<WS>(Wc + (int64_t)(k0 + 4 + kk) * ldw);
       }
@@ -248,10 +254,10 @@ DEVINL void mm_rows_t(const MM& m) {
       for (int r = 0; r < RMAX; ++r) {
         if (r >= rcnt) break;
         const float4 a = *reinterpret_cast<const float4*>(inc + r * rstep + k0);
-        acc[r][0] = fmaf(a.x, w0.x, acc[r][0]); acc[r][1] = fmaf(a.x, w0.y, acc[r][1]); acc[r][2] = fmaf(a.x, w0.z, acc[r][2]); acc[r][3] = fmaf(a.x, w0.w, acc[r][3]);
-        acc[r][0] = fmaf(a.y, w1.x, acc[r][0]); acc[r][1] = fmaf(a.y, w1.y, acc[r][1]); acc[r][2] = fmaf(a.y, w1.z, acc[r][2]); acc[r][3] = fmaf(a.y, w1.w, acc[r][3]);
-        acc[r][0] = fmaf(a.z, w2.x, acc[r][0]); acc[r][1] = fmaf(a.z, w2.y, acc[r][1]); acc[r][2] = fmaf(a.z, w2.z, acc[r][2]); acc[r][3] = fmaf(a.z, w2.w, acc[r][3]);
-        acc[r][0] = fmaf(a.w, w3.x, acc[r][0]); acc[r][1] = fmaf(a.w, w3.y, acc[r][1]); acc[r][2] = fmaf(a.w, w3.z, acc[r][2]); acc[r][3] = fmaf(a.w, w3.w, acc[r][3]);
+        acc[r][0] = fma2(dup2(a.x), lo2(w0), acc[r][0]); acc[r][1] = fma2(dup2(a.x), hi2(w0), acc[r][1]);
+        acc[r][0] = fma2(dup2(a.y), lo2(w1), acc[r][0]); acc[r][1] = fma2(dup2(a.y), hi2(w1), acc[r][1]);
+        acc[r][0] = fma2(dup2(a.z), lo2(w2), acc[r][0]); acc[r][1] = fma2(dup2(a.z), hi2(w2), acc[r][1]);
+        acc[r][0] = fma2(dup2(a.w), lo2(w3), acc[r][0]); acc[r][1] = fma2(dup2(a.w), hi2(w3), acc[r][1]);
       }
     }
     const int act = m.act;
@@ -264,10 +270,10 @@ DEVINL void mm_rows_t(const MM& m) {
       if (r >= rcnt) break;
       const int i = ip + r * IP;
       const float rs = m.rowscale ? m.rowscale[i] : 1.f;
-      float v[4];
+      float v[4] = {acc[r][0].x, acc[r][0].y, acc[r][1].x, acc[r][1].y};
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
-        v[q] = acc[r][q] * rs;
+        v[q] = v[q] * rs;
         if (act == ACT_ELU) v[q] = elu_f(v[q]);
         else if (act >= ACT_TANH) {
           v[q] = tanh_fast(v[q]);
@@ -312,7 +318,7 @@ DEVINL void gcn_degrees(const float* pin, int PM, int C, int n, int NBP, float* 
 
 // ax[c][i][8g..8g+7] = d_i * sum_j A~_c(i,j) d_j x[j][8g..8g+7]
 DEVINL void gcn_ax(const float* pin, int PM, const float* dinv, int NBP, const float* x, int ldx, int C, int n, int f8,
-                   int ldax, float* ax, const FastDiv& dn) {
+                   int ldax, float* ax, int cs, const FastDiv& dn) {
   const int tid = threadIdx.x, nt = blockDim.x;
   const FastDiv df(f8);
   for (int item = tid; item < C * n * f8; item += nt) {
@@ -322,36 +328,42 @@ DEVINL void gcn_ax(const float* pin, int PM, const float* dinv, int NBP, const f
     const float* dv = dinv + c * NBP;
     const float* xg = x + 8 * g;
     const float di = dv[i];
-    float acc[8];
+    float2 acc[4];
     {
       const float4 a = *reinterpret_cast<const float4*>(xg + i * ldx);
       const float4 b = *reinterpret_cast<const float4*>(xg + i * ldx + 4);
-      acc[0] = di * a.x; acc[1] = di * a.y; acc[2] = di * a.z; acc[3] = di * a.w;
-      acc[4] = di * b.x; acc[5] = di * b.y; acc[6] = di * b.z; acc[7] = di * b.w;
+      const float2 d2 = dup2(di);
+      acc[0] = __fmul2_rn(d2, lo2(a)); acc[1] = __fmul2_rn(d2, hi2(a));
+      acc[2] = __fmul2_rn(d2, lo2(b)); acc[3] = __fmul2_rn(d2, hi2(b));
     }
+    // entries (j, i), j < i: index step n - j - 2; then the contiguous run (i, j), j > i
     int idx = i - 1;
-    for (int j = 0; j < n; ++j) {
-      if (j == i) {
-        idx = i * (2 * n - i - 1) / 2;
-        continue;
-      }
-      const float w = pl[idx] * dv[j];
-      idx += j < i ? n - j - 2 : 1;
+    for (int j = 0; j < i; ++j) {
+      const float2 w = dup2(pl[idx] * dv[j]);
+      idx += n - j - 2;
       const float4 a = *reinterpret_cast<const float4*>(xg + j * ldx);
       const float4 b = *reinterpret_cast<const float4*>(xg + j * ldx + 4);
-      acc[0] = fmaf(w, a.x, acc[0]); acc[1] = fmaf(w, a.y, acc[1]); acc[2] = fmaf(w, a.z, acc[2]); acc[3] = fmaf(w, a.w, acc[3]);
-      acc[4] = fmaf(w, b.x, acc[4]); acc[5] = fmaf(w, b.y, acc[5]); acc[6] = fmaf(w, b.z, acc[6]); acc[7] = fmaf(w, b.w, acc[7]);
+      acc[0] = fma2(w, lo2(a), acc[0]); acc[1] = fma2(w, hi2(a), acc[1]);
+      acc[2] = fma2(w, lo2(b), acc[2]); acc[3] = fma2(w, hi2(b), acc[3]);
     }
-    float* o = ax + (c * n + i) * ldax + 8 * g;
-    *reinterpret_cast<float4*>(o) = make_float4(acc[0] * di, acc[1] * di, acc[2] * di, acc[3] * di);
-    *reinterpret_cast<float4*>(o + 4) = make_float4(acc[4] * di, acc[5] * di, acc[6] * di, acc[7] * di);
+    idx = i * (2 * n - i - 1) / 2;
+    for (int j = i + 1; j < n; ++j) {
+      const float2 w = dup2(pl[idx++] * dv[j]);
+      const float4 a = *reinterpret_cast<const float4*>(xg + j * ldx);
+      const float4 b = *reinterpret_cast<const float4*>(xg + j * ldx + 4);
+      acc[0] = fma2(w, lo2(a), acc[0]); acc[1] = fma2(w, hi2(a), acc[1]);
+      acc[2] = fma2(w, lo2(b), acc[2]); acc[3] = fma2(w, hi2(b), acc[3]);
+    }
+    float* o = ax + c * cs + i * ldax + 8 * g;
+    *reinterpret_cast<float4*>(o) = make_float4(acc[0].x * di, acc[0].y * di, acc[1].x * di, acc[1].y * di);
+    *reinterpret_cast<float4*>(o + 4) = make_float4(acc[2].x * di, acc[2].y * di, acc[3].x * di, acc[3].y * di);
   }
 }
 
 // first linear of `multi_channel` (attention.py:90, :106): h1[i][0..16) = elu(b + cat_c V_c[i] . W), the K
 // range split over 4 adjacent lanes and reduced with shuffles (the layer has only n x 4 column groups)
-DEVINL void node_l1(const float* V, int K, const float* W, const float* b, int n, float* h1) {
-  const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31;
+DEVINL void node_l1(const float* V, int K, const float* W, const float* b, int n, float* h1, int tid, int nt) {
+  const int lane = tid & 31;
   const int total = n * 16, kq = K >> 2;
   for (int base = tid - lane; base < total; base += nt) {
     const int idx = base + lane;
@@ -360,18 +372,19 @@ DEVINL void node_l1(const float* V, int K, const float* W, const float* b, int n
     const int i = id2 >> 4, og = (id2 >> 2) & 3, kp = id2 & 3;
     const float* vr = V + i * K + kp * kq;
     const float* wr = W + (int64_t)(kp * kq) * 16 + 4 * og;
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    float2 a0 = make_float2(0.f, 0.f), a1 = make_float2(0.f, 0.f);
     for (int k = 0; k < kq; k += 4) {
       const float4 v = *reinterpret_cast<const float4*>(vr + k);
       const float4 w0 = *reinterpret_cast<const float4*>(wr + (k + 0) * 16);
       const float4 w1 = *reinterpret_cast<const float4*>(wr + (k + 1) * 16);
       const float4 w2 = *reinterpret_cast<const float4*>(wr + (k + 2) * 16);
       const float4 w3 = *reinterpret_cast<const float4*>(wr + (k + 3) * 16);
-      acc.x = fmaf(v.x, w0.x, acc.x); acc.y = fmaf(v.x, w0.y, acc.y); acc.z = fmaf(v.x, w0.z, acc.z); acc.w = fmaf(v.x, w0.w, acc.w);
-      acc.x = fmaf(v.y, w1.x, acc.x); acc.y = fmaf(v.y, w1.y, acc.y); acc.z = fmaf(v.y, w1.z, acc.z); acc.w = fmaf(v.y, w1.w, acc.w);
-      acc.x = fmaf(v.z, w2.x, acc.x); acc.y = fmaf(v.z, w2.y, acc.y); acc.z = fmaf(v.z, w2.z, acc.z); acc.w = fmaf(v.z, w2.w, acc.w);
-      acc.x = fmaf(v.w, w3.x, acc.x); acc.y = fmaf(v.w, w3.y, acc.y); acc.z = fmaf(v.w, w3.z, acc.z); acc.w = fmaf(v.w, w3.w, acc.w);
+      a0 = fma2(dup2(v.x), lo2(w0), a0); a1 = fma2(dup2(v.x), hi2(w0), a1);
+      a0 = fma2(dup2(v.y), lo2(w1), a0); a1 = fma2(dup2(v.y), hi2(w1), a1);
+      a0 = fma2(dup2(v.z), lo2(w2), a0); a1 = fma2(dup2(v.z), hi2(w2), a1);
+      a0 = fma2(dup2(v.w), lo2(w3), a0); a1 = fma2(dup2(v.w), hi2(w3), a1);
     }
+    float4 acc = make_float4(a0.x, a0.y, a1.x, a1.y);
 #pragma unroll
     for (int o = 1; o <= 2; o <<= 1) {
       acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o);
@@ -390,7 +403,7 @@ DEVINL void node_l1(const float* V, int K, const float* W, const float* b, int n
 // attention maps (attention.py:35-49): M[c][p] = mean over the 4 heads and over the two orientations of
 // tanh(Q_h . K_h / sqrt(out_dim)); HD = head width (attn_dim / 4)
 template <int HD>
-DEVINL void attention_maps(const float* qk, int QKS, const unsigned* pix, int C, int n, int P, int PM, float scale, float* M, const FastDiv& dP) {
+DEVINL void attention_maps(const float* qk, int QKS, const unsigned* pix, int C, int n, int P, int MS, float scale, float* M, const FastDiv& dP) {
   const int tid = threadIdx.x, nt = blockDim.x;
   constexpr int AT = 4 * HD;
   for (int item = tid; item < C * P; item += nt) {
@@ -402,19 +415,19 @@ DEVINL void attention_maps(const float* qk, int QKS, const unsigned* pix, int C,
     float m = 0.f;
 #pragma unroll
     for (int h = 0; h < 4; ++h) {
-      float s1 = 0.f, s2 = 0.f;
+      float2 p1 = make_float2(0.f, 0.f), p2 = make_float2(0.f, 0.f);
 #pragma unroll
       for (int d = 0; d < HD; d += 4) {
         const float4 a1 = *reinterpret_cast<const float4*>(qi + h * HD + d);
         const float4 b1 = *reinterpret_cast<const float4*>(qj + AT + h * HD + d);
         const float4 a2 = *reinterpret_cast<const float4*>(qj + h * HD + d);
         const float4 b2 = *reinterpret_cast<const float4*>(qi + AT + h * HD + d);
-        s1 = fmaf(a1.x, b1.x, s1); s1 = fmaf(a1.y, b1.y, s1); s1 = fmaf(a1.z, b1.z, s1); s1 = fmaf(a1.w, b1.w, s1);
-        s2 = fmaf(a2.x, b2.x, s2); s2 = fmaf(a2.y, b2.y, s2); s2 = fmaf(a2.z, b2.z, s2); s2 = fmaf(a2.w, b2.w, s2);
+        p1 = fma2(lo2(a1), lo2(b1), p1); p1 = fma2(hi2(a1), hi2(b1), p1);
+        p2 = fma2(lo2(a2), lo2(b2), p2); p2 = fma2(hi2(a2), hi2(b2), p2);
       }
-      m += tanh_fast(s1 * scale) + tanh_fast(s2 * scale);
+      m += tanh_fast((p1.x + p1.y) * scale) + tanh_fast((p2.x + p2.y) * scale);
     }
-    M[c * PM + p] = m * 0.125f;
+    M[c * MS + p] = m * 0.125f;
   }
 }
 
@@ -422,9 +435,8 @@ DEVINL void attention_maps(const float* qk, int QKS, const unsigned* pix, int C,
 //   in = [M_0..M_{C-1}, P_0..P_{C-1}] -> 16 -> (16) -> c_out ; out = 2 * mlp * flag_i * flag_j
 // pout may alias pin (each pixel is read completely before it is written).
 template <int NLIN>
-DEVINL void edge_mlp(const float* M, const float* pin, int PM, const unsigned* pix, const float* fl, const float* wm,
-                     const FLayer& L, int P, float* pout, float* gout, int64_t gstride) {
-  const int tid = threadIdx.x, nt = blockDim.x;
+DEVINL void edge_mlp(const float* M, int MS, const float* pin, int PM, const unsigned* pix, const float* fl, const float* wm,
+                     const FLayer& L, int P, float* pout, float* gout, int64_t gstride, int tid, int nt) {
   const int sub = tid & 1;
   const int C = L.c_in, c_out = L.c_out;
   const float* W1 = wm + L.ew_o[0] + 8 * sub;                 // [2C][16]
@@ -439,31 +451,31 @@ DEVINL void edge_mlp(const float* M, const float* pin, int PM, const unsigned* p
     const int idx = base + (tid & 31);
     const bool valid = idx < total;
     const int p = valid ? (idx >> 1) : (P - 1);
-    float h[8];
+    float2 h2[4];
     {
       const float4 ba = *reinterpret_cast<const float4*>(b1 + 8 * sub);
       const float4 bb = *reinterpret_cast<const float4*>(b1 + 8 * sub + 4);
-      h[0] = ba.x; h[1] = ba.y; h[2] = ba.z; h[3] = ba.w; h[4] = bb.x; h[5] = bb.y; h[6] = bb.z; h[7] = bb.w;
+      h2[0] = lo2(ba); h2[1] = hi2(ba); h2[2] = lo2(bb); h2[3] = hi2(bb);
     }
     for (int k = 0; k < C; ++k) {
-      const float v = M[k * PM + p];
+      const float v = M[k * MS + p];
       const float4 wa = *reinterpret_cast<const float4*>(W1 + k * 16);
       const float4 wb = *reinterpret_cast<const float4*>(W1 + k * 16 + 4);
-      h[0] = fmaf(v, wa.x, h[0]); h[1] = fmaf(v, wa.y, h[1]); h[2] = fmaf(v, wa.z, h[2]); h[3] = fmaf(v, wa.w, h[3]);
-      h[4] = fmaf(v, wb.x, h[4]); h[5] = fmaf(v, wb.y, h[5]); h[6] = fmaf(v, wb.z, h[6]); h[7] = fmaf(v, wb.w, h[7]);
+      h2[0] = fma2(dup2(v), lo2(wa), h2[0]); h2[1] = fma2(dup2(v), hi2(wa), h2[1]);
+      h2[2] = fma2(dup2(v), lo2(wb), h2[2]); h2[3] = fma2(dup2(v), hi2(wb), h2[3]);
     }
     for (int k = 0; k < C; ++k) {
       const float v = pin[k * PM + p];
       const float4 wa = *reinterpret_cast<const float4*>(W1 + (C + k) * 16);
       const float4 wb = *reinterpret_cast<const float4*>(W1 + (C + k) * 16 + 4);
-      h[0] = fmaf(v, wa.x, h[0]); h[1] = fmaf(v, wa.y, h[1]); h[2] = fmaf(v, wa.z, h[2]); h[3] = fmaf(v, wa.w, h[3]);
-      h[4] = fmaf(v, wb.x, h[4]); h[5] = fmaf(v, wb.y, h[5]); h[6] = fmaf(v, wb.z, h[6]); h[7] = fmaf(v, wb.w, h[7]);
+      h2[0] = fma2(dup2(v), lo2(wa), h2[0]); h2[1] = fma2(dup2(v), hi2(wa), h2[1]);
+      h2[2] = fma2(dup2(v), lo2(wb), h2[2]); h2[3] = fma2(dup2(v), hi2(wb), h2[3]);
     }
     __syncwarp();                     // both lanes of the pixel have read their inputs (in-place update below)
     float hf[16];
 #pragma unroll
     for (int u = 0; u < 8; ++u) {
-      const float own = elu_f(h[u]);
+      const float own = elu_f((u & 1) ? h2[u >> 1].y : h2[u >> 1].x);
       const float oth = __shfl_xor_sync(0xffffffffu, own, 1);
       hf[u] = sub ? oth : own;
       hf[8 + u] = sub ? own : oth;
@@ -471,18 +483,18 @@ DEVINL void edge_mlp(const float* M, const float* pin, int PM, const unsigned* p
     if (NLIN == 3) {
       const float4 ba = *reinterpret_cast<const float4*>(b2 + 8 * sub);
       const float4 bb = *reinterpret_cast<const float4*>(b2 + 8 * sub + 4);
-      h[0] = ba.x; h[1] = ba.y; h[2] = ba.z; h[3] = ba.w; h[4] = bb.x; h[5] = bb.y; h[6] = bb.z; h[7] = bb.w;
+      h2[0] = lo2(ba); h2[1] = hi2(ba); h2[2] = lo2(bb); h2[3] = hi2(bb);
 #pragma unroll
       for (int u = 0; u < 16; ++u) {
         const float v = hf[u];
         const float4 wa = *reinterpret_cast<const float4*>(W2 + u * 16);
         const float4 wb = *reinterpret_cast<const float4*>(W2 + u * 16 + 4);
-        h[0] = fmaf(v, wa.x, h[0]); h[1] = fmaf(v, wa.y, h[1]); h[2] = fmaf(v, wa.z, h[2]); h[3] = fmaf(v, wa.w, h[3]);
-        h[4] = fmaf(v, wb.x, h[4]); h[5] = fmaf(v, wb.y, h[5]); h[6] = fmaf(v, wb.z, h[6]); h[7] = fmaf(v, wb.w, h[7]);
+        h2[0] = fma2(dup2(v), lo2(wa), h2[0]); h2[1] = fma2(dup2(v), hi2(wa), h2[1]);
+        h2[2] = fma2(dup2(v), lo2(wb), h2[2]); h2[3] = fma2(dup2(v), hi2(wb), h2[3]);
       }
 #pragma unroll
       for (int u = 0; u < 8; ++u) {
-        const float own = elu_f(h[u]);
+        const float own = elu_f((u & 1) ? h2[u >> 1].y : h2[u >> 1].x);
         const float oth = __shfl_xor_sync(0xffffffffu, own, 1);
         hf[u] = sub ? oth : own;
         hf[8 + u] = sub ? own : oth;
@@ -490,13 +502,15 @@ DEVINL void edge_mlp(const float* M, const float* pin, int PM, const unsigned* p
     }
     float4 o4 = make_float4(0.f, 0.f, 0.f, 0.f);
     if (act3) {
-      o4 = *reinterpret_cast<const float4*>(b3 + 4 * sub);
+      const float4 b4 = *reinterpret_cast<const float4*>(b3 + 4 * sub);
+      float2 oa = lo2(b4), ob = hi2(b4);
 #pragma unroll
       for (int u = 0; u < 16; ++u) {
-        const float v = hf[u];
         const float4 wv = *reinterpret_cast<const float4*>(W3 + u * c_out + 4 * sub);
-        o4.x = fmaf(v, wv.x, o4.x); o4.y = fmaf(v, wv.y, o4.y); o4.z = fmaf(v, wv.z, o4.z); o4.w = fmaf(v, wv.w, o4.w);
+        oa = fma2(dup2(hf[u]), lo2(wv), oa);
+        ob = fma2(dup2(hf[u]), hi2(wv), ob);
       }
+      o4 = make_float4(oa.x, oa.y, ob.x, ob.y);
     }
     if (valid) {
       const unsigned ij = pix[p];
@@ -511,6 +525,168 @@ DEVINL void edge_mlp(const float* M, const float* pin, int PM, const unsigned* p
         }
       }
     }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// channel_pipeline: ONE WARP runs the whole per-channel chain of an AttentionLayer for channel c
+//   degrees -> A^ x -> Q|K|V -> attention map
+// with only __syncwarp() between the steps (the channels of a layer are independent until the per-edge MLP,
+// attention.py:97-105), so the warps of a CTA never wait for each other inside the chain.
+// ---------------------------------------------------------------------------------------
+template <bool WS, int HD>
+DEVINL void channel_pipeline(int lane, const float* pl, float* dv, const float* x, int ldx, int n, int f, float* axc,
+                             const float* Wc, int qkvw, const float* bc, float* qkc, int QKS, float* vcol, int ldv, int h,
+                             bool need_edge, bool need_node, const unsigned* pix, int P, float scale, float* Mc) {
+  constexpr int AT = 4 * HD;
+  // ---- degrees (layers.py:72-78): row i walked as (j, i), j < i, then the contiguous run (i, j), j > i
+  for (int i = lane; i < n; i += 32) {
+    float s = 1.f;
+    int idx = i - 1;
+    for (int j = 0; j < i; ++j) {
+      s += pl[idx];
+      idx += n - j - 2;
+    }
+    idx = i * (2 * n - i - 1) / 2;
+    for (int j = i + 1; j < n; ++j) s += pl[idx++];
+    dv[i] = 1.0f / sqrtf(fmaxf(s, 1.0f));
+  }
+  __syncwarp();
+  // ---- A^ x : items (row i, 8-column group g)
+  const int f8 = (f + 7) >> 3, ldax = 8 * f8;
+  {
+    const FastDiv df(f8);
+    for (int item = lane; item < n * f8; item += 32) {
+      const int i = df.div(item), g = item - i * f8;
+      const float* xg = x + 8 * g;
+      const float di = dv[i];
+      float2 acc[4];
+      {
+        const float4 a = *reinterpret_cast<const float4*>(xg + i * ldx);
+        const float4 b = *reinterpret_cast<const float4*>(xg + i * ldx + 4);
+        const float2 d2 = dup2(di);
+        acc[0] = __fmul2_rn(d2, lo2(a)); acc[1] = __fmul2_rn(d2, hi2(a));
+        acc[2] = __fmul2_rn(d2, lo2(b)); acc[3] = __fmul2_rn(d2, hi2(b));
+      }
+      int idx = i - 1;
+      for (int j = 0; j < i; ++j) {
+        const float2 w = dup2(pl[idx] * dv[j]);
+        idx += n - j - 2;
+        const float4 a = *reinterpret_cast<const float4*>(xg + j * ldx);
+        const float4 b = *reinterpret_cast<const float4*>(xg + j * ldx + 4);
+        acc[0] = fma2(w, lo2(a), acc[0]); acc[1] = fma2(w, hi2(a), acc[1]);
+        acc[2] = fma2(w, lo2(b), acc[2]); acc[3] = fma2(w, hi2(b), acc[3]);
+      }
+      idx = i * (2 * n - i - 1) / 2;
+      for (int j = i + 1; j < n; ++j) {
+        const float2 w = dup2(pl[idx++] * dv[j]);
+        const float4 a = *reinterpret_cast<const float4*>(xg + j * ldx);
+        const float4 b = *reinterpret_cast<const float4*>(xg + j * ldx + 4);
+        acc[0] = fma2(w, lo2(a), acc[0]); acc[1] = fma2(w, hi2(a), acc[1]);
+        acc[2] = fma2(w, lo2(b), acc[2]); acc[3] = fma2(w, hi2(b), acc[3]);
+      }
+      float* o = axc + i * ldax + 8 * g;
+      *reinterpret_cast<float4*>(o) = make_float4(acc[0].x * di, acc[0].y * di, acc[1].x * di, acc[1].y * di);
+      *reinterpret_cast<float4*>(o + 4) = make_float4(acc[2].x * di, acc[2].y * di, acc[3].x * di, acc[3].y * di);
+    }
+  }
+  __syncwarp();
+  // ---- Q | K | V = (A^ x) W + b : items (row pair, 4-column group); V goes to column block c of the [i][c][h] rows
+  {
+    const int o_lo = need_edge ? 0 : 2 * AT, o_hi = need_node ? qkvw : 2 * AT;
+    const int ogn = (o_hi - o_lo) >> 2, half = (n + 1) >> 1;
+    const int K4 = (f + 3) & ~3;
+    const FastDiv dog(ogn);
+    for (int item = lane; item < half * ogn; item += 32) {
+      const int r0 = dog.div(item), og = item - r0 * ogn;
+      const int r1 = r0 + half, r1c = r1 < n ? r1 : r0;
+      const int o = o_lo + 4 * og;
+      const float4 bv = ldw4<WS>(bc + o);
+      float2 a00 = lo2(bv), a01 = hi2(bv), a10 = a00, a11 = a01;
+      const float* in0 = axc + r0 * ldax;
+      const float* in1 = axc + r1c * ldax;
+      const float* wp = Wc + o;
+      for (int k0 = 0; k0 < K4; k0 += 4) {
+        const float4 w0 = ldw4<WS>(wp + (k0 + 0) * qkvw), w1 = ldw4<WS>(wp + (k0 + 1) * qkvw);
+        const float4 w2 = ldw4<WS>(wp + (k0 + 2) * qkvw), w3 = ldw4<WS>(wp + (k0 + 3) * qkvw);
+        const float4 x0 = *reinterpret_cast<const float4*>(in0 + k0);
+        const float4 x1 = *reinterpret_cast<const float4*>(in1 + k0);
+        a00 = fma2(dup2(x0.x), lo2(w0), a00); a01 = fma2(dup2(x0.x), hi2(w0), a01);
+        a10 = fma2(dup2(x1.x), lo2(w0), a10); a11 = fma2(dup2(x1.x), hi2(w0), a11);
+        a00 = fma2(dup2(x0.y), lo2(w1), a00); a01 = fma2(dup2(x0.y), hi2(w1), a01);
+        a10 = fma2(dup2(x1.y), lo2(w1), a10); a11 = fma2(dup2(x1.y), hi2(w1), a11);
+        a00 = fma2(dup2(x0.z), lo2(w2), a00); a01 = fma2(dup2(x0.z), hi2(w2), a01);
+        a10 = fma2(dup2(x1.z), lo2(w2), a10); a11 = fma2(dup2(x1.z), hi2(w2), a11);
+        a00 = fma2(dup2(x0.w), lo2(w3), a00); a01 = fma2(dup2(x0.w), hi2(w3), a01);
+        a10 = fma2(dup2(x1.w), lo2(w3), a10); a11 = fma2(dup2(x1.w), hi2(w3), a11);
+      }
+      if (o < 2 * AT) {
+        *reinterpret_cast<float4*>(qkc + r0 * QKS + o) = make_float4(a00.x, a00.y, a01.x, a01.y);
+        if (r1 < n) *reinterpret_cast<float4*>(qkc + r1 * QKS + o) = make_float4(a10.x, a10.y, a11.x, a11.y);
+      } else {
+        *reinterpret_cast<float4*>(vcol + r0 * ldv + (o - 2 * AT)) = make_float4(a00.x, a00.y, a01.x, a01.y);
+        if (r1 < n) *reinterpret_cast<float4*>(vcol + r1 * ldv + (o - 2 * AT)) = make_float4(a10.x, a10.y, a11.x, a11.y);
+      }
+    }
+  }
+  __syncwarp();
+  // ---- attention map (attention.py:35-49): mean over the 4 heads and both orientations of tanh(Q_h.K_h / sqrt(out_dim))
+  if (need_edge) {
+    for (int p = lane; p < P; p += 32) {
+      const unsigned ij = pix[p];
+      const int i = ij >> 8, j = ij & 255;
+      const float* qi = qkc + i * QKS;
+      const float* qj = qkc + j * QKS;
+      float m = 0.f;
+#pragma unroll
+      for (int hh = 0; hh < 4; ++hh) {
+        float2 p1 = make_float2(0.f, 0.f), p2 = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int d = 0; d < HD; d += 4) {
+          const float4 a1 = *reinterpret_cast<const float4*>(qi + hh * HD + d);
+          const float4 b1 = *reinterpret_cast<const float4*>(qj + AT + hh * HD + d);
+          const float4 a2 = *reinterpret_cast<const float4*>(qj + hh * HD + d);
+          const float4 b2 = *reinterpret_cast<const float4*>(qi + AT + hh * HD + d);
+          p1 = fma2(lo2(a1), lo2(b1), p1); p1 = fma2(hi2(a1), hi2(b1), p1);
+          p2 = fma2(lo2(a2), lo2(b2), p2); p2 = fma2(hi2(a2), hi2(b2), p2);
+        }
+        m += tanh_fast((p1.x + p1.y) * scale) + tanh_fast((p2.x + p2.y) * scale);
+      }
+      Mc[p] = m * 0.125f;
+    }
+  }
+}
+
+// second linear of `multi_channel` + mask + tanh (attention.py:106-107; tanh'd twice in X_GMH, ScoreNetwork_X.py:81):
+// items (row, 4-column group) over a subset of the CTA's threads
+DEVINL void node_l2(const float* h1, const float* W, const float* b, int n, int h, const float* fl, bool twice, float* xo,
+                    int ldo, int tid, int nt) {
+  const int og_n = h >> 2;
+  const FastDiv dg(og_n);
+  for (int item = tid; item < n * og_n; item += nt) {
+    const int i = dg.div(item), og = item - i * og_n;
+    const float4 bv = *reinterpret_cast<const float4*>(b + 4 * og);
+    float2 a0 = lo2(bv), a1 = hi2(bv);
+#pragma unroll
+    for (int k0 = 0; k0 < 16; k0 += 4) {
+      const float4 v = *reinterpret_cast<const float4*>(h1 + i * 16 + k0);
+      const float4 w0 = *reinterpret_cast<const float4*>(W + (k0 + 0) * h + 4 * og);
+      const float4 w1 = *reinterpret_cast<const float4*>(W + (k0 + 1) * h + 4 * og);
+      const float4 w2 = *reinterpret_cast<const float4*>(W + (k0 + 2) * h + 4 * og);
+      const float4 w3 = *reinterpret_cast<const float4*>(W + (k0 + 3) * h + 4 * og);
+      a0 = fma2(dup2(v.x), lo2(w0), a0); a1 = fma2(dup2(v.x), hi2(w0), a1);
+      a0 = fma2(dup2(v.y), lo2(w1), a0); a1 = fma2(dup2(v.y), hi2(w1), a1);
+      a0 = fma2(dup2(v.z), lo2(w2), a0); a1 = fma2(dup2(v.z), hi2(w2), a1);
+      a0 = fma2(dup2(v.w), lo2(w3), a0); a1 = fma2(dup2(v.w), hi2(w3), a1);
+    }
+    const float f = fl[i];
+    float v[4] = {a0.x * f, a0.y * f, a1.x * f, a1.y * f};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      v[q] = tanh_fast(v[q]);
+      if (twice) v[q] = tanh_fast(v[q]);
+    }
+    *reinterpret_cast<float4*>(xo + i * ldo + 4 * og) = make_float4(v[0], v[1], v[2], v[3]);
   }
 }
 
@@ -650,9 +826,10 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1) fused_layers_kernel(con
       gcn_degrees(P0, PM, 1, n, NBP, dinv, dn);
       __syncthreads();
       const float* xin = x0;
+      const int RS0 = S.RS;
       for (int l = 0; l < net.depth; ++l) {
         const int f = l == 0 ? F : h, f8 = (f + 7) >> 3;
-        gcn_ax(P0, PM, dinv, NBP, xin, XS, 1, n, f8, 8 * f8, R1, dn);
+        gcn_ax(P0, PM, dinv, NBP, xin, XS, 1, n, f8, 8 * f8, R1, RS0, dn);
         __syncthreads();
         mm_rows(mm_make(R1, 0, 8 * f8, f, net.gw[l], 0, h, net.gb[l], 0, 1, n, 0, h, xb, 0, XS, h, nullptr, 0, 0, nullptr, ACT_TANH));
         __syncthreads();
@@ -676,49 +853,78 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1) fused_layers_kernel(con
       tma_fetch(wq, net.L[0].blk_q, net.L[0].q_floats, &mbar_q);
       tma_fetch(wm, net.L[0].blk_m, net.L[0].m_floats, &mbar_m);
     }
+    const int warp = tid >> 5, lane = tid & 31, nwarps = nt >> 5;
+    const int RS = S.RS;
     for (int l = 0; l < net.depth; ++l) {
       const FLayer& L = net.L[l];
       const int C = L.c_in, f = L.f_in, f8 = (f + 7) >> 3, attn = L.attn;
       const bool more = l + 1 < net.depth;
-      gcn_degrees(pin, PM, C, n, NBP, dinv, dn);
-      __syncthreads();
-      PHASE(1);
-      gcn_ax(pin, PM, dinv, NBP, xin, XS, C, n, f8, 8 * f8, R1, dn);
-      __syncthreads();
-      PHASE(2);
-      // Q | K | V = (A^ x) W + b for every channel (attention.py:32-34); V rows are stored [i][c][h]
-      if (WSM) {
-        mbar_wait_parity(&mbar_q, ph_q);
-        ph_q ^= 1;
-      }
       const float* wqp = WSM ? wq : L.blk_q;
-      mm_rows_t<WSM>(mm_make(R1, n * 8 * f8, 8 * f8, f, wqp, L.f_in_p * L.qkvw, L.qkvw, wqp + L.bq_o, L.qkvw, C, n,
-                             L.need_edge ? 0 : 2 * attn, L.need_node ? L.qkvw : 2 * attn, QK, n * QKS, QKS, 2 * attn, R2, h, C * h,
-                             nullptr, ACT_NONE));
-      __syncthreads();
-      if (WSM && more && tid == 0) tma_fetch(wq, net.L[l + 1].blk_q, net.L[l + 1].q_floats, &mbar_q);
-      PHASE(3);
-      // x_out = tanh(mask_x(multi_channel(cat_c V_c)))  (attention.py:106-107), tanh'd twice in X_GMH (:81).
+      if (2 * C > nwarps) {
+        // ---- one warp per channel, no CTA barrier inside the chain
+        if (WSM) {
+          mbar_wait_parity(&mbar_q, ph_q);
+          ph_q ^= 1;
+        }
+        for (int c = warp; c < C; c += nwarps) {
+          const float* Wc = wqp + c * L.f_in_p * L.qkvw;
+          const float* bc = wqp + L.bq_o + c * L.qkvw;
+          if (attn == 16)
+            channel_pipeline<WSM, 4>(lane, pin + c * PM, dinv + c * NBP, xin, XS, n, f, R1 + c * RS, Wc, L.qkvw, bc, QK + c * n * QKS, QKS,
+                                     R2 + c * h, C * h, h, L.need_edge, L.need_node, pix, P, scale, R1 + c * RS);
+          else
+            channel_pipeline<WSM, 8>(lane, pin + c * PM, dinv + c * NBP, xin, XS, n, f, R1 + c * RS, Wc, L.qkvw, bc, QK + c * n * QKS, QKS,
+                                     R2 + c * h, C * h, h, L.need_edge, L.need_node, pix, P, scale, R1 + c * RS);
+        }
+        __syncthreads();
+        if (WSM && more && tid == 0) tma_fetch(wq, net.L[l + 1].blk_q, net.L[l + 1].q_floats, &mbar_q);
+        PHASE(3);
+      } else {
+        // ---- few channels (first layer): every step spread over the whole CTA
+        gcn_degrees(pin, PM, C, n, NBP, dinv, dn);
+        __syncthreads();
+        PHASE(1);
+        gcn_ax(pin, PM, dinv, NBP, xin, XS, C, n, f8, 8 * f8, R1, RS, dn);
+        __syncthreads();
+        PHASE(2);
+        // Q | K | V = (A^ x) W + b for every channel (attention.py:32-34); V rows are stored [i][c][h]
+        if (WSM) {
+          mbar_wait_parity(&mbar_q, ph_q);
+          ph_q ^= 1;
+        }
+        mm_rows_t<WSM>(mm_make(R1, RS, 8 * f8, f, wqp, L.f_in_p * L.qkvw, L.qkvw, wqp + L.bq_o, L.qkvw, C, n,
+                               L.need_edge ? 0 : 2 * attn, L.need_node ? L.qkvw : 2 * attn, QK, n * QKS, QKS, 2 * attn, R2, h, C * h,
+                               nullptr, ACT_NONE));
+        __syncthreads();
+        if (WSM && more && tid == 0) tma_fetch(wq, net.L[l + 1].blk_q, net.L[l + 1].q_floats, &mbar_q);
+        if (L.need_edge) {
+          if (attn == 16) attention_maps<4>(QK, QKS, pix, C, n, P, RS, scale, R1, dP);
+          else attention_maps<8>(QK, QKS, pix, C, n, P, RS, scale, R1, dP);
+        }
+        __syncthreads();
+        PHASE(4);
+      }
+      // ---- node MLP (attention.py:106-107) on the last two warps, per-edge MLP (:109-114) on the others.
       // x_in is dead by now: layers >= 1 update xb in place (layer 0 reads x0, which the X network needs again)
       if (WSM) {
         mbar_wait_parity(&mbar_m, ph_m);
         ph_m ^= 1;
       }
       const float* wmp = WSM ? wm : L.blk_m;
-      if (L.need_node) node_l1(R2, C * h, wmp + L.nw0_o, wmp + L.nb0_o, n, h1);
-      if (L.need_edge) {
-        if (attn == 16) attention_maps<4>(QK, QKS, pix, C, n, P, PM, scale, R1, dP);
-        else attention_maps<8>(QK, QKS, pix, C, n, P, PM, scale, R1, dP);
+      const int node_warps = (L.need_node && L.need_edge && nwarps >= 4) ? 2 : 0;     // split only when both exist
+      const int nt_edge = nt - 32 * node_warps;
+      if (L.need_node && (node_warps == 0 || tid >= nt_edge)) {
+        const int ltid = node_warps ? tid - nt_edge : tid, lnt = node_warps ? 32 * node_warps : nt;
+        node_l1(R2, C * h, wmp + L.nw0_o, wmp + L.nb0_o, n, h1, ltid, lnt);
+        if (node_warps) asm volatile("bar.sync 1, %0;" ::"r"(lnt) : "memory");
+        else __syncthreads();
+        node_l2(h1, wmp + L.nw1_o, wmp + L.nb1_o, n, h, fl, !isA, xb, XS, ltid, lnt);
       }
-      __syncthreads();
-      PHASE(4);
-      if (L.need_node)
-        mm_rows_t<WSM>(mm_make(h1, 0, 16, 16, wmp + L.nw1_o, 0, h, wmp + L.nb1_o, 0, 1, n, 0, h, xb, 0, XS, h, nullptr, 0, 0, fl,
-                               isA ? ACT_TANH : ACT_TANH2));
-      if (L.need_edge) {
+      if (L.need_edge && (node_warps == 0 || tid < nt_edge)) {
+        if (!node_warps && L.need_node) __syncthreads();       // (never both: kept for symmetry of the barrier count)
         float* gout = isA ? A.stackT + (int64_t)cbase * A.pstride + gp0 : nullptr;
-        if (L.nlin == 3) edge_mlp<3>(R1, pin, PM, pix, fl, wmp, L, P, more ? PA : nullptr, gout, A.pstride);
-        else edge_mlp<2>(R1, pin, PM, pix, fl, wmp, L, P, more ? PA : nullptr, gout, A.pstride);
+        if (L.nlin == 3) edge_mlp<3>(R1, RS, pin, PM, pix, fl, wmp, L, P, more ? PA : nullptr, gout, A.pstride, tid, nt_edge);
+        else edge_mlp<2>(R1, RS, pin, PM, pix, fl, wmp, L, P, more ? PA : nullptr, gout, A.pstride, tid, nt_edge);
       }
       __syncthreads();
       if (WSM && more && tid == 0) tma_fetch(wm, net.L[l + 1].blk_m, net.L[l + 1].m_floats, &mbar_m);
@@ -1242,8 +1448,8 @@ static int64_t plan_smem(const gdss_ctx* ctx, int NB, FSmem* s, bool wsm = true)
   s->wm = take(wsm ? wmf : 4);
   s->p0 = take(cinit * s->PM);
   s->pa = take(Cmax * s->PM);
-  int r1 = Cmax * NB * fmax;                         // A.x products [C][n][f rounded up to 8]
-  if (r1 < Cmax * s->PM) r1 = Cmax * s->PM;          // attention maps [C][P]
+  s->RS = NB * fmax > s->PM ? NB * fmax : s->PM;     // per channel: A.x rows [n][f rounded up to 8], then attention map [P]
+  int r1 = Cmax * s->RS;
   if (r1 < NB * s->LD) r1 = NB * s->LD;              // dense A while the power stack is built
   int qk = Cmax * NB * s->QKS;
   if (r1 + qk < 2 * NB * Hx) qk = 2 * NB * Hx - r1;  // [R1 | QK] hosts the two hidden buffers of the final node MLP
