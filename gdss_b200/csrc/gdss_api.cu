@@ -74,6 +74,8 @@ extern "C" gdss_ctx* gdss_ctx_create(int32_t N, int32_t F, const gdss_net_desc* 
   if (!(nf && nf[0] == '1')) c->fused = fused_supported(c);
   const char* ntc = getenv("GDSS_NO_TC");
   c->use_tc = !(ntc && ntc[0] == '1');
+  const char* nmma = getenv("GDSS_NO_MMA");
+  c->use_mma = !(nmma && nmma[0] == '1');
   return c;
 }
 

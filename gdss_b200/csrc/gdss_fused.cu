@@ -134,6 +134,7 @@ struct FusedArgs {
   const int* order;        // graph ids sorted by size bucket
   const int* meta;
   int bucket;
+  int use_mma;              // warp-level tensor-core (mma.sync 3xTF32) variants of the per-graph contractions
   unsigned long long* prof;   // optional [16] per-phase clock cycles (thread 0 of every CTA, summed), else null
   int64_t pstride;
   int N, F;
@@ -529,6 +530,155 @@ DEVINL void edge_mlp(const float* M, int MS, const float* pin, int PM, const uns
 }
 
 // ---------------------------------------------------------------------------------------
+// Warp-level tensor-core pieces: mma.sync m16n8k8 TF32 with the 3xTF32 split
+//   a*b ~= lo(a) hi(b) + hi(a) lo(b) + hi(a) hi(b)      (hi = round-to-nearest TF32, lo = TF32 of the remainder)
+// fp32 accumulation; measured |err| 2.7e-7 on unit-range operands (tools/mma_probe.cu), the same as an fp32 FMA chain.
+// Fragment layout (g = lane >> 2, t = lane & 3):
+//   A 16x8: a0 (g, t)  a1 (g+8, t)  a2 (g, t+4)  a3 (g+8, t+4)      B 8x8: b0 (k = t, n = g)  b1 (k = t+4, n = g)
+//   C 16x8: c0 (g, 2t)  c1 (g, 2t+1)  c2 (g+8, 2t)  c3 (g+8, 2t+1)
+// A C tile feeds the next layer's A operand without any data movement when the next layer's k index is *defined* as
+// k-step s: column t <-> unit 8s + 2t, column t+4 <-> unit 8s + 2t + 1 (the sum over k does not care about the order);
+// the B fragments of that layer are gathered with the same permutation.
+// ---------------------------------------------------------------------------------------
+struct Split { uint32_t hi, lo; };
+
+DEVINL Split split_tf32(float v) {
+  Split s;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(s.hi) : "f"(v));
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(s.lo) : "f"(v - __uint_as_float(s.hi)));
+  return s;
+}
+
+DEVINL void mma_tf32(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+// c += A B with both operands split (A: ah/al, B: bh/bl fragments)
+DEVINL void mma3(float (&c)[4], const uint32_t (&ah)[4], const uint32_t (&al)[4], const Split& b0, const Split& b1) {
+  mma_tf32(c, al, b0.hi, b1.hi);
+  mma_tf32(c, ah, b0.lo, b1.lo);
+  mma_tf32(c, ah, b0.hi, b1.hi);
+}
+
+// per-pixel MLP of one AttentionLayer (attention.py:109-114) on the tensor cores: one warp = 16 pixels per tile, the
+// three layers chained in registers (C fragment -> next A fragment), weights held as split B fragments.
+//   in = [M_0..M_{C-1}, P_0..P_{C-1}] -> 16 -> (16) -> c_out ; out = 2 * mlp * flag_i * flag_j
+// pout may alias pin: a warp reads all inputs of its 16 pixels before it writes them (mma.sync is warp-synchronous).
+template <int NLIN>
+DEVINL void edge_mlp_mma(const float* M, int MS, const float* pin, int PM, const unsigned* pix, const float* fl, const float* wm,
+                         const FLayer& L, int P, float* pout, float* gout, int64_t gstride, int warp, int nwarps, int lane) {
+  const int g = lane >> 2, t = lane & 3;
+  const int C = L.c_in, c_out = L.c_out, K1 = 2 * C;
+  const float* W1 = wm + L.ew_o[0];                 // [2C][16]
+  const float* W2 = wm + L.ew_o[1];                 // [16][16] (NLIN == 3)
+  const float* W3 = wm + L.ew_o[NLIN - 1];          // [16][c_out]
+  const float* b1 = wm + L.eb_o[0];
+  const float* b2 = wm + L.eb_o[1];
+  const float* b3 = wm + L.eb_o[NLIN - 1];
+  // ---- B fragments (split once per call)
+  Split w1[2][2][2], w2[2][2][2], w3[2][2];          // [k-step][n-tile][b0 | b1]
+#pragma unroll
+  for (int s = 0; s < 2; ++s)
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int k0 = 8 * s + t, k1 = 8 * s + t + 4;             // layer 1: natural k order (inputs come from memory)
+      w1[s][j][0] = split_tf32(k0 < K1 ? W1[k0 * 16 + 8 * j + g] : 0.f);
+      w1[s][j][1] = split_tf32(k1 < K1 ? W1[k1 * 16 + 8 * j + g] : 0.f);
+      if (NLIN == 3) {
+        w2[s][j][0] = split_tf32(W2[(8 * s + 2 * t) * 16 + 8 * j + g]);          // permuted k order (see above)
+        w2[s][j][1] = split_tf32(W2[(8 * s + 2 * t + 1) * 16 + 8 * j + g]);
+      }
+    }
+#pragma unroll
+  for (int s = 0; s < 2; ++s) {
+    w3[s][0] = split_tf32(g < c_out ? W3[(8 * s + 2 * t) * c_out + g] : 0.f);
+    w3[s][1] = split_tf32(g < c_out ? W3[(8 * s + 2 * t + 1) * c_out + g] : 0.f);
+  }
+  float bia1[2][2], bia2[2][2], bia3[2];
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    bia1[j][0] = b1[8 * j + 2 * t]; bia1[j][1] = b1[8 * j + 2 * t + 1];
+    bia2[j][0] = NLIN == 3 ? b2[8 * j + 2 * t] : 0.f; bia2[j][1] = NLIN == 3 ? b2[8 * j + 2 * t + 1] : 0.f;
+  }
+  bia3[0] = 2 * t < c_out ? b3[2 * t] : 0.f;
+  bia3[1] = 2 * t + 1 < c_out ? b3[2 * t + 1] : 0.f;
+  const int ks1 = (K1 + 7) >> 3;                     // k-steps of layer 1 (1 or 2)
+  const int ntile = (P + 15) >> 4;
+  for (int tile = warp; tile < ntile; tile += nwarps) {
+    const int pa = tile * 16 + g, pb = pa + 8;
+    const int pac = pa < P ? pa : P - 1, pbc = pb < P ? pb : P - 1;
+    // ---- layer 1: A fragments gathered from the channel planes
+    float c[2][4];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) { c[j][0] = bia1[j][0]; c[j][1] = bia1[j][1]; c[j][2] = bia1[j][0]; c[j][3] = bia1[j][1]; }
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+      if (s < ks1) {
+        uint32_t ah[4], al[4];
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          const int k = 8 * s + t + 4 * q;
+          float va = 0.f, vb = 0.f;
+          if (k < K1) {
+            const float* pl = k < C ? M + k * MS : pin + (k - C) * PM;
+            va = pl[pac];
+            vb = pl[pbc];
+          }
+          const Split sa = split_tf32(va), sb = split_tf32(vb);
+          ah[2 * q] = sa.hi; al[2 * q] = sa.lo; ah[2 * q + 1] = sb.hi; al[2 * q + 1] = sb.lo;
+        }
+#pragma unroll
+        for (int j = 0; j < 2; ++j) mma3(c[j], ah, al, w1[s][j][0], w1[s][j][1]);
+      }
+    }
+    __syncwarp();                    // every lane has read its inputs (in-place update below)
+    if (NLIN == 3) {
+      float d[2][4];
+#pragma unroll
+      for (int j = 0; j < 2; ++j) { d[j][0] = bia2[j][0]; d[j][1] = bia2[j][1]; d[j][2] = bia2[j][0]; d[j][3] = bia2[j][1]; }
+#pragma unroll
+      for (int s = 0; s < 2; ++s) {
+        uint32_t ah[4], al[4];
+        const Split e0 = split_tf32(elu_f(c[s][0])), e1 = split_tf32(elu_f(c[s][1]));
+        const Split e2 = split_tf32(elu_f(c[s][2])), e3 = split_tf32(elu_f(c[s][3]));
+        ah[0] = e0.hi; al[0] = e0.lo; ah[1] = e2.hi; al[1] = e2.lo; ah[2] = e1.hi; al[2] = e1.lo; ah[3] = e3.hi; al[3] = e3.lo;
+#pragma unroll
+        for (int j = 0; j < 2; ++j) mma3(d[j], ah, al, w2[s][j][0], w2[s][j][1]);
+      }
+#pragma unroll
+      for (int j = 0; j < 2; ++j)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) c[j][q] = d[j][q];
+    }
+    float o[4] = {bia3[0], bia3[1], bia3[0], bia3[1]};
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+      uint32_t ah[4], al[4];
+      const Split e0 = split_tf32(elu_f(c[s][0])), e1 = split_tf32(elu_f(c[s][1]));
+      const Split e2 = split_tf32(elu_f(c[s][2])), e3 = split_tf32(elu_f(c[s][3]));
+      ah[0] = e0.hi; al[0] = e0.lo; ah[1] = e2.hi; al[1] = e2.lo; ah[2] = e1.hi; al[2] = e1.lo; ah[3] = e3.hi; al[3] = e3.lo;
+      mma3(o, ah, al, w3[s][0], w3[s][1]);
+    }
+    // ---- (S + S^T), mask_adjs, stores: channels 2t, 2t+1 of pixels pa (o[0], o[1]) and pb (o[2], o[3])
+    if (2 * t < c_out) {
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        const int p = r ? pb : pa;
+        if (p < P) {
+          const unsigned ij = pix[p];
+          const float fm = 2.f * fl[ij >> 8] * fl[ij & 255];
+          const float v0 = o[2 * r] * fm, v1 = o[2 * r + 1] * fm;
+          if (pout) { pout[(2 * t) * PM + p] = v0; pout[(2 * t + 1) * PM + p] = v1; }
+          if (gout) { gout[(int64_t)(2 * t) * gstride + p] = v0; gout[(int64_t)(2 * t + 1) * gstride + p] = v1; }
+        }
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
 // channel_pipeline: ONE WARP runs the whole per-channel chain of an AttentionLayer for channel c
 //   degrees -> A^ x -> Q|K|V -> attention map
 // with only __syncwarp() between the steps (the channels of a layer are independent until the per-edge MLP,
@@ -876,6 +1026,7 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1) fused_layers_kernel(con
             channel_pipeline<WSM, 8>(lane, pin + c * PM, dinv + c * NBP, xin, XS, n, f, R1 + c * RS, Wc, L.qkvw, bc, QK + c * n * QKS, QKS,
                                      R2 + c * h, C * h, h, L.need_edge, L.need_node, pix, P, scale, R1 + c * RS);
         }
+        PHASE(8);                    // warp 0's own channel chain; PHASE(3) below = its wait for the slowest warp
         __syncthreads();
         if (WSM && more && tid == 0) tma_fetch(wq, net.L[l + 1].blk_q, net.L[l + 1].q_floats, &mbar_q);
         PHASE(3);
@@ -923,9 +1074,15 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1) fused_layers_kernel(con
       if (L.need_edge && (node_warps == 0 || tid < nt_edge)) {
         if (!node_warps && L.need_node) __syncthreads();       // (never both: kept for symmetry of the barrier count)
         float* gout = isA ? A.stackT + (int64_t)cbase * A.pstride + gp0 : nullptr;
-        if (L.nlin == 3) edge_mlp<3>(R1, RS, pin, PM, pix, fl, wmp, L, P, more ? PA : nullptr, gout, A.pstride, tid, nt_edge);
-        else edge_mlp<2>(R1, RS, pin, PM, pix, fl, wmp, L, P, more ? PA : nullptr, gout, A.pstride, tid, nt_edge);
+        if (A.use_mma) {
+          if (L.nlin == 3) edge_mlp_mma<3>(R1, RS, pin, PM, pix, fl, wmp, L, P, more ? PA : nullptr, gout, A.pstride, warp, nt_edge >> 5, lane);
+          else edge_mlp_mma<2>(R1, RS, pin, PM, pix, fl, wmp, L, P, more ? PA : nullptr, gout, A.pstride, warp, nt_edge >> 5, lane);
+        } else {
+          if (L.nlin == 3) edge_mlp<3>(R1, RS, pin, PM, pix, fl, wmp, L, P, more ? PA : nullptr, gout, A.pstride, tid, nt_edge);
+          else edge_mlp<2>(R1, RS, pin, PM, pix, fl, wmp, L, P, more ? PA : nullptr, gout, A.pstride, tid, nt_edge);
+        }
       }
+      PHASE(7);                      // warp 0's share of the per-edge MLP; PHASE(5) below = its wait (node warps, other edge warps)
       __syncthreads();
       if (WSM && more && tid == 0) tma_fetch(wm, net.L[l + 1].blk_m, net.L[l + 1].m_floats, &mbar_m);
       PHASE(5);
@@ -1514,6 +1671,7 @@ int launch_eval_fused(const gdss_ctx* ctx, const float* x, const float* adj, con
   fa.poff = reinterpret_cast<const int*>(ws + w.off[R_POFF]);
   fa.pstride = w.pstride;
   fa.N = N; fa.F = ctx->F;
+  fa.use_mma = ctx->use_mma ? 1 : 0;
   fa.prof = getenv("GDSS_PHASE_PROF") ? reinterpret_cast<unsigned long long*>(ws + w.off[R_META] + 128) : nullptr;
   fa.order = reinterpret_cast<const int*>(ws + w.off[R_ORDER]);
   fa.meta = reinterpret_cast<const int*>(ws + w.off[R_META]);

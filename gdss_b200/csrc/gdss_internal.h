@@ -64,6 +64,7 @@ struct gdss_ctx {
   int smem_optin;               // max dynamic shared memory per block
   int num_sms;
   bool fused;                   // small-graph path: one CTA per graph (gdss_fused.cu)
+  bool use_mma;                 // per-graph contractions on mma.sync (3xTF32); GDSS_NO_MMA=1 selects the FFMA variants
   bool use_tc;                  // final edge MLP on tcgen05 tensor cores (3xTF32); GDSS_NO_TC=1 selects the FFMA kernel
 };
 

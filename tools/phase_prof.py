@@ -26,9 +26,10 @@ iters = 3
 x, adj, xm, am = eng.sample(sdesc, table, fl, x=x, adj=adj, first_step=2, n_iters=iters, seed=1, use_graph=False)
 torch.cuda.synchronize()
 p = prof[16:32].cpu().numpy().astype(np.float64)
-names = ["stage+pow", "degrees", "A.x", "QKV", "nodeL1+maps", "nodeL2+edge MLP", "final X MLP"]
+names = ["stage+pow", "degrees", "A.x", "chain: wait for slowest warp (or QKV, first layer)", "nodeL1+maps", "edge/node MLP: wait", "final X MLP",
+         "edge MLP (warp 0)", "channel chain (warp 0)"]
 evals = iters * wl["evals"] * B
-tot = p[:7].sum()
+tot = p[:9].sum()
 print(f"graph-evals {evals}, mean cycles per graph-eval {tot / evals:.0f}")
-for nme, v in zip(names, p[:7]):
-    print(f"  {nme:18s} {v / evals:9.0f} cycles  {v / tot * 100:5.1f}%")
+for nme, v in zip(names, p[:9]):
+    print(f"  {nme:52s} {v / evals:9.0f} cycles  {v / tot * 100:5.1f}%")
