@@ -363,7 +363,7 @@ DEVINL void gcn_ax(const float* pin, int PM, const float* dinv, int NBP, const f
 
 // first linear of `multi_channel` (attention.py:90, :106): h1[i][0..16) = elu(b + cat_c V_c[i] . W), the K
 // range split over 4 adjacent lanes and reduced with shuffles (the layer has only n x 4 column groups)
-DEVINL void node_l1(const float* V, int K, const float* W, const float* b, int n, float* h1, int tid, int nt) {
+DEVINL void node_l1(const float* V, int ldv, int K, const float* W, const float* b, int n, float* h1, int tid, int nt) {
   const int lane = tid & 31;
   const int total = n * 16, kq = K >> 2;
   for (int base = tid - lane; base < total; base += nt) {
@@ -371,7 +371,7 @@ DEVINL void node_l1(const float* V, int K, const float* W, const float* b, int n
     const bool valid = idx < total;
     const int id2 = valid ? idx : total - 1;
     const int i = id2 >> 4, og = (id2 >> 2) & 3, kp = id2 & 3;
-    const float* vr = V + i * K + kp * kq;
+    const float* vr = V + i * ldv + kp * kq;
     const float* wr = W + (int64_t)(kp * kq) * 16 + 4 * og;
     float2 a0 = make_float2(0.f, 0.f), a1 = make_float2(0.f, 0.f);
     for (int k = 0; k < kq; k += 4) {
@@ -674,6 +674,65 @@ DEVINL void edge_mlp_mma(const float* M, int MS, const float* pin, int PM, const
           if (gout) { gout[(int64_t)(2 * t) * gstride + p] = v0; gout[(int64_t)(2 * t + 1) * gstride + p] = v1; }
         }
       }
+    }
+  }
+}
+
+// node MLP `multi_channel` of one AttentionLayer (attention.py:90, :106-107) on the tensor cores: one warp = 16 rows,
+//   cat_c V_c[i] (K = c_in * nhid) -> 16 (ELU) -> nhid, mask, tanh (twice in X_GMH, ScoreNetwork_X.py:81)
+// both layers chained in registers.  V rows have stride ldv = K + 4 (bank-conflict-free A fragments).
+DEVINL void node_mlp_mma(const float* V, int ldv, int K, const float* W1, const float* b1, const float* W2, const float* b2, int n,
+                         int h, const float* fl, bool twice, float* xo, int ldo, int warp, int nwarps, int lane) {
+  const int g = lane >> 2, t = lane & 3;
+  const int mt = (n + 15) >> 4;
+  for (int m = warp; m < mt; m += nwarps) {
+    const int ra = 16 * m + g, rb = ra + 8;
+    const float* va = V + (ra < n ? ra : n - 1) * ldv;
+    const float* vb = V + (rb < n ? rb : n - 1) * ldv;
+    float c[2][4];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      c[j][0] = c[j][2] = b1[8 * j + 2 * t];
+      c[j][1] = c[j][3] = b1[8 * j + 2 * t + 1];
+    }
+#pragma unroll 2
+    for (int k0 = 0; k0 < K; k0 += 8) {
+      uint32_t ah[4], al[4];
+      const Split a0 = split_tf32(va[k0 + t]), a1 = split_tf32(vb[k0 + t]);
+      const Split a2 = split_tf32(va[k0 + t + 4]), a3 = split_tf32(vb[k0 + t + 4]);
+      ah[0] = a0.hi; al[0] = a0.lo; ah[1] = a1.hi; al[1] = a1.lo; ah[2] = a2.hi; al[2] = a2.lo; ah[3] = a3.hi; al[3] = a3.lo;
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const Split w0 = split_tf32(W1[(k0 + t) * 16 + 8 * j + g]), w1 = split_tf32(W1[(k0 + t + 4) * 16 + 8 * j + g]);
+        mma3(c[j], ah, al, w0, w1);
+      }
+    }
+    uint32_t eh[2][4], el[2][4];                       // ELU(h1) as the A fragments of the second linear (permuted k order)
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+      const Split e0 = split_tf32(elu_f(c[s][0])), e1 = split_tf32(elu_f(c[s][1]));
+      const Split e2 = split_tf32(elu_f(c[s][2])), e3 = split_tf32(elu_f(c[s][3]));
+      eh[s][0] = e0.hi; el[s][0] = e0.lo; eh[s][1] = e2.hi; el[s][1] = e2.lo;
+      eh[s][2] = e1.hi; el[s][2] = e1.lo; eh[s][3] = e3.hi; el[s][3] = e3.lo;
+    }
+    const float fa = ra < n ? fl[ra] : 0.f, fb = rb < n ? fl[rb] : 0.f;
+    for (int o0 = 0; o0 < h; o0 += 8) {
+      float d[4];
+      d[0] = d[2] = b2[o0 + 2 * t];
+      d[1] = d[3] = b2[o0 + 2 * t + 1];
+#pragma unroll
+      for (int s = 0; s < 2; ++s) {
+        const Split w0 = split_tf32(W2[(8 * s + 2 * t) * h + o0 + g]), w1 = split_tf32(W2[(8 * s + 2 * t + 1) * h + o0 + g]);
+        mma3(d, eh[s], el[s], w0, w1);
+      }
+      float v[4] = {d[0] * fa, d[1] * fa, d[2] * fb, d[3] * fb};
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        v[q] = tanh_fast(v[q]);
+        if (twice) v[q] = tanh_fast(v[q]);
+      }
+      if (ra < n) *reinterpret_cast<float2*>(xo + ra * ldo + o0 + 2 * t) = make_float2(v[0], v[1]);
+      if (rb < n) *reinterpret_cast<float2*>(xo + rb * ldo + o0 + 2 * t) = make_float2(v[2], v[3]);
     }
   }
 }
@@ -1009,6 +1068,7 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1) fused_layers_kernel(con
       const FLayer& L = net.L[l];
       const int C = L.c_in, f = L.f_in, f8 = (f + 7) >> 3, attn = L.attn;
       const bool more = l + 1 < net.depth;
+      const int LDV = C * h + 4;       // row stride of the V rows [i][c][h] (+4: conflict-free mma A fragments)
       const float* wqp = WSM ? wq : L.blk_q;
       if (2 * C > nwarps) {
         // ---- one warp per channel, no CTA barrier inside the chain
@@ -1021,10 +1081,10 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1) fused_layers_kernel(con
           const float* bc = wqp + L.bq_o + c * L.qkvw;
           if (attn == 16)
             channel_pipeline<WSM, 4>(lane, pin + c * PM, dinv + c * NBP, xin, XS, n, f, R1 + c * RS, Wc, L.qkvw, bc, QK + c * n * QKS, QKS,
-                                     R2 + c * h, C * h, h, L.need_edge, L.need_node, pix, P, scale, R1 + c * RS);
+                                     R2 + c * h, LDV, h, L.need_edge, L.need_node, pix, P, scale, R1 + c * RS);
           else
             channel_pipeline<WSM, 8>(lane, pin + c * PM, dinv + c * NBP, xin, XS, n, f, R1 + c * RS, Wc, L.qkvw, bc, QK + c * n * QKS, QKS,
-                                     R2 + c * h, C * h, h, L.need_edge, L.need_node, pix, P, scale, R1 + c * RS);
+                                     R2 + c * h, LDV, h, L.need_edge, L.need_node, pix, P, scale, R1 + c * RS);
         }
         PHASE(8);                    // warp 0's own channel chain; PHASE(3) below = its wait for the slowest warp
         __syncthreads();
@@ -1044,7 +1104,7 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1) fused_layers_kernel(con
           ph_q ^= 1;
         }
         mm_rows_t<WSM>(mm_make(R1, RS, 8 * f8, f, wqp, L.f_in_p * L.qkvw, L.qkvw, wqp + L.bq_o, L.qkvw, C, n,
-                               L.need_edge ? 0 : 2 * attn, L.need_node ? L.qkvw : 2 * attn, QK, n * QKS, QKS, 2 * attn, R2, h, C * h,
+                               L.need_edge ? 0 : 2 * attn, L.need_node ? L.qkvw : 2 * attn, QK, n * QKS, QKS, 2 * attn, R2, h, LDV,
                                nullptr, ACT_NONE));
         __syncthreads();
         if (WSM && more && tid == 0) tma_fetch(wq, net.L[l + 1].blk_q, net.L[l + 1].q_floats, &mbar_q);
@@ -1066,10 +1126,15 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1) fused_layers_kernel(con
       const int nt_edge = nt - 32 * node_warps;
       if (L.need_node && (node_warps == 0 || tid >= nt_edge)) {
         const int ltid = node_warps ? tid - nt_edge : tid, lnt = node_warps ? 32 * node_warps : nt;
-        node_l1(R2, C * h, wmp + L.nw0_o, wmp + L.nb0_o, n, h1, ltid, lnt);
-        if (node_warps) asm volatile("bar.sync 1, %0;" ::"r"(lnt) : "memory");
-        else __syncthreads();
-        node_l2(h1, wmp + L.nw1_o, wmp + L.nb1_o, n, h, fl, !isA, xb, XS, ltid, lnt);
+        if (A.use_mma) {
+          node_mlp_mma(R2, LDV, C * h, wmp + L.nw0_o, wmp + L.nb0_o, wmp + L.nw1_o, wmp + L.nb1_o, n, h, fl, !isA, xb, XS, ltid >> 5,
+                       lnt >> 5, lane);
+        } else {
+          node_l1(R2, LDV, C * h, wmp + L.nw0_o, wmp + L.nb0_o, n, h1, ltid, lnt);
+          if (node_warps) asm volatile("bar.sync 1, %0;" ::"r"(lnt) : "memory");
+          else __syncthreads();
+          node_l2(h1, wmp + L.nw1_o, wmp + L.nb1_o, n, h, fl, !isA, xb, XS, ltid, lnt);
+        }
       }
       if (L.need_edge && (node_warps == 0 || tid < nt_edge)) {
         if (!node_warps && L.need_node) __syncthreads();       // (never both: kept for symmetry of the barrier count)
@@ -1612,7 +1677,7 @@ static int64_t plan_smem(const gdss_ctx* ctx, int NB, FSmem* s, bool wsm = true)
   if (r1 + qk < 2 * NB * Hx) qk = 2 * NB * Hx - r1;  // [R1 | QK] hosts the two hidden buffers of the final node MLP
   s->r1 = take(r1);
   s->qk = take(qk);
-  s->r2 = take(Cmax * NB * hmax);
+  s->r2 = take(NB * (Cmax * hmax + 4));            // V rows [i][c][h], row stride c_in * nhid + 4
   s->total = cur;
   return (int64_t)cur * 4;
 }
