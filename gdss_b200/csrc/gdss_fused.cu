@@ -119,8 +119,9 @@ struct FNet {
 
 // float offsets into dynamic shared memory
 struct FSmem {
-  int fl, dinv, pix, x0, xb, xs, h1, wq, wm, p0, pa, r1, qk, r2, total;
+  int fl, dinv, pix, x0, xb, xs, h1, wq, wm, p0, pa, r1, qk, r2, tab, total;
   int LD, XS, QKS, PM, NBP, XSS, RS;     // RS: per-channel stride of R1 (A.x rows / attention maps of one channel)
+  int TC;                                // columns of the triangle-index table (8 * ceil(NB / 8)); rows = 16 * ceil(NB / 16)
 };
 
 struct FusedArgs {
@@ -130,6 +131,8 @@ struct FusedArgs {
   const int* neff;
   float* raw_x;
   float* stackT;
+  float* xst;              // X network: node-feature stack [fdim][nstride] in global memory (final MLP runs in the batched
+  int64_t nstride;         // tensor-core kernel) or null (final MLP inside this kernel); row = b * N + i
   const int* poff;
   const int* order;        // graph ids sorted by size bucket
   const int* meta;
@@ -542,15 +545,18 @@ DEVINL void edge_mlp(const float* M, int MS, const float* pin, int PM, const uns
 // ---------------------------------------------------------------------------------------
 struct Split { uint32_t hi, lo; };
 
+// cvt.rna.tf32.f32 is emulated on sm_100a (add, NaN/Inf test, select, mask = 4 instructions per conversion); the tensor
+// core ignores the 13 low mantissa bits of a TF32 operand, so round-to-nearest is one integer add of half an ulp and the
+// hardware's own truncation.  hi is masked explicitly because lo is computed from it.  (Inf stays Inf, NaN stays NaN.)
 DEVINL Split split_tf32(float v) {
   Split s;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(s.hi) : "f"(v));
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(s.lo) : "f"(v - __uint_as_float(s.hi)));
+  s.hi = (__float_as_uint(v) + 0x1000u) & 0xffffe000u;
+  s.lo = __float_as_uint(v - __uint_as_float(s.hi)) + 0x1000u;
   return s;
 }
 
 DEVINL void mma_tf32(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+  asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
                : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
@@ -866,6 +872,122 @@ DEVINL void channel_pipeline(int lane, const float* pl, float* dv, const float* 
   }
 }
 
+// channel_chain_mma: the same per-channel chain with the two contractions on the tensor cores (mma.sync 3xTF32):
+//   degrees -> C1 = A~ (d . x) -> [scale rows by d: A^ x, kept in registers as the next A operand] -> Q|K|V = (A^ x) W + b -> map
+// A~ is gathered from the strict-upper-triangle plane through the index table tab[i][j] (diagonal -> the 1.0 slot,
+// padding -> the 0.0 slot), so the planes keep the layout the per-edge MLP reads and writes.  f <= 32.
+template <bool WS, int HD, int NF>       // NF: compile-time bound of the feature tiles (f <= 8 NF)
+__device__ __noinline__ void channel_chain_mma(int lane, const float* pl, const unsigned short* tab, int TC, float* dv, const float* x, int ldx, int n,
+                              int f, int f_in_p, const float* Wc, int qkvw, const float* bc, float* qkc, int QKS, float* vcol, int ldv,
+                              bool need_edge, bool need_node, const unsigned* pix, int P, float scale, float* Mc) {
+  constexpr int AT = 4 * HD;
+  const int g = lane >> 2, t = lane & 3;
+  const int ks = (n + 7) >> 3, mt = (n + 15) >> 4, nf = (f + 7) >> 3;      // k-steps over nodes, row tiles, feature tiles (<= 4)
+  // ---- degrees (layers.py:72-78): row sums of A~ (self loop included through the table)
+  for (int i = lane; i < n; i += 32) {
+    const unsigned short* tr = tab + i * TC;
+    float s0 = 0.f, s1 = 0.f;
+    for (int j = 0; j < 8 * ks; j += 4) {
+      const uint2 tt = *reinterpret_cast<const uint2*>(tr + j);
+      s0 += pl[tt.x & 0xffff]; s1 += pl[tt.x >> 16];
+      s0 += pl[tt.y & 0xffff]; s1 += pl[tt.y >> 16];
+    }
+    dv[i] = 1.0f / sqrtf(fmaxf(s0 + s1, 1.0f));
+  }
+  __syncwarp();
+  const int o_lo = need_edge ? 0 : 2 * AT, o_hi = need_node ? qkvw : 2 * AT;
+  for (int m = 0; m < mt; ++m) {
+    const int ra = 16 * m + g, rb = ra + 8;
+    const unsigned short* ta = tab + ra * TC;
+    const unsigned short* tb = tab + rb * TC;
+    float c1[NF][4];
+#pragma unroll
+    for (int jn = 0; jn < NF; ++jn)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) c1[jn][q] = 0.f;
+    for (int s = 0; s < ks; ++s) {
+      const int j0 = 8 * s + t, j1 = j0 + 4;
+      uint32_t ah[4], al[4];
+      const Split a0 = split_tf32(pl[ta[j0]]), a1 = split_tf32(pl[tb[j0]]), a2 = split_tf32(pl[ta[j1]]), a3 = split_tf32(pl[tb[j1]]);
+      ah[0] = a0.hi; al[0] = a0.lo; ah[1] = a1.hi; al[1] = a1.lo; ah[2] = a2.hi; al[2] = a2.lo; ah[3] = a3.hi; al[3] = a3.lo;
+      const float d0 = j0 < n ? dv[j0] : 0.f, d1 = j1 < n ? dv[j1] : 0.f;
+      const float* x0r = x + (j0 < n ? j0 : 0) * ldx + g;
+      const float* x1r = x + (j1 < n ? j1 : 0) * ldx + g;
+#pragma unroll
+      for (int jn = 0; jn < NF; ++jn) {
+        if (jn < nf) {
+          const Split b0 = split_tf32(x0r[8 * jn] * d0), b1 = split_tf32(x1r[8 * jn] * d1);
+          mma3(c1[jn], ah, al, b0, b1);
+        }
+      }
+    }
+    // rows scaled by d_i: A^ x, re-used as the A operand of the Q|K|V contraction (k-step jn: column t <-> feature
+    // 8 jn + 2t, column t+4 <-> feature 8 jn + 2t + 1)
+    const float da = ra < n ? dv[ra] : 0.f, db = rb < n ? dv[rb] : 0.f;
+    uint32_t qh[NF][4], ql[NF][4];
+#pragma unroll
+    for (int jn = 0; jn < NF; ++jn) {
+      if (jn < nf) {
+        const Split e0 = split_tf32(c1[jn][0] * da), e1 = split_tf32(c1[jn][1] * da);
+        const Split e2 = split_tf32(c1[jn][2] * db), e3 = split_tf32(c1[jn][3] * db);
+        qh[jn][0] = e0.hi; ql[jn][0] = e0.lo; qh[jn][1] = e2.hi; ql[jn][1] = e2.lo;
+        qh[jn][2] = e1.hi; ql[jn][2] = e1.lo; qh[jn][3] = e3.hi; ql[jn][3] = e3.lo;
+      }
+    }
+    for (int o0 = o_lo; o0 < o_hi; o0 += 8) {
+      float c[4];
+      {
+        const float2 bv = WS ? *reinterpret_cast<const float2*>(bc + o0 + 2 * t) : __ldg(reinterpret_cast<const float2*>(bc + o0 + 2 * t));
+        c[0] = c[2] = bv.x;
+        c[1] = c[3] = bv.y;
+      }
+#pragma unroll
+      for (int jn = 0; jn < NF; ++jn) {
+        if (jn < nf) {
+          const int k0 = 8 * jn + 2 * t, k1 = k0 + 1;
+          const float w0 = k0 < f_in_p ? (WS ? Wc[k0 * qkvw + o0 + g] : __ldg(Wc + k0 * qkvw + o0 + g)) : 0.f;
+          const float w1 = k1 < f_in_p ? (WS ? Wc[k1 * qkvw + o0 + g] : __ldg(Wc + k1 * qkvw + o0 + g)) : 0.f;
+          mma3(c, qh[jn], ql[jn], split_tf32(w0), split_tf32(w1));
+        }
+      }
+      const int oc = o0 + 2 * t;
+      if (o0 < 2 * AT) {
+        if (ra < n) *reinterpret_cast<float2*>(qkc + ra * QKS + oc) = make_float2(c[0], c[1]);
+        if (rb < n) *reinterpret_cast<float2*>(qkc + rb * QKS + oc) = make_float2(c[2], c[3]);
+      } else {
+        if (ra < n) *reinterpret_cast<float2*>(vcol + ra * ldv + (oc - 2 * AT)) = make_float2(c[0], c[1]);
+        if (rb < n) *reinterpret_cast<float2*>(vcol + rb * ldv + (oc - 2 * AT)) = make_float2(c[2], c[3]);
+      }
+    }
+  }
+  __syncwarp();
+  // ---- attention map (attention.py:35-49): mean over the 4 heads and both orientations of tanh(Q_h.K_h / sqrt(out_dim))
+  if (need_edge) {
+    for (int p = lane; p < P; p += 32) {
+      const unsigned ij = pix[p];
+      const int i = ij >> 8, j = ij & 255;
+      const float* qi = qkc + i * QKS;
+      const float* qj = qkc + j * QKS;
+      float m = 0.f;
+#pragma unroll
+      for (int hh = 0; hh < 4; ++hh) {
+        float2 p1 = make_float2(0.f, 0.f), p2 = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int d = 0; d < HD; d += 4) {
+          const float4 a1 = *reinterpret_cast<const float4*>(qi + hh * HD + d);
+          const float4 b1 = *reinterpret_cast<const float4*>(qj + AT + hh * HD + d);
+          const float4 a2 = *reinterpret_cast<const float4*>(qj + hh * HD + d);
+          const float4 b2 = *reinterpret_cast<const float4*>(qi + AT + hh * HD + d);
+          p1 = fma2(lo2(a1), lo2(b1), p1); p1 = fma2(hi2(a1), hi2(b1), p1);
+          p2 = fma2(lo2(a2), lo2(b2), p2); p2 = fma2(hi2(a2), hi2(b2), p2);
+        }
+        m += tanh_fast((p1.x + p1.y) * scale) + tanh_fast((p2.x + p2.y) * scale);
+      }
+      Mc[p] = m * 0.125f;
+    }
+  }
+}
+
 // second linear of `multi_channel` + mask + tanh (attention.py:106-107; tanh'd twice in X_GMH, ScoreNetwork_X.py:81):
 // items (row, 4-column group) over a subset of the CTA's threads
 DEVINL void node_l2(const float* h1, const float* W, const float* b, int n, int h, const float* fl, bool twice, float* xo,
@@ -963,6 +1085,7 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1) fused_layers_kernel(con
   float* R1 = sm + S.r1;           // dense A (power stack), then A.x products, then attention maps
   float* QK = sm + S.qk;           // Q|K rows [c][i][2 attn + 4]   ([R1 | QK] also hosts the final node MLP's hidden rows)
   float* R2 = sm + S.r2;           // V rows [i][c][nhid]
+  unsigned short* tab = reinterpret_cast<unsigned short*>(sm + S.tab);   // triangle index of (i, j); diagonal / padding -> constant slots
   const int64_t gp0 = A.poff[b];
   const FastDiv dn(n), dP(P);
 
@@ -977,6 +1100,28 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1) fused_layers_kernel(con
   for (int i = tid; i < n; i += nt) {
     const int rs = i * (2 * n - i - 1) / 2;
     for (int j = i + 1; j < n; ++j) pix[rs + j - i - 1] = (unsigned)((i << 8) | j);
+  }
+  if (A.use_mma) {
+    const int TC = S.TC, rows = 16 * ((n + 15) >> 4);
+    const FastDiv dt(TC);
+    for (int idx = tid; idx < rows * TC; idx += nt) {
+      const int i = dt.div(idx), j = idx - i * TC;
+      int v = PM - 1;                                     // padding: the 0.0 slot
+      if (i < n && j < n) {
+        const int lo = i < j ? i : j, hi = i < j ? j : i;
+        v = i == j ? PM - 2 : lo * (2 * n - lo - 1) / 2 + hi - lo - 1;
+      }
+      tab[idx] = (unsigned short)v;
+    }
+    int cpl = 1;                                          // planes of P0 (power stack) and PA (layer outputs)
+    if (A.has_a) cpl = A.a.c_init;
+    if (A.has_x && A.x.type == GDSS_NET_X_GMH && A.x.c_init > cpl) cpl = A.x.c_init;
+    const int npl = cpl + (S.r1 - S.pa) / PM;
+    for (int c = tid; c < npl; c += nt) {
+      float* plane = c < cpl ? P0 + c * PM : PA + (c - cpl) * PM;
+      plane[PM - 2] = 1.f;
+      plane[PM - 1] = 0.f;
+    }
   }
   {
     const FastDiv dx(XS);
@@ -1020,10 +1165,17 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1) fused_layers_kernel(con
     const FNet& net = isA ? A.a : A.x;
     if (!isA) {
       // node feature stack [x, x_1 .. x_depth] (ScoreNetwork_X.py:40, :84), padded columns zero
-      const FastDiv dq(XSS);
-      for (int idx = tid; idx < n * XSS; idx += nt) {
-        const int i = dq.div(idx), k = idx - i * XSS;
-        xs[idx] = k < F ? x0[i * XS + k] : 0.f;
+      if (A.xst) {
+        for (int idx = tid; idx < n * F; idx += nt) {
+          const int k = dn.div(idx), i = idx - k * n;
+          A.xst[(int64_t)k * A.nstride + (int64_t)b * N + i] = x0[i * XS + k];
+        }
+      } else {
+        const FastDiv dq(XSS);
+        for (int idx = tid; idx < n * XSS; idx += nt) {
+          const int i = dq.div(idx), k = idx - i * XSS;
+          xs[idx] = k < F ? x0[i * XS + k] : 0.f;
+        }
       }
     }
     const int h = net.nhid;
@@ -1042,14 +1194,21 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1) fused_layers_kernel(con
         __syncthreads();
         mm_rows(mm_make(R1, 0, 8 * f8, f, net.gw[l], 0, h, net.gb[l], 0, 1, n, 0, h, xb, 0, XS, h, nullptr, 0, 0, nullptr, ACT_TANH));
         __syncthreads();
-        for (int idx = tid; idx < n * h; idx += nt) {
-          const int i = dh.div(idx), o = idx - i * h;
-          xs[i * XSS + F + l * h + o] = xb[i * XS + o];
+        if (A.xst) {
+          for (int idx = tid; idx < n * h; idx += nt) {
+            const int o = dn.div(idx), i = idx - o * n;
+            A.xst[(int64_t)(F + l * h + o) * A.nstride + (int64_t)b * N + i] = xb[i * XS + o];
+          }
+        } else {
+          for (int idx = tid; idx < n * h; idx += nt) {
+            const int i = dh.div(idx), o = idx - i * h;
+            xs[i * XSS + F + l * h + o] = xb[i * XS + o];
+          }
         }
         xin = xb;
       }
       __syncthreads();
-      final_node_mlp(net, xs, XSS, n, fl, hA, hB, A.raw_x + (int64_t)b * N * F, F);
+      if (!A.xst) final_node_mlp(net, xs, XSS, n, fl, hA, hB, A.raw_x + (int64_t)b * N * F, F);
       continue;
     }
     // AttentionLayer stack (ScoreNetwork_A.py:131-141, ScoreNetwork_X.py:75-84)
@@ -1079,7 +1238,13 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1) fused_layers_kernel(con
         for (int c = warp; c < C; c += nwarps) {
           const float* Wc = wqp + c * L.f_in_p * L.qkvw;
           const float* bc = wqp + L.bq_o + c * L.qkvw;
-          if (attn == 16)
+          if (A.use_mma && f <= 16 && attn == 16) {
+            channel_chain_mma<WSM, 4, 2>(lane, pin + c * PM, tab, S.TC, dinv + c * NBP, xin, XS, n, f, L.f_in_p, Wc, L.qkvw, bc,
+                                         QK + c * n * QKS, QKS, R2 + c * h, LDV, L.need_edge, L.need_node, pix, P, scale, R1 + c * RS);
+          } else if (A.use_mma && f <= 32 && attn == 32) {
+            channel_chain_mma<WSM, 8, 4>(lane, pin + c * PM, tab, S.TC, dinv + c * NBP, xin, XS, n, f, L.f_in_p, Wc, L.qkvw, bc,
+                                         QK + c * n * QKS, QKS, R2 + c * h, LDV, L.need_edge, L.need_node, pix, P, scale, R1 + c * RS);
+          } else if (attn == 16)
             channel_pipeline<WSM, 4>(lane, pin + c * PM, dinv + c * NBP, xin, XS, n, f, R1 + c * RS, Wc, L.qkvw, bc, QK + c * n * QKS, QKS,
                                      R2 + c * h, LDV, h, L.need_edge, L.need_node, pix, P, scale, R1 + c * RS);
           else
@@ -1153,9 +1318,16 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1) fused_layers_kernel(con
       PHASE(5);
       if (L.need_node) {
         if (!isA) {
-          for (int idx = tid; idx < n * h; idx += nt) {
-            const int i = dh.div(idx), o = idx - i * h;
-            xs[i * XSS + F + l * h + o] = xb[i * XS + o];
+          if (A.xst) {
+            for (int idx = tid; idx < n * h; idx += nt) {
+              const int o = dn.div(idx), i = idx - o * n;
+              A.xst[(int64_t)(F + l * h + o) * A.nstride + (int64_t)b * N + i] = xb[i * XS + o];
+            }
+          } else {
+            for (int idx = tid; idx < n * h; idx += nt) {
+              const int i = dh.div(idx), o = idx - i * h;
+              xs[i * XSS + F + l * h + o] = xb[i * XS + o];
+            }
           }
         }
         xin = xb;
@@ -1163,7 +1335,7 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1) fused_layers_kernel(con
       pin = PA;
       cbase += L.c_out;
     }
-    if (!isA) {
+    if (!isA && !A.xst) {
       __syncthreads();
       final_node_mlp(net, xs, XSS, n, fl, hA, hB, A.raw_x + (int64_t)b * N * F, F);
       PHASE(6);
@@ -1181,6 +1353,7 @@ struct FinalTriArgs {
   const float* w1; const float* b1; const float* w2; const float* b2; const float* w3; const float* b3;
   float* out; const float* flags;
   int N, fdim, H, Hs;
+  const int* neff; int B, F, foutp;      // node mode (X networks): rows = b * N + i, F outputs per row, w3 [Hs][foutp]
 };
 
 template <int OPT>
@@ -1378,7 +1551,7 @@ DEVINL void tc_sync_before_mma() {         // tcgen05.st / ld of every thread or
   asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
 }
 
-template <int NP, int K1P>
+template <int NP, int K1P, int FOP, bool NODE>      // NODE: final MLP of an X network (FOP = padded output width), rows = nodes
 __global__ void __launch_bounds__(256, 1) final_edge_tc_kernel(FinalTriArgs a, int* __restrict__ err) {
   extern __shared__ __align__(128) float sm[];
   constexpr int KH = K1P / 2;             // layer-1 operand columns per column half
@@ -1390,8 +1563,8 @@ __global__ void __launch_bounds__(256, 1) final_edge_tc_kernel(FinalTriArgs a, i
   float* W2lo = W2hi + NP * NP;
   float* b1s = W2lo + NP * NP;            // [NP]
   float* b2s = b1s + NP;
-  float* w3s = b2s + NP;
-  float* part = w3s + NP;                 // [128] partial dot products of column half 1
+  float* w3s = b2s + NP;                  // [NP] (edge) / [NP][FOP] (node)
+  float* part = w3s + NP * (NODE ? FOP : 1);   // [128] ([128][FOP]) partial dot products of column half 1
   __shared__ uint32_t tmem_base_s;
   __shared__ __align__(8) uint64_t mbar;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -1418,8 +1591,13 @@ __global__ void __launch_bounds__(256, 1) final_edge_tc_kernel(FinalTriArgs a, i
   for (int idx = tid; idx < NP; idx += 256) {
     b1s[idx] = idx < H ? a.b1[idx] : 0.f;
     b2s[idx] = idx < H ? a.b2[idx] : 0.f;
-    w3s[idx] = idx < H ? a.w3[idx * 4] : 0.f;
+    if (!NODE) w3s[idx] = idx < H ? a.w3[idx * 4] : 0.f;
   }
+  if (NODE)
+    for (int idx = tid; idx < NP * FOP; idx += 256) {
+      const int k = idx / FOP, o = idx - k * FOP;
+      w3s[idx] = (k < H && o < a.foutp) ? a.w3[k * a.foutp + o] : 0.f;
+    }
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;\n" ::"r"(smem_u32(&tmem_base_s)) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
@@ -1441,7 +1619,7 @@ __global__ void __launch_bounds__(256, 1) final_edge_tc_kernel(FinalTriArgs a, i
   const float b3 = a.b3[0];
   uint32_t phase = 0;
   bool ok = true;
-  const int ntiles = a.meta[1];
+  const int ntiles = NODE ? (a.B * N + 127) / 128 : a.meta[1];
   for (int tile = blockIdx.x; tile < ntiles && ok; tile += gridDim.x) {
     const int64_t gp = (int64_t)tile * 128 + row;
     // ---- layer-1 operand: channel values of this pixel -> hi / lo -> tensor memory
@@ -1515,6 +1693,46 @@ __global__ void __launch_bounds__(256, 1) final_edge_tc_kernel(FinalTriArgs a, i
     ok = ok && mbar_wait(mb, phase);
     phase ^= 1;
     asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+    if (NODE) {
+      // ---- epilogue 2 (X networks, ScoreNetwork_X.py:43-46, :86-89): ELU(D + b2) W3 + b3, mask_x
+      float dv[FOP];
+#pragma unroll
+      for (int o = 0; o < FOP; ++o) dv[o] = 0.f;
+#pragma unroll
+      for (int c0 = 0; c0 < CH; c0 += 8) {
+        const int col = half * CH + c0;
+        float d[8];
+        tmem_ld8(tlane + colD + col, d);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float e = elu_f(d[q] + b2s[col + q]);
+#pragma unroll
+          for (int o = 0; o < FOP; o += 4) {
+            const float4 w = *reinterpret_cast<const float4*>(w3s + (col + q) * FOP + o);
+            dv[o] = fmaf(e, w.x, dv[o]); dv[o + 1] = fmaf(e, w.y, dv[o + 1]);
+            dv[o + 2] = fmaf(e, w.z, dv[o + 2]); dv[o + 3] = fmaf(e, w.w, dv[o + 3]);
+          }
+        }
+      }
+      if (half == 1) {
+#pragma unroll
+        for (int o = 0; o < FOP; ++o) part[o * 128 + row] = dv[o];
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+      __syncthreads();
+      if (half == 0 && gp < (int64_t)a.B * N) {
+        const int b = (int)(gp / N), i = (int)(gp - (int64_t)b * N);
+        if (i < a.neff[b]) {
+          const float f = a.flags[(int64_t)b * N + i];
+          float* O = a.out + gp * a.F;
+#pragma unroll
+          for (int o = 0; o < FOP; ++o)
+            if (o < a.F) O[o] = (dv[o] + part[o * 128 + row] + a.b3[o]) * f;
+        }
+      }
+      ok = __syncthreads_and(ok);
+      continue;
+    }
     // ---- epilogue 2: ELU(D + b2) . w3 + b3, zero diagonal / flag mask (ScoreNetwork_A.py:143-148), mirrored store
     float dot = 0.f;
 #pragma unroll
@@ -1552,10 +1770,21 @@ static final_tc_fn pick_final_tc(int fdim, int* np, int* k1p) {
   const int H = 2 * fdim, NP = (H + 15) & ~15, K1P = (fdim + 7) & ~7;
   *np = NP;
   *k1p = K1P;
-  if (NP == 96 && K1P == 48) return final_edge_tc_kernel<96, 48>;     // fdim 46 (ZINC250k: 2 + 8*5 + 4)
-  if (NP == 80 && K1P == 40) return final_edge_tc_kernel<80, 40>;     // fdim 38 (community_small, ego_small)
-  if (NP == 48 && K1P == 24) return final_edge_tc_kernel<48, 24>;     // fdim 22 (QM9)
-  if (NP == 112 && K1P == 56) return final_edge_tc_kernel<112, 56>;   // fdim 54 (ENZYMES, grid)
+  if (NP == 96 && K1P == 48) return final_edge_tc_kernel<96, 48, 4, false>;     // fdim 46 (ZINC250k: 2 + 8*5 + 4)
+  if (NP == 80 && K1P == 40) return final_edge_tc_kernel<80, 40, 4, false>;     // fdim 38 (community_small, ego_small)
+  if (NP == 48 && K1P == 24) return final_edge_tc_kernel<48, 24, 4, false>;     // fdim 22 (QM9)
+  if (NP == 112 && K1P == 56) return final_edge_tc_kernel<112, 56, 4, false>;   // fdim 54 (ENZYMES, grid)
+  return nullptr;
+}
+
+// node mode: the X networks whose hidden width fits tensor memory (3 NP <= 512 columns)
+static final_tc_fn pick_final_tc_node(int fdim, int foutp, int* np, int* k1p, int* fop) {
+  const int H = 2 * fdim, NP = (H + 15) & ~15, K1P = (fdim + 7) & ~7;
+  *np = NP;
+  *k1p = K1P;
+  *fop = foutp;
+  if (NP == 96 && K1P == 48 && foutp == 12) return final_edge_tc_kernel<96, 48, 12, true>;   // ZINC250k: fdim 9 + 2*16, F = 9
+  if (NP == 80 && K1P == 40 && foutp == 4) return final_edge_tc_kernel<80, 40, 4, true>;     // QM9: fdim 4 + 2*16, F = 4
   return nullptr;
 }
 
@@ -1640,8 +1869,12 @@ static int64_t plan_smem(const gdss_ctx* ctx, int NB, FSmem* s, bool wsm = true)
   }
   if (fmax < ((hmax + 7) & ~7)) fmax = (hmax + 7) & ~7;
   const int NBP = (NB + 3) & ~3;
-  const int PM = ((NB * (NB - 1) / 2) + 3) & ~3;
-  s->NBP = NBP; s->PM = PM > 4 ? PM : 4;
+  // plane stride: the P pixels + two constant slots (PM-2 holds 1.0 = the self loop, PM-1 holds 0.0 = padding; both are
+  // addressed through the triangle-index table), rounded up to 8 (mod 32) so that the four planes an mma A fragment
+  // gathers from fall into disjoint banks
+  int PM = NB * (NB - 1) / 2 + 2;
+  while ((PM & 31) != 8) ++PM;
+  s->NBP = NBP; s->PM = PM;
   s->LD = NB | 1;
   s->XS = fmax;
   s->QKS = 2 * amax + 4;
@@ -1671,6 +1904,7 @@ static int64_t plan_smem(const gdss_ctx* ctx, int NB, FSmem* s, bool wsm = true)
   s->p0 = take(cinit * s->PM);
   s->pa = take(Cmax * s->PM);
   s->RS = NB * fmax > s->PM ? NB * fmax : s->PM;     // per channel: A.x rows [n][f rounded up to 8], then attention map [P]
+  while ((s->RS & 31) != 8) ++s->RS;
   int r1 = Cmax * s->RS;
   if (r1 < NB * s->LD) r1 = NB * s->LD;              // dense A while the power stack is built
   int qk = Cmax * NB * s->QKS;
@@ -1678,6 +1912,8 @@ static int64_t plan_smem(const gdss_ctx* ctx, int NB, FSmem* s, bool wsm = true)
   s->r1 = take(r1);
   s->qk = take(qk);
   s->r2 = take(NB * (Cmax * hmax + 4));            // V rows [i][c][h], row stride c_in * nhid + 4
+  s->TC = 8 * ((NB + 7) / 8);
+  s->tab = take((16 * ((NB + 15) / 16) * s->TC + 1) / 2);      // uint16 entries
   s->total = cur;
   return (int64_t)cur * 4;
 }
@@ -1736,6 +1972,15 @@ int launch_eval_fused(const gdss_ctx* ctx, const float* x, const float* adj, con
   fa.poff = reinterpret_cast<const int*>(ws + w.off[R_POFF]);
   fa.pstride = w.pstride;
   fa.N = N; fa.F = ctx->F;
+  // X network's final MLP: batched tensor-core kernel when its shape has an instance, else inside the per-graph kernel
+  int xnp = 0, xk1p = 0, xfop = 0;
+  final_tc_fn xfn = (want_x && ctx->use_tc && w.nstride > 0) ? pick_final_tc_node(ctx->px.fdim, ctx->px.foutp, &xnp, &xk1p, &xfop) : nullptr;
+  const size_t xsm = sizeof(float) * (2 * (size_t)(xk1p * xnp + xnp * xnp) + 2 * xnp + (size_t)xnp * xfop + 128 * (size_t)xfop) + 256;
+  if (xfn && (int)xsm > ctx->smem_optin) xfn = nullptr;
+  if (xfn) {
+    fa.xst = reinterpret_cast<float*>(ws + w.off[R_XS]);
+    fa.nstride = w.nstride;
+  }
   fa.use_mma = ctx->use_mma ? 1 : 0;
   fa.prof = getenv("GDSS_PHASE_PROF") ? reinterpret_cast<unsigned long long*>(ws + w.off[R_META] + 128) : nullptr;
   fa.order = reinterpret_cast<const int*>(ws + w.off[R_ORDER]);
@@ -1771,9 +2016,30 @@ int launch_eval_fused(const gdss_ctx* ctx, const float* x, const float* adj, con
     LAUNCH_CHECK();
   }
   cudaError_t e;
+  if (xfn) {
+    const NetPlan& p = ctx->px;
+    FinalTriArgs ta;
+    memset(&ta, 0, sizeof(ta));
+    ta.stackT = fa.xst; ta.pstride = w.nstride;
+    ta.meta = reinterpret_cast<const int*>(ws + w.off[R_META]);
+    ta.w1 = ctx->blob_x + p.fw[0]; ta.b1 = ctx->blob_x + p.fb[0]; ta.w2 = ctx->blob_x + p.fw[1]; ta.b2 = ctx->blob_x + p.fb[1];
+    ta.w3 = ctx->blob_x + p.fw[2]; ta.b3 = ctx->blob_x + p.fb[2];
+    ta.out = score_x; ta.flags = flags; ta.N = N; ta.fdim = p.fdim; ta.H = 2 * p.fdim; ta.Hs = p.Hp;
+    ta.neff = neff; ta.B = B; ta.F = ctx->F; ta.foutp = p.foutp;
+    e = cudaFuncSetAttribute(xfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xsm);
+    if (e != cudaSuccess) return (int)e;
+    const int64_t tiles = ((int64_t)B * N + 127) / 128;
+    int grid = ctx->num_sms > 0 ? ctx->num_sms : 148;
+    if ((int64_t)grid > tiles) grid = (int)tiles;
+    int* errflag = reinterpret_cast<int*>(ws + w.off[R_META]) + 16;
+    xfn<<<grid, 256, xsm, st>>>(ta, errflag);
+    launched(K_FINAL_NODE, st);
+    LAUNCH_CHECK();
+  }
   if (want_a) {
     const NetPlan& p = ctx->pa;
     FinalTriArgs ta;
+    memset(&ta, 0, sizeof(ta));
     ta.stackT = fa.stackT; ta.pstride = w.pstride;
     ta.gmap = reinterpret_cast<const int*>(ws + w.off[R_GMAP]);
     ta.meta = reinterpret_cast<const int*>(ws + w.off[R_META]);

@@ -51,6 +51,7 @@ enum Region {
 struct Workspace {
   int64_t off[R_COUNT + 1];
   int64_t pstride;              // fused path: floats per channel plane of the pixel-major stack
+  int64_t nstride;              // fused path: floats per feature plane of the X network's node stack (rows b * N + i)
 };
 
 }  // namespace gdss

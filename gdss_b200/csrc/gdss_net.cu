@@ -714,6 +714,7 @@ void layout_workspace(const gdss_ctx* ctx, int B, Workspace* w) {
   sz[R_XA0] = 4 * (int64_t)B * N * nh;
   sz[R_XA1] = 4 * (int64_t)B * N * nh;
   w->pstride = 0;
+  w->nstride = 0;
   if (ctx->fused) {
     // the per-graph kernel keeps everything but the A-network's channel stack on chip
     sz[R_STACK_A] = sz[R_STACK_X] = sz[R_DIS] = sz[R_QKV] = sz[R_XA0] = sz[R_XA1] = sz[R_XS] = 0;
@@ -724,6 +725,9 @@ void layout_workspace(const gdss_ctx* ctx, int B, Workspace* w) {
     sz[R_GMAP] = 4 * w->pstride;
     sz[R_ORDER] = 4 * (int64_t)B;
     sz[R_STACKT] = ctx->has_a ? 4 * w->pstride * ctx->pa.fdim : 0;
+    // X network: node-feature stack [fdim][nstride] read by the batched tensor-core final MLP
+    w->nstride = ((int64_t)B * N + 127) / 128 * 128 + 128;
+    sz[R_XS] = ctx->has_x ? 4 * w->nstride * ctx->px.fdim : 0;
   }
   sz[R_RAW_X] = 4 * (int64_t)B * N * F;
   sz[R_RAW_ADJ] = 4 * (int64_t)B * N * N;

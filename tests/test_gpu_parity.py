@@ -194,10 +194,11 @@ def test_public_sampler_api_runs_and_is_deterministic():
     assert rel(ma.cuda()(x.cuda(), adj.cuda(), fl.cuda()), ref) <= TOL
 
 
-@pytest.mark.parametrize("env", ["GDSS_NO_FUSED", "GDSS_NO_TC"])
+@pytest.mark.parametrize("env", ["GDSS_NO_FUSED", "GDSS_NO_TC", "GDSS_NO_MMA"])
 @pytest.mark.parametrize("name", ["zinc250k_v2", "community_small", "qm9"])
 def test_alternate_kernel_paths_agree(name, env, monkeypatch):
-    """The general multi-kernel path (GDSS_NO_FUSED=1) and the FP32 final-MLP kernel (GDSS_NO_TC=1) stay parity-green."""
+    """The general multi-kernel path (GDSS_NO_FUSED=1), the FP32 final-MLP kernels (GDSS_NO_TC=1) and the FFMA variants of
+    the per-graph contractions (GDSS_NO_MMA=1) stay parity-green."""
     from gdss_b200.engine import Engine
     monkeypatch.setenv(env, "1")
     ck = load_golden_ckpt(name)

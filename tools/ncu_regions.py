@@ -16,17 +16,45 @@ from collections import defaultdict
 sass_csv, gi_txt, kname = sys.argv[1:4]
 by_line = len(sys.argv) > 4
 
-HELPERS = [(12, 31), (146, 163), (205, 210)]          # tiny inlined helpers of gdss_fused.cu (attribute to the caller)
-REGIONS = [(212, 296, "mm_rows"), (302, 318, "gcn_degrees"), (319, 362, "gcn_ax"), (363, 402, "node_l1"),
-           (403, 433, "attention_maps"), (434, 530, "edge_mlp"), (542, 555, "pipe:degrees"), (556, 593, "pipe:A.x"),
-           (594, 632, "pipe:QKV"), (633, 658, "pipe:maps"), (660, 692, "node_l2"), (703, 716, "final_node_mlp"),
-           (760, 806, "kernel:stage+pow"), (807, 951, "kernel:glue")]
+HELPER_NAMES = {"tanh_fast", "fma2", "dup2", "lo2", "hi2", "FastDiv", "div", "ldw4", "split_tf32", "mma_tf32", "mma3", "sm_addr",
+                "tma_fetch", "mbar_wait_parity", "mm_make"}
+SRC = __import__("os").path.join(__import__("os").path.dirname(__import__("os").path.abspath(__file__)), "..", "gdss_b200", "csrc",
+                                 "gdss_fused.cu")
+
+
+def scan_functions(path):
+    """(first line, last line, name) of every top-level function body of the source file."""
+    out, name, start, depth = [], None, 0, 0
+    sig = re.compile(r"^(?:DEVINL|__device__|__global__|static|template)\b.*?([A-Za-z_][A-Za-z0-9_]*)\s*\(")
+    lines = open(path).read().split("\n")
+    for k, line in enumerate(lines, 1):
+        if name is None:
+            m = sig.match(line)
+            if m and not line.startswith("template"):
+                name, start = m.group(1), k
+            elif line.startswith("  DEVINL") or line.startswith("  DEVINL explicit"):
+                pass
+            if name and "{" in line and line.rstrip().endswith("}") and line.count("{") == line.count("}"):
+                out.append((start, k, name)); name = None          # one-line body
+            continue
+        if line.startswith("}"):
+            out.append((start, k, name))
+            name = None
+    return out
+
+
+FUNCS = scan_functions(SRC)
+KSTART = next((a for a, b, nm in FUNCS if nm == 'fused_layers_kernel'), 10 ** 9)
+HELPERS = [(a, b) for a, b, nm in FUNCS if nm in HELPER_NAMES] + [(146, 156)]
+REGIONS = [(a, b, nm) for a, b, nm in FUNCS if nm not in HELPER_NAMES]
 
 
 def region_of(chain):
     for f, ln in chain:                                 # innermost first
         if not f.endswith("gdss_fused.cu"):
             continue
+        if FUNCS and ln >= KSTART:                      # kernel body: split by the call-site comment blocks
+            return ("kernel:glue", ln)
         if any(a <= ln <= b for a, b in HELPERS):
             continue
         for a, b, name in REGIONS:
