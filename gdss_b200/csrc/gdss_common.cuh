@@ -10,7 +10,18 @@ namespace gdss {
 // ---- activations ---------------------------------------------------------------------
 // ELU (alpha = 1) as torch.nn.functional.elu (models/layers.py:150).  ex2.approx based:
 // absolute error ~1e-7 on the negative branch, exact on the positive one.
-DEVINL float elu_f(float v) { return v > 0.f ? v : (__expf(v) - 1.f); }
+// Direct MUFU forms (no denormal fix-up code around them: a flushed result only meets exp(-88) ~ 0):
+DEVINL float ex2_ftz(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+DEVINL float rcp_ftz(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+DEVINL float elu_f(float v) { return v > 0.f ? v : (ex2_ftz(v * 1.4426950408889634f) - 1.f); }
 
 // tanh via one ex2.approx and one rcp.approx: |err| <= ~3e-7 absolute (tanh.approx.f32 is
 // 2^-11 and breaks the 1e-4 per-step parity bar).

@@ -25,9 +25,10 @@ namespace gdss {
   } while (0)
 
 DEVINL float tanh_fast(float v) {      // no clamp needed: ex2 -> inf gives 1, -> 0 gives -1
-  float e = __expf(2.f * v);
-  return 1.f - __fdividef(2.f, e + 1.f);
+  return fmaf(-2.f, rcp_ftz(ex2_ftz(v * 2.8853900817779268f) + 1.f), 1.f);
 }
+// 1 / (exp(2 z) + 1) with the 2 log2(e) factor already folded into the argument: tanh(z) = 1 - 2 * sig2(z * 2 log2 e)
+DEVINL float sig2(float a) { return rcp_ftz(ex2_ftz(a) + 1.f); }
 
 // ---------------------------------------------------------------------------------------
 // pixel bookkeeping (depends on the flags only: once per sampler call)
@@ -896,73 +897,88 @@ __device__ __noinline__ void channel_chain_mma(int lane, const float* pl, const 
   }
   __syncwarp();
   const int o_lo = need_edge ? 0 : 2 * AT, o_hi = need_node ? qkvw : 2 * AT;
-  for (int m = 0; m < mt; ++m) {
-    const int ra = 16 * m + g, rb = ra + 8;
-    const unsigned short* ta = tab + ra * TC;
-    const unsigned short* tb = tab + rb * TC;
-    float c1[NF][4];
+  constexpr int MB = NF <= 2 ? 2 : 1;                   // row tiles per pass (they share every B fragment)
+  for (int m0 = 0; m0 < mt; m0 += MB) {
+    float c1[MB][NF][4];
 #pragma unroll
-    for (int jn = 0; jn < NF; ++jn)
+    for (int mb = 0; mb < MB; ++mb)
 #pragma unroll
-      for (int q = 0; q < 4; ++q) c1[jn][q] = 0.f;
+      for (int jn = 0; jn < NF; ++jn)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) c1[mb][jn][q] = 0.f;
     for (int s = 0; s < ks; ++s) {
       const int j0 = 8 * s + t, j1 = j0 + 4;
-      uint32_t ah[4], al[4];
-      const Split a0 = split_tf32(pl[ta[j0]]), a1 = split_tf32(pl[tb[j0]]), a2 = split_tf32(pl[ta[j1]]), a3 = split_tf32(pl[tb[j1]]);
-      ah[0] = a0.hi; al[0] = a0.lo; ah[1] = a1.hi; al[1] = a1.lo; ah[2] = a2.hi; al[2] = a2.lo; ah[3] = a3.hi; al[3] = a3.lo;
       const float d0 = j0 < n ? dv[j0] : 0.f, d1 = j1 < n ? dv[j1] : 0.f;
       const float* x0r = x + (j0 < n ? j0 : 0) * ldx + g;
       const float* x1r = x + (j1 < n ? j1 : 0) * ldx + g;
+      Split b0[NF], b1[NF];
 #pragma unroll
       for (int jn = 0; jn < NF; ++jn) {
-        if (jn < nf) {
-          const Split b0 = split_tf32(x0r[8 * jn] * d0), b1 = split_tf32(x1r[8 * jn] * d1);
-          mma3(c1[jn], ah, al, b0, b1);
+        b0[jn] = split_tf32(jn < nf ? x0r[8 * jn] * d0 : 0.f);
+        b1[jn] = split_tf32(jn < nf ? x1r[8 * jn] * d1 : 0.f);
+      }
+#pragma unroll
+      for (int mb = 0; mb < MB; ++mb) {
+        if (m0 + mb < mt) {
+          const unsigned short* ta = tab + (16 * (m0 + mb) + g) * TC;
+          const unsigned short* tb = ta + 8 * TC;
+          uint32_t ah[4], al[4];
+          const Split a0 = split_tf32(pl[ta[j0]]), a1 = split_tf32(pl[tb[j0]]), a2 = split_tf32(pl[ta[j1]]), a3 = split_tf32(pl[tb[j1]]);
+          ah[0] = a0.hi; al[0] = a0.lo; ah[1] = a1.hi; al[1] = a1.lo; ah[2] = a2.hi; al[2] = a2.lo; ah[3] = a3.hi; al[3] = a3.lo;
+#pragma unroll
+          for (int jn = 0; jn < NF; ++jn)
+            if (jn < nf) mma3(c1[mb][jn], ah, al, b0[jn], b1[jn]);
         }
       }
     }
     // rows scaled by d_i: A^ x, re-used as the A operand of the Q|K|V contraction (k-step jn: column t <-> feature
     // 8 jn + 2t, column t+4 <-> feature 8 jn + 2t + 1)
-    const float da = ra < n ? dv[ra] : 0.f, db = rb < n ? dv[rb] : 0.f;
-    uint32_t qh[NF][4], ql[NF][4];
+    uint32_t qh[MB][NF][4], ql[MB][NF][4];
 #pragma unroll
-    for (int jn = 0; jn < NF; ++jn) {
-      if (jn < nf) {
-        const Split e0 = split_tf32(c1[jn][0] * da), e1 = split_tf32(c1[jn][1] * da);
-        const Split e2 = split_tf32(c1[jn][2] * db), e3 = split_tf32(c1[jn][3] * db);
-        qh[jn][0] = e0.hi; ql[jn][0] = e0.lo; qh[jn][1] = e2.hi; ql[jn][1] = e2.lo;
-        qh[jn][2] = e1.hi; ql[jn][2] = e1.lo; qh[jn][3] = e3.hi; ql[jn][3] = e3.lo;
+    for (int mb = 0; mb < MB; ++mb) {
+      const int ra = 16 * (m0 + mb) + g, rb = ra + 8;
+      const float da = ra < n ? dv[ra] : 0.f, db = rb < n ? dv[rb] : 0.f;
+#pragma unroll
+      for (int jn = 0; jn < NF; ++jn) {
+        const Split e0 = split_tf32(c1[mb][jn][0] * da), e1 = split_tf32(c1[mb][jn][1] * da);
+        const Split e2 = split_tf32(c1[mb][jn][2] * db), e3 = split_tf32(c1[mb][jn][3] * db);
+        qh[mb][jn][0] = e0.hi; ql[mb][jn][0] = e0.lo; qh[mb][jn][1] = e2.hi; ql[mb][jn][1] = e2.lo;
+        qh[mb][jn][2] = e1.hi; ql[mb][jn][2] = e1.lo; qh[mb][jn][3] = e3.hi; ql[mb][jn][3] = e3.lo;
       }
     }
     for (int o0 = o_lo; o0 < o_hi; o0 += 8) {
-      float c[4];
-      {
-        const float2 bv = WS ? *reinterpret_cast<const float2*>(bc + o0 + 2 * t) : __ldg(reinterpret_cast<const float2*>(bc + o0 + 2 * t));
-        c[0] = c[2] = bv.x;
-        c[1] = c[3] = bv.y;
-      }
+      const float2 bv = WS ? *reinterpret_cast<const float2*>(bc + o0 + 2 * t) : __ldg(reinterpret_cast<const float2*>(bc + o0 + 2 * t));
+      Split w0[NF], w1[NF];
 #pragma unroll
       for (int jn = 0; jn < NF; ++jn) {
-        if (jn < nf) {
-          const int k0 = 8 * jn + 2 * t, k1 = k0 + 1;
-          const float w0 = k0 < f_in_p ? (WS ? Wc[k0 * qkvw + o0 + g] : __ldg(Wc + k0 * qkvw + o0 + g)) : 0.f;
-          const float w1 = k1 < f_in_p ? (WS ? Wc[k1 * qkvw + o0 + g] : __ldg(Wc + k1 * qkvw + o0 + g)) : 0.f;
-          mma3(c, qh[jn], ql[jn], split_tf32(w0), split_tf32(w1));
-        }
+        const int k0 = 8 * jn + 2 * t, k1 = k0 + 1;
+        w0[jn] = split_tf32(k0 < f_in_p ? (WS ? Wc[k0 * qkvw + o0 + g] : __ldg(Wc + k0 * qkvw + o0 + g)) : 0.f);
+        w1[jn] = split_tf32(k1 < f_in_p ? (WS ? Wc[k1 * qkvw + o0 + g] : __ldg(Wc + k1 * qkvw + o0 + g)) : 0.f);
       }
       const int oc = o0 + 2 * t;
-      if (o0 < 2 * AT) {
-        if (ra < n) *reinterpret_cast<float2*>(qkc + ra * QKS + oc) = make_float2(c[0], c[1]);
-        if (rb < n) *reinterpret_cast<float2*>(qkc + rb * QKS + oc) = make_float2(c[2], c[3]);
-      } else {
-        if (ra < n) *reinterpret_cast<float2*>(vcol + ra * ldv + (oc - 2 * AT)) = make_float2(c[0], c[1]);
-        if (rb < n) *reinterpret_cast<float2*>(vcol + rb * ldv + (oc - 2 * AT)) = make_float2(c[2], c[3]);
+#pragma unroll
+      for (int mb = 0; mb < MB; ++mb) {
+        if (m0 + mb < mt) {
+          float c[4] = {bv.x, bv.y, bv.x, bv.y};
+#pragma unroll
+          for (int jn = 0; jn < NF; ++jn)
+            if (jn < nf) mma3(c, qh[mb][jn], ql[mb][jn], w0[jn], w1[jn]);
+          const int ra = 16 * (m0 + mb) + g, rb = ra + 8;
+          if (o0 < 2 * AT) {
+            if (ra < n) *reinterpret_cast<float2*>(qkc + ra * QKS + oc) = make_float2(c[0], c[1]);
+            if (rb < n) *reinterpret_cast<float2*>(qkc + rb * QKS + oc) = make_float2(c[2], c[3]);
+          } else {
+            if (ra < n) *reinterpret_cast<float2*>(vcol + ra * ldv + (oc - 2 * AT)) = make_float2(c[0], c[1]);
+            if (rb < n) *reinterpret_cast<float2*>(vcol + rb * ldv + (oc - 2 * AT)) = make_float2(c[2], c[3]);
+          }
+        }
       }
     }
   }
   __syncwarp();
   // ---- attention map (attention.py:35-49): mean over the 4 heads and both orientations of tanh(Q_h.K_h / sqrt(out_dim))
   if (need_edge) {
+    const float scale2 = scale * 2.8853900817779268f;
     for (int p = lane; p < P; p += 32) {
       const unsigned ij = pix[p];
       const int i = ij >> 8, j = ij & 255;
@@ -981,9 +997,9 @@ __device__ __noinline__ void channel_chain_mma(int lane, const float* pl, const 
           p1 = fma2(lo2(a1), lo2(b1), p1); p1 = fma2(hi2(a1), hi2(b1), p1);
           p2 = fma2(lo2(a2), lo2(b2), p2); p2 = fma2(hi2(a2), hi2(b2), p2);
         }
-        m += tanh_fast((p1.x + p1.y) * scale) + tanh_fast((p2.x + p2.y) * scale);
+        m += sig2((p1.x + p1.y) * scale2) + sig2((p2.x + p2.y) * scale2);
       }
-      Mc[p] = m * 0.125f;
+      Mc[p] = fmaf(-0.25f, m, 1.f);             // mean of the 8 tanh = 1 - (2 / 8) * sum of 1 / (exp(2 z) + 1)
     }
   }
 }
