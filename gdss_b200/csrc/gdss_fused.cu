@@ -562,12 +562,24 @@ DEVINL void mma_tf32(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
-// c += A B with both operands split (A: ah/al, B: bh/bl fragments)
-DEVINL void mma3(float (&c)[4], const uint32_t (&ah)[4], const uint32_t (&al)[4], const Split& b0, const Split& b1) {
-  mma_tf32(c, al, b0.hi, b1.hi);
-  mma_tf32(c, ah, b0.lo, b1.lo);
-  mma_tf32(c, ah, b0.hi, b1.hi);
+// One output tile accumulated as three independent chains (main term, two correction terms): a dependent mma.sync
+// issues only every ~20 cycles, so every k-step puts three independent instructions in flight instead of three chained ones.
+struct Acc { float m[4], s0[4], s1[4]; };
+
+DEVINL void acc_init(Acc& a, float b0, float b1) {
+  a.m[0] = a.m[2] = b0;
+  a.m[1] = a.m[3] = b1;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) a.s0[q] = a.s1[q] = 0.f;
 }
+
+DEVINL void mma3(Acc& c, const uint32_t (&ah)[4], const uint32_t (&al)[4], const Split& b0, const Split& b1) {
+  mma_tf32(c.s0, al, b0.hi, b1.hi);
+  mma_tf32(c.s1, ah, b0.lo, b1.lo);
+  mma_tf32(c.m, ah, b0.hi, b1.hi);
+}
+
+DEVINL float acc_get(const Acc& c, int q) { return c.m[q] + (c.s0[q] + c.s1[q]); }
 
 // per-pixel MLP of one AttentionLayer (attention.py:109-114) on the tensor cores: one warp = 16 pixels per tile, the
 // three layers chained in registers (C fragment -> next A fragment), weights held as split B fragments.
@@ -617,9 +629,9 @@ DEVINL void edge_mlp_mma(const float* M, int MS, const float* pin, int PM, const
     const int pa = tile * 16 + g, pb = pa + 8;
     const int pac = pa < P ? pa : P - 1, pbc = pb < P ? pb : P - 1;
     // ---- layer 1: A fragments gathered from the channel planes
-    float c[2][4];
+    Acc c[2];
 #pragma unroll
-    for (int j = 0; j < 2; ++j) { c[j][0] = bia1[j][0]; c[j][1] = bia1[j][1]; c[j][2] = bia1[j][0]; c[j][3] = bia1[j][1]; }
+    for (int j = 0; j < 2; ++j) acc_init(c[j], bia1[j][0], bia1[j][1]);
 #pragma unroll
     for (int s = 0; s < 2; ++s) {
       if (s < ks1) {
@@ -642,32 +654,32 @@ DEVINL void edge_mlp_mma(const float* M, int MS, const float* pin, int PM, const
     }
     __syncwarp();                    // every lane has read its inputs (in-place update below)
     if (NLIN == 3) {
-      float d[2][4];
+      Acc d[2];
 #pragma unroll
-      for (int j = 0; j < 2; ++j) { d[j][0] = bia2[j][0]; d[j][1] = bia2[j][1]; d[j][2] = bia2[j][0]; d[j][3] = bia2[j][1]; }
+      for (int j = 0; j < 2; ++j) acc_init(d[j], bia2[j][0], bia2[j][1]);
 #pragma unroll
       for (int s = 0; s < 2; ++s) {
         uint32_t ah[4], al[4];
-        const Split e0 = split_tf32(elu_f(c[s][0])), e1 = split_tf32(elu_f(c[s][1]));
-        const Split e2 = split_tf32(elu_f(c[s][2])), e3 = split_tf32(elu_f(c[s][3]));
+        const Split e0 = split_tf32(elu_f(acc_get(c[s], 0))), e1 = split_tf32(elu_f(acc_get(c[s], 1)));
+        const Split e2 = split_tf32(elu_f(acc_get(c[s], 2))), e3 = split_tf32(elu_f(acc_get(c[s], 3)));
         ah[0] = e0.hi; al[0] = e0.lo; ah[1] = e2.hi; al[1] = e2.lo; ah[2] = e1.hi; al[2] = e1.lo; ah[3] = e3.hi; al[3] = e3.lo;
 #pragma unroll
         for (int j = 0; j < 2; ++j) mma3(d[j], ah, al, w2[s][j][0], w2[s][j][1]);
       }
 #pragma unroll
-      for (int j = 0; j < 2; ++j)
-#pragma unroll
-        for (int q = 0; q < 4; ++q) c[j][q] = d[j][q];
+      for (int j = 0; j < 2; ++j) c[j] = d[j];
     }
-    float o[4] = {bia3[0], bia3[1], bia3[0], bia3[1]};
+    Acc oa;
+    acc_init(oa, bia3[0], bia3[1]);
 #pragma unroll
     for (int s = 0; s < 2; ++s) {
       uint32_t ah[4], al[4];
-      const Split e0 = split_tf32(elu_f(c[s][0])), e1 = split_tf32(elu_f(c[s][1]));
-      const Split e2 = split_tf32(elu_f(c[s][2])), e3 = split_tf32(elu_f(c[s][3]));
+      const Split e0 = split_tf32(elu_f(acc_get(c[s], 0))), e1 = split_tf32(elu_f(acc_get(c[s], 1)));
+      const Split e2 = split_tf32(elu_f(acc_get(c[s], 2))), e3 = split_tf32(elu_f(acc_get(c[s], 3)));
       ah[0] = e0.hi; al[0] = e0.lo; ah[1] = e2.hi; al[1] = e2.lo; ah[2] = e1.hi; al[2] = e1.lo; ah[3] = e3.hi; al[3] = e3.lo;
-      mma3(o, ah, al, w3[s][0], w3[s][1]);
+      mma3(oa, ah, al, w3[s][0], w3[s][1]);
     }
+    const float o[4] = {acc_get(oa, 0), acc_get(oa, 1), acc_get(oa, 2), acc_get(oa, 3)};
     // ---- (S + S^T), mask_adjs, stores: channels 2t, 2t+1 of pixels pa (o[0], o[1]) and pb (o[2], o[3])
     if (2 * t < c_out) {
 #pragma unroll
@@ -696,12 +708,9 @@ DEVINL void node_mlp_mma(const float* V, int ldv, int K, const float* W1, const 
     const int ra = 16 * m + g, rb = ra + 8;
     const float* va = V + (ra < n ? ra : n - 1) * ldv;
     const float* vb = V + (rb < n ? rb : n - 1) * ldv;
-    float c[2][4];
+    Acc c[2];
 #pragma unroll
-    for (int j = 0; j < 2; ++j) {
-      c[j][0] = c[j][2] = b1[8 * j + 2 * t];
-      c[j][1] = c[j][3] = b1[8 * j + 2 * t + 1];
-    }
+    for (int j = 0; j < 2; ++j) acc_init(c[j], b1[8 * j + 2 * t], b1[8 * j + 2 * t + 1]);
 #pragma unroll 2
     for (int k0 = 0; k0 < K; k0 += 8) {
       uint32_t ah[4], al[4];
@@ -717,22 +726,21 @@ DEVINL void node_mlp_mma(const float* V, int ldv, int K, const float* W1, const 
     uint32_t eh[2][4], el[2][4];                       // ELU(h1) as the A fragments of the second linear (permuted k order)
 #pragma unroll
     for (int s = 0; s < 2; ++s) {
-      const Split e0 = split_tf32(elu_f(c[s][0])), e1 = split_tf32(elu_f(c[s][1]));
-      const Split e2 = split_tf32(elu_f(c[s][2])), e3 = split_tf32(elu_f(c[s][3]));
+      const Split e0 = split_tf32(elu_f(acc_get(c[s], 0))), e1 = split_tf32(elu_f(acc_get(c[s], 1)));
+      const Split e2 = split_tf32(elu_f(acc_get(c[s], 2))), e3 = split_tf32(elu_f(acc_get(c[s], 3)));
       eh[s][0] = e0.hi; el[s][0] = e0.lo; eh[s][1] = e2.hi; el[s][1] = e2.lo;
       eh[s][2] = e1.hi; el[s][2] = e1.lo; eh[s][3] = e3.hi; el[s][3] = e3.lo;
     }
     const float fa = ra < n ? fl[ra] : 0.f, fb = rb < n ? fl[rb] : 0.f;
     for (int o0 = 0; o0 < h; o0 += 8) {
-      float d[4];
-      d[0] = d[2] = b2[o0 + 2 * t];
-      d[1] = d[3] = b2[o0 + 2 * t + 1];
+      Acc d;
+      acc_init(d, b2[o0 + 2 * t], b2[o0 + 2 * t + 1]);
 #pragma unroll
       for (int s = 0; s < 2; ++s) {
         const Split w0 = split_tf32(W2[(8 * s + 2 * t) * h + o0 + g]), w1 = split_tf32(W2[(8 * s + 2 * t + 1) * h + o0 + g]);
         mma3(d, eh[s], el[s], w0, w1);
       }
-      float v[4] = {d[0] * fa, d[1] * fa, d[2] * fb, d[3] * fb};
+      float v[4] = {acc_get(d, 0) * fa, acc_get(d, 1) * fa, acc_get(d, 2) * fb, acc_get(d, 3) * fb};
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         v[q] = tanh_fast(v[q]);
@@ -917,19 +925,24 @@ __device__ __noinline__ void channel_chain_mma(int lane, const float* pl, const 
         b0[jn] = split_tf32(jn < nf ? x0r[8 * jn] * d0 : 0.f);
         b1[jn] = split_tf32(jn < nf ? x1r[8 * jn] * d1 : 0.f);
       }
+      uint32_t ah[MB][4], al[MB][4];
 #pragma unroll
       for (int mb = 0; mb < MB; ++mb) {
-        if (m0 + mb < mt) {
-          const unsigned short* ta = tab + (16 * (m0 + mb) + g) * TC;
-          const unsigned short* tb = ta + 8 * TC;
-          uint32_t ah[4], al[4];
-          const Split a0 = split_tf32(pl[ta[j0]]), a1 = split_tf32(pl[tb[j0]]), a2 = split_tf32(pl[ta[j1]]), a3 = split_tf32(pl[tb[j1]]);
-          ah[0] = a0.hi; al[0] = a0.lo; ah[1] = a1.hi; al[1] = a1.lo; ah[2] = a2.hi; al[2] = a2.lo; ah[3] = a3.hi; al[3] = a3.lo;
+        const int mrow = m0 + mb < mt ? m0 + mb : m0;            // (a missing second tile repeats the first; never stored)
+        const unsigned short* ta = tab + (16 * mrow + g) * TC;
+        const unsigned short* tb = ta + 8 * TC;
+        const Split a0 = split_tf32(pl[ta[j0]]), a1 = split_tf32(pl[tb[j0]]), a2 = split_tf32(pl[ta[j1]]), a3 = split_tf32(pl[tb[j1]]);
+        ah[mb][0] = a0.hi; al[mb][0] = a0.lo; ah[mb][1] = a1.hi; al[mb][1] = a1.lo;
+        ah[mb][2] = a2.hi; al[mb][2] = a2.lo; ah[mb][3] = a3.hi; al[mb][3] = a3.lo;
+      }
+      // term-major issue order: consecutive mma.sync hit different accumulators
+#pragma unroll
+      for (int term = 0; term < 3; ++term)
+#pragma unroll
+        for (int mb = 0; mb < MB; ++mb)
 #pragma unroll
           for (int jn = 0; jn < NF; ++jn)
-            if (jn < nf) mma3(c1[mb][jn], ah, al, b0[jn], b1[jn]);
-        }
-      }
+            mma_tf32(c1[mb][jn], term == 0 ? al[mb] : ah[mb], term == 1 ? b0[jn].lo : b0[jn].hi, term == 1 ? b1[jn].lo : b1[jn].hi);
     }
     // rows scaled by d_i: A^ x, re-used as the A operand of the Q|K|V contraction (k-step jn: column t <-> feature
     // 8 jn + 2t, column t+4 <-> feature 8 jn + 2t + 1)
@@ -959,10 +972,12 @@ __device__ __noinline__ void channel_chain_mma(int lane, const float* pl, const 
 #pragma unroll
       for (int mb = 0; mb < MB; ++mb) {
         if (m0 + mb < mt) {
-          float c[4] = {bv.x, bv.y, bv.x, bv.y};
+          Acc ca;
+          acc_init(ca, bv.x, bv.y);
 #pragma unroll
           for (int jn = 0; jn < NF; ++jn)
-            if (jn < nf) mma3(c, qh[mb][jn], ql[mb][jn], w0[jn], w1[jn]);
+            if (jn < nf) mma3(ca, qh[mb][jn], ql[mb][jn], w0[jn], w1[jn]);
+          const float c[4] = {acc_get(ca, 0), acc_get(ca, 1), acc_get(ca, 2), acc_get(ca, 3)};
           const int ra = 16 * (m0 + mb) + g, rb = ra + 8;
           if (o0 < 2 * AT) {
             if (ra < n) *reinterpret_cast<float2*>(qkc + ra * QKS + oc) = make_float2(c[0], c[1]);
