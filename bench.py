@@ -210,8 +210,8 @@ def workload_config(args, wl, B):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="zinc250k_v2", choices=list(WORKLOADS))
     ap.add_argument("--batch", type=int, default=0)
@@ -222,6 +222,7 @@ def main():
     ap.add_argument("--no-profile", action="store_true")
     ap.add_argument("--no-torch-baseline", action="store_true")
     ap.add_argument("--torch-batch", type=int, default=10000)
+    ap.add_argument("--burn-in", type=int, default=20, help="untimed solver steps before the warm-up steps")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     weights = load_weights(wl)
@@ -264,6 +265,9 @@ def main():
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    # ---- burn-in (untimed, before the W warm-up steps): clocks out of idle, allocator / module loading / L2 settled
+    x, adj, xm, am = eng.sample(sdesc, table, fl_local, n_iters=args.burn_in, **kw)
+    barrier()
     # ---- warm-up: W untimed steps from the prior
     x, adj, xm, am = eng.sample(sdesc, table, fl_local, n_iters=max(W, 1), **kw)
     barrier()

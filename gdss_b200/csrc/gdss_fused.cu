@@ -1550,6 +1550,14 @@ DEVINL void tmem_st8(uint32_t taddr, const float* v) {
                : "memory");
 }
 
+DEVINL void tmem_ld8_nowait(uint32_t taddr, uint32_t* r) {      // results are valid after tmem_ld_wait()
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+}
+DEVINL void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory"); }
+
 DEVINL void tmem_ld8(uint32_t taddr, float* v) {
   uint32_t r[8];
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n"
@@ -1651,26 +1659,38 @@ __global__ void __launch_bounds__(256, 1) final_edge_tc_kernel(FinalTriArgs a, i
   uint32_t phase = 0;
   bool ok = true;
   const int ntiles = NODE ? (a.B * N + 127) / 128 : a.meta[1];
+  // channel values of this thread's pixel for the first tile; every later tile is fetched one tile ahead (the loads
+  // are in flight during the two contractions and epilogues of the current tile)
+  float v[KH];
+  {
+    const int64_t gp0 = (int64_t)blockIdx.x * 128 + row;
+#pragma unroll
+    for (int kk = 0; kk < KH; ++kk) {
+      const int c = half * KH + kk;
+      v[kk] = (c < K1 && (int)blockIdx.x < ntiles) ? __ldg(a.stackT + (int64_t)c * a.pstride + gp0) : 0.f;
+    }
+  }
   for (int tile = blockIdx.x; tile < ntiles && ok; tile += gridDim.x) {
     const int64_t gp = (int64_t)tile * 128 + row;
     // ---- layer-1 operand: channel values of this pixel -> hi / lo -> tensor memory
-    {
-      float v[KH];
+#pragma unroll
+    for (int kk = 0; kk < KH; kk += 4) {
+      float h[4], l[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const Split sp = split_tf32(v[kk + q]);
+        h[q] = __uint_as_float(sp.hi);
+        l[q] = __uint_as_float(sp.lo);
+      }
+      tmem_st4(tlane + colAhi + half * KH + kk, h[0], h[1], h[2], h[3]);
+      tmem_st4(tlane + colAhi + K1P + half * KH + kk, l[0], l[1], l[2], l[3]);
+    }
+    if (tile + (int)gridDim.x < ntiles) {
+      const int64_t gpn = gp + (int64_t)gridDim.x * 128;
 #pragma unroll
       for (int kk = 0; kk < KH; ++kk) {
         const int c = half * KH + kk;
-        v[kk] = c < K1 ? __ldg(a.stackT + (int64_t)c * a.pstride + gp) : 0.f;
-      }
-#pragma unroll
-      for (int kk = 0; kk < KH; kk += 4) {
-        float h[4], l[4];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          h[q] = tf32_rna(v[kk + q]);
-          l[q] = tf32_rna(v[kk + q] - h[q]);
-        }
-        tmem_st4(tlane + colAhi + half * KH + kk, h[0], h[1], h[2], h[3]);
-        tmem_st4(tlane + colAhi + K1P + half * KH + kk, l[0], l[1], l[2], l[3]);
+        v[kk] = c < K1 ? __ldg(a.stackT + (int64_t)c * a.pstride + gpn) : 0.f;
       }
     }
     tc_sync_before_mma();
@@ -1692,19 +1712,29 @@ __global__ void __launch_bounds__(256, 1) final_edge_tc_kernel(FinalTriArgs a, i
     phase ^= 1;
     asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
     // ---- epilogue 1: ELU(D + b1) -> hi / lo -> layer-2 operand
+    {
+      constexpr int NB8 = CH / 8;                      // 8-column groups of this thread's column half
+      constexpr int GB = NB8 % 3 == 0 ? 3 : (NB8 % 2 == 0 ? 2 : 1);      // groups per batch (one tcgen05.wait::ld per batch)
 #pragma unroll
-    for (int c0 = 0; c0 < CH; c0 += 8) {
-      const int col = half * CH + c0;
-      float d[8], h[8], l[8];
-      tmem_ld8(tlane + colD + col, d);
+      for (int b0 = 0; b0 < NB8; b0 += GB) {
+        uint32_t dr[GB][8];
 #pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        const float e = elu_f(d[q] + b1s[col + q]);
-        h[q] = tf32_rna(e);
-        l[q] = tf32_rna(e - h[q]);
+        for (int u = 0; u < GB; ++u) tmem_ld8_nowait(tlane + colD + half * CH + 8 * (b0 + u), dr[u]);
+        tmem_ld_wait();
+#pragma unroll
+        for (int u = 0; u < GB; ++u) {
+          const int col = half * CH + 8 * (b0 + u);
+          float h[8], l[8];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const Split sp = split_tf32(elu_f(__uint_as_float(dr[u][q]) + b1s[col + q]));
+            h[q] = __uint_as_float(sp.hi);
+            l[q] = __uint_as_float(sp.lo);
+          }
+          tmem_st8(tlane + colAhi + col, h);
+          tmem_st8(tlane + colAlo + col, l);
+        }
       }
-      tmem_st8(tlane + colAhi + col, h);
-      tmem_st8(tlane + colAlo + col, l);
     }
     tc_sync_before_mma();
     if (tid == 0) {
@@ -1766,13 +1796,27 @@ __global__ void __launch_bounds__(256, 1) final_edge_tc_kernel(FinalTriArgs a, i
     }
     // ---- epilogue 2: ELU(D + b2) . w3 + b3, zero diagonal / flag mask (ScoreNetwork_A.py:143-148), mirrored store
     float dot = 0.f;
+    {
+      constexpr int NB8 = CH / 8;
+      constexpr int GB = NB8 % 3 == 0 ? 3 : (NB8 % 2 == 0 ? 2 : 1);
+      float dot2 = 0.f;
 #pragma unroll
-    for (int c0 = 0; c0 < CH; c0 += 8) {
-      const int col = half * CH + c0;
-      float d[8];
-      tmem_ld8(tlane + colD + col, d);
+      for (int b0 = 0; b0 < NB8; b0 += GB) {
+        uint32_t dr[GB][8];
 #pragma unroll
-      for (int q = 0; q < 8; ++q) dot = fmaf(elu_f(d[q] + b2s[col + q]), w3s[col + q], dot);
+        for (int u = 0; u < GB; ++u) tmem_ld8_nowait(tlane + colD + half * CH + 8 * (b0 + u), dr[u]);
+        tmem_ld_wait();
+#pragma unroll
+        for (int u = 0; u < GB; ++u) {
+          const int col = half * CH + 8 * (b0 + u);
+#pragma unroll
+          for (int q = 0; q < 8; q += 2) {
+            dot = fmaf(elu_f(__uint_as_float(dr[u][q]) + b2s[col + q]), w3s[col + q], dot);
+            dot2 = fmaf(elu_f(__uint_as_float(dr[u][q + 1]) + b2s[col + q + 1]), w3s[col + q + 1], dot2);
+          }
+        }
+      }
+      dot += dot2;
     }
     if (half == 1) part[row] = dot;
     asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
