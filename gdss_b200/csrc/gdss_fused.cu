@@ -1088,8 +1088,8 @@ DEVINL void final_node_mlp(const FNet& net, const float* xs, int XSS, int n, con
     }                                                                  \
   } while (0)
 
-template <int NT, bool WSM>      // WSM: layer weights staged in shared memory by TMA (else read from global / L2)
-__global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1) fused_layers_kernel(const __grid_constant__ FusedArgs A) {
+template <int NT, bool WSM, int OCC>      // WSM: layer weights staged in shared memory by TMA (else read from global / L2)
+__global__ void __launch_bounds__(NT, OCC) fused_layers_kernel(const __grid_constant__ FusedArgs A) {
   extern __shared__ __align__(16) float sm[];
   __shared__ __align__(8) uint64_t mbar_q, mbar_m;
   long long tprev = A.prof ? clock64() : 0;
@@ -2068,24 +2068,25 @@ int launch_eval_fused(const gdss_ctx* ctx, const float* x, const float* adj, con
     fa.bucket = k;
     // Preferred: layer weights staged in shared memory by TMA with two CTAs of 256 threads per SM; if only the
     // weight-less plan fits twice, read the weights through L2 instead; the largest graphs run one CTA of 512.
+    // (three CTAs of 85 registers per SM with the weights read through L2 measured 5 % slower than two with staged weights)
     const int limit2 = (227 * 1024) / 2 - 1024;
     int64_t smem = plan_smem(ctx, nb[k], &fa.sl, true);
     cudaError_t e;
     if (smem <= limit2) {
-      e = cudaFuncSetAttribute(fused_layers_kernel<256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      e = cudaFuncSetAttribute(fused_layers_kernel<256, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e != cudaSuccess) return (int)e;
-      fused_layers_kernel<256, true><<<B, nb[k] <= 12 ? 128 : 256, smem, st>>>(fa);
+      fused_layers_kernel<256, true, 2><<<B, nb[k] <= 12 ? 128 : 256, smem, st>>>(fa);
     } else if (plan_smem(ctx, nb[k], &fa.sl, false) <= limit2) {
       smem = plan_smem(ctx, nb[k], &fa.sl, false);
-      e = cudaFuncSetAttribute(fused_layers_kernel<256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      e = cudaFuncSetAttribute(fused_layers_kernel<256, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e != cudaSuccess) return (int)e;
-      fused_layers_kernel<256, false><<<B, 256, smem, st>>>(fa);
+      fused_layers_kernel<256, false, 2><<<B, 256, smem, st>>>(fa);
     } else {
       smem = plan_smem(ctx, nb[k], &fa.sl, true);
       if (smem <= 0 || smem > ctx->smem_optin) return GDSS_E_UNSUPPORTED;
-      e = cudaFuncSetAttribute(fused_layers_kernel<512, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      e = cudaFuncSetAttribute(fused_layers_kernel<512, true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e != cudaSuccess) return (int)e;
-      fused_layers_kernel<512, true><<<B, 512, smem, st>>>(fa);
+      fused_layers_kernel<512, true, 1><<<B, 512, smem, st>>>(fa);
     }
     launched(K_FUSED, st);
     LAUNCH_CHECK();
