@@ -888,7 +888,10 @@ DEVINL void channel_pipeline(int lane, const float* pl, float* dv, const float* 
 template <bool WS, int HD, int NF>       // NF: compile-time bound of the feature tiles (f <= 8 NF)
 __device__ __noinline__ void channel_chain_mma(int lane, const float* pl, const unsigned short* tab, int TC, float* dv, const float* x, int ldx, int n,
                               int f, int f_in_p, const float* Wc, int qkvw, const float* bc, float* qkc, int QKS, float* vcol, int ldv,
-                              bool need_edge, bool need_node, const unsigned* pix, int P, float scale, float* Mc) {
+                              bool need_edge, bool need_node, const unsigned* pix, int P, float scale, float* Mc, int part, int nparts,
+                              int bar_id) {
+  // part / nparts: the warps of one channel split the row-tile passes and the pixels of the map; they meet at the named
+  // barrier bar_id once Q|K are complete (each computes the degrees itself: identical values)
   constexpr int AT = 4 * HD;
   const int g = lane >> 2, t = lane & 3;
   const int ks = (n + 7) >> 3, mt = (n + 15) >> 4, nf = (f + 7) >> 3;      // k-steps over nodes, row tiles, feature tiles (<= 4)
@@ -906,7 +909,7 @@ __device__ __noinline__ void channel_chain_mma(int lane, const float* pl, const 
   __syncwarp();
   const int o_lo = need_edge ? 0 : 2 * AT, o_hi = need_node ? qkvw : 2 * AT;
   constexpr int MB = NF <= 2 ? 2 : 1;                   // row tiles per pass (they share every B fragment)
-  for (int m0 = 0; m0 < mt; m0 += MB) {
+  for (int m0 = part * MB; m0 < mt; m0 += MB * nparts) {
     float c1[MB][NF][4];
 #pragma unroll
     for (int mb = 0; mb < MB; ++mb)
@@ -990,11 +993,12 @@ __device__ __noinline__ void channel_chain_mma(int lane, const float* pl, const 
       }
     }
   }
-  __syncwarp();
+  if (nparts > 1) asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(32 * nparts) : "memory");
+  else __syncwarp();
   // ---- attention map (attention.py:35-49): mean over the 4 heads and both orientations of tanh(Q_h.K_h / sqrt(out_dim))
   if (need_edge) {
     const float scale2 = scale * 2.8853900817779268f;
-    for (int p = lane; p < P; p += 32) {
+    for (int p = part * 32 + lane; p < P; p += 32 * nparts) {
       const unsigned ij = pix[p];
       const int i = ij >> 8, j = ij & 255;
       const float* qi = qkc + i * QKS;
@@ -1260,21 +1264,26 @@ __global__ void __launch_bounds__(NT, OCC) fused_layers_kernel(const __grid_cons
       const bool more = l + 1 < net.depth;
       const int LDV = C * h + 4;       // row stride of the V rows [i][c][h] (+4: conflict-free mma A fragments)
       const float* wqp = WSM ? wq : L.blk_q;
-      if (2 * C > nwarps) {
+      const bool chain_mma = A.use_mma && ((f <= 16 && attn == 16) || (f <= 32 && attn == 32));
+      if (chain_mma || 2 * C > nwarps) {
         // ---- one warp per channel, no CTA barrier inside the chain
         if (WSM) {
           mbar_wait_parity(&mbar_q, ph_q);
           ph_q ^= 1;
         }
-        for (int c = warp; c < C; c += nwarps) {
+        const int nparts = (chain_mma && nwarps >= 2 * C) ? nwarps / C : 1;       // warps per channel (mma chain only)
+        for (int u = warp; u < C * nparts; u += nwarps) {
+          const int c = nparts > 1 ? u % C : u, part = nparts > 1 ? u / C : 0;
           const float* Wc = wqp + c * L.f_in_p * L.qkvw;
           const float* bc = wqp + L.bq_o + c * L.qkvw;
           if (A.use_mma && f <= 16 && attn == 16) {
             channel_chain_mma<WSM, 4, 2>(lane, pin + c * PM, tab, S.TC, dinv + c * NBP, xin, XS, n, f, L.f_in_p, Wc, L.qkvw, bc,
-                                         QK + c * n * QKS, QKS, R2 + c * h, LDV, L.need_edge, L.need_node, pix, P, scale, R1 + c * RS);
+                                         QK + c * n * QKS, QKS, R2 + c * h, LDV, L.need_edge, L.need_node, pix, P, scale, R1 + c * RS, part, nparts, 2 + c);
           } else if (A.use_mma && f <= 32 && attn == 32) {
             channel_chain_mma<WSM, 8, 4>(lane, pin + c * PM, tab, S.TC, dinv + c * NBP, xin, XS, n, f, L.f_in_p, Wc, L.qkvw, bc,
-                                         QK + c * n * QKS, QKS, R2 + c * h, LDV, L.need_edge, L.need_node, pix, P, scale, R1 + c * RS);
+                                         QK + c * n * QKS, QKS, R2 + c * h, LDV, L.need_edge, L.need_node, pix, P, scale, R1 + c * RS, part, nparts, 2 + c);
+          } else if (part > 0) {
+            // (the FFMA chain runs one warp per channel)
           } else if (attn == 16)
             channel_pipeline<WSM, 4>(lane, pin + c * PM, dinv + c * NBP, xin, XS, n, f, R1 + c * RS, Wc, L.qkvw, bc, QK + c * n * QKS, QKS,
                                      R2 + c * h, LDV, h, L.need_edge, L.need_node, pix, P, scale, R1 + c * RS);
@@ -2076,7 +2085,7 @@ int launch_eval_fused(const gdss_ctx* ctx, const float* x, const float* adj, con
       e = cudaFuncSetAttribute(fused_layers_kernel<256, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e != cudaSuccess) return (int)e;
       fused_layers_kernel<256, true, 2><<<B, nb[k] <= 12 ? 128 : 256, smem, st>>>(fa);
-    } else if (plan_smem(ctx, nb[k], &fa.sl, false) <= limit2) {
+    } else if (plan_smem(ctx, nb[k], &fa.sl, false) <= limit2) {   // (one CTA of 512 with staged weights measured 20 % slower here)
       smem = plan_smem(ctx, nb[k], &fa.sl, false);
       e = cudaFuncSetAttribute(fused_layers_kernel<256, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e != cudaSuccess) return (int)e;
