@@ -32,11 +32,11 @@ sys.path.insert(0, ROOT)
 WORKLOADS = {
     "zinc250k_v2": dict(ckpt="zinc250k_v2", N=38, F=9, B=10000, sde_x=("VP", .1, 1.), sde_adj=("VE", .2, 1.),
                         predictor="Reverse", corrector="Langevin", snr=.2, scale_eps=.8, evals=2,
-                        flop_eval=6.504e6 + 5.849e7, flop_final=2 * 1444 * (46 * 92 + 92 * 92 + 92), cpu_B=32, cpu_steps=4,
+                        flop_eval=6.504e6 + 5.849e7, flop_final=2 * 1444 * (46 * 92 + 92 * 92 + 92), flop_final_x=2 * 38 * (41 * 82 + 82 * 82 + 82 * 9), cpu_B=32, cpu_steps=4,
                         desc="C3 ZINC250k v2 (N=38, F=9, ScoreNetworkX_GMH + ScoreNetworkA) Reverse+Langevin snr .2 scale_eps .8"),
     "qm9_s4": dict(ckpt="qm9", N=9, F=4, B=10000, sde_x=("VE", .1, 1.), sde_adj=("VE", .1, 1.), predictor="S4",
                    corrector="None", snr=.2, scale_eps=.7, evals=1, flop_eval=1.561e5 + 1.260e6,
-                   flop_final=2 * 81 * (22 * 44 + 44 * 44 + 44), cpu_B=1000, cpu_steps=8,
+                   flop_final=2 * 81 * (22 * 44 + 44 * 44 + 44), flop_final_x=2 * 9 * (36 * 72 + 72 * 72 + 72 * 4), cpu_B=1000, cpu_steps=8,
                    desc="C2 QM9 (N=9, F=4, ScoreNetworkX + ScoreNetworkA) S4 snr .2 scale_eps .7"),
     "community_small": dict(ckpt="community_small", N=20, F=10, B=100, sde_x=("VP", .1, 1.), sde_adj=("VP", .1, 1.),
                             predictor="Euler", corrector="Langevin", snr=.05, scale_eps=.7, evals=2,
@@ -352,11 +352,15 @@ def main():
                     "share_of_step": k["share"], "pipe": pipe_name, "pipe_peak_tflops": pipe_peak,
                     "frac_of_pipe_peak": ach / pipe_peak, "note": note}
 
-        # the dominant kernel first: the fused per-graph layer kernel (everything except ScoreNetworkA.final)
-        roofline = roof("fused_layers_kernel", wl["flop_eval"] - wl["flop_final"],
-                        "FP32 FFMA pipe (strict fp32 parity); algorithmic FLOPs = the reference's dense GEMM count of both "
-                        "networks minus ScoreNetworkA.final, at padded N, no symmetry / flag / dead-layer credit",
-                        fp32_peak, "fp32 FFMA at the observed SM clock")
+        # the dominant kernel first: the fused per-graph layer kernel (everything except the two final MLPs)
+        flop_final_x = wl.get("flop_final_x", 0.0)
+        mma_peak = 148 * 512 * 2 * (clk["sm_mhz"] or peaks["sm_max_mhz"]) * 1e6 / 1e12 / 3.0
+        roofline = roof("fused_layers_kernel", wl["flop_eval"] - wl["flop_final"] - flop_final_x,
+                        "per-graph contractions on mma.sync m16n8k8 TF32 with the 3xTF32 split (strict fp32 parity), tanh / ELU / "
+                        "attention dot products on the FP32 and MUFU pipes; algorithmic FLOPs = the reference's dense GEMM count of "
+                        "both networks minus the two final MLPs, at padded N, no symmetry / flag / dead-layer credit; the kernel is "
+                        "issue / latency bound (profiles/README.md), not pipe bound",
+                        mma_peak, "mma.sync TF32 (512 FMA/clk/SM measured, tools/mma_probe.cu) / 3 (3xTF32) at the observed SM clock")
         roofline_final = roof("final_edge_kernel", wl["flop_final"],
                               "tcgen05 kind::tf32, 3xTF32 split (3 MMAs per product): the pipe peak is taken as "
                               "measured bf16 / 2 (TF32 rate) / 3; algorithmic FLOPs = dense count over all N^2 pixels",
