@@ -78,6 +78,8 @@ def lib():
         "gdss_pow_tensor": (C.c_int, [fp, fp, i32, i32, i32, vp]),
         "gdss_quantize": (C.c_int, [fp, fp, C.c_float, i64, vp]),
         "gdss_quantize_mol": (C.c_int, [fp, vp, i64, vp]),
+        "gdss_decode_mol": (C.c_int, [fp, fp, vp, vp, i32, i32, i32, vp]),
+        "gdss_init_flags": (C.c_int, [fp, fp, i32, i32, u64, i64, vp]),
         "gdss_launch_count": (i64, []),
         "gdss_prof_begin": (C.c_int, [vp]),
         "gdss_prof_end": (C.c_int, [fp, vp, i32]),

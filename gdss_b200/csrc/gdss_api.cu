@@ -189,6 +189,46 @@ __global__ void quantize_mol_kernel(const float* a, int64_t* out, int64_t n) {
   }
 }
 
+// Post-sampling decode of a molecule batch (sampler.py:131-138) in one pass, compact int8 outputs:
+//   bond[b][i][j]  = class index of quantize_mol(adj) - 1 with -1 -> 3  (0 single, 1 double, 2 triple, 3 no bond)
+//   atom[b][i][f]  = x > 0.5 for f < F;  atom[b][i][F] = 1 - sum_f atom[b][i][f]   (the virtual-atom channel)
+__global__ void decode_mol_kernel(const float* __restrict__ x, const float* __restrict__ adj, int8_t* __restrict__ atom,
+                                  int8_t* __restrict__ bond, int64_t rows, int N, int F) {
+  const int64_t nb = rows * N;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < nb; idx += (int64_t)gridDim.x * blockDim.x) {
+    const float v = adj[idx];
+    const int q = v >= 2.5f ? 3 : (v >= 1.5f ? 2 : (v >= 0.5f ? 1 : 0));
+    bond[idx] = (int8_t)(q == 0 ? 3 : q - 1);
+  }
+  for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < rows; r += (int64_t)gridDim.x * blockDim.x) {
+    int s = 0;
+    for (int f = 0; f < F; ++f) {
+      const int a = x[r * F + f] > 0.5f ? 1 : 0;
+      atom[r * (F + 1) + f] = (int8_t)a;
+      s += a;
+    }
+    atom[r * (F + 1) + F] = (int8_t)(1 - s);
+  }
+}
+
+// init_flags (utils/graph_utils.py:66-74) on the device: the reference draws a training graph uniformly and takes its
+// node flags, i.e. a node count from the training set's histogram.  cdf = inclusive cumulative counts of node numbers
+// 0..N (cdf[N] = number of training graphs); graph b draws u from the Philox stream (domain 2) and gets the first
+// n_b flags set, n_b = min { k : u * cdf[N] < cdf[k] }.
+__global__ void init_flags_kernel(const float* __restrict__ cdf, float* __restrict__ flags, int B, int N, uint64_t seed,
+                                  int64_t graph_offset) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const uint64_t gid = (uint64_t)(graph_offset + b);
+  uint4 c = make_uint4(0u, (uint32_t)gid, ((uint32_t)(gid >> 32) & 0x3fffffffu) | (2u << 30), 0u);
+  const uint4 r = philox4x32_10(c, make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+  const float u = (float)(r.x >> 8) * (1.0f / 16777216.0f) * cdf[N];        // [0, total)
+  int n = N;
+  for (int k = 0; k <= N; ++k)
+    if (u < cdf[k]) { n = k; break; }
+  for (int i = 0; i < N; ++i) flags[(int64_t)b * N + i] = i < n ? 1.f : 0.f;
+}
+
 // full (unmirrored) batched product for the standalone pow_tensor helper
 __global__ void __launch_bounds__(256) bmm_kernel(const float* __restrict__ Lp, int64_t l_bs, const float* __restrict__ Ap,
                                                   int64_t a_bs, float* __restrict__ out, int64_t o_bs, int N) {
@@ -289,6 +329,27 @@ extern "C" int gdss_quantize_mol(const float* adj, int64_t* out, int64_t numel, 
   if (!adj || !out || numel <= 0) return GDSS_E_BADARG;
   if (gdss_device_count() == 0) return GDSS_E_UNSUPPORTED;
   quantize_mol_kernel<<<grid_for(numel), 256, 0, (cudaStream_t)stream>>>(adj, out, numel);
+  count_launch();
+  LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int gdss_decode_mol(const float* x, const float* adj, int8_t* atom, int8_t* bond, int32_t B, int32_t N, int32_t F,
+                               void* stream) {
+  if (!x || !adj || !atom || !bond || B <= 0 || N <= 0 || F <= 0) return GDSS_E_BADARG;
+  if (gdss_device_count() == 0) return GDSS_E_UNSUPPORTED;
+  const int64_t rows = (int64_t)B * N;
+  decode_mol_kernel<<<grid_for(rows * N), 256, 0, (cudaStream_t)stream>>>(x, adj, atom, bond, rows, N, F);
+  count_launch();
+  LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int gdss_init_flags(const float* node_count_cdf, float* flags, int32_t B, int32_t N, uint64_t seed,
+                               int64_t graph_offset, void* stream) {
+  if (!node_count_cdf || !flags || B <= 0 || N <= 0) return GDSS_E_BADARG;
+  if (gdss_device_count() == 0) return GDSS_E_UNSUPPORTED;
+  init_flags_kernel<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(node_count_cdf, flags, B, N, seed, graph_offset);
   count_launch();
   LAUNCH_CHECK();
   return 0;

@@ -88,6 +88,38 @@ def quantize_mol(adjs):
     return out.cpu().numpy()
 
 
+def decode_mol(x, adj, one_hot=True):
+    """sampler.py:131-138 on the device: quantize_mol -> bond-class remap (0,1,2,3 -> 3,0,1,2) and x > 0.5 with the
+    virtual-atom channel appended.  Returns (x [B,N,F+1], adj) where adj is the reference's one-hot [B,4,N,N] int64
+    (one_hot=True) or the compact int8 class index [B,N,N]; the fp32 state never leaves the device."""
+    require_cuda()
+    x, adj = _prep(x), _prep(adj)
+    B, N, F = x.shape
+    atom = torch.empty(B, N, F + 1, dtype=torch.int8, device=x.device)
+    bond = torch.empty(B, N, N, dtype=torch.int8, device=x.device)
+    with torch.cuda.device(x.device):
+        check(lib().gdss_decode_mol(x.data_ptr(), adj.data_ptr(), atom.data_ptr(), bond.data_ptr(), B, N, F, _stream(x)),
+              "gdss_decode_mol")
+    if not one_hot:
+        return atom, bond
+    return atom.to(torch.int64), torch.nn.functional.one_hot(bond.to(torch.int64), num_classes=4).permute(0, 3, 1, 2)
+
+
+def init_flags_device(node_counts, max_node_num, batch_size, device="cuda", seed=None, graph_offset=0):
+    """utils/graph_utils.py:66-74 without the host round trip: ``node_counts`` = the node numbers of the training
+    graphs (any iterable of ints); flags [batch_size, max_node_num] are drawn on the device from their histogram."""
+    require_cuda()
+    N = int(max_node_num)
+    hist = np.bincount(np.clip(np.asarray(list(node_counts), dtype=np.int64), 0, N), minlength=N + 1).astype(np.float64)
+    cdf = torch.from_numpy(np.cumsum(hist).astype(np.float32)).to(device)
+    flags = torch.empty(int(batch_size), N, device=device)
+    seed = torch.initial_seed() if seed is None else seed
+    with torch.cuda.device(flags.device):
+        check(lib().gdss_init_flags(cdf.data_ptr(), flags.data_ptr(), int(batch_size), N, int(seed) & (2 ** 64 - 1),
+                                    int(graph_offset), _stream(flags)), "gdss_init_flags")
+    return flags
+
+
 def node_flags(adj, eps=1e-5):
     """utils/graph_utils.py:33-39 (host-side glue, torch)."""
     flags = torch.abs(adj).sum(-1).gt(eps).to(dtype=torch.float32)

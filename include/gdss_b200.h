@@ -176,6 +176,16 @@ int gdss_gen_noise(float* out, const float* raw_or_null, const float* flags, int
 int gdss_pow_tensor(const float* adj, float* out /* [B,cnum,N,N] */, int32_t B, int32_t N, int32_t cnum, void* stream);
 int gdss_quantize(const float* adj, float* out, float thr, int64_t numel, void* stream);
 int gdss_quantize_mol(const float* adj, int64_t* out, int64_t numel, void* stream);
+/* Post-sampling decode of a molecule batch in one pass (replaces sampler.py:131-138: quantize_mol, the bond-class
+ * remap 0,1,2,3 -> 3,0,1,2, x > 0.5 and the virtual-atom channel) with compact int8 outputs:
+ * atom [B][N][F+1], bond [B][N][N] (class index; one_hot(bond, 4).permute(0,3,1,2) is the reference's adj). */
+int gdss_decode_mol(const float* x, const float* adj, int8_t* atom, int8_t* bond, int32_t B, int32_t N, int32_t F,
+                    void* stream);
+/* init_flags (utils/graph_utils.py:66-74) on the device: node_count_cdf = float[N+1], inclusive cumulative counts of
+ * the training graphs' node numbers 0..N; graph b gets its first n_b flags set, n_b drawn from that histogram with the
+ * library's Philox stream keyed by (seed, graph_offset + b): independent of how the batch is sharded. */
+int gdss_init_flags(const float* node_count_cdf, float* flags, int32_t B, int32_t N, uint64_t seed, int64_t graph_offset,
+                    void* stream);
 
 /* ---- introspection for tests / profiling ---------------------------------------------- */
 /* number of kernel launches the library has enqueued since process start (all contexts) */

@@ -112,6 +112,18 @@ def quantize_mol(adjs: Tensor) -> np.ndarray:
     return out.numpy()
 
 
+def decode_mol(x: Tensor, adj: Tensor) -> Tuple[Tensor, Tensor]:
+    """sampler.py:131-138 -- what Sampler_mol does with the sampler's output before gen_mol: quantize_mol, bond classes
+    remapped (0 no bond, 1 S, 2 D, 3 T) -> (3, 0, 1, 2), one-hot over 4 classes as [B,4,N,N]; atoms x > 0.5 with the
+    virtual-atom channel 1 - sum appended.  -> (x [B,N,F+1] int64, adj [B,4,N,N] int64)."""
+    q = torch.from_numpy(quantize_mol(adj)) - 1
+    q[q == -1] = 3
+    a = torch.nn.functional.one_hot(q, num_classes=4).permute(0, 3, 1, 2)
+    xi = torch.where(x > 0.5, 1, 0)
+    xi = torch.concat([xi, 1 - xi.sum(dim=-1, keepdim=True)], dim=-1)
+    return xi, a
+
+
 # --------------------------------------------------------------------------
 # layers  (models/layers.py, models/attention.py)
 # --------------------------------------------------------------------------

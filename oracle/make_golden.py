@@ -13,6 +13,8 @@ Produces
                                   numpy's frozen RandomState(seed) stream so the same raw draws
                                   can be replayed through the oracle and injected into the
                                   CUDA path
+  tests/golden/decode_zinc_v2.npz sampler.py:131-138 (quantize_mol, bond-class remap, one-hot, atom threshold + virtual
+                                  atom) applied to the final state of the full ZINC250k v2 reference run
   tests/golden/MANIFEST.json      what was generated, from which torch version
 
 The reference code is imported and called, never copied.
@@ -145,6 +147,22 @@ def make_traj():
     return out
 
 
+def make_decode():
+    """sampler.py:131-138 executed literally on the final state of the full ZINC250k v2 reference run (quantize_mol is
+    the reference's own function; the remaining lines are inline in Sampler_mol.sample, which needs rdkit to import)."""
+    from utils.graph_utils import quantize_mol
+    z = np.load(os.path.join(GOLD, "traj_zinc_v2_rev_lang_full.npz"))
+    x, adj = torch.from_numpy(z["x"]), torch.from_numpy(z["adj"])
+    samples_int = quantize_mol(adj.clone())
+    samples_int = samples_int - 1
+    samples_int[samples_int == -1] = 3
+    a = torch.nn.functional.one_hot(torch.tensor(samples_int), num_classes=4).permute(0, 3, 1, 2)
+    xi = torch.where(x > 0.5, 1, 0)
+    xi = torch.concat([xi, 1 - xi.sum(dim=-1, keepdim=True)], dim=-1)
+    np.savez_compressed(os.path.join(GOLD, "decode_zinc_v2.npz"), x=xi.numpy().astype(np.int8), adj=a.numpy().astype(np.int8))
+    return {"decode_zinc_v2": [list(xi.shape), list(a.shape)]}
+
+
 def main():
     refimport.activate()
     torch.set_num_threads(os.cpu_count())
@@ -153,9 +171,20 @@ def main():
     manifest["ckpt"] = convert_ckpts()
     manifest["kat"] = make_kat()
     manifest["traj"] = make_traj()
+    manifest["decode"] = make_decode()
     with open(os.path.join(GOLD, "MANIFEST.json"), "w") as f:
         json.dump(manifest, f, indent=1, sort_keys=True)
 
 
+def only_decode():
+    """python oracle/make_golden.py decode : just the post-sampling decode fixture (needs the traj fixtures)."""
+    refimport.activate()
+    mpath = os.path.join(GOLD, "MANIFEST.json")
+    manifest = json.load(open(mpath))
+    manifest["decode"] = make_decode()
+    with open(mpath, "w") as f:
+        json.dump(manifest, f, indent=1, sort_keys=True)
+
+
 if __name__ == "__main__":
-    main()
+    only_decode() if sys.argv[1:] == ["decode"] else main()

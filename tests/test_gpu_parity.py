@@ -3,11 +3,14 @@ unmodified reference and against the CPU oracle on the same injected noise.
 
 Tolerances (fp32 path): per-evaluation raw scores and teacher-forced per-step state rel-L2 <= 1e-4
 (BASELINE.json north_star); thresholded final adjacency of the 1000-step runs bit-exact."""
+import os
+
 import numpy as np
 import pytest
 import torch
 
 from oracle import gdss_oracle as O
+from oracle.cases import GOLD
 from oracle.cases import CKPTS, SHORT_CASES, FULL_CASES, load_golden_ckpt, load_kat
 from tests.gpu_common import rel, injected_noise, case_setup, oracle_trace
 
@@ -234,3 +237,42 @@ def test_tensor_core_kernel_is_used_and_clean():
     assert int(meta[0]) == npix and int(meta[1]) == (npix + 127) // 128 and int(meta[16]) == 0
     sa_c = sa.cpu()
     assert float((sa_c - sa_c.transpose(-1, -2)).abs().max()) == 0.0
+
+
+def test_decode_mol_is_bit_exact():
+    """Post-sampling decode (sampler.py:131-138) on the device: golden fixture of the reference lines + random states
+    straddling every threshold, bit-exact against the oracle."""
+    from gdss_b200.graph_utils import decode_mol
+    z = np.load(os.path.join(GOLD, "traj_zinc_v2_rev_lang_full.npz"))
+    d = np.load(os.path.join(GOLD, "decode_zinc_v2.npz"))
+    xi, a = decode_mol(torch.from_numpy(z["x"]).cuda(), torch.from_numpy(z["adj"]).cuda())
+    assert np.array_equal(xi.cpu().numpy(), d["x"]) and np.array_equal(a.cpu().numpy(), d["adj"])
+    g = torch.Generator().manual_seed(5)
+    x = torch.rand(64, 38, 9, generator=g)
+    adj = torch.rand(64, 38, 38, generator=g) * 4 - 0.5
+    adj[0, 0, :8] = torch.tensor([0.5, 1.5, 2.5, 0.49999997, 1.4999999, 2.4999998, -3.0, 9.0])
+    x[0, 0, :3] = torch.tensor([0.5, 0.50000006, 0.49999997])
+    ox, oa = O.decode_mol(x, adj)
+    gx, ga = decode_mol(x.cuda(), adj.cuda())
+    assert torch.equal(gx.cpu(), ox) and torch.equal(ga.cpu(), oa)
+    atom, bond = decode_mol(x.cuda(), adj.cuda(), one_hot=False)
+    assert atom.dtype == torch.int8 and bond.dtype == torch.int8 and bond.shape == (64, 38, 38)
+
+
+def test_init_flags_device_follows_the_histogram():
+    """init_flags (graph_utils.py:66-74) on the device: prefix flags, node counts distributed as the training set's,
+    independent of sharding."""
+    from gdss_b200.graph_utils import init_flags_device
+    rs = np.random.RandomState(3)
+    counts = np.clip(np.round(rs.normal(23.2, 4.5, 5000)), 6, 38).astype(int)
+    B, N = 20000, 38
+    fl = init_flags_device(counts, N, B, seed=11)
+    n = fl.sum(1).long().cpu().numpy()
+    assert torch.equal(fl, (torch.arange(N, device="cuda")[None, :] < fl.sum(1, keepdim=True)).float())    # prefix flags
+    ref = np.bincount(counts, minlength=N + 1) / len(counts)
+    got = np.bincount(n, minlength=N + 1) / B
+    assert set(np.nonzero(got)[0]) <= set(np.nonzero(ref)[0])
+    assert np.abs(got - ref).max() < 4 * np.sqrt(0.25 / B) + 1e-3
+    lo = init_flags_device(counts, N, B // 2, seed=11)
+    hi = init_flags_device(counts, N, B // 2, seed=11, graph_offset=B // 2)
+    assert torch.equal(torch.cat([lo, hi]), fl)
