@@ -313,6 +313,9 @@ def main():
            "call": f"sampler(model_x, model_adj, host_flags) for {K} solver steps + D2H of (x, adj); bytes are per call / {K}"}
 
     if rank != 0:
+        shard.close()
+        if world > 1:
+            dist.destroy_process_group()
         return
     peaks, peak_src = measured_peaks()
     # ---- per-kernel timing of eager launches (1 GPU view) -> roofline of the dominant kernel
@@ -394,6 +397,8 @@ def main():
             "mean_nodes": float(np.mean(counts)), "finite": finite, "kernel_ms": kernel_ms}
     print(json.dumps(line), flush=True)
     shard.close()
+    if world > 1:
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":

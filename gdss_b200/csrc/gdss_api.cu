@@ -69,6 +69,13 @@ extern "C" gdss_ctx* gdss_ctx_create(int32_t N, int32_t F, const gdss_net_desc* 
     cudaDeviceGetAttribute(&c->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
     cudaDeviceGetAttribute(&c->num_sms, cudaDevAttrMultiProcessorCount, dev);
   }
+  if (c->num_sms > 0 && !(getenv("GDSS_NO_FORK") && getenv("GDSS_NO_FORK")[0] == '1')) {
+    bool ok = cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming) == cudaSuccess;
+    for (int k = 0; k < 2 && ok; ++k)
+      ok = cudaStreamCreateWithFlags(&c->side[k], cudaStreamNonBlocking) == cudaSuccess &&
+           cudaEventCreateWithFlags(&c->ev_join[k], cudaEventDisableTiming) == cudaSuccess;
+    if (!ok) c->side[0] = c->side[1] = nullptr;
+  }
   c->fused = false;
   const char* nf = getenv("GDSS_NO_FUSED");
   if (!(nf && nf[0] == '1')) c->fused = fused_supported(c);
@@ -79,7 +86,15 @@ extern "C" gdss_ctx* gdss_ctx_create(int32_t N, int32_t F, const gdss_net_desc* 
   return c;
 }
 
-extern "C" void gdss_ctx_destroy(gdss_ctx* ctx) { free(ctx); }
+extern "C" void gdss_ctx_destroy(gdss_ctx* ctx) {
+  if (!ctx) return;
+  for (int k = 0; k < 2; ++k) {
+    if (ctx->side[k]) cudaStreamDestroy(ctx->side[k]);
+    if (ctx->ev_join[k]) cudaEventDestroy(ctx->ev_join[k]);
+  }
+  if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+  free(ctx);
+}
 
 extern "C" int64_t gdss_workspace_bytes(const gdss_ctx* ctx, int32_t B) {
   if (!ctx || B <= 0) return GDSS_E_BADARG;

@@ -2071,7 +2071,18 @@ int launch_eval_fused(const gdss_ctx* ctx, const float* x, const float* adj, con
   fa.meta = reinterpret_cast<const int*>(ws + w.off[R_META]);
   int nb[3];
   const int nbk = size_buckets(N, nb);
-  for (int k = 0; k < nbk; ++k) {
+  // The size buckets are independent: they run as parallel branches (the largest graphs first, on the caller's stream,
+  // the others on the context's side streams; fork / join by events, also when the caller is capturing a CUDA graph), so
+  // a bucket that does not fill the GPU (few large graphs, small shards at 8 GPUs) overlaps with the others.
+  const bool fork = nbk > 1 && ctx->side[0] && ctx->side[1];
+  if (fork) {
+    cudaError_t fe = cudaEventRecord(ctx->ev_fork, st);
+    for (int k = 0; k < nbk - 1 && fe == cudaSuccess; ++k) fe = cudaStreamWaitEvent(ctx->side[k], ctx->ev_fork, 0);
+    if (fe != cudaSuccess) return (int)fe;
+  }
+  for (int kk = 0; kk < nbk; ++kk) {
+    const int k = nbk - 1 - kk;                         // largest bucket first
+    cudaStream_t ks = (fork && kk > 0) ? ctx->side[kk - 1] : st;
     // one launch per size bucket: B CTAs, those beyond the bucket's population exit at once (the counts live
     // on the device; no host synchronisation)
     fa.bucket = k;
@@ -2084,22 +2095,29 @@ int launch_eval_fused(const gdss_ctx* ctx, const float* x, const float* adj, con
     if (smem <= limit2) {
       e = cudaFuncSetAttribute(fused_layers_kernel<256, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e != cudaSuccess) return (int)e;
-      fused_layers_kernel<256, true, 2><<<B, nb[k] <= 12 ? 128 : 256, smem, st>>>(fa);
+      fused_layers_kernel<256, true, 2><<<B, nb[k] <= 12 ? 128 : 256, smem, ks>>>(fa);
     } else if (plan_smem(ctx, nb[k], &fa.sl, false) <= limit2) {   // (one CTA of 512 with staged weights measured 20 % slower here)
       smem = plan_smem(ctx, nb[k], &fa.sl, false);
       e = cudaFuncSetAttribute(fused_layers_kernel<256, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e != cudaSuccess) return (int)e;
-      fused_layers_kernel<256, false, 2><<<B, 256, smem, st>>>(fa);
+      fused_layers_kernel<256, false, 2><<<B, 256, smem, ks>>>(fa);
     } else {
       smem = plan_smem(ctx, nb[k], &fa.sl, true);
       if (smem <= 0 || smem > ctx->smem_optin) return GDSS_E_UNSUPPORTED;
       e = cudaFuncSetAttribute(fused_layers_kernel<512, true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e != cudaSuccess) return (int)e;
-      fused_layers_kernel<512, true, 1><<<B, 512, smem, st>>>(fa);
+      fused_layers_kernel<512, true, 1><<<B, 512, smem, ks>>>(fa);
     }
-    launched(K_FUSED, st);
+    count_launch();
+    if (!fork) prof_tick(K_FUSED, st);
     LAUNCH_CHECK();
+    if (fork && kk > 0) {
+      cudaError_t je = cudaEventRecord(ctx->ev_join[kk - 1], ks);
+      if (je == cudaSuccess) je = cudaStreamWaitEvent(st, ctx->ev_join[kk - 1], 0);
+      if (je != cudaSuccess) return (int)je;
+    }
   }
+  if (fork) prof_tick(K_FUSED, st);                     // one interval for the parallel branches (after the join)
   cudaError_t e;
   if (xfn) {
     const NetPlan& p = ctx->px;

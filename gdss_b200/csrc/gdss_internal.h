@@ -65,6 +65,10 @@ struct gdss_ctx {
   int smem_optin;               // max dynamic shared memory per block
   int num_sms;
   bool fused;                   // small-graph path: one CTA per graph (gdss_fused.cu)
+  // side streams / events of the size-bucket launches of the per-graph kernel (they run as parallel branches; one call per
+  // context in flight at a time)
+  cudaStream_t side[2];
+  cudaEvent_t ev_fork, ev_join[2];
   bool use_mma;                 // per-graph contractions on mma.sync (3xTF32); GDSS_NO_MMA=1 selects the FFMA variants
   bool use_tc;                  // final edge MLP on tcgen05 tensor cores (3xTF32); GDSS_NO_TC=1 selects the FFMA kernel
 };

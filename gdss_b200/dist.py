@@ -88,6 +88,9 @@ def init_from_env():
     if torch.cuda.is_available():
         torch.cuda.set_device(local)
     if world > 1 and not dist.is_initialized():
-        dist.init_process_group("nccl" if torch.cuda.is_available() else "gloo")
+        if torch.cuda.is_available():
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        else:
+            dist.init_process_group("gloo")
     dev = torch.device("cuda", local) if torch.cuda.is_available() else torch.device("cpu")
     return ShardInfo(world, rank, create_comm=torch.cuda.is_available(), device=dev), dev
