@@ -276,3 +276,46 @@ def test_init_flags_device_follows_the_histogram():
     lo = init_flags_device(counts, N, B // 2, seed=11)
     hi = init_flags_device(counts, N, B // 2, seed=11, graph_offset=B // 2)
     assert torch.equal(torch.cat([lo, hi]), fl)
+
+
+def test_full_size_batch_properties():
+    """BASELINE config C3 at its full size (B = 10 000, ragged ZINC-like node counts), where the oracle is too slow:
+    size-independent properties.  Raw scores of a graph do not depend on the batch it is evaluated in (bit-identical
+    to a 64-graph slice, and that slice is checked against the oracle); the score is symmetric with a zero diagonal
+    and zero on masked nodes; a few solver steps keep the state symmetric / masked / finite and are deterministic."""
+    from gdss_b200.engine import Engine, make_sampler_desc
+    from gdss_b200.schedule import build_table
+    from gdss_b200.sde import VPSDE, VESDE
+    ck = load_golden_ckpt("zinc250k_v2")
+    B, N, F = 10000, 38, 9
+    rs = np.random.RandomState(42)
+    counts = np.clip(np.round(rs.normal(23.2, 4.5, B)), 6, 38).astype(int)
+    flags = (torch.arange(N)[None, :] < torch.from_numpy(counts)[:, None]).float()
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(B, N, F, generator=g) * flags[:, :, None]
+    a = torch.randn(B, N, N, generator=g).triu(1)
+    adj = (a + a.transpose(-1, -2)) * flags[:, :, None] * flags[:, None, :]
+    eng = Engine(ck["x_state_dict"], ck["adj_state_dict"], N, "cuda")
+    xc, ac, fc = x.cuda(), adj.cuda(), flags.cuda()
+    sx, sa = eng.score(xc, ac, fc, inputs_masked=True)
+    sl = slice(4000, 4064)
+    sx64, sa64 = eng.score(xc[sl], ac[sl], fc[sl], inputs_masked=True)
+    assert torch.equal(sx[sl], sx64) and torch.equal(sa[sl], sa64)
+    with torch.no_grad():
+        ox = O.run_model(ck["x_state_dict"], ck["params_x"], x[sl], adj[sl], flags[sl])
+        oa = O.run_model(ck["adj_state_dict"], ck["params_adj"], x[sl], adj[sl], flags[sl])
+    assert rel(sx64, ox) <= TOL and rel(sa64, oa) <= TOL
+    pair = fc[:, :, None] * fc[:, None, :]
+    assert torch.equal(sa, sa.transpose(-1, -2)) and float(sa.diagonal(dim1=-2, dim2=-1).abs().max()) == 0
+    assert float((sa * (1 - pair)).abs().max()) == 0 and float((sx * (1 - fc[:, :, None])).abs().max()) == 0
+    assert torch.isfinite(sx).all() and torch.isfinite(sa).all()
+    sdx, sda = VPSDE(.1, 1., 1000), VESDE(.2, 1., 1000)
+    table = build_table(sdx, sda, "Reverse", "Langevin", .2, .8, 1e-4)
+    sdesc = make_sampler_desc(sdx, sda, "Reverse", "Langevin", .2, .8, 1e-4, 1, False, True)
+    r1 = eng.sample(sdesc, table, fc, n_iters=3, seed=9)
+    r2 = eng.sample(sdesc, table, fc, n_iters=3, seed=9)
+    for t1, t2 in zip(r1, r2):
+        assert torch.equal(t1, t2) and torch.isfinite(t1).all()
+    xs, as_, xm, am = r1
+    assert torch.equal(as_, as_.transpose(-1, -2)) and float((as_ * (1 - pair)).abs().max()) == 0
+    assert float(am.diagonal(dim1=-2, dim2=-1).abs().max()) == 0 and float((xm * (1 - fc[:, :, None])).abs().max()) == 0
