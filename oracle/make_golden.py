@@ -15,6 +15,8 @@ Produces
                                   CUDA path
   tests/golden/decode_zinc_v2.npz sampler.py:131-138 (quantize_mol, bond-class remap, one-hot, atom threshold + virtual
                                   atom) applied to the final state of the full ZINC250k v2 reference run
+  tests/golden/c1_community_reference.npz  BASELINE config C1 run with the reference on the CPU (flags, thresholded
+                                  samples, training graphs) for the statistical parity test
   tests/golden/MANIFEST.json      what was generated, from which torch version
 
 The reference code is imported and called, never copied.
@@ -172,19 +174,59 @@ def main():
     manifest["kat"] = make_kat()
     manifest["traj"] = make_traj()
     manifest["decode"] = make_decode()
+    manifest["c1"] = make_c1_stats()
     with open(os.path.join(GOLD, "MANIFEST.json"), "w") as f:
         json.dump(manifest, f, indent=1, sort_keys=True)
 
 
-def only_decode():
-    """python oracle/make_golden.py decode : just the post-sampling decode fixture (needs the traj fixtures)."""
+def make_c1_stats():
+    """BASELINE config C1 exactly as SURVEY 8d specifies it, run with the UNMODIFIED reference on the CPU: community_small,
+    B = 100, Euler + Langevin (snr .05, scale_eps .7), 1000 steps, flags = node counts of training graphs
+    data/community_small.pkl[20:] drawn with RandomState(11).randint, torch.manual_seed(11).  Stored: the flags, the
+    thresholded adjacency of the samples and of the training graphs (for degree / edge statistics in the GPU tests)."""
+    import pickle
+    import sde as RSDE
+    import solver as RS
+    with open(os.path.join(refimport.REF, "data", "community_small.pkl"), "rb") as f:
+        graphs = pickle.load(f)
+    train = graphs[int(0.2 * len(graphs)):]
+    N, F, B = 20, 10, 100
+    idx = np.random.RandomState(11).randint(0, len(train), B)
+    counts = np.array([train[i].number_of_nodes() for i in idx])
+    flags = (torch.arange(N)[None, :] < torch.from_numpy(counts)[:, None]).float()
+    import networkx as nx
+    train_adj = np.zeros((len(train), N, N), dtype=np.int8)
+    for k, gph in enumerate(train):
+        a = nx.to_numpy_array(gph)
+        train_adj[k, :a.shape[0], :a.shape[1]] = a > 0
+    mx, ma, px, pa = ref_models("community_small")
+    sx, sa = RSDE.VPSDE(.1, 1., 1000), RSDE.VPSDE(.1, 1., 1000)
+    fn = RS.get_pc_sampler(sx, sa, (B, N, F), (B, N, N), predictor="Euler", corrector="Langevin", snr=.05, scale_eps=.7,
+                           n_steps=1, probability_flow=False, continuous=True, denoise=True, eps=1e-4, device="cpu")
+    torch.manual_seed(11)
+    with contextlib.redirect_stdout(io.StringIO()), contextlib.redirect_stderr(io.StringIO()):
+        x, adj, _ = fn(mx, ma, flags)
+    q = (adj >= 0.5).numpy().astype(np.int8)
+    np.savez_compressed(os.path.join(GOLD, "c1_community_reference.npz"), counts=counts.astype(np.int16), samples=q,
+                        train=train_adj, train_counts=np.array([g.number_of_nodes() for g in train], dtype=np.int16))
+    e = q.sum(axis=(1, 2)) / 2
+    return {"mean_nodes": float(counts.mean()), "edges_mean": float(e.mean()), "edges_std": float(e.std())}
+
+
+def only(which):
+    """python oracle/make_golden.py decode | c1 : just one of the small fixtures."""
     refimport.activate()
+    torch.set_num_threads(os.cpu_count())
     mpath = os.path.join(GOLD, "MANIFEST.json")
     manifest = json.load(open(mpath))
-    manifest["decode"] = make_decode()
+    if which == "decode":
+        manifest["decode"] = make_decode()
+    else:
+        manifest["c1"] = make_c1_stats()
+        print(manifest["c1"])
     with open(mpath, "w") as f:
         json.dump(manifest, f, indent=1, sort_keys=True)
 
 
 if __name__ == "__main__":
-    only_decode() if sys.argv[1:] == ["decode"] else main()
+    only(sys.argv[1]) if sys.argv[1:] in (["decode"], ["c1"]) else main()

@@ -319,3 +319,41 @@ def test_full_size_batch_properties():
     xs, as_, xm, am = r1
     assert torch.equal(as_, as_.transpose(-1, -2)) and float((as_ * (1 - pair)).abs().max()) == 0
     assert float(am.diagonal(dim1=-2, dim2=-1).abs().max()) == 0 and float((xm * (1 - fc[:, :, None])).abs().max()) == 0
+
+
+def test_c1_sample_statistics_match_the_reference_run():
+    """SURVEY 8c protocol (iv), BASELINE config C1: community_small, Euler + Langevin, 1000 steps, the reference run's own
+    flags.  The CUDA sampler draws its noise from Philox (not torch's generator), so the samples differ; their statistics
+    must agree with the reference run's within sampling error: edges per graph, density among valid pairs, degree MMD
+    (evaluation/stats.py:28 restated in oracle/stats.py) against the training graphs."""
+    from oracle import stats as S
+    from gdss_b200.solver import get_pc_sampler
+    from gdss_b200.sde import VPSDE
+    from gdss_b200.graph_utils import quantize
+    z = np.load(os.path.join(GOLD, "c1_community_reference.npz"))
+    counts, ref, train, tc = z["counts"].astype(int), z["samples"], z["train"], z["train_counts"].astype(int)
+    ck = load_golden_ckpt("community_small")
+    rep = 10                                                   # 10 x the reference's batch for a tighter estimate
+    cnt = np.tile(counts, rep)
+    B, N, F = len(cnt), 20, 10
+    flags = (torch.arange(N)[None, :] < torch.from_numpy(cnt)[:, None]).float()
+    fn = get_pc_sampler(VPSDE(.1, 1., 1000), VPSDE(.1, 1., 1000), (B, N, F), (B, N, N), predictor="Euler", corrector="Langevin",
+                        snr=.05, scale_eps=.7, n_steps=1, probability_flow=False, continuous=True, denoise=True, eps=1e-4,
+                        device="cuda")
+    torch.manual_seed(11)
+    x, adj, n_evals = fn(ck["x_state_dict"], ck["adj_state_dict"], flags)
+    assert n_evals == 2000 and torch.isfinite(adj).all()
+    q = quantize(adj).cpu().numpy().astype(np.int8)
+    assert np.array_equal(q, q.transpose(0, 2, 1)) and q.diagonal(axis1=1, axis2=2).sum() == 0
+    pair = (flags[:, :, None] * flags[:, None, :]).numpy()
+    assert (q * (1 - pair)).sum() == 0
+    e_ref, e = S.edge_counts(ref), S.edge_counts(q)
+    se = np.sqrt(e_ref.var() / len(e_ref) + e.var() / len(e))
+    assert abs(e.mean() - e_ref.mean()) < 4 * se, (e.mean(), e_ref.mean(), se)
+    valid = lambda c: (c * (c - 1) / 2).sum()
+    d_ref, d = e_ref.sum() / valid(counts), e.sum() / valid(cnt)
+    assert abs(d - d_ref) < 0.03, (d, d_ref)
+    ht = S.degree_histograms(train, tc)
+    mmd_ref = S.degree_mmd(ht, S.degree_histograms(ref, counts))
+    mmd = S.degree_mmd(ht, S.degree_histograms(q[:300], cnt[:300]))
+    assert mmd < mmd_ref + 0.03, (mmd, mmd_ref)
