@@ -78,8 +78,10 @@ namespace gdss {
 void layout_workspace(const gdss_ctx* ctx, int B, Workspace* w);
 
 // Enqueue one joint evaluation of the bound networks (raw outputs).  neff = device int[B].
+// zero_fill: clear the outputs first (entries of padded nodes are never written).  The fused path writes valid entries
+// only, so a sampler clears its score buffers once and passes false for every step.
 int launch_eval(const gdss_ctx* ctx, const float* x, const float* adj, const float* flags, const int* neff,
-                float* score_x, float* score_adj, int B, char* ws, const Workspace& w, cudaStream_t st);
+                float* score_x, float* score_adj, int B, char* ws, const Workspace& w, cudaStream_t st, bool zero_fill = true);
 int launch_neff(const float* flags, int* neff, int B, int N, int inputs_masked, cudaStream_t st);
 
 void count_launch(int n = 1);

@@ -993,10 +993,11 @@ int launch_setup(const gdss_ctx* ctx, const float* flags, int B, int inputs_mask
 }
 
 int launch_eval(const gdss_ctx* ctx, const float* x, const float* adj, const float* flags, const int* neff,
-                float* score_x, float* score_adj, int B, char* ws, const Workspace& w, cudaStream_t st) {
+                float* score_x, float* score_adj, int B, char* ws, const Workspace& w, cudaStream_t st, bool zero_fill) {
   const int N = ctx->N, F = ctx->F;
   cudaError_t e;
   if (ctx->fused) {
+    if (!zero_fill) return launch_eval_fused(ctx, x, adj, flags, neff, score_x, score_adj, B, ws, w, st);
     if (score_adj && ctx->has_a) {
       e = cudaMemsetAsync(score_adj, 0, sizeof(float) * (size_t)B * N * N, st);
       if (e != cudaSuccess) return (int)e;

@@ -338,7 +338,7 @@ static int enqueue_step(const StepPlan& p, cudaStream_t st) {
   int chunks = (work + 255) / 256;
   if (chunks > 64) chunks = 64;
   dim3 ugrid(chunks, B);
-  int rc = launch_eval(p.ctx, u.x, u.adj, u.flags, u.neff, raw_x, raw_a, B, p.ws, p.w, st);
+  int rc = launch_eval(p.ctx, u.x, u.adj, u.flags, u.neff, raw_x, raw_a, B, p.ws, p.w, st, !p.ctx->fused);
   if (rc) return rc;
   if (p.s4 || p.langevin) {
     norms_kernel<<<B, 256, 0, st>>>(u.ns, raw_x, raw_a, u.flags, u.neff, u.table, u.step_ptr, p.norms);
@@ -361,7 +361,7 @@ static int enqueue_step(const StepPlan& p, cudaStream_t st) {
       update_kernel<MODE_CORR><<<ugrid, 256, 0, st>>>(u);
       launched(K_UPDATE, st);
       LAUNCH_CHECK();
-      rc = launch_eval(p.ctx, u.x, u.adj, u.flags, u.neff, raw_x, raw_a, B, p.ws, p.w, st);
+      rc = launch_eval(p.ctx, u.x, u.adj, u.flags, u.neff, raw_x, raw_a, B, p.ws, p.w, st, !p.ctx->fused);
       if (rc) return rc;
     }
     update_kernel<MODE_PRED><<<ugrid, 256, 0, st>>>(u);
@@ -456,6 +456,12 @@ extern "C" int gdss_sample(gdss_ctx* ctx, const gdss_sampler_desc* s, const gdss
     if (e != cudaSuccess) return (int)e;
   }
   if (n_iters == 0) return GDSS_OK;
+  if (ctx->fused) {
+    // the fused evaluation writes the valid entries only: the score buffers are cleared once per call, not per step
+    e = cudaMemsetAsync(const_cast<float*>(u.raw_x), 0, sizeof(float) * (size_t)B * N * F, st);
+    if (e == cudaSuccess) e = cudaMemsetAsync(const_cast<float*>(u.raw_adj), 0, sizeof(float) * (size_t)B * N * N, st);
+    if (e != cudaSuccess) return (int)e;
+  }
 
   // step 0 runs eagerly (sets kernel attributes, surfaces launch errors); the remaining steps replay
   // one captured graph -- the step index is read from device memory, so every replay is identical.
