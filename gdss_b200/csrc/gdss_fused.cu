@@ -138,6 +138,7 @@ struct FusedArgs {
   const int* order;        // graph ids sorted by size bucket
   const int* meta;
   int bucket;
+  int mb1;                  // every graph of the launch has at most 16 nodes (one mma row tile)
   int use_mma;              // warp-level tensor-core (mma.sync 3xTF32) variants of the per-graph contractions
   unsigned long long* prof;   // optional [16] per-phase clock cycles (thread 0 of every CTA, summed), else null
   int64_t pstride;
@@ -885,7 +886,7 @@ DEVINL void channel_pipeline(int lane, const float* pl, float* dv, const float* 
 //   degrees -> C1 = A~ (d . x) -> [scale rows by d: A^ x, kept in registers as the next A operand] -> Q|K|V = (A^ x) W + b -> map
 // A~ is gathered from the strict-upper-triangle plane through the index table tab[i][j] (diagonal -> the 1.0 slot,
 // padding -> the 0.0 slot), so the planes keep the layout the per-edge MLP reads and writes.  f <= 32.
-template <bool WS, int HD, int NF>       // NF: compile-time bound of the feature tiles (f <= 8 NF)
+template <bool WS, int HD, int NF, int MB>       // NF: compile-time bound of the feature tiles (f <= 8 NF); MB: row tiles per pass
 __device__ __noinline__ void channel_chain_mma(int lane, const float* pl, const unsigned short* tab, int TC, float* dv, const float* x, int ldx, int n,
                               int f, int f_in_p, const float* Wc, int qkvw, const float* bc, float* qkc, int QKS, float* vcol, int ldv,
                               bool need_edge, bool need_node, const unsigned* pix, int P, float scale, float* Mc, int part, int nparts,
@@ -908,7 +909,6 @@ __device__ __noinline__ void channel_chain_mma(int lane, const float* pl, const 
   }
   __syncwarp();
   const int o_lo = need_edge ? 0 : 2 * AT, o_hi = need_node ? qkvw : 2 * AT;
-  constexpr int MB = NF <= 2 ? 2 : 1;                   // row tiles per pass (they share every B fragment)
   for (int m0 = part * MB; m0 < mt; m0 += MB * nparts) {
     float c1[MB][NF][4];
 #pragma unroll
@@ -1276,11 +1276,14 @@ __global__ void __launch_bounds__(NT, OCC) fused_layers_kernel(const __grid_cons
           const int c = nparts > 1 ? u % C : u, part = nparts > 1 ? u / C : 0;
           const float* Wc = wqp + c * L.f_in_p * L.qkvw;
           const float* bc = wqp + L.bq_o + c * L.qkvw;
-          if (A.use_mma && f <= 16 && attn == 16) {
-            channel_chain_mma<WSM, 4, 2>(lane, pin + c * PM, tab, S.TC, dinv + c * NBP, xin, XS, n, f, L.f_in_p, Wc, L.qkvw, bc,
-                                         QK + c * n * QKS, QKS, R2 + c * h, LDV, L.need_edge, L.need_node, pix, P, scale, R1 + c * RS, part, nparts, 2 + c);
+          if (A.use_mma && f <= 16 && attn == 16 && A.mb1) {         // graphs of at most 16 nodes: one row tile
+            channel_chain_mma<WSM, 4, 2, 1>(lane, pin + c * PM, tab, S.TC, dinv + c * NBP, xin, XS, n, f, L.f_in_p, Wc, L.qkvw, bc,
+                                            QK + c * n * QKS, QKS, R2 + c * h, LDV, L.need_edge, L.need_node, pix, P, scale, R1 + c * RS, part, nparts, 2 + c);
+          } else if (A.use_mma && f <= 16 && attn == 16) {
+            channel_chain_mma<WSM, 4, 2, 2>(lane, pin + c * PM, tab, S.TC, dinv + c * NBP, xin, XS, n, f, L.f_in_p, Wc, L.qkvw, bc,
+                                            QK + c * n * QKS, QKS, R2 + c * h, LDV, L.need_edge, L.need_node, pix, P, scale, R1 + c * RS, part, nparts, 2 + c);
           } else if (A.use_mma && f <= 32 && attn == 32) {
-            channel_chain_mma<WSM, 8, 4>(lane, pin + c * PM, tab, S.TC, dinv + c * NBP, xin, XS, n, f, L.f_in_p, Wc, L.qkvw, bc,
+            channel_chain_mma<WSM, 8, 4, 1>(lane, pin + c * PM, tab, S.TC, dinv + c * NBP, xin, XS, n, f, L.f_in_p, Wc, L.qkvw, bc,
                                          QK + c * n * QKS, QKS, R2 + c * h, LDV, L.need_edge, L.need_node, pix, P, scale, R1 + c * RS, part, nparts, 2 + c);
           } else if (part > 0) {
             // (the FFMA chain runs one warp per channel)
@@ -2086,6 +2089,7 @@ int launch_eval_fused(const gdss_ctx* ctx, const float* x, const float* adj, con
     // one launch per size bucket: B CTAs, those beyond the bucket's population exit at once (the counts live
     // on the device; no host synchronisation)
     fa.bucket = k;
+    fa.mb1 = nb[k] <= 16 ? 1 : 0;
     // Preferred: layer weights staged in shared memory by TMA with two CTAs of 256 threads per SM; if only the
     // weight-less plan fits twice, read the weights through L2 instead; the largest graphs run one CTA of 512.
     // (three CTAs of 85 registers per SM with the weights read through L2 measured 5 % slower than two with staged weights)
