@@ -68,6 +68,8 @@ def lib():
         "gdss_score_forward": (C.c_int, [vp, fp, fp, fp, fp, fp, i32, i32, vp, i64, vp]),
         "gdss_sample": (C.c_int, [vp, C.POINTER(SamplerDesc), fp, i32, i32, fp, fp, fp, fp, fp, i32, i32, u64, i64, i64,
                                    fp, fp, fp, vp, i32, vp, i64, vp]),
+        "gdss_dsm_scratch_floats": (i64, [vp, i32]),
+        "gdss_dsm_loss": (C.c_int, [vp, fp, fp, fp, fp, fp, i32, i32, fp, i64, fp, vp, i64, vp]),
         "gdss_nccl_unique_id": (C.c_int, [vp]),
         "gdss_nccl_comm_create": (C.c_int, [vp, i32, i32, C.POINTER(vp)]),
         "gdss_nccl_comm_destroy": (C.c_int, [vp]),

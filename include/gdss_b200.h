@@ -159,6 +159,19 @@ int gdss_sample(gdss_ctx* ctx, const gdss_sampler_desc* s, const gdss_step_coef*
                 const float* inj_x, const float* inj_adj, float* trace, void* nccl_comm, int32_t use_graph,
                 void* workspace, int64_t workspace_bytes, void* stream);
 
+/* ---- denoising-score-matching loss, forward only -----------------------------------------------
+ * Replaces loss_fn of losses.py:37-81 (likelihood_weighting = False) as the trainer's evaluation loop calls it under
+ * torch.no_grad() (trainer.py:84-99): flags = node_flags(adj), z = gen_noise from the supplied raw N(0,1) draws
+ * (raw_x [B,N,F], raw_adj [B,N,N]), perturbed = mask(mean * y + std * z), both score networks, per-graph
+ * reduce_op(square(score * std + z)), batch mean -> loss_out[0] (x), loss_out[1] (adj) on the device.
+ * coef = float[B][6]: mean_x, std_x, div_x, mean_adj, std_adj, div_adj from sde.marginal_prob(., t_b); div = std for
+ * VP / subVP (score = -net / std), 0 for VE (score = net).  scratch >= gdss_dsm_scratch_floats floats.
+ * The backward pass / optimizer step of trainer.py:57-79 is not part of this library yet. */
+int64_t gdss_dsm_scratch_floats(const gdss_ctx* ctx, int32_t B);
+int gdss_dsm_loss(gdss_ctx* ctx, const float* x, const float* adj, const float* coef, const float* raw_x,
+                  const float* raw_adj, int32_t B, int32_t reduce_mean, float* scratch, int64_t scratch_floats,
+                  float* loss_out, void* workspace, int64_t workspace_bytes, void* stream);
+
 /* ---- NCCL plumbing (dlopen'ed; the library loads without NCCL) ------------------------- */
 int gdss_nccl_unique_id(void* id128);                         /* rank 0: 128-byte id       */
 int gdss_nccl_comm_create(const void* id128, int32_t world, int32_t rank, void** comm_out);

@@ -370,6 +370,41 @@ def make_score_fn(sde: SDESpec, sd: StateDict, params: dict):
 # --------------------------------------------------------------------------
 # solver  (solver.py)
 # --------------------------------------------------------------------------
+def dsm_loss(sde_x: "SDESpec", sde_adj: "SDESpec", sd_x: StateDict, p_x: dict, sd_a: StateDict, p_a: dict, x: Tensor,
+             adj: Tensor, t: Tensor, raw_x: Tensor, raw_adj: Tensor, reduce_mean: bool = False) -> Tuple[Tensor, Tensor]:
+    """losses.py:37-81 (likelihood_weighting = False) with the three random draws supplied: t [B] (losses.py:47),
+    raw_x / raw_adj = the randn_like draws inside gen_noise (losses.py:50, :55)."""
+    def marginal(sde, y, tt):                       # sde.py:134-138 / :196-199 / :259-263 with a [B] time vector
+        if sde.kind == "VE":
+            return y, sde.lo * (sde.hi / sde.lo) ** tt
+        lmc = -0.25 * tt ** 2 * (sde.hi - sde.lo) - 0.5 * tt * sde.lo
+        mean = torch.exp(lmc).view((-1,) + (1,) * (y.dim() - 1)) * y
+        return mean, (torch.sqrt(1. - torch.exp(2. * lmc)) if sde.kind == "VP" else 1 - torch.exp(2. * lmc))
+
+    def score(sde, sd, p, px, pa, fl):              # losses.py:6-34
+        net = run_model(sd, p, px, pa, fl)
+        if sde.kind == "VE":
+            return net
+        std = marginal(sde, torch.zeros_like(pa), t)[1]
+        return -net / std.view((-1,) + (1,) * (net.dim() - 1))
+
+    reduce_op = torch.mean if reduce_mean else (lambda v, dim: 0.5 * torch.sum(v, dim=dim))
+    flags = node_flags(adj)
+    z_x = mask_x(raw_x, flags)
+    mean_x, std_x = marginal(sde_x, x, t)
+    pert_x = mask_x(mean_x + std_x[:, None, None] * z_x, flags)
+    z_adj = sym_noise_from_raw(raw_adj, flags)
+    mean_a, std_a = marginal(sde_adj, adj, t)
+    pert_a = mask_adjs(mean_a + std_a[:, None, None] * z_adj, flags)
+    s_x = score(sde_x, sd_x, p_x, pert_x, pert_a, flags)
+    s_a = score(sde_adj, sd_a, p_a, pert_x, pert_a, flags)
+    l_x = torch.square(s_x * std_x[:, None, None] + z_x)
+    l_x = reduce_op(l_x.reshape(l_x.shape[0], -1), dim=-1)
+    l_a = torch.square(s_a * std_a[:, None, None] + z_adj)
+    l_a = reduce_op(l_a.reshape(l_a.shape[0], -1), dim=-1)
+    return torch.mean(l_x), torch.mean(l_a)
+
+
 def _batch_mean_norm(v: Tensor) -> Tensor:
     """solver.py:130-131 -- per-graph Frobenius norm, then the mean over the batch."""
     return torch.norm(v.reshape(v.shape[0], -1), dim=-1).mean()

@@ -17,6 +17,7 @@ Produces
                                   atom) applied to the final state of the full ZINC250k v2 reference run
   tests/golden/c1_community_reference.npz  BASELINE config C1 run with the reference on the CPU (flags, thresholded
                                   samples, training graphs) for the statistical parity test
+  tests/golden/dsm_<ckpt>_<sum|mean>.npz  loss_fn of losses.py:37-81 on a synthetic batch with recorded t / noise draws
   tests/golden/MANIFEST.json      what was generated, from which torch version
 
 The reference code is imported and called, never copied.
@@ -175,6 +176,7 @@ def main():
     manifest["traj"] = make_traj()
     manifest["decode"] = make_decode()
     manifest["c1"] = make_c1_stats()
+    manifest["dsm"] = make_dsm()
     with open(os.path.join(GOLD, "MANIFEST.json"), "w") as f:
         json.dump(manifest, f, indent=1, sort_keys=True)
 
@@ -213,6 +215,68 @@ def make_c1_stats():
     return {"mean_nodes": float(counts.mean()), "edges_mean": float(e.mean()), "edges_std": float(e.std())}
 
 
+DSM_CASES = [("qm9", ("VE", .1, 1.), ("VE", .1, 1.)), ("zinc250k_v2", ("VP", .1, 1.), ("VE", .2, 1.)),
+             ("community_small", ("VP", .1, 1.), ("VP", .1, 1.)), ("ego_small", ("subVP", .1, 1.), ("VE", .1, 1.))]
+
+
+def dsm_inputs(N, F, B, seed):
+    """Synthetic training batch of the reference's shape: one-hot node features, symmetric integer bond orders, ragged
+    node counts (real data is not shipped)."""
+    rs = np.random.RandomState(seed)
+    x = np.zeros((B, N, F), dtype=np.float32)
+    adj = np.zeros((B, N, N), dtype=np.float32)
+    for b in range(B):
+        n = rs.randint(max(3, N // 2), N + 1)
+        x[b, np.arange(n), rs.randint(0, F, n)] = 1
+        a = np.triu((rs.rand(n, n) < 0.3) * rs.randint(1, 4, (n, n)), 1).astype(np.float32)
+        adj[b, :n, :n] = a + a.T
+        for i in range(n):                               # every node keeps at least one bond (node_flags sees it)
+            if adj[b, i, :n].sum() == 0:
+                j = (i + 1) % n
+                adj[b, i, j] = adj[b, j, i] = 1
+    return torch.from_numpy(x), torch.from_numpy(adj)
+
+
+def make_dsm():
+    """loss_fn of the UNMODIFIED reference (losses.py:37-81) with torch.rand / torch.randn_like served from a recorded
+    numpy stream; stores the inputs, the three draws and the two loss values."""
+    import losses as RL
+    import sde as RSDE
+    out = {}
+    cls = {"VP": RSDE.VPSDE, "VE": RSDE.VESDE, "subVP": RSDE.subVPSDE}
+    for k, (name, sx_, sa_) in enumerate(DSM_CASES):
+        mx, ma, px, pa = ref_models(name)
+        N, F, B = pa["max_node_num"], pa["max_feat_num"], 6
+        x, adj = dsm_inputs(N, F, B, 300 + k)
+        sx, sa = cls[sx_[0]](sx_[1], sx_[2], 1000), cls[sa_[0]](sa_[1], sa_[2], 1000)
+        for rm in (False, True):
+            fn = RL.get_sde_loss_fn(sx, sa, train=False, reduce_mean=rm, continuous=True, likelihood_weighting=False, eps=1e-5)
+            rs = np.random.RandomState(400 + k)
+            tape = []
+            orig_rand, orig_like = torch.rand, torch.randn_like
+
+            def rand(*shape, **kw):
+                v = torch.from_numpy(rs.rand(*shape).astype(np.float32)); tape.append(v); return v
+
+            def randn_like(tt, **kw):
+                v = torch.from_numpy(rs.randn(*tt.shape).astype(np.float32)); tape.append(v); return v
+
+            torch.rand, torch.randn_like = rand, randn_like
+            try:
+                with torch.no_grad():
+                    lx, la = fn(mx, ma, x, adj)
+            finally:
+                torch.rand, torch.randn_like = orig_rand, orig_like
+            assert len(tape) == 3
+            key = f"{name}_{'mean' if rm else 'sum'}"
+            np.savez_compressed(os.path.join(GOLD, f"dsm_{key}.npz"), x=x.numpy(), adj=adj.numpy(), t=tape[0].numpy(),
+                                raw_x=tape[1].numpy(), raw_adj=tape[2].numpy(), loss_x=float(lx), loss_adj=float(la),
+                                sde=json.dumps([sx_, sa_]), reduce_mean=rm)
+            out[key] = [float(lx), float(la)]
+            print("dsm", key, out[key], flush=True)
+    return out
+
+
 def only(which):
     """python oracle/make_golden.py decode | c1 : just one of the small fixtures."""
     refimport.activate()
@@ -221,6 +285,8 @@ def only(which):
     manifest = json.load(open(mpath))
     if which == "decode":
         manifest["decode"] = make_decode()
+    elif which == "dsm":
+        manifest["dsm"] = make_dsm()
     else:
         manifest["c1"] = make_c1_stats()
         print(manifest["c1"])
@@ -229,4 +295,4 @@ def only(which):
 
 
 if __name__ == "__main__":
-    only(sys.argv[1]) if sys.argv[1:] in (["decode"], ["c1"]) else main()
+    only(sys.argv[1]) if sys.argv[1:] in (["decode"], ["c1"], ["dsm"]) else main()
