@@ -563,24 +563,22 @@ DEVINL void mma_tf32(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
-// One output tile accumulated as three independent chains (main term, two correction terms): a dependent mma.sync
-// issues only every ~20 cycles, so every k-step puts three independent instructions in flight instead of three chained ones.
-struct Acc { float m[4], s0[4], s1[4]; };
+// One output tile: c += A B with both operands split, smallest terms first.  (Three independent accumulator chains per
+// tile were measured 1 % slower than this dependent chain: the kernel is bound by issue slots, not by mma latency.)
+struct Acc { float m[4]; };
 
 DEVINL void acc_init(Acc& a, float b0, float b1) {
   a.m[0] = a.m[2] = b0;
   a.m[1] = a.m[3] = b1;
-#pragma unroll
-  for (int q = 0; q < 4; ++q) a.s0[q] = a.s1[q] = 0.f;
 }
 
 DEVINL void mma3(Acc& c, const uint32_t (&ah)[4], const uint32_t (&al)[4], const Split& b0, const Split& b1) {
-  mma_tf32(c.s0, al, b0.hi, b1.hi);
-  mma_tf32(c.s1, ah, b0.lo, b1.lo);
+  mma_tf32(c.m, al, b0.hi, b1.hi);
+  mma_tf32(c.m, ah, b0.lo, b1.lo);
   mma_tf32(c.m, ah, b0.hi, b1.hi);
 }
 
-DEVINL float acc_get(const Acc& c, int q) { return c.m[q] + (c.s0[q] + c.s1[q]); }
+DEVINL float acc_get(const Acc& c, int q) { return c.m[q]; }
 
 // per-pixel MLP of one AttentionLayer (attention.py:109-114) on the tensor cores: one warp = 16 pixels per tile, the
 // three layers chained in registers (C fragment -> next A fragment), weights held as split B fragments.
