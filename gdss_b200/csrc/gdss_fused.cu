@@ -1328,7 +1328,8 @@ __global__ void __launch_bounds__(NT, OCC) fused_layers_kernel(const __grid_cons
         ph_m ^= 1;
       }
       const float* wmp = WSM ? wm : L.blk_m;
-      const int node_warps = (L.need_node && L.need_edge && nwarps >= 4) ? 2 : 0;     // split only when both exist
+      // split only when both exist; one node warp per 16-row tile (the mma node MLP works on whole tiles)
+      const int node_warps = (L.need_node && L.need_edge && nwarps >= 4) ? ((A.use_mma && (nwarps < 8 || n <= 16)) ? 1 : 2) : 0;
       const int nt_edge = nt - 32 * node_warps;
       if (L.need_node && (node_warps == 0 || tid >= nt_edge)) {
         const int ltid = node_warps ? tid - nt_edge : tid, lnt = node_warps ? 32 * node_warps : nt;
