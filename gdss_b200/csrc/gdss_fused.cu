@@ -1601,11 +1601,15 @@ DEVINL void tc_sync_before_mma() {         // tcgen05.st / ld of every thread or
   asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
 }
 
-template <int NP, int K1P, int FOP, bool NODE>      // NODE: final MLP of an X network (FOP = padded output width), rows = nodes
-__global__ void __launch_bounds__(256, 1) final_edge_tc_kernel(FinalTriArgs a, int* __restrict__ err) {
+// NODE: final MLP of an X network (FOP = padded output width), rows = nodes.  NS: column splits = warps per TMEM lane
+// quarter (128 NS threads).  NS = 4 did not help (the tile time is the serial sum of the MMAs and the epilogues' ALU work,
+// not latency): every instance uses NS = 2.
+template <int NP, int K1P, int FOP, bool NODE, int NS>
+__global__ void __launch_bounds__(128 * NS, 1) final_edge_tc_kernel(FinalTriArgs a, int* __restrict__ err) {
   extern __shared__ __align__(128) float sm[];
-  constexpr int KH = K1P / 2;             // layer-1 operand columns per column half
-  constexpr int CH = NP / 2;              // hidden columns per column half
+  constexpr int NT = 128 * NS;
+  constexpr int KH = K1P / NS;            // layer-1 operand columns per column split
+  constexpr int CH = NP / NS;             // hidden columns per column split
   static_assert(NP % 16 == 0 && K1P % 8 == 0 && K1P <= NP && 3 * NP <= 512 && CH % 8 == 0 && KH % 4 == 0, "shape");
   float* W1hi = sm;                       // [K1P/4][NP][4]
   float* W1lo = W1hi + K1P * NP;
@@ -1614,15 +1618,15 @@ __global__ void __launch_bounds__(256, 1) final_edge_tc_kernel(FinalTriArgs a, i
   float* b1s = W2lo + NP * NP;            // [NP]
   float* b2s = b1s + NP;
   float* w3s = b2s + NP;                  // [NP] (edge) / [NP][FOP] (node)
-  float* part = w3s + NP * (NODE ? FOP : 1);   // [128] ([128][FOP]) partial dot products of column half 1
+  float* part = w3s + NP * (NODE ? FOP : 1);   // [NS-1][128] ([NS-1][FOP][128]) partial dot products of column splits 1..
   __shared__ uint32_t tmem_base_s;
   __shared__ __align__(8) uint64_t mbar;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int half = warp >> 2;
+  const int half = warp >> 2;             // column split of this warp (0 .. NS-1)
   const int row = 32 * (warp & 3) + lane;
   const int K1 = a.fdim, H = a.H, N = a.N;
   // ---- one-time set-up: B operands (hi / lo), biases, tensor memory, mbarrier
-  for (int idx = tid; idx < K1P * NP; idx += 256) {
+  for (int idx = tid; idx < K1P * NP; idx += NT) {
     const int k = idx / NP, n = idx - k * NP;
     const float w = (k < K1 && n < H) ? a.w1[k * a.Hs + n] : 0.f;
     const float hi = tf32_rna(w);
@@ -1630,7 +1634,7 @@ __global__ void __launch_bounds__(256, 1) final_edge_tc_kernel(FinalTriArgs a, i
     W1hi[o] = hi;
     W1lo[o] = tf32_rna(w - hi);
   }
-  for (int idx = tid; idx < NP * NP; idx += 256) {
+  for (int idx = tid; idx < NP * NP; idx += NT) {
     const int k = idx / NP, n = idx - k * NP;
     const float w = (k < H && n < H) ? a.w2[k * a.Hs + n] : 0.f;
     const float hi = tf32_rna(w);
@@ -1638,13 +1642,13 @@ __global__ void __launch_bounds__(256, 1) final_edge_tc_kernel(FinalTriArgs a, i
     W2hi[o] = hi;
     W2lo[o] = tf32_rna(w - hi);
   }
-  for (int idx = tid; idx < NP; idx += 256) {
+  for (int idx = tid; idx < NP; idx += NT) {
     b1s[idx] = idx < H ? a.b1[idx] : 0.f;
     b2s[idx] = idx < H ? a.b2[idx] : 0.f;
     if (!NODE) w3s[idx] = idx < H ? a.w3[idx * 4] : 0.f;
   }
   if (NODE)
-    for (int idx = tid; idx < NP * FOP; idx += 256) {
+    for (int idx = tid; idx < NP * FOP; idx += NT) {
       const int k = idx / FOP, o = idx - k * FOP;
       w3s[idx] = (k < H && o < a.foutp) ? a.w3[k * a.foutp + o] : 0.f;
     }
@@ -1786,9 +1790,9 @@ __global__ void __launch_bounds__(256, 1) final_edge_tc_kernel(FinalTriArgs a, i
           }
         }
       }
-      if (half == 1) {
+      if (half > 0) {
 #pragma unroll
-        for (int o = 0; o < FOP; ++o) part[o * 128 + row] = dv[o];
+        for (int o = 0; o < FOP; ++o) part[((half - 1) * FOP + o) * 128 + row] = dv[o];
       }
       asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
       __syncthreads();
@@ -1798,8 +1802,12 @@ __global__ void __launch_bounds__(256, 1) final_edge_tc_kernel(FinalTriArgs a, i
           const float f = a.flags[(int64_t)b * N + i];
           float* O = a.out + gp * a.F;
 #pragma unroll
-          for (int o = 0; o < FOP; ++o)
-            if (o < a.F) O[o] = (dv[o] + part[o * 128 + row] + a.b3[o]) * f;
+          for (int o = 0; o < FOP; ++o) {
+            float acc = dv[o];
+#pragma unroll
+            for (int q = 0; q < NS - 1; ++q) acc += part[(q * FOP + o) * 128 + row];
+            if (o < a.F) O[o] = (acc + a.b3[o]) * f;
+          }
         }
       }
       ok = __syncthreads_and(ok);
@@ -1829,7 +1837,7 @@ __global__ void __launch_bounds__(256, 1) final_edge_tc_kernel(FinalTriArgs a, i
       }
       dot += dot2;
     }
-    if (half == 1) part[row] = dot;
+    if (half > 0) part[(half - 1) * 128 + row] = dot;
     asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
     __syncthreads();                        // also: every thread is done reading D before the next tile's MMA
     if (half == 0) {
@@ -1837,7 +1845,10 @@ __global__ void __launch_bounds__(256, 1) final_edge_tc_kernel(FinalTriArgs a, i
       if (v >= 0) {
         const int b = v >> 12, i = (v >> 6) & 63, j = v & 63;
         const float* fl = a.flags + (int64_t)b * N;
-        const float s = (dot + part[row] + b3) * (fl[i] * fl[j]);
+        float acc = dot;
+#pragma unroll
+        for (int q = 0; q < NS - 1; ++q) acc += part[q * 128 + row];
+        const float s = (acc + b3) * (fl[i] * fl[j]);
         float* O = a.out + (int64_t)b * N * N;
         O[i * N + j] = s;
         O[j * N + i] = s;
@@ -1852,25 +1863,27 @@ __global__ void __launch_bounds__(256, 1) final_edge_tc_kernel(FinalTriArgs a, i
 }
 
 typedef void (*final_tc_fn)(FinalTriArgs, int*);
-static final_tc_fn pick_final_tc(int fdim, int* np, int* k1p) {
+static final_tc_fn pick_final_tc(int fdim, int* np, int* k1p, int* ns) {
   const int H = 2 * fdim, NP = (H + 15) & ~15, K1P = (fdim + 7) & ~7;
   *np = NP;
   *k1p = K1P;
-  if (NP == 96 && K1P == 48) return final_edge_tc_kernel<96, 48, 4, false>;     // fdim 46 (ZINC250k: 2 + 8*5 + 4)
-  if (NP == 80 && K1P == 40) return final_edge_tc_kernel<80, 40, 4, false>;     // fdim 38 (community_small, ego_small)
-  if (NP == 48 && K1P == 24) return final_edge_tc_kernel<48, 24, 4, false>;     // fdim 22 (QM9)
-  if (NP == 112 && K1P == 56) return final_edge_tc_kernel<112, 56, 4, false>;   // fdim 54 (ENZYMES, grid)
+  *ns = 2;
+  if (NP == 96 && K1P == 48) return final_edge_tc_kernel<96, 48, 4, false, 2>;  // fdim 46 (ZINC250k: 2 + 8*5 + 4); NS = 4 measured 3 % slower
+  if (NP == 80 && K1P == 40) return final_edge_tc_kernel<80, 40, 4, false, 2>;     // fdim 38 (community_small, ego_small)
+  if (NP == 48 && K1P == 24) return final_edge_tc_kernel<48, 24, 4, false, 2>;     // fdim 22 (QM9)
+  if (NP == 112 && K1P == 56) return final_edge_tc_kernel<112, 56, 4, false, 2>;   // fdim 54 (ENZYMES, grid)
   return nullptr;
 }
 
 // node mode: the X networks whose hidden width fits tensor memory (3 NP <= 512 columns)
-static final_tc_fn pick_final_tc_node(int fdim, int foutp, int* np, int* k1p, int* fop) {
+static final_tc_fn pick_final_tc_node(int fdim, int foutp, int* np, int* k1p, int* fop, int* ns) {
   const int H = 2 * fdim, NP = (H + 15) & ~15, K1P = (fdim + 7) & ~7;
   *np = NP;
   *k1p = K1P;
   *fop = foutp;
-  if (NP == 96 && K1P == 48 && foutp == 12) return final_edge_tc_kernel<96, 48, 12, true>;   // ZINC250k: fdim 9 + 2*16, F = 9
-  if (NP == 80 && K1P == 40 && foutp == 4) return final_edge_tc_kernel<80, 40, 4, true>;     // QM9: fdim 4 + 2*16, F = 4
+  *ns = 2;
+  if (NP == 96 && K1P == 48 && foutp == 12) return final_edge_tc_kernel<96, 48, 12, true, 2>;   // ZINC250k: fdim 9 + 2*16, F = 9
+  if (NP == 80 && K1P == 40 && foutp == 4) return final_edge_tc_kernel<80, 40, 4, true, 2>;     // QM9: fdim 4 + 2*16, F = 4
   return nullptr;
 }
 
@@ -2059,9 +2072,9 @@ int launch_eval_fused(const gdss_ctx* ctx, const float* x, const float* adj, con
   fa.pstride = w.pstride;
   fa.N = N; fa.F = ctx->F;
   // X network's final MLP: batched tensor-core kernel when its shape has an instance, else inside the per-graph kernel
-  int xnp = 0, xk1p = 0, xfop = 0;
-  final_tc_fn xfn = (want_x && ctx->use_tc && w.nstride > 0) ? pick_final_tc_node(ctx->px.fdim, ctx->px.foutp, &xnp, &xk1p, &xfop) : nullptr;
-  const size_t xsm = sizeof(float) * (2 * (size_t)(xk1p * xnp + xnp * xnp) + 2 * xnp + (size_t)xnp * xfop + 128 * (size_t)xfop) + 256;
+  int xnp = 0, xk1p = 0, xfop = 0, xns = 2;
+  final_tc_fn xfn = (want_x && ctx->use_tc && w.nstride > 0) ? pick_final_tc_node(ctx->px.fdim, ctx->px.foutp, &xnp, &xk1p, &xfop, &xns) : nullptr;
+  const size_t xsm = sizeof(float) * (2 * (size_t)(xk1p * xnp + xnp * xnp) + 2 * xnp + (size_t)xnp * xfop + 128 * (size_t)xfop * (xns - 1)) + 256;
   if (xfn && (int)xsm > ctx->smem_optin) xfn = nullptr;
   if (xfn) {
     fa.xst = reinterpret_cast<float*>(ws + w.off[R_XS]);
@@ -2145,7 +2158,7 @@ int launch_eval_fused(const gdss_ctx* ctx, const float* x, const float* adj, con
     int grid = ctx->num_sms > 0 ? ctx->num_sms : 148;
     if ((int64_t)grid > tiles) grid = (int)tiles;
     int* errflag = reinterpret_cast<int*>(ws + w.off[R_META]) + 16;
-    xfn<<<grid, 256, xsm, st>>>(ta, errflag);
+    xfn<<<grid, 128 * xns, xsm, st>>>(ta, errflag);
     launched(K_FINAL_NODE, st);
     LAUNCH_CHECK();
   }
@@ -2160,17 +2173,17 @@ int launch_eval_fused(const gdss_ctx* ctx, const float* x, const float* adj, con
     ta.w3 = ctx->blob_a + p.fw[2]; ta.b3 = ctx->blob_a + p.fb[2];
     ta.out = score_adj; ta.flags = flags; ta.N = N; ta.fdim = p.fdim; ta.H = 2 * p.fdim; ta.Hs = p.Hp;
     const int64_t max_tiles = ((int64_t)B * (N * (N - 1) / 2) + 127) / 128;
-    int np = 0, k1p = 0;
-    final_tc_fn tfn = ctx->use_tc ? pick_final_tc(p.fdim, &np, &k1p) : nullptr;
+    int np = 0, k1p = 0, tns = 2;
+    final_tc_fn tfn = ctx->use_tc ? pick_final_tc(p.fdim, &np, &k1p, &tns) : nullptr;
     if (tfn && max_tiles > 0) {
-      const size_t tsm = sizeof(float) * (2 * (size_t)(k1p * np + np * np) + 3 * np + 128) + 256;
+      const size_t tsm = sizeof(float) * (2 * (size_t)(k1p * np + np * np) + 3 * np + 128 * (size_t)(tns - 1)) + 256;
       if ((int)tsm <= ctx->smem_optin) {
         e = cudaFuncSetAttribute(tfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsm);
         if (e != cudaSuccess) return (int)e;
         int grid = ctx->num_sms > 0 ? ctx->num_sms : 148;
         if ((int64_t)grid > max_tiles) grid = (int)max_tiles;
         int* errflag = reinterpret_cast<int*>(ws + w.off[R_META]) + 16;
-        tfn<<<grid, 256, tsm, st>>>(ta, errflag);
+        tfn<<<grid, 128 * tns, tsm, st>>>(ta, errflag);
         launched(K_FINAL_EDGE, st);
         LAUNCH_CHECK();
         return 0;
