@@ -1620,7 +1620,7 @@ __global__ void __launch_bounds__(128 * NS, 1) final_edge_tc_kernel(FinalTriArgs
   float* w3s = b2s + NP;                  // [NP] (edge) / [NP][FOP] (node)
   float* part = w3s + NP * (NODE ? FOP : 1);   // [NS-1][128] ([NS-1][FOP][128]) partial dot products of column splits 1..
   __shared__ uint32_t tmem_base_s;
-  __shared__ __align__(8) uint64_t mbar;
+  __shared__ __align__(8) uint64_t mbar, mbar2;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int half = warp >> 2;             // column split of this warp (0 .. NS-1)
   const int row = 32 * (warp & 3) + lane;
@@ -1658,6 +1658,7 @@ __global__ void __launch_bounds__(128 * NS, 1) final_edge_tc_kernel(FinalTriArgs
   }
   if (tid == 0) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(smem_u32(&mbar)) : "memory");
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(smem_u32(&mbar2)) : "memory");
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
   asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");     // generic-proxy writes of W -> async proxy (UMMA)
@@ -1666,12 +1667,19 @@ __global__ void __launch_bounds__(128 * NS, 1) final_edge_tc_kernel(FinalTriArgs
   asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
   const uint32_t tb = tmem_base_s;
   const uint32_t tlane = tb + ((uint32_t)(32 * (warp & 3)) << 16);
-  constexpr uint32_t colAhi = 0, colAlo = NP, colD = 2 * NP;
+  // Tensor-memory columns.  When they fit (2 K1P + 4 NP <= 512) the layer-1 operand, the layer-2 operand and the two
+  // accumulators have their own columns, and the first contraction of the NEXT tile is issued together with the second
+  // contraction of the current one: it runs on the tensor pipe while the threads are busy with the second epilogue.
+  constexpr bool PIPE = 2 * K1P + 4 * NP <= 512;
+  constexpr uint32_t colA1 = 0;                                   // layer-1 operand: hi [0, K1P), lo [K1P, 2 K1P)
+  constexpr uint32_t colAhi = PIPE ? 2 * K1P : 0, colAlo = colAhi + NP;     // layer-2 operand hi / lo
+  constexpr uint32_t colD = colAlo + NP;                          // accumulator of the first contraction
+  constexpr uint32_t colD2 = PIPE ? colD + NP : colD;             // accumulator of the second contraction
   constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NP >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
   constexpr uint32_t LBO = NP * 16, SBO = 128;
-  const uint32_t mb = smem_u32(&mbar);
+  const uint32_t mb = smem_u32(&mbar), mb2 = smem_u32(&mbar2);
   const float b3 = a.b3[0];
-  uint32_t phase = 0;
+  uint32_t phase = 0, phase2 = 0;
   bool ok = true;
   const int ntiles = NODE ? (a.B * N + 127) / 128 : a.meta[1];
   // channel values of this thread's pixel for the first tile; every later tile is fetched one tile ahead (the loads
@@ -1685,9 +1693,8 @@ __global__ void __launch_bounds__(128 * NS, 1) final_edge_tc_kernel(FinalTriArgs
       v[kk] = (c < K1 && (int)blockIdx.x < ntiles) ? __ldg(a.stackT + (int64_t)c * a.pstride + gp0) : 0.f;
     }
   }
-  for (int tile = blockIdx.x; tile < ntiles && ok; tile += gridDim.x) {
-    const int64_t gp = (int64_t)tile * 128 + row;
-    // ---- layer-1 operand: channel values of this pixel -> hi / lo -> tensor memory
+  // layer-1 operand of the tile held in v[] -> hi / lo -> tensor memory; then v[] <- the tile `pre` (if any)
+  auto stage_a1 = [&](int pre) {
 #pragma unroll
     for (int kk = 0; kk < KH; kk += 4) {
       float h[4], l[4];
@@ -1697,31 +1704,45 @@ __global__ void __launch_bounds__(128 * NS, 1) final_edge_tc_kernel(FinalTriArgs
         h[q] = __uint_as_float(sp.hi);
         l[q] = __uint_as_float(sp.lo);
       }
-      tmem_st4(tlane + colAhi + half * KH + kk, h[0], h[1], h[2], h[3]);
-      tmem_st4(tlane + colAhi + K1P + half * KH + kk, l[0], l[1], l[2], l[3]);
+      tmem_st4(tlane + colA1 + half * KH + kk, h[0], h[1], h[2], h[3]);
+      tmem_st4(tlane + colA1 + K1P + half * KH + kk, l[0], l[1], l[2], l[3]);
     }
-    if (tile + (int)gridDim.x < ntiles) {
-      const int64_t gpn = gp + (int64_t)gridDim.x * 128;
+    if (pre < ntiles) {
+      const int64_t gpn = (int64_t)pre * 128 + row;
 #pragma unroll
       for (int kk = 0; kk < KH; ++kk) {
         const int c = half * KH + kk;
         v[kk] = c < K1 ? __ldg(a.stackT + (int64_t)c * a.pstride + gpn) : 0.f;
       }
     }
-    tc_sync_before_mma();
-    if (tid == 0) {
-      uint32_t acc = 0;
+  };
+  // first contraction (3xTF32: hi.hi + lo.hi + hi.lo) of the staged layer-1 operand -> colD, completion on `mb`
+  auto issue_mma1 = [&]() {
+    uint32_t acc = 0;
 #pragma unroll
-      for (int ps = 0; ps < 3; ++ps) {
-        const uint32_t acol = tb + colAhi + (ps == 1 ? K1P : 0);
-        const uint32_t bbase = smem_u32(ps == 2 ? W1lo : W1hi);
+    for (int ps = 0; ps < 3; ++ps) {
+      const uint32_t acol = tb + colA1 + (ps == 1 ? K1P : 0);
+      const uint32_t bbase = smem_u32(ps == 2 ? W1lo : W1hi);
 #pragma unroll
-        for (int s = 0; s < K1P / 8; ++s) {
-          umma_tf32_ts(tb + colD, acol + s * 8, umma_bdesc(bbase + s * 2 * LBO, LBO, SBO), idesc, acc);
-          acc = 1;
-        }
+      for (int s = 0; s < K1P / 8; ++s) {
+        umma_tf32_ts(tb + colD, acol + s * 8, umma_bdesc(bbase + s * 2 * LBO, LBO, SBO), idesc, acc);
+        acc = 1;
       }
-      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(mb) : "memory");
+    }
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(mb) : "memory");
+  };
+  if (PIPE && (int)blockIdx.x < ntiles) {                    // prologue: the first tile's first contraction
+    stage_a1(blockIdx.x + gridDim.x);
+    tc_sync_before_mma();
+    if (tid == 0) issue_mma1();
+  }
+  for (int tile = blockIdx.x; tile < ntiles && ok; tile += gridDim.x) {
+    const int64_t gp = (int64_t)tile * 128 + row;
+    const int next = tile + (int)gridDim.x;
+    if (!PIPE) {
+      stage_a1(next);
+      tc_sync_before_mma();
+      if (tid == 0) issue_mma1();
     }
     ok = mbar_wait(mb, phase);
     phase ^= 1;
@@ -1751,6 +1772,7 @@ __global__ void __launch_bounds__(128 * NS, 1) final_edge_tc_kernel(FinalTriArgs
         }
       }
     }
+    if (PIPE && next < ntiles) stage_a1(next + (int)gridDim.x);     // the layer-1 columns are free: its contraction is complete
     tc_sync_before_mma();
     if (tid == 0) {
       uint32_t acc = 0;
@@ -1760,14 +1782,20 @@ __global__ void __launch_bounds__(128 * NS, 1) final_edge_tc_kernel(FinalTriArgs
         const uint32_t bbase = smem_u32(ps == 2 ? W2lo : W2hi);
 #pragma unroll
         for (int s = 0; s < NP / 8; ++s) {
-          umma_tf32_ts(tb + colD, acol + s * 8, umma_bdesc(bbase + s * 2 * LBO, LBO, SBO), idesc, acc);
+          umma_tf32_ts(tb + colD2, acol + s * 8, umma_bdesc(bbase + s * 2 * LBO, LBO, SBO), idesc, acc);
           acc = 1;
         }
       }
-      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(mb) : "memory");
+      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(PIPE ? mb2 : mb) : "memory");
+      if (PIPE && next < ntiles) issue_mma1();          // next tile's first contraction: overlaps the epilogue below
     }
-    ok = ok && mbar_wait(mb, phase);
-    phase ^= 1;
+    if (PIPE) {
+      ok = ok && mbar_wait(mb2, phase2);
+      phase2 ^= 1;
+    } else {
+      ok = ok && mbar_wait(mb, phase);
+      phase ^= 1;
+    }
     asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
     if (NODE) {
       // ---- epilogue 2 (X networks, ScoreNetwork_X.py:43-46, :86-89): ELU(D + b2) W3 + b3, mask_x
@@ -1778,7 +1806,7 @@ __global__ void __launch_bounds__(128 * NS, 1) final_edge_tc_kernel(FinalTriArgs
       for (int c0 = 0; c0 < CH; c0 += 8) {
         const int col = half * CH + c0;
         float d[8];
-        tmem_ld8(tlane + colD + col, d);
+        tmem_ld8(tlane + colD2 + col, d);
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
           const float e = elu_f(d[q] + b2s[col + q]);
@@ -1823,7 +1851,7 @@ __global__ void __launch_bounds__(128 * NS, 1) final_edge_tc_kernel(FinalTriArgs
       for (int b0 = 0; b0 < NB8; b0 += GB) {
         uint32_t dr[GB][8];
 #pragma unroll
-        for (int u = 0; u < GB; ++u) tmem_ld8_nowait(tlane + colD + half * CH + 8 * (b0 + u), dr[u]);
+        for (int u = 0; u < GB; ++u) tmem_ld8_nowait(tlane + colD2 + half * CH + 8 * (b0 + u), dr[u]);
         tmem_ld_wait();
 #pragma unroll
         for (int u = 0; u < GB; ++u) {
