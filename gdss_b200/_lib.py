@@ -65,6 +65,7 @@ def lib():
         "gdss_ctx_destroy": (None, [vp]),
         "gdss_workspace_bytes": (i64, [vp, i32]),
         "gdss_workspace_offset": (i64, [vp, i32, C.c_char_p]),
+        "gdss_ctx_query": (i64, [vp, C.c_char_p]),
         "gdss_score_forward": (C.c_int, [vp, fp, fp, fp, fp, fp, i32, i32, vp, i64, vp]),
         "gdss_sample": (C.c_int, [vp, C.POINTER(SamplerDesc), fp, i32, i32, fp, fp, fp, fp, fp, i32, i32, u64, i64, i64,
                                    fp, fp, fp, vp, i32, vp, i64, vp]),

@@ -114,6 +114,17 @@ extern "C" int64_t gdss_workspace_offset(const gdss_ctx* ctx, int32_t B, const c
   return GDSS_E_BADARG;
 }
 
+extern "C" int64_t gdss_ctx_query(const gdss_ctx* ctx, const char* key) {
+  if (!ctx || !key) return GDSS_E_BADARG;
+  if (!strcmp(key, "fused")) return ctx->fused ? 1 : 0;
+  if (!strcmp(key, "fused_fusable")) return fused_query(ctx, 0);
+  if (!strcmp(key, "fused_smem_bytes")) return fused_query(ctx, 1);
+  if (!strcmp(key, "smem_optin")) return ctx->smem_optin;
+  if (!strcmp(key, "use_tc")) return ctx->use_tc ? 1 : 0;
+  if (!strcmp(key, "use_mma")) return ctx->use_mma ? 1 : 0;
+  return GDSS_E_BADARG;
+}
+
 extern "C" int gdss_score_forward(gdss_ctx* ctx, const float* x, const float* adj, const float* flags, float* score_x,
                                   float* score_adj, int32_t B, int32_t inputs_masked, void* workspace,
                                   int64_t workspace_bytes, void* stream) {

@@ -34,64 +34,79 @@ DEVINL float sig2(float a) { return rcp_ftz(ex2_ftz(a) + 1.f); }
 // pixel bookkeeping (depends on the flags only: once per sampler call)
 // ---------------------------------------------------------------------------------------
 // meta: [0] total pixels, [1] 128-pixel tiles, [2..4] graphs per size bucket, [5..7] first slot of each bucket in order[]
+// order[]: graph ids grouped by size bucket and, inside a bucket, sorted by node count in DESCENDING order (counting sort;
+// the longest CTAs of a launch start first, so the last wave of a launch is made of its shortest graphs).  The position
+// of a graph among those of equal size is arbitrary; results do not depend on it.  wide: gmap fields of 9 bits (general
+// path, N <= 511) instead of 6.
+#define TRI_BINS 66
 __global__ void __launch_bounds__(1024) tri_scan_kernel(const int* __restrict__ neff, int B, int nb0, int nb1,
                                                         int* __restrict__ poff, int* __restrict__ meta,
                                                         int* __restrict__ gmap, int* __restrict__ order) {
   __shared__ int part[1024];
-  __shared__ int tot_s[4];
+  __shared__ int hist[TRI_BINS], cursor[TRI_BINS];
+  __shared__ int bstart[3], bcount[3];
   const int t = threadIdx.x;
   const int chunk = (B + 1023) / 1024;
   const int lo = min(B, t * chunk), hi = min(B, lo + chunk);
-  int s = 0, cnt[3] = {0, 0, 0};
+  if (t < TRI_BINS) hist[t] = 0;
+  __syncthreads();
+  int s = 0;
   for (int b = lo; b < hi; ++b) {
     const int n = neff[b];
     s += n * (n - 1) / 2;
-    cnt[n <= nb0 ? 0 : (n <= nb1 ? 1 : 2)]++;
+    atomicAdd(&hist[min(max(n, 0), TRI_BINS - 1)], 1);
   }
-  int excl[4];
-  for (int q = 0; q < 4; ++q) {
-    const int v0 = q == 0 ? s : cnt[q - 1];
-    part[t] = v0;
+  // exclusive prefix of the pixel counts over the threads' chunks
+  part[t] = s;
+  __syncthreads();
+  for (int off = 1; off < 1024; off <<= 1) {
+    int v = t >= off ? part[t - off] : 0;
     __syncthreads();
-    for (int off = 1; off < 1024; off <<= 1) {
-      int v = t >= off ? part[t - off] : 0;
-      __syncthreads();
-      part[t] += v;
-      __syncthreads();
+    part[t] += v;
+    __syncthreads();
+  }
+  int base = part[t] - s;
+  const int tot = part[1023];
+  if (t == 0) {
+    int cur = 0;
+    for (int k = 0; k < 3; ++k) {
+      const int blo = k == 0 ? 0 : (k == 1 ? nb0 + 1 : nb1 + 1);
+      const int bhi = min(TRI_BINS - 1, k == 0 ? nb0 : (k == 1 ? nb1 : TRI_BINS - 1));
+      bstart[k] = cur;
+      for (int n = bhi; n >= blo; --n) {
+        cursor[n] = cur;
+        cur += hist[n];
+      }
+      bcount[k] = cur - bstart[k];
     }
-    excl[q] = part[t] - v0;
-    if (t == 1023) tot_s[q] = part[1023];
-    __syncthreads();
   }
-  const int start[3] = {0, tot_s[1], tot_s[1] + tot_s[2]};
-  int base = excl[0];
-  int pos[3] = {start[0] + excl[1], start[1] + excl[2], start[2] + excl[3]};
+  __syncthreads();
   for (int b = lo; b < hi; ++b) {
     poff[b] = base;
     const int n = neff[b];
     base += n * (n - 1) / 2;
-    order[pos[n <= nb0 ? 0 : (n <= nb1 ? 1 : 2)]++] = b;
+    order[atomicAdd(&cursor[min(max(n, 0), TRI_BINS - 1)], 1)] = b;
   }
   if (t == 1023) {
-    const int tot = tot_s[0];
     poff[B] = tot;
     meta[0] = tot;
     meta[1] = (tot + 127) / 128;
     meta[16] = 0;                          // error flag of the tensor-core kernel (lost mbarrier arrival)
     for (int q = 0; q < 3; ++q) {
-      meta[2 + q] = tot_s[1 + q];
-      meta[5 + q] = start[q];
+      meta[2 + q] = bcount[q];
+      meta[5 + q] = bstart[q];
     }
     for (int k = tot; k < ((tot + 127) / 128) * 128; ++k) gmap[k] = -1;
   }
 }
 
+// gmap[gp] = b << 2 fb | i << fb | j  (fb = 6 bits for the per-graph path, 9 for the general path)
 __global__ void __launch_bounds__(64) tri_map_kernel(const int* __restrict__ neff, const int* __restrict__ poff,
-                                                     int* __restrict__ gmap) {
+                                                     int* __restrict__ gmap, int fb) {
   const int b = blockIdx.x, n = neff[b], base = poff[b];
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
     const int rs = i * (2 * n - i - 1) / 2;
-    for (int j = i + 1; j < n; ++j) gmap[base + rs + j - i - 1] = (b << 12) | (i << 6) | j;
+    for (int j = i + 1; j < n; ++j) gmap[base + rs + j - i - 1] = (b << (2 * fb)) | (i << fb) | j;
   }
 }
 
@@ -1396,6 +1411,8 @@ struct FinalTriArgs {
   float* out; const float* flags;
   int N, fdim, H, Hs;
   const int* neff; int B, F, foutp;      // node mode (X networks): rows = b * N + i, F outputs per row, w3 [Hs][foutp]
+  int fb;                                // bits per index field of gmap (6: per-graph path, 9: general path)
+  int64_t dense_bs;                      // != 0 (general path): stackT is the dense channel stack [b][c][N][N] with this batch stride
 };
 
 template <int OPT>
@@ -1685,14 +1702,27 @@ __global__ void __launch_bounds__(128 * NS, 1) final_edge_tc_kernel(FinalTriArgs
   // channel values of this thread's pixel for the first tile; every later tile is fetched one tile ahead (the loads
   // are in flight during the two contractions and epilogues of the current tile)
   float v[KH];
-  {
-    const int64_t gp0 = (int64_t)blockIdx.x * 128 + row;
+  // channel values of this thread's pixel of tile `tile`: channel-major planes over the batch's pixels (per-graph path) or,
+  // on the general path, the dense channel stack [b][c][N][N] addressed through gmap
+  auto fetch = [&](int tile) {
+    const int64_t gpn = (int64_t)tile * 128 + row;
+    bool valid = tile < ntiles;
+    const float* src = a.stackT + gpn;
+    int64_t cs = a.pstride;
+    if (!NODE && a.dense_bs) {
+      const int g = valid ? __ldg(a.gmap + gpn) : -1;
+      valid = g >= 0;
+      const int b = g >> (2 * a.fb), i = (g >> a.fb) & ((1 << a.fb) - 1), j = g & ((1 << a.fb) - 1);
+      src = a.stackT + (valid ? (int64_t)b * a.dense_bs + (int64_t)i * N + j : 0);
+      cs = (int64_t)N * N;
+    }
 #pragma unroll
     for (int kk = 0; kk < KH; ++kk) {
       const int c = half * KH + kk;
-      v[kk] = (c < K1 && (int)blockIdx.x < ntiles) ? __ldg(a.stackT + (int64_t)c * a.pstride + gp0) : 0.f;
+      v[kk] = (c < K1 && valid) ? __ldg(src + (int64_t)c * cs) : 0.f;
     }
-  }
+  };
+  fetch(blockIdx.x);
   // layer-1 operand of the tile held in v[] -> hi / lo -> tensor memory; then v[] <- the tile `pre` (if any)
   auto stage_a1 = [&](int pre) {
 #pragma unroll
@@ -1707,14 +1737,7 @@ __global__ void __launch_bounds__(128 * NS, 1) final_edge_tc_kernel(FinalTriArgs
       tmem_st4(tlane + colA1 + half * KH + kk, h[0], h[1], h[2], h[3]);
       tmem_st4(tlane + colA1 + K1P + half * KH + kk, l[0], l[1], l[2], l[3]);
     }
-    if (pre < ntiles) {
-      const int64_t gpn = (int64_t)pre * 128 + row;
-#pragma unroll
-      for (int kk = 0; kk < KH; ++kk) {
-        const int c = half * KH + kk;
-        v[kk] = c < K1 ? __ldg(a.stackT + (int64_t)c * a.pstride + gpn) : 0.f;
-      }
-    }
+    if (pre < ntiles) fetch(pre);
   };
   // first contraction (3xTF32: hi.hi + lo.hi + hi.lo) of the staged layer-1 operand -> colD, completion on `mb`
   auto issue_mma1 = [&]() {
@@ -1871,15 +1894,15 @@ __global__ void __launch_bounds__(128 * NS, 1) final_edge_tc_kernel(FinalTriArgs
     if (half == 0) {
       const int v = a.gmap[gp];
       if (v >= 0) {
-        const int b = v >> 12, i = (v >> 6) & 63, j = v & 63;
+        const int b = v >> (2 * a.fb), i = (v >> a.fb) & ((1 << a.fb) - 1), j = v & ((1 << a.fb) - 1);
         const float* fl = a.flags + (int64_t)b * N;
         float acc = dot;
 #pragma unroll
         for (int q = 0; q < NS - 1; ++q) acc += part[q * 128 + row];
         const float s = (acc + b3) * (fl[i] * fl[j]);
         float* O = a.out + (int64_t)b * N * N;
-        O[i * N + j] = s;
-        O[j * N + i] = s;
+        O[(int64_t)i * N + j] = s;
+        O[(int64_t)j * N + i] = s;
       }
     }
     ok = __syncthreads_and(ok);             // part[] is reused by the next tile; uniform loop exit
@@ -2061,7 +2084,17 @@ bool fused_supported(const gdss_ctx* ctx) {
   if (ctx->has_x && !net_fusable(ctx->px)) return false;
   FSmem s;
   const int64_t bytes = plan_smem(ctx, ctx->N, &s);
-  return bytes > 0 && bytes <= ctx->smem_optin;
+  if (bytes > 0 && bytes <= ctx->smem_optin) return true;
+  const int64_t bytes_l2 = plan_smem(ctx, ctx->N, &s, false);       // layer weights read through L2 instead of staged
+  return bytes_l2 > 0 && bytes_l2 <= ctx->smem_optin;
+}
+
+int64_t fused_query(const gdss_ctx* ctx, int what) {
+  const bool ok = ctx->N <= 64 && ctx->N >= 2 && (!ctx->has_a || net_fusable(ctx->pa)) && (!ctx->has_x || net_fusable(ctx->px));
+  if (what == 0) return ok ? 1 : 0;
+  if (!ok) return -1;
+  FSmem s;
+  return plan_smem(ctx, ctx->N, &s);
 }
 
 int launch_tri_setup(const gdss_ctx* ctx, const int* neff, int B, char* ws, const Workspace& w, cudaStream_t st) {
@@ -2076,7 +2109,7 @@ int launch_tri_setup(const gdss_ctx* ctx, const int* neff, int B, char* ws, cons
   tri_scan_kernel<<<1, 1024, 0, st>>>(neff, B, b0, b1, poff, meta, gmap, order);
   launched(K_MISC, st);
   LAUNCH_CHECK();
-  tri_map_kernel<<<B, 64, 0, st>>>(neff, poff, gmap);
+  tri_map_kernel<<<B, 64, 0, st>>>(neff, poff, gmap, ctx->fused ? 6 : 9);
   launched(K_MISC, st);
   LAUNCH_CHECK();
   return 0;
@@ -2152,12 +2185,19 @@ int launch_eval_fused(const gdss_ctx* ctx, const float* x, const float* adj, con
       e = cudaFuncSetAttribute(fused_layers_kernel<256, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e != cudaSuccess) return (int)e;
       fused_layers_kernel<256, false, 2><<<B, 256, smem, ks>>>(fa);
-    } else {
+    } else if (smem > 0 && smem <= ctx->smem_optin) {
       smem = plan_smem(ctx, nb[k], &fa.sl, true);
-      if (smem <= 0 || smem > ctx->smem_optin) return GDSS_E_UNSUPPORTED;
       e = cudaFuncSetAttribute(fused_layers_kernel<512, true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e != cudaSuccess) return (int)e;
       fused_layers_kernel<512, true, 1><<<B, 512, smem, ks>>>(fa);
+    } else {
+      // wide layers (nhid = adim = 32, 8 channels: community_small's 96 KB of Q|K|V weights per layer): the staged plan
+      // does not fit an SM at all; one CTA of 256 per SM with the weights read through L1 / L2
+      smem = plan_smem(ctx, nb[k], &fa.sl, false);
+      if (smem <= 0 || smem > ctx->smem_optin) return GDSS_E_UNSUPPORTED;
+      e = cudaFuncSetAttribute(fused_layers_kernel<256, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return (int)e;
+      fused_layers_kernel<256, false, 2><<<B, 256, smem, ks>>>(fa);
     }
     count_launch();
     if (!fork) prof_tick(K_FUSED, st);
@@ -2200,6 +2240,7 @@ int launch_eval_fused(const gdss_ctx* ctx, const float* x, const float* adj, con
     ta.w1 = ctx->blob_a + p.fw[0]; ta.b1 = ctx->blob_a + p.fb[0]; ta.w2 = ctx->blob_a + p.fw[1]; ta.b2 = ctx->blob_a + p.fb[1];
     ta.w3 = ctx->blob_a + p.fw[2]; ta.b3 = ctx->blob_a + p.fb[2];
     ta.out = score_adj; ta.flags = flags; ta.N = N; ta.fdim = p.fdim; ta.H = 2 * p.fdim; ta.Hs = p.Hp;
+    ta.fb = 6;
     const int64_t max_tiles = ((int64_t)B * (N * (N - 1) / 2) + 127) / 128;
     int np = 0, k1p = 0, tns = 2;
     final_tc_fn tfn = ctx->use_tc ? pick_final_tc(p.fdim, &np, &k1p, &tns) : nullptr;
@@ -2234,6 +2275,48 @@ int launch_eval_fused(const gdss_ctx* ctx, const float* x, const float* adj, con
       LAUNCH_CHECK();
     }
   }
+  return 0;
+}
+
+// ---- general path (N > 64): ScoreNetworkA.final on the tensor-core kernel, reading the dense channel stack
+static size_t final_tc_smem(int np, int k1p, int ns) {
+  return sizeof(float) * (2 * (size_t)(k1p * np + np * np) + 3 * np + 128 * (size_t)(ns - 1)) + 256;
+}
+
+bool final_tc_dense_ok(const gdss_ctx* ctx, int B) {
+  if (ctx->fused || !ctx->has_a || !ctx->use_tc || ctx->N > 511 || B >= 8192) return false;
+  if ((int64_t)B * (ctx->N * (ctx->N - 1) / 2) >= (int64_t)1 << 30) return false;
+  int np, k1p, ns;
+  if (!pick_final_tc(ctx->pa.fdim, &np, &k1p, &ns)) return false;
+  return (int)final_tc_smem(np, k1p, ns) <= ctx->smem_optin;
+}
+
+int launch_final_tc_dense(const gdss_ctx* ctx, const float* stack, int64_t s_bs, const float* flags, float* score_adj, int B,
+                          char* ws, const Workspace& w, cudaStream_t st) {
+  const NetPlan& p = ctx->pa;
+  const int N = ctx->N;
+  FinalTriArgs ta;
+  memset(&ta, 0, sizeof(ta));
+  ta.stackT = stack; ta.pstride = 0; ta.dense_bs = s_bs; ta.fb = 9;
+  ta.gmap = reinterpret_cast<const int*>(ws + w.off[R_GMAP]);
+  ta.meta = reinterpret_cast<const int*>(ws + w.off[R_META]);
+  ta.w1 = ctx->blob_a + p.fw[0]; ta.b1 = ctx->blob_a + p.fb[0]; ta.w2 = ctx->blob_a + p.fw[1]; ta.b2 = ctx->blob_a + p.fb[1];
+  ta.w3 = ctx->blob_a + p.fw[2]; ta.b3 = ctx->blob_a + p.fb[2];
+  ta.out = score_adj; ta.flags = flags; ta.N = N; ta.fdim = p.fdim; ta.H = 2 * p.fdim; ta.Hs = p.Hp;
+  int np = 0, k1p = 0, tns = 2;
+  final_tc_fn tfn = pick_final_tc(p.fdim, &np, &k1p, &tns);
+  if (!tfn) return GDSS_E_UNSUPPORTED;
+  const size_t tsm = final_tc_smem(np, k1p, tns);
+  cudaError_t e = cudaFuncSetAttribute(tfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsm);
+  if (e != cudaSuccess) return (int)e;
+  const int64_t max_tiles = ((int64_t)B * (N * (N - 1) / 2) + 127) / 128;
+  if (max_tiles <= 0) return 0;
+  int grid = ctx->num_sms > 0 ? ctx->num_sms : 148;
+  if ((int64_t)grid > max_tiles) grid = (int)max_tiles;
+  int* errflag = reinterpret_cast<int*>(ws + w.off[R_META]) + 16;
+  tfn<<<grid, 128 * tns, tsm, st>>>(ta, errflag);
+  launched(K_FINAL_EDGE, st);
+  LAUNCH_CHECK();
   return 0;
 }
 

@@ -95,9 +95,14 @@ inline void launched(int kid, cudaStream_t st) { count_launch(); prof_tick(kid, 
 
 // fused small-graph path (gdss_fused.cu)
 bool fused_supported(const gdss_ctx* ctx);
+int64_t fused_query(const gdss_ctx* ctx, int what);   // 0: networks fusable, 1: shared-memory bytes at N
 int launch_tri_setup(const gdss_ctx* ctx, const int* neff, int B, char* ws, const Workspace& w, cudaStream_t st);
 int launch_eval_fused(const gdss_ctx* ctx, const float* x, const float* adj, const float* flags, const int* neff,
                       float* score_x, float* score_adj, int B, char* ws, const Workspace& w, cudaStream_t st);
+// general path: ScoreNetworkA.final on the tensor-core kernel over the dense channel stack (needs the pixel bookkeeping)
+bool final_tc_dense_ok(const gdss_ctx* ctx, int B);
+int launch_final_tc_dense(const gdss_ctx* ctx, const float* stack, int64_t s_bs, const float* flags, float* score_adj, int B,
+                          char* ws, const Workspace& w, cudaStream_t st);
 // flags -> neff (+ the pixel bookkeeping of the fused path); call once per flags tensor
 int launch_setup(const gdss_ctx* ctx, const float* flags, int B, int inputs_masked, char* ws, const Workspace& w,
                  cudaStream_t st);

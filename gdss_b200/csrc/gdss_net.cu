@@ -596,47 +596,76 @@ struct FinalNodeArgs {
   float* out; const float* flags; const int* neff; int N;
 };
 
-#define FN_ROWS 32
+#define FN_ROWS 16
+
+// one linear of the MLP on a 16-row tile: inT [K][16] (k-major) -> outT [Hout][16] (ELU) or, for the last layer, global
+// rows.  Thread = (64-wide column lane, 4-row group); 4 rows x 3 columns of accumulators per pass, weights [K][ldw]
+// read through L1 / L2 (coalesced over the column lanes), inputs as one broadcast float4 per k.
+template <bool LAST>
+DEVINL void fn_linear(const float* inT, int K, const float* __restrict__ W, int ldw, const float* __restrict__ bias, int Hout,
+                      float* outT, float* O, int64_t ldo, const float* fl, int rows, int tid) {
+  const int cg = tid & 63, rg = tid >> 6;
+  for (int o0 = 0; o0 < Hout; o0 += 192) {
+    const int o[3] = {o0 + cg, o0 + cg + 64, o0 + cg + 128};
+    if (o[0] >= Hout) break;
+    const bool on[3] = {true, o[1] < Hout, o[2] < Hout};
+    const float* wp[3] = {W + o[0], W + (on[1] ? o[1] : o[0]), W + (on[2] ? o[2] : o[0])};
+    float acc[4][3];
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+      const float bb = on[q] ? __ldg(bias + o[q]) : 0.f;
+#pragma unroll
+      for (int r = 0; r < 4; ++r) acc[r][q] = bb;
+    }
+#pragma unroll 4
+    for (int k = 0; k < K; ++k) {
+      const float4 xv = *reinterpret_cast<const float4*>(inT + k * FN_ROWS + 4 * rg);
+      const float w0 = __ldg(wp[0] + (int64_t)k * ldw), w1 = __ldg(wp[1] + (int64_t)k * ldw), w2 = __ldg(wp[2] + (int64_t)k * ldw);
+      acc[0][0] = fmaf(xv.x, w0, acc[0][0]); acc[1][0] = fmaf(xv.y, w0, acc[1][0]);
+      acc[2][0] = fmaf(xv.z, w0, acc[2][0]); acc[3][0] = fmaf(xv.w, w0, acc[3][0]);
+      acc[0][1] = fmaf(xv.x, w1, acc[0][1]); acc[1][1] = fmaf(xv.y, w1, acc[1][1]);
+      acc[2][1] = fmaf(xv.z, w1, acc[2][1]); acc[3][1] = fmaf(xv.w, w1, acc[3][1]);
+      acc[0][2] = fmaf(xv.x, w2, acc[0][2]); acc[1][2] = fmaf(xv.y, w2, acc[1][2]);
+      acc[2][2] = fmaf(xv.z, w2, acc[2][2]); acc[3][2] = fmaf(xv.w, w2, acc[3][2]);
+    }
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+      if (!on[q]) continue;
+      if (LAST) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+          if (4 * rg + r < rows) O[(int64_t)(4 * rg + r) * ldo + o[q]] = acc[r][q] * fl[4 * rg + r];
+      } else {
+        *reinterpret_cast<float4*>(outT + o[q] * FN_ROWS + 4 * rg) =
+            make_float4(elu_f(acc[0][q]), elu_f(acc[1][q]), elu_f(acc[2][q]), elu_f(acc[3][q]));
+      }
+    }
+  }
+}
 
 __global__ void __launch_bounds__(256) final_node_kernel(FinalNodeArgs a) {
-  extern __shared__ float sm[];
+  extern __shared__ __align__(16) float sm[];
   const int b = blockIdx.y, n = a.neff[b];
   const int i0 = blockIdx.x * FN_ROWS;
   if (i0 >= n) return;
   const int rows = min(FN_ROWS, n - i0);
   const int K = a.fdim, H = a.H;
-  float* X0 = sm;                    // [rows][K]
-  float* H1 = X0 + FN_ROWS * K;      // [rows][H]
-  float* H2 = H1 + FN_ROWS * H;      // [rows][H]
+  float* X0 = sm;                    // [K][16]
+  float* H1 = X0 + FN_ROWS * K;      // [H][16]
+  float* H2 = H1 + FN_ROWS * H;      // [H][16]
   const int tid = threadIdx.x;
-  const float* XS = a.xs + b * a.xs_bs;
-  for (int idx = tid; idx < rows * K; idx += 256) {
-    int r = idx / K, k = idx - r * K;
-    X0[idx] = XS[(int64_t)(i0 + r) * K + k];
+  const float* XS = a.xs + b * a.xs_bs + (int64_t)i0 * K;
+  for (int idx = tid; idx < FN_ROWS * K; idx += 256) {
+    const int r = idx / K, k = idx - r * K;
+    X0[k * FN_ROWS + r] = r < rows ? XS[idx] : 0.f;
   }
   __syncthreads();
-  for (int idx = tid; idx < rows * H; idx += 256) {
-    int r = idx / H, o = idx - r * H;
-    float s = a.b1[o];
-    for (int k = 0; k < K; ++k) s = fmaf(X0[r * K + k], __ldg(a.w1 + k * a.Hs + o), s);
-    H1[idx] = elu_f(s);
-  }
+  fn_linear<false>(X0, K, a.w1, a.Hs, a.b1, H, H1, nullptr, 0, nullptr, rows, tid);
   __syncthreads();
-  for (int idx = tid; idx < rows * H; idx += 256) {
-    int r = idx / H, o = idx - r * H;
-    float s = a.b2[o];
-    for (int k = 0; k < H; ++k) s = fmaf(H1[r * H + k], __ldg(a.w2 + k * a.Hs + o), s);
-    H2[idx] = elu_f(s);
-  }
+  fn_linear<false>(H1, H, a.w2, a.Hs, a.b2, H, H2, nullptr, 0, nullptr, rows, tid);
   __syncthreads();
-  const float* fl = a.flags + (int64_t)b * a.N;
-  float* O = a.out + (int64_t)b * a.N * a.fout;
-  for (int idx = tid; idx < rows * a.fout; idx += 256) {
-    int r = idx / a.fout, o = idx - r * a.fout;
-    float s = a.b3[o];
-    for (int k = 0; k < H; ++k) s = fmaf(H2[r * H + k], __ldg(a.w3 + k * a.fouts + o), s);
-    O[(int64_t)(i0 + r) * a.fout + o] = s * fl[i0 + r];
-  }
+  fn_linear<true>(H2, H, a.w3, a.fouts, a.b3, a.fout, nullptr, a.out + ((int64_t)b * a.N + i0) * a.fout, a.fout,
+                  a.flags + (int64_t)b * a.N + i0, rows, tid);
 }
 
 // x rows -> first F columns of the node feature stack
@@ -728,6 +757,14 @@ void layout_workspace(const gdss_ctx* ctx, int B, Workspace* w) {
     // X network: node-feature stack [fdim][nstride] read by the batched tensor-core final MLP
     w->nstride = ((int64_t)B * N + 127) / 128 * 128 + 128;
     sz[R_XS] = ctx->has_x ? 4 * w->nstride * ctx->px.fdim : 0;
+  }
+  if (final_tc_dense_ok(ctx, B)) {
+    // general path with the tensor-core final MLP: pixel bookkeeping only (the kernel reads the dense stack)
+    const int64_t pmax = (int64_t)B * (N * (N - 1) / 2);
+    sz[R_POFF] = 4 * ((int64_t)B + 1);
+    sz[R_META] = 256;
+    sz[R_GMAP] = 4 * ((pmax + 127) / 128 * 128 + 128);
+    sz[R_ORDER] = 4 * (int64_t)B;
   }
   sz[R_RAW_X] = 4 * (int64_t)B * N * F;
   sz[R_RAW_ADJ] = 4 * (int64_t)B * N * N;
@@ -905,7 +942,10 @@ static int run_attn_net(const gdss_ctx* ctx, const NetPlan& p, const float* blob
     }
     cur += L.c_in;
   }
-  if (isA) {
+  if (isA && final_tc_dense_ok(ctx, B)) {
+    int rc = launch_final_tc_dense(ctx, stack, s_bs, flags, score, B, ws, w, st);
+    if (rc) return rc;
+  } else if (isA) {
     FinalEdgeArgs fa;
     fa.stack = stack; fa.s_bs = s_bs;
     fa.w1 = blob + p.fw[0]; fa.b1 = blob + p.fb[0]; fa.w2 = blob + p.fw[1]; fa.b2 = blob + p.fb[1];
@@ -988,7 +1028,7 @@ int launch_setup(const gdss_ctx* ctx, const float* flags, int B, int inputs_mask
   int* neff = reinterpret_cast<int*>(ws + w.off[R_NEFF]);
   int rc = launch_neff(flags, neff, B, ctx->N, inputs_masked, st);
   if (rc) return rc;
-  if (ctx->fused) rc = launch_tri_setup(ctx, neff, B, ws, w, st);
+  if (ctx->fused || final_tc_dense_ok(ctx, B)) rc = launch_tri_setup(ctx, neff, B, ws, w, st);
   return rc;
 }
 
