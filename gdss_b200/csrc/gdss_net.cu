@@ -139,7 +139,8 @@ __global__ void __launch_bounds__(256) deg_kernel(const float* __restrict__ plan
   const float* P = planes + b * p_bs + (int64_t)c * N * N;
   float* D = dis + b * d_bs + (int64_t)c * N;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  for (int i = w; i < n; i += 8) {
+  // blockIdx.z: tile of 32 rows (4 per warp)
+  for (int i = blockIdx.z * 32 + w; i < min(n, blockIdx.z * 32 + 32); i += 8) {
     float s = 0.f;
     for (int j = lane; j < n; j += 32) s += (j == i) ? 1.f : P[(int64_t)i * N + j];
     s = warp_sum(s);
@@ -163,48 +164,61 @@ struct GcnArgs {
 };
 
 #define GCN_JC 64
-#define GCN_MAXIT 6
+#define GCN_MAXIT 3            // register-blocked items (4 rows x 1 column) per thread
 
+// Both contractions are register-blocked over 4 consecutive rows: the left operand is kept k-major in shared memory
+// ([j][TIP] / [f][TIP]) so that the 4 row values are one broadcast float4, the right operand (x rows / W rows) is read
+// once per k and used for 4 FMAs.  The accumulation order per output (j ascending, then f ascending) is the natural one.
 __global__ void __launch_bounds__(256) gcn_kernel(GcnArgs a) {
-  extern __shared__ float sm[];
+  extern __shared__ __align__(16) float sm[];
   const int b = blockIdx.z, c = blockIdx.y, n = a.neff[b];
   const int i0 = blockIdx.x * a.TI;
   if (i0 >= n) return;
   const int ti = min(a.TI, n - i0);
   const int F = a.f_in, N = a.N;
+  const int TIP = a.TI + 4, q4 = (ti + 3) >> 2;      // padded row count (a.TI is a multiple of 4), row quads of this tile
   float* xs = sm;                         // [JC][F]
-  float* As = xs + GCN_JC * F;            // [TI][JC+1]
-  float* AX = As + a.TI * (GCN_JC + 1);   // [TI][F+1]
+  float* AsT = xs + GCN_JC * F;           // [JC][TIP]   A~ diag(dis), k-major
+  float* AXT = AsT + GCN_JC * TIP;        // [F][TIP]    dis_i * (A~ diag(dis) x), k-major
   const float* P = a.planes + b * a.p_bs + (int64_t)c * N * N;
   const float* X = a.x + b * a.x_bs;
   const float* D = a.dis + b * a.d_bs + (int64_t)c * N;
   const int tid = threadIdx.x;
-  const int items = ti * F;
-  float acc[GCN_MAXIT];
+  const int items = q4 * F;               // (row quad, feature)
+  float acc[GCN_MAXIT][4];
 #pragma unroll
-  for (int q = 0; q < GCN_MAXIT; ++q) acc[q] = 0.f;
+  for (int q = 0; q < GCN_MAXIT; ++q)
+#pragma unroll
+    for (int r = 0; r < 4; ++r) acc[q][r] = 0.f;
   for (int j0 = 0; j0 < n; j0 += GCN_JC) {
     const int jc = min(GCN_JC, n - j0);
     for (int idx = tid; idx < jc * F; idx += 256) {
       int j = idx / F, f = idx - j * F;
       xs[idx] = X[(int64_t)(j0 + j) * a.ldx + f];
     }
-    for (int idx = tid; idx < ti * jc; idx += 256) {
+    for (int idx = tid; idx < 4 * q4 * jc; idx += 256) {
       int i = idx / jc, j = idx - i * jc;
       int gi = i0 + i, gj = j0 + j;
-      float v = (gi == gj) ? 1.f : P[(int64_t)gi * N + gj];
-      As[i * (GCN_JC + 1) + j] = v * D[gj];
+      float v = 0.f;
+      if (i < ti) v = ((gi == gj) ? 1.f : P[(int64_t)gi * N + gj]) * D[gj];
+      AsT[j * TIP + i] = v;
     }
     __syncthreads();
 #pragma unroll
     for (int q = 0; q < GCN_MAXIT; ++q) {
       int idx = tid + q * 256;
       if (idx < items) {
-        int i = idx / F, f = idx - i * F;
-        const float* ar = As + i * (GCN_JC + 1);
-        float s = acc[q];
-        for (int j = 0; j < jc; ++j) s = fmaf(ar[j], xs[j * F + f], s);
-        acc[q] = s;
+        int iq = idx / F, f = idx - iq * F;
+        const float* ar = AsT + 4 * iq;
+        const float* xr = xs + f;
+        float s0 = acc[q][0], s1 = acc[q][1], s2 = acc[q][2], s3 = acc[q][3];
+#pragma unroll 4
+        for (int j = 0; j < jc; ++j) {
+          const float4 av = *reinterpret_cast<const float4*>(ar + j * TIP);
+          const float xv = xr[j * F];
+          s0 = fmaf(av.x, xv, s0); s1 = fmaf(av.y, xv, s1); s2 = fmaf(av.z, xv, s2); s3 = fmaf(av.w, xv, s3);
+        }
+        acc[q][0] = s0; acc[q][1] = s1; acc[q][2] = s2; acc[q][3] = s3;
       }
     }
     __syncthreads();
@@ -213,21 +227,40 @@ __global__ void __launch_bounds__(256) gcn_kernel(GcnArgs a) {
   for (int q = 0; q < GCN_MAXIT; ++q) {
     int idx = tid + q * 256;
     if (idx < items) {
-      int i = idx / F, f = idx - i * F;
-      AX[i * (F + 1) + f] = acc[q] * D[i0 + i];
+      int iq = idx / F, f = idx - iq * F;
+      float4 o;
+      o.x = acc[q][0] * (4 * iq + 0 < ti ? D[i0 + 4 * iq + 0] : 0.f);
+      o.y = acc[q][1] * (4 * iq + 1 < ti ? D[i0 + 4 * iq + 1] : 0.f);
+      o.z = acc[q][2] * (4 * iq + 2 < ti ? D[i0 + 4 * iq + 2] : 0.f);
+      o.w = acc[q][3] * (4 * iq + 3 < ti ? D[i0 + 4 * iq + 3] : 0.f);
+      *reinterpret_cast<float4*>(AXT + f * TIP + 4 * iq) = o;
     }
   }
   __syncthreads();
   const float* W = a.W + (int64_t)c * a.w_cs;
   const float* Bv = a.bias + (int64_t)c * a.b_cs;
   float* O = a.out + b * a.o_bs + (int64_t)c * a.o_cs;
-  for (int idx = tid; idx < ti * a.ow; idx += 256) {
-    int i = idx / a.ow, o = idx - i * a.ow + a.col0;
-    float s = Bv[o];
-    const float* axr = AX + i * (F + 1);
-    for (int f = 0; f < F; ++f) s = fmaf(axr[f], __ldg(W + (int64_t)f * a.w_ld + o), s);
-    if (a.act == 1) s = tanh_f(s);
-    O[(int64_t)(i0 + i) * a.ldo + o] = s;
+  for (int idx = tid; idx < q4 * a.ow; idx += 256) {
+    int iq = idx / a.ow, o = idx - iq * a.ow + a.col0;
+    const float bb = Bv[o];
+    float s0 = bb, s1 = bb, s2 = bb, s3 = bb;
+    const float* axr = AXT + 4 * iq;
+    const float* wp = W + o;
+#pragma unroll 4
+    for (int f = 0; f < F; ++f) {
+      const float4 av = *reinterpret_cast<const float4*>(axr + f * TIP);
+      const float wv = __ldg(wp + (int64_t)f * a.w_ld);
+      s0 = fmaf(av.x, wv, s0); s1 = fmaf(av.y, wv, s1); s2 = fmaf(av.z, wv, s2); s3 = fmaf(av.w, wv, s3);
+    }
+    const float sv[4] = {s0, s1, s2, s3};
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      if (4 * iq + r < ti) {
+        float s = sv[r];
+        if (a.act == 1) s = tanh_f(s);
+        O[(int64_t)(i0 + 4 * iq + r) * a.ldo + o] = s;
+      }
+    }
   }
 }
 
@@ -689,8 +722,8 @@ static int node_tile(int N) {            // balanced row tiles of at most 48 row
 }
 
 static int gcn_tile(int N, int f_in) {
-  int ti = node_tile(N);
-  while (ti > 1 && ti * f_in > 256 * GCN_MAXIT) --ti;
+  int ti = (node_tile(N) + 3) & ~3;                  // row quads
+  while (ti > 4 && (ti / 4) * f_in > 256 * GCN_MAXIT) ti -= 4;
   return ti;
 }
 
@@ -822,7 +855,8 @@ static final_fn pick_final(int H, int* hp) {
 }
 
 static int launch_gcn(const GcnArgs& g, int C, int B, cudaStream_t st) {
-  size_t smem = sizeof(float) * ((size_t)GCN_JC * g.f_in + (size_t)g.TI * (GCN_JC + 1) + (size_t)g.TI * (g.f_in + 1));
+  if ((g.TI / 4) * g.f_in > 256 * GCN_MAXIT) return GDSS_E_UNSUPPORTED;
+  size_t smem = sizeof(float) * ((size_t)GCN_JC * g.f_in + (size_t)(g.TI + 4) * (GCN_JC + g.f_in));
   int rc = set_smem(gcn_kernel, smem);
   if (rc) return rc;
   dim3 grid((g.N + g.TI - 1) / g.TI, C, B);
@@ -878,7 +912,7 @@ static int run_attn_net(const gdss_ctx* ctx, const NetPlan& p, const float* blob
     const bool need_edge = isA || !last;   // X_GMH: the last layer's adj_out (hence Q, K) is dead
     const bool need_node = !isA || !last;  // A: the last layer's x_out (hence V) is dead
     const float* pin = stack + (int64_t)cur * NN;
-    deg_kernel<<<dim3(L.c_in, B), 256, 0, st>>>(pin, s_bs, dis, d_bs, neff, N);
+    deg_kernel<<<dim3(L.c_in, B, (N + 31) / 32), 256, 0, st>>>(pin, s_bs, dis, d_bs, neff, N);
     launched(K_DEG, st);
     LAUNCH_CHECK();
     GcnArgs g;
@@ -993,7 +1027,7 @@ static int run_gcn_net(const gdss_ctx* ctx, const NetPlan& p, const float* blob,
   copy_x_kernel<<<dim3((N * F + 255) / 256, B), 256, 0, st>>>(x, xs, N, F, p.fdim, neff);
   launched(K_COPY, st);
   LAUNCH_CHECK();
-  deg_kernel<<<dim3(1, B), 256, 0, st>>>(adj, NN, dis, N, neff, N);
+  deg_kernel<<<dim3(1, B, (N + 31) / 32), 256, 0, st>>>(adj, NN, dis, N, neff, N);
   launched(K_DEG, st);
   LAUNCH_CHECK();
   for (int l = 0; l < p.depth; ++l) {
