@@ -563,12 +563,29 @@ DEVINL void edge_mlp(const float* M, int MS, const float* pin, int PM, const uns
 struct Split { uint32_t hi, lo; };
 
 // cvt.rna.tf32.f32 is emulated on sm_100a (add, NaN/Inf test, select, mask = 4 instructions per conversion); the tensor
-// core ignores the 13 low mantissa bits of a TF32 operand, so round-to-nearest is one integer add of half an ulp and the
-// hardware's own truncation.  hi is masked explicitly because lo is computed from it.  (Inf stays Inf, NaN stays NaN.)
+// core ignores the 13 low mantissa bits of a TF32 operand, so the split needs no explicit conversion at all:
+//   mode 2 (default): hi = v with the low 13 bits masked (truncation; v - hi is then exact), lo = v - hi handed to the
+//           tensor core as it is (the hardware truncates it): 2 instructions per value.  The truncation of lo is one-sided
+//           (|operand| is under-estimated by < 2^-20 relative): measured error of the raw scores against the reference
+//           fixtures 1e-6 .. 4.4e-6 rel-L2 (bar: 1e-4), thresholded 1000-step outputs unchanged (tools/err_probe.py)
+//   mode 1: lo rounded to nearest (+ half an ulp before the hardware truncation): 3 instructions
+//   mode 0: hi and lo both rounded to nearest: 4 instructions, 0.7e-6 .. 1.6e-6; 4 % slower end to end than mode 2
+// (Inf stays Inf, NaN stays NaN in every mode.)
+#ifndef GDSS_SPLIT_MODE
+#define GDSS_SPLIT_MODE 2
+#endif
 DEVINL Split split_tf32(float v) {
   Split s;
+#if GDSS_SPLIT_MODE == 0
   s.hi = (__float_as_uint(v) + 0x1000u) & 0xffffe000u;
   s.lo = __float_as_uint(v - __uint_as_float(s.hi)) + 0x1000u;
+#elif GDSS_SPLIT_MODE == 1
+  s.hi = __float_as_uint(v) & 0xffffe000u;                       // truncated hi: v - hi is exact
+  s.lo = __float_as_uint(v - __uint_as_float(s.hi)) + 0x1000u;   // lo rounded to nearest by the add + hardware truncation
+#else
+  s.hi = __float_as_uint(v) & 0xffffe000u;
+  s.lo = __float_as_uint(v - __uint_as_float(s.hi));             // lo truncated by the tensor core
+#endif
   return s;
 }
 
@@ -922,6 +939,7 @@ __device__ __noinline__ void channel_chain_mma(int lane, const float* pl, const 
   }
   __syncwarp();
   const int o_lo = need_edge ? 0 : 2 * AT, o_hi = need_node ? qkvw : 2 * AT;
+  const float scale2 = scale * 2.8853900817779268f;
   for (int m0 = part * MB; m0 < mt; m0 += MB * nparts) {
     float c1[MB][NF][4];
 #pragma unroll
@@ -993,7 +1011,9 @@ __device__ __noinline__ void channel_chain_mma(int lane, const float* pl, const 
 #pragma unroll
           for (int jn = 0; jn < NF; ++jn)
             if (jn < nf) mma3(ca, qh[mb][jn], ql[mb][jn], w0[jn], w1[jn]);
-          const float c[4] = {acc_get(ca, 0), acc_get(ca, 1), acc_get(ca, 2), acc_get(ca, 3)};
+          // Q columns carry the map's 2 log2(e) / sqrt(out_dim) factor (one multiply per Q value instead of one per product)
+          const float qs = o0 < AT ? scale2 : 1.f;
+          const float c[4] = {acc_get(ca, 0) * qs, acc_get(ca, 1) * qs, acc_get(ca, 2) * qs, acc_get(ca, 3) * qs};
           const int ra = 16 * (m0 + mb) + g, rb = ra + 8;
           if (o0 < 2 * AT) {
             if (ra < n) *reinterpret_cast<float2*>(qkc + ra * QKS + oc) = make_float2(c[0], c[1]);
@@ -1010,7 +1030,6 @@ __device__ __noinline__ void channel_chain_mma(int lane, const float* pl, const 
   else __syncwarp();
   // ---- attention map (attention.py:35-49): mean over the 4 heads and both orientations of tanh(Q_h.K_h / sqrt(out_dim))
   if (need_edge) {
-    const float scale2 = scale * 2.8853900817779268f;
     for (int p = part * 32 + lane; p < P; p += 32 * nparts) {
       const unsigned ij = pix[p];
       const int i = ij >> 8, j = ij & 255;
@@ -1029,7 +1048,7 @@ __device__ __noinline__ void channel_chain_mma(int lane, const float* pl, const 
           p1 = fma2(lo2(a1), lo2(b1), p1); p1 = fma2(hi2(a1), hi2(b1), p1);
           p2 = fma2(lo2(a2), lo2(b2), p2); p2 = fma2(hi2(a2), hi2(b2), p2);
         }
-        m += sig2((p1.x + p1.y) * scale2) + sig2((p2.x + p2.y) * scale2);
+        m += sig2(p1.x + p1.y) + sig2(p2.x + p2.y);
       }
       Mc[p] = fmaf(-0.25f, m, 1.f);             // mean of the 8 tanh = 1 - (2 / 8) * sum of 1 / (exp(2 z) + 1)
     }
