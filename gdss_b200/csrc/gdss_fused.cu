@@ -1781,6 +1781,28 @@ __global__ void __launch_bounds__(128 * NS, 1) final_edge_tc_kernel(FinalTriArgs
   for (int tile = blockIdx.x; tile < ntiles && ok; tile += gridDim.x) {
     const int64_t gp = (int64_t)tile * 128 + row;
     const int next = tile + (int)gridDim.x;
+    // where this thread's result goes and its flag mask: a chain of two dependent global loads, issued here so that it is
+    // complete long before the second epilogue needs it (it used to stall the whole CTA at the end of every tile)
+    int out_b = -1, out_i = 0, out_j = 0;
+    float out_f = 0.f;
+    if (half == 0) {
+      if (NODE) {
+        if (gp < (int64_t)a.B * N) {
+          const int b = (int)(gp / N), i = (int)(gp - (int64_t)b * N);
+          if (i < __ldg(a.neff + b)) {
+            out_b = b;
+            out_f = __ldg(a.flags + (int64_t)b * N + i);
+          }
+        }
+      } else {
+        const int gv = __ldg(a.gmap + gp);
+        if (gv >= 0) {
+          out_b = gv >> (2 * a.fb); out_i = (gv >> a.fb) & ((1 << a.fb) - 1); out_j = gv & ((1 << a.fb) - 1);
+          const float* fl = a.flags + (int64_t)out_b * N;
+          out_f = __ldg(fl + out_i) * __ldg(fl + out_j);
+        }
+      }
+    }
     if (!PIPE) {
       stage_a1(next);
       tc_sync_before_mma();
@@ -1866,10 +1888,9 @@ __global__ void __launch_bounds__(128 * NS, 1) final_edge_tc_kernel(FinalTriArgs
       }
       asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
       __syncthreads();
-      if (half == 0 && gp < (int64_t)a.B * N) {
-        const int b = (int)(gp / N), i = (int)(gp - (int64_t)b * N);
-        if (i < a.neff[b]) {
-          const float f = a.flags[(int64_t)b * N + i];
+      if (half == 0 && out_b >= 0) {
+        {
+          const float f = out_f;
           float* O = a.out + gp * a.F;
 #pragma unroll
           for (int o = 0; o < FOP; ++o) {
@@ -1911,14 +1932,12 @@ __global__ void __launch_bounds__(128 * NS, 1) final_edge_tc_kernel(FinalTriArgs
     asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
     __syncthreads();                        // also: every thread is done reading D before the next tile's MMA
     if (half == 0) {
-      const int v = a.gmap[gp];
-      if (v >= 0) {
-        const int b = v >> (2 * a.fb), i = (v >> a.fb) & ((1 << a.fb) - 1), j = v & ((1 << a.fb) - 1);
-        const float* fl = a.flags + (int64_t)b * N;
+      if (out_b >= 0) {
+        const int b = out_b, i = out_i, j = out_j;
         float acc = dot;
 #pragma unroll
         for (int q = 0; q < NS - 1; ++q) acc += part[q * 128 + row];
-        const float s = (acc + b3) * (fl[i] * fl[j]);
+        const float s = (acc + b3) * out_f;
         float* O = a.out + (int64_t)b * N * N;
         O[(int64_t)i * N + j] = s;
         O[(int64_t)j * N + i] = s;
@@ -2194,6 +2213,7 @@ int launch_eval_fused(const gdss_ctx* ctx, const float* x, const float* adj, con
       smem = plan_smem(ctx, nb[k], &fa.sl, false);
       e = cudaFuncSetAttribute(fused_layers_kernel<256, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e != cudaSuccess) return (int)e;
+      // (64 / 96 / 256 threads per CTA measured 20 % / 12 % / 31 % slower than 128 on C2)
       fused_layers_kernel<256, false, 2><<<B, 128, smem, ks>>>(fa);
     } else if (smem <= limit2) {
       e = cudaFuncSetAttribute(fused_layers_kernel<256, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -239,6 +239,49 @@ def test_tensor_core_kernel_is_used_and_clean():
     assert float((sa_c - sa_c.transpose(-1, -2)).abs().max()) == 0.0
 
 
+@pytest.mark.parametrize("name,fused", [("community_small", 1), ("ego_small", 1), ("qm9", 1), ("zinc250k_v2", 1), ("enzymes", 0),
+                                        ("grid", 0)])
+def test_kernel_path_selection(name, fused):
+    """Every checkpoint with N <= 64 runs on the per-graph kernel (community_small through the weight-less shared-memory
+    plan), ENZYMES / grid on the tiled general path; gdss_ctx_query reports it."""
+    from gdss_b200.engine import Engine
+    ck = load_golden_ckpt(name)
+    eng = Engine(ck["x_state_dict"], ck["adj_state_dict"], int(ck["params_adj"]["max_node_num"]), "cuda")
+    q = lambda k: int(eng.L.gdss_ctx_query(eng.ctx, k.encode()))
+    assert q("fused") == fused and q("fused_fusable") == fused
+    assert q("use_tc") == 1 and q("use_mma") == 1 and q("smem_optin") >= 227 * 1024
+    assert q("no_such_key") < 0
+
+
+def test_general_path_tensor_core_final_on_ragged_large_graphs():
+    """N = 125 (general path): ScoreNetworkA.final on the tcgen05 kernel reading the dense channel stack through the
+    9-bit pixel map, ragged batch spanning several 128-pixel tiles per graph; against the oracle, error flag clear."""
+    from gdss_b200.engine import Engine
+    ck = load_golden_ckpt("enzymes")
+    N, F, B = 125, 10, 5
+    g = torch.Generator().manual_seed(5)
+    counts = [125, 17, 64, 2, 99]
+    flags = torch.zeros(B, N)
+    for b, c in enumerate(counts):
+        flags[b, :c] = 1
+    x = torch.randn(B, N, F, generator=g) * flags[:, :, None]
+    a = torch.randn(B, N, N, generator=g).triu(1)
+    adj = (a + a.transpose(-1, -2)) * flags[:, :, None] * flags[:, None, :]
+    with torch.no_grad():
+        ox = O.run_model(ck["x_state_dict"], ck["params_x"], x, adj, flags)
+        oa = O.run_model(ck["adj_state_dict"], ck["params_adj"], x, adj, flags)
+    eng = Engine(ck["x_state_dict"], ck["adj_state_dict"], N, "cuda")
+    sx, sa = eng.score(x.cuda(), adj.cuda(), flags.cuda(), inputs_masked=True)
+    torch.cuda.synchronize()
+    assert rel(sx, ox) <= TOL and rel(sa, oa) <= TOL, (rel(sx, ox), rel(sa, oa))
+    meta = eng.region(B, "meta", (32,), torch.int32).cpu()
+    npix = sum(c * (c - 1) // 2 for c in counts)
+    assert int(meta[0]) == npix and int(meta[1]) == (npix + 127) // 128 and int(meta[16]) == 0
+    sa_c = sa.cpu()
+    assert float((sa_c - sa_c.transpose(-1, -2)).abs().max()) == 0.0
+    assert float((sa_c * (1 - flags[:, :, None] * flags[:, None, :])).abs().max()) == 0.0
+
+
 def test_decode_mol_is_bit_exact():
     """Post-sampling decode (sampler.py:131-138) on the device: golden fixture of the reference lines + random states
     straddling every threshold, bit-exact against the oracle."""

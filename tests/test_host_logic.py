@@ -166,6 +166,36 @@ def test_shard_bounds_cover_the_batch():
             assert max(sizes) - min(sizes) <= 1
 
 
+@pytest.mark.parametrize("name,fusable", [("community_small", 1), ("ego_small", 1), ("qm9", 1), ("zinc250k", 1),
+                                          ("zinc250k_v2", 1), ("enzymes", 0), ("grid", 0)])
+def test_ctx_query_reports_the_plan_of_every_checkpoint(name, fusable):
+    """Planning is host logic: a context can be created (not run) without a device, and gdss_ctx_query tells which networks
+    fit the per-graph kernel and how much shared memory its staged-weights plan needs."""
+    from gdss_b200._lib import lib
+    from gdss_b200.engine import pack_network
+    L = lib()
+    ck = load_golden_ckpt(name)
+    N = int(ck["params_adj"]["max_node_num"])
+    dx, bx = pack_network(ck["x_state_dict"], N)
+    da, ba = pack_network(ck["adj_state_dict"], N)
+    ctx = L.gdss_ctx_create(N, int(dx.max_feat_num), C.byref(dx), bx.data_ptr(), C.byref(da), ba.data_ptr())
+    assert ctx
+    try:
+        q = lambda k: int(L.gdss_ctx_query(ctx, k.encode()))
+        assert q("fused_fusable") == fusable
+        smem = q("fused_smem_bytes")
+        assert (smem > 0) == bool(fusable)
+        if name == "zinc250k_v2":
+            assert smem <= 227 * 1024                      # one 512-thread CTA of the largest graphs fits an SM
+        if name == "community_small":
+            assert smem > 227 * 1024                       # 96 KB of Q|K|V weights per layer: runs the weight-less plan
+        assert q("bogus") < 0
+        if not HAS_CUDA:
+            assert q("smem_optin") == 48 * 1024            # no device: the default limit, nothing is launched
+    finally:
+        L.gdss_ctx_destroy(ctx)
+
+
 @pytest.mark.skipif(HAS_CUDA, reason="CPU-only behaviour")
 def test_compute_calls_fail_loudly_without_cuda():
     from gdss_b200 import _lib
