@@ -1637,6 +1637,8 @@ DEVINL void tc_sync_before_mma() {         // tcgen05.st / ld of every thread or
   asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
 }
 
+// (Measured and dropped: issuing the second contraction in two K chunks so that its first half overlaps the conversion of
+// the second half of the layer-2 operand -- the extra CTA barrier per tile cost more than the overlap gained, +5 %.)
 // NODE: final MLP of an X network (FOP = padded output width), rows = nodes.  NS: column splits = warps per TMEM lane
 // quarter (128 NS threads).  NS = 4 did not help (the tile time is the serial sum of the MMAs and the epilogues' ALU work,
 // not latency): every instance uses NS = 2.
