@@ -1889,7 +1889,7 @@ __global__ void __launch_bounds__(128 * NS, 1) final_edge_tc_kernel(FinalTriArgs
         for (int o = 0; o < FOP; ++o) part[((half - 1) * FOP + o) * 128 + row] = dv[o];
       }
       asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
-      __syncthreads();
+      ok = __syncthreads_and(ok);             // the tile's only barrier after the MMAs: partial sums visible, uniform loop exit
       if (half == 0 && out_b >= 0) {
         {
           const float f = out_f;
@@ -1903,8 +1903,7 @@ __global__ void __launch_bounds__(128 * NS, 1) final_edge_tc_kernel(FinalTriArgs
           }
         }
       }
-      ok = __syncthreads_and(ok);
-      continue;
+      continue;                               // (part[] is rewritten only after the next tile's barrier before its MMAs)
     }
     // ---- epilogue 2: ELU(D + b2) . w3 + b3, zero diagonal / flag mask (ScoreNetwork_A.py:143-148), mirrored store
     float dot = 0.f;
@@ -1932,7 +1931,8 @@ __global__ void __launch_bounds__(128 * NS, 1) final_edge_tc_kernel(FinalTriArgs
     }
     if (half > 0) part[(half - 1) * 128 + row] = dot;
     asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
-    __syncthreads();                        // also: every thread is done reading D before the next tile's MMA
+    ok = __syncthreads_and(ok);             // partial sums visible; every thread is done reading D before the next tile's MMA;
+                                            // uniform loop exit.  part[] is rewritten only after the next tile's barrier
     if (half == 0) {
       if (out_b >= 0) {
         const int b = out_b, i = out_i, j = out_j;
@@ -1945,7 +1945,6 @@ __global__ void __launch_bounds__(128 * NS, 1) final_edge_tc_kernel(FinalTriArgs
         O[(int64_t)j * N + i] = s;
       }
     }
-    ok = __syncthreads_and(ok);             // part[] is reused by the next tile; uniform loop exit
   }
   if (!ok && tid == 0) atomicExch(err, 1);
   asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
