@@ -618,7 +618,10 @@ DEVINL float acc_get(const Acc& c, int q) { return c.m[q]; }
 // pout may alias pin: a warp reads all inputs of its 16 pixels before it writes them (mma.sync is warp-synchronous).
 template <int NLIN>
 DEVINL void edge_mlp_mma(const float* M, int MS, const float* pin, int PM, const unsigned* pix, const float* fl, const float* wm,
-                         const FLayer& L, int P, float* pout, float* gout, int64_t gstride, int warp, int nwarps, int lane) {
+                         const FLayer& L, int P, float* pout, float* gout, int64_t gstride, int warp, int nwarps, int lane,
+                         int* queue) {
+  // queue != nullptr: the 16-pixel tiles are handed out through a shared counter (zeroed before the CTA barrier that
+  // precedes this call), so that warps arriving late (the node-MLP warps) and early finishers even out
   const int g = lane >> 2, t = lane & 3;
   const int C = L.c_in, c_out = L.c_out, K1 = 2 * C;
   const float* W1 = wm + L.ew_o[0];                 // [2C][16]
@@ -656,7 +659,13 @@ DEVINL void edge_mlp_mma(const float* M, int MS, const float* pin, int PM, const
   bia3[1] = 2 * t + 1 < c_out ? b3[2 * t + 1] : 0.f;
   const int ks1 = (K1 + 7) >> 3;                     // k-steps of layer 1 (1 or 2)
   const int ntile = (P + 15) >> 4;
-  for (int tile = warp; tile < ntile; tile += nwarps) {
+  for (int tile = warp;; tile += nwarps) {
+    if (queue) {
+      int tq = 0;
+      if (lane == 0) tq = atomicAdd(queue, 1);
+      tile = __shfl_sync(0xffffffffu, tq, 0);
+    }
+    if (tile >= ntile) break;
     const int pa = tile * 16 + g, pb = pa + 8;
     const int pac = pa < P ? pa : P - 1, pbc = pb < P ? pb : P - 1;
     // ---- layer 1: A fragments gathered from the channel planes
@@ -938,9 +947,26 @@ __device__ __noinline__ void channel_chain_mma(int lane, const float* pl, const 
     dv[i] = 1.0f / sqrtf(fmaxf(s0 + s1, 1.0f));
   }
   __syncwarp();
-  const int o_lo = need_edge ? 0 : 2 * AT, o_hi = need_node ? qkvw : 2 * AT;
+  int o_lo = need_edge ? 0 : 2 * AT, o_hi = need_node ? qkvw : 2 * AT;
   const float scale2 = scale * 2.8853900817779268f;
-  for (int m0 = part * MB; m0 < mt; m0 += MB * nparts) {
+  // Work split of the warps of one channel: row-tile groups first; warps beyond the row groups split the Q|K|V output
+  // column tiles of a row group (each recomputes that group's A^ x: cheaper than idling at the barrier below).
+  int rp = part, rstride = nparts;
+  {
+    const int nrow = (mt + MB - 1) / MB;
+    if (nparts > nrow) {
+      const int og = nparts / nrow, op = part / nrow;
+      rp = part - op * nrow;
+      rstride = nrow;
+      if (op >= og) rp = mt;                               // spare warp: no row group
+      else {
+        const int T = (o_hi - o_lo) >> 3, lo = o_lo;
+        o_lo = lo + 8 * ((op * T) / og);
+        o_hi = lo + 8 * (((op + 1) * T) / og);
+      }
+    }
+  }
+  for (int m0 = rp * MB; m0 < mt; m0 += MB * rstride) {
     float c1[MB][NF][4];
 #pragma unroll
     for (int mb = 0; mb < MB; ++mb)
@@ -1308,7 +1334,8 @@ __global__ void __launch_bounds__(NT, OCC) fused_layers_kernel(const __grid_cons
           const int c = nparts > 1 ? u % C : u, part = nparts > 1 ? u / C : 0;
           const float* Wc = wqp + c * L.f_in_p * L.qkvw;
           const float* bc = wqp + L.bq_o + c * L.qkvw;
-          if (A.use_mma && f <= 16 && attn == 16 && A.mb1) {         // graphs of at most 16 nodes: one row tile
+          if (A.use_mma && f <= 16 && attn == 16 && (A.mb1 || nparts > 1)) {   // graphs of at most 16 nodes: one row tile;
+                                                                               // several warps per channel: one tile per warp
             channel_chain_mma<WSM, 4, 2, 1>(lane, pin + c * PM, tab, S.TC, dinv + c * NBP, xin, XS, n, f, L.f_in_p, Wc, L.qkvw, bc,
                                             QK + c * n * QKS, QKS, R2 + c * h, LDV, L.need_edge, L.need_node, pix, P, scale, R1 + c * RS, part, nparts, 2 + c);
           } else if (A.use_mma && f <= 16 && attn == 16) {
@@ -1381,8 +1408,10 @@ __global__ void __launch_bounds__(NT, OCC) fused_layers_kernel(const __grid_cons
         if (!node_warps && L.need_node) __syncthreads();       // (never both: kept for symmetry of the barrier count)
         float* gout = isA ? A.stackT + (int64_t)cbase * A.pstride + gp0 : nullptr;
         if (A.use_mma) {
-          if (L.nlin == 3) edge_mlp_mma<3>(R1, RS, pin, PM, pix, fl, wmp, L, P, more ? PA : nullptr, gout, A.pstride, warp, nt_edge >> 5, lane);
-          else edge_mlp_mma<2>(R1, RS, pin, PM, pix, fl, wmp, L, P, more ? PA : nullptr, gout, A.pstride, warp, nt_edge >> 5, lane);
+          int* q = nullptr;      // (a shared tile queue that lets the node warps join was measured 3 % slower: per-warp weight
+                                 // fragment set-up and the atomic + shuffle per tile cost more than the imbalance)
+          if (L.nlin == 3) edge_mlp_mma<3>(R1, RS, pin, PM, pix, fl, wmp, L, P, more ? PA : nullptr, gout, A.pstride, warp, nt_edge >> 5, lane, q);
+          else edge_mlp_mma<2>(R1, RS, pin, PM, pix, fl, wmp, L, P, more ? PA : nullptr, gout, A.pstride, warp, nt_edge >> 5, lane, q);
         } else {
           if (L.nlin == 3) edge_mlp<3>(R1, RS, pin, PM, pix, fl, wmp, L, P, more ? PA : nullptr, gout, A.pstride, tid, nt_edge);
           else edge_mlp<2>(R1, RS, pin, PM, pix, fl, wmp, L, P, more ? PA : nullptr, gout, A.pstride, tid, nt_edge);
