@@ -201,7 +201,10 @@ def run_reference_arm(args, wl, weights):
 
 
 def workload_config(args, wl, B):
-    return {"workload": wl["desc"], "batch": B, "flags": args.flags, "solver_steps_per_sample": 1000,
+    world = max(1, int(os.environ.get("WORLD_SIZE", "1")))
+    return {"workload": wl["desc"], "batch": B, "batch_per_gpu": B // world if args.impl != "reference" else B,
+            "sharding": f"{world} contiguous shards of independent graphs, one 4-float all-reduce per solver phase" if world > 1 else "none",
+            "flags": args.flags, "solver_steps_per_sample": 1000,
             "step": "one reverse-diffusion solver step over the whole batch", "l2": "inputs larger than L2 (per-step working "
             "set = edge-channel stacks >> 126 MB at B=10000)" if B * wl["N"] ** 2 * 46 * 4 > 126e6 else "working set fits L2",
             "weights": "shipped checkpoint (tests/golden/ckpt)", "noise": "in-kernel Philox4x32-10, seed 42"}
@@ -217,7 +220,9 @@ def main():
     ap.add_argument("--batch", type=int, default=0)
     ap.add_argument("--cpu-batch", type=int, default=0)
     ap.add_argument("--flags", default="ragged", choices=["ragged", "full"])
-    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"])
+    ap.add_argument("--scaling", default="weak", choices=["strong", "weak"],
+                    help="weak (default): the BASELINE batch per GPU, independent graphs sharded over the ranks; strong: the "
+                         "BASELINE batch in total")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-profile", action="store_true")
     ap.add_argument("--no-torch-baseline", action="store_true")
@@ -294,15 +299,15 @@ def main():
              scale_eps=wl["scale_eps"], n_steps=1, probability_flow=False, continuous=True, denoise=True, eps=1e-4,
              device=str(dev), shard=shard if world > 1 else None, max_iters=K)
     host_flags = flags.pin_memory()
-    out_x = torch.empty(B, N, F).pin_memory()
-    out_a = torch.empty(B, N, N).pin_memory()
+    out_x = torch.empty(hi - lo, N, F).pin_memory()     # every rank reads back its own shard of the gathered result
+    out_a = torch.empty(hi - lo, N, N).pin_memory()
     torch.manual_seed(42)
     fn(sdx, sda, host_flags)                            # warm (engine cache, allocator)
     barrier()
     t0 = time.perf_counter()
     ex, ea, _ = fn(sdx, sda, host_flags)
-    out_x.copy_(ex, non_blocking=True)
-    out_a.copy_(ea, non_blocking=True)
+    out_x.copy_(ex[lo:hi], non_blocking=True)
+    out_a.copy_(ea[lo:hi], non_blocking=True)
     torch.cuda.synchronize(dev)
     t_e2e = torch.tensor([time.perf_counter() - t0], device=dev)
     if world > 1:
@@ -310,7 +315,8 @@ def main():
     e2e_val = B * K / (1000.0 * float(t_e2e))
     e2e = {"value": e2e_val, "unit": "graphs/s", "h2d_bytes_per_step": host_flags.numel() * 4 / K,
            "d2h_bytes_per_step": (out_x.numel() + out_a.numel()) * 4 / K,
-           "call": f"sampler(model_x, model_adj, host_flags) for {K} solver steps + D2H of (x, adj); bytes are per call / {K}"}
+           "call": f"sampler(model_x, model_adj, host_flags) for {K} solver steps (+ the final NCCL gather at N > 1) + D2H of "
+                   f"the rank's shard of (x, adj); bytes are per rank and call / {K}"}
 
     if rank != 0:
         shard.close()

@@ -1390,7 +1390,10 @@ __global__ void __launch_bounds__(NT, OCC) fused_layers_kernel(const __grid_cons
       }
       const float* wmp = WSM ? wm : L.blk_m;
       // split only when both exist; one node warp per 16-row tile (the mma node MLP works on whole tiles)
-      const int node_warps = (L.need_node && L.need_edge && nwarps >= 4) ? ((A.use_mma && (nwarps < 8 || n <= 16)) ? 1 : 2) : 0;
+      // (16 warps, 33 .. 48 nodes: three row tiles -> three node warps; two would leave one of them with two tiles, the long pole)
+      const int node_warps = (L.need_node && L.need_edge && nwarps >= 4)
+                                 ? ((A.use_mma && (nwarps < 8 || n <= 16)) ? 1 : ((A.use_mma && nwarps >= 16 && n > 32) ? 3 : 2))
+                                 : 0;
       const int nt_edge = nt - 32 * node_warps;
       if (L.need_node && (node_warps == 0 || tid >= nt_edge)) {
         const int ltid = node_warps ? tid - nt_edge : tid, lnt = node_warps ? 32 * node_warps : nt;

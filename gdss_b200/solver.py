@@ -60,7 +60,12 @@ def _make(sde_x, sde_adj, shape_x, shape_adj, predictor, corrector, snr, scale_e
             lo, hi = shard.bounds(flags.shape[0])
             x, adj, xm, am = eng.sample(sdesc, table, flags[lo:hi], n_iters=iters, seed=seed, graph_offset=lo,
                                         global_B=flags.shape[0], comm=shard.comm, use_graph=use_graph)
-            x, adj, xm, am = [shard.gather(t, flags.shape[0]) for t in (x, adj, xm, am)]
+            # the final gather (every rank returns the whole batch, like the single-process reference): only the pair
+            # that is returned travels
+            if denoise:
+                xm, am = [shard.gather(t, flags.shape[0]) for t in (xm, am)]
+            else:
+                x, adj = [shard.gather(t, flags.shape[0]) for t in (x, adj)]
         n_evals = 0 if s4 else steps * (int(n_steps) + 1)            # solver.py:195, :279
         return (xm if denoise else x), (am if denoise else adj), n_evals
 
