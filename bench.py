@@ -223,12 +223,17 @@ def main():
     ap.add_argument("--scaling", default="weak", choices=["strong", "weak"],
                     help="weak (default): the BASELINE batch per GPU, independent graphs sharded over the ranks; strong: the "
                          "BASELINE batch in total")
+    ap.add_argument("--precision", default="fp32", choices=["fp32", "tf32"],
+                    help="fp32 (default, the parity build: 3xTF32 split, <= 1e-4) or tf32 (libgdss_b200_tf32.so: single-pass "
+                         "TF32, <= 3e-2; a reduced-precision line, never the headline)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-profile", action="store_true")
     ap.add_argument("--no-torch-baseline", action="store_true")
     ap.add_argument("--torch-batch", type=int, default=10000)
     ap.add_argument("--burn-in", type=int, default=20, help="untimed solver steps before the warm-up steps")
     args = ap.parse_args()
+    if args.precision == "tf32":
+        os.environ["GDSS_PRECISION"] = "tf32"           # read by gdss_b200._lib at its first use
     wl = WORKLOADS[args.workload]
     weights = load_weights(wl)
     if args.impl == "reference":
@@ -401,7 +406,8 @@ def main():
     path_tflops = value * 1000 * wl["evals"] * wl["flop_eval"] / 1e12
     line = {"metric": "sampled graphs/sec (1000-step reverse SDE)", "value": value, "unit": "graphs/s", "n_gpus": world,
             "steps": K, "warmup": W, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": args.scaling,
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic flags (SURVEY 8d node-count recipe), shipped checkpoint weights",
+            "vs_baseline": None, "dtype": "f32" if args.precision == "fp32" else "tf32 (reduced-precision variant, <= 3e-2 on the raw scores)",
+            "data": "synthetic flags (SURVEY 8d node-count recipe), shipped checkpoint weights",
             "config": workload_config(args, wl, B), "clocks": clk, "e2e": e2e, "gpu_launches": int(launches) * world,
             "roofline": roofline, "roofline_final_mlp": (roofline_final if not args.no_profile else None), "cpu_baseline": cpu, "torch_eager_same_gpu": torch_gpu,
             "path_algorithmic_tflops": path_tflops,

@@ -8,7 +8,11 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libgdss_b200.so")
+# GDSS_PRECISION=tf32 (read once, at the first call) selects the reduced-precision build of the same sources: single-pass
+# TF32 contractions instead of the 3xTF32 split, raw scores within 3e-2 rel-L2 of the reference instead of 1e-4.  Anything
+# else (the default) is the fp32-parity library.
+PRECISION = "tf32" if os.environ.get("GDSS_PRECISION", "").lower() == "tf32" else "fp32"
+LIB_PATH = os.path.join(_HERE, "csrc", "libgdss_b200_tf32.so" if PRECISION == "tf32" else "libgdss_b200.so")
 
 NET_X, NET_X_GMH, NET_A = 0, 1, 2
 SDE_VP, SDE_VE, SDE_SUBVP = 0, 1, 2

@@ -568,6 +568,8 @@ struct Split { uint32_t hi, lo; };
 //           tensor core as it is (the hardware truncates it): 2 instructions per value.  The truncation of lo is one-sided
 //           (|operand| is under-estimated by < 2^-20 relative): measured error of the raw scores against the reference
 //           fixtures 1e-6 .. 4.4e-6 rel-L2 (bar: 1e-4), thresholded 1000-step outputs unchanged (tools/err_probe.py)
+//   mode 3 (the separate library libgdss_b200_tf32.so, GDSS_PRECISION=tf32): single-pass TF32, one MMA per product, no lo
+//           term -- the reduced-precision variant; raw scores within 3e-2 rel-L2 of the reference (tested), not the default
 //   mode 1: lo rounded to nearest (+ half an ulp before the hardware truncation): 3 instructions
 //   mode 0: hi and lo both rounded to nearest: 4 instructions, 0.7e-6 .. 1.6e-6; 4 % slower end to end than mode 2
 // (Inf stays Inf, NaN stays NaN in every mode.)
@@ -582,9 +584,12 @@ DEVINL Split split_tf32(float v) {
 #elif GDSS_SPLIT_MODE == 1
   s.hi = __float_as_uint(v) & 0xffffe000u;                       // truncated hi: v - hi is exact
   s.lo = __float_as_uint(v - __uint_as_float(s.hi)) + 0x1000u;   // lo rounded to nearest by the add + hardware truncation
-#else
+#elif GDSS_SPLIT_MODE == 2
   s.hi = __float_as_uint(v) & 0xffffe000u;
   s.lo = __float_as_uint(v - __uint_as_float(s.hi));             // lo truncated by the tensor core
+#else
+  s.hi = __float_as_uint(v) + 0x1000u;                           // single-pass TF32: round to nearest (add + hardware truncation)
+  s.lo = 0u;
 #endif
   return s;
 }
@@ -605,8 +610,10 @@ DEVINL void acc_init(Acc& a, float b0, float b1) {
 }
 
 DEVINL void mma3(Acc& c, const uint32_t (&ah)[4], const uint32_t (&al)[4], const Split& b0, const Split& b1) {
+#if GDSS_SPLIT_MODE != 3
   mma_tf32(c.m, al, b0.hi, b1.hi);
   mma_tf32(c.m, ah, b0.lo, b1.lo);
+#endif
   mma_tf32(c.m, ah, b0.hi, b1.hi);
 }
 
@@ -997,7 +1004,7 @@ __device__ __noinline__ void channel_chain_mma(int lane, const float* pl, const 
       }
       // term-major issue order: consecutive mma.sync hit different accumulators
 #pragma unroll
-      for (int term = 0; term < 3; ++term)
+      for (int term = GDSS_SPLIT_MODE == 3 ? 2 : 0; term < 3; ++term)
 #pragma unroll
         for (int mb = 0; mb < MB; ++mb)
 #pragma unroll
@@ -1788,7 +1795,7 @@ __global__ void __launch_bounds__(128 * NS, 1) final_edge_tc_kernel(FinalTriArgs
         l[q] = __uint_as_float(sp.lo);
       }
       tmem_st4(tlane + colA1 + half * KH + kk, h[0], h[1], h[2], h[3]);
-      tmem_st4(tlane + colA1 + K1P + half * KH + kk, l[0], l[1], l[2], l[3]);
+      if (GDSS_SPLIT_MODE != 3) tmem_st4(tlane + colA1 + K1P + half * KH + kk, l[0], l[1], l[2], l[3]);
     }
     if (pre < ntiles) fetch(pre);
   };
@@ -1796,7 +1803,7 @@ __global__ void __launch_bounds__(128 * NS, 1) final_edge_tc_kernel(FinalTriArgs
   auto issue_mma1 = [&]() {
     uint32_t acc = 0;
 #pragma unroll
-    for (int ps = 0; ps < 3; ++ps) {
+    for (int ps = 0; ps < (GDSS_SPLIT_MODE == 3 ? 1 : 3); ++ps) {
       const uint32_t acol = tb + colA1 + (ps == 1 ? K1P : 0);
       const uint32_t bbase = smem_u32(ps == 2 ? W1lo : W1hi);
 #pragma unroll
@@ -1866,7 +1873,7 @@ __global__ void __launch_bounds__(128 * NS, 1) final_edge_tc_kernel(FinalTriArgs
             l[q] = __uint_as_float(sp.lo);
           }
           tmem_st8(tlane + colAhi + col, h);
-          tmem_st8(tlane + colAlo + col, l);
+          if (GDSS_SPLIT_MODE != 3) tmem_st8(tlane + colAlo + col, l);
         }
       }
     }
@@ -1875,7 +1882,7 @@ __global__ void __launch_bounds__(128 * NS, 1) final_edge_tc_kernel(FinalTriArgs
     if (tid == 0) {
       uint32_t acc = 0;
 #pragma unroll
-      for (int ps = 0; ps < 3; ++ps) {
+      for (int ps = 0; ps < (GDSS_SPLIT_MODE == 3 ? 1 : 3); ++ps) {
         const uint32_t acol = tb + (ps == 1 ? colAlo : colAhi);
         const uint32_t bbase = smem_u32(ps == 2 ? W2lo : W2hi);
 #pragma unroll

@@ -177,6 +177,7 @@ def main():
     manifest["decode"] = make_decode()
     manifest["c1"] = make_c1_stats()
     manifest["dsm"] = make_dsm()
+    manifest["mol_stats"] = make_mol_stats()
     with open(os.path.join(GOLD, "MANIFEST.json"), "w") as f:
         json.dump(manifest, f, indent=1, sort_keys=True)
 
@@ -213,6 +214,43 @@ def make_c1_stats():
                         train=train_adj, train_counts=np.array([g.number_of_nodes() for g in train], dtype=np.int16))
     e = q.sum(axis=(1, 2)) / 2
     return {"mean_nodes": float(counts.mean()), "edges_mean": float(e.mean()), "edges_std": float(e.std())}
+
+
+def make_mol_stats():
+    """BASELINE configs C2 / C3 at a reduced batch, run with the UNMODIFIED reference on the CPU for the full 1000 steps with
+    torch's own generator (torch.manual_seed(42)) and the SURVEY 8d node-count recipes (RandomState(42)):
+      C2  QM9, S4_solver (snr .2, scale_eps .7, VE / VE), B = 384
+      C3  ZINC250k v2, get_pc_sampler Reverse + Langevin (snr .2, scale_eps .8, VP / VE), B = 24
+    Stored: node counts, quantize_mol(adj) (bond orders 0..3) and x > 0.5 (atom channels) of the samples -- the statistics the
+    GPU test compares (the CUDA sampler draws from Philox, so only distributions can agree)."""
+    import sde as RSDE
+    import solver as RS
+    from utils.graph_utils import quantize_mol
+    out = {}
+    rs = np.random.RandomState(42)
+    specs = [("qm9", "qm9", 9, 4, 384, rs.choice([9, 8, 7, 6, 5], size=384, p=[.83, .14, .025, .004, .001]),
+              (RSDE.VESDE(.1, 1., 1000), RSDE.VESDE(.1, 1., 1000)), ("S4", "None", .2, .7)),
+             ("zinc250k_v2", "zinc_v2", 38, 9, 24,
+              np.clip(np.round(np.random.RandomState(42).normal(23.2, 4.5, 24)), 6, 38).astype(int),
+              (RSDE.VPSDE(.1, 1., 1000), RSDE.VESDE(.2, 1., 1000)), ("Reverse", "Langevin", .2, .8))]
+    for ckpt, tag, N, F, B, counts, (sx, sa), (pred, corr, snr, seps) in specs:
+        flags = (torch.arange(N)[None, :] < torch.from_numpy(np.asarray(counts))[:, None]).float()
+        mx, ma, px, pa = ref_models(ckpt)
+        get = RS.S4_solver if pred == "S4" else RS.get_pc_sampler
+        fn = get(sx, sa, (B, N, F), (B, N, N), predictor=pred, corrector=corr, snr=snr, scale_eps=seps, n_steps=1,
+                 probability_flow=False, continuous=True, denoise=True, eps=1e-4, device="cpu")
+        torch.manual_seed(42)
+        with contextlib.redirect_stdout(io.StringIO()), contextlib.redirect_stderr(io.StringIO()):
+            x, adj, _ = fn(mx, ma, flags)
+        assert torch.isfinite(x).all() and torch.isfinite(adj).all()
+        bonds = quantize_mol(adj.clone()).astype(np.int8)
+        atoms = (x > 0.5).numpy().astype(np.int8)
+        np.savez_compressed(os.path.join(GOLD, f"stats_{tag}_reference.npz"), counts=np.asarray(counts, dtype=np.int16),
+                            bonds=bonds, atoms=atoms)
+        out[tag] = {"B": B, "bond_hist": np.bincount(bonds.reshape(-1), minlength=4).tolist(),
+                    "atom_on": int(atoms.sum())}
+        print("mol stats", tag, out[tag], flush=True)
+    return out
 
 
 DSM_CASES = [("qm9", ("VE", .1, 1.), ("VE", .1, 1.)), ("zinc250k_v2", ("VP", .1, 1.), ("VE", .2, 1.)),
@@ -278,7 +316,7 @@ def make_dsm():
 
 
 def only(which):
-    """python oracle/make_golden.py decode | c1 : just one of the small fixtures."""
+    """python oracle/make_golden.py decode | c1 | dsm | mol : just one of the small fixtures."""
     refimport.activate()
     torch.set_num_threads(os.cpu_count())
     mpath = os.path.join(GOLD, "MANIFEST.json")
@@ -287,6 +325,8 @@ def only(which):
         manifest["decode"] = make_decode()
     elif which == "dsm":
         manifest["dsm"] = make_dsm()
+    elif which == "mol":
+        manifest["mol_stats"] = make_mol_stats()
     else:
         manifest["c1"] = make_c1_stats()
         print(manifest["c1"])
@@ -295,4 +335,4 @@ def only(which):
 
 
 if __name__ == "__main__":
-    only(sys.argv[1]) if sys.argv[1:] in (["decode"], ["c1"], ["dsm"]) else main()
+    only(sys.argv[1]) if sys.argv[1:] in (["decode"], ["c1"], ["dsm"], ["mol"]) else main()

@@ -282,6 +282,52 @@ def test_general_path_tensor_core_final_on_ragged_large_graphs():
     assert float((sa_c * (1 - flags[:, :, None] * flags[:, None, :])).abs().max()) == 0.0
 
 
+TF32_PROBE = r"""
+import json, os, sys, time, torch
+sys.path.insert(0, os.environ["GDSS_ROOT"])
+from oracle import gdss_oracle as O
+from oracle.cases import load_golden_ckpt, load_kat
+from tests.gpu_common import rel
+from gdss_b200 import _lib
+from gdss_b200.engine import Engine
+out = {"precision": _lib.PRECISION, "lib": os.path.basename(_lib.LIB_PATH)}
+for name in ("qm9", "zinc250k_v2", "community_small"):
+    ck, kat = load_golden_ckpt(name), load_kat(name)
+    B, N, F = int(kat["B"]), int(kat["N"]), int(kat["F"])
+    x, adj, flags = O.kat_inputs(N, F, B)
+    eng = Engine(ck["x_state_dict"], ck["adj_state_dict"], N, "cuda")
+    sx, sa = eng.score(x.cuda(), adj.cuda(), flags.cuda())
+    torch.cuda.synchronize()
+    out[name] = [rel(sx, torch.from_numpy(kat["score_x"])), rel(sa, torch.from_numpy(kat["score_adj"])),
+                 float((sa - sa.transpose(-1, -2)).abs().max())]
+print("TF32PROBE " + json.dumps(out))
+"""
+
+
+def test_tf32_variant_library_has_its_stated_tolerance():
+    """GDSS_PRECISION=tf32 loads libgdss_b200_tf32.so (same sources, single-pass TF32 contractions): raw scores within the
+    stated 3e-2 rel-L2 of the reference fixtures -- and measurably NOT within the fp32 bar, i.e. it really is the reduced
+    variant; the default library is untouched.  Runs in a subprocess (the library is chosen once per process)."""
+    import json
+    import subprocess
+    import sys
+    from gdss_b200 import _lib
+    assert _lib.PRECISION == "fp32" and _lib.LIB_PATH.endswith("libgdss_b200.so")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, GDSS_PRECISION="tf32", GDSS_ROOT=root)
+    r = subprocess.run([sys.executable, "-c", TF32_PROBE], env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = [l for l in r.stdout.splitlines() if l.startswith("TF32PROBE ")][-1]
+    out = json.loads(line[len("TF32PROBE "):])
+    assert out["precision"] == "tf32" and out["lib"] == "libgdss_b200_tf32.so"
+    worst = 0.0
+    for name in ("qm9", "zinc250k_v2", "community_small"):
+        ex, ea, asym = out[name]
+        assert ex <= 3e-2 and ea <= 3e-2 and asym == 0.0, (name, out[name])
+        worst = max(worst, ex, ea)
+    assert worst > 1e-5, out                    # a single-pass TF32 result cannot be as close as the 3xTF32 build
+
+
 def test_decode_mol_is_bit_exact():
     """Post-sampling decode (sampler.py:131-138) on the device: golden fixture of the reference lines + random states
     straddling every threshold, bit-exact against the oracle."""
@@ -400,6 +446,58 @@ def test_c1_sample_statistics_match_the_reference_run():
     mmd_ref = S.degree_mmd(ht, S.degree_histograms(ref, counts))
     mmd = S.degree_mmd(ht, S.degree_histograms(q[:300], cnt[:300]))
     assert mmd < mmd_ref + 0.03, (mmd, mmd_ref)
+
+
+@pytest.mark.parametrize("tag", ["qm9", "zinc_v2"])
+def test_molecule_sample_statistics_match_the_reference_run(tag):
+    """SURVEY 8c protocol (iv) for BASELINE configs C2 (QM9, S4) and C3 (ZINC250k v2, Reverse + Langevin): full 1000-step
+    runs of the CUDA sampler (Philox noise) against a full run of the unmodified reference on the CPU at a reduced batch
+    (tests/golden/stats_*_reference.npz, oracle/make_golden.py mol) with the same node counts: per-graph bond count, bond-order
+    sum, multiple-bond count and atom count agree within 4 standard errors of the difference of the means; masks, symmetry and
+    the bond-order histogram over valid pairs are checked on the way."""
+    from gdss_b200.solver import get_pc_sampler, S4_solver
+    from gdss_b200.sde import VPSDE, VESDE
+    from gdss_b200.graph_utils import quantize_mol
+    z = np.load(os.path.join(GOLD, f"stats_{tag}_reference.npz"))
+    counts, bonds_ref, atoms_ref = z["counts"].astype(int), z["bonds"].astype(int), z["atoms"].astype(int)
+    if tag == "qm9":
+        ck, N, F, rep = load_golden_ckpt("qm9"), 9, 4, 8
+        make = lambda B: S4_solver(VESDE(.1, 1., 1000), VESDE(.1, 1., 1000), (B, N, F), (B, N, N), predictor="S4", corrector="None",
+                                   snr=.2, scale_eps=.7, n_steps=1, continuous=True, denoise=True, eps=1e-4, device="cuda")
+    else:
+        ck, N, F, rep = load_golden_ckpt("zinc250k_v2"), 38, 9, 32
+        make = lambda B: get_pc_sampler(VPSDE(.1, 1., 1000), VESDE(.2, 1., 1000), (B, N, F), (B, N, N), predictor="Reverse",
+                                        corrector="Langevin", snr=.2, scale_eps=.8, n_steps=1, continuous=True, denoise=True,
+                                        eps=1e-4, device="cuda")
+    cnt = np.tile(counts, rep)
+    B = len(cnt)
+    flags = (torch.arange(N)[None, :] < torch.from_numpy(cnt)[:, None]).float()
+    torch.manual_seed(42)
+    x, adj, _ = make(B)(ck["x_state_dict"], ck["adj_state_dict"], flags)
+    assert torch.isfinite(x).all() and torch.isfinite(adj).all()
+    bonds = quantize_mol(adj).astype(int)
+    atoms = (x > 0.5).cpu().numpy().astype(int)
+    pair = (flags[:, :, None] * flags[:, None, :]).numpy()
+    assert np.array_equal(bonds, bonds.transpose(0, 2, 1)) and bonds.diagonal(axis1=1, axis2=2).sum() == 0
+    assert (bonds * (1 - pair)).sum() == 0 and (atoms * (1 - flags.numpy()[:, :, None])).sum() == 0
+
+    def per_graph(b, a):
+        return {"bonds": (b > 0).sum(axis=(1, 2)) / 2.0, "order_sum": b.sum(axis=(1, 2)) / 2.0,
+                "multiple": (b > 1).sum(axis=(1, 2)) / 2.0, "atoms": a.sum(axis=(1, 2)).astype(float)}
+
+    ours, ref = per_graph(bonds, atoms), per_graph(bonds_ref, atoms_ref)
+    report = {}
+    for k in ours:
+        se = np.sqrt(ref[k].var() / len(ref[k]) + ours[k].var() / len(ours[k])) + 1e-9
+        report[k] = (round(float(ours[k].mean()), 3), round(float(ref[k].mean()), 3), round(float(se), 3))
+        assert abs(ours[k].mean() - ref[k].mean()) < 4 * se + 0.02 * abs(ref[k].mean()), (tag, k, report[k])
+    # bond-order histogram over the valid pairs: total-variation distance to the reference run's
+    iu = np.triu(np.ones((N, N)), 1)[None] * 1
+    hist = lambda b, c: np.bincount((b * iu)[(np.arange(N)[None, :, None] < c[:, None, None]) & (np.arange(N)[None, None, :] < c[:, None, None]) & (iu > 0)].reshape(-1), minlength=4)
+    h, hr = hist(bonds, cnt).astype(float), hist(bonds_ref, counts).astype(float)
+    tv = 0.5 * np.abs(h / h.sum() - hr / hr.sum()).sum()
+    assert tv < 0.02, (tag, tv, h / h.sum(), hr / hr.sum())
+    print(tag, report, "TV", round(float(tv), 4))
 
 
 @pytest.mark.parametrize("key", [f"{n}_{r}" for n in ("qm9", "zinc250k_v2", "community_small", "ego_small") for r in ("sum", "mean")])

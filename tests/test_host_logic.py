@@ -31,6 +31,18 @@ def test_library_exports_every_symbol_of_the_header():
     assert b"workspace" in L.gdss_error_string(-3)
 
 
+def test_tf32_variant_library_exports_the_same_abi():
+    """libgdss_b200_tf32.so (GDSS_PRECISION=tf32) is the same C ABI built with single-pass TF32 contractions."""
+    import ctypes
+    from gdss_b200 import _lib
+    assert _lib.PRECISION == "fp32"                         # the default library is the fp32-parity build
+    alt = ctypes.CDLL(os.path.join(ROOT, "gdss_b200", "csrc", "libgdss_b200_tf32.so"))
+    hdr = open(os.path.join(ROOT, "include", "gdss_b200.h")).read()
+    for n in sorted(set(re.findall(r"\b(gdss_[a-z0-9_]+)\s*\(", hdr))):
+        assert hasattr(alt, n), n
+    assert alt.gdss_abi_version() == 1
+
+
 def test_struct_sizes_match_the_header():
     from gdss_b200 import _lib
     assert C.sizeof(_lib.NetDesc) == 48
