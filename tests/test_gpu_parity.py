@@ -492,7 +492,7 @@ def test_molecule_sample_statistics_match_the_reference_run(tag):
         report[k] = (round(float(ours[k].mean()), 3), round(float(ref[k].mean()), 3), round(float(se), 3))
         assert abs(ours[k].mean() - ref[k].mean()) < 4 * se + 0.02 * abs(ref[k].mean()), (tag, k, report[k])
     # bond-order histogram over the valid pairs: total-variation distance to the reference run's
-    iu = np.triu(np.ones((N, N)), 1)[None] * 1
+    iu = np.triu(np.ones((N, N), dtype=int), 1)[None]
     hist = lambda b, c: np.bincount((b * iu)[(np.arange(N)[None, :, None] < c[:, None, None]) & (np.arange(N)[None, None, :] < c[:, None, None]) & (iu > 0)].reshape(-1), minlength=4)
     h, hr = hist(bonds, cnt).astype(float), hist(bonds_ref, counts).astype(float)
     tv = 0.5 * np.abs(h / h.sum() - hr / hr.sum()).sum()
