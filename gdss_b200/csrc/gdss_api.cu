@@ -119,6 +119,11 @@ extern "C" int64_t gdss_ctx_query(const gdss_ctx* ctx, const char* key) {
   if (!strcmp(key, "fused")) return ctx->fused ? 1 : 0;
   if (!strcmp(key, "fused_fusable")) return fused_query(ctx, 0);
   if (!strcmp(key, "fused_smem_bytes")) return fused_query(ctx, 1);
+  if (!strncmp(key, "bucket_smem_bytes:", 18)) {          // "bucket_smem_bytes:<NB>:<0|1>" (nodes of the bucket, weights staged)
+    int nb = 0, wsm = 0;
+    if (sscanf(key + 18, "%d:%d", &nb, &wsm) != 2) return GDSS_E_BADARG;
+    return fused_query(ctx, 1000 + 2 * nb + (wsm ? 1 : 0));
+  }
   if (!strcmp(key, "smem_optin")) return ctx->smem_optin;
   if (!strcmp(key, "use_tc")) return ctx->use_tc ? 1 : 0;
   if (!strcmp(key, "use_mma")) return ctx->use_mma ? 1 : 0;
