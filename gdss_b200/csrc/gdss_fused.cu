@@ -2173,7 +2173,11 @@ int64_t fused_query(const gdss_ctx* ctx, int what) {
   if (what == 0) return ok ? 1 : 0;
   if (!ok) return -1;
   FSmem s;
-  return plan_smem(ctx, ctx->N, &s);
+  if (what == 1) return plan_smem(ctx, ctx->N, &s);
+  // what = 1000 + 2 * NB + wsm: the plan of a size bucket of at most NB nodes, with / without staged weights
+  const int nb = (what - 1000) >> 1;
+  if (nb < 2 || nb > ctx->N) return -1;
+  return plan_smem(ctx, nb, &s, (what & 1) != 0);
 }
 
 int launch_tri_setup(const gdss_ctx* ctx, const int* neff, int B, char* ws, const Workspace& w, cudaStream_t st) {

@@ -214,7 +214,8 @@ const char* gdss_prof_name(int32_t kernel_class);
 int64_t gdss_workspace_offset(const gdss_ctx* ctx, int32_t B, const char* region);
 /* which kernel path a context selected: key = "fused" (1: per-graph fused kernel, 0: tiled general path),
  * "fused_fusable" (the networks' shapes are inside the fused kernel's limits), "fused_smem_bytes" (shared memory
- * the per-graph kernel needs for N nodes; -1 if its regions cannot be planned), "smem_optin", "use_tc", "use_mma".
+ * the per-graph kernel needs for N nodes; -1 if its regions cannot be planned), "bucket_smem_bytes:<NB>:<0|1>" (the same for a
+ * size bucket of at most NB nodes, with / without the layer weights staged), "smem_optin", "use_tc", "use_mma".
  * Returns <0 if the key is unknown. */
 int64_t gdss_ctx_query(const gdss_ctx* ctx, const char* key);
 

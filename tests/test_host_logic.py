@@ -199,6 +199,10 @@ def test_ctx_query_reports_the_plan_of_every_checkpoint(name, fusable):
         assert (smem > 0) == bool(fusable)
         if name == "zinc250k_v2":
             assert smem <= 227 * 1024                      # one 512-thread CTA of the largest graphs fits an SM
+            half = (227 * 1024) // 2 - 1024                # two CTAs per SM: n <= 23 with staged weights, n <= 32 without
+            assert q("bucket_smem_bytes:23:1") <= half < q("bucket_smem_bytes:24:1")
+            assert q("bucket_smem_bytes:32:0") <= half < q("bucket_smem_bytes:32:1")
+            assert q("bucket_smem_bytes:99:0") < 0
         if name == "community_small":
             assert smem > 227 * 1024                       # 96 KB of Q|K|V weights per layer: runs the weight-less plan
         assert q("bogus") < 0
