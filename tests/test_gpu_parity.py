@@ -328,6 +328,53 @@ def test_tf32_variant_library_has_its_stated_tolerance():
     assert worst > 1e-5, out                    # a single-pass TF32 result cannot be as close as the 3xTF32 build
 
 
+@pytest.mark.parametrize("name", ["zinc250k_v2", "qm9", "community_small", "enzymes"])
+def test_degenerate_graphs_follow_the_reference(name):
+    """Edge cases of the flags: an empty graph (all flags 0), a single node, a pair, a full graph, and flags with holes
+    (node 0 off, interior nodes off -- the reference masks by flag, not by a node count).  Raw scores against the oracle on
+    the per-graph kernel (N <= 64) and on the general path (ENZYMES), plus three solver steps that must stay finite, masked
+    and symmetric."""
+    from gdss_b200.engine import Engine, make_sampler_desc
+    from gdss_b200.schedule import build_table
+    from gdss_b200.sde import VPSDE, VESDE
+    ck = load_golden_ckpt(name)
+    N, F = int(ck["params_adj"]["max_node_num"]), int(ck["params_adj"]["max_feat_num"])
+    flags = torch.zeros(7, N)
+    flags[1, 0] = 1                                  # single node
+    flags[2, :2] = 1                                 # one pair
+    flags[3, :] = 1                                  # full
+    flags[4, 1:N // 2] = 1                           # node 0 off
+    flags[5, ::2] = 1                                # every other node
+    flags[6, N - 1] = 1                              # only the last node
+    B = flags.shape[0]
+    g = torch.Generator().manual_seed(17)
+    x = torch.randn(B, N, F, generator=g) * flags[:, :, None]
+    a = torch.randn(B, N, N, generator=g).triu(1)
+    adj = (a + a.transpose(-1, -2)) * flags[:, :, None] * flags[:, None, :]
+    with torch.no_grad():
+        ox = O.run_model(ck["x_state_dict"], ck["params_x"], x, adj, flags)
+        oa = O.run_model(ck["adj_state_dict"], ck["params_adj"], x, adj, flags)
+    eng = Engine(ck["x_state_dict"], ck["adj_state_dict"], N, "cuda")
+    fc = flags.cuda()
+    sx, sa = eng.score(x.cuda(), adj.cuda(), fc, inputs_masked=True)
+    torch.cuda.synchronize()
+    assert torch.isfinite(sx).all() and torch.isfinite(sa).all()
+    assert rel(sx, ox) <= TOL and rel(sa, oa) <= TOL, (rel(sx, ox), rel(sa, oa))
+    for b in (0, 1, 6):                              # no pair of valid nodes: the edge score is exactly zero
+        assert float(sa[b].abs().max()) == 0.0
+    assert float(sx[0].abs().max()) == 0.0
+    pair = fc[:, :, None] * fc[:, None, :]
+    assert float((sa * (1 - pair)).abs().max()) == 0.0 and float((sx * (1 - fc[:, :, None])).abs().max()) == 0.0
+    sdx, sda = VPSDE(.1, 1., 1000), VESDE(.2, 1., 1000)
+    table = build_table(sdx, sda, "Reverse", "Langevin", .2, .8, 1e-4)
+    sdesc = make_sampler_desc(sdx, sda, "Reverse", "Langevin", .2, .8, 1e-4, 1, False, True)
+    xs, as_, xm, am = eng.sample(sdesc, table, fc, n_iters=3, seed=5)
+    for t in (xs, as_, xm, am):
+        assert torch.isfinite(t).all()
+    assert torch.equal(as_, as_.transpose(-1, -2)) and float((as_ * (1 - pair)).abs().max()) == 0.0
+    assert float((xs * (1 - fc[:, :, None])).abs().max()) == 0.0 and float(as_[0].abs().max()) == 0.0
+
+
 def test_decode_mol_is_bit_exact():
     """Post-sampling decode (sampler.py:131-138) on the device: golden fixture of the reference lines + random states
     straddling every threshold, bit-exact against the oracle."""
