@@ -493,6 +493,14 @@ def test_c1_sample_statistics_match_the_reference_run():
     mmd_ref = S.degree_mmd(ht, S.degree_histograms(ref, counts))
     mmd = S.degree_mmd(ht, S.degree_histograms(q[:300], cnt[:300]))
     assert mmd < mmd_ref + 0.03, (mmd, mmd_ref)
+    # clustering-coefficient and spectral MMD (evaluation/stats.py:61-148, gaussian_emd kernels) against the training graphs:
+    # the first 100 CUDA samples carry the reference run's own node counts, so the two estimates have the same bias
+    c_ref, s_ref = S.clustering_mmd(train, tc, ref, counts), S.spectral_mmd(train, tc, ref, counts)
+    c_our, s_our = S.clustering_mmd(train, tc, q[:100], cnt[:100]), S.spectral_mmd(train, tc, q[:100], cnt[:100])
+    print("C1 MMD (ours / reference run): degree", round(mmd, 4), round(mmd_ref, 4), "cluster", round(c_our, 4), round(c_ref, 4),
+          "spectral", round(s_our, 4), round(s_ref, 4))
+    assert c_our < c_ref + 0.03, (c_our, c_ref)
+    assert s_our < s_ref + 0.03, (s_our, s_ref)
 
 
 @pytest.mark.parametrize("tag", ["qm9", "zinc_v2"])
