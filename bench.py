@@ -289,11 +289,24 @@ def main():
     ev1.record()
     barrier()
     launches = L.gdss_launch_count() - before
-    ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
+    ms_own = ev0.elapsed_time(ev1)
+    ms = torch.tensor([ms_own], device=dev)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms_total = float(ms)
     clk = clocks.stop()
+    if world > 1:
+        # every rank sampled its own GPU: the slowest clock / highest power / any throttle reason over the ranks, and the spread
+        # of the ranks' own device times (the per-phase all-reduce makes every rank wait for the slowest GPU of the box)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        lo_t = torch.tensor([clk["sm_mhz"] or 1e9, ms_own], device=dev)
+        hi_t = torch.tensor([clk.get("power_w_max") or 0.0, ms_own] + [1.0 if n in clk["reasons"] else 0.0 for n in names], device=dev)
+        dist.all_reduce(lo_t, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi_t, op=dist.ReduceOp.MAX)
+        clk["sm_mhz_min_over_ranks"] = float(lo_t[0])
+        clk["power_w_max_over_ranks"] = float(hi_t[0])
+        clk["reasons_any_rank"] = [n for k, n in enumerate(names) if float(hi_t[2 + k]) > 0]
+        clk["rank_ms_min_max"] = [float(lo_t[1]), float(hi_t[1])]
     ms_per_step = ms_total / K
     value = B / (1000.0 * ms_per_step * 1e-3)
     finite = bool(torch.isfinite(am).all())

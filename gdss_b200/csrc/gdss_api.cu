@@ -458,6 +458,11 @@ extern "C" int gdss_nccl_comm_destroy(void* comm) {
   return g_nccl.destroy(comm) == 0 ? 0 : GDSS_E_NCCL;
 }
 
+extern "C" int gdss_nccl_allreduce(void* comm, float* buf, int64_t count, void* stream) {
+  if (!comm || !buf || count <= 0 || count > 0x7fffffff) return GDSS_E_BADARG;
+  return nccl_allreduce_sum(comm, buf, (int)count, (cudaStream_t)stream);
+}
+
 extern "C" int gdss_nccl_allgather(void* comm, const float* send, float* recv, int64_t count_per_rank, void* stream) {
   if (!comm || !send || !recv || count_per_rank <= 0) return GDSS_E_BADARG;
   if (!load_nccl()) return GDSS_E_NCCL;

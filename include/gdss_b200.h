@@ -177,6 +177,21 @@ int gdss_nccl_unique_id(void* id128);                         /* rank 0: 128-byt
 int gdss_nccl_comm_create(const void* id128, int32_t world, int32_t rank, void** comm_out);
 int gdss_nccl_comm_destroy(void* comm);
 int gdss_nccl_allgather(void* comm, const float* send, float* recv, int64_t count_per_rank, void* stream);
+/* in-place sum over the ranks: the data-parallel trainer's gradient all-reduce (replaces nn.DataParallel's reduction,
+ * trainer.py:57-79 / utils/loader.py:37-48); pass grad_scale = 1 / world to gdss_adam_ema_step for the batch mean */
+int gdss_nccl_allreduce(void* comm, float* buf, int64_t count, void* stream);
+
+/* ---- optimizer half of the training step (trainer.py:66-79) on the flat fp32 arrays of ONE network --------------------
+ * clip_grad_norm_(params, grad_clip) (skipped when grad_clip <= 0) -> torch.optim.Adam step (L2 weight decay folded into
+ * the gradient, bias correction for the 1-based `step`) -> ExponentialMovingAverage.update (utils/ema.py:18-35; skipped
+ * when ema_shadow is NULL; ema_num_updates = updates BEFORE this one, the warm-up decay min(decay, (1+n)/(10+n)) is applied;
+ * pass -1 to use ema_decay as it is).  grads are read as grads * grad_scale.  scratch: gdss_optim_scratch_floats() floats.
+ * grad_norm_out (optional, device): the total gradient norm before clipping.  Two launches, no host synchronisation. */
+int64_t gdss_optim_scratch_floats(void);
+int gdss_adam_ema_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, float* ema_shadow, int64_t n,
+                       float lr, float beta1, float beta2, float eps, float weight_decay, float grad_clip, float grad_scale,
+                       int32_t step, float ema_decay, int64_t ema_num_updates, float* scratch, float* grad_norm_out,
+                       void* stream);
 
 /* ---- tensor helpers -----------------------------------------------------------------
  * Replace utils/graph_utils.py: mask_x :8-12, mask_adjs :16-29 (3-D or 4-D via C channels),

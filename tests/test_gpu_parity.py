@@ -375,6 +375,47 @@ def test_degenerate_graphs_follow_the_reference(name):
     assert float((xs * (1 - fc[:, :, None])).abs().max()) == 0.0 and float(as_[0].abs().max()) == 0.0
 
 
+@pytest.mark.parametrize("clip,wd,ema", [(1.0, 0.0, 0.999), (0.0, 1e-4, None), (1e6, 1e-4, 0.9)])
+def test_fused_clip_adam_ema_matches_torch(clip, wd, ema):
+    """Optimizer half of the training step (trainer.py:66-79): clip_grad_norm_ + torch.optim.Adam + the reference's
+    ExponentialMovingAverage (utils/ema.py:18-35, restated inline below) on the ZINC250k v2 ScoreNetworkA parameters, five
+    steps with random gradients whose norm makes the clip active (clip = 1) / inactive (1e6) / absent (0)."""
+    from gdss_b200.optim import FusedAdamEMA, flatten_state, unflatten_state
+    ck = load_golden_ckpt("zinc250k_v2")
+    flat, metas = flatten_state(ck["adj_state_dict"])
+    assert flat.numel() == 62873                               # SURVEY 8e: ScoreNetworkA of ZINC250k v2
+    params = [torch.nn.Parameter(v.clone().float()) for v in ck["adj_state_dict"].values()]
+    opt = torch.optim.Adam(params, lr=5e-3, weight_decay=wd)
+    shadow = [p.detach().clone() for p in params]
+    num_updates = 0
+    fused = FusedAdamEMA(flat.cuda().contiguous(), lr=5e-3, weight_decay=wd, grad_norm=clip, ema_decay=ema)
+    g = torch.Generator().manual_seed(3)
+    for step in range(5):
+        grads = [torch.randn(p.shape, generator=g) * 0.05 for p in params]
+        for p, gr in zip(params, grads):
+            p.grad = gr.clone()
+        norm_ref = torch.nn.utils.clip_grad_norm_(params, clip) if clip > 0 else None
+        opt.step()
+        if ema is not None:                                    # utils/ema.py:26-35
+            num_updates += 1
+            decay = min(ema, (1 + num_updates) / (10 + num_updates))
+            with torch.no_grad():
+                for sp, p in zip(shadow, params):
+                    sp.sub_((1.0 - decay) * (sp - p))
+        norm = fused.step(torch.cat([gr.reshape(-1) for gr in grads]).cuda())
+        if clip > 0:
+            assert abs(float(norm) - float(norm_ref)) <= 1e-5 * float(norm_ref)
+    torch.cuda.synchronize()
+    ref_flat = torch.cat([p.detach().reshape(-1) for p in params])
+    assert rel(fused.p, ref_flat) <= 1e-6, rel(fused.p, ref_flat)
+    assert float((fused.p.cpu() - ref_flat).abs().max()) <= 2e-6
+    if ema is not None:
+        sh = torch.cat([sp.reshape(-1) for sp in shadow])
+        assert rel(fused.shadow, sh) <= 1e-6
+    back = unflatten_state(fused.p, metas)
+    assert list(back) == list(ck["adj_state_dict"]) and all(back[k].shape == v.shape for k, v in ck["adj_state_dict"].items())
+
+
 def test_decode_mol_is_bit_exact():
     """Post-sampling decode (sampler.py:131-138) on the device: golden fixture of the reference lines + random states
     straddling every threshold, bit-exact against the oracle."""

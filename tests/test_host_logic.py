@@ -231,9 +231,14 @@ def test_compute_calls_fail_loudly_without_cuda():
         m(torch.zeros(1, 9, 4), torch.zeros(1, 9, 9), torch.ones(1, 9))
     with pytest.raises(RuntimeError, match="CUDA"):
         G.mask_x(torch.zeros(1, 9, 4), torch.ones(1, 9))
+    from gdss_b200.optim import FusedAdamEMA
+    with pytest.raises(_lib.GdssError, match="no CPU fallback"):
+        FusedAdamEMA(torch.zeros(8))
     # the C entry points themselves refuse, they do not silently compute on the host
     L = _lib.lib()
     assert L.gdss_quantize(C.c_void_p(8), C.c_void_p(8), 0.5, 4, None) == -2
+    assert L.gdss_adam_ema_step(C.c_void_p(8), C.c_void_p(8), C.c_void_p(8), C.c_void_p(8), None, 4, 1e-3, .9, .999, 1e-8, 0., 1.,
+                                1., 1, .999, 0, C.c_void_p(8), None, None) == -2
 
 
 WORKER = r"""

@@ -33,3 +33,26 @@ dist.all_reduce(t)
 shard.close()
 dist.destroy_process_group()
 sys.exit(int(t.item()) != 0)
+
+# data-parallel gradient exchange of the trainer (gdss_nccl_allreduce through gdss_b200.optim.allreduce_grads) + one fused
+# clip / Adam / EMA step with grad_scale = 1 / world: every rank must end with the same parameters as a single process that
+# saw the mean gradient
+from gdss_b200.optim import FusedAdamEMA, allreduce_grads
+n = 85594                                                     # ZINC250k v2: 22 721 + 62 873 parameters
+gen = torch.Generator().manual_seed(1)
+p0 = torch.randn(n, generator=gen)
+gr = [torch.randn(n, generator=gen) for _ in range(shard.world)]
+mine = gr[shard.rank].to(dev)
+allreduce_grads(shard, mine)
+torch.cuda.synchronize()
+want = torch.stack(gr).sum(0)
+e_sum = float((mine.cpu() - want).abs().max())
+opt = FusedAdamEMA(p0.to(dev).contiguous(), lr=1e-3, grad_norm=1.0, ema_decay=0.999)
+opt.step(mine, grad_scale=1.0 / shard.world)
+ref = torch.nn.Parameter(p0.clone())
+ref.grad = want / shard.world
+torch.nn.utils.clip_grad_norm_([ref], 1.0)
+torch.optim.Adam([ref], lr=1e-3).step()
+e_p = float((opt.p.cpu() - ref.detach()).abs().max())
+ok2 = e_sum <= 1e-5 and e_p <= 2e-6
+print(f"rank {shard.rank}/{shard.world}: gradient all-reduce max err {e_sum:.2e}, parameters after the fused step vs torch {e_p:.2e}  {'OK' if ok2 else 'FAIL'}", flush=True)
