@@ -28,11 +28,6 @@ ex = float((full[0] - part[0]).abs().max()); ea = float((full[1] - part[1]).abs(
 rx = float((full[0] - part[0]).norm() / full[0].norm()); ra = float((full[1] - part[1]).norm() / full[1].norm())
 ok = rx <= 1e-5 and ra <= 1e-5 and bool(torch.isfinite(part[1]).all())
 print(f"rank {shard.rank}/{shard.world}: sharded vs single-GPU  max|dx| {ex:.3e} max|dadj| {ea:.3e}  rel {rx:.2e} {ra:.2e}  {'OK' if ok else 'FAIL'}", flush=True)
-t = torch.tensor([0 if ok else 1], device=dev)
-dist.all_reduce(t)
-shard.close()
-dist.destroy_process_group()
-sys.exit(int(t.item()) != 0)
 
 # data-parallel gradient exchange of the trainer (gdss_nccl_allreduce through gdss_b200.optim.allreduce_grads) + one fused
 # clip / Adam / EMA step with grad_scale = 1 / world: every rank must end with the same parameters as a single process that
@@ -56,3 +51,8 @@ torch.optim.Adam([ref], lr=1e-3).step()
 e_p = float((opt.p.cpu() - ref.detach()).abs().max())
 ok2 = e_sum <= 1e-5 and e_p <= 2e-6
 print(f"rank {shard.rank}/{shard.world}: gradient all-reduce max err {e_sum:.2e}, parameters after the fused step vs torch {e_p:.2e}  {'OK' if ok2 else 'FAIL'}", flush=True)
+t = torch.tensor([0 if (ok and ok2) else 1], device=dev)
+dist.all_reduce(t)
+shard.close()
+dist.destroy_process_group()
+sys.exit(int(t.item()) != 0)
