@@ -625,10 +625,9 @@ DEVINL float acc_get(const Acc& c, int q) { return c.m[q]; }
 // pout may alias pin: a warp reads all inputs of its 16 pixels before it writes them (mma.sync is warp-synchronous).
 template <int NLIN>
 DEVINL void edge_mlp_mma(const float* M, int MS, const float* pin, int PM, const unsigned* pix, const float* fl, const float* wm,
-                         const FLayer& L, int P, float* pout, float* gout, int64_t gstride, int warp, int nwarps, int lane,
-                         int* queue) {
-  // queue != nullptr: the 16-pixel tiles are handed out through a shared counter (zeroed before the CTA barrier that
-  // precedes this call), so that warps arriving late (the node-MLP warps) and early finishers even out
+                         const FLayer& L, int P, float* pout, float* gout, int64_t gstride, int warp, int nwarps, int lane) {
+  // (handing the tiles out through a shared counter, so that the node-MLP warps could join once their rows are done, was
+  // measured 3 % slower: per-warp weight-fragment set-up and an atomic + shuffle per tile cost more than the imbalance)
   const int g = lane >> 2, t = lane & 3;
   const int C = L.c_in, c_out = L.c_out, K1 = 2 * C;
   const float* W1 = wm + L.ew_o[0];                 // [2C][16]
@@ -666,13 +665,7 @@ DEVINL void edge_mlp_mma(const float* M, int MS, const float* pin, int PM, const
   bia3[1] = 2 * t + 1 < c_out ? b3[2 * t + 1] : 0.f;
   const int ks1 = (K1 + 7) >> 3;                     // k-steps of layer 1 (1 or 2)
   const int ntile = (P + 15) >> 4;
-  for (int tile = warp;; tile += nwarps) {
-    if (queue) {
-      int tq = 0;
-      if (lane == 0) tq = atomicAdd(queue, 1);
-      tile = __shfl_sync(0xffffffffu, tq, 0);
-    }
-    if (tile >= ntile) break;
+  for (int tile = warp; tile < ntile; tile += nwarps) {
     const int pa = tile * 16 + g, pb = pa + 8;
     const int pac = pa < P ? pa : P - 1, pbc = pb < P ? pb : P - 1;
     // ---- layer 1: A fragments gathered from the channel planes
@@ -1419,10 +1412,8 @@ __global__ void __launch_bounds__(NT, OCC) fused_layers_kernel(const __grid_cons
         if (!node_warps && L.need_node) __syncthreads();       // (never both: kept for symmetry of the barrier count)
         float* gout = isA ? A.stackT + (int64_t)cbase * A.pstride + gp0 : nullptr;
         if (A.use_mma) {
-          int* q = nullptr;      // (a shared tile queue that lets the node warps join was measured 3 % slower: per-warp weight
-                                 // fragment set-up and the atomic + shuffle per tile cost more than the imbalance)
-          if (L.nlin == 3) edge_mlp_mma<3>(R1, RS, pin, PM, pix, fl, wmp, L, P, more ? PA : nullptr, gout, A.pstride, warp, nt_edge >> 5, lane, q);
-          else edge_mlp_mma<2>(R1, RS, pin, PM, pix, fl, wmp, L, P, more ? PA : nullptr, gout, A.pstride, warp, nt_edge >> 5, lane, q);
+          if (L.nlin == 3) edge_mlp_mma<3>(R1, RS, pin, PM, pix, fl, wmp, L, P, more ? PA : nullptr, gout, A.pstride, warp, nt_edge >> 5, lane);
+          else edge_mlp_mma<2>(R1, RS, pin, PM, pix, fl, wmp, L, P, more ? PA : nullptr, gout, A.pstride, warp, nt_edge >> 5, lane);
         } else {
           if (L.nlin == 3) edge_mlp<3>(R1, RS, pin, PM, pix, fl, wmp, L, P, more ? PA : nullptr, gout, A.pstride, tid, nt_edge);
           else edge_mlp<2>(R1, RS, pin, PM, pix, fl, wmp, L, P, more ? PA : nullptr, gout, A.pstride, tid, nt_edge);
