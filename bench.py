@@ -82,15 +82,16 @@ def load_weights(wl):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region by ONE process (rank 0) for all
+    the GPUs of the job: a poller per rank (8 concurrent nvidia-smi loops on an 8-GPU box) perturbs the run it watches."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index):
-        self.rows, self.proc = [], None
+    def __init__(self, primary, n_gpus=1):
+        self.rows, self.proc, self.primary, self.n_gpus = [], None, int(primary), int(n_gpus)
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "200"],
+            sel = [f"--id={primary}"] if n_gpus == 1 else []
+            self.proc = subprocess.Popen(["nvidia-smi", *sel, f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
@@ -110,13 +111,28 @@ class ClockSampler:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
-        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
-        pw = [float(r[2]) for r in self.rows if len(r) >= 7 and r[2].replace(".", "").isdigit()]
+        num = lambda v: v.replace(".", "").isdigit()
+        rows = [r for r in self.rows if len(r) >= 8 and r[0].isdigit() and num(r[1])]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for k, n in enumerate(names) if any(len(r) >= 7 and r[3 + k].lower().startswith("active") for r in self.rows)]
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": reasons}
+
+        def summary(sel):
+            sm = [float(r[1]) for r in sel]
+            mx = [float(r[2]) for r in sel if num(r[2])]
+            pw = [float(r[3]) for r in sel if num(r[3])]
+            reasons = [n for k, n in enumerate(names) if any(r[4 + k].lower().startswith("active") for r in sel)]
+            return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                    "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": reasons}
+
+        mine = [r for r in rows if int(r[0]) == self.primary] or rows
+        out = summary(mine)
+        if self.n_gpus > 1:
+            per = [summary([r for r in rows if int(r[0]) == g]) for g in sorted({int(r[0]) for r in rows})][: self.n_gpus]
+            meds = [p["sm_mhz"] for p in per if p["sm_mhz"] is not None]
+            out["sm_mhz_min_over_gpus"] = min(meds) if meds else None
+            out["power_w_max_over_gpus"] = max([p["power_w_max"] or 0.0 for p in per]) if per else None
+            out["reasons_any_gpu"] = sorted({n for p in per for n in p["reasons"]})
+            out["gpus_sampled"] = len(per)
+        return out
 
 
 def measured_peaks():
@@ -281,7 +297,7 @@ def main():
     # ---- warm-up: W untimed steps from the prior
     x, adj, xm, am = eng.sample(sdesc, table, fl_local, n_iters=max(W, 1), **kw)
     barrier()
-    clocks = ClockSampler(dev.index if dev.index is not None else 0)
+    clocks = ClockSampler(dev.index if dev.index is not None else 0, world) if rank == 0 else None
     before = L.gdss_launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
@@ -294,19 +310,12 @@ def main():
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms_total = float(ms)
-    clk = clocks.stop()
+    clk = clocks.stop() if clocks is not None else {}
     if world > 1:
-        # every rank sampled its own GPU: the slowest clock / highest power / any throttle reason over the ranks, and the spread
-        # of the ranks' own device times (the per-phase all-reduce makes every rank wait for the slowest GPU of the box)
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        lo_t = torch.tensor([clk["sm_mhz"] or 1e9, ms_own], device=dev)
-        hi_t = torch.tensor([clk.get("power_w_max") or 0.0, ms_own] + [1.0 if n in clk["reasons"] else 0.0 for n in names], device=dev)
+        # spread of the ranks' own device times (the per-phase all-reduce makes every rank wait for the slowest GPU of the box)
+        lo_t = torch.tensor([ms_own], device=dev)
         dist.all_reduce(lo_t, op=dist.ReduceOp.MIN)
-        dist.all_reduce(hi_t, op=dist.ReduceOp.MAX)
-        clk["sm_mhz_min_over_ranks"] = float(lo_t[0])
-        clk["power_w_max_over_ranks"] = float(hi_t[0])
-        clk["reasons_any_rank"] = [n for k, n in enumerate(names) if float(hi_t[2 + k]) > 0]
-        clk["rank_ms_min_max"] = [float(lo_t[1]), float(hi_t[1])]
+        clk["rank_ms_min_max"] = [float(lo_t[0]), ms_total]
     ms_per_step = ms_total / K
     value = B / (1000.0 * ms_per_step * 1e-3)
     finite = bool(torch.isfinite(am).all())
