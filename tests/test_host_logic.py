@@ -267,3 +267,53 @@ def test_two_rank_gloo_sharding_and_id_exchange(tmp_path):
                          env=env, capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
     assert (tmp_path / "rank0.txt").read_text() == "ok 0 6" and (tmp_path / "rank1.txt").read_text() == "ok 6 11"
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """bench.py --impl reference (the CPU oracle port timed on the host cores) prints one JSON line with the keys the driver
+    reads; bounded sample (1 timed step of 1000 on 32 graphs)."""
+    import json
+    import subprocess
+    import sys
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"],
+                       capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
+    assert line["impl"] == "reference" and line["unit"] == "graphs/s" and line["higher_is_better"] is True
+    assert line["value"] > 0 and line["metric"].startswith("sampled graphs/sec")
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1 and line["cpu_baseline"]["value"] == line["value"]
+    assert line["e2e"] == {"value": line["value"], "unit": "graphs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "ZINC250k v2" in line["config"]["workload"] and line["dtype"] == "f32"
+
+
+def test_clock_sampler_parses_single_and_multi_gpu_rows():
+    """bench.ClockSampler.stop(): medians per GPU, the slowest clock / highest power / any throttle reason over the GPUs of
+    the job (one poller on rank 0 for all of them), from canned nvidia-smi rows."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+
+    class FakeProc:
+        def terminate(self):
+            pass
+
+        def wait(self, timeout=None):
+            return 0
+
+    def make(primary, n, rows):
+        cs = bench.ClockSampler.__new__(bench.ClockSampler)
+        cs.rows, cs.proc, cs.primary, cs.n_gpus = [[c.strip() for c in r.split(",")] for r in rows], FakeProc(), primary, n
+        return cs.stop()
+
+    na = "Not Active"
+    one = make(0, 1, [f"0, 1965, 1965, 350.5, {na}, {na}, {na}, {na}", f"0, 1950, 1965, 371.0, {na}, {na}, {na}, Active", "garbage"])
+    assert one["sm_mhz"] == 1957.5 and one["sm_max_mhz"] == 1965.0 and one["power_w_max"] == 371.0 and one["samples"] == 2
+    assert one["reasons"] == ["sw_power_cap"] and "sm_mhz_min_over_gpus" not in one
+    rows = []
+    for g, (mhz, pw, therm) in enumerate([(1965, 400.0, na), (1800, 410.5, "Active"), (1965, 390.0, na)]):
+        rows += [f"{g}, {mhz}, 1965, {pw}, {na}, {na}, {therm}, {na}"] * 2
+    many = make(0, 3, rows)
+    assert many["sm_mhz"] == 1965.0 and many["reasons"] == [] and many["gpus_sampled"] == 3
+    assert many["sm_mhz_min_over_gpus"] == 1800.0 and many["power_w_max_over_gpus"] == 410.5
+    assert many["reasons_any_gpu"] == ["sw_thermal_slowdown"]
