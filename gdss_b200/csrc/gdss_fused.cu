@@ -2239,7 +2239,8 @@ int launch_eval_fused(const gdss_ctx* ctx, const float* x, const float* adj, con
     fa.mb1 = nb[k] <= 16 ? 1 : 0;
     // Preferred: layer weights staged in shared memory by TMA with two CTAs of 256 threads per SM; if only the
     // weight-less plan fits twice, read the weights through L2 instead; the largest graphs run one CTA of 512.
-    // (three CTAs of 85 registers per SM with the weights read through L2 measured 5 % slower than two with staged weights)
+    // (three CTAs of 85 registers per SM with the weights read through L2 measured 5 % slower than two with staged weights;
+    //  re-measured on the final build for the n <= 23 bucket: 80 registers, 388 B of spills, 6 % slower)
     const int limit2 = (227 * 1024) / 2 - 1024;
     int64_t smem = plan_smem(ctx, nb[k], &fa.sl, true);
     cudaError_t e;
