@@ -178,6 +178,7 @@ def main():
     manifest["c1"] = make_c1_stats()
     manifest["dsm"] = make_dsm()
     manifest["mol_stats"] = make_mol_stats()
+    manifest["dsm_grad"] = make_dsm_grads()
     with open(os.path.join(GOLD, "MANIFEST.json"), "w") as f:
         json.dump(manifest, f, indent=1, sort_keys=True)
 
@@ -315,8 +316,54 @@ def make_dsm():
     return out
 
 
+def make_dsm_grads():
+    """Gradients of the two DSM losses (losses.py:37-81, train = True, reduce_mean = False) with respect to every parameter
+    of both score networks, from the UNMODIFIED reference's autograd, for the inputs / recorded draws of the existing
+    dsm_*_sum.npz fixtures (same seeds).  Stored flat in parameters() order: the parity target of the backward kernels
+    (trainer.py:57-65: loss_x.backward(); loss_adj.backward())."""
+    import losses as RL
+    import sde as RSDE
+    out = {}
+    cls = {"VP": RSDE.VPSDE, "VE": RSDE.VESDE, "subVP": RSDE.subVPSDE}
+    for k, (name, sx_, sa_) in enumerate(DSM_CASES):
+        mx, ma, px, pa = ref_models(name)
+        z = np.load(os.path.join(GOLD, f"dsm_{name}_sum.npz"))
+        x, adj = torch.from_numpy(z["x"]), torch.from_numpy(z["adj"])
+        sx, sa = cls[sx_[0]](sx_[1], sx_[2], 1000), cls[sa_[0]](sa_[1], sa_[2], 1000)
+        fn = RL.get_sde_loss_fn(sx, sa, train=True, reduce_mean=False, continuous=True, likelihood_weighting=False, eps=1e-5)
+        tape = [torch.from_numpy(z["t"]), torch.from_numpy(z["raw_x"]), torch.from_numpy(z["raw_adj"])]
+        it = iter(tape)
+        orig_rand, orig_like = torch.rand, torch.randn_like
+        torch.rand, torch.randn_like = (lambda *a, **kw: next(it)), (lambda tt, **kw: next(it))
+        try:
+            for m in (mx, ma):
+                for p_ in m.parameters():
+                    p_.requires_grad_(True)
+                m.zero_grad()
+            lx, la = fn(mx, ma, x, adj)
+            lx.backward()
+            la.backward()
+        finally:
+            torch.rand, torch.randn_like = orig_rand, orig_like
+        assert abs(float(lx) - float(z["loss_x"])) <= 1e-5 * abs(float(z["loss_x"])) + 1e-6
+        # parameters the loss never reaches keep grad = None in torch (the last AttentionLayer's multi_channel MLP of
+        # ScoreNetworkA: its x output is dropped, ScoreNetwork_A.py:139-141) and torch.optim.Adam skips them: stored as
+        # zeros with a per-element mask
+        def flat(m):
+            g = [(p_.grad if p_.grad is not None else torch.zeros_like(p_)).reshape(-1) for p_ in m.parameters()]
+            has = [torch.full((p_.numel(),), 0 if p_.grad is None else 1, dtype=torch.uint8) for p_ in m.parameters()]
+            return torch.cat(g).numpy(), torch.cat(has).numpy()
+        (gx, hx), (ga, ha) = flat(mx), flat(ma)
+        np.savez_compressed(os.path.join(GOLD, f"dsm_grad_{name}_sum.npz"), grad_x=gx, grad_adj=ga, has_grad_x=hx, has_grad_adj=ha,
+                            loss_x=float(lx), loss_adj=float(la))
+        out[name] = [int(gx.size), int(ga.size), float(np.linalg.norm(gx)), float(np.linalg.norm(ga))]
+        print("dsm grad", name, out[name], flush=True)
+        mx.eval(); ma.eval()
+    return out
+
+
 def only(which):
-    """python oracle/make_golden.py decode | c1 | dsm | mol : just one of the small fixtures."""
+    """python oracle/make_golden.py decode | c1 | dsm | mol | dsmgrad : just one of the small fixtures."""
     refimport.activate()
     torch.set_num_threads(os.cpu_count())
     mpath = os.path.join(GOLD, "MANIFEST.json")
@@ -327,6 +374,8 @@ def only(which):
         manifest["dsm"] = make_dsm()
     elif which == "mol":
         manifest["mol_stats"] = make_mol_stats()
+    elif which == "dsmgrad":
+        manifest["dsm_grad"] = make_dsm_grads()
     else:
         manifest["c1"] = make_c1_stats()
         print(manifest["c1"])
@@ -335,4 +384,4 @@ def only(which):
 
 
 if __name__ == "__main__":
-    only(sys.argv[1]) if sys.argv[1:] in (["decode"], ["c1"], ["dsm"], ["mol"]) else main()
+    only(sys.argv[1]) if sys.argv[1:] in (["decode"], ["c1"], ["dsm"], ["mol"], ["dsmgrad"]) else main()
