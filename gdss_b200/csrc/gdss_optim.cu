@@ -42,6 +42,7 @@ struct AdamArgs {
   float* p; const float* g; float* m; float* v; float* shadow;
   int64_t n;
   float lr, beta1, beta2, eps, weight_decay, grad_clip, grad_scale, bc1, bc2_sqrt, ema_one_minus_decay;
+  const unsigned char* active; // optional per-parameter mask: 0 = the loss never reaches it (grad None in torch: Adam skips it)
   const float* partial;        // OPT_BLOCKS partial squared norms (grad_clip > 0)
   float* norm_out;             // optional: the total gradient norm (what clip_grad_norm_ returns)
 };
@@ -65,6 +66,13 @@ __global__ void __launch_bounds__(256) adam_ema_kernel(AdamArgs a) {
   const float step_size = a.lr / a.bc1;
   for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < a.n; i += (int64_t)gridDim.x * 256) {
     float p = a.p[i];
+    if (a.active && !a.active[i]) {                                // torch.optim.Adam skips parameters without a gradient:
+      if (a.shadow) {                                              // no weight decay, no moment update; the EMA still runs
+        const float s = a.shadow[i];
+        a.shadow[i] = s - a.ema_one_minus_decay * (s - p);
+      }
+      continue;
+    }
     float g = a.g[i] * coef;
     if (a.weight_decay != 0.f) g = fmaf(a.weight_decay, p, g);      // Adam (not AdamW): grad += weight_decay * param
     const float m = a.beta1 * a.m[i] + (1.f - a.beta1) * g;        // exp_avg.lerp_(grad, 1 - beta1)
@@ -89,8 +97,8 @@ extern "C" int64_t gdss_optim_scratch_floats(void) { return OPT_BLOCKS + 4; }
 
 extern "C" int gdss_adam_ema_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, float* ema_shadow,
                                   int64_t n, float lr, float beta1, float beta2, float eps, float weight_decay, float grad_clip,
-                                  float grad_scale, int32_t step, float ema_decay, int64_t ema_num_updates, float* scratch,
-                                  float* grad_norm_out, void* stream) {
+                                  float grad_scale, int32_t step, float ema_decay, int64_t ema_num_updates,
+                                  const unsigned char* active, float* scratch, float* grad_norm_out, void* stream) {
   if (!params || !grads || !exp_avg || !exp_avg_sq || n <= 0 || step < 1 || !scratch) return GDSS_E_BADARG;
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return GDSS_E_UNSUPPORTED;   // no CPU fallback
@@ -115,6 +123,7 @@ extern "C" int gdss_adam_ema_step(float* params, const float* grads, float* exp_
     if (warm < decay) decay = warm;
   }
   a.ema_one_minus_decay = (float)(1.0 - decay);
+  a.active = active;
   a.partial = scratch;
   a.norm_out = grad_norm_out;
   int blocks = (int)((n + 255) / 256);

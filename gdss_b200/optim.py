@@ -39,9 +39,11 @@ class FusedAdamEMA:
     """Adam moments + EMA shadow of one network's flat parameter vector on a CUDA device.
 
     lr / weight_decay / betas / eps: torch.optim.Adam's; grad_norm: the trainer's clip (config train.grad_norm, <= 0: none);
-    ema_decay: config train.ema (None: no EMA)."""
+    ema_decay: config train.ema (None: no EMA); active: optional uint8 vector, 0 for parameters the loss never reaches
+    (grad None in torch, skipped by torch.optim.Adam: no weight decay, no moment update)."""
 
-    def __init__(self, flat_params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, grad_norm=0.0, ema_decay=None):
+    def __init__(self, flat_params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, grad_norm=0.0, ema_decay=None,
+                 active=None):
         require_cuda()
         if flat_params.device.type != "cuda" or flat_params.dtype != torch.float32 or not flat_params.is_contiguous():
             raise ValueError("flat_params must be a contiguous fp32 CUDA tensor")
@@ -53,6 +55,11 @@ class FusedAdamEMA:
         self.lr, self.betas, self.eps, self.wd = float(lr), (float(betas[0]), float(betas[1])), float(eps), float(weight_decay)
         self.grad_norm, self.ema_decay = float(grad_norm or 0.0), ema_decay
         self.step_count, self.num_updates = 0, 0
+        self.active = None
+        if active is not None:
+            self.active = active.to(flat_params.device, torch.uint8).contiguous()
+            if self.active.numel() != flat_params.numel():
+                raise ValueError("active mask does not match the parameters")
         self.scratch = torch.zeros(int(self.L.gdss_optim_scratch_floats()), device=flat_params.device)
         self.norm = torch.zeros(1, device=flat_params.device)
 
@@ -68,6 +75,7 @@ class FusedAdamEMA:
                                             self.p.numel(), self.lr, self.betas[0], self.betas[1], self.eps, self.wd,
                                             self.grad_norm, float(grad_scale), self.step_count,
                                             float(self.ema_decay if self.ema_decay is not None else 0.0), self.num_updates,
+                                            self.active.data_ptr() if self.active is not None else None,
                                             self.scratch.data_ptr(), self.norm.data_ptr(), st), "gdss_adam_ema_step")
         if self.shadow is not None:
             self.num_updates += 1

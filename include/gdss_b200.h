@@ -186,12 +186,15 @@ int gdss_nccl_allreduce(void* comm, float* buf, int64_t count, void* stream);
  * the gradient, bias correction for the 1-based `step`) -> ExponentialMovingAverage.update (utils/ema.py:18-35; skipped
  * when ema_shadow is NULL; ema_num_updates = updates BEFORE this one, the warm-up decay min(decay, (1+n)/(10+n)) is applied;
  * pass -1 to use ema_decay as it is).  grads are read as grads * grad_scale.  scratch: gdss_optim_scratch_floats() floats.
- * grad_norm_out (optional, device): the total gradient norm before clipping.  Two launches, no host synchronisation. */
+ * grad_norm_out (optional, device): the total gradient norm before clipping.  active_or_null (device, one byte per
+ * parameter): 0 marks parameters the loss never reaches (grad None in torch, e.g. the last AttentionLayer's node MLP of
+ * ScoreNetworkA) -- torch.optim.Adam skips them (no weight decay, no moment update), and so does this step; their gradient
+ * entries must be 0 (they do not enter the norm).  Two launches, no host synchronisation. */
 int64_t gdss_optim_scratch_floats(void);
 int gdss_adam_ema_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, float* ema_shadow, int64_t n,
                        float lr, float beta1, float beta2, float eps, float weight_decay, float grad_clip, float grad_scale,
-                       int32_t step, float ema_decay, int64_t ema_num_updates, float* scratch, float* grad_norm_out,
-                       void* stream);
+                       int32_t step, float ema_decay, int64_t ema_num_updates, const unsigned char* active_or_null,
+                       float* scratch, float* grad_norm_out, void* stream);
 
 /* ---- tensor helpers -----------------------------------------------------------------
  * Replace utils/graph_utils.py: mask_x :8-12, mask_adjs :16-29 (3-D or 4-D via C channels),

@@ -416,6 +416,37 @@ def test_fused_clip_adam_ema_matches_torch(clip, wd, ema):
     assert list(back) == list(ck["adj_state_dict"]) and all(back[k].shape == v.shape for k, v in ck["adj_state_dict"].items())
 
 
+def test_fused_optimizer_skips_parameters_without_a_gradient():
+    """torch.optim.Adam skips parameters whose grad is None (the last AttentionLayer's node MLP of ScoreNetworkA is never
+    reached by the loss: `has_grad_adj` of the reference-autograd fixture) -- with weight decay that matters: they must keep
+    their values, the others must follow torch."""
+    from gdss_b200.optim import FusedAdamEMA, flatten_state
+    ck = load_golden_ckpt("zinc250k_v2")
+    g = np.load(os.path.join(GOLD, "dsm_grad_zinc250k_v2_sum.npz"))
+    flat, _ = flatten_state(ck["adj_state_dict"])
+    has = torch.from_numpy(g["has_grad_adj"])
+    grad = torch.from_numpy(g["grad_adj"])
+    assert has.numel() == flat.numel() and int((has == 0).sum()) > 0 and float(grad[has == 0].abs().max()) == 0.0
+    params = [torch.nn.Parameter(v.clone().float()) for v in ck["adj_state_dict"].values()]
+    opt = torch.optim.Adam(params, lr=5e-3, weight_decay=1e-4)
+    fused = FusedAdamEMA(flat.cuda().contiguous(), lr=5e-3, weight_decay=1e-4, grad_norm=1.0, ema_decay=0.999, active=has)
+    for step in range(3):
+        o = 0
+        for p in params:
+            n = p.numel()
+            p.grad = grad[o:o + n].view_as(p).clone() if int(has[o]) else None
+            o += n
+        torch.nn.utils.clip_grad_norm_(params, 1.0)
+        opt.step()
+        fused.step(grad.cuda())
+    torch.cuda.synchronize()
+    ref_flat = torch.cat([p.detach().reshape(-1) for p in params])
+    out = fused.p.cpu()
+    assert torch.equal(out[has == 0], flat[has == 0])                     # untouched, bit for bit
+    assert rel(out, ref_flat) <= 1e-6 and float((out - ref_flat).abs().max()) <= 2e-6
+    assert torch.equal(fused.shadow.cpu()[has == 0], flat[has == 0])     # EMA of an unchanged parameter stays put
+
+
 def test_decode_mol_is_bit_exact():
     """Post-sampling decode (sampler.py:131-138) on the device: golden fixture of the reference lines + random states
     straddling every threshold, bit-exact against the oracle."""

@@ -238,7 +238,7 @@ def test_compute_calls_fail_loudly_without_cuda():
     L = _lib.lib()
     assert L.gdss_quantize(C.c_void_p(8), C.c_void_p(8), 0.5, 4, None) == -2
     assert L.gdss_adam_ema_step(C.c_void_p(8), C.c_void_p(8), C.c_void_p(8), C.c_void_p(8), None, 4, 1e-3, .9, .999, 1e-8, 0., 1.,
-                                1., 1, .999, 0, C.c_void_p(8), None, None) == -2
+                                1., 1, .999, 0, None, C.c_void_p(8), None, None) == -2
 
 
 WORKER = r"""
