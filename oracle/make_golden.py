@@ -179,6 +179,7 @@ def main():
     manifest["dsm"] = make_dsm()
     manifest["mol_stats"] = make_mol_stats()
     manifest["dsm_grad"] = make_dsm_grads()
+    manifest["train_steps"] = make_train_steps()
     with open(os.path.join(GOLD, "MANIFEST.json"), "w") as f:
         json.dump(manifest, f, indent=1, sort_keys=True)
 
@@ -362,8 +363,56 @@ def make_dsm_grads():
     return out
 
 
+def make_train_steps():
+    """Two consecutive iterations of the UNMODIFIED reference's training loop body (trainer.py:57-79) on ZINC250k v2 with the
+    shipped config's optimizer settings (config/zinc250k.yaml:35-47: Adam lr 0.005, weight_decay 1e-4, grad_norm 1.0, ema
+    0.999; optimizers as utils/loader.py:51-64 builds them, EMA = utils/ema.py), starting from the checkpoint, on the batch /
+    recorded draws of dsm_zinc250k_v2_sum.npz (the same draws in both iterations).  Stored: losses, pre-clip gradient norms,
+    flat parameters and EMA shadows of both networks after each iteration."""
+    import losses as RL
+    import sde as RSDE
+    from utils.ema import ExponentialMovingAverage
+    name = "zinc250k_v2"
+    mx, ma, px, pa = ref_models(name)
+    z = np.load(os.path.join(GOLD, f"dsm_{name}_sum.npz"))
+    x, adj = torch.from_numpy(z["x"]), torch.from_numpy(z["adj"])
+    sx, sa = RSDE.VPSDE(.1, 1., 1000), RSDE.VESDE(.2, 1., 1000)
+    fn = RL.get_sde_loss_fn(sx, sa, train=True, reduce_mean=False, continuous=True, likelihood_weighting=False, eps=1e-5)
+    for m in (mx, ma):
+        for p_ in m.parameters():
+            p_.requires_grad_(True)
+    ox = torch.optim.Adam(mx.parameters(), lr=0.005, weight_decay=0.0001)
+    oa = torch.optim.Adam(ma.parameters(), lr=0.005, weight_decay=0.0001)
+    ex, ea = ExponentialMovingAverage(mx.parameters(), decay=0.999), ExponentialMovingAverage(ma.parameters(), decay=0.999)
+    rec = {}
+    orig_rand, orig_like = torch.rand, torch.randn_like
+    try:
+        for it_ in range(2):
+            tape = iter([torch.from_numpy(z["t"]), torch.from_numpy(z["raw_x"]), torch.from_numpy(z["raw_adj"])])
+            torch.rand, torch.randn_like = (lambda *a, **kw: next(tape)), (lambda tt, **kw: next(tape))
+            mx.train(); ma.train()
+            ox.zero_grad(); oa.zero_grad()
+            lx, la = fn(mx, ma, x, adj)
+            lx.backward(); la.backward()
+            nx_ = torch.nn.utils.clip_grad_norm_(mx.parameters(), 1.0)
+            na_ = torch.nn.utils.clip_grad_norm_(ma.parameters(), 1.0)
+            ox.step(); oa.step()
+            ex.update(mx.parameters()); ea.update(ma.parameters())
+            flat = lambda ps: torch.cat([p_.detach().reshape(-1) for p_ in ps]).numpy().copy()
+            rec[f"loss_{it_}"] = np.array([float(lx), float(la)])
+            rec[f"gnorm_{it_}"] = np.array([float(nx_), float(na_)])
+            rec[f"px_{it_}"], rec[f"pa_{it_}"] = flat(mx.parameters()), flat(ma.parameters())
+            rec[f"ex_{it_}"], rec[f"ea_{it_}"] = flat(ex.shadow_params), flat(ea.shadow_params)
+    finally:
+        torch.rand, torch.randn_like = orig_rand, orig_like
+    np.savez_compressed(os.path.join(GOLD, f"train_steps_{name}.npz"), **rec)
+    out = {k: rec[k].tolist() for k in rec if k.startswith(("loss", "gnorm"))}
+    print("train steps", out, flush=True)
+    return out
+
+
 def only(which):
-    """python oracle/make_golden.py decode | c1 | dsm | mol | dsmgrad : just one of the small fixtures."""
+    """python oracle/make_golden.py decode | c1 | dsm | mol | dsmgrad | train : just one of the small fixtures."""
     refimport.activate()
     torch.set_num_threads(os.cpu_count())
     mpath = os.path.join(GOLD, "MANIFEST.json")
@@ -376,6 +425,8 @@ def only(which):
         manifest["mol_stats"] = make_mol_stats()
     elif which == "dsmgrad":
         manifest["dsm_grad"] = make_dsm_grads()
+    elif which == "train":
+        manifest["train_steps"] = make_train_steps()
     else:
         manifest["c1"] = make_c1_stats()
         print(manifest["c1"])
@@ -384,4 +435,4 @@ def only(which):
 
 
 if __name__ == "__main__":
-    only(sys.argv[1]) if sys.argv[1:] in (["decode"], ["c1"], ["dsm"], ["mol"], ["dsmgrad"]) else main()
+    only(sys.argv[1]) if sys.argv[1:] in (["decode"], ["c1"], ["dsm"], ["mol"], ["dsmgrad"], ["train"]) else main()
