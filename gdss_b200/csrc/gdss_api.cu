@@ -83,6 +83,24 @@ extern "C" gdss_ctx* gdss_ctx_create(int32_t N, int32_t F, const gdss_net_desc* 
   c->use_tc = !(ntc && ntc[0] == '1');
   const char* nmma = getenv("GDSS_NO_MMA");
   c->use_mma = !(nmma && nmma[0] == '1');
+  const char* pp = getenv("GDSS_PHASE_PROF");
+  c->phase_prof = pp && pp[0] == '1';
+  // dead sub-network elimination (gdss_pack.cu analyze_liveness): needs the weights on the host once
+  const char* np = getenv("GDSS_NO_PRUNE");
+  if (c->num_sms > 0 && !(np && np[0] == '1')) {
+    const float* blobs[2] = {c->has_x ? dev_blob_x : nullptr, c->has_a ? dev_blob_a : nullptr};
+    NetPlan* plans[2] = {&c->px, &c->pa};
+    for (int k = 0; k < 2; ++k) {
+      if (!blobs[k] || plans[k]->type == GDSS_NET_X) continue;
+      float* host = (float*)malloc(sizeof(float) * (size_t)plans[k]->total);
+      if (!host) continue;
+      if (cudaMemcpy(host, blobs[k], sizeof(float) * (size_t)plans[k]->total, cudaMemcpyDeviceToHost) == cudaSuccess)
+        c->pruned += analyze_liveness(plans[k], host);
+      else
+        cudaGetLastError();
+      free(host);
+    }
+  }
   return c;
 }
 
@@ -105,7 +123,7 @@ extern "C" int64_t gdss_workspace_bytes(const gdss_ctx* ctx, int32_t B) {
 
 extern "C" int64_t gdss_workspace_offset(const gdss_ctx* ctx, int32_t B, const char* region) {
   static const char* names[R_COUNT] = {"neff", "step", "table", "means", "norms", "stack_a", "stack_x", "dis",
-                                       "qkv", "xa0", "xa1", "xs", "raw_x", "raw_adj", "poff", "meta", "gmap", "order", "stackT"};
+                                       "qkv", "xa0", "xa1", "xs", "raw_x", "raw_adj", "poff", "meta", "gmap", "order", "stackT", "x0", "a0"};
   if (!ctx || B <= 0 || !region) return GDSS_E_BADARG;
   Workspace w;
   layout_workspace(ctx, B, &w);
@@ -127,6 +145,7 @@ extern "C" int64_t gdss_ctx_query(const gdss_ctx* ctx, const char* key) {
   if (!strcmp(key, "smem_optin")) return ctx->smem_optin;
   if (!strcmp(key, "use_tc")) return ctx->use_tc ? 1 : 0;
   if (!strcmp(key, "use_mma")) return ctx->use_mma ? 1 : 0;
+  if (!strcmp(key, "pruned")) return ctx->pruned;
   return GDSS_E_BADARG;
 }
 
@@ -210,11 +229,13 @@ __global__ void gen_noise_kernel(float* out, const float* raw, const float* flag
 
 __global__ void quantize_kernel(const float* a, float* out, float thr, int64_t n) {
   for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < n; idx += (int64_t)gridDim.x * blockDim.x)
-    out[idx] = a[idx] >= thr ? 1.f : 0.f;
+    out[idx] = a[idx] < thr ? 0.f : 1.f;       // torch.where(adjs < thr, 0, 1): NaN -> 1, like the reference
 }
 
 __global__ void quantize_mol_kernel(const float* a, int64_t* out, int64_t n) {
   for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < n; idx += (int64_t)gridDim.x * blockDim.x) {
+    // graph_utils.py:101-104: three successive torch.where passes; a NaN fails every comparison and the reference
+    // then casts the NaN itself to int64 (undefined); here NaN -> 0 (documented, asserted in the host mirror)
     float v = a[idx];
     out[idx] = v >= 2.5f ? 3 : (v >= 1.5f ? 2 : (v >= 0.5f ? 1 : 0));
   }

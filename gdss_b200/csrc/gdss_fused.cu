@@ -121,6 +121,13 @@ __global__ void __launch_bounds__(64) tri_map_kernel(const int* __restrict__ nef
 // (TMA, cp.async.bulk) one phase group ahead of its use.  *_o = float offsets inside the run.
 struct FLayer {
   int c_in, c_out, f_in, f_in_p, attn, nlin, qkvw, need_edge, need_node;
+  // dead sub-network elimination (gdss_pack.cu analyze_liveness): channels whose Q/K chain + map (qk_live) or V
+  // convolution (v_live) can reach an output; act[] = channels with any live chain, qkc[] = those with a live map;
+  // edge_const: the per-edge MLP's output is the constant cst[] (times the flag mask)
+  unsigned qk_live, v_live;
+  int nact, nqk, edge_const;
+  signed char act[8], qkc[8];
+  float cst[8];
   const float* blk_q; int q_floats, bq_o;                 // [c_in][f_in_p][qkvw] then biases [c_in][qkvw]
   const float* blk_m; int m_floats, ew_o[3], eb_o[3], nw0_o, nb0_o, nw1_o, nb1_o;
 };
@@ -626,6 +633,9 @@ DEVINL float acc_get(const Acc& c, int q) { return c.m[q]; }
 template <int NLIN>
 DEVINL void edge_mlp_mma(const float* M, int MS, const float* pin, int PM, const unsigned* pix, const float* fl, const float* wm,
                          const FLayer& L, int P, float* pout, float* gout, int64_t gstride, int warp, int nwarps, int lane) {
+  // kmask: bit k set = input k of the first linear is live (maps of dead Q/K chains are identically zero: not gathered,
+  // and a k-step made of dead inputs only is not issued)
+  const unsigned kmask = (L.qk_live & ((1u << L.c_in) - 1u)) | (((1u << L.c_in) - 1u) << L.c_in);
   // (handing the tiles out through a shared counter, so that the node-MLP warps could join once their rows are done, was
   // measured 3 % slower: per-warp weight-fragment set-up and an atomic + shuffle per tile cost more than the imbalance)
   const int g = lane >> 2, t = lane & 3;
@@ -674,13 +684,13 @@ DEVINL void edge_mlp_mma(const float* M, int MS, const float* pin, int PM, const
     for (int j = 0; j < 2; ++j) acc_init(c[j], bia1[j][0], bia1[j][1]);
 #pragma unroll
     for (int s = 0; s < 2; ++s) {
-      if (s < ks1) {
+      if (s < ks1 && ((kmask >> (8 * s)) & 0xffu)) {
         uint32_t ah[4], al[4];
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
           const int k = 8 * s + t + 4 * q;
           float va = 0.f, vb = 0.f;
-          if (k < K1) {
+          if (k < K1 && ((kmask >> k) & 1u)) {
             const float* pl = k < C ? M + k * MS : pin + (k - C) * PM;
             va = pl[pac];
             vb = pl[pbc];
@@ -741,7 +751,8 @@ DEVINL void edge_mlp_mma(const float* M, int MS, const float* pin, int PM, const
 //   cat_c V_c[i] (K = c_in * nhid) -> 16 (ELU) -> nhid, mask, tanh (twice in X_GMH, ScoreNetwork_X.py:81)
 // both layers chained in registers.  V rows have stride ldv = K + 4 (bank-conflict-free A fragments).
 DEVINL void node_mlp_mma(const float* V, int ldv, int K, const float* W1, const float* b1, const float* W2, const float* b2, int n,
-                         int h, const float* fl, bool twice, float* xo, int ldo, int warp, int nwarps, int lane) {
+                         int h, const float* fl, bool twice, float* xo, int ldo, int warp, int nwarps, int lane, unsigned vmask) {
+  // vmask: bit c set = the V block of channel c is live (k-steps of dead blocks are skipped; h is a multiple of 8)
   const int g = lane >> 2, t = lane & 3;
   const int mt = (n + 15) >> 4;
   for (int m = warp; m < mt; m += nwarps) {
@@ -753,6 +764,7 @@ DEVINL void node_mlp_mma(const float* V, int ldv, int K, const float* W1, const 
     for (int j = 0; j < 2; ++j) acc_init(c[j], b1[8 * j + 2 * t], b1[8 * j + 2 * t + 1]);
 #pragma unroll 2
     for (int k0 = 0; k0 < K; k0 += 8) {
+      if (!((vmask >> (k0 / h)) & 1u)) continue;
       uint32_t ah[4], al[4];
       const Split a0 = split_tf32(va[k0 + t]), a1 = split_tf32(vb[k0 + t]);
       const Split a2 = split_tf32(va[k0 + t + 4]), a3 = split_tf32(vb[k0 + t + 4]);
@@ -929,7 +941,7 @@ template <bool WS, int HD, int NF, int MB>       // NF: compile-time bound of th
 __device__ __noinline__ void channel_chain_mma(int lane, const float* pl, const unsigned short* tab, int TC, float* dv, const float* x, int ldx, int n,
                               int f, int f_in_p, const float* Wc, int qkvw, const float* bc, float* qkc, int QKS, float* vcol, int ldv,
                               bool need_edge, bool need_node, const unsigned* pix, int P, float scale, float* Mc, int part, int nparts,
-                              int bar_id) {
+                              int bar_id, bool do_map) {
   // part / nparts: the warps of one channel split the row-tile passes and the pixels of the map; they meet at the named
   // barrier bar_id once Q|K are complete (each computes the degrees itself: identical values)
   constexpr int AT = 4 * HD;
@@ -1053,6 +1065,7 @@ __device__ __noinline__ void channel_chain_mma(int lane, const float* pl, const 
       }
     }
   }
+  if (!do_map) return;                 // the maps are computed CTA-wide after a barrier (maps_cta)
   if (nparts > 1) asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(32 * nparts) : "memory");
   else __syncwarp();
   // ---- attention map (attention.py:35-49): mean over the 4 heads and both orientations of tanh(Q_h.K_h / sqrt(out_dim))
@@ -1079,6 +1092,44 @@ __device__ __noinline__ void channel_chain_mma(int lane, const float* pl, const 
       }
       Mc[p] = fmaf(-0.25f, m, 1.f);             // mean of the 8 tanh = 1 - (2 / 8) * sum of 1 / (exp(2 z) + 1)
     }
+  }
+}
+
+// maps_cta: the attention maps of the live channels spread evenly over the warps of the CTA (items = channel x 32-pixel
+// block).  Used instead of the in-chain maps when the channels of a layer do not have equal work (dead Q/K chains or V
+// convolutions switched off, or a channel count that does not divide the warp count).  Q carries the 2 log2(e) / sqrt(out_dim)
+// factor (channel_chain_mma).
+template <int HD>
+DEVINL void maps_cta(const float* QK, int QKS, int n, const unsigned* pix, int P, float* R1, int RS, const FLayer& L, int warp,
+                     int nwarps, int lane) {
+  constexpr int AT = 4 * HD;
+  const int nblk = (P + 31) >> 5;
+  const FastDiv db(nblk);
+  for (int item = warp; item < L.nqk * nblk; item += nwarps) {
+    const int ci = db.div(item), p = (item - ci * nblk) * 32 + lane;
+    const int c = L.qkc[ci];
+    if (p >= P) continue;
+    const float* qkc = QK + c * n * QKS;
+    const unsigned ij = pix[p];
+    const int i = ij >> 8, j = ij & 255;
+    const float* qi = qkc + i * QKS;
+    const float* qj = qkc + j * QKS;
+    float m = 0.f;
+#pragma unroll
+    for (int hh = 0; hh < 4; ++hh) {
+      float2 p1 = make_float2(0.f, 0.f), p2 = make_float2(0.f, 0.f);
+#pragma unroll
+      for (int d = 0; d < HD; d += 4) {
+        const float4 a1 = *reinterpret_cast<const float4*>(qi + hh * HD + d);
+        const float4 b1 = *reinterpret_cast<const float4*>(qj + AT + hh * HD + d);
+        const float4 a2 = *reinterpret_cast<const float4*>(qj + hh * HD + d);
+        const float4 b2 = *reinterpret_cast<const float4*>(qi + AT + hh * HD + d);
+        p1 = fma2(lo2(a1), lo2(b1), p1); p1 = fma2(hi2(a1), hi2(b1), p1);
+        p2 = fma2(lo2(a2), lo2(b2), p2); p2 = fma2(hi2(a2), hi2(b2), p2);
+      }
+      m += sig2(p1.x + p1.y) + sig2(p2.x + p2.y);
+    }
+    R1[c * RS + p] = fmaf(-0.25f, m, 1.f);
   }
 }
 
@@ -1324,42 +1375,53 @@ __global__ void __launch_bounds__(NT, OCC) fused_layers_kernel(const __grid_cons
       const int LDV = C * h + 4;       // row stride of the V rows [i][c][h] (+4: conflict-free mma A fragments)
       const float* wqp = WSM ? wq : L.blk_q;
       const bool chain_mma = A.use_mma && ((f <= 16 && attn == 16) || (f <= 32 && attn == 32));
-      if (chain_mma || 2 * C > nwarps) {
+      const int nact = L.nact;           // channels with a live Q/K chain or V convolution (all of them unless pruned)
+      const bool any_qk = L.nqk > 0, any_v = L.v_live != 0;
+      if (WSM) {
+        mbar_wait_parity(&mbar_q, ph_q);
+        ph_q ^= 1;
+      }
+      if (nact == 0) {
+        // nothing of this layer's convolutions reaches an output
+      } else if (chain_mma || 2 * C > nwarps) {
         // ---- one warp per channel, no CTA barrier inside the chain
-        if (WSM) {
-          mbar_wait_parity(&mbar_q, ph_q);
-          ph_q ^= 1;
-        }
-        const int nparts = (chain_mma && nwarps >= 2 * C) ? nwarps / C : 1;       // warps per channel (mma chain only)
-        for (int u = warp; u < C * nparts; u += nwarps) {
-          const int c = nparts > 1 ? u % C : u, part = nparts > 1 ? u / C : 0;
+        const int nparts = (chain_mma && nwarps >= 2 * nact) ? nwarps / nact : 1;       // warps per channel (mma chain only)
+        // channels of unequal work (dead chains switched off) or a channel count that leaves warps idle: the maps are
+        // computed CTA-wide after a barrier instead of inside the chains
+        const bool split_maps = chain_mma && any_qk && (L.nqk != nact || (nact * nparts) % nwarps != 0);
+        for (int u = warp; u < nact * nparts; u += nwarps) {
+          const int ci = nparts > 1 ? u % nact : u, part = nparts > 1 ? u / nact : 0;
+          const int c = L.act[ci];
+          const bool ce = (L.qk_live >> c) & 1u, cn = (L.v_live >> c) & 1u;
           const float* Wc = wqp + c * L.f_in_p * L.qkvw;
           const float* bc = wqp + L.bq_o + c * L.qkvw;
           if (A.use_mma && f <= 16 && attn == 16 && (A.mb1 || nparts > 1)) {   // graphs of at most 16 nodes: one row tile;
                                                                                // several warps per channel: one tile per warp
             channel_chain_mma<WSM, 4, 2, 1>(lane, pin + c * PM, tab, S.TC, dinv + c * NBP, xin, XS, n, f, L.f_in_p, Wc, L.qkvw, bc,
-                                            QK + c * n * QKS, QKS, R2 + c * h, LDV, L.need_edge, L.need_node, pix, P, scale, R1 + c * RS, part, nparts, 2 + c);
+                                            QK + c * n * QKS, QKS, R2 + c * h, LDV, ce, cn, pix, P, scale, R1 + c * RS, part, nparts, 2 + c, !split_maps);
           } else if (A.use_mma && f <= 16 && attn == 16) {
             channel_chain_mma<WSM, 4, 2, 2>(lane, pin + c * PM, tab, S.TC, dinv + c * NBP, xin, XS, n, f, L.f_in_p, Wc, L.qkvw, bc,
-                                            QK + c * n * QKS, QKS, R2 + c * h, LDV, L.need_edge, L.need_node, pix, P, scale, R1 + c * RS, part, nparts, 2 + c);
+                                            QK + c * n * QKS, QKS, R2 + c * h, LDV, ce, cn, pix, P, scale, R1 + c * RS, part, nparts, 2 + c, !split_maps);
           } else if (A.use_mma && f <= 32 && attn == 32) {
             channel_chain_mma<WSM, 8, 4, 1>(lane, pin + c * PM, tab, S.TC, dinv + c * NBP, xin, XS, n, f, L.f_in_p, Wc, L.qkvw, bc,
-                                         QK + c * n * QKS, QKS, R2 + c * h, LDV, L.need_edge, L.need_node, pix, P, scale, R1 + c * RS, part, nparts, 2 + c);
+                                         QK + c * n * QKS, QKS, R2 + c * h, LDV, ce, cn, pix, P, scale, R1 + c * RS, part, nparts, 2 + c, !split_maps);
           } else if (part > 0) {
             // (the FFMA chain runs one warp per channel)
           } else if (attn == 16)
             channel_pipeline<WSM, 4>(lane, pin + c * PM, dinv + c * NBP, xin, XS, n, f, R1 + c * RS, Wc, L.qkvw, bc, QK + c * n * QKS, QKS,
-                                     R2 + c * h, LDV, h, L.need_edge, L.need_node, pix, P, scale, R1 + c * RS);
+                                     R2 + c * h, LDV, h, ce, cn, pix, P, scale, R1 + c * RS);
           else
             channel_pipeline<WSM, 8>(lane, pin + c * PM, dinv + c * NBP, xin, XS, n, f, R1 + c * RS, Wc, L.qkvw, bc, QK + c * n * QKS, QKS,
-                                     R2 + c * h, LDV, h, L.need_edge, L.need_node, pix, P, scale, R1 + c * RS);
+                                     R2 + c * h, LDV, h, ce, cn, pix, P, scale, R1 + c * RS);
         }
         PHASE(8);                    // warp 0's own channel chain; PHASE(3) below = its wait for the slowest warp
-        __syncthreads();
-        if (WSM && more && tid == 0) tma_fetch(wq, net.L[l + 1].blk_q, net.L[l + 1].q_floats, &mbar_q);
-        PHASE(3);
+        if (split_maps) {
+          __syncthreads();           // Q | K of every live channel complete
+          if (attn == 16) maps_cta<4>(QK, QKS, n, pix, P, R1, RS, L, warp, nwarps, lane);
+          else maps_cta<8>(QK, QKS, n, pix, P, R1, RS, L, warp, nwarps, lane);
+        }
       } else {
-        // ---- few channels (first layer): every step spread over the whole CTA
+        // ---- few channels (first layer): every step spread over the whole CTA (all channels are evaluated when any is live)
         gcn_degrees(pin, PM, C, n, NBP, dinv, dn);
         __syncthreads();
         PHASE(1);
@@ -1367,22 +1429,38 @@ __global__ void __launch_bounds__(NT, OCC) fused_layers_kernel(const __grid_cons
         __syncthreads();
         PHASE(2);
         // Q | K | V = (A^ x) W + b for every channel (attention.py:32-34); V rows are stored [i][c][h]
-        if (WSM) {
-          mbar_wait_parity(&mbar_q, ph_q);
-          ph_q ^= 1;
-        }
         mm_rows_t<WSM>(mm_make(R1, RS, 8 * f8, f, wqp, L.f_in_p * L.qkvw, L.qkvw, wqp + L.bq_o, L.qkvw, C, n,
-                               L.need_edge ? 0 : 2 * attn, L.need_node ? L.qkvw : 2 * attn, QK, n * QKS, QKS, 2 * attn, R2, h, LDV,
+                               any_qk ? 0 : 2 * attn, any_v ? L.qkvw : 2 * attn, QK, n * QKS, QKS, 2 * attn, R2, h, LDV,
                                nullptr, ACT_NONE));
         __syncthreads();
-        if (WSM && more && tid == 0) tma_fetch(wq, net.L[l + 1].blk_q, net.L[l + 1].q_floats, &mbar_q);
-        if (L.need_edge) {
+        if (any_qk) {
           if (attn == 16) attention_maps<4>(QK, QKS, pix, C, n, P, RS, scale, R1, dP);
           else attention_maps<8>(QK, QKS, pix, C, n, P, RS, scale, R1, dP);
         }
-        __syncthreads();
         PHASE(4);
       }
+      // dead chains: their maps are identically zero / their V blocks are never read with a live weight -- zero both so
+      // that every reader sees finite values (the regions are private to the dead channel)
+      if (L.need_edge && !L.edge_const && L.nqk < C) {
+        const bool full_eval = nact > 0 && !(chain_mma || 2 * C > nwarps) && any_qk;     // the CTA-wide path wrote every map
+        if (!full_eval)
+          for (int c = 0; c < C; ++c)
+            if (!((L.qk_live >> c) & 1u))
+              for (int p = tid; p < P; p += nt) R1[c * RS + p] = 0.f;
+      }
+      if (L.need_node && L.v_live != ((1u << C) - 1u)) {
+        const bool full_eval = nact > 0 && !(chain_mma || 2 * C > nwarps) && any_v;
+        if (!full_eval)
+          for (int c = 0; c < C; ++c)
+            if (!((L.v_live >> c) & 1u))
+              for (int idx = tid; idx < n * h; idx += nt) {
+                const int i = dh.div(idx), o = idx - i * h;
+                R2[i * LDV + c * h + o] = 0.f;
+              }
+      }
+      __syncthreads();
+      if (WSM && more && tid == 0) tma_fetch(wq, net.L[l + 1].blk_q, net.L[l + 1].q_floats, &mbar_q);
+      PHASE(3);
       // ---- node MLP (attention.py:106-107) on the last two warps, per-edge MLP (:109-114) on the others.
       // x_in is dead by now: layers >= 1 update xb in place (layer 0 reads x0, which the X network needs again)
       if (WSM) {
@@ -1400,7 +1478,7 @@ __global__ void __launch_bounds__(NT, OCC) fused_layers_kernel(const __grid_cons
         const int ltid = node_warps ? tid - nt_edge : tid, lnt = node_warps ? 32 * node_warps : nt;
         if (A.use_mma) {
           node_mlp_mma(R2, LDV, C * h, wmp + L.nw0_o, wmp + L.nb0_o, wmp + L.nw1_o, wmp + L.nb1_o, n, h, fl, !isA, xb, XS, ltid >> 5,
-                       lnt >> 5, lane);
+                       lnt >> 5, lane, L.v_live);
         } else {
           node_l1(R2, LDV, C * h, wmp + L.nw0_o, wmp + L.nb0_o, n, h1, ltid, lnt);
           if (node_warps) asm volatile("bar.sync 1, %0;" ::"r"(lnt) : "memory");
@@ -1411,12 +1489,24 @@ __global__ void __launch_bounds__(NT, OCC) fused_layers_kernel(const __grid_cons
       if (L.need_edge && (node_warps == 0 || tid < nt_edge)) {
         if (!node_warps && L.need_node) __syncthreads();       // (never both: kept for symmetry of the barrier count)
         float* gout = isA ? A.stackT + (int64_t)cbase * A.pstride + gp0 : nullptr;
-        if (A.use_mma) {
-          if (L.nlin == 3) edge_mlp_mma<3>(R1, RS, pin, PM, pix, fl, wmp, L, P, more ? PA : nullptr, gout, A.pstride, warp, nt_edge >> 5, lane);
-          else edge_mlp_mma<2>(R1, RS, pin, PM, pix, fl, wmp, L, P, more ? PA : nullptr, gout, A.pstride, warp, nt_edge >> 5, lane);
+        float* pout = more ? PA : nullptr;
+        if (L.edge_const) {
+          // every input weight of `mlp` is dead: the channels are the constant mlp(0) (attention.py:109-114), symmetrised and masked
+          for (int p = tid; p < P; p += nt_edge) {
+            const unsigned ij = pix[p];
+            const float fm = 2.f * fl[ij >> 8] * fl[ij & 255];
+            for (int o = 0; o < L.c_out; ++o) {
+              const float v = L.cst[o] * fm;
+              if (pout) pout[o * PM + p] = v;
+              if (gout) gout[(int64_t)o * A.pstride + p] = v;
+            }
+          }
+        } else if (A.use_mma) {
+          if (L.nlin == 3) edge_mlp_mma<3>(R1, RS, pin, PM, pix, fl, wmp, L, P, pout, gout, A.pstride, warp, nt_edge >> 5, lane);
+          else edge_mlp_mma<2>(R1, RS, pin, PM, pix, fl, wmp, L, P, pout, gout, A.pstride, warp, nt_edge >> 5, lane);
         } else {
-          if (L.nlin == 3) edge_mlp<3>(R1, RS, pin, PM, pix, fl, wmp, L, P, more ? PA : nullptr, gout, A.pstride, tid, nt_edge);
-          else edge_mlp<2>(R1, RS, pin, PM, pix, fl, wmp, L, P, more ? PA : nullptr, gout, A.pstride, tid, nt_edge);
+          if (L.nlin == 3) edge_mlp<3>(R1, RS, pin, PM, pix, fl, wmp, L, P, pout, gout, A.pstride, tid, nt_edge);
+          else edge_mlp<2>(R1, RS, pin, PM, pix, fl, wmp, L, P, pout, gout, A.pstride, tid, nt_edge);
         }
       }
       PHASE(7);                      // warp 0's share of the per-edge MLP; PHASE(5) below = its wait (node warps, other edge warps)
@@ -2055,7 +2145,16 @@ static void fill_net(const NetPlan& p, const float* blob, FNet* f) {
     const bool last = l == p.depth - 1;
     o.c_in = L.c_in; o.c_out = L.c_out; o.f_in = L.f_in; o.f_in_p = L.f_in_p; o.attn = L.attn; o.nlin = L.nlin; o.qkvw = L.qkvw;
     o.need_edge = (p.type == GDSS_NET_A || !last) ? 1 : 0;   // X_GMH: the last layer's adj_out is never read
-    o.need_node = (p.type != GDSS_NET_A || !last) ? 1 : 0;   // A: the last layer's x_out is never read
+    o.need_node = ((p.type != GDSS_NET_A || !last) && L.node_live) ? 1 : 0;   // A: the last layer's x_out is never read
+    o.edge_const = (o.need_edge && L.edge_const) ? 1 : 0;
+    o.qk_live = (o.need_edge && !o.edge_const) ? L.qk_live : 0u;
+    o.v_live = o.need_node ? L.v_live : 0u;
+    o.nact = o.nqk = 0;
+    for (int c = 0; c < L.c_in && c < 8; ++c) {
+      if (((o.qk_live | o.v_live) >> c) & 1u) o.act[o.nact++] = (signed char)c;
+      if ((o.qk_live >> c) & 1u) o.qkc[o.nqk++] = (signed char)c;
+    }
+    for (int c = 0; c < 8; ++c) o.cst[c] = c < L.c_out ? L.edge_cst[c] : 0.f;
     o.blk_q = blob + L.wqkv;
     o.bq_o = (int)(L.bqkv - L.wqkv);
     o.q_floats = (int)(L.ew[0] - L.wqkv);                        // wqkv + bqkv (both padded to 4 floats)
@@ -2216,7 +2315,7 @@ int launch_eval_fused(const gdss_ctx* ctx, const float* x, const float* adj, con
     fa.nstride = w.nstride;
   }
   fa.use_mma = ctx->use_mma ? 1 : 0;
-  fa.prof = getenv("GDSS_PHASE_PROF") ? reinterpret_cast<unsigned long long*>(ws + w.off[R_META] + 128) : nullptr;
+  fa.prof = ctx->phase_prof ? reinterpret_cast<unsigned long long*>(ws + w.off[R_META] + 128) : nullptr;
   fa.order = reinterpret_cast<const int*>(ws + w.off[R_ORDER]);
   fa.meta = reinterpret_cast<const int*>(ws + w.off[R_META]);
   int nb[3];

@@ -24,6 +24,12 @@ struct LayerPlan {
   int64_t ew[GDSS_MAX_LIN];     // edge MLP `mlp`: (2 c_in -> hid), (hid -> hid)*, (hid -> c_out)
   int64_t eb[GDSS_MAX_LIN];
   int64_t nw[2], nb[2];         // node MLP `multi_channel`: (c_in*nhid -> hid), (hid -> nhid)
+  // Dead sub-network elimination (analyze_liveness, gdss_pack.cu): bit c set = the Q/K chain + attention map (qk_live)
+  // or the V convolution (v_live) of channel c can reach an output.  plan_net sets everything live.
+  uint32_t qk_live, v_live;
+  int node_live;                // the layer's node output x_out is read by something downstream
+  int edge_const;               // every input weight of `mlp` is dead: its output is the constant edge_cst per pixel
+  float edge_cst[GDSS_MAX_CH];
 };
 
 struct NetPlan {
@@ -40,11 +46,15 @@ struct NetPlan {
 };
 
 int plan_net(const gdss_net_desc* d, int N, NetPlan* p);
+// Marks the parts of an AttentionLayer stack that cannot influence the output because whole weight blocks are below
+// GDSS_DEAD_EPS in magnitude (weight-decayed dead sub-networks of the shipped checkpoints).  host_blob = the packed blob.
+// Returns the number of (layer, channel) chains / MLPs it switched off.
+int analyze_liveness(NetPlan* p, const float* host_blob);
 
 // named workspace regions (byte offsets, 256-aligned)
 enum Region {
   R_NEFF = 0, R_STEP, R_TABLE, R_MEANS, R_NORMS, R_STACK_A, R_STACK_X, R_DIS, R_QKV, R_XA0, R_XA1, R_XS, R_RAW_X, R_RAW_ADJ,
-  R_POFF, R_META, R_GMAP, R_ORDER, R_STACKT,
+  R_POFF, R_META, R_GMAP, R_ORDER, R_STACKT, R_X0, R_A0,
   R_COUNT
 };
 
@@ -71,6 +81,8 @@ struct gdss_ctx {
   cudaEvent_t ev_fork, ev_join[2];
   bool use_mma;                 // per-graph contractions on mma.sync (3xTF32); GDSS_NO_MMA=1 selects the FFMA variants
   bool use_tc;                  // final edge MLP on tcgen05 tensor cores (3xTF32); GDSS_NO_TC=1 selects the FFMA kernel
+  int pruned;                   // number of dead chains / MLPs switched off by analyze_liveness (GDSS_NO_PRUNE=1: 0)
+  bool phase_prof;              // GDSS_PHASE_PROF=1 (read once at creation): per-phase cycle counters in the workspace
 };
 
 namespace gdss {

@@ -12,6 +12,7 @@
 // pixels are never produced nor read (DenseGCNConv overwrites them with 1, the final score
 // zeroes them, ScoreNetwork_A.py:145).
 #include <stdio.h>
+#include <string.h>
 
 #include <vector>
 
@@ -134,8 +135,9 @@ __global__ void __launch_bounds__(256) pow_kernel(const float* __restrict__ Lp, 
 // one warp per row, lanes along j (coalesced).
 // ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) deg_kernel(const float* __restrict__ planes, int64_t p_bs, float* __restrict__ dis,
-                                                  int64_t d_bs, const int* __restrict__ neff, int N) {
+                                                  int64_t d_bs, const int* __restrict__ neff, int N, unsigned live) {
   const int b = blockIdx.y, c = blockIdx.x, n = neff[b];
+  if (!((live >> c) & 1u)) return;          // no live convolution reads this channel's degrees
   const float* P = planes + b * p_bs + (int64_t)c * N * N;
   float* D = dis + b * d_bs + (int64_t)c * N;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -161,6 +163,9 @@ struct GcnArgs {
   float* out; int64_t o_bs; int64_t o_cs; int ldo;
   const int* neff;
   int act; int N; int TI;
+  // per-channel column ranges (dead sub-network elimination): channel c computes Q|K iff bit c of qk_live, V iff bit c of v_live
+  int per_channel, attn, nhid;
+  unsigned qk_live, v_live;
 };
 
 #define GCN_JC 64
@@ -174,6 +179,13 @@ __global__ void __launch_bounds__(256) gcn_kernel(GcnArgs a) {
   const int b = blockIdx.z, c = blockIdx.y, n = a.neff[b];
   const int i0 = blockIdx.x * a.TI;
   if (i0 >= n) return;
+  int col0 = a.col0, ow = a.ow;
+  if (a.per_channel) {
+    const bool q = (a.qk_live >> c) & 1u, v = (a.v_live >> c) & 1u;
+    if (!q && !v) return;
+    col0 = q ? 0 : 2 * a.attn;
+    ow = (q ? 2 * a.attn : 0) + (v ? a.nhid : 0);
+  }
   const int ti = min(a.TI, n - i0);
   const int F = a.f_in, N = a.N;
   const int TIP = a.TI + 4, q4 = (ti + 3) >> 2;      // padded row count (a.TI is a multiple of 4), row quads of this tile
@@ -240,8 +252,8 @@ __global__ void __launch_bounds__(256) gcn_kernel(GcnArgs a) {
   const float* W = a.W + (int64_t)c * a.w_cs;
   const float* Bv = a.bias + (int64_t)c * a.b_cs;
   float* O = a.out + b * a.o_bs + (int64_t)c * a.o_cs;
-  for (int idx = tid; idx < q4 * a.ow; idx += 256) {
-    int iq = idx / a.ow, o = idx - iq * a.ow + a.col0;
+  for (int idx = tid; idx < q4 * ow; idx += 256) {
+    int iq = idx / ow, o = idx - iq * ow + col0;
     const float bb = Bv[o];
     float s0 = bb, s1 = bb, s2 = bb, s3 = bb;
     const float* axr = AXT + 4 * iq;
@@ -277,6 +289,7 @@ struct EdgeArgs {
   const float* w[GDSS_MAX_LIN]; const float* bias[GDSS_MAX_LIN];
   const float* flags; const int* neff;
   int N; int T; int ntile; int cin, hid, cout;
+  unsigned qk_live;            // bit c: the attention map of channel c is live (else it is identically zero)
 };
 
 // y[OUTP] = bias + x[IN] . W[IN][OUTP], weights in shared memory read as broadcast float4
@@ -326,6 +339,7 @@ __global__ void __launch_bounds__(256) edge_kernel(EdgeArgs a) {
     int v = idx % (qk >> 2);
     int rc = idx / (qk >> 2);
     int c = rc % a.cin, r = rc / a.cin;
+    if (!((a.qk_live >> c) & 1u)) continue;
     int node = r < mi ? i0 + r : j0 + (r - mi);
     float4 val = *reinterpret_cast<const float4*>(Q + (int64_t)c * a.q_cs + (int64_t)node * a.qkvw + 4 * v);
     float* dst = (r < mi ? SI + r * RS : SJ + (r - mi) * RS) + c * qk + 4 * v;
@@ -376,6 +390,11 @@ __global__ void __launch_bounds__(256) edge_kernel(EdgeArgs a) {
         in[CIN + c] = 0.f;
         continue;
       }
+      in[CIN + c] = Pin[(int64_t)c * N * N + (int64_t)gi * N + gj];
+      if (!((a.qk_live >> c) & 1u)) {
+        in[c] = 0.f;
+        continue;
+      }
       const float* qi = ri + c * qk;
       const float* ki = qi + a.attn;
       const float* qj = rj + c * qk;
@@ -394,7 +413,6 @@ __global__ void __launch_bounds__(256) edge_kernel(EdgeArgs a) {
         m += tanh_f(s1 * a.scale) + tanh_f(s2 * a.scale);
       }
       in[c] = m * mscale;
-      in[CIN + c] = Pin[(int64_t)c * N * N + (int64_t)gi * N + gj];
     }
     // ---- MLP (layers.py:135-153): Linear, ELU, ..., Linear
     constexpr int HIDP = (HID + 3) & ~3, COUTP = (COUT + 3) & ~3;
@@ -432,6 +450,7 @@ struct NodeArgs {
   float* out; int64_t o_bs; int ldo;
   const float* flags; const int* neff;
   int N, cin, nhid, hid, extra_tanh;
+  unsigned v_live;             // bit c: the V rows of channel c are live (dead blocks are never read)
 };
 
 #define NODE_ROWS 64
@@ -455,6 +474,7 @@ __global__ void __launch_bounds__(256) node_kernel(NodeArgs a) {
     int r = idx / H, u = idx - r * H;
     float s = a.b1[u];
     for (int c = 0; c < a.cin; ++c) {
+      if (!((a.v_live >> c) & 1u)) continue;
       const float* v = Q + (int64_t)c * a.q_cs + (int64_t)(i0 + r) * a.qkvw + a.vcol;
       const float* w = W1 + (c * NH) * H + u;
       for (int k = 0; k < NH; ++k) s = fmaf(v[k], w[k * H], s);
@@ -801,6 +821,8 @@ void layout_workspace(const gdss_ctx* ctx, int B, Workspace* w) {
   }
   sz[R_RAW_X] = 4 * (int64_t)B * N * F;
   sz[R_RAW_ADJ] = 4 * (int64_t)B * N * N;
+  sz[R_X0] = 4 * (int64_t)B * N * F;          // Langevin corrector with n_steps > 1: the state at the start of the phase
+  sz[R_A0] = 4 * (int64_t)B * N * N;
   int64_t cur = 0;
   for (int i = 0; i < R_COUNT; ++i) {
     w->off[i] = cur;
@@ -910,12 +932,17 @@ static int run_attn_net(const gdss_ctx* ctx, const NetPlan& p, const float* blob
     const LayerPlan& L = p.layers[l];
     const bool last = l == p.depth - 1;
     const bool need_edge = isA || !last;   // X_GMH: the last layer's adj_out (hence Q, K) is dead
-    const bool need_node = !isA || !last;  // A: the last layer's x_out (hence V) is dead
+    const bool need_node = (!isA || !last) && L.node_live;  // A: the last layer's x_out (hence V) is dead
+    // dead sub-network elimination (gdss_pack.cu analyze_liveness)
+    const unsigned qk_live = (need_edge && !L.edge_const) ? L.qk_live : 0u, v_live = need_node ? L.v_live : 0u;
     const float* pin = stack + (int64_t)cur * NN;
-    deg_kernel<<<dim3(L.c_in, B, (N + 31) / 32), 256, 0, st>>>(pin, s_bs, dis, d_bs, neff, N);
+    GcnArgs g;
+    memset(&g, 0, sizeof(g));
+    g.o_bs = (int64_t)L.c_in * N * L.qkvw; g.o_cs = (int64_t)N * L.qkvw;
+    if (qk_live | v_live) {
+    deg_kernel<<<dim3(L.c_in, B, (N + 31) / 32), 256, 0, st>>>(pin, s_bs, dis, d_bs, neff, N, qk_live | v_live);
     launched(K_DEG, st);
     LAUNCH_CHECK();
-    GcnArgs g;
     g.planes = pin; g.p_bs = s_bs;
     g.x = xin; g.x_bs = x_bs; g.ldx = ldx; g.f_in = L.f_in;
     g.dis = dis; g.d_bs = d_bs;
@@ -925,10 +952,14 @@ static int run_attn_net(const gdss_ctx* ctx, const NetPlan& p, const float* blob
     g.bias = blob + L.bqkv; g.b_cs = L.qkvw;
     g.out = qkv; g.o_bs = (int64_t)L.c_in * N * L.qkvw; g.o_cs = (int64_t)N * L.qkvw; g.ldo = L.qkvw;
     g.neff = neff; g.act = 0; g.N = N; g.TI = gcn_tile(N, L.f_in);
-    int rc = launch_gcn(g, L.c_in, B, st);
-    if (rc) return rc;
+    g.per_channel = 1; g.attn = L.attn; g.nhid = L.nhid; g.qk_live = qk_live; g.v_live = v_live;
+    int rc0 = launch_gcn(g, L.c_in, B, st);
+    if (rc0) return rc0;
+    }
+    int rc = 0;
     if (need_edge) {
       EdgeArgs ea;
+      ea.qk_live = qk_live;
       ea.qkv = qkv; ea.q_bs = g.o_bs; ea.q_cs = g.o_cs; ea.qkvw = L.qkvw; ea.attn = L.attn; ea.heads = p.heads;
       ea.scale = 1.0f / sqrtf((float)L.nhid);
       ea.pin = pin; ea.pin_bs = s_bs;
@@ -966,6 +997,7 @@ static int run_attn_net(const gdss_ctx* ctx, const NetPlan& p, const float* blob
       else { na.out = xs + F + l * p.nhid; na.o_bs = (int64_t)N * p.fdim; na.ldo = p.fdim; }
       na.flags = flags; na.neff = neff; na.N = N; na.cin = L.c_in; na.nhid = L.nhid; na.hid = L.hid;
       na.extra_tanh = isA ? 0 : 1;
+      na.v_live = v_live;
       size_t smem = sizeof(float) * ((size_t)L.c_in * L.nhid * L.hid + (size_t)L.hid * L.nhid + (size_t)NODE_ROWS * L.hid);
       rc = set_smem(node_kernel, smem);
       if (rc) return rc;
@@ -1027,11 +1059,12 @@ static int run_gcn_net(const gdss_ctx* ctx, const NetPlan& p, const float* blob,
   copy_x_kernel<<<dim3((N * F + 255) / 256, B), 256, 0, st>>>(x, xs, N, F, p.fdim, neff);
   launched(K_COPY, st);
   LAUNCH_CHECK();
-  deg_kernel<<<dim3(1, B, (N + 31) / 32), 256, 0, st>>>(adj, NN, dis, N, neff, N);
+  deg_kernel<<<dim3(1, B, (N + 31) / 32), 256, 0, st>>>(adj, NN, dis, N, neff, N, 1u);
   launched(K_DEG, st);
   LAUNCH_CHECK();
   for (int l = 0; l < p.depth; ++l) {
     GcnArgs g;
+    memset(&g, 0, sizeof(g));
     g.planes = adj; g.p_bs = NN;
     g.x = l == 0 ? xs : xs + F + (l - 1) * p.nhid; g.x_bs = (int64_t)N * p.fdim; g.ldx = p.fdim;
     g.f_in = l == 0 ? F : p.nhid;

@@ -1,5 +1,6 @@
 // Weight packing: reference state_dict (utils/loader.py:186-196 load_state_dict) -> one fp32 blob
 // per network with a fixed layout (gdss_internal.h NetPlan).  Host code only.
+#include <math.h>
 #include <string.h>
 
 #include "gdss_internal.h"
@@ -72,6 +73,9 @@ int plan_net(const gdss_net_desc* d, int N, NetPlan* p) {
       L.nb[1] = take(cur, L.nhid);
       nt += 4;
       chans += L.c_out;
+      L.qk_live = L.v_live = (1u << L.c_in) - 1u;
+      L.node_live = 1;
+      L.edge_const = 0;
     }
     if (p->type == GDSS_NET_A) {
       p->fdim = p->c_hid * (p->depth - 1) + p->c_final + p->c_init;
@@ -103,6 +107,82 @@ static void put_linear_t(float* dst, const float* src, int in, int out, int ld =
   if (ld <= 0) ld = out;
   for (int o = 0; o < out; ++o)
     for (int i = 0; i < in; ++i) dst[(int64_t)i * ld + o] = src[(int64_t)o * in + i];
+}
+
+// ---------------------------------------------------------------------------------------
+// Dead sub-network elimination.  The shipped checkpoints were trained with weight decay; whole weight blocks of them
+// have decayed into the fp32 denormal range (|w| ~ 1e-39: e.g. every gnn_q / gnn_k of layer 0 and the complete last
+// AttentionLayer of ScoreNetworkA in gdss_zinc250k_v2.pth).  A block below GDSS_DEAD_EPS contributes < 1e-28 to sums of
+// O(1e-2 .. 1) terms -- nothing in fp32 -- so the chain that only feeds it is not evaluated:
+//   * Q or K convolution dead (weights and bias)  -> the attention map is tanh(0) = 0 exactly (attention.py:41-49)
+//   * row c of mlp.linears.0 dead                 -> map c is never read (attention.py:109-110)
+//   * rows of multi_channel.linears.0 for V_c dead, or x_out unread downstream -> V_c is never read (attention.py:106)
+//   * every row of mlp.linears.0 dead             -> the layer's channels are the constant mlp(0) (times the flag mask)
+// Liveness of x_out is propagated from the last layer backwards (ScoreNetworkA reads x only through the next layer's
+// convolutions, ScoreNetwork_A.py:136-139; ScoreNetworkX_GMH concatenates every x, ScoreNetwork_X.py:79-84).
+// Random-init weights have no dead blocks and are evaluated in full.
+// ---------------------------------------------------------------------------------------
+#define GDSS_DEAD_EPS 1e-30f
+
+static bool block_dead(const float* w, int64_t rows, int64_t cols, int64_t ld) {
+  for (int64_t r = 0; r < rows; ++r)
+    for (int64_t c = 0; c < cols; ++c)
+      if (!(fabsf(w[r * ld + c]) < GDSS_DEAD_EPS)) return false;      // NaN counts as live
+  return true;
+}
+
+static float elu_host(float v) { return v > 0.f ? v : expm1f(v); }
+
+int analyze_liveness(NetPlan* p, const float* blob) {
+  if (!p || !blob || p->type == GDSS_NET_X) return 0;
+  const bool isA = p->type == GDSS_NET_A;
+  int off = 0;
+  bool x_needed = !isA;                      // is the x_out of the layer being visited read by a later layer / the final MLP?
+  for (int l = p->depth - 1; l >= 0; --l) {
+    LayerPlan& L = p->layers[l];
+    const bool last = l == p->depth - 1;
+    const bool need_edge = isA || !last, need_node = isA ? (!last && x_needed) : true;
+    const int C = L.c_in, h = L.nhid, A = L.attn;
+    const float* W1 = blob + L.ew[0];                       // [2C][hid]
+    L.edge_const = (need_edge && block_dead(W1, 2 * C, L.hid, L.hid)) ? 1 : 0;
+    if (L.edge_const) {
+      float hbuf[2][64], *cur = hbuf[0], *nxt = hbuf[1];
+      for (int o = 0; o < L.hid; ++o) cur[o] = elu_host(blob[L.eb[0] + o]);
+      for (int i = 1; i < L.nlin; ++i) {
+        const int out = i == L.nlin - 1 ? L.c_out : L.hid;
+        for (int o = 0; o < out; ++o) {
+          float s = blob[L.eb[i] + o];
+          for (int k = 0; k < L.hid; ++k) s = fmaf(cur[k], blob[L.ew[i] + (int64_t)k * out + o], s);
+          nxt[o] = i == L.nlin - 1 ? s : elu_host(s);
+        }
+        float* t = cur; cur = nxt; nxt = t;
+      }
+      for (int o = 0; o < L.c_out && o < GDSS_MAX_CH; ++o) L.edge_cst[o] = cur[o];
+      ++off;
+    }
+    uint32_t qk = 0, v = 0;
+    for (int c = 0; c < C; ++c) {
+      const float* Wc = blob + L.wqkv + (int64_t)c * L.f_in_p * L.qkvw;
+      const float* bc = blob + L.bqkv + (int64_t)c * L.qkvw;
+      const bool qdead = block_dead(Wc, L.f_in, A, L.qkvw) && block_dead(bc, 1, A, L.qkvw);
+      const bool kdead = block_dead(Wc + A, L.f_in, A, L.qkvw) && block_dead(bc + A, 1, A, L.qkvw);
+      const bool vdead = block_dead(Wc + 2 * A, L.f_in, h, L.qkvw) && block_dead(bc + 2 * A, 1, h, L.qkvw);
+      const bool mapdead = block_dead(W1 + (int64_t)c * L.hid, 1, L.hid, L.hid);
+      const bool vblkdead = block_dead(blob + L.nw[0] + (int64_t)c * h * L.hid, h, L.hid, L.hid);
+      if (need_edge && !L.edge_const && !qdead && !kdead && !mapdead) qk |= 1u << c;
+      if (need_node && !vdead && !vblkdead) v |= 1u << c;
+    }
+    const uint32_t all = (1u << C) - 1u;
+    const uint32_t qk_base = need_edge ? all : 0u, v_base = need_node ? all : 0u;
+    for (uint32_t m = (qk_base & ~qk) | (v_base & ~v); m; m &= m - 1) ++off;
+    L.qk_live = qk;
+    L.v_live = v;
+    L.node_live = need_node ? 1 : 0;
+    if (isA && !last && !need_node) ++off;
+    // x_{l-1} is read by this layer's convolutions only
+    x_needed = isA ? (qk != 0 || v != 0) : true;
+  }
+  return off;
 }
 
 struct Cursor {

@@ -18,14 +18,15 @@ struct NoiseSrc {
   const float* inj_x;     // [iters][dx][B][N][F] or null
   const float* inj_adj;   // [iters][da][B][N][N] or null
   int dx, da;
+  int dstride;            // Philox draw ids per step (4 unless a step has more draws: n_steps > 3 Langevin iterations)
   int first_step;
   uint64_t seed;
   int64_t graph_offset;
   int B, N, F;
 };
 
-// Philox draw id: the prior uses 0/1, step s draw d uses 4*(s+1)+d
-DEVINL uint32_t draw_id(int step, int d) { return (uint32_t)(4 * (step + 1) + d); }
+// Philox draw id: the prior uses 0/1, step s draw d uses dstride*(s+1)+d  (dstride = 4 for every shipped configuration)
+DEVINL uint32_t draw_id(const NoiseSrc& ns, int step, int d) { return (uint32_t)(ns.dstride * (step + 1) + d); }
 
 // four raw N(0,1) for node-feature elements (i, 4*g .. 4*g+3) of graph b
 DEVINL float4 noise_x4(const NoiseSrc& ns, int b, int step, int d, int i, int g) {
@@ -40,7 +41,7 @@ DEVINL float4 noise_x4(const NoiseSrc& ns, int b, int step, int d, int i, int g)
     return z;
   }
   const int gw = (ns.F + 3) >> 2;
-  return philox_normal4(ns.seed, (uint64_t)(ns.graph_offset + b), draw_id(step, d), 0u, (uint32_t)(i * gw + g));
+  return philox_normal4(ns.seed, (uint64_t)(ns.graph_offset + b), draw_id(ns, step, d), 0u, (uint32_t)(i * gw + g));
 }
 
 // four raw N(0,1) for adjacency elements (i, 4*g .. 4*g+3); only j > i is ever used
@@ -57,7 +58,7 @@ DEVINL float4 noise_a4(const NoiseSrc& ns, int b, int step, int d, int i, int g)
     return z;
   }
   const int gw = (ns.N + 3) >> 2;
-  return philox_normal4(ns.seed, (uint64_t)(ns.graph_offset + b), draw_id(step, d), 1u, (uint32_t)(i * gw + g));
+  return philox_normal4(ns.seed, (uint64_t)(ns.graph_offset + b), draw_id(ns, step, d), 1u, (uint32_t)(i * gw + g));
 }
 
 // ---------------------------------------------------------------------------------------
@@ -102,7 +103,8 @@ __global__ void __launch_bounds__(256) prior_kernel(NoiseSrc ns, float* __restri
 __global__ void __launch_bounds__(256) norms_kernel(NoiseSrc ns, const float* __restrict__ raw_x,
                                                     const float* __restrict__ raw_adj, const float* __restrict__ flags,
                                                     const int* __restrict__ neff, const gdss_step_coef* __restrict__ table,
-                                                    const int* __restrict__ step_ptr, float* __restrict__ norms) {
+                                                    const int* __restrict__ step_ptr, float* __restrict__ norms, int cd) {
+  // cd: draw index of this corrector iteration (0 unless n_steps > 1)
   __shared__ float red[33];
   const int b = blockIdx.x, N = ns.N, F = ns.F, n = neff[b];
   const int step = *step_ptr;
@@ -114,7 +116,7 @@ __global__ void __launch_bounds__(256) norms_kernel(NoiseSrc ns, const float* __
   float sx = 0.f, zx = 0.f, sa = 0.f, za = 0.f;
   for (int idx = threadIdx.x; idx < n * gwx; idx += 256) {
     int i = idx / gwx, g = idx - i * gwx;
-    float4 z = noise_x4(ns, b, step, 0, i, g);
+    float4 z = noise_x4(ns, b, step, cd, i, g);
     float f = fl[i];
 #pragma unroll
     for (int q = 0; q < 4; ++q)
@@ -127,7 +129,7 @@ __global__ void __launch_bounds__(256) norms_kernel(NoiseSrc ns, const float* __
   for (int idx = threadIdx.x; idx < n * gwa; idx += 256) {
     int i = idx / gwa, g = idx - i * gwa;
     if (4 * g + 3 <= i || 4 * g >= n) continue;
-    float4 z = noise_a4(ns, b, step, 0, i, g);
+    float4 z = noise_a4(ns, b, step, cd, i, g);
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       int j = 4 * g + q;
@@ -181,7 +183,8 @@ struct UpdateArgs {
   const gdss_step_coef* table; const int* step_ptr;
   const float* sums; float inv_gb;
   float* trace;          // [iters][8] or null
-  int pred_draw;         // draw index of the predictor noise (1 after a corrector, else 0)
+  int pred_draw;         // draw index of the predictor noise (n_steps after a corrector, else 0)
+  int corr_draw;         // draw index of this Langevin iteration (0 .. n_steps-1)
 };
 
 // ---------------------------------------------------------------------------------------
@@ -232,7 +235,7 @@ __global__ void __launch_bounds__(256) update_kernel(UpdateArgs a) {
       int i = idx / gwx, g = idx - i * gwx;
       const float f = fl[i];
       float4 z0, z1, z2;
-      if (MODE == MODE_CORR) z0 = noise_x4(ns, b, step, 0, i, g);
+      if (MODE == MODE_CORR) z0 = noise_x4(ns, b, step, a.corr_draw, i, g);
       if (MODE == MODE_PRED) z0 = noise_x4(ns, b, step, a.pred_draw, i, g);
       if (MODE == MODE_S4) {
         z0 = noise_x4(ns, b, step, 0, i, g);
@@ -272,7 +275,7 @@ __global__ void __launch_bounds__(256) update_kernel(UpdateArgs a) {
       if (4 * g + 3 < i + dg || 4 * g >= n) continue;
       const float fi = fl[i];
       float4 z0, z1, z2;
-      if (MODE == MODE_CORR) z0 = noise_a4(ns, b, step, 0, i, g);
+      if (MODE == MODE_CORR) z0 = noise_a4(ns, b, step, a.corr_draw, i, g);
       if (MODE == MODE_PRED) z0 = noise_a4(ns, b, step, a.pred_draw, i, g);
       if (MODE == MODE_S4) {
         z0 = noise_a4(ns, b, step, 0, i, g);
@@ -324,6 +327,8 @@ struct StepPlan {
   float* sums;
   int* step_ptr;
   void* comm;
+  int n_steps;           // Langevin iterations per step (solver.py:126, :138)
+  float* x0; float* a0;  // n_steps > 1: the state the corrector phase started from
 };
 
 static int enqueue_step(const StepPlan& p, cudaStream_t st) {
@@ -338,32 +343,55 @@ static int enqueue_step(const StepPlan& p, cudaStream_t st) {
   int chunks = (work + 255) / 256;
   if (chunks > 64) chunks = 64;
   dim3 ugrid(chunks, B);
-  int rc = launch_eval(p.ctx, u.x, u.adj, u.flags, u.neff, raw_x, raw_a, B, p.ws, p.w, st, !p.ctx->fused);
-  if (rc) return rc;
-  if (p.s4 || p.langevin) {
-    norms_kernel<<<B, 256, 0, st>>>(u.ns, raw_x, raw_a, u.flags, u.neff, u.table, u.step_ptr, p.norms);
+  int rc = 0;
+  // per-graph norms -> batch sums (-> all-reduce over the ranks) of the scores in raw_x / raw_a and of corrector draw cd
+  auto norm_means = [&](int cd) -> int {
+    norms_kernel<<<B, 256, 0, st>>>(u.ns, raw_x, raw_a, u.flags, u.neff, u.table, u.step_ptr, p.norms, cd);
     launched(K_NORMS, st);
     LAUNCH_CHECK();
     sums_kernel<<<1, 1024, 0, st>>>(p.norms, B, p.sums);
     launched(K_SUMS, st);
     LAUNCH_CHECK();
-    if (p.comm) {
-      rc = nccl_allreduce_sum(p.comm, p.sums, 4, st);
-      if (rc) return rc;
-    }
-  }
+    if (p.comm) return nccl_allreduce_sum(p.comm, p.sums, 4, st);
+    return 0;
+  };
   if (p.s4) {
+    rc = launch_eval(p.ctx, u.x, u.adj, u.flags, u.neff, raw_x, raw_a, B, p.ws, p.w, st, !p.ctx->fused);
+    if (rc) return rc;
+    rc = norm_means(0);
+    if (rc) return rc;
     update_kernel<MODE_S4><<<ugrid, 256, 0, st>>>(u);
     launched(K_UPDATE, st);
     LAUNCH_CHECK();
   } else {
     if (p.langevin) {
-      update_kernel<MODE_CORR><<<ugrid, 256, 0, st>>>(u);
-      launched(K_UPDATE, st);
-      LAUNCH_CHECK();
-      rc = launch_eval(p.ctx, u.x, u.adj, u.flags, u.neff, raw_x, raw_a, B, p.ws, p.w, st, !p.ctx->fused);
-      if (rc) return rc;
+      const int K = p.n_steps;
+      if (K > 1) {
+        // solver.py:187-189: the x corrector iterates on (x_k, adj_0), the adjacency corrector on (x_0, adj_k)
+        cudaError_t e = cudaMemcpyAsync(p.x0, u.x, sizeof(float) * (size_t)B * N * F, cudaMemcpyDeviceToDevice, st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(p.a0, u.adj, sizeof(float) * (size_t)B * N * N, cudaMemcpyDeviceToDevice, st);
+        if (e != cudaSuccess) return (int)e;
+      }
+      for (int k = 0; k < K; ++k) {
+        if (k == 0) {
+          rc = launch_eval(p.ctx, u.x, u.adj, u.flags, u.neff, raw_x, raw_a, B, p.ws, p.w, st, !p.ctx->fused);
+        } else {
+          rc = launch_eval(p.ctx, u.x, p.a0, u.flags, u.neff, raw_x, nullptr, B, p.ws, p.w, st, !p.ctx->fused);
+          if (rc) return rc;
+          rc = launch_eval(p.ctx, p.x0, u.adj, u.flags, u.neff, nullptr, raw_a, B, p.ws, p.w, st, !p.ctx->fused);
+        }
+        if (rc) return rc;
+        rc = norm_means(k);
+        if (rc) return rc;
+        UpdateArgs uk = u;
+        uk.corr_draw = k;
+        update_kernel<MODE_CORR><<<ugrid, 256, 0, st>>>(uk);
+        launched(K_UPDATE, st);
+        LAUNCH_CHECK();
+      }
     }
+    rc = launch_eval(p.ctx, u.x, u.adj, u.flags, u.neff, raw_x, raw_a, B, p.ws, p.w, st, !p.ctx->fused);
+    if (rc) return rc;
     update_kernel<MODE_PRED><<<ugrid, 256, 0, st>>>(u);
     launched(K_UPDATE, st);
     LAUNCH_CHECK();
@@ -386,7 +414,7 @@ extern "C" int gdss_sample(gdss_ctx* ctx, const gdss_sampler_desc* s, const gdss
   if (!ctx || !s || !table || !x || !adj || !flags || !x_mean || !adj_mean || !workspace) return GDSS_E_BADARG;
   if (B <= 0 || n_iters < 0 || first_step < 0 || first_step + n_iters > GDSS_MAX_STEPS) return GDSS_E_BADARG;
   if (!ctx->has_x || !ctx->has_a) return GDSS_E_BADARG;
-  if (s->n_steps != 1 || s->probability_flow != 0) return GDSS_E_UNSUPPORTED;
+  if (s->n_steps < 1 || s->n_steps > 64) return GDSS_E_BADARG;     // (probability_flow lives in the table: pb halved, pc = 0)
   if (!nccl_comm && global_B != B) return GDSS_E_BADARG;
   if (init_prior && (inj_x || inj_adj)) return GDSS_E_BADARG;   // an injected run supplies its own prior
   if (global_B < B) return GDSS_E_BADARG;
@@ -412,12 +440,16 @@ extern "C" int gdss_sample(gdss_ctx* ctx, const gdss_sampler_desc* s, const gdss
   p.sums = reinterpret_cast<float*>(ws + w.off[R_MEANS]);
   p.step_ptr = reinterpret_cast<int*>(ws + w.off[R_STEP]);
   p.comm = nccl_comm;
+  p.n_steps = langevin ? s->n_steps : 1;
+  p.x0 = reinterpret_cast<float*>(ws + w.off[R_X0]);
+  p.a0 = reinterpret_cast<float*>(ws + w.off[R_A0]);
   int* neff = reinterpret_cast<int*>(ws + w.off[R_NEFF]);
   gdss_step_coef* dtable = reinterpret_cast<gdss_step_coef*>(ws + w.off[R_TABLE]);
   UpdateArgs& u = p.ua;
   u.ns.inj_x = inj_x;
   u.ns.inj_adj = inj_adj;
-  u.ns.dx = u.ns.da = s4 ? 3 : (langevin ? 2 : 1);
+  u.ns.dx = u.ns.da = s4 ? 3 : (langevin ? p.n_steps + 1 : 1);
+  u.ns.dstride = u.ns.dx > 4 ? u.ns.dx : 4;
   u.ns.first_step = first_step;
   u.ns.seed = seed;
   u.ns.graph_offset = graph_offset;
@@ -431,7 +463,8 @@ extern "C" int gdss_sample(gdss_ctx* ctx, const gdss_sampler_desc* s, const gdss
   u.table = dtable; u.step_ptr = p.step_ptr;
   u.sums = p.sums; u.inv_gb = 1.0f / (float)global_B;
   u.trace = trace;
-  u.pred_draw = langevin ? 1 : 0;
+  u.pred_draw = langevin ? p.n_steps : 0;
+  u.corr_draw = 0;
 
   cudaError_t e;
   e = cudaMemcpyAsync(dtable, table, sizeof(gdss_step_coef) * (size_t)(first_step + n_iters), cudaMemcpyHostToDevice, st);

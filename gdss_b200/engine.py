@@ -57,12 +57,52 @@ def describe_network(sd, n_nodes):
     return d
 
 
-def pack_network(sd, n_nodes, desc=None):
-    """-> (NetDesc, host blob float32 tensor) via gdss_pack_weights."""
+def state_keys(desc):
+    """The state_dict keys of a network in the order gdss_pack_weights consumes them (key grammar: SURVEY.md 8b,
+    models/ScoreNetwork_X.py:17-30, models/attention.py:77-91, models/layers.py:96-133)."""
+    keys = []
+    if desc.model_type == _lib.NET_X:
+        for l in range(desc.depth):
+            keys += [f"layers.{l}.weight", f"layers.{l}.bias"]
+    else:
+        for l in range(desc.depth):
+            c_in = desc.c_init if l == 0 else desc.c_hid
+            for c in range(c_in):
+                for m in "qkv":
+                    keys += [f"layers.{l}.attn.{c}.gnn_{m}.weight", f"layers.{l}.attn.{c}.gnn_{m}.bias"]
+            for i in range(desc.num_linears):
+                keys += [f"layers.{l}.mlp.linears.{i}.weight", f"layers.{l}.mlp.linears.{i}.bias"]
+            for i in range(2):
+                keys += [f"layers.{l}.multi_channel.linears.{i}.weight", f"layers.{l}.multi_channel.linears.{i}.bias"]
+    for i in range(3):
+        keys += [f"final.linears.{i}.weight", f"final.linears.{i}.bias"]
+    return keys
+
+
+def pack_network(sd, n_nodes, desc=None, model=None):
+    """-> (NetDesc, host blob float32 tensor) via gdss_pack_weights.  Tensors are looked up BY KEY (a sorted, filtered
+    or rebuilt state_dict packs correctly or fails loudly); ``num_heads`` is read from the module when it has one and
+    anything but 4 is rejected (the kernels are built for the 4 heads of every shipped config)."""
     L = lib()
     sd = _strip(sd)
     desc = desc or describe_network(sd, n_nodes)
-    tensors = [v.detach().to("cpu", torch.float32).contiguous() for v in sd.values()]
+    heads = None
+    if model is not None and not isinstance(model, dict):
+        m = model.module if hasattr(model, "module") and hasattr(model.module, "state_dict") else model
+        heads = getattr(m, "num_heads", None)
+        if heads is None:
+            try:
+                heads = m.layers[0].attn[0].num_heads
+            except Exception:
+                heads = None
+    if heads is not None and int(heads) != 4:
+        raise _lib.GdssError(f"num_heads={heads} is not supported (the kernels are built for num_heads=4)")
+    keys = state_keys(desc)
+    missing = [k for k in keys if k not in sd]
+    extra = [k for k in sd if k not in set(keys)]
+    if missing or extra:
+        raise _lib.GdssError(f"state_dict does not match the network description: missing {missing[:3]}, unexpected {extra[:3]}")
+    tensors = [sd[k].detach().to("cpu", torch.float32).contiguous() for k in keys]
     n = len(tensors)
     total = L.gdss_packed_floats(C.byref(desc), n_nodes)
     if total < 0:
@@ -88,10 +128,10 @@ class Engine:
         self.blob_x = self.blob_a = None
         with torch.cuda.device(self.device):
             if model_x is not None:
-                self.desc_x, hb = pack_network(model_state(model_x), self.N)
+                self.desc_x, hb = pack_network(model_state(model_x), self.N, model=model_x)
                 self.blob_x = hb.to(self.device)
             if model_adj is not None:
-                self.desc_a, hb = pack_network(model_state(model_adj), self.N)
+                self.desc_a, hb = pack_network(model_state(model_adj), self.N, model=model_adj)
                 self.blob_a = hb.to(self.device)
                 if self.desc_a.model_type != _lib.NET_A:
                     raise ValueError("model_adj must be a ScoreNetworkA")

@@ -12,6 +12,11 @@ def _prep(t):
     return t.to(torch.float32).contiguous()
 
 
+def _fresh_seed():
+    """New 64-bit Philox seed per call from torch's default generator (see gdss_b200.solver.fresh_seed)."""
+    return int(torch.randint(0, 2 ** 62, (1,), dtype=torch.int64).item())
+
+
 def _stream(t):
     return torch.cuda.current_stream(t.device).cuda_stream
 
@@ -49,8 +54,9 @@ def gen_noise(x, flags, sym=True, raw=None, seed=None, draw_id=0, graph_offset=0
     out = torch.empty_like(x)
     B, N = x.shape[0], x.shape[1]
     F = 0 if sym else x.shape[2]
-    seed = torch.initial_seed() if seed is None else seed
-    rawp = _prep(raw).data_ptr() if raw is not None else None
+    seed = _fresh_seed() if seed is None else seed          # a new stream per call, like torch.randn_like in the reference
+    raw_t = _prep(raw) if raw is not None else None         # kept alive across the call
+    rawp = raw_t.data_ptr() if raw_t is not None else None
     with torch.cuda.device(x.device):
         check(lib().gdss_gen_noise(out.data_ptr(), rawp, flags.data_ptr(), B, N, F, int(bool(sym)),
                                    int(seed) & (2 ** 64 - 1), int(draw_id), int(graph_offset), _stream(x)), "gdss_gen_noise")
@@ -113,7 +119,7 @@ def init_flags_device(node_counts, max_node_num, batch_size, device="cuda", seed
     hist = np.bincount(np.clip(np.asarray(list(node_counts), dtype=np.int64), 0, N), minlength=N + 1).astype(np.float64)
     cdf = torch.from_numpy(np.cumsum(hist).astype(np.float32)).to(device)
     flags = torch.empty(int(batch_size), N, device=device)
-    seed = torch.initial_seed() if seed is None else seed
+    seed = _fresh_seed() if seed is None else seed
     with torch.cuda.device(flags.device):
         check(lib().gdss_init_flags(cdf.data_ptr(), flags.data_ptr(), int(batch_size), N, int(seed) & (2 ** 64 - 1),
                                     int(graph_offset), _stream(flags)), "gdss_init_flags")

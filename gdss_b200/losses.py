@@ -67,9 +67,10 @@ def get_sde_loss_fn(sde_x, sde_adj, train=True, reduce_mean=False, continuous=Tr
                 nfl = int(L.gdss_dsm_scratch_floats(eng.ctx, B))
                 scratch = torch.empty(nfl, device=dev)
                 out = torch.empty(2, device=dev)
+                rx = raw_x.to(dev, torch.float32).contiguous()          # bound to locals: alive across the call
+                ra = raw_adj.to(dev, torch.float32).contiguous()
                 check(L.gdss_dsm_loss(eng.ctx, x.data_ptr(), adj.data_ptr(), coef.data_ptr(),
-                                      raw_x.to(dev, torch.float32).contiguous().data_ptr(),
-                                      raw_adj.to(dev, torch.float32).contiguous().data_ptr(), B, int(bool(reduce_mean)),
+                                      rx.data_ptr(), ra.data_ptr(), B, int(bool(reduce_mean)),
                                       scratch.data_ptr(), nfl, out.data_ptr(), ws.data_ptr(), need,
                                       torch.cuda.current_stream(dev).cuda_stream), "gdss_dsm_loss")
         return out[0], out[1]

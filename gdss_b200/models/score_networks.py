@@ -60,8 +60,10 @@ class _CudaScoreNet(nn.Module):
     _is_adj = False
 
     def _engine(self, n_nodes, device):
-        ver = tuple(int(p._version) for p in self.parameters())
-        key = (int(n_nodes), str(device), ver)
+        # validated by a content fingerprint: in-place writes that do not bump ``_version`` (``param.data.copy_`` in
+        # utils/ema.py:46, :71) must re-pack the weights too
+        from ..solver import _fingerprint
+        key = (int(n_nodes), str(device), _fingerprint(self))
         if getattr(self, "_eng_key", None) != key:
             self._eng = Engine(None, self, n_nodes, device) if self._is_adj else Engine(self, None, n_nodes, device)
             self._eng_key = key

@@ -87,8 +87,7 @@ def build_table(sde_x, sde_adj, predictor, corrector, snr, scale_eps, eps, proba
 
     predictor in {'Euler', 'Reverse', 'S4'}; anything else maps to Euler, any corrector other than
     'Langevin' to none (solver.py:163-164)."""
-    if probability_flow:
-        raise NotImplementedError("probability_flow=True is not built (no shipped config uses it)")
+    pf = 0.5 if (probability_flow and predictor != "S4") else 1.0        # sde.py:89-91, :98-99 (S4 never builds an RSDE)
     sx, sa = _Scalars(sde_x), _Scalars(sde_adj)
     steps = sa.N
     ts = torch.linspace(1, eps, steps)                                   # solver.py:180, :218
@@ -121,12 +120,12 @@ def build_table(sde_x, sde_adj, predictor, corrector, snr, scale_eps, eps, proba
             elif predictor == "Reverse":
                 fc, G = sd.reverse_step(t)                               # solver.py:72-86, sde.py:94-100
                 row[COL["pa"] + d] = float(1.0 - fc)
-                row[COL["pb"] + d] = float(G ** 2 * cs)
-                row[COL["pc"] + d] = float(G)
+                row[COL["pb"] + d] = float(G ** 2 * cs * pf)
+                row[COL["pc"] + d] = float(G) if pf == 1.0 else 0.0      # rev_G = 0 for the probability-flow ODE
             else:
                 dt = -1. / sd.N                                          # solver.py:45-61, sde.py:85-92
                 g = sd.diffusion(t)
                 row[COL["pa"] + d] = float(1.0 + sd.drift_coeff(t) * dt)
-                row[COL["pb"] + d] = float(-(g ** 2) * cs * dt)
-                row[COL["pc"] + d] = float(g * np.sqrt(-dt))
+                row[COL["pb"] + d] = float(-(g ** 2) * cs * dt * pf)
+                row[COL["pc"] + d] = float(g * np.sqrt(-dt)) if pf == 1.0 else 0.0
     return tab

@@ -45,6 +45,18 @@ SHORT_CASES = [
     _case("community_rev_none_nodenoise_n10", "community_small", ("VP", .1, 1.), ("VE", .2, 1.), "Reverse", "None", .05, .7, 10, 3, 108, denoise=False),
     _case("enzymes_s4_n6", "enzymes", ("VP", .1, 1.), ("VE", .2, 1.), "S4", "None", .15, .7, 6, 3, 109, ema=True),
     _case("grid_rev_lang_n3", "grid", ("VP", .1, 1.), ("VP", .2, .8), "Reverse", "Langevin", .1, .7, 3, 1, 110, ema=True),
+    # probability-flow ODE (sde.py:98-99): reverse drift halved, no predictor noise (the draws are still consumed).  Only the
+    # Reverse predictor exists with it: EulerMaruyamaPredictor + probability_flow raises in the reference (solver.py:52
+    # indexes the float 0. that sde.py:91 returns as the diffusion)
+    _case("community_rev_none_pf_n10", "community_small", ("VP", .1, 1.), ("VE", .2, 1.), "Reverse", "None", .0, .0, 10, 4, 111,
+          probability_flow=True),
+    _case("qm9_rev_lang_pf_n10", "qm9", ("VE", .1, 1.), ("VE", .1, 1.), "Reverse", "Langevin", .2, .7, 10, 4, 112,
+          probability_flow=True),
+    # Langevin corrector with n_steps = 2 inner iterations (solver.py:126-147): the x corrector iterates on (x_k, adj), then
+    # the adjacency corrector on (x_0, adj_k)
+    _case("qm9_rev_lang_ns2_n10", "qm9", ("VE", .1, 1.), ("VE", .1, 1.), "Reverse", "Langevin", .2, .7, 10, 4, 113, n_steps=2),
+    _case("community_euler_lang_ns3_n8", "community_small", ("VP", .1, 1.), ("VP", .1, 1.), "Euler", "Langevin", .05, .7, 8, 3,
+          114, n_steps=3),
 ]
 
 # Full 1000-scale runs (the BASELINE.json configurations at a small batch).
@@ -53,6 +65,10 @@ FULL_CASES = [
     _case("qm9_rev_lang_full", "qm9", ("VE", .1, 1.), ("VE", .1, 1.), "Reverse", "Langevin", .2, .7, 1000, 4, 202),
     _case("community_euler_lang_full", "community_small", ("VP", .1, 1.), ("VP", .1, 1.), "Euler", "Langevin", .05, .7, 1000, 3, 203),
     _case("zinc_v2_rev_lang_full", "zinc250k_v2", ("VP", .1, 1.), ("VE", .2, 1.), "Reverse", "Langevin", .2, .8, 1000, 2, 204),
+    # larger batches for the bit-exact thresholded-output claim (32 molecules each) and a full-length C4 run
+    _case("qm9_s4_full_b32", "qm9", ("VE", .1, 1.), ("VE", .1, 1.), "S4", "None", .2, .7, 1000, 32, 205),
+    _case("zinc_v2_rev_lang_full_b32", "zinc250k_v2", ("VP", .1, 1.), ("VE", .2, 1.), "Reverse", "Langevin", .2, .8, 1000, 32, 206),
+    _case("enzymes_s4_full_b4", "enzymes", ("VP", .1, 1.), ("VE", .2, 1.), "S4", "None", .15, .7, 1000, 4, 207, ema=True),
 ]
 
 ALL_CASES = {c["name"]: c for c in SHORT_CASES + FULL_CASES}
