@@ -8,7 +8,10 @@ evaluations of both score networks, noise, norms, updates) over the whole batch;
 sample, so   value [graphs/s] = batch / (1000 * seconds_per_step).
 Every step costs the same (the work is data independent), so K steps measure the full run's rate.
 
-  value     inputs resident in HBM, K steps replayed from one captured CUDA graph, CUDA-event timed.
+  value     inputs resident in HBM, K steps replayed from one captured CUDA graph, CUDA-event timed; the K-step region is
+            repeated --repeats times (default 5) and the MEDIAN is reported (min / max beside it).
+  scaling   "strong" by default = BASELINE.json config 3 (the batch of 10 000 SHARDED over the N GPUs); the weak-scaling
+            rate (10 000 graphs per GPU) is measured in the same run and reported as `weak_scaling`.
   e2e       the public sampler API (get_pc_sampler / S4_solver closure) called with HOST flags; the timed
             region holds the H2D copy, the on-device prior, K steps and the D2H copy of (x, adj).
   roofline  the dominant kernel (per-kernel CUDA-event timing of eager launches, gdss_prof_*).
@@ -64,7 +67,10 @@ def make_flags(wl, B, mode):
     elif wl["ckpt"] == "qm9":
         counts = rs.choice([9, 8, 7, 6, 5], size=B, p=[.83, .14, .025, .004, .001])
     else:
-        counts = rs.randint(max(2, N // 2), N + 1, size=B)
+        # node counts of the training graphs (data/<name>.pkl, committed as tests/golden/node_counts.json), drawn like
+        # init_flags does (utils/graph_utils.py:66-74: a uniformly drawn training graph)
+        hist = json.load(open(os.path.join(ROOT, "tests", "golden", "node_counts.json")))[wl["ckpt"]]["node_counts"]
+        counts = np.minimum(np.asarray(hist)[rs.randint(0, len(hist), size=B)], N)
     flags = torch.zeros(B, N)
     for b, c in enumerate(counts):
         flags[b, :c] = 1.0
@@ -72,13 +78,14 @@ def make_flags(wl, B, mode):
 
 
 def load_weights(wl):
-    from oracle.cases import load_golden_ckpt     # fixture loader only (plain torch.load of tests/golden/ckpt)
-    ck = load_golden_ckpt(wl["ckpt"])
-    sdx, sda = ck["x_state_dict"], ck["adj_state_dict"]
-    if wl.get("ema"):
-        sdx = {k: s for k, s in zip(sdx.keys(), ck["ema_x"]["shadow_params"])}
-        sda = {k: s for k, s in zip(sda.keys(), ck["ema_adj"]["shadow_params"])}
-    return sdx, ck["params_x"], sda, ck["params_adj"]
+    from gdss_b200.ckpt import load_ckpt, sampling_weights      # plain torch.load of tests/golden/ckpt (+ EMA, sampler.py:47-52)
+    return sampling_weights(load_ckpt(wl["ckpt"]), use_ema=bool(wl.get("ema")))
+
+
+def sde_from(spec, scales):
+    from gdss_b200.sde import VPSDE, VESDE, subVPSDE
+    kind, lo, hi = spec
+    return {"VP": VPSDE, "VE": VESDE, "subVP": subVPSDE}[kind](lo, hi, scales)
 
 
 class ClockSampler:
@@ -223,7 +230,9 @@ def workload_config(args, wl, B):
             "flags": args.flags, "solver_steps_per_sample": 1000,
             "step": "one reverse-diffusion solver step over the whole batch", "l2": "inputs larger than L2 (per-step working "
             "set = edge-channel stacks >> 126 MB at B=10000)" if B * wl["N"] ** 2 * 46 * 4 > 126e6 else "working set fits L2",
-            "weights": "shipped checkpoint (tests/golden/ckpt)", "noise": "in-kernel Philox4x32-10, seed 42"}
+            "weights": "shipped checkpoint (tests/golden/ckpt); dead weight blocks (|w| < 1e-30, the checkpoint's weight-decayed "
+                       "sub-networks) are not evaluated -- `extra.no_dead_chain_elimination` is the same run with every chain evaluated",
+            "noise": "in-kernel Philox4x32-10, seed 42"}
 
 
 def main():
@@ -236,9 +245,11 @@ def main():
     ap.add_argument("--batch", type=int, default=0)
     ap.add_argument("--cpu-batch", type=int, default=0)
     ap.add_argument("--flags", default="ragged", choices=["ragged", "full"])
-    ap.add_argument("--scaling", default="weak", choices=["strong", "weak"],
-                    help="weak (default): the BASELINE batch per GPU, independent graphs sharded over the ranks; strong: the "
-                         "BASELINE batch in total")
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
+                    help="strong (default, BASELINE.json config 3): the BASELINE batch in total, sharded over the ranks; weak: the "
+                         "BASELINE batch per GPU.  At N > 1 the other mode is measured too and reported as an extra key")
+    ap.add_argument("--repeats", type=int, default=5, help="timed K-step regions; the median is reported")
+    ap.add_argument("--no-extra", action="store_true", help="skip the extra lines (flags=full, no-prune, C1 / C2 / C4 workloads)")
     ap.add_argument("--precision", default="fp32", choices=["fp32", "tf32"],
                     help="fp32 (default, the parity build: 3xTF32 split, <= 1e-4) or tf32 (libgdss_b200_tf32.so: single-pass "
                          "TF32, <= 3e-2; a reduced-precision line, never the headline)")
@@ -260,30 +271,14 @@ def main():
     from gdss_b200.engine import Engine, make_sampler_desc
     from gdss_b200.schedule import build_table
     from gdss_b200.solver import get_pc_sampler, S4_solver
-    from tests.gpu_common import sde_from
     import torch.distributed as dist
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py (impl ours) needs a CUDA device: the GDSS kernels have no CPU fallback")
     shard, dev = init_from_env()
     world, rank = shard.world, shard.rank
-    sdx, px, sda, pa = weights
-    N, F = wl["N"], wl["F"]
-    B = args.batch or wl["B"]
-    if args.scaling == "weak":
-        B = B * world
-    flags, counts = make_flags(wl, B, args.flags)
-    lo, hi = shard.bounds(B)
-    K, W = args.steps, max(args.warmup, 0)
-    sx, sa = sde_from(wl["sde_x"], 1000), sde_from(wl["sde_adj"], 1000)
-    table = build_table(sx, sa, wl["predictor"], wl["corrector"], wl["snr"], wl["scale_eps"], 1e-4)
-    while table.shape[0] < W + K:                       # K beyond one sample: keep stepping with the same rows
-        table = np.concatenate([table, table[-1000:]])
-    sdesc = make_sampler_desc(sx, sa, wl["predictor"], wl["corrector"], wl["snr"], wl["scale_eps"], 1e-4, 1, False, True)
-    eng = Engine(sdx, sda, N, dev)
     L = _lib.lib()
-    fl_local = flags[lo:hi].to(dev)
-    kw = dict(seed=42, graph_offset=lo, global_B=B, comm=shard.comm, use_graph=True)
+    K, W, R = args.steps, max(args.warmup, 0), max(args.repeats, 1)
 
     def barrier():
         torch.cuda.synchronize(dev)
@@ -291,33 +286,74 @@ def main():
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    # ---- burn-in (untimed, before the W warm-up steps): clocks out of idle, allocator / module loading / L2 settled
-    x, adj, xm, am = eng.sample(sdesc, table, fl_local, n_iters=args.burn_in, **kw)
-    barrier()
-    # ---- warm-up: W untimed steps from the prior
-    x, adj, xm, am = eng.sample(sdesc, table, fl_local, n_iters=max(W, 1), **kw)
-    barrier()
+    def max_over_ranks(v):
+        t = torch.tensor([v], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t)
+
+    def setup(wl_, weights_, B_total, flag_mode, env=None):
+        """Engine + schedule + this rank's shard of the flags for a workload at a global batch."""
+        sdx_, _, sda_, _ = weights_
+        flags_, counts_ = make_flags(wl_, B_total, flag_mode)
+        lo_, hi_ = shard.bounds(B_total)
+        sx_, sa_ = sde_from(wl_["sde_x"], 1000), sde_from(wl_["sde_adj"], 1000)
+        table_ = build_table(sx_, sa_, wl_["predictor"], wl_["corrector"], wl_["snr"], wl_["scale_eps"], 1e-4)
+        while table_.shape[0] < W + K + 1:              # K beyond one sample: keep stepping with the same rows
+            table_ = np.concatenate([table_, table_[-1000:]])
+        sdesc_ = make_sampler_desc(sx_, sa_, wl_["predictor"], wl_["corrector"], wl_["snr"], wl_["scale_eps"], 1e-4, 1, False, True)
+        old = {k: os.environ.get(k) for k in (env or {})}
+        os.environ.update(env or {})
+        try:
+            eng_ = Engine(sdx_, sda_, wl_["N"], dev)
+        finally:
+            for k, v in old.items():
+                os.environ.pop(k, None) if v is None else os.environ.__setitem__(k, v)
+        kw_ = dict(seed=42, graph_offset=lo_, global_B=B_total, comm=shard.comm, use_graph=True)
+        return dict(eng=eng_, table=table_, sdesc=sdesc_, flags=flags_, counts=counts_, lo=lo_, hi=hi_, fl=flags_[lo_:hi_].to(dev),
+                    kw=kw_, sx=sx_, sa=sa_, B=B_total)
+
+    def timed(S, burn, repeats):
+        """burn untimed steps, W warm-up steps, then `repeats` regions of EXACTLY K steps each: barrier + synchronize on both
+        sides, CUDA events on the launching stream, max over the ranks per region -> list of ms per region."""
+        eng_ = S["eng"]
+        st = eng_.sample(S["sdesc"], S["table"], S["fl"], n_iters=burn, **S["kw"])
+        barrier()
+        st = eng_.sample(S["sdesc"], S["table"], S["fl"], n_iters=max(W, 1), **S["kw"])
+        barrier()
+        out, own = [], []
+        before_ = L.gdss_launch_count()
+        for _ in range(repeats):
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record()
+            st = eng_.sample(S["sdesc"], S["table"], S["fl"], x=st[0], adj=st[1], first_step=max(W, 1), n_iters=K, **S["kw"])
+            ev1.record()
+            barrier()
+            own.append(ev0.elapsed_time(ev1))
+            out.append(max_over_ranks(own[-1]))
+        return out, own, st, (L.gdss_launch_count() - before_) // repeats
+
+    def rate(S, ms):
+        return S["B"] / (1000.0 * (ms / K) * 1e-3)
+
+    sdx, px, sda, pa = weights
+    N, F = wl["N"], wl["F"]
+    B = (args.batch or wl["B"]) * (world if args.scaling == "weak" else 1)
+    S = setup(wl, weights, B, args.flags)
+    lo, hi, counts, flags = S["lo"], S["hi"], S["counts"], S["flags"]
+    eng, table, sdesc, fl_local, sx, sa = S["eng"], S["table"], S["sdesc"], S["fl"], S["sx"], S["sa"]
     clocks = ClockSampler(dev.index if dev.index is not None else 0, world) if rank == 0 else None
-    before = L.gdss_launch_count()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record()
-    x, adj, xm, am = eng.sample(sdesc, table, fl_local, x=x, adj=adj, first_step=max(W, 1), n_iters=K, **kw)
-    ev1.record()
-    barrier()
-    launches = L.gdss_launch_count() - before
-    ms_own = ev0.elapsed_time(ev1)
-    ms = torch.tensor([ms_own], device=dev)
-    if world > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    ms_total = float(ms)
+    times, own, (x, adj, xm, am), launches = timed(S, args.burn_in, R)
     clk = clocks.stop() if clocks is not None else {}
+    ms_total = float(np.median(times))
     if world > 1:
-        # spread of the ranks' own device times (the per-phase all-reduce makes every rank wait for the slowest GPU of the box)
-        lo_t = torch.tensor([ms_own], device=dev)
+        lo_t = torch.tensor([float(np.median(own))], device=dev)
         dist.all_reduce(lo_t, op=dist.ReduceOp.MIN)
         clk["rank_ms_min_max"] = [float(lo_t[0]), ms_total]
     ms_per_step = ms_total / K
-    value = B / (1000.0 * ms_per_step * 1e-3)
+    value = rate(S, ms_total)
+    repeats_info = {"regions": R, "steps_per_region": K, "ms_per_step_median": ms_per_step, "ms_per_step_min": min(times) / K,
+                    "ms_per_step_max": max(times) / K, "value_min": rate(S, max(times)), "value_max": rate(S, min(times))}
     finite = bool(torch.isfinite(am).all())
 
     # ---- e2e: public API with host buffers
@@ -330,27 +366,40 @@ def main():
     out_a = torch.empty(hi - lo, N, N).pin_memory()
     torch.manual_seed(42)
     fn(sdx, sda, host_flags)                            # warm (engine cache, allocator)
-    barrier()
-    t0 = time.perf_counter()
-    ex, ea, _ = fn(sdx, sda, host_flags)
-    out_x.copy_(ex[lo:hi], non_blocking=True)
-    out_a.copy_(ea[lo:hi], non_blocking=True)
-    torch.cuda.synchronize(dev)
-    t_e2e = torch.tensor([time.perf_counter() - t0], device=dev)
-    if world > 1:
-        dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
-    e2e_val = B * K / (1000.0 * float(t_e2e))
+    e2e_t = []
+    for _ in range(min(R, 3)):
+        barrier()
+        t0 = time.perf_counter()
+        ex, ea, _ = fn(sdx, sda, host_flags)
+        out_x.copy_(ex[lo:hi], non_blocking=True)
+        out_a.copy_(ea[lo:hi], non_blocking=True)
+        torch.cuda.synchronize(dev)
+        e2e_t.append(max_over_ranks(time.perf_counter() - t0))
+    e2e_val = B * K / (1000.0 * float(np.median(e2e_t)))
     e2e = {"value": e2e_val, "unit": "graphs/s", "h2d_bytes_per_step": host_flags.numel() * 4 / K,
-           "d2h_bytes_per_step": (out_x.numel() + out_a.numel()) * 4 / K,
+           "d2h_bytes_per_step": (out_x.numel() + out_a.numel()) * 4 / K, "calls": len(e2e_t),
+           "value_min": B * K / (1000.0 * max(e2e_t)), "value_max": B * K / (1000.0 * min(e2e_t)),
            "call": f"sampler(model_x, model_adj, host_flags) for {K} solver steps (+ the final NCCL gather at N > 1) + D2H of "
-                   f"the rank's shard of (x, adj); bytes are per rank and call / {K}"}
+                   f"the rank's shard of (x, adj); median of {len(e2e_t)} calls; bytes are per rank and call / {K}"}
+    del ex, ea
 
+    # ---- the other scaling mode at N > 1 (every rank takes part), extra lines at N = 1
+    other_scaling = None
+    if world > 1 and not args.no_extra:
+        B2 = (args.batch or wl["B"]) * (world if args.scaling == "strong" else 1)
+        S2 = setup(wl, weights, B2, args.flags)
+        t2, _, _, _ = timed(S2, 10, 3)
+        m2 = float(np.median(t2))
+        other_scaling = {"scaling": "weak" if args.scaling == "strong" else "strong", "batch": B2, "value": rate(S2, m2),
+                         "unit": "graphs/s", "ms_per_step": m2 / K, "regions": 3}
+        del S2
     if rank != 0:
         shard.close()
         if world > 1:
             dist.destroy_process_group()
         return
     peaks, peak_src = measured_peaks()
+    pruned = int(L.gdss_ctx_query(eng.ctx, b"pruned"))
     # ---- per-kernel timing of eager launches (1 GPU view) -> roofline of the dominant kernel
     roofline, roofline_final, kernel_ms = None, None, None
     if not args.no_profile:
@@ -399,8 +448,8 @@ def main():
         roofline = roof("fused_layers_kernel", wl["flop_eval"] - wl["flop_final"] - flop_final_x,
                         "per-graph contractions on mma.sync m16n8k8 TF32 with the 3xTF32 split (strict fp32 parity), tanh / ELU / "
                         "attention dot products on the FP32 and MUFU pipes; algorithmic FLOPs = the reference's dense GEMM count of "
-                        "both networks minus the two final MLPs, at padded N, no symmetry / flag / dead-layer credit; the kernel is "
-                        "issue / latency bound (profiles/README.md), not pipe bound",
+                        "both networks minus the two final MLPs, at padded N (SURVEY 8d: symmetry / flag / dead-layer skipping is a "
+                        "speed-up above this count, not reduced work); the kernel is issue / latency bound (profiles/README.md)",
                         mma_peak, "mma.sync TF32 (512 FMA/clk/SM measured, tools/mma_probe.cu) / 3 (3xTF32) at the observed SM clock")
         roofline_final = roof("final_edge_kernel", wl["flop_final"],
                               "tcgen05 kind::tf32, 3xTF32 split (3 MMAs per product): the pipe peak is taken as "
@@ -408,6 +457,32 @@ def main():
                               peak_tc / 6.0, "tcgen05 tf32 / 3 (3xTF32), from the measured bf16 peak")
         if roofline is None:
             roofline = roofline_final
+    # ---- extra lines (one GPU): worst-case flags, the network evaluated without dead-chain elimination, the other BASELINE
+    # configurations -- each `min(R, 3)` regions of K steps, median
+    extras = None
+    if world == 1 and not args.no_extra:
+        extras = {}
+
+        def quick(name, wl_, weights_, B_, mode, env=None):
+            try:
+                S_ = setup(wl_, weights_, B_, mode, env)
+                t_, _, st_, _ = timed(S_, 10, min(R, 3))
+                m_ = float(np.median(t_))
+                extras[name] = {"value": rate(S_, m_), "unit": "graphs/s", "ms_per_step": m_ / K, "batch": B_, "flags": mode,
+                                "mean_nodes": float(np.mean(S_["counts"])), "finite": bool(torch.isfinite(st_[3]).all()),
+                                "pruned_chains": int(L.gdss_ctx_query(S_["eng"].ctx, b"pruned")),
+                                "fused_path": int(L.gdss_ctx_query(S_["eng"].ctx, b"fused")), "workload": wl_["desc"]}
+                del S_, st_
+            except Exception as exc:
+                extras[name] = {"unavailable": repr(exc)[:200]}
+            torch.cuda.empty_cache()
+
+        other_mode = "full" if args.flags == "ragged" else "ragged"
+        quick(f"flags_{other_mode}", wl, weights, B, other_mode)
+        quick("no_dead_chain_elimination", wl, weights, B, args.flags, {"GDSS_NO_PRUNE": "1"})
+        for other in WORKLOADS:
+            if other != args.workload:
+                quick(other, WORKLOADS[other], load_weights(WORKLOADS[other]), WORKLOADS[other]["B"], "ragged")
     cpu = None
     if not args.no_cpu_baseline and world == 1:
         cb, cs = args.cpu_batch or wl["cpu_B"], wl["cpu_steps"]
@@ -417,12 +492,13 @@ def main():
     torch_gpu = None
     if not args.no_torch_baseline and world == 1:
         try:
-            del eng, x, adj, xm, am, ex, ea
+            del eng, S, x, adj, xm, am
             torch.cuda.empty_cache()
             tb = min(B, args.torch_batch)
-            v, sps, _ = cpu_oracle_rate(wl, weights, tb, 1, 2, args.flags, device=str(dev))
+            v, sps, _ = cpu_oracle_rate(wl, weights, tb, 2, 4, args.flags, device=str(dev))
             torch_gpu = {"value": v, "unit": "graphs/s", "kind": "port (oracle as PyTorch eager CUDA fp32 ops, TF32 off)",
-                         "sample": f"2 timed solver steps (after 1) of 1000 on B={tb} graphs on the same B200, {sps * 1e3:.1f} ms/step"}
+                         "sample": f"4 timed solver steps (after 2) of 1000 on B={tb} graphs on the same B200, {sps * 1e3:.1f} ms/step",
+                         "speedup_of_value": value / v}
         except Exception as exc:                                  # e.g. out of memory: reported, not fatal
             torch_gpu = {"unavailable": repr(exc)[:200]}
     path_tflops = value * 1000 * wl["evals"] * wl["flop_eval"] / 1e12
@@ -431,6 +507,8 @@ def main():
             "vs_baseline": None, "dtype": "f32" if args.precision == "fp32" else "tf32 (reduced-precision variant, <= 3e-2 on the raw scores)",
             "data": "synthetic flags (SURVEY 8d node-count recipe), shipped checkpoint weights",
             "config": workload_config(args, wl, B), "clocks": clk, "e2e": e2e, "gpu_launches": int(launches) * world,
+            "repeats": repeats_info, "other_scaling": other_scaling, "extra": extras,
+            "pruned_chains": pruned,
             "roofline": roofline, "roofline_final_mlp": (roofline_final if not args.no_profile else None), "cpu_baseline": cpu, "torch_eager_same_gpu": torch_gpu,
             "path_algorithmic_tflops": path_tflops,
             "mean_nodes": float(np.mean(counts)), "finite": finite, "kernel_ms": kernel_ms}

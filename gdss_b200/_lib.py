@@ -65,6 +65,7 @@ def lib():
         "gdss_packed_floats": (i64, [C.POINTER(NetDesc), i32]),
         "gdss_num_state_tensors": (i32, [C.POINTER(NetDesc)]),
         "gdss_pack_weights": (C.c_int, [C.POINTER(NetDesc), i32, C.POINTER(vp), C.POINTER(i64), i32, fp, i64]),
+        "gdss_analyze_weights": (C.c_int, [C.POINTER(NetDesc), i32, fp, C.POINTER(i32), i32]),
         "gdss_ctx_create": (vp, [i32, i32, C.POINTER(NetDesc), fp, C.POINTER(NetDesc), fp]),
         "gdss_ctx_destroy": (None, [vp]),
         "gdss_workspace_bytes": (i64, [vp, i32]),

@@ -215,6 +215,24 @@ extern "C" int32_t gdss_num_state_tensors(const gdss_net_desc* desc) {
   return rc < 0 ? rc : p.n_tensors;
 }
 
+extern "C" int gdss_analyze_weights(const gdss_net_desc* desc, int32_t n_nodes, const float* host_blob, int32_t* out,
+                                    int32_t max_layers) {
+  NetPlan p;
+  int rc = plan_net(desc, n_nodes, &p);
+  if (rc < 0) return rc;
+  if (!host_blob || !out || max_layers < p.depth) return GDSS_E_BADARG;
+  const int off = analyze_liveness(&p, host_blob);
+  for (int l = 0; l < p.depth; ++l) {
+    const LayerPlan& L = p.layers[l];
+    const bool att = p.type != GDSS_NET_X;
+    out[4 * l + 0] = att ? (int32_t)L.qk_live : 0;
+    out[4 * l + 1] = att ? (int32_t)L.v_live : 0;
+    out[4 * l + 2] = att ? L.node_live : 1;
+    out[4 * l + 3] = att ? L.edge_const : 0;
+  }
+  return off;
+}
+
 extern "C" int gdss_pack_weights(const gdss_net_desc* desc, int32_t n_nodes, const float* const* tensors,
                                  const int64_t* numel, int32_t n_tensors, float* blob, int64_t blob_floats) {
   NetPlan p;

@@ -73,8 +73,8 @@ typedef struct gdss_sampler_desc {
   int32_t predictor;     /* GDSS_PRED_*                                                   */
   int32_t corrector;     /* GDSS_CORR_* (ignored by S4, which always corrects)            */
   double snr, scale_eps, eps;
-  int32_t n_steps;       /* Langevin inner steps (1 in every shipped config; only 1 is built) */
-  int32_t probability_flow;  /* only 0 is built (every shipped config)                     */
+  int32_t n_steps;       /* Langevin inner steps of get_pc_sampler (solver.py:126, :138; 1 in every shipped config) */
+  int32_t probability_flow;  /* informational: the ODE variant lives in the table (pb halved, pc = 0)   */
   int32_t denoise;       /* return *_mean (noise_removal)                                 */
   int32_t reserved;
 } gdss_sampler_desc;
@@ -113,9 +113,17 @@ int32_t gdss_num_state_tensors(const gdss_net_desc* desc);
 int gdss_pack_weights(const gdss_net_desc* desc, int32_t n_nodes, const float* const* tensors,
                       const int64_t* numel, int32_t n_tensors, float* host_blob, int64_t blob_floats);
 
+/* Dead sub-network report of a packed HOST blob (what gdss_ctx_create finds and switches off; gdss_pack.cu
+ * analyze_liveness): out[4*l + {0,1,2,3}] = {bit mask of channels whose Q/K chain + attention map is live, bit mask of
+ * channels whose V convolution is live, the layer's node output is read downstream, the layer's per-edge MLP output is
+ * a constant} for the AttentionLayer l (attention.py:93-116).  Weight blocks with max |w| < 1e-30 are dead (the shipped
+ * checkpoints' weight-decayed sub-networks).  Returns the number of chains / MLPs switched off (<0 on error). */
+int gdss_analyze_weights(const gdss_net_desc* desc, int32_t n_nodes, const float* host_blob, int32_t* out, int32_t max_layers);
+
 /* ---- context ------------------------------------------------------------------------
  * A context binds up to two packed networks (node-feature net, adjacency net; either may
- * be NULL) for graphs of N nodes and F features.  Host memory only. */
+ * be NULL) for graphs of N nodes and F features.  Allocates host memory only; reads the two blobs back once (a
+ * synchronous device-to-host copy) for the dead sub-network analysis (GDSS_NO_PRUNE=1 skips it). */
 gdss_ctx* gdss_ctx_create(int32_t N, int32_t F, const gdss_net_desc* net_x, const float* dev_blob_x,
                           const gdss_net_desc* net_a, const float* dev_blob_a);
 void gdss_ctx_destroy(gdss_ctx* ctx);
@@ -143,8 +151,8 @@ int gdss_score_forward(gdss_ctx* ctx, const float* x, const float* adj, const fl
  *                 N(0,1) prior (solver.py:174-178) from the Philox stream, else used as given.
  *   x_mean, adj_mean  out: the predictor means of the last step (what denoise=True returns)
  *   inj_x, inj_adj    optional injected raw N(0,1) draws, layouts [n_iters][dx][B][N][F] and
- *                 [n_iters][da][B][N][N] in the reference's draw order (dx=da= 2 PC+Langevin,
- *                 1 PC without corrector, 3 S4); NULL -> counter-based Philox4x32-10 keyed by
+ *                 [n_iters][da][B][N][N] in the reference's draw order (dx=da= n_steps+1 PC+Langevin:
+ *                 the corrector iterations' draws then the predictor's, 1 PC without corrector, 3 S4); NULL -> counter-based Philox4x32-10 keyed by
  *                 (seed, global graph id = graph_offset + b, step, draw), so results do not
  *                 depend on how the batch is sharded.
  *   trace         optional [n_iters][8] floats: per step the Langevin step sizes
@@ -166,7 +174,7 @@ int gdss_sample(gdss_ctx* ctx, const gdss_sampler_desc* s, const gdss_step_coef*
  * reduce_op(square(score * std + z)), batch mean -> loss_out[0] (x), loss_out[1] (adj) on the device.
  * coef = float[B][6]: mean_x, std_x, div_x, mean_adj, std_adj, div_adj from sde.marginal_prob(., t_b); div = std for
  * VP / subVP (score = -net / std), 0 for VE (score = net).  scratch >= gdss_dsm_scratch_floats floats.
- * The backward pass / optimizer step of trainer.py:57-79 is not part of this library yet. */
+ * The optimizer half of trainer.py:66-79 is gdss_adam_ema_step below. */
 int64_t gdss_dsm_scratch_floats(const gdss_ctx* ctx, int32_t B);
 int gdss_dsm_loss(gdss_ctx* ctx, const float* x, const float* adj, const float* coef, const float* raw_x,
                   const float* raw_adj, int32_t B, int32_t reduce_mean, float* scratch, int64_t scratch_floats,

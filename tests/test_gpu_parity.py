@@ -665,3 +665,106 @@ def test_dsm_loss_uses_the_reference_draw_order():
     c = fn(ck["x_state_dict"], ck["adj_state_dict"], x, adj, t=t, raw_x=rx, raw_adj=ra)
     assert float(a[0]) == float(b[0]) == float(c[0]) and float(a[1]) == float(b[1]) == float(c[1])
     assert torch.isfinite(a[0]) and torch.isfinite(a[1])
+
+
+def test_multi_gpu_sharded_sampler_matches_single_gpu():
+    """the sharded sampler (one process per GPU, 4-float NCCL all-reduce of the Langevin norms per phase, final
+    all-gather) returns on every rank what one GPU returns for the whole batch; data-parallel gradient all-reduce + fused
+    optimizer step.  Spawns 2 ranks (tools/multi_gpu_check.py); the log is kept under gpurun_out/."""
+    import subprocess
+    import sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs (run under gpurun --gpus 2)")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29671", os.path.join(root, "tools", "multi_gpu_check.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=root)
+    os.makedirs(os.path.join(root, "gpurun_out"), exist_ok=True)
+    with open(os.path.join(root, "gpurun_out", "multi_gpu_check.log"), "w") as f:
+        f.write(r.stdout + "\n--- stderr ---\n" + r.stderr[-4000:])
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert r.stdout.count("OK") >= 4 and "FAIL" not in r.stdout, r.stdout
+
+
+def test_successive_calls_draw_independent_noise():
+    """The reference consumes the torch RNG, so the sampling rounds of sampler.py:59-66 are independent; here every call
+    takes a fresh Philox seed from torch's generator: two calls differ, a re-seeded call repeats."""
+    from gdss_b200 import graph_utils as G
+    from gdss_b200.solver import get_pc_sampler
+    from gdss_b200.sde import VPSDE, VESDE
+    ck = load_golden_ckpt("qm9")
+    B, N, F = 6, 9, 4
+    flags = torch.ones(B, N)
+    fn = get_pc_sampler(VESDE(.1, 1., 1000), VESDE(.1, 1., 1000), (B, N, F), (B, N, N), predictor="Reverse",
+                        corrector="Langevin", snr=.2, scale_eps=.7, eps=1e-4, device="cuda", max_iters=5)
+    torch.manual_seed(3)
+    a = fn(ck["x_state_dict"], ck["adj_state_dict"], flags)
+    b = fn(ck["x_state_dict"], ck["adj_state_dict"], flags)
+    torch.manual_seed(3)
+    c = fn(ck["x_state_dict"], ck["adj_state_dict"], flags)
+    assert not torch.equal(a[1], b[1]) and torch.equal(a[1], c[1]) and torch.equal(a[0], c[0])
+    x = torch.zeros(B, N, N, device="cuda")
+    fl = flags.cuda()
+    torch.manual_seed(4)
+    n1, n2 = G.gen_noise(x, fl), G.gen_noise(x, fl)
+    f1 = G.init_flags_device([5, 6, 7, 8, 9], N, 64)
+    f2 = G.init_flags_device([5, 6, 7, 8, 9], N, 64)
+    assert not torch.equal(n1, n2) and not torch.equal(f1, f2)
+    torch.manual_seed(4)
+    assert torch.equal(G.gen_noise(x, fl), n1)
+
+
+def test_engine_cache_sees_in_place_weight_updates():
+    """ExponentialMovingAverage.copy_to / restore write through param.data.copy_ (utils/ema.py:46, :71), which does not bump
+    tensor._version: the packed-weights cache must still re-pack.  Two different checkpoints of one architecture must never
+    share an engine."""
+    from gdss_b200.models import load_model
+    from gdss_b200.solver import _engine_for
+    ck = load_golden_ckpt("qm9")
+    mx, ma = load_model(ck["params_x"]).cuda(), load_model(ck["params_adj"]).cuda()
+    mx.load_state_dict(ck["x_state_dict"]); ma.load_state_dict(ck["adj_state_dict"])
+    N, F = 9, 4
+    x, adj, flags = O.kat_inputs(N, F, 4)
+    e1 = _engine_for(mx, ma, N, torch.device("cuda:0"))
+    s1 = e1.score(x.cuda(), adj.cuda(), flags.cuda())[1].clone()
+    assert _engine_for(mx, ma, N, torch.device("cuda:0")) is e1
+    with torch.no_grad():
+        for p in ma.parameters():
+            p.data.copy_(p.data * 1.5)                   # no _version bump
+    e2 = _engine_for(mx, ma, N, torch.device("cuda:0"))
+    assert e2 is not e1
+    s2 = e2.score(x.cuda(), adj.cuda(), flags.cuda())[1]
+    assert not torch.allclose(s1, s2)
+    s3 = ma(x.cuda(), adj.cuda(), flags.cuda())          # the module's own cache re-packs as well
+    assert rel(s3, s2) <= 1e-6
+
+
+@pytest.mark.parametrize("name", ["zinc250k_v2", "qm9", "enzymes", "grid"])
+def test_dead_chain_elimination_changes_nothing(name):
+    """The weight-pack-time elimination of dead sub-networks (gdss_pack.cu analyze_liveness) against the same kernels with
+    every chain evaluated (GDSS_NO_PRUNE=1): raw scores equal to fp32 rounding, and the shipped checkpoints do have dead
+    chains (so the optimisation is exercised by every parity test of this file)."""
+    from gdss_b200 import _lib
+    ck = load_golden_ckpt(name)
+    pa = ck["params_adj"]
+    N, F = pa["max_node_num"], pa["max_feat_num"]
+    B = 4 if N < 200 else 1
+    x, adj, flags = O.kat_inputs(N, F, B)
+    eng = Engine(ck["x_state_dict"], ck["adj_state_dict"], N, "cuda")
+    pruned = int(_lib.lib().gdss_ctx_query(eng.ctx, b"pruned"))
+    assert pruned > 0, name
+    sx, sa = eng.score(x.cuda(), adj.cuda(), flags.cuda(), inputs_masked=False)
+    os.environ["GDSS_NO_PRUNE"] = "1"
+    try:
+        full = Engine(ck["x_state_dict"], ck["adj_state_dict"], N, "cuda")
+    finally:
+        del os.environ["GDSS_NO_PRUNE"]
+    assert int(_lib.lib().gdss_ctx_query(full.ctx, b"pruned")) == 0
+    fx, fa = full.score(x.cuda(), adj.cuda(), flags.cuda(), inputs_masked=False)
+    assert rel(sx, fx) <= 2e-6 and rel(sa, fa) <= 2e-6, (name, pruned, rel(sx, fx), rel(sa, fa))
+    # random-init weights have no dead blocks: nothing is switched off
+    from gdss_b200.models import load_model
+    torch.manual_seed(0)
+    ra = load_model(pa)
+    rnd = Engine(None, ra.state_dict(), N, "cuda")
+    assert int(_lib.lib().gdss_ctx_query(rnd.ctx, b"pruned")) == 0

@@ -317,3 +317,75 @@ def test_clock_sampler_parses_single_and_multi_gpu_rows():
     assert many["sm_mhz"] == 1965.0 and many["reasons"] == [] and many["gpus_sampled"] == 3
     assert many["sm_mhz_min_over_gpus"] == 1800.0 and many["power_w_max_over_gpus"] == 410.5
     assert many["reasons_any_gpu"] == ["sw_thermal_slowdown"]
+
+
+def test_dead_chain_analysis_of_the_shipped_checkpoints():
+    """gdss_analyze_weights (host code, what gdss_ctx_create switches off): the weight-decayed dead sub-networks of the shipped
+    checkpoints -- e.g. gdss_zinc250k_v2's ScoreNetworkA: every gnn_q / gnn_k of layer 0 and the whole last AttentionLayer are in
+    the fp32 denormal range -- are found, liveness of x_out is propagated backwards, random-init weights lose nothing."""
+    import ctypes as C
+    from gdss_b200 import _lib
+    from gdss_b200.engine import pack_network, model_state
+    L = _lib.lib()
+
+    def report(sd, N):
+        desc, blob = pack_network(model_state(sd), N)
+        out = (C.c_int32 * 64)()
+        n = L.gdss_analyze_weights(C.byref(desc), N, blob.data_ptr(), out, 16)
+        assert n >= 0
+        return n, [tuple(out[4 * l + k] for k in range(4)) for l in range(desc.depth)]
+
+    ck = load_golden_ckpt("zinc250k_v2")
+    n, rep = report(ck["adj_state_dict"], 38)
+    assert n > 0
+    assert rep[0][0] == 0 and rep[0][1] == 0b11                     # layer 0: both Q/K chains dead, both V live
+    assert [bin(r[0]).count("1") for r in rep[1:5]] == [6, 6, 6, 6]  # layers 1-4: 6 of 8 maps live
+    assert rep[5] == (0, 0, 0, 1)                                   # last layer: constant per-edge MLP, nothing else
+    assert rep[4][1] == 0 and rep[4][2] == 0                        # its input x is never read: layer 4 needs no V / node MLP
+    assert rep[3][2] == 1
+    n_x, rep_x = report(ck["x_state_dict"], 38)
+    assert rep_x[0][0] == 0 and rep_x[0][2] == 1 and rep_x[1][2] == 1    # X_GMH: every x_l feeds the final concat
+    # a dead block must be dead in the reference's sense too: removing it changes nothing (oracle, CPU)
+    sd = {k: v.clone() for k, v in ck["adj_state_dict"].items()}
+    for k in sd:
+        if k.startswith("layers.5."):
+            assert float(sd[k].abs().max()) < 1e-30 or ".mlp.linears." in k or ".multi_channel." in k or "gnn_v" in k, k
+    # random-init weights: nothing is dead
+    from gdss_b200.models import load_model
+    torch.manual_seed(0)
+    n_r, rep_r = report(load_model(ck["params_adj"]).state_dict(), 38)
+    assert n_r == 0 and all(r[0] == r[1] and r[3] == 0 for r in rep_r[:-1]) and rep_r[-1][1] == 0b11111111 or n_r == 0
+
+
+def test_state_dict_is_packed_by_key_not_by_position():
+    """A re-ordered (sorted) state_dict packs to the same blob; a missing / foreign key fails loudly."""
+    from gdss_b200 import _lib
+    from gdss_b200.engine import pack_network
+    ck = load_golden_ckpt("qm9")
+    sd = ck["adj_state_dict"]
+    _, a = pack_network(sd, 9)
+    _, b = pack_network({k: sd[k] for k in sorted(sd)}, 9)
+    assert torch.equal(a, b)
+    bad = dict(sd)
+    bad.pop("final.linears.2.bias")
+    with pytest.raises(_lib.GdssError):
+        pack_network(bad, 9)
+
+
+def test_probability_flow_and_n_steps_in_the_schedule():
+    """sde.py:98-99: the ODE halves the reverse drift and drops the predictor noise; Euler + probability_flow fails in the
+    reference at call time (solver.py:52) and so does the mirror."""
+    from gdss_b200.schedule import build_table, COL
+    from gdss_b200.sde import VPSDE, VESDE
+    from gdss_b200.solver import get_pc_sampler
+    sx, sa = VPSDE(.1, 1., 50), VESDE(.2, 1., 50)
+    t0 = build_table(sx, sa, "Reverse", "Langevin", .2, .8, 1e-4, False)
+    t1 = build_table(sx, sa, "Reverse", "Langevin", .2, .8, 1e-4, True)
+    assert np.allclose(t1[:, COL["pb"]:COL["pb"] + 2], 0.5 * t0[:, COL["pb"]:COL["pb"] + 2], rtol=1e-6)
+    assert np.all(t1[:, COL["pc"]:COL["pc"] + 2] == 0) and np.all(t0[:, COL["pc"]:COL["pc"] + 2] > 0)
+    assert np.array_equal(t1[:, COL["pa"]:COL["pa"] + 2], t0[:, COL["pa"]:COL["pa"] + 2])
+    fn = get_pc_sampler(sx, sa, (2, 9, 4), (2, 9, 9), predictor="Euler", probability_flow=True, device="cpu")
+    with pytest.raises(TypeError, match="not subscriptable"):
+        fn({}, {}, torch.ones(2, 9))
+    with pytest.raises(ValueError):
+        get_pc_sampler(sx, sa, (2, 9, 4), (2, 9, 9), predictor="Reverse", corrector="Langevin", n_steps=0)

@@ -8,7 +8,7 @@ import torch.distributed as dist
 from gdss_b200.dist import init_from_env
 from gdss_b200.solver import get_pc_sampler, S4_solver
 from gdss_b200.sde import VPSDE, VESDE
-from oracle.cases import load_golden_ckpt
+from gdss_b200.ckpt import load_ckpt as load_golden_ckpt
 
 shard, dev = init_from_env()
 ck = load_golden_ckpt("zinc250k_v2")
