@@ -230,7 +230,7 @@ def workload_config(args, wl, B):
             "flags": args.flags, "solver_steps_per_sample": 1000,
             "step": "one reverse-diffusion solver step over the whole batch", "l2": "inputs larger than L2 (per-step working "
             "set = edge-channel stacks >> 126 MB at B=10000)" if B * wl["N"] ** 2 * 46 * 4 > 126e6 else "working set fits L2",
-            "weights": "shipped checkpoint (tests/golden/ckpt); dead weight blocks (|w| < 1e-30, the checkpoint's weight-decayed "
+            "weights": "shipped checkpoint (tests/golden/ckpt); dead weight blocks (|w| < 1e-12, the checkpoint's weight-decayed "
                        "sub-networks) are not evaluated -- `extra.no_dead_chain_elimination` is the same run with every chain evaluated",
             "noise": "in-kernel Philox4x32-10, seed 42"}
 

@@ -76,6 +76,8 @@ def lib():
                                    fp, fp, fp, vp, i32, vp, i64, vp]),
         "gdss_dsm_scratch_floats": (i64, [vp, i32]),
         "gdss_dsm_loss": (C.c_int, [vp, fp, fp, fp, fp, fp, i32, i32, fp, i64, fp, vp, i64, vp]),
+        "gdss_train_workspace_bytes": (i64, [vp, i32]),
+        "gdss_dsm_loss_backward": (C.c_int, [vp, fp, fp, fp, fp, fp, i32, i32, fp, fp, fp, vp, i64, vp]),
         "gdss_optim_scratch_floats": (i64, []),
         "gdss_adam_ema_step": (C.c_int, [fp, fp, fp, fp, fp, i64, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float,
                                           C.c_float, i32, C.c_float, i64, fp, fp, fp, vp]),

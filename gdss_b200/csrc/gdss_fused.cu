@@ -762,9 +762,10 @@ DEVINL void node_mlp_mma(const float* V, int ldv, int K, const float* W1, const 
     Acc c[2];
 #pragma unroll
     for (int j = 0; j < 2; ++j) acc_init(c[j], b1[8 * j + 2 * t], b1[8 * j + 2 * t + 1]);
+    for (int cb = 0, ch = 0; cb < K; cb += h, ++ch) {          // channel blocks of the concatenated V rows (no division)
+      if (!((vmask >> ch) & 1u)) continue;
 #pragma unroll 2
-    for (int k0 = 0; k0 < K; k0 += 8) {
-      if (!((vmask >> (k0 / h)) & 1u)) continue;
+    for (int k0 = cb; k0 < cb + h; k0 += 8) {
       uint32_t ah[4], al[4];
       const Split a0 = split_tf32(va[k0 + t]), a1 = split_tf32(vb[k0 + t]);
       const Split a2 = split_tf32(va[k0 + t + 4]), a3 = split_tf32(vb[k0 + t + 4]);
@@ -774,6 +775,7 @@ DEVINL void node_mlp_mma(const float* V, int ldv, int K, const float* W1, const 
         const Split w0 = split_tf32(W1[(k0 + t) * 16 + 8 * j + g]), w1 = split_tf32(W1[(k0 + t + 4) * 16 + 8 * j + g]);
         mma3(c[j], ah, al, w0, w1);
       }
+    }
     }
     uint32_t eh[2][4], el[2][4];                       // ELU(h1) as the A fragments of the second linear (permuted k order)
 #pragma unroll

@@ -119,6 +119,10 @@ int launch_final_tc_dense(const gdss_ctx* ctx, const float* stack, int64_t s_bs,
 int launch_setup(const gdss_ctx* ctx, const float* flags, int B, int inputs_masked, char* ws, const Workspace& w,
                  cudaStream_t st);
 
+// losses.py:47-58 (gdss_loss.cu): node flags of the data, masked noise from the raw draws, perturbed inputs
+int launch_dsm_perturb(const float* x, const float* adj, const float* coef, const float* raw_x, const float* raw_adj, float* flags,
+                       float* px, float* padj, float* zx, float* zadj, int B, int N, int F, cudaStream_t st);
+
 // NCCL (dlopen'ed)
 int nccl_allreduce_sum(void* comm, float* buf, int count, cudaStream_t st);
 

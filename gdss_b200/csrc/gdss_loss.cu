@@ -97,6 +97,14 @@ __global__ void __launch_bounds__(1024) dsm_mean_kernel(const float* __restrict_
   }
 }
 
+int launch_dsm_perturb(const float* x, const float* adj, const float* coef, const float* raw_x, const float* raw_adj, float* flags,
+                       float* px, float* padj, float* zx, float* zadj, int B, int N, int F, cudaStream_t st) {
+  dsm_perturb_kernel<<<B, 256, sizeof(float) * N, st>>>(x, adj, coef, raw_x, raw_adj, flags, px, padj, zx, zadj, N, F);
+  launched(K_MISC, st);
+  LAUNCH_CHECK();
+  return 0;
+}
+
 }  // namespace gdss
 
 extern "C" int64_t gdss_dsm_scratch_floats(const gdss_ctx* ctx, int32_t B) {

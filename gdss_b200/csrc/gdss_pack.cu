@@ -112,8 +112,9 @@ static void put_linear_t(float* dst, const float* src, int in, int out, int ld =
 // ---------------------------------------------------------------------------------------
 // Dead sub-network elimination.  The shipped checkpoints were trained with weight decay; whole weight blocks of them
 // have decayed into the fp32 denormal range (|w| ~ 1e-39: e.g. every gnn_q / gnn_k of layer 0 and the complete last
-// AttentionLayer of ScoreNetworkA in gdss_zinc250k_v2.pth).  A block below GDSS_DEAD_EPS contributes < 1e-28 to sums of
-// O(1e-2 .. 1) terms -- nothing in fp32 -- so the chain that only feeds it is not evaluated:
+// AttentionLayer of ScoreNetworkA in gdss_zinc250k_v2.pth; the EMA shadows ENZYMES / grid sample with lag behind at
+// 1e-14 .. 1e-30).  A block below GDSS_DEAD_EPS = 1e-12 moves sums of O(1e-2 .. 1) terms by < 1e-9 relative -- 1/60 of an
+// fp32 ulp -- so the chain that only feeds it is not evaluated:
 //   * Q or K convolution dead (weights and bias)  -> the attention map is tanh(0) = 0 exactly (attention.py:41-49)
 //   * row c of mlp.linears.0 dead                 -> map c is never read (attention.py:109-110)
 //   * rows of multi_channel.linears.0 for V_c dead, or x_out unread downstream -> V_c is never read (attention.py:106)
@@ -122,7 +123,7 @@ static void put_linear_t(float* dst, const float* src, int in, int out, int ld =
 // convolutions, ScoreNetwork_A.py:136-139; ScoreNetworkX_GMH concatenates every x, ScoreNetwork_X.py:79-84).
 // Random-init weights have no dead blocks and are evaluated in full.
 // ---------------------------------------------------------------------------------------
-#define GDSS_DEAD_EPS 1e-30f
+#define GDSS_DEAD_EPS 1e-12f
 
 static bool block_dead(const float* w, int64_t rows, int64_t cols, int64_t ld) {
   for (int64_t r = 0; r < rows; ++r)

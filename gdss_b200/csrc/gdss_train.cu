@@ -1,0 +1,1139 @@
+// Denoising-score-matching training step: forward WITH saved activations and the hand-derived reverse sweep of both score
+// networks (BASELINE config C5; losses.py:37-81 + trainer.py:57-65: loss_x.backward(), loss_adj.backward()).
+//
+// This is the HBM-staged, multi-kernel formulation (one launch per tensor operation of the reference's graph, activations
+// kept in a caller-provided arena): dense [B, N, N] / [B, N, F] layouts, every node evaluated (no neff shortcut), fp32 FFMA.
+// Each kernel is the gradient of the forward restatement of the same name in the oracle (oracle/gdss_backward.py, test
+// infrastructure) and cites the reference lines it differentiates.  Parameter gradients are accumulated in the layout of
+// the packed weight blob (gdss_pack.cu): the host mirror maps them back to state_dict order.
+//
+//   Linear / MLP (layers.py:135-153)     tr_linear_kernel (forward and data gradient), tr_wgrad_kernel (weight / bias gradient,
+//                                        per-CTA partial sums over a row chunk, then one atomicAdd per weight per CTA)
+//   DenseGCNConv (layers.py:49-88)       tr_gcn_fwd_kernel / tr_gcn_bwd_kernel: one CTA per (graph, channel); the gradient reaches
+//                                        the adjacency CHANNEL through A^ = D^-1/2 A~ D^-1/2 (planes of layers >= 1 are activations)
+//   Attention maps (attention.py:35-49)  tr_maps_fwd_kernel / tr_maps_bwd_kernel (tanh recomputed from Q, K)
+//   AttentionLayer glue (attention.py:93-116), final MLPs, masks, symmetrisation: gather / scatter kernels below
+#include <string.h>
+
+#include "gdss_common.cuh"
+#include "gdss_internal.h"
+
+namespace gdss {
+
+#define LAUNCH_CHECK()                          \
+  do {                                          \
+    cudaError_t e__ = cudaGetLastError();       \
+    if (e__ != cudaSuccess) return (int)e__;    \
+  } while (0)
+
+#define TR_TM 64            // rows per CTA of the linear kernel
+#define TR_WG_ROWS 32       // rows per shared-memory tile of the weight-gradient kernel
+#define TR_WG_MAXI 12       // (k, 4 outputs) items per thread: K * NO <= 12288
+#define TR_WG_CHUNK 2048    // rows per CTA of the weight-gradient kernel
+
+DEVINL float elu_exact(float v) { return v > 0.f ? v : expm1f(v); }
+
+// Y[m][o] (+)= act(bias[o] + sum_k X[m][k] * Wm[k][o]),  Wm[k][o] = W[k * ldw + o]  (trans = 0: the packed [in][out] weights)
+//                                                     or W[o * ldw + k]  (trans = 1: data gradient dX = dY W)
+__global__ void __launch_bounds__(256) tr_linear_kernel(const float* __restrict__ X, int ldx, const float* __restrict__ W, int ldw,
+                                                        const float* __restrict__ bias, float* __restrict__ Y, int ldy, int64_t M,
+                                                        int K, int NO, int trans, int act, int accumulate) {
+  extern __shared__ __align__(16) float sm[];
+  const int NOP = (NO + 3) & ~3, KS = K + 1;
+  float* Ws = sm;                   // [K][NOP]
+  float* Xs = Ws + K * NOP;         // [TR_TM][K + 1]
+  const int tid = threadIdx.x;
+  for (int idx = tid; idx < K * NOP; idx += 256) {
+    const int k = idx / NOP, o = idx - k * NOP;
+    Ws[idx] = o < NO ? (trans ? W[(int64_t)o * ldw + k] : W[(int64_t)k * ldw + o]) : 0.f;
+  }
+  const int64_t m0 = (int64_t)blockIdx.x * TR_TM;
+  for (int idx = tid; idx < TR_TM * K; idx += 256) {
+    const int r = idx / K, k = idx - r * K;
+    const int64_t m = m0 + r;
+    Xs[r * KS + k] = m < M ? X[m * ldx + k] : 0.f;
+  }
+  __syncthreads();
+  const int og = NOP >> 2;
+  for (int item = tid; item < TR_TM * og; item += 256) {
+    const int r = item / og, o4 = (item - r * og) * 4;
+    const int64_t m = m0 + r;
+    if (m >= M) continue;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    if (bias) {
+      a0 = o4 < NO ? bias[o4] : 0.f; a1 = o4 + 1 < NO ? bias[o4 + 1] : 0.f;
+      a2 = o4 + 2 < NO ? bias[o4 + 2] : 0.f; a3 = o4 + 3 < NO ? bias[o4 + 3] : 0.f;
+    }
+    const float* xr = Xs + r * KS;
+    for (int k = 0; k < K; ++k) {
+      const float xv = xr[k];
+      const float4 w = *reinterpret_cast<const float4*>(Ws + k * NOP + o4);
+      a0 = fmaf(xv, w.x, a0); a1 = fmaf(xv, w.y, a1); a2 = fmaf(xv, w.z, a2); a3 = fmaf(xv, w.w, a3);
+    }
+    float v[4] = {a0, a1, a2, a3};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      if (o4 + q >= NO) continue;
+      float y = v[q];
+      if (act == 1) y = elu_exact(y);
+      float* dst = Y + m * ldy + o4 + q;
+      *dst = accumulate ? *dst + y : y;
+    }
+  }
+}
+
+// dW[k * ldw + o] += sum_m X[m][k] dY[m][o];  db[o] += sum_m dY[m][o]  over this CTA's row chunk
+__global__ void __launch_bounds__(256) tr_wgrad_kernel(const float* __restrict__ X, int ldx, const float* __restrict__ dY, int ldy,
+                                                       float* __restrict__ dW, int ldw, float* __restrict__ db, int64_t M, int K,
+                                                       int NO) {
+  extern __shared__ __align__(16) float sm[];
+  const int NOP = (NO + 3) & ~3;
+  float* Xs = sm;                        // [ROWS][K]
+  float* Ys = Xs + TR_WG_ROWS * K;       // [ROWS][NOP]
+  const int tid = threadIdx.x;
+  const int og = NOP >> 2, items = K * og;
+  float4 acc[TR_WG_MAXI];
+#pragma unroll
+  for (int it = 0; it < TR_WG_MAXI; ++it) acc[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+  float bacc = 0.f;
+  const int64_t m_lo = (int64_t)blockIdx.x * TR_WG_CHUNK;
+  const int64_t m_hi = m_lo + TR_WG_CHUNK < M ? m_lo + TR_WG_CHUNK : M;
+  for (int64_t m0 = m_lo; m0 < m_hi; m0 += TR_WG_ROWS) {
+    for (int idx = tid; idx < TR_WG_ROWS * K; idx += 256) {
+      const int r = idx / K, k = idx - r * K;
+      Xs[idx] = m0 + r < m_hi ? X[(m0 + r) * ldx + k] : 0.f;
+    }
+    for (int idx = tid; idx < TR_WG_ROWS * NOP; idx += 256) {
+      const int r = idx / NOP, o = idx - r * NOP;
+      Ys[idx] = (m0 + r < m_hi && o < NO) ? dY[(m0 + r) * ldy + o] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int it = 0; it < TR_WG_MAXI; ++it) {
+      const int item = tid + it * 256;
+      if (item < items) {
+        const int k = item / og, o4 = (item - k * og) * 4;
+        float4 a = acc[it];
+#pragma unroll 8
+        for (int r = 0; r < TR_WG_ROWS; ++r) {
+          const float xv = Xs[r * K + k];
+          const float4 y = *reinterpret_cast<const float4*>(Ys + r * NOP + o4);
+          a.x = fmaf(xv, y.x, a.x); a.y = fmaf(xv, y.y, a.y); a.z = fmaf(xv, y.z, a.z); a.w = fmaf(xv, y.w, a.w);
+        }
+        acc[it] = a;
+      }
+    }
+    if (db && tid < NO) {
+      for (int r = 0; r < TR_WG_ROWS; ++r) bacc += Ys[r * NOP + tid];
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int it = 0; it < TR_WG_MAXI; ++it) {
+    const int item = tid + it * 256;
+    if (item < items) {
+      const int k = item / og, o4 = (item - k * og) * 4;
+      const float v[4] = {acc[it].x, acc[it].y, acc[it].z, acc[it].w};
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        if (o4 + q < NO) atomicAdd(dW + (int64_t)k * ldw + o4 + q, v[q]);
+    }
+  }
+  if (db && tid < NO) atomicAdd(db + tid, bacc);
+}
+
+// g *= ELU'(pre) with the saved post-activation h: ELU'(pre) = 1 (pre > 0) or exp(pre) = h + 1   (layers.py:150)
+__global__ void tr_elu_bwd_kernel(float* __restrict__ g, const float* __restrict__ h, int64_t n) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float hv = h[i];
+    g[i] *= hv > 0.f ? 1.f : hv + 1.f;
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// DenseGCNConv (layers.py:49-88), one CTA per (channel c, graph b):
+//   A~ = plane with unit diagonal, deg = rowsum A~, d = clamp(deg, 1)^-1/2, XW = x W_c, Y = d_i sum_j A~_ij d_j XW_j + b_c
+// per-channel row tensors are laid out [c][b * N + i][OW]
+// ---------------------------------------------------------------------------------------
+struct GcnT {
+  const float* planes; int64_t p_bs;       // plane c of graph b = planes + b * p_bs + c * N * N
+  const float* x; int ldx; int fin;        // node features [B * N][ldx]
+  const float* W; int64_t w_cs; int ldw;   // W_c = W + c * w_cs, [fin][ldw]
+  const float* bias; int b_cs;
+  float* degraw; float* d;                 // [C][B * N]
+  float* XW; float* Y;                     // [C][B * N][OW]
+  int B, N, OW;
+};
+
+__global__ void __launch_bounds__(256) tr_gcn_fwd_kernel(GcnT a) {
+  extern __shared__ __align__(16) float sm[];
+  const int c = blockIdx.x, b = blockIdx.y, N = a.N, OW = a.OW, NS = N + 1;
+  float* At = sm;                 // [N][N + 1]
+  float* dv = At + N * NS;        // [N]
+  float* xw = dv + N;             // [N][OW]
+  const int tid = threadIdx.x;
+  const float* P = a.planes + b * a.p_bs + (int64_t)c * N * N;
+  for (int idx = tid; idx < N * N; idx += 256) {
+    const int i = idx / N, j = idx - i * N;
+    At[i * NS + j] = i == j ? 1.f : P[idx];
+  }
+  __syncthreads();
+  const int64_t r0 = ((int64_t)c * a.B + b) * N;
+  for (int i = tid; i < N; i += 256) {
+    float s = 0.f;
+    for (int j = 0; j < N; ++j) s += At[i * NS + j];
+    const float dd = 1.0f / sqrtf(fmaxf(s, 1.0f));
+    dv[i] = dd;
+    a.degraw[r0 + i] = s;
+    a.d[r0 + i] = dd;
+  }
+  const float* X = a.x + (int64_t)b * N * a.ldx;
+  const float* W = a.W + (int64_t)c * a.w_cs;
+  for (int idx = tid; idx < N * OW; idx += 256) {
+    const int j = idx / OW, o = idx - j * OW;
+    float s = 0.f;
+    for (int f = 0; f < a.fin; ++f) s = fmaf(X[j * a.ldx + f], W[(int64_t)f * a.ldw + o], s);
+    xw[idx] = s;
+    a.XW[(r0 + j) * OW + o] = s;
+  }
+  __syncthreads();
+  const float* bias = a.bias + (int64_t)c * a.b_cs;
+  for (int idx = tid; idx < N * OW; idx += 256) {
+    const int i = idx / OW, o = idx - i * OW;
+    float s = 0.f;
+    for (int j = 0; j < N; ++j) s = fmaf(At[i * NS + j] * dv[j], xw[j * OW + o], s);
+    a.Y[(r0 + i) * OW + o] = dv[i] * s + bias[o];
+  }
+}
+
+struct GcnBT {
+  const float* planes; int64_t p_bs;
+  const float* degraw; const float* d;     // saved by the forward
+  const float* XW; const float* dY;        // [C][B * N][OW]
+  float* dXW;                              // out: A^T dY = A^ dY  [C][B * N][OW]
+  float* dplanes; int64_t dp_bs;           // in/out (+=): gradient of the adjacency channels, or null
+  float* dbias; int b_cs;                  // atomics
+  int B, N, OW;
+};
+
+__global__ void __launch_bounds__(256) tr_gcn_bwd_kernel(GcnBT a) {
+  extern __shared__ __align__(16) float sm[];
+  const int c = blockIdx.x, b = blockIdx.y, N = a.N, OW = a.OW, NS = N + 1;
+  float* At = sm;                 // [N][N + 1]
+  float* G = At + N * NS;         // [N][N + 1]   dA^_ij = sum_o dY_io XW_jo
+  float* dv = G + N * NS;         // [N]
+  float* dg = dv + N;             // [N]  degraw
+  float* dd = dg + N;             // [N]  d loss / d deg
+  float* xw = dd + N;             // [N][OW]
+  float* dy = xw + N * OW;        // [N][OW]
+  const int tid = threadIdx.x;
+  const float* P = a.planes + b * a.p_bs + (int64_t)c * N * N;
+  const int64_t r0 = ((int64_t)c * a.B + b) * N;
+  for (int idx = tid; idx < N * N; idx += 256) {
+    const int i = idx / N, j = idx - i * N;
+    At[i * NS + j] = i == j ? 1.f : P[idx];
+  }
+  for (int i = tid; i < N; i += 256) {
+    dv[i] = a.d[r0 + i];
+    dg[i] = a.degraw[r0 + i];
+  }
+  for (int idx = tid; idx < N * OW; idx += 256) {
+    xw[idx] = a.XW[r0 * OW + idx];
+    dy[idx] = a.dY[r0 * OW + idx];
+  }
+  __syncthreads();
+  // d(xW)_j = sum_i A^_ij dY_i
+  for (int idx = tid; idx < N * OW; idx += 256) {
+    const int j = idx / OW, o = idx - j * OW;
+    float s = 0.f;
+    for (int i = 0; i < N; ++i) s = fmaf(At[i * NS + j] * dv[i], dy[i * OW + o], s);
+    a.dXW[(r0 + j) * OW + o] = dv[j] * s;
+  }
+  if (a.dbias) {
+    for (int o = tid; o < OW; o += 256) {
+      float s = 0.f;
+      for (int i = 0; i < N; ++i) s += dy[i * OW + o];
+      atomicAdd(a.dbias + (int64_t)c * a.b_cs + o, s);
+    }
+  }
+  if (!a.dplanes) return;
+  for (int idx = tid; idx < N * N; idx += 256) {
+    const int i = idx / N, j = idx - i * N;
+    float s = 0.f;
+    for (int o = 0; o < OW; ++o) s = fmaf(dy[i * OW + o], xw[j * OW + o], s);
+    G[i * NS + j] = s;
+  }
+  __syncthreads();
+  // d as the row factor + as the column factor of A^_ij = d_i A~_ij d_j; deg_i = sum_j A~_ij; d = clamp(deg, 1)^-1/2
+  for (int k = tid; k < N; k += 256) {
+    float s = 0.f;
+    for (int j = 0; j < N; ++j) s = fmaf(G[k * NS + j] * At[k * NS + j], dv[j], s);
+    for (int i = 0; i < N; ++i) s = fmaf(G[i * NS + k] * At[i * NS + k], dv[i], s);
+    const float d3 = dv[k] * dv[k] * dv[k];
+    dd[k] = dg[k] >= 1.f ? -0.5f * d3 * s : 0.f;
+  }
+  __syncthreads();
+  float* dP = a.dplanes + b * a.dp_bs + (int64_t)c * N * N;
+  for (int idx = tid; idx < N * N; idx += 256) {
+    const int i = idx / N, j = idx - i * N;
+    if (i == j) continue;                                  // the diagonal of A~ is the constant 1
+    dP[idx] += dv[i] * G[i * NS + j] * dv[j] + dd[i];
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// attention maps (attention.py:35-49): T = mean_h tanh(Q_h K_h^T / sqrt(out_dim)), M = (T + T^T) / 2
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) tr_maps_fwd_kernel(const float* __restrict__ Y, float* __restrict__ M, int B, int C, int N,
+                                                          int OW, int attn, int heads, float scale) {
+  extern __shared__ __align__(16) float sm[];
+  const int c = blockIdx.x, b = blockIdx.y, NS = N + 1;
+  float* qk = sm;                  // [N][2 attn]
+  float* T = qk + N * 2 * attn;    // [N][N + 1]
+  const int tid = threadIdx.x, hd = attn / heads;
+  const int64_t r0 = ((int64_t)c * B + b) * N;
+  for (int idx = tid; idx < N * 2 * attn; idx += 256) {
+    const int i = idx / (2 * attn), o = idx - i * 2 * attn;
+    qk[idx] = Y[(r0 + i) * OW + o];
+  }
+  __syncthreads();
+  for (int idx = tid; idx < N * N; idx += 256) {
+    const int i = idx / N, j = idx - i * N;
+    const float* q = qk + i * 2 * attn;
+    const float* k = qk + j * 2 * attn + attn;
+    float t = 0.f;
+    for (int h = 0; h < heads; ++h) {
+      float s = 0.f;
+      for (int e = 0; e < hd; ++e) s = fmaf(q[h * hd + e], k[h * hd + e], s);
+      t += tanhf(s * scale);
+    }
+    T[i * NS + j] = t / (float)heads;
+  }
+  __syncthreads();
+  float* Mo = M + ((int64_t)b * C + c) * N * N;
+  for (int idx = tid; idx < N * N; idx += 256) {
+    const int i = idx / N, j = idx - i * N;
+    Mo[idx] = 0.5f * (T[i * NS + j] + T[j * NS + i]);
+  }
+}
+
+// dT = (dM + dM^T) / 2; dS_h = dT / H * (1 - tanh^2) * scale; dQ_h = dS_h K_h; dK_h = dS_h^T Q_h  -> dY columns [0, 2 attn)
+__global__ void __launch_bounds__(256) tr_maps_bwd_kernel(const float* __restrict__ Y, const float* __restrict__ dM,
+                                                          float* __restrict__ dY, int B, int C, int N, int OW, int attn, int heads,
+                                                          float scale) {
+  extern __shared__ __align__(16) float sm[];
+  const int c = blockIdx.x, b = blockIdx.y, NS = N + 1;
+  float* qk = sm;                  // [N][2 attn]
+  float* dT = qk + N * 2 * attn;   // [N][N + 1]
+  const int tid = threadIdx.x, hd = attn / heads;
+  const int64_t r0 = ((int64_t)c * B + b) * N;
+  for (int idx = tid; idx < N * 2 * attn; idx += 256) {
+    const int i = idx / (2 * attn), o = idx - i * 2 * attn;
+    qk[idx] = Y[(r0 + i) * OW + o];
+  }
+  const float* Mi = dM + ((int64_t)b * C + c) * N * N;
+  for (int idx = tid; idx < N * N; idx += 256) {
+    const int i = idx / N, j = idx - i * N;
+    dT[i * NS + j] = 0.5f * (Mi[idx] + Mi[j * N + i]);
+  }
+  __syncthreads();
+  const float hs = scale / (float)heads;
+  // items: (node, head, q | k)
+  for (int item = tid; item < N * heads * 2; item += 256) {
+    const int which = item / (N * heads), rem = item - which * N * heads;
+    const int i = rem / heads, h = rem - i * heads;
+    float acc[16];                  // head width <= 16 (attn <= 64)
+#pragma unroll
+    for (int e = 0; e < 16; ++e) acc[e] = 0.f;
+    for (int j = 0; j < N; ++j) {
+      // which = 0: dQ_i += dS_ij K_j ;  which = 1: dK_i += dS_ji Q_j
+      const float* q = which == 0 ? qk + i * 2 * attn + h * hd : qk + j * 2 * attn + h * hd;
+      const float* k = which == 0 ? qk + j * 2 * attn + attn + h * hd : qk + i * 2 * attn + attn + h * hd;
+      float s = 0.f;
+      for (int e = 0; e < hd; ++e) s = fmaf(q[e], k[e], s);
+      const float th = tanhf(s * scale);
+      const float ds = (which == 0 ? dT[i * NS + j] : dT[j * NS + i]) * hs * (1.f - th * th);
+      const float* other = which == 0 ? k : q;
+#pragma unroll
+      for (int e = 0; e < 16; ++e)
+        if (e < hd) acc[e] = fmaf(ds, other[e], acc[e]);
+    }
+    float* dst = dY + (r0 + i) * OW + which * attn + h * hd;
+#pragma unroll
+    for (int e = 0; e < 16; ++e)
+      if (e < hd) dst[e] = acc[e];
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// glue kernels (grid-stride over elements)
+// ---------------------------------------------------------------------------------------
+#define GRID_STRIDE(i, n) for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < (n); i += (int64_t)gridDim.x * blockDim.x)
+
+// utils/graph_utils.py:133-142: plane 0 = adj, plane 1 = adj @ adj (c_init <= 2)
+__global__ void tr_pow_kernel(const float* __restrict__ adj, float* __restrict__ S, int64_t s_bs, int B, int N, int cinit) {
+  GRID_STRIDE(e, (int64_t)B * N * N) {
+    const int64_t b = e / (N * N);
+    const int idx = (int)(e - b * N * N), i = idx / N, j = idx - i * N;
+    const float* A = adj + b * N * N;
+    S[b * s_bs + idx] = A[idx];
+    if (cinit > 1) {
+      float s = 0.f;
+      for (int m = 0; m < N; ++m) s = fmaf(A[i * N + m], A[m * N + j], s);
+      S[b * s_bs + (int64_t)N * N + idx] = s;
+    }
+  }
+}
+
+// edge-MLP input rows (attention.py:109-110): ein[(b, i, j)] = [M_0 .. M_{C-1}, P_0 .. P_{C-1}]
+__global__ void tr_edge_rows_kernel(const float* __restrict__ M, const float* __restrict__ planes, int64_t p_bs,
+                                    float* __restrict__ ein, int B, int C, int N) {
+  GRID_STRIDE(e, (int64_t)B * N * N * 2 * C) {
+    const int k = (int)(e % (2 * C));
+    const int64_t row = e / (2 * C);
+    const int64_t b = row / (N * N);
+    const int ij = (int)(row - b * N * N);
+    ein[e] = k < C ? M[(b * C + k) * N * N + ij] : planes[b * p_bs + (int64_t)(k - C) * N * N + ij];
+  }
+}
+
+// adj_out = mask_adjs(s + s^T) (attention.py:113-114) from the MLP output rows s[(b, i, j)][o]
+__global__ void tr_edge_out_kernel(const float* __restrict__ s, const float* __restrict__ flags, float* __restrict__ planes,
+                                   int64_t p_bs, int B, int Co, int N) {
+  GRID_STRIDE(e, (int64_t)B * Co * N * N) {
+    const int ij = (int)(e % (N * N));
+    const int64_t bo = e / (N * N);
+    const int o = (int)(bo % Co);
+    const int64_t b = bo / Co;
+    const int i = ij / N, j = ij - i * N;
+    const float v = s[(b * N * N + ij) * Co + o] + s[(b * N * N + (int64_t)j * N + i) * Co + o];
+    planes[b * p_bs + (int64_t)o * N * N + ij] = v * flags[b * N + i] * flags[b * N + j];
+  }
+}
+
+// gradient of the rows: g[(b, i, j)][o] = f_i f_j (dP_o[i][j] + dP_o[j][i])
+__global__ void tr_edge_gin_kernel(const float* __restrict__ dplanes, int64_t p_bs, const float* __restrict__ flags,
+                                   float* __restrict__ g, int B, int Co, int N) {
+  GRID_STRIDE(e, (int64_t)B * N * N * Co) {
+    const int o = (int)(e % Co);
+    const int64_t row = e / Co;
+    const int64_t b = row / (N * N);
+    const int ij = (int)(row - b * N * N), i = ij / N, j = ij - i * N;
+    const float* dP = dplanes + b * p_bs + (int64_t)o * N * N;
+    g[e] = flags[b * N + i] * flags[b * N + j] * (dP[ij] + dP[j * N + i]);
+  }
+}
+
+// d ein -> dM (assign) and the input planes' gradient (+=)
+__global__ void tr_edge_dein_kernel(const float* __restrict__ dein, float* __restrict__ dM, float* __restrict__ dplanes,
+                                    int64_t p_bs, int B, int C, int N) {
+  GRID_STRIDE(e, (int64_t)B * N * N * 2 * C) {
+    const int k = (int)(e % (2 * C));
+    const int64_t row = e / (2 * C);
+    const int64_t b = row / (N * N);
+    const int ij = (int)(row - b * N * N);
+    if (k < C) dM[(b * C + k) * N * N + ij] = dein[e];
+    else dplanes[b * p_bs + (int64_t)(k - C) * N * N + ij] += dein[e];
+  }
+}
+
+// cat_c V_c rows (attention.py:106) from the per-channel convolution outputs
+__global__ void tr_node_gather_kernel(const float* __restrict__ Y, float* __restrict__ V, int B, int C, int N, int OW, int col0, int h) {
+  GRID_STRIDE(e, (int64_t)B * N * C * h) {
+    const int o = (int)(e % h);
+    const int c = (int)((e / h) % C);
+    const int64_t r = e / ((int64_t)C * h);
+    V[e] = Y[((int64_t)c * B * N + r) * OW + col0 + o];
+  }
+}
+
+__global__ void tr_node_scatter_kernel(const float* __restrict__ dV, float* __restrict__ dY, int B, int C, int N, int OW, int col0, int h) {
+  GRID_STRIDE(e, (int64_t)B * N * C * h) {
+    const int o = (int)(e % h);
+    const int c = (int)((e / h) % C);
+    const int64_t r = e / ((int64_t)C * h);
+    dY[((int64_t)c * B * N + r) * OW + col0 + o] = dV[e];
+  }
+}
+
+// x_out = tanh(mask_x(hn)) (attention.py:107); x2 = tanh(x_out) for ScoreNetworkX_GMH (ScoreNetwork_X.py:81)
+__global__ void tr_node_out_kernel(const float* __restrict__ hn, const float* __restrict__ flags, float* __restrict__ xout,
+                                   float* __restrict__ x2, int64_t rows, int h) {
+  GRID_STRIDE(e, rows * h) {
+    const float v = tanhf(hn[e] * flags[e / h]);
+    xout[e] = v;
+    if (x2) x2[e] = tanhf(v);
+  }
+}
+
+// dpre = mask_x((g_a + g_b) * (1 - x2^2) * (1 - xout^2)):  g_a = gradient from the next layer (or null), g_b = slice of the final
+// MLP's input gradient (row stride ldb, or null); x2 = null for ScoreNetworkA
+__global__ void tr_node_dpre_kernel(const float* __restrict__ ga, const float* __restrict__ gb, int ldb, const float* __restrict__ xout,
+                                    const float* __restrict__ x2, const float* __restrict__ flags, float* __restrict__ dpre,
+                                    int64_t rows, int h) {
+  GRID_STRIDE(e, rows * h) {
+    const int64_t r = e / h;
+    const int o = (int)(e - r * h);
+    float g = (ga ? ga[e] : 0.f) + (gb ? gb[r * ldb + o] : 0.f);
+    if (x2) g *= 1.f - x2[e] * x2[e];
+    const float xo = xout[e];
+    dpre[e] = flags[r] * g * (1.f - xo * xo);
+  }
+}
+
+// final MLP of ScoreNetworkA: input rows = the concatenated stack per pixel (ScoreNetwork_A.py:141-142)
+__global__ void tr_stack_rows_kernel(const float* __restrict__ S, int64_t s_bs, float* __restrict__ rows, int B, int P, int N) {
+  GRID_STRIDE(e, (int64_t)B * N * N * P) {
+    const int p = (int)(e % P);
+    const int64_t row = e / P;
+    const int64_t b = row / (N * N);
+    rows[e] = S[b * s_bs + (int64_t)p * N * N + (row - b * N * N)];
+  }
+}
+
+__global__ void tr_stack_rows_bwd_kernel(const float* __restrict__ drows, float* __restrict__ dS, int64_t s_bs, int B, int P, int N) {
+  GRID_STRIDE(e, (int64_t)B * N * N * P) {
+    const int p = (int)(e % P);
+    const int64_t row = e / P;
+    const int64_t b = row / (N * N);
+    dS[b * s_bs + (int64_t)p * N * N + (row - b * N * N)] = drows[e];
+  }
+}
+
+// score_adj = mask_adjs(out) with a zero diagonal (ScoreNetwork_A.py:143-148); the same factor on the way back
+__global__ void tr_adj_mask_kernel(const float* __restrict__ in, const float* __restrict__ flags, float* __restrict__ out, int B, int N) {
+  GRID_STRIDE(e, (int64_t)B * N * N) {
+    const int64_t b = e / (N * N);
+    const int ij = (int)(e - b * N * N), i = ij / N, j = ij - i * N;
+    out[e] = i == j ? 0.f : in[e] * flags[b * N + i] * flags[b * N + j];
+  }
+}
+
+__global__ void tr_x_mask_kernel(const float* __restrict__ in, const float* __restrict__ flags, float* __restrict__ out, int64_t rows, int F) {
+  GRID_STRIDE(e, rows * F) out[e] = in[e] * flags[e / F];
+}
+
+// strided copy of a [rows][w] block into / out of wider rows
+__global__ void tr_copy_cols_kernel(const float* __restrict__ src, int lds, float* __restrict__ dst, int ldd, int64_t rows, int w) {
+  GRID_STRIDE(e, rows * w) {
+    const int64_t r = e / w;
+    const int o = (int)(e - r * w);
+    dst[r * ldd + o] = src[r * lds + o];
+  }
+}
+
+// tanh'(.) of a plain GCN layer of ScoreNetworkX: g = (g_a + g_b) * (1 - x_l^2)
+__global__ void tr_tanh_bwd_kernel(const float* __restrict__ ga, const float* __restrict__ gb, int ldb, const float* __restrict__ xl,
+                                   int ldx, float* __restrict__ g, int64_t rows, int h) {
+  GRID_STRIDE(e, rows * h) {
+    const int64_t r = e / h;
+    const int o = (int)(e - r * h);
+    const float v = xl[r * ldx + o];
+    g[e] = ((ga ? ga[e] : 0.f) + (gb ? gb[r * ldb + o] : 0.f)) * (1.f - v * v);
+  }
+}
+
+__global__ void tr_tanh_rows_kernel(const float* __restrict__ in, float* __restrict__ out, int ldo, int64_t rows, int h) {
+  GRID_STRIDE(e, rows * h) {
+    const int64_t r = e / h;
+    out[r * ldo + (e - r * h)] = tanhf(in[e]);
+  }
+}
+
+// losses.py:62-79: per-graph loss and d loss / d net.  which = 0 (x, [B][N][F]) or 1 (adj, [B][N][N])
+__global__ void __launch_bounds__(256) tr_dsm_dnet_kernel(const float* __restrict__ net, const float* __restrict__ z,
+                                                          const float* __restrict__ coef, float* __restrict__ dnet,
+                                                          float* __restrict__ lossb, int per, int which, int reduce_mean, int B) {
+  __shared__ float red[40];
+  const int b = blockIdx.x;
+  const float std = coef[b * 6 + 1 + 3 * which], dv = coef[b * 6 + 2 + 3 * which];
+  const float lw = reduce_mean ? 2.f / (float)per : 1.f;         // d(mean of squares) or d(0.5 sum of squares)
+  const float chain = (dv != 0.f ? -std / dv : std) * lw / (float)B;
+  float acc = 0.f;
+  for (int idx = threadIdx.x; idx < per; idx += 256) {
+    const int64_t e = (int64_t)b * per + idx;
+    const float s = dv != 0.f ? -net[e] / dv : net[e];
+    const float r = s * std + z[e];
+    acc = fmaf(r, r, acc);
+    dnet[e] = r * chain;
+  }
+  acc = block_sum(acc, red);
+  if (threadIdx.x == 0) lossb[b * 2 + which] = reduce_mean ? acc / (float)per : 0.5f * acc;
+}
+
+__global__ void __launch_bounds__(1024) tr_mean_kernel(const float* __restrict__ lossb, int B, float* __restrict__ out) {
+  __shared__ float red[40];
+  float a = 0.f, c = 0.f;
+  for (int b = threadIdx.x; b < B; b += blockDim.x) {
+    a += lossb[b * 2 + 0];
+    c += lossb[b * 2 + 1];
+  }
+  a = block_sum(a, red);
+  c = block_sum(c, red);
+  if (threadIdx.x == 0) {
+    out[0] = a / (float)B;
+    out[1] = c / (float)B;
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------
+static inline int egrid(int64_t n) {
+  int64_t g = (n + 255) / 256;
+  return (int)(g > 148 * 32 ? 148 * 32 : (g < 1 ? 1 : g));
+}
+
+struct Arena {
+  char* base;
+  int64_t cur;
+  float* take(int64_t floats) {
+    const int64_t o = cur;
+    cur += ((floats * 4 + 255) / 256) * 256;
+    return base ? reinterpret_cast<float*>(base + o) : nullptr;
+  }
+};
+
+static int set_smem_attr(const void* fn, size_t bytes) {
+  if (bytes > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e != cudaSuccess) return (int)e;
+  }
+  return 0;
+}
+
+static int linear(const float* X, int ldx, const float* W, int ldw, const float* bias, float* Y, int ldy, int64_t M, int K, int NO,
+                  int trans, int act, int accumulate, cudaStream_t st) {
+  const size_t smem = sizeof(float) * ((size_t)K * ((NO + 3) & ~3) + (size_t)TR_TM * (K + 1));
+  int rc = set_smem_attr((const void*)tr_linear_kernel, smem);
+  if (rc) return rc;
+  tr_linear_kernel<<<(unsigned)((M + TR_TM - 1) / TR_TM), 256, smem, st>>>(X, ldx, W, ldw, bias, Y, ldy, M, K, NO, trans, act, accumulate);
+  count_launch();
+  LAUNCH_CHECK();
+  return 0;
+}
+
+static int wgrad(const float* X, int ldx, const float* dY, int ldy, float* dW, int ldw, float* db, int64_t M, int K, int NO,
+                 cudaStream_t st) {
+  if ((int64_t)K * (((NO + 3) & ~3) / 4) > 256 * TR_WG_MAXI) return GDSS_E_UNSUPPORTED;
+  const size_t smem = sizeof(float) * ((size_t)TR_WG_ROWS * K + (size_t)TR_WG_ROWS * ((NO + 3) & ~3));
+  int rc = set_smem_attr((const void*)tr_wgrad_kernel, smem);
+  if (rc) return rc;
+  tr_wgrad_kernel<<<(unsigned)((M + TR_WG_CHUNK - 1) / TR_WG_CHUNK), 256, smem, st>>>(X, ldx, dY, ldy, dW, ldw, db, M, K, NO);
+  count_launch();
+  LAUNCH_CHECK();
+  return 0;
+}
+
+// one Linear of an MLP in the packed blob: W [in][ld] at woff, bias at boff
+struct Lin { int64_t woff, boff; int in, out, ld; };
+
+// forward of an MLP (layers.py:135-153) over M rows; hidden activations are saved in H[0 .. n-2]; returns through `out`
+static int mlp_fwd(const float* blob, const Lin* lin, int n, const float* X, int ldx, float* const* H, float* out, int ldo, int64_t M,
+                   cudaStream_t st) {
+  const float* cur = X;
+  int ld = ldx;
+  for (int i = 0; i < n; ++i) {
+    const bool last = i == n - 1;
+    float* dst = last ? out : H[i];
+    const int ldd = last ? ldo : lin[i].out;
+    int rc = linear(cur, ld, blob + lin[i].woff, lin[i].ld, blob + lin[i].boff, dst, ldd, M, lin[i].in, lin[i].out, 0, last ? 0 : 1, 0, st);
+    if (rc) return rc;
+    cur = dst;
+    ld = ldd;
+  }
+  return 0;
+}
+
+// reverse sweep of an MLP: g = gradient of the output rows [M][out_last] (destroyed); dX (optional) = gradient of the input rows;
+// sa / sb = two scratch row buffers of at least max width
+static int mlp_bwd(const float* blob, float* gblob, const Lin* lin, int n, const float* X, int ldx, float* const* H, float* g, int64_t M,
+                   float* dX, int lddx, float* sa, float* sb, cudaStream_t st) {
+  float* gcur = g;
+  for (int i = n - 1; i >= 0; --i) {
+    if (i < n - 1) {
+      tr_elu_bwd_kernel<<<egrid(M * lin[i].out), 256, 0, st>>>(gcur, H[i], M * lin[i].out);
+      count_launch();
+      LAUNCH_CHECK();
+    }
+    const float* Xi = i == 0 ? X : H[i - 1];
+    const int ldi = i == 0 ? ldx : lin[i - 1].out;
+    int rc = wgrad(Xi, ldi, gcur, lin[i].out, gblob + lin[i].woff, lin[i].ld, gblob + lin[i].boff, M, lin[i].in, lin[i].out, st);
+    if (rc) return rc;
+    if (i > 0 || dX) {
+      float* dst = i == 0 ? dX : (gcur == sa ? sb : sa);
+      const int ldd = i == 0 ? lddx : lin[i].in;
+      rc = linear(gcur, lin[i].out, blob + lin[i].woff, lin[i].ld, nullptr, dst, ldd, M, lin[i].out, lin[i].in, 1, 0, 0, st);
+      if (rc) return rc;
+      gcur = dst;
+    }
+  }
+  return 0;
+}
+
+static size_t gcn_fwd_smem(int N, int OW) { return sizeof(float) * ((size_t)N * (N + 1) + N + (size_t)N * OW); }
+static size_t gcn_bwd_smem(int N, int OW) { return sizeof(float) * (2 * (size_t)N * (N + 1) + 3 * N + 2 * (size_t)N * OW); }
+static size_t maps_smem(int N, int attn) { return sizeof(float) * ((size_t)N * 2 * attn + (size_t)N * (N + 1)); }
+
+// everything one network needs for forward + backward; planned twice (sizes only, then with the arena)
+struct LayerBufs {
+  float *degraw, *d, *XW, *Y, *M, *ein, *H[GDSS_MAX_LIN], *Vcat, *Hn, *xout, *x2;
+};
+
+struct NetBufs {
+  LayerBufs L[GDSS_MAX_LAYERS];
+  float *S, *dS;                    // channel stacks [B][P][N][N] (attention networks)
+  float *cat, *Hf[2], *out;         // final MLP: input rows, hidden rows, output rows
+  float *xcat;                      // X networks: [B * N][fdim]
+  float *xl;                        // ScoreNetworkX: GCN outputs live in xcat; degraw / d / XW per layer in L[]
+  float *dY, *dXW, *dM, *ga, *gb, *gc, *dV, *dHn, *dpre, *dx[2], *dxcat, *hn;
+  int P;                            // planes of the stack
+  int64_t s_bs;
+};
+
+static void plan_bufs(const NetPlan& p, int B, Arena& ar, NetBufs* nb) {
+  memset(nb, 0, sizeof(*nb));
+  const int64_t N = p.N, R = (int64_t)B * N * N, Rn = (int64_t)B * N;
+  const bool isA = p.type == GDSS_NET_A, gcn = p.type == GDSS_NET_X;
+  int64_t wmax = 2 * p.fdim > 4 ? 2 * p.fdim : 4;          // widest row of the MLPs on edge rows
+  if (gcn) {
+    for (int l = 0; l < p.depth; ++l) {
+      nb->L[l].degraw = ar.take(Rn);
+      nb->L[l].d = ar.take(Rn);
+      nb->L[l].XW = ar.take(Rn * p.nhid);
+      nb->L[l].Y = ar.take(Rn * p.nhid);
+    }
+    nb->xcat = ar.take(Rn * p.fdim);
+    nb->Hf[0] = ar.take(Rn * 2 * p.fdim);
+    nb->Hf[1] = ar.take(Rn * 2 * p.fdim);
+    nb->out = ar.take(Rn * p.fout);
+    nb->dxcat = ar.take(Rn * p.fdim);
+    nb->ga = ar.take(Rn * wmax);
+    nb->gb = ar.take(Rn * wmax);
+    nb->gc = ar.take(Rn * wmax);
+    nb->dY = ar.take(Rn * p.nhid);
+    nb->dXW = ar.take(Rn * p.nhid);
+    nb->dx[0] = ar.take(Rn * p.nhid);
+    nb->dx[1] = ar.take(Rn * p.nhid);
+    return;
+  }
+  int P = p.c_init, cmax = p.c_init, owmax = 0;
+  for (int l = 0; l < p.depth; ++l) {
+    const LayerPlan& L = p.layers[l];
+    P += L.c_out;
+    cmax = cmax > L.c_in ? cmax : L.c_in;
+    cmax = cmax > L.c_out ? cmax : L.c_out;
+    owmax = owmax > L.qkvw ? owmax : L.qkvw;
+    wmax = wmax > L.hid ? wmax : L.hid;
+    wmax = wmax > 2 * L.c_in ? wmax : 2 * L.c_in;
+  }
+  nb->P = P;
+  nb->s_bs = (int64_t)P * N * N;
+  nb->S = ar.take((int64_t)B * nb->s_bs);
+  nb->dS = ar.take((int64_t)B * nb->s_bs);
+  for (int l = 0; l < p.depth; ++l) {
+    const LayerPlan& L = p.layers[l];
+    LayerBufs& b = nb->L[l];
+    b.degraw = ar.take(L.c_in * Rn);
+    b.d = ar.take(L.c_in * Rn);
+    b.XW = ar.take(L.c_in * Rn * L.qkvw);
+    b.Y = ar.take(L.c_in * Rn * L.qkvw);
+    b.M = ar.take((int64_t)B * L.c_in * N * N);
+    b.ein = ar.take(R * 2 * L.c_in);
+    for (int i = 0; i < L.nlin - 1; ++i) b.H[i] = ar.take(R * L.hid);
+    b.Vcat = ar.take(Rn * L.c_in * L.nhid);
+    b.Hn = ar.take(Rn * L.hid);
+    b.xout = ar.take(Rn * L.nhid);
+    b.x2 = isA ? nullptr : ar.take(Rn * L.nhid);
+  }
+  if (isA) {
+    nb->cat = ar.take(R * p.fdim);
+    nb->Hf[0] = ar.take(R * 2 * p.fdim);
+    nb->Hf[1] = ar.take(R * 2 * p.fdim);
+    nb->out = ar.take(R);
+  } else {
+    nb->xcat = ar.take(Rn * p.fdim);
+    nb->Hf[0] = ar.take(Rn * 2 * p.fdim);
+    nb->Hf[1] = ar.take(Rn * 2 * p.fdim);
+    nb->out = ar.take(Rn * p.fout);
+    nb->dxcat = ar.take(Rn * p.fdim);
+  }
+  nb->dY = ar.take(cmax * Rn * owmax);
+  nb->dXW = ar.take(cmax * Rn * owmax);
+  nb->dM = ar.take((int64_t)B * cmax * N * N);
+  nb->ga = ar.take(R * wmax);
+  nb->gb = ar.take(R * wmax);
+  nb->gc = ar.take(R * wmax);
+  nb->dV = ar.take(Rn * cmax * p.nhid);
+  nb->dHn = ar.take(Rn * wmax);
+  nb->dpre = ar.take(Rn * p.nhid);
+  nb->dx[0] = ar.take(Rn * (p.nhid > p.F ? p.nhid : p.F));
+  nb->dx[1] = ar.take(Rn * (p.nhid > p.F ? p.nhid : p.F));
+  nb->hn = ar.take(Rn * p.nhid);
+}
+
+static void final_lins(const NetPlan& p, Lin* lin) {
+  const int dims[4] = {p.fdim, 2 * p.fdim, 2 * p.fdim, p.fout};
+  const int lds[3] = {p.Hp, p.Hp, p.foutp};
+  for (int i = 0; i < 3; ++i) lin[i] = Lin{p.fw[i], p.fb[i], dims[i], dims[i + 1], lds[i]};
+}
+
+static void edge_lins(const LayerPlan& L, Lin* lin) {
+  for (int i = 0; i < L.nlin; ++i) {
+    const int in = i == 0 ? 2 * L.c_in : L.hid, out = i == L.nlin - 1 ? L.c_out : L.hid;
+    lin[i] = Lin{L.ew[i], L.eb[i], in, out, out};
+  }
+}
+
+static void node_lins(const LayerPlan& L, Lin* lin) {
+  lin[0] = Lin{L.nw[0], L.nb[0], L.c_in * L.nhid, L.hid, L.hid};
+  lin[1] = Lin{L.nw[1], L.nb[1], L.hid, L.nhid, L.nhid};
+}
+
+struct TrainCtx {
+  const float *px, *padj, *flags;   // perturbed inputs, node flags
+  int B;
+  cudaStream_t st;
+};
+
+#define KCHECK()      \
+  do {                \
+    count_launch();   \
+    LAUNCH_CHECK();   \
+  } while (0)
+
+// ---- AttentionLayer networks (ScoreNetworkA, ScoreNetworkX_GMH): forward with saved activations -> net output
+static int attn_forward(const NetPlan& p, const float* blob, NetBufs& nb, const TrainCtx& t, float* net_out) {
+  const int B = t.B, N = p.N, F = p.F;
+  const int64_t R = (int64_t)B * N * N, Rn = (int64_t)B * N;
+  const bool isA = p.type == GDSS_NET_A;
+  cudaStream_t st = t.st;
+  tr_pow_kernel<<<egrid(R), 256, 0, st>>>(t.padj, nb.S, nb.s_bs, B, N, p.c_init);
+  KCHECK();
+  if (!isA) {
+    tr_copy_cols_kernel<<<egrid(Rn * F), 256, 0, st>>>(t.px, F, nb.xcat, p.fdim, Rn, F);
+    KCHECK();
+  }
+  const float* xin = t.px;
+  int ldx = F, fin = F, cur = 0;
+  for (int l = 0; l < p.depth; ++l) {
+    const LayerPlan& L = p.layers[l];
+    LayerBufs& b = nb.L[l];
+    const bool last = l == p.depth - 1;
+    const bool need_edge = isA || !last, need_node = !isA || !last;
+    GcnT g;
+    g.planes = nb.S + (int64_t)cur * N * N; g.p_bs = nb.s_bs;
+    g.x = xin; g.ldx = ldx; g.fin = fin;
+    g.W = blob + L.wqkv; g.w_cs = (int64_t)L.f_in_p * L.qkvw; g.ldw = L.qkvw;
+    g.bias = blob + L.bqkv; g.b_cs = L.qkvw;
+    g.degraw = b.degraw; g.d = b.d; g.XW = b.XW; g.Y = b.Y;
+    g.B = B; g.N = N; g.OW = L.qkvw;
+    int rc = set_smem_attr((const void*)tr_gcn_fwd_kernel, gcn_fwd_smem(N, L.qkvw));
+    if (rc) return rc;
+    tr_gcn_fwd_kernel<<<dim3(L.c_in, B), 256, gcn_fwd_smem(N, L.qkvw), st>>>(g);
+    KCHECK();
+    if (need_edge) {
+      rc = set_smem_attr((const void*)tr_maps_fwd_kernel, maps_smem(N, L.attn));
+      if (rc) return rc;
+      tr_maps_fwd_kernel<<<dim3(L.c_in, B), 256, maps_smem(N, L.attn), st>>>(b.Y, b.M, B, L.c_in, N, L.qkvw, L.attn, p.heads,
+                                                                             1.0f / sqrtf((float)L.nhid));
+      KCHECK();
+      tr_edge_rows_kernel<<<egrid(R * 2 * L.c_in), 256, 0, st>>>(b.M, nb.S + (int64_t)cur * N * N, nb.s_bs, b.ein, B, L.c_in, N);
+      KCHECK();
+      Lin lin[GDSS_MAX_LIN];
+      edge_lins(L, lin);
+      rc = mlp_fwd(blob, lin, L.nlin, b.ein, 2 * L.c_in, b.H, nb.ga, L.c_out, R, st);
+      if (rc) return rc;
+      tr_edge_out_kernel<<<egrid(R * L.c_out), 256, 0, st>>>(nb.ga, t.flags, nb.S + (int64_t)(cur + L.c_in) * N * N, nb.s_bs, B, L.c_out, N);
+      KCHECK();
+    }
+    if (need_node) {
+      tr_node_gather_kernel<<<egrid(Rn * L.c_in * L.nhid), 256, 0, st>>>(b.Y, b.Vcat, B, L.c_in, N, L.qkvw, 2 * L.attn, L.nhid);
+      KCHECK();
+      Lin lin[2];
+      node_lins(L, lin);
+      float* H[1] = {b.Hn};
+      rc = mlp_fwd(blob, lin, 2, b.Vcat, L.c_in * L.nhid, H, nb.hn, L.nhid, Rn, st);
+      if (rc) return rc;
+      tr_node_out_kernel<<<egrid(Rn * L.nhid), 256, 0, st>>>(nb.hn, t.flags, b.xout, b.x2, Rn, L.nhid);
+      KCHECK();
+      if (!isA) {
+        tr_copy_cols_kernel<<<egrid(Rn * L.nhid), 256, 0, st>>>(b.x2, L.nhid, nb.xcat + F + l * p.nhid, p.fdim, Rn, L.nhid);
+        KCHECK();
+      }
+      xin = isA ? b.xout : b.x2;
+      ldx = L.nhid;
+      fin = L.nhid;
+    }
+    cur += L.c_in;
+  }
+  Lin fl[3];
+  final_lins(p, fl);
+  if (isA) {
+    tr_stack_rows_kernel<<<egrid(R * p.fdim), 256, 0, st>>>(nb.S, nb.s_bs, nb.cat, B, p.fdim, N);
+    KCHECK();
+    int rc = mlp_fwd(blob, fl, 3, nb.cat, p.fdim, nb.Hf, nb.out, 1, R, st);
+    if (rc) return rc;
+    tr_adj_mask_kernel<<<egrid(R), 256, 0, st>>>(nb.out, t.flags, net_out, B, N);
+    KCHECK();
+  } else {
+    int rc = mlp_fwd(blob, fl, 3, nb.xcat, p.fdim, nb.Hf, nb.out, p.fout, Rn, st);
+    if (rc) return rc;
+    tr_x_mask_kernel<<<egrid(Rn * F), 256, 0, st>>>(nb.out, t.flags, net_out, Rn, F);
+    KCHECK();
+  }
+  return 0;
+}
+
+// ---- reverse sweep: dnet = d loss / d (network output) -> parameter gradients in blob layout (gblob, accumulated)
+static int attn_backward(const NetPlan& p, const float* blob, float* gblob, NetBufs& nb, const TrainCtx& t, const float* dnet) {
+  const int B = t.B, N = p.N, F = p.F;
+  const int64_t R = (int64_t)B * N * N, Rn = (int64_t)B * N;
+  const bool isA = p.type == GDSS_NET_A;
+  cudaStream_t st = t.st;
+  cudaError_t e;
+  Lin fl[3];
+  final_lins(p, fl);
+  int rc;
+  if (isA) {
+    // ScoreNetwork_A.py:143-148: zero diagonal, mask_adjs; then the final MLP over the pixel rows; its input gradient IS the
+    // gradient of every plane of the stack
+    tr_adj_mask_kernel<<<egrid(R), 256, 0, st>>>(dnet, t.flags, nb.ga, B, N);
+    KCHECK();
+    rc = mlp_bwd(blob, gblob, fl, 3, nb.cat, p.fdim, nb.Hf, nb.ga, R, nb.gc, p.fdim, nb.ga, nb.gb, st);
+    if (rc) return rc;
+    tr_stack_rows_bwd_kernel<<<egrid(R * p.fdim), 256, 0, st>>>(nb.gc, nb.dS, nb.s_bs, B, p.fdim, N);
+    KCHECK();
+  } else {
+    tr_x_mask_kernel<<<egrid(Rn * F), 256, 0, st>>>(dnet, t.flags, nb.ga, Rn, F);
+    KCHECK();
+    rc = mlp_bwd(blob, gblob, fl, 3, nb.xcat, p.fdim, nb.Hf, nb.ga, Rn, nb.dxcat, p.fdim, nb.ga, nb.gb, st);
+    if (rc) return rc;
+    e = cudaMemsetAsync(nb.dS, 0, sizeof(float) * (size_t)B * nb.s_bs, st);
+    if (e != cudaSuccess) return (int)e;
+  }
+  int cur = 0;
+  for (int l = 0; l < p.depth; ++l) cur += p.layers[l].c_in;
+  const float* dxn = nullptr;           // gradient of this layer's node output coming from the next layer
+  int flip = 0;
+  for (int l = p.depth - 1; l >= 0; --l) {
+    const LayerPlan& L = p.layers[l];
+    LayerBufs& b = nb.L[l];
+    cur -= L.c_in;
+    const bool last = l == p.depth - 1;
+    const bool need_edge = isA || !last, need_node = !isA || !last;
+    const float* xin = l == 0 ? t.px : (isA ? nb.L[l - 1].xout : nb.L[l - 1].x2);
+    const int ldx = l == 0 ? F : L.nhid, fin = L.f_in;
+    e = cudaMemsetAsync(nb.dY, 0, sizeof(float) * (size_t)L.c_in * Rn * L.qkvw, st);
+    if (e != cudaSuccess) return (int)e;
+    if (need_node && (dxn || !isA)) {
+      // attention.py:106-107 backwards: tanh', mask_x, multi_channel MLP, split over the channels' V blocks
+      tr_node_dpre_kernel<<<egrid(Rn * L.nhid), 256, 0, st>>>(dxn, isA ? nullptr : nb.dxcat + F + l * p.nhid, p.fdim, b.xout, b.x2,
+                                                               t.flags, nb.dpre, Rn, L.nhid);
+      KCHECK();
+      Lin lin[2];
+      node_lins(L, lin);
+      float* H[1] = {b.Hn};
+      rc = mlp_bwd(blob, gblob, lin, 2, b.Vcat, L.c_in * L.nhid, H, nb.dpre, Rn, nb.dV, L.c_in * L.nhid, nb.dHn, nb.hn, st);
+      if (rc) return rc;
+      tr_node_scatter_kernel<<<egrid(Rn * L.c_in * L.nhid), 256, 0, st>>>(nb.dV, nb.dY, B, L.c_in, N, L.qkvw, 2 * L.attn, L.nhid);
+      KCHECK();
+    }
+    if (need_edge) {
+      // attention.py:109-114 backwards: mask_adjs, s + s^T, the per-edge MLP, split into the maps' and the planes' gradient
+      tr_edge_gin_kernel<<<egrid(R * L.c_out), 256, 0, st>>>(nb.dS + (int64_t)(cur + L.c_in) * N * N, nb.s_bs, t.flags, nb.ga, B, L.c_out, N);
+      KCHECK();
+      Lin lin[GDSS_MAX_LIN];
+      edge_lins(L, lin);
+      rc = mlp_bwd(blob, gblob, lin, L.nlin, b.ein, 2 * L.c_in, b.H, nb.ga, R, nb.gc, 2 * L.c_in, nb.ga, nb.gb, st);
+      if (rc) return rc;
+      tr_edge_dein_kernel<<<egrid(R * 2 * L.c_in), 256, 0, st>>>(nb.gc, nb.dM, nb.dS + (int64_t)cur * N * N, nb.s_bs, B, L.c_in, N);
+      KCHECK();
+      rc = set_smem_attr((const void*)tr_maps_bwd_kernel, maps_smem(N, L.attn));
+      if (rc) return rc;
+      tr_maps_bwd_kernel<<<dim3(L.c_in, B), 256, maps_smem(N, L.attn), st>>>(b.Y, nb.dM, nb.dY, B, L.c_in, N, L.qkvw, L.attn, p.heads,
+                                                                             1.0f / sqrtf((float)L.nhid));
+      KCHECK();
+    }
+    // the three convolutions of every channel at once (they share A^ and x): layers.py:49-88 backwards
+    GcnBT g;
+    g.planes = nb.S + (int64_t)cur * N * N; g.p_bs = nb.s_bs;
+    g.degraw = b.degraw; g.d = b.d; g.XW = b.XW; g.dY = nb.dY; g.dXW = nb.dXW;
+    g.dplanes = nb.dS + (int64_t)cur * N * N; g.dp_bs = nb.s_bs;
+    g.dbias = gblob + L.bqkv; g.b_cs = L.qkvw;
+    g.B = B; g.N = N; g.OW = L.qkvw;
+    rc = set_smem_attr((const void*)tr_gcn_bwd_kernel, gcn_bwd_smem(N, L.qkvw));
+    if (rc) return rc;
+    tr_gcn_bwd_kernel<<<dim3(L.c_in, B), 256, gcn_bwd_smem(N, L.qkvw), st>>>(g);
+    KCHECK();
+    float* dxi = nb.dx[flip];
+    for (int c = 0; c < L.c_in; ++c) {
+      const float* dxw = nb.dXW + (int64_t)c * Rn * L.qkvw;
+      rc = wgrad(xin, ldx, dxw, L.qkvw, gblob + L.wqkv + (int64_t)c * L.f_in_p * L.qkvw, L.qkvw, nullptr, Rn, fin, L.qkvw, st);
+      if (rc) return rc;
+      if (l > 0) {
+        rc = linear(dxw, L.qkvw, blob + L.wqkv + (int64_t)c * L.f_in_p * L.qkvw, L.qkvw, nullptr, dxi, fin, Rn, L.qkvw, fin, 1, 0,
+                    c > 0 ? 1 : 0, st);
+        if (rc) return rc;
+      }
+    }
+    dxn = l > 0 ? dxi : nullptr;
+    flip ^= 1;
+  }
+  return 0;
+}
+
+// ---- ScoreNetworkX (ScoreNetwork_X.py:32-46): x_l = tanh(DenseGCNConv_l(x_{l-1}, adj)), final MLP on [x, x_1, ..]
+static int gcn_forward(const NetPlan& p, const float* blob, NetBufs& nb, const TrainCtx& t, float* net_out) {
+  const int B = t.B, N = p.N, F = p.F, h = p.nhid;
+  const int64_t Rn = (int64_t)B * N;
+  cudaStream_t st = t.st;
+  tr_copy_cols_kernel<<<egrid(Rn * F), 256, 0, st>>>(t.px, F, nb.xcat, p.fdim, Rn, F);
+  KCHECK();
+  for (int l = 0; l < p.depth; ++l) {
+    LayerBufs& b = nb.L[l];
+    GcnT g;
+    g.planes = t.padj; g.p_bs = (int64_t)N * N;
+    g.x = l == 0 ? nb.xcat : nb.xcat + F + (l - 1) * h; g.ldx = p.fdim; g.fin = l == 0 ? F : h;
+    g.W = blob + p.gw[l]; g.w_cs = 0; g.ldw = h; g.bias = blob + p.gb[l]; g.b_cs = 0;
+    g.degraw = b.degraw; g.d = b.d; g.XW = b.XW; g.Y = b.Y;
+    g.B = B; g.N = N; g.OW = h;
+    int rc = set_smem_attr((const void*)tr_gcn_fwd_kernel, gcn_fwd_smem(N, h));
+    if (rc) return rc;
+    tr_gcn_fwd_kernel<<<dim3(1, B), 256, gcn_fwd_smem(N, h), st>>>(g);
+    KCHECK();
+    tr_tanh_rows_kernel<<<egrid(Rn * h), 256, 0, st>>>(b.Y, nb.xcat + F + l * h, p.fdim, Rn, h);
+    KCHECK();
+  }
+  Lin fl[3];
+  final_lins(p, fl);
+  int rc = mlp_fwd(blob, fl, 3, nb.xcat, p.fdim, nb.Hf, nb.out, p.fout, Rn, st);
+  if (rc) return rc;
+  tr_x_mask_kernel<<<egrid(Rn * F), 256, 0, st>>>(nb.out, t.flags, net_out, Rn, F);
+  KCHECK();
+  return 0;
+}
+
+static int gcn_backward(const NetPlan& p, const float* blob, float* gblob, NetBufs& nb, const TrainCtx& t, const float* dnet) {
+  const int B = t.B, N = p.N, F = p.F, h = p.nhid;
+  const int64_t Rn = (int64_t)B * N;
+  cudaStream_t st = t.st;
+  Lin fl[3];
+  final_lins(p, fl);
+  tr_x_mask_kernel<<<egrid(Rn * F), 256, 0, st>>>(dnet, t.flags, nb.ga, Rn, F);
+  KCHECK();
+  int rc = mlp_bwd(blob, gblob, fl, 3, nb.xcat, p.fdim, nb.Hf, nb.ga, Rn, nb.dxcat, p.fdim, nb.ga, nb.gb, st);
+  if (rc) return rc;
+  const float* dh = nullptr;
+  int flip = 0;
+  for (int l = p.depth - 1; l >= 0; --l) {
+    LayerBufs& b = nb.L[l];
+    tr_tanh_bwd_kernel<<<egrid(Rn * h), 256, 0, st>>>(dh, nb.dxcat + F + l * h, p.fdim, nb.xcat + F + l * h, p.fdim, nb.dY, Rn, h);
+    KCHECK();
+    GcnBT g;
+    g.planes = t.padj; g.p_bs = (int64_t)N * N;
+    g.degraw = b.degraw; g.d = b.d; g.XW = b.XW; g.dY = nb.dY; g.dXW = nb.dXW;
+    g.dplanes = nullptr; g.dp_bs = 0;                       // the adjacency is an input here, not an activation
+    g.dbias = gblob + p.gb[l]; g.b_cs = 0;
+    g.B = B; g.N = N; g.OW = h;
+    rc = set_smem_attr((const void*)tr_gcn_bwd_kernel, gcn_bwd_smem(N, h));
+    if (rc) return rc;
+    tr_gcn_bwd_kernel<<<dim3(1, B), 256, gcn_bwd_smem(N, h), st>>>(g);
+    KCHECK();
+    const float* xin = l == 0 ? nb.xcat : nb.xcat + F + (l - 1) * h;
+    const int fin = l == 0 ? F : h;
+    rc = wgrad(xin, p.fdim, nb.dXW, h, gblob + p.gw[l], h, nullptr, Rn, fin, h, st);
+    if (rc) return rc;
+    if (l > 0) {
+      rc = linear(nb.dXW, h, blob + p.gw[l], h, nullptr, nb.dx[flip], fin, Rn, h, fin, 1, 0, 0, st);
+      if (rc) return rc;
+      dh = nb.dx[flip];
+      flip ^= 1;
+    }
+  }
+  return 0;
+}
+
+struct TrainLayout {
+  NetBufs nx, na;
+  float *flags, *px, *padj, *zx, *zadj, *netx, *neta, *dnetx, *dneta, *lossb;
+  int64_t total;
+};
+
+static void layout_train(const gdss_ctx* ctx, int B, char* base, TrainLayout* t) {
+  Arena ar{base, 0};
+  const int64_t N = ctx->N, F = ctx->F;
+  t->flags = ar.take(B * N);
+  t->px = ar.take(B * N * F);
+  t->zx = ar.take(B * N * F);
+  t->netx = ar.take(B * N * F);
+  t->dnetx = ar.take(B * N * F);
+  t->padj = ar.take(B * N * N);
+  t->zadj = ar.take(B * N * N);
+  t->neta = ar.take(B * N * N);
+  t->dneta = ar.take(B * N * N);
+  t->lossb = ar.take(2 * (int64_t)B);
+  if (ctx->has_x) plan_bufs(ctx->px, B, ar, &t->nx);
+  if (ctx->has_a) plan_bufs(ctx->pa, B, ar, &t->na);
+  t->total = ar.cur;
+}
+
+}  // namespace gdss
+
+using namespace gdss;
+
+extern "C" int64_t gdss_train_workspace_bytes(const gdss_ctx* ctx, int32_t B) {
+  if (!ctx || B <= 0) return GDSS_E_BADARG;
+  if (ctx->N > 128) return GDSS_E_UNSUPPORTED;
+  TrainLayout t;
+  layout_train(ctx, B, nullptr, &t);
+  return t.total;
+}
+
+extern "C" int gdss_dsm_loss_backward(gdss_ctx* ctx, const float* x, const float* adj, const float* coef, const float* raw_x,
+                                      const float* raw_adj, int32_t B, int32_t reduce_mean, float* grad_blob_x, float* grad_blob_a,
+                                      float* loss_out, void* train_workspace, int64_t train_workspace_bytes, void* stream) {
+  if (!ctx || !x || !adj || !coef || !raw_x || !raw_adj || !grad_blob_x || !grad_blob_a || !loss_out || !train_workspace || B <= 0)
+    return GDSS_E_BADARG;
+  if (!ctx->has_x || !ctx->has_a) return GDSS_E_BADARG;
+  if (gdss_device_count() == 0) return GDSS_E_UNSUPPORTED;          // no CPU fallback
+  if (ctx->N > 128) return GDSS_E_UNSUPPORTED;
+  const int N = ctx->N, F = ctx->F;
+  TrainLayout t;
+  layout_train(ctx, B, (char*)train_workspace, &t);
+  if (train_workspace_bytes < t.total) return GDSS_E_WORKSPACE;
+  {
+    const size_t need = gcn_bwd_smem(N, ctx->pa.layers[0].qkvw > ctx->pa.nhid ? ctx->pa.layers[0].qkvw : ctx->pa.nhid);
+    if ((int64_t)need > ctx->smem_optin) return GDSS_E_UNSUPPORTED;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaError_t e = cudaMemsetAsync(grad_blob_x, 0, sizeof(float) * (size_t)ctx->px.total, st);
+  if (e == cudaSuccess) e = cudaMemsetAsync(grad_blob_a, 0, sizeof(float) * (size_t)ctx->pa.total, st);
+  if (e != cudaSuccess) return (int)e;
+  // losses.py:47-58: node flags of the data, masked noise, perturbed inputs
+  int rc = launch_dsm_perturb(x, adj, coef, raw_x, raw_adj, t.flags, t.px, t.padj, t.zx, t.zadj, B, N, F, st);
+  if (rc) return rc;
+  TrainCtx tc{t.px, t.padj, t.flags, B, st};
+  // ---- node-feature network: forward, loss (losses.py:60-67), reverse sweep
+  if (ctx->px.type == GDSS_NET_X) rc = gcn_forward(ctx->px, ctx->blob_x, t.nx, tc, t.netx);
+  else rc = attn_forward(ctx->px, ctx->blob_x, t.nx, tc, t.netx);
+  if (rc) return rc;
+  tr_dsm_dnet_kernel<<<B, 256, 0, st>>>(t.netx, t.zx, coef, t.dnetx, t.lossb, N * F, 0, reduce_mean, B);
+  count_launch();
+  LAUNCH_CHECK();
+  if (ctx->px.type == GDSS_NET_X) rc = gcn_backward(ctx->px, ctx->blob_x, grad_blob_x, t.nx, tc, t.dnetx);
+  else rc = attn_backward(ctx->px, ctx->blob_x, grad_blob_x, t.nx, tc, t.dnetx);
+  if (rc) return rc;
+  // ---- adjacency network
+  rc = attn_forward(ctx->pa, ctx->blob_a, t.na, tc, t.neta);
+  if (rc) return rc;
+  tr_dsm_dnet_kernel<<<B, 256, 0, st>>>(t.neta, t.zadj, coef, t.dneta, t.lossb, N * N, 1, reduce_mean, B);
+  count_launch();
+  LAUNCH_CHECK();
+  rc = attn_backward(ctx->pa, ctx->blob_a, grad_blob_a, t.na, tc, t.dneta);
+  if (rc) return rc;
+  tr_mean_kernel<<<1, 1024, 0, st>>>(t.lossb, B, loss_out);
+  count_launch();
+  LAUNCH_CHECK();
+  return 0;
+}

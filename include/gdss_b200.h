@@ -116,8 +116,8 @@ int gdss_pack_weights(const gdss_net_desc* desc, int32_t n_nodes, const float* c
 /* Dead sub-network report of a packed HOST blob (what gdss_ctx_create finds and switches off; gdss_pack.cu
  * analyze_liveness): out[4*l + {0,1,2,3}] = {bit mask of channels whose Q/K chain + attention map is live, bit mask of
  * channels whose V convolution is live, the layer's node output is read downstream, the layer's per-edge MLP output is
- * a constant} for the AttentionLayer l (attention.py:93-116).  Weight blocks with max |w| < 1e-30 are dead (the shipped
- * checkpoints' weight-decayed sub-networks).  Returns the number of chains / MLPs switched off (<0 on error). */
+ * a constant} for the AttentionLayer l (attention.py:93-116).  Weight blocks with max |w| < 1e-12 are dead (the shipped
+ * checkpoints' weight-decayed sub-networks, 1e-14 .. 1e-40: their contribution is below 1/60 of an fp32 ulp).  Returns the number of chains / MLPs switched off (<0 on error). */
 int gdss_analyze_weights(const gdss_net_desc* desc, int32_t n_nodes, const float* host_blob, int32_t* out, int32_t max_layers);
 
 /* ---- context ------------------------------------------------------------------------
@@ -179,6 +179,21 @@ int64_t gdss_dsm_scratch_floats(const gdss_ctx* ctx, int32_t B);
 int gdss_dsm_loss(gdss_ctx* ctx, const float* x, const float* adj, const float* coef, const float* raw_x,
                   const float* raw_adj, int32_t B, int32_t reduce_mean, float* scratch, int64_t scratch_floats,
                   float* loss_out, void* workspace, int64_t workspace_bytes, void* stream);
+
+/* ---- denoising-score-matching training step: both losses AND their parameter gradients -------------------------------
+ * Replaces trainer.py:57-65 (loss_fn, loss_x.backward(), loss_adj.backward()) for one batch: the forward of gdss_dsm_loss with
+ * every activation kept in `train_workspace`, then the hand-derived reverse sweep of both score networks (DenseGCNConv incl.
+ * the gradient through the degree normalisation into the adjacency channels, tanh attention maps, per-edge / node / final
+ * MLPs, symmetrisation, masks; layers.py:49-88, :135-153, attention.py:25-51, :93-116, ScoreNetwork_A.py:131-150,
+ * ScoreNetwork_X.py:32-46, :75-89).  x / adj / coef / raw_x / raw_adj / reduce_mean as in gdss_dsm_loss.
+ * grad_blob_x / grad_blob_a (device, gdss_packed_floats floats each, overwritten): d loss_x / d theta_x and
+ * d loss_adj / d theta_adj in the LAYOUT OF THE PACKED BLOBS (padding entries stay 0); parameters a loss never reaches get 0.
+ * The context's blobs are read as the current weights (update them in place between steps).  Every node is evaluated (dense
+ * layouts, no dead-chain elimination); N <= 128.  loss_out[0..1] on the device.  No host synchronisation. */
+int64_t gdss_train_workspace_bytes(const gdss_ctx* ctx, int32_t B);
+int gdss_dsm_loss_backward(gdss_ctx* ctx, const float* x, const float* adj, const float* coef, const float* raw_x,
+                           const float* raw_adj, int32_t B, int32_t reduce_mean, float* grad_blob_x, float* grad_blob_a,
+                           float* loss_out, void* train_workspace, int64_t train_workspace_bytes, void* stream);
 
 /* ---- NCCL plumbing (dlopen'ed; the library loads without NCCL) ------------------------- */
 int gdss_nccl_unique_id(void* id128);                         /* rank 0: 128-byte id       */
