@@ -126,6 +126,7 @@ struct FLayer {
   // edge_const: the per-edge MLP's output is the constant cst[] (times the flag mask)
   unsigned qk_live, v_live;
   int nact, nqk, edge_const;
+  unsigned long long vk_live;          // k-steps (8 inputs each) of the node MLP's first linear that belong to live V blocks
   signed char act[8], qkc[8];
   float cst[8];
   const float* blk_q; int q_floats, bq_o;                 // [c_in][f_in_p][qkvw] then biases [c_in][qkvw]
@@ -674,6 +675,16 @@ DEVINL void edge_mlp_mma(const float* M, int MS, const float* pin, int PM, const
   bia3[0] = 2 * t < c_out ? b3[2 * t] : 0.f;
   bia3[1] = 2 * t + 1 < c_out ? b3[2 * t + 1] : 0.f;
   const int ks1 = (K1 + 7) >> 3;                     // k-steps of layer 1 (1 or 2)
+  bool klive[2][2], slive[2];                        // this lane's layer-1 inputs (k = 8 s + t + 4 q) / whole k-steps that are live
+#pragma unroll
+  for (int s = 0; s < 2; ++s) {
+    slive[s] = s < ks1 && ((kmask >> (8 * s)) & 0xffu);
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const int k = 8 * s + t + 4 * q;
+      klive[s][q] = k < K1 && ((kmask >> k) & 1u);
+    }
+  }
   const int ntile = (P + 15) >> 4;
   for (int tile = warp; tile < ntile; tile += nwarps) {
     const int pa = tile * 16 + g, pb = pa + 8;
@@ -684,13 +695,13 @@ DEVINL void edge_mlp_mma(const float* M, int MS, const float* pin, int PM, const
     for (int j = 0; j < 2; ++j) acc_init(c[j], bia1[j][0], bia1[j][1]);
 #pragma unroll
     for (int s = 0; s < 2; ++s) {
-      if (s < ks1 && ((kmask >> (8 * s)) & 0xffu)) {
+      if (slive[s]) {
         uint32_t ah[4], al[4];
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
           const int k = 8 * s + t + 4 * q;
           float va = 0.f, vb = 0.f;
-          if (k < K1 && ((kmask >> k) & 1u)) {
+          if (klive[s][q]) {
             const float* pl = k < C ? M + k * MS : pin + (k - C) * PM;
             va = pl[pac];
             vb = pl[pbc];
@@ -751,8 +762,9 @@ DEVINL void edge_mlp_mma(const float* M, int MS, const float* pin, int PM, const
 //   cat_c V_c[i] (K = c_in * nhid) -> 16 (ELU) -> nhid, mask, tanh (twice in X_GMH, ScoreNetwork_X.py:81)
 // both layers chained in registers.  V rows have stride ldv = K + 4 (bank-conflict-free A fragments).
 DEVINL void node_mlp_mma(const float* V, int ldv, int K, const float* W1, const float* b1, const float* W2, const float* b2, int n,
-                         int h, const float* fl, bool twice, float* xo, int ldo, int warp, int nwarps, int lane, unsigned vmask) {
-  // vmask: bit c set = the V block of channel c is live (k-steps of dead blocks are skipped; h is a multiple of 8)
+                         int h, const float* fl, bool twice, float* xo, int ldo, int warp, int nwarps, int lane,
+                         unsigned long long kstep_live) {
+  // kstep_live: bit s set = k-step s (inputs 8 s .. 8 s + 7 of the concatenated V rows) belongs to a live channel
   const int g = lane >> 2, t = lane & 3;
   const int mt = (n + 15) >> 4;
   for (int m = warp; m < mt; m += nwarps) {
@@ -762,10 +774,9 @@ DEVINL void node_mlp_mma(const float* V, int ldv, int K, const float* W1, const 
     Acc c[2];
 #pragma unroll
     for (int j = 0; j < 2; ++j) acc_init(c[j], b1[8 * j + 2 * t], b1[8 * j + 2 * t + 1]);
-    for (int cb = 0, ch = 0; cb < K; cb += h, ++ch) {          // channel blocks of the concatenated V rows (no division)
-      if (!((vmask >> ch) & 1u)) continue;
 #pragma unroll 2
-    for (int k0 = cb; k0 < cb + h; k0 += 8) {
+    for (int k0 = 0; k0 < K; k0 += 8) {
+      if (!((kstep_live >> (k0 >> 3)) & 1ull)) continue;
       uint32_t ah[4], al[4];
       const Split a0 = split_tf32(va[k0 + t]), a1 = split_tf32(vb[k0 + t]);
       const Split a2 = split_tf32(va[k0 + t + 4]), a3 = split_tf32(vb[k0 + t + 4]);
@@ -775,7 +786,6 @@ DEVINL void node_mlp_mma(const float* V, int ldv, int K, const float* W1, const 
         const Split w0 = split_tf32(W1[(k0 + t) * 16 + 8 * j + g]), w1 = split_tf32(W1[(k0 + t + 4) * 16 + 8 * j + g]);
         mma3(c[j], ah, al, w0, w1);
       }
-    }
     }
     uint32_t eh[2][4], el[2][4];                       // ELU(h1) as the A fragments of the second linear (permuted k order)
 #pragma unroll
@@ -1480,7 +1490,7 @@ __global__ void __launch_bounds__(NT, OCC) fused_layers_kernel(const __grid_cons
         const int ltid = node_warps ? tid - nt_edge : tid, lnt = node_warps ? 32 * node_warps : nt;
         if (A.use_mma) {
           node_mlp_mma(R2, LDV, C * h, wmp + L.nw0_o, wmp + L.nb0_o, wmp + L.nw1_o, wmp + L.nb1_o, n, h, fl, !isA, xb, XS, ltid >> 5,
-                       lnt >> 5, lane, L.v_live);
+                       lnt >> 5, lane, L.vk_live);
         } else {
           node_l1(R2, LDV, C * h, wmp + L.nw0_o, wmp + L.nb0_o, n, h1, ltid, lnt);
           if (node_warps) asm volatile("bar.sync 1, %0;" ::"r"(lnt) : "memory");
@@ -2157,6 +2167,10 @@ static void fill_net(const NetPlan& p, const float* blob, FNet* f) {
       if ((o.qk_live >> c) & 1u) o.qkc[o.nqk++] = (signed char)c;
     }
     for (int c = 0; c < 8; ++c) o.cst[c] = c < L.c_out ? L.edge_cst[c] : 0.f;
+    o.vk_live = 0ull;
+    for (int c = 0; c < L.c_in && c < 8; ++c)
+      if ((o.v_live >> c) & 1u)
+        for (int k = c * L.nhid / 8; k < (c + 1) * L.nhid / 8 && k < 64; ++k) o.vk_live |= 1ull << k;
     o.blk_q = blob + L.wqkv;
     o.bq_o = (int)(L.bqkv - L.wqkv);
     o.q_floats = (int)(L.ew[0] - L.wqkv);                        // wqkv + bqkv (both padded to 4 floats)

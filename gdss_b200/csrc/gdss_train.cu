@@ -602,26 +602,42 @@ static int set_smem_attr(const void* fn, size_t bytes) {
   return 0;
 }
 
+#define TR_NO_TILE 96        // output columns per launch of the linear kernel (wide layers are tiled over their outputs)
+#define TR_K_TILE 128        // input rows per launch of the weight-gradient kernel
+
 static int linear(const float* X, int ldx, const float* W, int ldw, const float* bias, float* Y, int ldy, int64_t M, int K, int NO,
                   int trans, int act, int accumulate, cudaStream_t st) {
-  const size_t smem = sizeof(float) * ((size_t)K * ((NO + 3) & ~3) + (size_t)TR_TM * (K + 1));
-  int rc = set_smem_attr((const void*)tr_linear_kernel, smem);
-  if (rc) return rc;
-  tr_linear_kernel<<<(unsigned)((M + TR_TM - 1) / TR_TM), 256, smem, st>>>(X, ldx, W, ldw, bias, Y, ldy, M, K, NO, trans, act, accumulate);
-  count_launch();
-  LAUNCH_CHECK();
+  for (int o0 = 0; o0 < NO; o0 += TR_NO_TILE) {
+    const int no = NO - o0 < TR_NO_TILE ? NO - o0 : TR_NO_TILE;
+    const size_t smem = sizeof(float) * ((size_t)K * ((no + 3) & ~3) + (size_t)TR_TM * (K + 1));
+    int rc = set_smem_attr((const void*)tr_linear_kernel, smem);
+    if (rc) return rc;
+    // output column o of the tile = column o0 + o: W[k][o0 + o] (trans = 0) or row o0 + o of W (trans = 1)
+    const float* Wt = trans ? W + (int64_t)o0 * ldw : W + o0;
+    tr_linear_kernel<<<(unsigned)((M + TR_TM - 1) / TR_TM), 256, smem, st>>>(X, ldx, Wt, ldw, bias ? bias + o0 : nullptr, Y + o0, ldy, M, K,
+                                                                             no, trans, act, accumulate);
+    count_launch();
+    LAUNCH_CHECK();
+  }
   return 0;
 }
 
 static int wgrad(const float* X, int ldx, const float* dY, int ldy, float* dW, int ldw, float* db, int64_t M, int K, int NO,
                  cudaStream_t st) {
-  if ((int64_t)K * (((NO + 3) & ~3) / 4) > 256 * TR_WG_MAXI) return GDSS_E_UNSUPPORTED;
-  const size_t smem = sizeof(float) * ((size_t)TR_WG_ROWS * K + (size_t)TR_WG_ROWS * ((NO + 3) & ~3));
-  int rc = set_smem_attr((const void*)tr_wgrad_kernel, smem);
-  if (rc) return rc;
-  tr_wgrad_kernel<<<(unsigned)((M + TR_WG_CHUNK - 1) / TR_WG_CHUNK), 256, smem, st>>>(X, ldx, dY, ldy, dW, ldw, db, M, K, NO);
-  count_launch();
-  LAUNCH_CHECK();
+  for (int k0 = 0; k0 < K; k0 += TR_K_TILE) {
+    const int kt = K - k0 < TR_K_TILE ? K - k0 : TR_K_TILE;
+    for (int o0 = 0; o0 < NO; o0 += TR_NO_TILE) {
+      const int no = NO - o0 < TR_NO_TILE ? NO - o0 : TR_NO_TILE;
+      if ((int64_t)kt * (((no + 3) & ~3) / 4) > 256 * TR_WG_MAXI) return GDSS_E_UNSUPPORTED;
+      const size_t smem = sizeof(float) * ((size_t)TR_WG_ROWS * kt + (size_t)TR_WG_ROWS * ((no + 3) & ~3));
+      int rc = set_smem_attr((const void*)tr_wgrad_kernel, smem);
+      if (rc) return rc;
+      tr_wgrad_kernel<<<(unsigned)((M + TR_WG_CHUNK - 1) / TR_WG_CHUNK), 256, smem, st>>>(
+          X + k0, ldx, dY + o0, ldy, dW + (int64_t)k0 * ldw + o0, ldw, (db && k0 == 0) ? db + o0 : nullptr, M, kt, no);
+      count_launch();
+      LAUNCH_CHECK();
+    }
+  }
   return 0;
 }
 

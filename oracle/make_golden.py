@@ -153,6 +153,95 @@ def make_traj(missing_only=False):
     return out
 
 
+class _EveryNth(list):
+    """trace sink that keeps the state after every n-th solver step only."""
+
+    def __init__(self, n):
+        super().__init__()
+        self.n, self.count = n, 0
+
+    def append(self, rec):
+        self.count += 1
+        if self.count % self.n == 0:
+            super().append({k: rec[k].clone() for k in ("x", "adj", "x_mean", "adj_mean")})
+
+
+SEGMENT_CASES = ["zinc_v2_rev_lang_full_b32"]
+
+
+def make_segments_s4_ref(name="enzymes_s4_full_b4", every=100):
+    """The same for an S4 run whose oracle replay is close but not bit-identical (ENZYMES, N = 125): the intermediate states are
+    taken from the UNMODIFIED reference run itself -- S4_solver evaluates model_x exactly once per step on the current state
+    (solver.py:228), so a forward pre-hook on model_x sees the state after k steps at its k-th call."""
+    import sde as RSDE
+    import solver as RS
+    from oracle.cases import ALL_CASES
+    case = ALL_CASES[name]
+    z = np.load(os.path.join(GOLD, f"traj_{name}.npz"))
+    mx, ma, px, pa = ref_models(case["ckpt"], ema=case.get("ema", False))
+    N, F, B = pa["max_node_num"], pa["max_feat_num"], case["B"]
+    flags = torch.from_numpy(z["flags"])
+    cls = {"VP": RSDE.VPSDE, "VE": RSDE.VESDE, "subVP": RSDE.subVPSDE}
+    sx = cls[case["sde_x"][0]](case["sde_x"][1], case["sde_x"][2], case["scales"])
+    sa = cls[case["sde_adj"][0]](case["sde_adj"][1], case["sde_adj"][2], case["scales"])
+    fn = RS.S4_solver(sx, sa, (B, N, F), (B, N, N), predictor="S4", corrector=case["corrector"], snr=case["snr"],
+                      scale_eps=case["scale_eps"], n_steps=1, probability_flow=False, continuous=True, denoise=True, eps=1e-4,
+                      device="cpu")
+    xs, as_, calls = [], [], [0]
+
+    def hook(mod, args):
+        if calls[0] > 0 and calls[0] % every == 0:
+            xs.append(args[0].detach().clone())
+            as_.append(args[1].detach().clone())
+        calls[0] += 1
+
+    h = mx.register_forward_pre_hook(hook)
+    with numpy_randn(case["seed"]), contextlib.redirect_stdout(io.StringIO()), contextlib.redirect_stderr(io.StringIO()):
+        x, adj, _ = fn(mx, ma, flags)
+    h.remove()
+    same = lambda a, b: torch.equal(a.contiguous().view(torch.int32), torch.from_numpy(b).contiguous().view(torch.int32))
+    assert same(x, z["x"]) and same(adj, z["adj"]) and calls[0] == case["scales"], "the re-run does not reproduce the fixture"
+    # the state after the last step is not seen by a hook: segment k < last ends at xs[k]; the last one at the fixture's means
+    np.savez_compressed(os.path.join(GOLD, f"seg_{name}.npz"), every=every, x=torch.stack(xs).numpy(), adj=torch.stack(as_).numpy(),
+                        x_mean=z["x"], adj_mean=z["adj"])
+    print("segments (reference hooks)", name, len(xs), flush=True)
+    return {name: {"segments": len(xs) + 1, "every": every, "source": "reference forward pre-hook"}}
+
+
+def make_segments(every=100):
+    """Intermediate states of the full-length runs, every `every` solver steps, for segment-wise (teacher-forced) parity of
+    trajectories that are chaotic over 1000 steps (a 2e-7 relative perturbation of the prior changes the reference's own
+    final ZINC250k sample by O(1): tools/chaos_probe.py).  Produced by the oracle, whose final state must equal the
+    UNMODIFIED reference's fixture bit for bit first (same torch ops in the same order), which pins every intermediate."""
+    from oracle.cases import ALL_CASES, case_weights
+    out = {}
+    for name in SEGMENT_CASES:
+        case = ALL_CASES[name]
+        z = np.load(os.path.join(GOLD, f"traj_{name}.npz"))
+        flags = torch.from_numpy(z["flags"])
+        sdx, px, sda, pa = case_weights(case)
+        N, F, B = pa["max_node_num"], pa["max_feat_num"], case["B"]
+        sx, sa = O.SDESpec(*case["sde_x"], case["scales"]), O.SDESpec(*case["sde_adj"], case["scales"])
+        sink = _EveryNth(every)
+        draw = NumpyDraws(case["seed"])
+        with torch.no_grad():
+            if case["predictor"] == "S4":
+                x, adj, _ = O.s4_sample(sx, sa, sdx, px, sda, pa, (B, N, F), (B, N, N), flags, draw, snr=case["snr"],
+                                        scale_eps=case["scale_eps"], denoise=True, eps=1e-4, trace=sink)
+            else:
+                x, adj, _ = O.pc_sample(sx, sa, sdx, px, sda, pa, (B, N, F), (B, N, N), flags, draw, predictor=case["predictor"],
+                                        corrector=case["corrector"], snr=case["snr"], scale_eps=case["scale_eps"], denoise=True,
+                                        eps=1e-4, trace=sink)
+        same = lambda a, b: torch.equal(a.contiguous().view(torch.int32), torch.from_numpy(b).contiguous().view(torch.int32))
+        assert same(x, z["x"]) and same(adj, z["adj"]), f"{name}: the oracle is not bit-identical to the reference run"
+        np.savez_compressed(os.path.join(GOLD, f"seg_{name}.npz"), every=every,
+                            x=torch.stack([r["x"] for r in sink]).numpy(), adj=torch.stack([r["adj"] for r in sink]).numpy(),
+                            x_mean=sink[-1]["x_mean"].numpy(), adj_mean=sink[-1]["adj_mean"].numpy())
+        out[name] = {"segments": len(sink), "every": every}
+        print("segments", name, out[name], flush=True)
+    return out
+
+
 def make_decode():
     """sampler.py:131-138 executed literally on the final state of the full ZINC250k v2 reference run (quantize_mol is
     the reference's own function; the remaining lines are inline in Sampler_mol.sample, which needs rdkit to import)."""
@@ -430,6 +519,10 @@ def only(which):
         manifest["dsm_grad"] = make_dsm_grads()
     elif which == "train":
         manifest["train_steps"] = make_train_steps()
+    elif which == "segs":
+        manifest["segments"] = make_segments()
+    elif which == "segs_ref":
+        manifest.setdefault("segments", {}).update(make_segments_s4_ref())
     elif which == "traj_new":
         manifest["traj"].update(make_traj(missing_only=True))
     else:
@@ -440,4 +533,4 @@ def only(which):
 
 
 if __name__ == "__main__":
-    only(sys.argv[1]) if sys.argv[1:] in (["decode"], ["c1"], ["dsm"], ["mol"], ["dsmgrad"], ["train"], ["traj_new"]) else main()
+    only(sys.argv[1]) if sys.argv[1:] in (["decode"], ["c1"], ["dsm"], ["mol"], ["dsmgrad"], ["train"], ["traj_new"], ["segs"], ["segs_ref"]) else main()

@@ -10,7 +10,8 @@ import sys
 from collections import OrderedDict
 
 tag, outp = sys.argv[1], sys.argv[2]
-CMD = "python bench.py --steps 2 --warmup 3 --batch 2000 --no-cpu-baseline --no-torch-baseline --no-profile"
+CMD = (sys.argv[3] if len(sys.argv) > 3 else
+       "python bench.py --steps 2 --warmup 3 --burn-in 1 --repeats 1 --no-extra --no-cpu-baseline --no-torch-baseline --no-profile")
 
 
 def short(name):
@@ -56,7 +57,7 @@ rd = list(csv.reader(io.StringIO(raw)))
 hdr, units, data = rd[0], rd[1], rd[2:]
 col = {h: i for i, h in enumerate(hdr)}
 with open(f"profiles/{outp}_ncu_full.csv", "w") as f:
-    f.write(f"# ncu --set full --clock-control none --import-source on -k regex:fused_layers_kernel|final_edge_tc_kernel -s 20 -c 6 : {CMD}\n")
+    f.write(f"# ncu --set full --clock-control none --import-source on -k regex:fused_layers_kernel|final_edge_tc_kernel : {CMD}\n")
     f.write("metric,unit," + ",".join('"' + short(r[col["Kernel Name"]]) + '"' for r in data) + "\n")
     for m in METRICS:
         if m in col:
