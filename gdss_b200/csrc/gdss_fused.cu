@@ -1453,14 +1453,15 @@ __global__ void __launch_bounds__(NT, OCC) fused_layers_kernel(const __grid_cons
       }
       // dead chains: their maps are identically zero / their V blocks are never read with a live weight -- zero both so
       // that every reader sees finite values (the regions are private to the dead channel)
-      if (L.need_edge && !L.edge_const && L.nqk < C) {
+      // (the mma variants never read them: edge_mlp_mma gathers live inputs only, node_mlp_mma skips dead k-steps)
+      if (!A.use_mma && L.need_edge && !L.edge_const && L.nqk < C) {
         const bool full_eval = nact > 0 && !(chain_mma || 2 * C > nwarps) && any_qk;     // the CTA-wide path wrote every map
         if (!full_eval)
           for (int c = 0; c < C; ++c)
             if (!((L.qk_live >> c) & 1u))
               for (int p = tid; p < P; p += nt) R1[c * RS + p] = 0.f;
       }
-      if (L.need_node && L.v_live != ((1u << C) - 1u)) {
+      if (!A.use_mma && L.need_node && L.v_live != ((1u << C) - 1u)) {
         const bool full_eval = nact > 0 && !(chain_mma || 2 * C > nwarps) && any_v;
         if (!full_eval)
           for (int c = 0; c < C; ++c)

@@ -208,7 +208,7 @@ def make_segments_s4_ref(name="enzymes_s4_full_b4", every=100):
     return {name: {"segments": len(xs) + 1, "every": every, "source": "reference forward pre-hook"}}
 
 
-def make_segments(every=100):
+def make_segments(every=50):
     """Intermediate states of the full-length runs, every `every` solver steps, for segment-wise (teacher-forced) parity of
     trajectories that are chaotic over 1000 steps (a 2e-7 relative perturbation of the prior changes the reference's own
     final ZINC250k sample by O(1): tools/chaos_probe.py).  Produced by the oracle, whose final state must equal the
@@ -239,6 +239,60 @@ def make_segments(every=100):
                             x_mean=sink[-1]["x_mean"].numpy(), adj_mean=sink[-1]["adj_mean"].numpy())
         out[name] = {"segments": len(sink), "every": every}
         print("segments", name, out[name], flush=True)
+    return out
+
+
+LAYER_KAT = ["qm9", "zinc250k_v2", "community_small"]
+
+
+def make_layer_kat():
+    """Op-level known answers (SURVEY 8c protocol (i)): outputs of the reference's own sub-modules on the KAT inputs, captured
+    with forward hooks -- every AttentionLayer of ScoreNetworkA (node output, adjacency-channel output), the Q / K / V
+    DenseGCNConv outputs of its LAST layer, pow_tensor's stack, and every layer's node features of the X network (as they
+    enter the final concatenation)."""
+    from utils.graph_utils import pow_tensor
+    out = {}
+    for name in LAYER_KAT:
+        mx, ma, px, pa = ref_models(name)
+        N, F, B = pa["max_node_num"], pa["max_feat_num"], 2
+        x, adj, flags = O.kat_inputs(N, F, B)
+        rec = {}
+        hooks = []
+        for l, layer in enumerate(ma.layers):
+            hooks.append(layer.register_forward_hook(lambda m, i, o, l=l: rec.update({f"a_x_{l}": o[0].detach().numpy(), f"a_adj_{l}": o[1].detach().numpy()})))
+        last = ma.layers[-1]
+        for c, att in enumerate(last.attn):
+            for nm in "qkv":
+                hooks.append(getattr(att, f"gnn_{nm}").register_forward_hook(
+                    lambda m, i, o, c=c, nm=nm: rec.update({f"a_last_{nm}_{c}": o.detach().numpy()})))
+        with torch.no_grad():
+            sa = ma(x, adj, flags)
+        for h in hooks:
+            h.remove()
+        # X network: the tensors that enter its final concatenation (ScoreNetwork_X.py:40, :84)
+        xs, hooks = [], []
+        orig_cat = torch.cat
+
+        def spy(tensors, dim=0, **kw):
+            if dim == -1 and len(tensors) == len(mx.layers) + 1 and tensors[0].shape == x.shape:
+                xs.extend(t.detach().numpy() for t in tensors)
+            return orig_cat(tensors, dim=dim, **kw)
+
+        torch.cat = spy
+        try:
+            with torch.no_grad():
+                sxo = mx(x, adj, flags)
+        finally:
+            torch.cat = orig_cat
+        assert len(xs) == len(mx.layers) + 1, "the X network's concatenation was not seen"
+        for l, t in enumerate(xs[1:]):
+            rec[f"x_x_{l}"] = t
+        rec["pow"] = pow_tensor(adj, pa["c_init"]).numpy()
+        rec["score_x"], rec["score_adj"] = sxo.numpy(), sa.numpy()
+        np.savez_compressed(os.path.join(GOLD, f"kat_layers_{name}.npz"), B=B, N=N, F=F, a_layers=len(ma.layers), x_layers=len(mx.layers),
+                            **rec)
+        out[name] = sorted(rec.keys())
+        print("layer kat", name, len(rec), flush=True)
     return out
 
 
@@ -519,6 +573,8 @@ def only(which):
         manifest["dsm_grad"] = make_dsm_grads()
     elif which == "train":
         manifest["train_steps"] = make_train_steps()
+    elif which == "layers":
+        manifest["layer_kat"] = make_layer_kat()
     elif which == "segs":
         manifest["segments"] = make_segments()
     elif which == "segs_ref":
@@ -533,4 +589,4 @@ def only(which):
 
 
 if __name__ == "__main__":
-    only(sys.argv[1]) if sys.argv[1:] in (["decode"], ["c1"], ["dsm"], ["mol"], ["dsmgrad"], ["train"], ["traj_new"], ["segs"], ["segs_ref"]) else main()
+    only(sys.argv[1]) if sys.argv[1:] in (["decode"], ["c1"], ["dsm"], ["mol"], ["dsmgrad"], ["train"], ["traj_new"], ["segs"], ["segs_ref"], ["layers"]) else main()

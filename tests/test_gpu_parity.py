@@ -860,3 +860,85 @@ def test_two_training_iterations_match_the_reference_loop_on_gpu():
     sdx, sda = tr.state_dicts()
     assert list(sdx.keys()) == list(ck["x_state_dict"].keys()) and all(sdx[k].shape == ck["x_state_dict"][k].shape for k in sdx)
     assert list(sda.keys()) == list(ck["adj_state_dict"].keys())
+
+
+@pytest.mark.parametrize("name", ["qm9", "zinc250k_v2", "community_small"])
+@pytest.mark.parametrize("path", ["general", "fused"])
+def test_op_level_outputs_match_reference_modules(name, path):
+    """SURVEY 8c protocol (i): the intermediates of the CUDA paths against outputs of the reference's own sub-modules captured
+    with forward hooks (fixtures kat_layers_*.npz): pow_tensor's stack (a10), D^-1/2 and the Q | K convolutions of the last
+    AttentionLayer (DenseGCNConv a11, Attention a12), every AttentionLayer's adjacency-channel and node output (a13) and every
+    layer's node features of the X network.  `general` reads the HBM-staged path's workspace regions (stack_a, qkv, dis, xa*,
+    xs), `fused` the per-graph kernel's only external intermediates (the pixel-major channel stack stackT, the node stack xs)."""
+    from gdss_b200.engine import Engine
+    z = np.load(os.path.join(GOLD, f"kat_layers_{name}.npz"))
+    ck = load_golden_ckpt(name)
+    B, N, F, LA, LX = int(z["B"]), int(z["N"]), int(z["F"]), int(z["a_layers"]), int(z["x_layers"])
+    x, adj, flags = O.kat_inputs(N, F, B)
+    env = {"GDSS_NO_FUSED": "1", "GDSS_NO_PRUNE": "1"} if path == "general" else {}
+    os.environ.update(env)
+    try:
+        eng = Engine(ck["x_state_dict"], ck["adj_state_dict"], N, "cuda")
+    finally:
+        for k in env:
+            del os.environ[k]
+    ref_stack = torch.from_numpy(np.concatenate([z["pow"]] + [z[f"a_adj_{l}"] for l in range(LA)], axis=1))     # [B, fdim, N, N]
+    fdim = ref_stack.shape[1]
+    ref_xcat = torch.from_numpy(np.concatenate([x.numpy()] + [z[f"x_x_{l}"] for l in range(LX)], axis=-1))      # [B, N, fdim_x]
+    xg, ag, fg = x.cuda(), adj.cuda(), flags.cuda()
+    errs = {}
+    if path == "general":
+        _, sa = eng.score(xg, ag, fg, want_x=False, want_adj=True, inputs_masked=False)
+        torch.cuda.synchronize()
+        stack = eng.region(B, "stack_a", (B, fdim, N, N)).clone()
+        errs["stack"] = rel(stack, ref_stack)
+        for c in range(ref_stack.shape[1]):
+            errs[f"plane{c}"] = rel(stack[:, c], ref_stack[:, c]) if float(ref_stack[:, c].abs().max()) > 1e-20 else 0.0
+        # last AttentionLayer: D^-1/2 of its input channels (layers.py:72-78) and its Q | K convolutions
+        c_in = len([k for k in z.files if k.startswith("a_last_q_")])
+        q0 = torch.from_numpy(z["a_last_q_0"])
+        attn = q0.shape[-1]
+        nh = z["a_last_v_0"].shape[-1]
+        qkvw = 2 * attn + nh
+        qkv = eng.region(B, "qkv", (B, c_in, N, qkvw)).clone()
+        for c in range(c_in):
+            for nm, lo in (("q", 0), ("k", attn)):
+                ref = torch.from_numpy(z[f"a_last_{nm}_{c}"])
+                if float(ref.abs().max()) > 1e-20:
+                    errs[f"{nm}{c}"] = rel(qkv[:, c, :, lo:lo + attn], ref)
+        lo_plane = fdim - z[f"a_adj_{LA - 1}"].shape[1] - c_in
+        planes_in = ref_stack[:, lo_plane:lo_plane + c_in]
+        eye = torch.eye(N)
+        deg = (planes_in * (1 - eye) + eye).sum(-1).clamp(min=1).pow(-0.5)                         # [B, c_in, N]
+        maxc = max([z["pow"].shape[1]] + [z[f"a_adj_{l}"].shape[1] for l in range(LA - 1)])
+        dis = eng.region(B, "dis", (B, maxc, N)).clone()
+        errs["dis"] = rel(dis[:, :c_in], deg)
+        if LA > 1:
+            xa = eng.region(B, "xa0" if (LA - 2) % 2 == 0 else "xa1", (B, N, nh)).clone()
+            errs["x_out"] = rel(xa, torch.from_numpy(z[f"a_x_{LA - 2}"]))
+        eng.score(xg, ag, fg, want_x=True, want_adj=False, inputs_masked=False)
+        torch.cuda.synchronize()
+        xs = eng.region(B, "xs", (B, N, ref_xcat.shape[-1])).clone()
+        errs["xcat"] = rel(xs, ref_xcat)
+    else:
+        sx, sa = eng.score(xg, ag, fg, inputs_masked=False)
+        torch.cuda.synchronize()
+        P = N * (N - 1) // 2
+        pstride = ((B * P + 127) // 128) * 128 + 128
+        st = eng.region(B, "stackT", (fdim, pstride)).clone().cpu()
+        iu = torch.triu_indices(N, N, 1)
+        ref_tri = ref_stack[:, :, iu[0], iu[1]]                                                    # [B, fdim, P], row-major (i < j)
+        got = st[:, :B * P].view(fdim, B, P).permute(1, 0, 2)
+        errs["stackT"] = rel(got, ref_tri)
+        for c in range(fdim):
+            errs[f"plane{c}"] = rel(got[:, c], ref_tri[:, c]) if float(ref_tri[:, c].abs().max()) > 1e-20 else 0.0
+        from gdss_b200 import _lib
+        if name != "community_small":           # its X network's final MLP has no tensor-core instance: the node stack stays on chip
+            fx = ref_xcat.shape[-1]
+            nstride = ((B * N + 127) // 128) * 128 + 128
+            xs = eng.region(B, "xs", (fx, nstride)).clone().cpu()
+            errs["xcat"] = rel(xs[:, :B * N].view(fx, B, N).permute(1, 2, 0), ref_xcat)
+        assert rel(sa, torch.from_numpy(z["score_adj"])) <= TOL and rel(sx, torch.from_numpy(z["score_x"])) <= TOL
+    bad = {k: v for k, v in errs.items() if not v <= TOL}
+    assert not bad, (name, path, bad)
+    print(name, path, "worst op-level error", max(errs.values()))
