@@ -123,7 +123,7 @@ extern "C" int64_t gdss_workspace_bytes(const gdss_ctx* ctx, int32_t B) {
 
 extern "C" int64_t gdss_workspace_offset(const gdss_ctx* ctx, int32_t B, const char* region) {
   static const char* names[R_COUNT] = {"neff", "step", "table", "means", "norms", "stack_a", "stack_x", "dis",
-                                       "qkv", "xa0", "xa1", "xs", "raw_x", "raw_adj", "poff", "meta", "gmap", "order", "stackT", "x0", "a0"};
+                                       "qkv", "xa0", "xa1", "xs", "raw_x", "raw_adj", "poff", "meta", "gmap", "order", "stackT", "x0", "a0", "noff", "nmap"};
   if (!ctx || B <= 0 || !region) return GDSS_E_BADARG;
   Workspace w;
   layout_workspace(ctx, B, &w);

@@ -41,8 +41,10 @@ DEVINL float sig2(float a) { return rcp_ftz(ex2_ftz(a) + 1.f); }
 #define TRI_BINS 66
 __global__ void __launch_bounds__(1024) tri_scan_kernel(const int* __restrict__ neff, int B, int nb0, int nb1,
                                                         int* __restrict__ poff, int* __restrict__ meta,
-                                                        int* __restrict__ gmap, int* __restrict__ order) {
+                                                        int* __restrict__ gmap, int* __restrict__ order,
+                                                        int* __restrict__ noff, int* __restrict__ nmap) {
   __shared__ int part[1024];
+  __shared__ int npart[1024];          // node counts: the compact row index of node (b, i) is noff[b] + i
   __shared__ int hist[TRI_BINS], cursor[TRI_BINS];
   __shared__ int bstart[3], bcount[3];
   const int t = threadIdx.x;
@@ -50,23 +52,28 @@ __global__ void __launch_bounds__(1024) tri_scan_kernel(const int* __restrict__ 
   const int lo = min(B, t * chunk), hi = min(B, lo + chunk);
   if (t < TRI_BINS) hist[t] = 0;
   __syncthreads();
-  int s = 0;
+  int s = 0, sn = 0;
   for (int b = lo; b < hi; ++b) {
     const int n = neff[b];
     s += n * (n - 1) / 2;
+    sn += max(n, 0);
     atomicAdd(&hist[min(max(n, 0), TRI_BINS - 1)], 1);
   }
-  // exclusive prefix of the pixel counts over the threads' chunks
+  // exclusive prefix of the pixel / node counts over the threads' chunks
   part[t] = s;
+  npart[t] = sn;
   __syncthreads();
   for (int off = 1; off < 1024; off <<= 1) {
     int v = t >= off ? part[t - off] : 0;
+    int vn = t >= off ? npart[t - off] : 0;
     __syncthreads();
     part[t] += v;
+    npart[t] += vn;
     __syncthreads();
   }
   int base = part[t] - s;
-  const int tot = part[1023];
+  int nbase = npart[t] - sn;
+  const int tot = part[1023], ntot = npart[1023];
   if (t == 0) {
     int cur = 0;
     for (int k = 0; k < 3; ++k) {
@@ -83,14 +90,21 @@ __global__ void __launch_bounds__(1024) tri_scan_kernel(const int* __restrict__ 
   __syncthreads();
   for (int b = lo; b < hi; ++b) {
     poff[b] = base;
+    if (noff) noff[b] = nbase;
     const int n = neff[b];
     base += n * (n - 1) / 2;
+    nbase += max(n, 0);
     order[atomicAdd(&cursor[min(max(n, 0), TRI_BINS - 1)], 1)] = b;
   }
   if (t == 1023) {
     poff[B] = tot;
     meta[0] = tot;
     meta[1] = (tot + 127) / 128;
+    meta[8] = ntot;                        // valid nodes of the batch / 128-row tiles of the compact node stack
+    meta[9] = (ntot + 127) / 128;
+    if (noff) noff[B] = ntot;
+    if (nmap)
+      for (int k = ntot; k < ((ntot + 127) / 128) * 128; ++k) nmap[k] = -1;
     meta[16] = 0;                          // error flag of the tensor-core kernel (lost mbarrier arrival)
     for (int q = 0; q < 3; ++q) {
       meta[2 + q] = bcount[q];
@@ -102,8 +116,11 @@ __global__ void __launch_bounds__(1024) tri_scan_kernel(const int* __restrict__ 
 
 // gmap[gp] = b << 2 fb | i << fb | j  (fb = 6 bits for the per-graph path, 9 for the general path)
 __global__ void __launch_bounds__(64) tri_map_kernel(const int* __restrict__ neff, const int* __restrict__ poff,
-                                                     int* __restrict__ gmap, int fb) {
+                                                     int* __restrict__ gmap, int fb, const int* __restrict__ noff,
+                                                     int* __restrict__ nmap) {
   const int b = blockIdx.x, n = neff[b], base = poff[b];
+  if (nmap)                                                // compact node rows: nmap[noff[b] + i] = b << 6 | i
+    for (int i = threadIdx.x; i < n; i += blockDim.x) nmap[noff[b] + i] = (b << 6) | i;
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
     const int rs = i * (2 * n - i - 1) / 2;
     for (int j = i + 1; j < n; ++j) gmap[base + rs + j - i - 1] = (b << (2 * fb)) | (i << fb) | j;
@@ -158,6 +175,7 @@ struct FusedArgs {
   float* xst;              // X network: node-feature stack [fdim][nstride] in global memory (final MLP runs in the batched
   int64_t nstride;         // tensor-core kernel) or null (final MLP inside this kernel); row = b * N + i
   const int* poff;
+  const int* noff;         // compact row offset of a graph's nodes in the X network's node stack
   const int* order;        // graph ids sorted by size bucket
   const int* meta;
   int bucket;
@@ -1244,6 +1262,7 @@ __global__ void __launch_bounds__(NT, OCC) fused_layers_kernel(const __grid_cons
   float* R2 = sm + S.r2;           // V rows [i][c][nhid]
   unsigned short* tab = reinterpret_cast<unsigned short*>(sm + S.tab);   // triangle index of (i, j); diagonal / padding -> constant slots
   const int64_t gp0 = A.poff[b];
+  const int64_t xrow0 = A.xst ? A.noff[b] : 0;
   const FastDiv dn(n), dP(P);
 
   if (tid == 0) {
@@ -1325,7 +1344,7 @@ __global__ void __launch_bounds__(NT, OCC) fused_layers_kernel(const __grid_cons
       if (A.xst) {
         for (int idx = tid; idx < n * F; idx += nt) {
           const int k = dn.div(idx), i = idx - k * n;
-          A.xst[(int64_t)k * A.nstride + (int64_t)b * N + i] = x0[i * XS + k];
+          A.xst[(int64_t)k * A.nstride + xrow0 + i] = x0[i * XS + k];
         }
       } else {
         const FastDiv dq(XSS);
@@ -1354,7 +1373,7 @@ __global__ void __launch_bounds__(NT, OCC) fused_layers_kernel(const __grid_cons
         if (A.xst) {
           for (int idx = tid; idx < n * h; idx += nt) {
             const int o = dn.div(idx), i = idx - o * n;
-            A.xst[(int64_t)(F + l * h + o) * A.nstride + (int64_t)b * N + i] = xb[i * XS + o];
+            A.xst[(int64_t)(F + l * h + o) * A.nstride + xrow0 + i] = xb[i * XS + o];
           }
         } else {
           for (int idx = tid; idx < n * h; idx += nt) {
@@ -1531,7 +1550,7 @@ __global__ void __launch_bounds__(NT, OCC) fused_layers_kernel(const __grid_cons
           if (A.xst) {
             for (int idx = tid; idx < n * h; idx += nt) {
               const int o = dn.div(idx), i = idx - o * n;
-              A.xst[(int64_t)(F + l * h + o) * A.nstride + (int64_t)b * N + i] = xb[i * XS + o];
+              A.xst[(int64_t)(F + l * h + o) * A.nstride + xrow0 + i] = xb[i * XS + o];
             }
           } else {
             for (int idx = tid; idx < n * h; idx += nt) {
@@ -1565,6 +1584,7 @@ struct FinalTriArgs {
   int N, fdim, H, Hs;
   const int* neff; int B, F, foutp;      // node mode (X networks): rows = b * N + i, F outputs per row, w3 [Hs][foutp]
   int fb;                                // bits per index field of gmap (6: per-graph path, 9: general path)
+  const int* nmap;                       // node mode: compact row -> b << 6 | i  (-1 on the padding of the last tile)
   int64_t dense_bs;                      // != 0 (general path): stackT is the dense channel stack [b][c][N][N] with this batch stride
 };
 
@@ -1853,7 +1873,7 @@ __global__ void __launch_bounds__(128 * NS, 1) final_edge_tc_kernel(FinalTriArgs
   const float b3 = a.b3[0];
   uint32_t phase = 0, phase2 = 0;
   bool ok = true;
-  const int ntiles = NODE ? (a.B * N + 127) / 128 : a.meta[1];
+  const int ntiles = NODE ? a.meta[9] : a.meta[1];
   // channel values of this thread's pixel for the first tile; every later tile is fetched one tile ahead (the loads
   // are in flight during the two contractions and epilogues of the current tile)
   float v[KH];
@@ -1923,12 +1943,11 @@ __global__ void __launch_bounds__(128 * NS, 1) final_edge_tc_kernel(FinalTriArgs
     float out_f = 0.f;
     if (half == 0) {
       if (NODE) {
-        if (gp < (int64_t)a.B * N) {
-          const int b = (int)(gp / N), i = (int)(gp - (int64_t)b * N);
-          if (i < __ldg(a.neff + b)) {
-            out_b = b;
-            out_f = __ldg(a.flags + (int64_t)b * N + i);
-          }
+        const int nm = __ldg(a.nmap + gp);
+        if (nm >= 0) {
+          out_b = nm >> 6;
+          out_i = nm & 63;
+          out_f = __ldg(a.flags + (int64_t)out_b * N + out_i);
         }
       } else {
         const int gv = __ldg(a.gmap + gp);
@@ -2027,7 +2046,7 @@ __global__ void __launch_bounds__(128 * NS, 1) final_edge_tc_kernel(FinalTriArgs
       if (half == 0 && out_b >= 0) {
         {
           const float f = out_f;
-          float* O = a.out + gp * a.F;
+          float* O = a.out + ((int64_t)out_b * N + out_i) * a.F;
 #pragma unroll
           for (int o = 0; o < FOP; ++o) {
             float acc = dv[o];
@@ -2296,10 +2315,12 @@ int launch_tri_setup(const gdss_ctx* ctx, const int* neff, int B, char* ws, cons
   const int k = size_buckets(ctx->N, nb);
   // scan kernel buckets: n <= nb0 -> 0, n <= nb1 -> 1, else 2 (unused buckets get bounds that never match)
   const int b0 = nb[0], b1 = k > 1 ? nb[1] : nb[0];
-  tri_scan_kernel<<<1, 1024, 0, st>>>(neff, B, b0, b1, poff, meta, gmap, order);
+  int* noff = ctx->fused ? reinterpret_cast<int*>(ws + w.off[R_NOFF]) : nullptr;
+  int* nmap = ctx->fused ? reinterpret_cast<int*>(ws + w.off[R_NMAP]) : nullptr;
+  tri_scan_kernel<<<1, 1024, 0, st>>>(neff, B, b0, b1, poff, meta, gmap, order, noff, nmap);
   launched(K_MISC, st);
   LAUNCH_CHECK();
-  tri_map_kernel<<<B, 64, 0, st>>>(neff, poff, gmap, ctx->fused ? 6 : 9);
+  tri_map_kernel<<<B, 64, 0, st>>>(neff, poff, gmap, ctx->fused ? 6 : 9, noff, nmap);
   launched(K_MISC, st);
   LAUNCH_CHECK();
   return 0;
@@ -2320,6 +2341,7 @@ int launch_eval_fused(const gdss_ctx* ctx, const float* x, const float* adj, con
   fa.raw_x = score_x;
   fa.stackT = reinterpret_cast<float*>(ws + w.off[R_STACKT]);
   fa.poff = reinterpret_cast<const int*>(ws + w.off[R_POFF]);
+  fa.noff = reinterpret_cast<const int*>(ws + w.off[R_NOFF]);
   fa.pstride = w.pstride;
   fa.N = N; fa.F = ctx->F;
   // X network's final MLP: batched tensor-core kernel when its shape has an instance, else inside the per-graph kernel
@@ -2412,6 +2434,7 @@ int launch_eval_fused(const gdss_ctx* ctx, const float* x, const float* adj, con
     ta.w3 = ctx->blob_x + p.fw[2]; ta.b3 = ctx->blob_x + p.fb[2];
     ta.out = score_x; ta.flags = flags; ta.N = N; ta.fdim = p.fdim; ta.H = 2 * p.fdim; ta.Hs = p.Hp;
     ta.neff = neff; ta.B = B; ta.F = ctx->F; ta.foutp = p.foutp;
+    ta.nmap = reinterpret_cast<const int*>(ws + w.off[R_NMAP]);
     e = cudaFuncSetAttribute(xfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xsm);
     if (e != cudaSuccess) return (int)e;
     const int64_t tiles = ((int64_t)B * N + 127) / 128;

@@ -54,7 +54,7 @@ int analyze_liveness(NetPlan* p, const float* host_blob);
 // named workspace regions (byte offsets, 256-aligned)
 enum Region {
   R_NEFF = 0, R_STEP, R_TABLE, R_MEANS, R_NORMS, R_STACK_A, R_STACK_X, R_DIS, R_QKV, R_XA0, R_XA1, R_XS, R_RAW_X, R_RAW_ADJ,
-  R_POFF, R_META, R_GMAP, R_ORDER, R_STACKT, R_X0, R_A0,
+  R_POFF, R_META, R_GMAP, R_ORDER, R_STACKT, R_X0, R_A0, R_NOFF, R_NMAP,
   R_COUNT
 };
 

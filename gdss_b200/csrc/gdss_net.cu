@@ -810,6 +810,8 @@ void layout_workspace(const gdss_ctx* ctx, int B, Workspace* w) {
     // X network: node-feature stack [fdim][nstride] read by the batched tensor-core final MLP
     w->nstride = ((int64_t)B * N + 127) / 128 * 128 + 128;
     sz[R_XS] = ctx->has_x ? 4 * w->nstride * ctx->px.fdim : 0;
+    sz[R_NOFF] = 4 * ((int64_t)B + 1);           // compact node rows of the X network's node stack
+    sz[R_NMAP] = 4 * w->nstride;
   }
   if (final_tc_dense_ok(ctx, B)) {
     // general path with the tensor-core final MLP: pixel bookkeeping only (the kernel reads the dense stack)
