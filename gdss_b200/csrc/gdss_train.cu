@@ -26,82 +26,108 @@ namespace gdss {
     if (e__ != cudaSuccess) return (int)e__;    \
   } while (0)
 
-#define TR_TM 64            // rows per CTA of the linear kernel
+#define TR_TM 256           // rows per CTA of the linear kernel
 #define TR_WG_ROWS 32       // rows per shared-memory tile of the weight-gradient kernel
-#define TR_WG_MAXI 12       // (k, 4 outputs) items per thread: K * NO <= 12288
+#define TR_WG_MAXI 3        // (4 inputs x 4 outputs) items per thread: K * NO <= 12288 per launch
 #define TR_WG_CHUNK 2048    // rows per CTA of the weight-gradient kernel
 
 DEVINL float elu_exact(float v) { return v > 0.f ? v : expm1f(v); }
 
 // Y[m][o] (+)= act(bias[o] + sum_k X[m][k] * Wm[k][o]),  Wm[k][o] = W[k * ldw + o]  (trans = 0: the packed [in][out] weights)
 //                                                     or W[o * ldw + k]  (trans = 1: data gradient dX = dY W)
+// Register-blocked FP32 GEMM for M >> K, NO: one CTA = TR_TM rows x all NO (<= TR_NO_TILE) outputs; the X tile is kept
+// TRANSPOSED in shared memory ([k][row]) so that a thread's 8 rows are two float4 loads, the weights [k][o] give its 4 output
+// columns as one float4: 3 shared-memory loads feed 32 FMAs per k.
 __global__ void __launch_bounds__(256) tr_linear_kernel(const float* __restrict__ X, int ldx, const float* __restrict__ W, int ldw,
                                                         const float* __restrict__ bias, float* __restrict__ Y, int ldy, int64_t M,
-                                                        int K, int NO, int trans, int act, int accumulate) {
+                                                        int K, int NO, int trans, int act, int accumulate, int TM) {
   extern __shared__ __align__(16) float sm[];
-  const int NOP = (NO + 3) & ~3, KS = K + 1;
+  const int NOP = (NO + 3) & ~3;
+  const int TMS = TM + 4;           // row stride of the transposed X tile (16-byte aligned rows); TM = rows per CTA (multiple of 8)
   float* Ws = sm;                   // [K][NOP]
-  float* Xs = Ws + K * NOP;         // [TR_TM][K + 1]
+  float* Xs = Ws + K * NOP;         // [K][TM + 4]
   const int tid = threadIdx.x;
   for (int idx = tid; idx < K * NOP; idx += 256) {
     const int k = idx / NOP, o = idx - k * NOP;
     Ws[idx] = o < NO ? (trans ? W[(int64_t)o * ldw + k] : W[(int64_t)k * ldw + o]) : 0.f;
   }
-  const int64_t m0 = (int64_t)blockIdx.x * TR_TM;
-  for (int idx = tid; idx < TR_TM * K; idx += 256) {
+  const int64_t m0 = (int64_t)blockIdx.x * TM;
+  for (int idx = tid; idx < TM * K; idx += 256) {          // coalesced along k, transposed into shared memory
     const int r = idx / K, k = idx - r * K;
     const int64_t m = m0 + r;
-    Xs[r * KS + k] = m < M ? X[m * ldx + k] : 0.f;
+    Xs[k * TMS + r] = m < M ? X[m * ldx + k] : 0.f;
   }
   __syncthreads();
   const int og = NOP >> 2;
-  for (int item = tid; item < TR_TM * og; item += 256) {
-    const int r = item / og, o4 = (item - r * og) * 4;
-    const int64_t m = m0 + r;
-    if (m >= M) continue;
-    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-    if (bias) {
-      a0 = o4 < NO ? bias[o4] : 0.f; a1 = o4 + 1 < NO ? bias[o4 + 1] : 0.f;
-      a2 = o4 + 2 < NO ? bias[o4 + 2] : 0.f; a3 = o4 + 3 < NO ? bias[o4 + 3] : 0.f;
-    }
-    const float* xr = Xs + r * KS;
-    for (int k = 0; k < K; ++k) {
-      const float xv = xr[k];
-      const float4 w = *reinterpret_cast<const float4*>(Ws + k * NOP + o4);
-      a0 = fmaf(xv, w.x, a0); a1 = fmaf(xv, w.y, a1); a2 = fmaf(xv, w.z, a2); a3 = fmaf(xv, w.w, a3);
-    }
-    float v[4] = {a0, a1, a2, a3};
+  for (int item = tid; item < (TM / 8) * og; item += 256) {
+    const int rg = item / og, o4 = (item - rg * og) * 4;
+    float acc[8][4];
+    {
+      float b4[4] = {0.f, 0.f, 0.f, 0.f};
+      if (bias) {
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      if (o4 + q >= NO) continue;
-      float y = v[q];
-      if (act == 1) y = elu_exact(y);
-      float* dst = Y + m * ldy + o4 + q;
-      *dst = accumulate ? *dst + y : y;
+        for (int q = 0; q < 4; ++q) b4[q] = o4 + q < NO ? bias[o4 + q] : 0.f;
+      }
+#pragma unroll
+      for (int r = 0; r < 8; ++r)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) acc[r][q] = b4[q];
+    }
+    const float* xp = Xs + rg * 8;
+    const float* wp = Ws + o4;
+#pragma unroll 4
+    for (int k = 0; k < K; ++k) {
+      const float4 xa = *reinterpret_cast<const float4*>(xp + k * TMS);
+      const float4 xb = *reinterpret_cast<const float4*>(xp + k * TMS + 4);
+      const float4 w = *reinterpret_cast<const float4*>(wp + k * NOP);
+      const float xv[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
+#pragma unroll
+      for (int r = 0; r < 8; ++r) {
+        acc[r][0] = fmaf(xv[r], w.x, acc[r][0]); acc[r][1] = fmaf(xv[r], w.y, acc[r][1]);
+        acc[r][2] = fmaf(xv[r], w.z, acc[r][2]); acc[r][3] = fmaf(xv[r], w.w, acc[r][3]);
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      const int64_t m = m0 + rg * 8 + r;
+      if (m >= M) continue;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        if (o4 + q >= NO) continue;
+        float y = acc[r][q];
+        if (act == 1) y = elu_exact(y);
+        float* dst = Y + m * ldy + o4 + q;
+        *dst = accumulate ? *dst + y : y;
+      }
     }
   }
 }
 
-// dW[k * ldw + o] += sum_m X[m][k] dY[m][o];  db[o] += sum_m dY[m][o]  over this CTA's row chunk
+// dW[k * ldw + o] += sum_m X[m][k] dY[m][o];  db[o] += sum_m dY[m][o]  over this CTA's row chunk.  One item = 4 inputs x 4
+// outputs (16 accumulators): per row two float4 loads feed 16 FMAs.
 __global__ void __launch_bounds__(256) tr_wgrad_kernel(const float* __restrict__ X, int ldx, const float* __restrict__ dY, int ldy,
                                                        float* __restrict__ dW, int ldw, float* __restrict__ db, int64_t M, int K,
                                                        int NO) {
   extern __shared__ __align__(16) float sm[];
-  const int NOP = (NO + 3) & ~3;
-  float* Xs = sm;                        // [ROWS][K]
-  float* Ys = Xs + TR_WG_ROWS * K;       // [ROWS][NOP]
+  const int NOP = (NO + 3) & ~3, KP = (K + 3) & ~3;
+  float* Xs = sm;                        // [ROWS][KP]
+  float* Ys = Xs + TR_WG_ROWS * KP;      // [ROWS][NOP]
   const int tid = threadIdx.x;
-  const int og = NOP >> 2, items = K * og;
-  float4 acc[TR_WG_MAXI];
+  const int og = NOP >> 2, kg = KP >> 2, items = kg * og;
+  float acc[TR_WG_MAXI][4][4];
 #pragma unroll
-  for (int it = 0; it < TR_WG_MAXI; ++it) acc[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int it = 0; it < TR_WG_MAXI; ++it)
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) acc[it][a][q] = 0.f;
   float bacc = 0.f;
   const int64_t m_lo = (int64_t)blockIdx.x * TR_WG_CHUNK;
   const int64_t m_hi = m_lo + TR_WG_CHUNK < M ? m_lo + TR_WG_CHUNK : M;
   for (int64_t m0 = m_lo; m0 < m_hi; m0 += TR_WG_ROWS) {
-    for (int idx = tid; idx < TR_WG_ROWS * K; idx += 256) {
-      const int r = idx / K, k = idx - r * K;
-      Xs[idx] = m0 + r < m_hi ? X[(m0 + r) * ldx + k] : 0.f;
+    for (int idx = tid; idx < TR_WG_ROWS * KP; idx += 256) {
+      const int r = idx / KP, k = idx - r * KP;
+      Xs[idx] = (m0 + r < m_hi && k < K) ? X[(m0 + r) * ldx + k] : 0.f;
     }
     for (int idx = tid; idx < TR_WG_ROWS * NOP; idx += 256) {
       const int r = idx / NOP, o = idx - r * NOP;
@@ -112,15 +138,18 @@ __global__ void __launch_bounds__(256) tr_wgrad_kernel(const float* __restrict__
     for (int it = 0; it < TR_WG_MAXI; ++it) {
       const int item = tid + it * 256;
       if (item < items) {
-        const int k = item / og, o4 = (item - k * og) * 4;
-        float4 a = acc[it];
-#pragma unroll 8
+        const int k4 = (item / og) * 4, o4 = (item - (item / og) * og) * 4;
+#pragma unroll 4
         for (int r = 0; r < TR_WG_ROWS; ++r) {
-          const float xv = Xs[r * K + k];
+          const float4 x = *reinterpret_cast<const float4*>(Xs + r * KP + k4);
           const float4 y = *reinterpret_cast<const float4*>(Ys + r * NOP + o4);
-          a.x = fmaf(xv, y.x, a.x); a.y = fmaf(xv, y.y, a.y); a.z = fmaf(xv, y.z, a.z); a.w = fmaf(xv, y.w, a.w);
+          const float xv[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+          for (int a = 0; a < 4; ++a) {
+            acc[it][a][0] = fmaf(xv[a], y.x, acc[it][a][0]); acc[it][a][1] = fmaf(xv[a], y.y, acc[it][a][1]);
+            acc[it][a][2] = fmaf(xv[a], y.z, acc[it][a][2]); acc[it][a][3] = fmaf(xv[a], y.w, acc[it][a][3]);
+          }
         }
-        acc[it] = a;
       }
     }
     if (db && tid < NO) {
@@ -132,11 +161,12 @@ __global__ void __launch_bounds__(256) tr_wgrad_kernel(const float* __restrict__
   for (int it = 0; it < TR_WG_MAXI; ++it) {
     const int item = tid + it * 256;
     if (item < items) {
-      const int k = item / og, o4 = (item - k * og) * 4;
-      const float v[4] = {acc[it].x, acc[it].y, acc[it].z, acc[it].w};
+      const int k4 = (item / og) * 4, o4 = (item - (item / og) * og) * 4;
 #pragma unroll
-      for (int q = 0; q < 4; ++q)
-        if (o4 + q < NO) atomicAdd(dW + (int64_t)k * ldw + o4 + q, v[q]);
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          if (k4 + a < K && o4 + q < NO) atomicAdd(dW + (int64_t)(k4 + a) * ldw + o4 + q, acc[it][a][q]);
     }
   }
   if (db && tid < NO) atomicAdd(db + tid, bacc);
@@ -609,13 +639,15 @@ static int linear(const float* X, int ldx, const float* W, int ldw, const float*
                   int trans, int act, int accumulate, cudaStream_t st) {
   for (int o0 = 0; o0 < NO; o0 += TR_NO_TILE) {
     const int no = NO - o0 < TR_NO_TILE ? NO - o0 : TR_NO_TILE;
-    const size_t smem = sizeof(float) * ((size_t)K * ((no + 3) & ~3) + (size_t)TR_TM * (K + 1));
+    int tm = TR_TM;                   // rows per CTA: the largest tile whose transposed copy fits next to the weights
+    while (tm > 32 && sizeof(float) * ((size_t)K * ((no + 3) & ~3) + (size_t)K * (tm + 4)) > 200 * 1024) tm >>= 1;
+    const size_t smem = sizeof(float) * ((size_t)K * ((no + 3) & ~3) + (size_t)K * (tm + 4));
     int rc = set_smem_attr((const void*)tr_linear_kernel, smem);
     if (rc) return rc;
     // output column o of the tile = column o0 + o: W[k][o0 + o] (trans = 0) or row o0 + o of W (trans = 1)
     const float* Wt = trans ? W + (int64_t)o0 * ldw : W + o0;
-    tr_linear_kernel<<<(unsigned)((M + TR_TM - 1) / TR_TM), 256, smem, st>>>(X, ldx, Wt, ldw, bias ? bias + o0 : nullptr, Y + o0, ldy, M, K,
-                                                                             no, trans, act, accumulate);
+    tr_linear_kernel<<<(unsigned)((M + tm - 1) / tm), 256, smem, st>>>(X, ldx, Wt, ldw, bias ? bias + o0 : nullptr, Y + o0, ldy, M, K, no,
+                                                                       trans, act, accumulate, tm);
     count_launch();
     LAUNCH_CHECK();
   }
@@ -628,8 +660,8 @@ static int wgrad(const float* X, int ldx, const float* dY, int ldy, float* dW, i
     const int kt = K - k0 < TR_K_TILE ? K - k0 : TR_K_TILE;
     for (int o0 = 0; o0 < NO; o0 += TR_NO_TILE) {
       const int no = NO - o0 < TR_NO_TILE ? NO - o0 : TR_NO_TILE;
-      if ((int64_t)kt * (((no + 3) & ~3) / 4) > 256 * TR_WG_MAXI) return GDSS_E_UNSUPPORTED;
-      const size_t smem = sizeof(float) * ((size_t)TR_WG_ROWS * kt + (size_t)TR_WG_ROWS * ((no + 3) & ~3));
+      if ((int64_t)(((kt + 3) & ~3) / 4) * (((no + 3) & ~3) / 4) > 256 * TR_WG_MAXI) return GDSS_E_UNSUPPORTED;
+      const size_t smem = sizeof(float) * ((size_t)TR_WG_ROWS * ((kt + 3) & ~3) + (size_t)TR_WG_ROWS * ((no + 3) & ~3));
       int rc = set_smem_attr((const void*)tr_wgrad_kernel, smem);
       if (rc) return rc;
       tr_wgrad_kernel<<<(unsigned)((M + TR_WG_CHUNK - 1) / TR_WG_CHUNK), 256, smem, st>>>(

@@ -893,7 +893,8 @@ def test_op_level_outputs_match_reference_modules(name, path):
         # (diagonal pixels are never produced by the CUDA paths: DenseGCNConv overwrites them with 1, layers.py:72-74, and the
         # final score zeroes them, ScoreNetwork_A.py:145 -- compare the off-diagonal entries)
         offd = (1 - torch.eye(N)).view(1, 1, N, N)
-        stack = eng.region(B, "stack_a", (B, fdim, N, N)).clone().cpu() * offd
+        stack = eng.region(B, "stack_a", (B, fdim, N, N)).clone().cpu()
+        stack = torch.where(offd.bool().expand_as(stack), stack, torch.zeros(()))      # (never written: may hold anything)
         ref_off = ref_stack * offd
         errs["stack"] = rel(stack, ref_off)
         for c in range(ref_stack.shape[1]):
