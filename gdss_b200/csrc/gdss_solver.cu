@@ -194,11 +194,8 @@ struct UpdateArgs {
 //   S4    solver.py:235-277   correction, half transition, drift, half transition
 // grid = (chunks, B); the adjacency is updated on the strict upper triangle and mirrored.
 // ---------------------------------------------------------------------------------------
-// STAGE (small graphs, one CTA per graph): the updated upper triangle is mirrored in shared memory and written back as whole
-// rows -- coalesced stores instead of one strided store per mirrored element.  Same values, same order of operations.
-template <int MODE, bool STAGE>
+template <int MODE>
 __global__ void __launch_bounds__(256) update_kernel(UpdateArgs a) {
-  extern __shared__ float stage_sm[];
   const NoiseSrc& ns = a.ns;
   const int b = blockIdx.y, N = ns.N, F = ns.F;
   const int step = *a.step_ptr;
@@ -273,10 +270,6 @@ __global__ void __launch_bounds__(256) update_kernel(UpdateArgs a) {
     float* A = a.adj + (int64_t)b * N * N;
     float* AM = a.adj_mean + (int64_t)b * N * N;
     const float* RA = a.raw_adj + (int64_t)b * N * N;
-    const bool staged = STAGE && finite;              // (uniform over the CTA)
-    const int NS = N + 1;
-    float* As = stage_sm;                             // [N][N + 1]
-    float* AMs = stage_sm + N * NS;
     for (int idx = t0; idx < n * gwa; idx += stride) {
       int i = idx / gwa, g = idx - i * gwa;
       if (4 * g + 3 < i + dg || 4 * g >= n) continue;
@@ -301,29 +294,20 @@ __global__ void __launch_bounds__(256) update_kernel(UpdateArgs a) {
           y = y + eps_a * (c.cs[1] * r) + nza * (f4_get(z0, q) * f);
         } else if (MODE == MODE_PRED) {
           float m = c.pa[1] * y + c.pb[1] * r;
-          if (staged) { AMs[i * NS + j] = m; AMs[j * NS + i] = m; }
-          else { AM[e] = m; AM[et] = m; }
+          AM[e] = m;
+          AM[et] = m;
           y = m + c.pc[1] * (f4_get(z0, q) * f);
         } else {
           y = y + eps_a * (c.cs[1] * r) + nza * (f4_get(z0, q) * f);
           y = c.mu1[1] * y + c.sig1[1] * (f4_get(z1, q) * f);
           y = y + c.drift[1] * r;
           float m = c.mu2[1] * y;
-          if (staged) { AMs[i * NS + j] = m; AMs[j * NS + i] = m; }
-          else { AM[e] = m; AM[et] = m; }
+          AM[e] = m;
+          AM[et] = m;
           y = m + c.sig2[1] * (f4_get(z2, q) * f);
         }
-        if (staged) { As[i * NS + j] = y; As[j * NS + i] = y; }
-        else { A[e] = y; A[et] = y; }
-      }
-    }
-    if (staged) {
-      __syncthreads();
-      for (int idx = threadIdx.x; idx < n * n; idx += 256) {
-        const int i = idx / n, j = idx - i * n;
-        if (i == j) continue;                          // (the diagonal is not touched in the finite case)
-        A[i * N + j] = As[i * NS + j];
-        if (MODE != MODE_CORR) AM[i * N + j] = AMs[i * NS + j];
+        A[e] = y;
+        A[et] = y;
       }
     }
   }
@@ -358,10 +342,6 @@ static int enqueue_step(const StepPlan& p, cudaStream_t st) {
   if (wx > work) work = wx;
   int chunks = (work + 255) / 256;
   if (chunks > 64) chunks = 64;
-  // small graphs: one CTA per graph with the mirrored triangle staged in shared memory (coalesced row stores)
-  const bool stage = N <= 64;
-  if (stage) chunks = 1;
-  const size_t usm = stage ? sizeof(float) * 2 * (size_t)N * (N + 1) : 0;
   dim3 ugrid(chunks, B);
   int rc = 0;
   // per-graph norms -> batch sums (-> all-reduce over the ranks) of the scores in raw_x / raw_a and of corrector draw cd
@@ -380,8 +360,7 @@ static int enqueue_step(const StepPlan& p, cudaStream_t st) {
     if (rc) return rc;
     rc = norm_means(0);
     if (rc) return rc;
-    if (stage) update_kernel<MODE_S4, true><<<ugrid, 256, usm, st>>>(u);
-    else update_kernel<MODE_S4, false><<<ugrid, 256, 0, st>>>(u);
+    update_kernel<MODE_S4><<<ugrid, 256, 0, st>>>(u);
     launched(K_UPDATE, st);
     LAUNCH_CHECK();
   } else {
@@ -406,16 +385,14 @@ static int enqueue_step(const StepPlan& p, cudaStream_t st) {
         if (rc) return rc;
         UpdateArgs uk = u;
         uk.corr_draw = k;
-        if (stage) update_kernel<MODE_CORR, true><<<ugrid, 256, usm, st>>>(uk);
-        else update_kernel<MODE_CORR, false><<<ugrid, 256, 0, st>>>(uk);
+        update_kernel<MODE_CORR><<<ugrid, 256, 0, st>>>(uk);
         launched(K_UPDATE, st);
         LAUNCH_CHECK();
       }
     }
     rc = launch_eval(p.ctx, u.x, u.adj, u.flags, u.neff, raw_x, raw_a, B, p.ws, p.w, st, !p.ctx->fused);
     if (rc) return rc;
-    if (stage) update_kernel<MODE_PRED, true><<<ugrid, 256, usm, st>>>(u);
-    else update_kernel<MODE_PRED, false><<<ugrid, 256, 0, st>>>(u);
+    update_kernel<MODE_PRED><<<ugrid, 256, 0, st>>>(u);
     launched(K_UPDATE, st);
     LAUNCH_CHECK();
   }

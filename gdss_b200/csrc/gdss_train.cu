@@ -396,103 +396,115 @@ __global__ void __launch_bounds__(256) tr_maps_bwd_kernel(const float* __restric
 }
 
 // ---------------------------------------------------------------------------------------
-// glue kernels (grid-stride over elements)
+// glue kernels: blockIdx.y = graph, 32-bit grid-stride over the graph's elements (no 64-bit divisions in the loops)
 // ---------------------------------------------------------------------------------------
-#define GRID_STRIDE(i, n) for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < (n); i += (int64_t)gridDim.x * blockDim.x)
+#define PER_GRAPH(i, n) for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < (n); i += gridDim.x * blockDim.x)
 
 // utils/graph_utils.py:133-142: plane 0 = adj, plane 1 = adj @ adj (c_init <= 2)
-__global__ void tr_pow_kernel(const float* __restrict__ adj, float* __restrict__ S, int64_t s_bs, int B, int N, int cinit) {
-  GRID_STRIDE(e, (int64_t)B * N * N) {
-    const int64_t b = e / (N * N);
-    const int idx = (int)(e - b * N * N), i = idx / N, j = idx - i * N;
-    const float* A = adj + b * N * N;
-    S[b * s_bs + idx] = A[idx];
+__global__ void tr_pow_kernel(const float* __restrict__ adj, float* __restrict__ S, int64_t s_bs, int N, int cinit) {
+  const int64_t b = blockIdx.y;
+  const float* A = adj + b * N * N;
+  float* Sb = S + b * s_bs;
+  PER_GRAPH(idx, N * N) {
+    const int i = idx / N, j = idx - i * N;
+    Sb[idx] = A[idx];
     if (cinit > 1) {
       float s = 0.f;
       for (int m = 0; m < N; ++m) s = fmaf(A[i * N + m], A[m * N + j], s);
-      S[b * s_bs + (int64_t)N * N + idx] = s;
+      Sb[N * N + idx] = s;
     }
   }
 }
 
 // edge-MLP input rows (attention.py:109-110): ein[(b, i, j)] = [M_0 .. M_{C-1}, P_0 .. P_{C-1}]
 __global__ void tr_edge_rows_kernel(const float* __restrict__ M, const float* __restrict__ planes, int64_t p_bs,
-                                    float* __restrict__ ein, int B, int C, int N) {
-  GRID_STRIDE(e, (int64_t)B * N * N * 2 * C) {
-    const int k = (int)(e % (2 * C));
-    const int64_t row = e / (2 * C);
-    const int64_t b = row / (N * N);
-    const int ij = (int)(row - b * N * N);
-    ein[e] = k < C ? M[(b * C + k) * N * N + ij] : planes[b * p_bs + (int64_t)(k - C) * N * N + ij];
+                                    float* __restrict__ ein, int C, int N) {
+  const int64_t b = blockIdx.y;
+  const int NN = N * N, C2 = 2 * C;
+  const float* Mb = M + b * C * NN;
+  const float* Pb = planes + b * p_bs;
+  float* eb = ein + b * NN * C2;
+  PER_GRAPH(e, NN * C2) {
+    const int ij = e / C2, k = e - ij * C2;
+    eb[e] = k < C ? Mb[k * NN + ij] : Pb[(k - C) * NN + ij];
   }
 }
 
 // adj_out = mask_adjs(s + s^T) (attention.py:113-114) from the MLP output rows s[(b, i, j)][o]
 __global__ void tr_edge_out_kernel(const float* __restrict__ s, const float* __restrict__ flags, float* __restrict__ planes,
-                                   int64_t p_bs, int B, int Co, int N) {
-  GRID_STRIDE(e, (int64_t)B * Co * N * N) {
-    const int ij = (int)(e % (N * N));
-    const int64_t bo = e / (N * N);
-    const int o = (int)(bo % Co);
-    const int64_t b = bo / Co;
+                                   int64_t p_bs, int Co, int N) {
+  const int64_t b = blockIdx.y;
+  const int NN = N * N;
+  const float* sb = s + b * NN * Co;
+  const float* fl = flags + b * N;
+  float* Pb = planes + b * p_bs;
+  PER_GRAPH(e, Co * NN) {
+    const int o = e / NN, ij = e - o * NN;
     const int i = ij / N, j = ij - i * N;
-    const float v = s[(b * N * N + ij) * Co + o] + s[(b * N * N + (int64_t)j * N + i) * Co + o];
-    planes[b * p_bs + (int64_t)o * N * N + ij] = v * flags[b * N + i] * flags[b * N + j];
+    Pb[e] = (sb[ij * Co + o] + sb[(j * N + i) * Co + o]) * fl[i] * fl[j];
   }
 }
 
 // gradient of the rows: g[(b, i, j)][o] = f_i f_j (dP_o[i][j] + dP_o[j][i])
 __global__ void tr_edge_gin_kernel(const float* __restrict__ dplanes, int64_t p_bs, const float* __restrict__ flags,
-                                   float* __restrict__ g, int B, int Co, int N) {
-  GRID_STRIDE(e, (int64_t)B * N * N * Co) {
-    const int o = (int)(e % Co);
-    const int64_t row = e / Co;
-    const int64_t b = row / (N * N);
-    const int ij = (int)(row - b * N * N), i = ij / N, j = ij - i * N;
-    const float* dP = dplanes + b * p_bs + (int64_t)o * N * N;
-    g[e] = flags[b * N + i] * flags[b * N + j] * (dP[ij] + dP[j * N + i]);
+                                   float* __restrict__ g, int Co, int N) {
+  const int64_t b = blockIdx.y;
+  const int NN = N * N;
+  const float* dPb = dplanes + b * p_bs;
+  const float* fl = flags + b * N;
+  float* gb = g + b * NN * Co;
+  PER_GRAPH(e, NN * Co) {
+    const int ij = e / Co, o = e - ij * Co;
+    const int i = ij / N, j = ij - i * N;
+    gb[e] = fl[i] * fl[j] * (dPb[o * NN + ij] + dPb[o * NN + j * N + i]);
   }
 }
 
 // d ein -> dM (assign) and the input planes' gradient (+=)
 __global__ void tr_edge_dein_kernel(const float* __restrict__ dein, float* __restrict__ dM, float* __restrict__ dplanes,
-                                    int64_t p_bs, int B, int C, int N) {
-  GRID_STRIDE(e, (int64_t)B * N * N * 2 * C) {
-    const int k = (int)(e % (2 * C));
-    const int64_t row = e / (2 * C);
-    const int64_t b = row / (N * N);
-    const int ij = (int)(row - b * N * N);
-    if (k < C) dM[(b * C + k) * N * N + ij] = dein[e];
-    else dplanes[b * p_bs + (int64_t)(k - C) * N * N + ij] += dein[e];
+                                    int64_t p_bs, int C, int N) {
+  const int64_t b = blockIdx.y;
+  const int NN = N * N, C2 = 2 * C;
+  const float* db_ = dein + b * NN * C2;
+  float* dMb = dM + b * C * NN;
+  float* dPb = dplanes + b * p_bs;
+  PER_GRAPH(e, NN * C2) {
+    const int ij = e / C2, k = e - ij * C2;
+    if (k < C) dMb[k * NN + ij] = db_[e];
+    else dPb[(k - C) * NN + ij] += db_[e];
   }
 }
 
-// cat_c V_c rows (attention.py:106) from the per-channel convolution outputs
+// cat_c V_c rows (attention.py:106) from the per-channel convolution outputs [c][b * N + i][OW]
 __global__ void tr_node_gather_kernel(const float* __restrict__ Y, float* __restrict__ V, int B, int C, int N, int OW, int col0, int h) {
-  GRID_STRIDE(e, (int64_t)B * N * C * h) {
-    const int o = (int)(e % h);
-    const int c = (int)((e / h) % C);
-    const int64_t r = e / ((int64_t)C * h);
-    V[e] = Y[((int64_t)c * B * N + r) * OW + col0 + o];
+  const int64_t b = blockIdx.y;
+  const int Ch = C * h;
+  float* Vb = V + b * N * Ch;
+  PER_GRAPH(e, N * Ch) {
+    const int i = e / Ch, r = e - i * Ch, c = r / h, o = r - c * h;
+    Vb[e] = Y[(((int64_t)c * B + b) * N + i) * OW + col0 + o];
   }
 }
 
 __global__ void tr_node_scatter_kernel(const float* __restrict__ dV, float* __restrict__ dY, int B, int C, int N, int OW, int col0, int h) {
-  GRID_STRIDE(e, (int64_t)B * N * C * h) {
-    const int o = (int)(e % h);
-    const int c = (int)((e / h) % C);
-    const int64_t r = e / ((int64_t)C * h);
-    dY[((int64_t)c * B * N + r) * OW + col0 + o] = dV[e];
+  const int64_t b = blockIdx.y;
+  const int Ch = C * h;
+  const float* Vb = dV + b * N * Ch;
+  PER_GRAPH(e, N * Ch) {
+    const int i = e / Ch, r = e - i * Ch, c = r / h, o = r - c * h;
+    dY[(((int64_t)c * B + b) * N + i) * OW + col0 + o] = Vb[e];
   }
 }
 
 // x_out = tanh(mask_x(hn)) (attention.py:107); x2 = tanh(x_out) for ScoreNetworkX_GMH (ScoreNetwork_X.py:81)
 __global__ void tr_node_out_kernel(const float* __restrict__ hn, const float* __restrict__ flags, float* __restrict__ xout,
-                                   float* __restrict__ x2, int64_t rows, int h) {
-  GRID_STRIDE(e, rows * h) {
-    const float v = tanhf(hn[e] * flags[e / h]);
-    xout[e] = v;
-    if (x2) x2[e] = tanhf(v);
+                                   float* __restrict__ x2, int N, int h) {
+  const int64_t b = blockIdx.y;
+  const int64_t base = b * N * h;
+  PER_GRAPH(e, N * h) {
+    const float v = tanhf(hn[base + e] * flags[b * N + e / h]);
+    xout[base + e] = v;
+    if (x2) x2[base + e] = tanhf(v);
   }
 }
 
@@ -500,73 +512,83 @@ __global__ void tr_node_out_kernel(const float* __restrict__ hn, const float* __
 // MLP's input gradient (row stride ldb, or null); x2 = null for ScoreNetworkA
 __global__ void tr_node_dpre_kernel(const float* __restrict__ ga, const float* __restrict__ gb, int ldb, const float* __restrict__ xout,
                                     const float* __restrict__ x2, const float* __restrict__ flags, float* __restrict__ dpre,
-                                    int64_t rows, int h) {
-  GRID_STRIDE(e, rows * h) {
-    const int64_t r = e / h;
-    const int o = (int)(e - r * h);
-    float g = (ga ? ga[e] : 0.f) + (gb ? gb[r * ldb + o] : 0.f);
-    if (x2) g *= 1.f - x2[e] * x2[e];
-    const float xo = xout[e];
-    dpre[e] = flags[r] * g * (1.f - xo * xo);
+                                    int N, int h) {
+  const int64_t b = blockIdx.y;
+  const int64_t base = b * N * h;
+  PER_GRAPH(e, N * h) {
+    const int i = e / h, o = e - i * h;
+    float g = (ga ? ga[base + e] : 0.f) + (gb ? gb[(b * N + i) * ldb + o] : 0.f);
+    if (x2) g *= 1.f - x2[base + e] * x2[base + e];
+    const float xo = xout[base + e];
+    dpre[base + e] = flags[b * N + i] * g * (1.f - xo * xo);
   }
 }
 
 // final MLP of ScoreNetworkA: input rows = the concatenated stack per pixel (ScoreNetwork_A.py:141-142)
-__global__ void tr_stack_rows_kernel(const float* __restrict__ S, int64_t s_bs, float* __restrict__ rows, int B, int P, int N) {
-  GRID_STRIDE(e, (int64_t)B * N * N * P) {
-    const int p = (int)(e % P);
-    const int64_t row = e / P;
-    const int64_t b = row / (N * N);
-    rows[e] = S[b * s_bs + (int64_t)p * N * N + (row - b * N * N)];
+__global__ void tr_stack_rows_kernel(const float* __restrict__ S, int64_t s_bs, float* __restrict__ rows, int P, int N) {
+  const int64_t b = blockIdx.y;
+  const int NN = N * N;
+  const float* Sb = S + b * s_bs;
+  float* rb = rows + b * NN * P;
+  PER_GRAPH(e, NN * P) {
+    const int ij = e / P, p = e - ij * P;
+    rb[e] = Sb[p * NN + ij];
   }
 }
 
-__global__ void tr_stack_rows_bwd_kernel(const float* __restrict__ drows, float* __restrict__ dS, int64_t s_bs, int B, int P, int N) {
-  GRID_STRIDE(e, (int64_t)B * N * N * P) {
-    const int p = (int)(e % P);
-    const int64_t row = e / P;
-    const int64_t b = row / (N * N);
-    dS[b * s_bs + (int64_t)p * N * N + (row - b * N * N)] = drows[e];
+__global__ void tr_stack_rows_bwd_kernel(const float* __restrict__ drows, float* __restrict__ dS, int64_t s_bs, int P, int N) {
+  const int64_t b = blockIdx.y;
+  const int NN = N * N;
+  const float* rb = drows + b * NN * P;
+  float* Sb = dS + b * s_bs;
+  PER_GRAPH(e, P * NN) {
+    const int p = e / NN, ij = e - p * NN;
+    Sb[e] = rb[ij * P + p];
   }
 }
 
 // score_adj = mask_adjs(out) with a zero diagonal (ScoreNetwork_A.py:143-148); the same factor on the way back
-__global__ void tr_adj_mask_kernel(const float* __restrict__ in, const float* __restrict__ flags, float* __restrict__ out, int B, int N) {
-  GRID_STRIDE(e, (int64_t)B * N * N) {
-    const int64_t b = e / (N * N);
-    const int ij = (int)(e - b * N * N), i = ij / N, j = ij - i * N;
-    out[e] = i == j ? 0.f : in[e] * flags[b * N + i] * flags[b * N + j];
+__global__ void tr_adj_mask_kernel(const float* __restrict__ in, const float* __restrict__ flags, float* __restrict__ out, int N) {
+  const int64_t b = blockIdx.y;
+  const int64_t base = b * N * N;
+  PER_GRAPH(ij, N * N) {
+    const int i = ij / N, j = ij - i * N;
+    out[base + ij] = i == j ? 0.f : in[base + ij] * flags[b * N + i] * flags[b * N + j];
   }
 }
 
-__global__ void tr_x_mask_kernel(const float* __restrict__ in, const float* __restrict__ flags, float* __restrict__ out, int64_t rows, int F) {
-  GRID_STRIDE(e, rows * F) out[e] = in[e] * flags[e / F];
+__global__ void tr_x_mask_kernel(const float* __restrict__ in, const float* __restrict__ flags, float* __restrict__ out, int N, int F) {
+  const int64_t b = blockIdx.y;
+  const int64_t base = b * N * F;
+  PER_GRAPH(e, N * F) out[base + e] = in[base + e] * flags[b * N + e / F];
 }
 
-// strided copy of a [rows][w] block into / out of wider rows
-__global__ void tr_copy_cols_kernel(const float* __restrict__ src, int lds, float* __restrict__ dst, int ldd, int64_t rows, int w) {
-  GRID_STRIDE(e, rows * w) {
-    const int64_t r = e / w;
-    const int o = (int)(e - r * w);
-    dst[r * ldd + o] = src[r * lds + o];
+// strided copy of a [N][w] block per graph into / out of wider rows
+__global__ void tr_copy_cols_kernel(const float* __restrict__ src, int lds, float* __restrict__ dst, int ldd, int N, int w) {
+  const int64_t b = blockIdx.y;
+  PER_GRAPH(e, N * w) {
+    const int i = e / w, o = e - i * w;
+    dst[(b * N + i) * ldd + o] = src[(b * N + i) * lds + o];
   }
 }
 
 // tanh'(.) of a plain GCN layer of ScoreNetworkX: g = (g_a + g_b) * (1 - x_l^2)
 __global__ void tr_tanh_bwd_kernel(const float* __restrict__ ga, const float* __restrict__ gb, int ldb, const float* __restrict__ xl,
-                                   int ldx, float* __restrict__ g, int64_t rows, int h) {
-  GRID_STRIDE(e, rows * h) {
-    const int64_t r = e / h;
-    const int o = (int)(e - r * h);
+                                   int ldx, float* __restrict__ g, int N, int h) {
+  const int64_t b = blockIdx.y;
+  PER_GRAPH(e, N * h) {
+    const int i = e / h, o = e - i * h;
+    const int64_t r = b * N + i;
     const float v = xl[r * ldx + o];
-    g[e] = ((ga ? ga[e] : 0.f) + (gb ? gb[r * ldb + o] : 0.f)) * (1.f - v * v);
+    g[r * h + o] = ((ga ? ga[r * h + o] : 0.f) + (gb ? gb[r * ldb + o] : 0.f)) * (1.f - v * v);
   }
 }
 
-__global__ void tr_tanh_rows_kernel(const float* __restrict__ in, float* __restrict__ out, int ldo, int64_t rows, int h) {
-  GRID_STRIDE(e, rows * h) {
-    const int64_t r = e / h;
-    out[r * ldo + (e - r * h)] = tanhf(in[e]);
+__global__ void tr_tanh_rows_kernel(const float* __restrict__ in, float* __restrict__ out, int ldo, int N, int h) {
+  const int64_t b = blockIdx.y;
+  PER_GRAPH(e, N * h) {
+    const int i = e / h, o = e - i * h;
+    out[(b * N + i) * ldo + o] = tanhf(in[(b * N + i) * h + o]);
   }
 }
 
@@ -609,6 +631,12 @@ __global__ void __launch_bounds__(1024) tr_mean_kernel(const float* __restrict__
 // ---------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------
+// grid of a per-graph glue kernel: blockIdx.y = graph, blockIdx.x covers `per` elements (capped; grid-stride inside)
+static inline dim3 ggrid(int64_t per, int B) {
+  int64_t g = (per + 255) / 256;
+  return dim3((unsigned)(g > 64 ? 64 : (g < 1 ? 1 : g)), (unsigned)B);
+}
+
 static inline int egrid(int64_t n) {
   int64_t g = (n + 255) / 256;
   return (int)(g > 148 * 32 ? 148 * 32 : (g < 1 ? 1 : g));
@@ -856,10 +884,10 @@ static int attn_forward(const NetPlan& p, const float* blob, NetBufs& nb, const 
   const int64_t R = (int64_t)B * N * N, Rn = (int64_t)B * N;
   const bool isA = p.type == GDSS_NET_A;
   cudaStream_t st = t.st;
-  tr_pow_kernel<<<egrid(R), 256, 0, st>>>(t.padj, nb.S, nb.s_bs, B, N, p.c_init);
+  tr_pow_kernel<<<ggrid(N * N, B), 256, 0, st>>>(t.padj, nb.S, nb.s_bs, N, p.c_init);
   KCHECK();
   if (!isA) {
-    tr_copy_cols_kernel<<<egrid(Rn * F), 256, 0, st>>>(t.px, F, nb.xcat, p.fdim, Rn, F);
+    tr_copy_cols_kernel<<<ggrid(N * F, B), 256, 0, st>>>(t.px, F, nb.xcat, p.fdim, N, F);
     KCHECK();
   }
   const float* xin = t.px;
@@ -886,27 +914,27 @@ static int attn_forward(const NetPlan& p, const float* blob, NetBufs& nb, const 
       tr_maps_fwd_kernel<<<dim3(L.c_in, B), 256, maps_smem(N, L.attn), st>>>(b.Y, b.M, B, L.c_in, N, L.qkvw, L.attn, p.heads,
                                                                              1.0f / sqrtf((float)L.nhid));
       KCHECK();
-      tr_edge_rows_kernel<<<egrid(R * 2 * L.c_in), 256, 0, st>>>(b.M, nb.S + (int64_t)cur * N * N, nb.s_bs, b.ein, B, L.c_in, N);
+      tr_edge_rows_kernel<<<ggrid((int64_t)N * N * 2 * L.c_in, B), 256, 0, st>>>(b.M, nb.S + (int64_t)cur * N * N, nb.s_bs, b.ein, L.c_in, N);
       KCHECK();
       Lin lin[GDSS_MAX_LIN];
       edge_lins(L, lin);
       rc = mlp_fwd(blob, lin, L.nlin, b.ein, 2 * L.c_in, b.H, nb.ga, L.c_out, R, st);
       if (rc) return rc;
-      tr_edge_out_kernel<<<egrid(R * L.c_out), 256, 0, st>>>(nb.ga, t.flags, nb.S + (int64_t)(cur + L.c_in) * N * N, nb.s_bs, B, L.c_out, N);
+      tr_edge_out_kernel<<<ggrid((int64_t)N * N * L.c_out, B), 256, 0, st>>>(nb.ga, t.flags, nb.S + (int64_t)(cur + L.c_in) * N * N, nb.s_bs, L.c_out, N);
       KCHECK();
     }
     if (need_node) {
-      tr_node_gather_kernel<<<egrid(Rn * L.c_in * L.nhid), 256, 0, st>>>(b.Y, b.Vcat, B, L.c_in, N, L.qkvw, 2 * L.attn, L.nhid);
+      tr_node_gather_kernel<<<ggrid((int64_t)N * L.c_in * L.nhid, B), 256, 0, st>>>(b.Y, b.Vcat, B, L.c_in, N, L.qkvw, 2 * L.attn, L.nhid);
       KCHECK();
       Lin lin[2];
       node_lins(L, lin);
       float* H[1] = {b.Hn};
       rc = mlp_fwd(blob, lin, 2, b.Vcat, L.c_in * L.nhid, H, nb.hn, L.nhid, Rn, st);
       if (rc) return rc;
-      tr_node_out_kernel<<<egrid(Rn * L.nhid), 256, 0, st>>>(nb.hn, t.flags, b.xout, b.x2, Rn, L.nhid);
+      tr_node_out_kernel<<<ggrid(N * L.nhid, B), 256, 0, st>>>(nb.hn, t.flags, b.xout, b.x2, N, L.nhid);
       KCHECK();
       if (!isA) {
-        tr_copy_cols_kernel<<<egrid(Rn * L.nhid), 256, 0, st>>>(b.x2, L.nhid, nb.xcat + F + l * p.nhid, p.fdim, Rn, L.nhid);
+        tr_copy_cols_kernel<<<ggrid(N * L.nhid, B), 256, 0, st>>>(b.x2, L.nhid, nb.xcat + F + l * p.nhid, p.fdim, N, L.nhid);
         KCHECK();
       }
       xin = isA ? b.xout : b.x2;
@@ -918,16 +946,16 @@ static int attn_forward(const NetPlan& p, const float* blob, NetBufs& nb, const 
   Lin fl[3];
   final_lins(p, fl);
   if (isA) {
-    tr_stack_rows_kernel<<<egrid(R * p.fdim), 256, 0, st>>>(nb.S, nb.s_bs, nb.cat, B, p.fdim, N);
+    tr_stack_rows_kernel<<<ggrid((int64_t)N * N * p.fdim, B), 256, 0, st>>>(nb.S, nb.s_bs, nb.cat, p.fdim, N);
     KCHECK();
     int rc = mlp_fwd(blob, fl, 3, nb.cat, p.fdim, nb.Hf, nb.out, 1, R, st);
     if (rc) return rc;
-    tr_adj_mask_kernel<<<egrid(R), 256, 0, st>>>(nb.out, t.flags, net_out, B, N);
+    tr_adj_mask_kernel<<<ggrid(N * N, B), 256, 0, st>>>(nb.out, t.flags, net_out, N);
     KCHECK();
   } else {
     int rc = mlp_fwd(blob, fl, 3, nb.xcat, p.fdim, nb.Hf, nb.out, p.fout, Rn, st);
     if (rc) return rc;
-    tr_x_mask_kernel<<<egrid(Rn * F), 256, 0, st>>>(nb.out, t.flags, net_out, Rn, F);
+    tr_x_mask_kernel<<<ggrid(N * F, B), 256, 0, st>>>(nb.out, t.flags, net_out, N, F);
     KCHECK();
   }
   return 0;
@@ -946,14 +974,14 @@ static int attn_backward(const NetPlan& p, const float* blob, float* gblob, NetB
   if (isA) {
     // ScoreNetwork_A.py:143-148: zero diagonal, mask_adjs; then the final MLP over the pixel rows; its input gradient IS the
     // gradient of every plane of the stack
-    tr_adj_mask_kernel<<<egrid(R), 256, 0, st>>>(dnet, t.flags, nb.ga, B, N);
+    tr_adj_mask_kernel<<<ggrid(N * N, B), 256, 0, st>>>(dnet, t.flags, nb.ga, N);
     KCHECK();
     rc = mlp_bwd(blob, gblob, fl, 3, nb.cat, p.fdim, nb.Hf, nb.ga, R, nb.gc, p.fdim, nb.ga, nb.gb, st);
     if (rc) return rc;
-    tr_stack_rows_bwd_kernel<<<egrid(R * p.fdim), 256, 0, st>>>(nb.gc, nb.dS, nb.s_bs, B, p.fdim, N);
+    tr_stack_rows_bwd_kernel<<<ggrid((int64_t)N * N * p.fdim, B), 256, 0, st>>>(nb.gc, nb.dS, nb.s_bs, p.fdim, N);
     KCHECK();
   } else {
-    tr_x_mask_kernel<<<egrid(Rn * F), 256, 0, st>>>(dnet, t.flags, nb.ga, Rn, F);
+    tr_x_mask_kernel<<<ggrid(N * F, B), 256, 0, st>>>(dnet, t.flags, nb.ga, N, F);
     KCHECK();
     rc = mlp_bwd(blob, gblob, fl, 3, nb.xcat, p.fdim, nb.Hf, nb.ga, Rn, nb.dxcat, p.fdim, nb.ga, nb.gb, st);
     if (rc) return rc;
@@ -976,26 +1004,26 @@ static int attn_backward(const NetPlan& p, const float* blob, float* gblob, NetB
     if (e != cudaSuccess) return (int)e;
     if (need_node && (dxn || !isA)) {
       // attention.py:106-107 backwards: tanh', mask_x, multi_channel MLP, split over the channels' V blocks
-      tr_node_dpre_kernel<<<egrid(Rn * L.nhid), 256, 0, st>>>(dxn, isA ? nullptr : nb.dxcat + F + l * p.nhid, p.fdim, b.xout, b.x2,
-                                                               t.flags, nb.dpre, Rn, L.nhid);
+      tr_node_dpre_kernel<<<ggrid(N * L.nhid, B), 256, 0, st>>>(dxn, isA ? nullptr : nb.dxcat + F + l * p.nhid, p.fdim, b.xout, b.x2,
+                                                                t.flags, nb.dpre, N, L.nhid);
       KCHECK();
       Lin lin[2];
       node_lins(L, lin);
       float* H[1] = {b.Hn};
       rc = mlp_bwd(blob, gblob, lin, 2, b.Vcat, L.c_in * L.nhid, H, nb.dpre, Rn, nb.dV, L.c_in * L.nhid, nb.dHn, nb.hn, st);
       if (rc) return rc;
-      tr_node_scatter_kernel<<<egrid(Rn * L.c_in * L.nhid), 256, 0, st>>>(nb.dV, nb.dY, B, L.c_in, N, L.qkvw, 2 * L.attn, L.nhid);
+      tr_node_scatter_kernel<<<ggrid((int64_t)N * L.c_in * L.nhid, B), 256, 0, st>>>(nb.dV, nb.dY, B, L.c_in, N, L.qkvw, 2 * L.attn, L.nhid);
       KCHECK();
     }
     if (need_edge) {
       // attention.py:109-114 backwards: mask_adjs, s + s^T, the per-edge MLP, split into the maps' and the planes' gradient
-      tr_edge_gin_kernel<<<egrid(R * L.c_out), 256, 0, st>>>(nb.dS + (int64_t)(cur + L.c_in) * N * N, nb.s_bs, t.flags, nb.ga, B, L.c_out, N);
+      tr_edge_gin_kernel<<<ggrid((int64_t)N * N * L.c_out, B), 256, 0, st>>>(nb.dS + (int64_t)(cur + L.c_in) * N * N, nb.s_bs, t.flags, nb.ga, L.c_out, N);
       KCHECK();
       Lin lin[GDSS_MAX_LIN];
       edge_lins(L, lin);
       rc = mlp_bwd(blob, gblob, lin, L.nlin, b.ein, 2 * L.c_in, b.H, nb.ga, R, nb.gc, 2 * L.c_in, nb.ga, nb.gb, st);
       if (rc) return rc;
-      tr_edge_dein_kernel<<<egrid(R * 2 * L.c_in), 256, 0, st>>>(nb.gc, nb.dM, nb.dS + (int64_t)cur * N * N, nb.s_bs, B, L.c_in, N);
+      tr_edge_dein_kernel<<<ggrid((int64_t)N * N * 2 * L.c_in, B), 256, 0, st>>>(nb.gc, nb.dM, nb.dS + (int64_t)cur * N * N, nb.s_bs, L.c_in, N);
       KCHECK();
       rc = set_smem_attr((const void*)tr_maps_bwd_kernel, maps_smem(N, L.attn));
       if (rc) return rc;
@@ -1036,7 +1064,7 @@ static int gcn_forward(const NetPlan& p, const float* blob, NetBufs& nb, const T
   const int B = t.B, N = p.N, F = p.F, h = p.nhid;
   const int64_t Rn = (int64_t)B * N;
   cudaStream_t st = t.st;
-  tr_copy_cols_kernel<<<egrid(Rn * F), 256, 0, st>>>(t.px, F, nb.xcat, p.fdim, Rn, F);
+  tr_copy_cols_kernel<<<ggrid(N * F, B), 256, 0, st>>>(t.px, F, nb.xcat, p.fdim, N, F);
   KCHECK();
   for (int l = 0; l < p.depth; ++l) {
     LayerBufs& b = nb.L[l];
@@ -1050,14 +1078,14 @@ static int gcn_forward(const NetPlan& p, const float* blob, NetBufs& nb, const T
     if (rc) return rc;
     tr_gcn_fwd_kernel<<<dim3(1, B), 256, gcn_fwd_smem(N, h), st>>>(g);
     KCHECK();
-    tr_tanh_rows_kernel<<<egrid(Rn * h), 256, 0, st>>>(b.Y, nb.xcat + F + l * h, p.fdim, Rn, h);
+    tr_tanh_rows_kernel<<<ggrid(N * h, B), 256, 0, st>>>(b.Y, nb.xcat + F + l * h, p.fdim, N, h);
     KCHECK();
   }
   Lin fl[3];
   final_lins(p, fl);
   int rc = mlp_fwd(blob, fl, 3, nb.xcat, p.fdim, nb.Hf, nb.out, p.fout, Rn, st);
   if (rc) return rc;
-  tr_x_mask_kernel<<<egrid(Rn * F), 256, 0, st>>>(nb.out, t.flags, net_out, Rn, F);
+  tr_x_mask_kernel<<<ggrid(N * F, B), 256, 0, st>>>(nb.out, t.flags, net_out, N, F);
   KCHECK();
   return 0;
 }
@@ -1068,7 +1096,7 @@ static int gcn_backward(const NetPlan& p, const float* blob, float* gblob, NetBu
   cudaStream_t st = t.st;
   Lin fl[3];
   final_lins(p, fl);
-  tr_x_mask_kernel<<<egrid(Rn * F), 256, 0, st>>>(dnet, t.flags, nb.ga, Rn, F);
+  tr_x_mask_kernel<<<ggrid(N * F, B), 256, 0, st>>>(dnet, t.flags, nb.ga, N, F);
   KCHECK();
   int rc = mlp_bwd(blob, gblob, fl, 3, nb.xcat, p.fdim, nb.Hf, nb.ga, Rn, nb.dxcat, p.fdim, nb.ga, nb.gb, st);
   if (rc) return rc;
@@ -1076,7 +1104,7 @@ static int gcn_backward(const NetPlan& p, const float* blob, float* gblob, NetBu
   int flip = 0;
   for (int l = p.depth - 1; l >= 0; --l) {
     LayerBufs& b = nb.L[l];
-    tr_tanh_bwd_kernel<<<egrid(Rn * h), 256, 0, st>>>(dh, nb.dxcat + F + l * h, p.fdim, nb.xcat + F + l * h, p.fdim, nb.dY, Rn, h);
+    tr_tanh_bwd_kernel<<<ggrid(N * h, B), 256, 0, st>>>(dh, nb.dxcat + F + l * h, p.fdim, nb.xcat + F + l * h, p.fdim, nb.dY, N, h);
     KCHECK();
     GcnBT g;
     g.planes = t.padj; g.p_bs = (int64_t)N * N;
