@@ -85,6 +85,8 @@ extern "C" gdss_ctx* gdss_ctx_create(int32_t N, int32_t F, const gdss_net_desc* 
   c->use_mma = !(nmma && nmma[0] == '1');
   const char* pp = getenv("GDSS_PHASE_PROF");
   c->phase_prof = pp && pp[0] == '1';
+  const char* to = getenv("GDSS_TINY_OCC");
+  c->tiny_occ = to ? atoi(to) : 4;
   // dead sub-network elimination (gdss_pack.cu analyze_liveness): needs the weights on the host once
   const char* np = getenv("GDSS_NO_PRUNE");
   if (c->num_sms > 0 && !(np && np[0] == '1')) {

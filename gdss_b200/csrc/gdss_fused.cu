@@ -2386,10 +2386,15 @@ int launch_eval_fused(const gdss_ctx* ctx, const float* x, const float* adj, con
       // tiny graphs (QM9): 128-thread CTAs; without the staged weights (38 KB) four of them fit an SM (register bound)
       // and the weights of all layers stay in the then large L1 -- measured +18 % on C2
       smem = plan_smem(ctx, nb[k], &fa.sl, false);
-      e = cudaFuncSetAttribute(fused_layers_kernel<256, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      if (e != cudaSuccess) return (int)e;
       // (64 / 96 / 256 threads per CTA measured 20 % / 12 % / 31 % slower than 128 on C2)
-      fused_layers_kernel<256, false, 2><<<B, 128, smem, ks>>>(fa);
+      // tiny_occ: CTAs per SM the register allocation is capped for (4: 128 registers, 5: 96, 6: 80, 8: 64)
+      void (*tk)(const FusedArgs) = ctx->tiny_occ == 8   ? fused_layers_kernel<128, false, 8>
+                                    : ctx->tiny_occ == 6 ? fused_layers_kernel<128, false, 6>
+                                    : ctx->tiny_occ == 5 ? fused_layers_kernel<128, false, 5>
+                                                         : fused_layers_kernel<256, false, 2>;
+      e = cudaFuncSetAttribute(tk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return (int)e;
+      tk<<<B, 128, smem, ks>>>(fa);
     } else if (smem <= limit2) {
       e = cudaFuncSetAttribute(fused_layers_kernel<256, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e != cudaSuccess) return (int)e;

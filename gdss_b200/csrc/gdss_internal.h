@@ -82,6 +82,7 @@ struct gdss_ctx {
   bool use_mma;                 // per-graph contractions on mma.sync (3xTF32); GDSS_NO_MMA=1 selects the FFMA variants
   bool use_tc;                  // final edge MLP on tcgen05 tensor cores (3xTF32); GDSS_NO_TC=1 selects the FFMA kernel
   int pruned;                   // number of dead chains / MLPs switched off by analyze_liveness (GDSS_NO_PRUNE=1: 0)
+  int tiny_occ;                 // per-graph kernel of tiny graphs (n <= 12): CTAs per SM the registers are capped for (GDSS_TINY_OCC)
   bool phase_prof;              // GDSS_PHASE_PROF=1 (read once at creation): per-phase cycle counters in the workspace
 };
 

@@ -670,7 +670,7 @@ DEVINL void fn_linear(const float* inT, int K, const float* __restrict__ W, int 
 #pragma unroll
       for (int r = 0; r < 4; ++r) acc[r][q] = bb;
     }
-#pragma unroll 4
+#pragma unroll 8              // 24 weight loads (L1 / L2) in flight per thread: the kernel is bound by their latency
     for (int k = 0; k < K; ++k) {
       const float4 xv = *reinterpret_cast<const float4*>(inT + k * FN_ROWS + 4 * rg);
       const float w0 = __ldg(wp[0] + (int64_t)k * ldw), w1 = __ldg(wp[1] + (int64_t)k * ldw), w2 = __ldg(wp[2] + (int64_t)k * ldw);

@@ -104,16 +104,20 @@ __global__ void __launch_bounds__(256) tr_linear_kernel(const float* __restrict_
 }
 
 // dW[k * ldw + o] += sum_m X[m][k] dY[m][o];  db[o] += sum_m dY[m][o]  over this CTA's row chunk.  One item = 4 inputs x 4
-// outputs (16 accumulators): per row two float4 loads feed 16 FMAs.
+// outputs (16 accumulators): per row two float4 loads feed 16 FMAs.  Small weight matrices (K * NO / 16 items < 256: the
+// per-edge / per-channel layers) would leave most of the CTA idle, so G = 256 / items thread groups share the rows of a tile
+// (group g takes rows g, g + G, ..) and their partial sums are added in shared memory before the one atomicAdd per weight.
+// The bias gradient rides on the items of the first input group (k4 = 0).
 __global__ void __launch_bounds__(256) tr_wgrad_kernel(const float* __restrict__ X, int ldx, const float* __restrict__ dY, int ldy,
                                                        float* __restrict__ dW, int ldw, float* __restrict__ db, int64_t M, int K,
-                                                       int NO) {
+                                                       int NO, int chunk, int rows_tile) {
   extern __shared__ __align__(16) float sm[];
   const int NOP = (NO + 3) & ~3, KP = (K + 3) & ~3;
-  float* Xs = sm;                        // [ROWS][KP]
-  float* Ys = Xs + TR_WG_ROWS * KP;      // [ROWS][NOP]
+  float* Xs = sm;                        // [rows_tile][KP]
+  float* Ys = Xs + rows_tile * KP;      // [ROWS][NOP]
   const int tid = threadIdx.x;
   const int og = NOP >> 2, kg = KP >> 2, items = kg * og;
+  const int G = items < 256 ? 256 / items : 1;           // row groups (1: every thread owns up to TR_WG_MAXI items)
   float acc[TR_WG_MAXI][4][4];
 #pragma unroll
   for (int it = 0; it < TR_WG_MAXI; ++it)
@@ -121,41 +125,90 @@ __global__ void __launch_bounds__(256) tr_wgrad_kernel(const float* __restrict__
     for (int a = 0; a < 4; ++a)
 #pragma unroll
       for (int q = 0; q < 4; ++q) acc[it][a][q] = 0.f;
-  float bacc = 0.f;
-  const int64_t m_lo = (int64_t)blockIdx.x * TR_WG_CHUNK;
-  const int64_t m_hi = m_lo + TR_WG_CHUNK < M ? m_lo + TR_WG_CHUNK : M;
-  for (int64_t m0 = m_lo; m0 < m_hi; m0 += TR_WG_ROWS) {
-    for (int idx = tid; idx < TR_WG_ROWS * KP; idx += 256) {
+  float bacc[TR_WG_MAXI][4];
+#pragma unroll
+  for (int it = 0; it < TR_WG_MAXI; ++it)
+#pragma unroll
+    for (int q = 0; q < 4; ++q) bacc[it][q] = 0.f;
+  const int64_t m_lo = (int64_t)blockIdx.x * chunk;
+  const int64_t m_hi = m_lo + chunk < M ? m_lo + chunk : M;
+  const int g_item = tid % items, g_row = tid / items;   // G > 1: this thread's item and row group
+  for (int64_t m0 = m_lo; m0 < m_hi; m0 += rows_tile) {
+    for (int idx = tid; idx < rows_tile * KP; idx += 256) {
       const int r = idx / KP, k = idx - r * KP;
       Xs[idx] = (m0 + r < m_hi && k < K) ? X[(m0 + r) * ldx + k] : 0.f;
     }
-    for (int idx = tid; idx < TR_WG_ROWS * NOP; idx += 256) {
+    for (int idx = tid; idx < rows_tile * NOP; idx += 256) {
       const int r = idx / NOP, o = idx - r * NOP;
       Ys[idx] = (m0 + r < m_hi && o < NO) ? dY[(m0 + r) * ldy + o] : 0.f;
     }
     __syncthreads();
-#pragma unroll
-    for (int it = 0; it < TR_WG_MAXI; ++it) {
-      const int item = tid + it * 256;
-      if (item < items) {
-        const int k4 = (item / og) * 4, o4 = (item - (item / og) * og) * 4;
-#pragma unroll 4
-        for (int r = 0; r < TR_WG_ROWS; ++r) {
+    if (G > 1) {
+      if (g_row < G) {
+        const int k4 = (g_item / og) * 4, o4 = (g_item - (g_item / og) * og) * 4;
+        const bool bias_item = k4 == 0;
+        for (int r = g_row; r < rows_tile; r += G) {
           const float4 x = *reinterpret_cast<const float4*>(Xs + r * KP + k4);
           const float4 y = *reinterpret_cast<const float4*>(Ys + r * NOP + o4);
           const float xv[4] = {x.x, x.y, x.z, x.w};
 #pragma unroll
           for (int a = 0; a < 4; ++a) {
-            acc[it][a][0] = fmaf(xv[a], y.x, acc[it][a][0]); acc[it][a][1] = fmaf(xv[a], y.y, acc[it][a][1]);
-            acc[it][a][2] = fmaf(xv[a], y.z, acc[it][a][2]); acc[it][a][3] = fmaf(xv[a], y.w, acc[it][a][3]);
+            acc[0][a][0] = fmaf(xv[a], y.x, acc[0][a][0]); acc[0][a][1] = fmaf(xv[a], y.y, acc[0][a][1]);
+            acc[0][a][2] = fmaf(xv[a], y.z, acc[0][a][2]); acc[0][a][3] = fmaf(xv[a], y.w, acc[0][a][3]);
+          }
+          if (bias_item) { bacc[0][0] += y.x; bacc[0][1] += y.y; bacc[0][2] += y.z; bacc[0][3] += y.w; }
+        }
+      }
+    } else {
+#pragma unroll
+      for (int it = 0; it < TR_WG_MAXI; ++it) {
+        const int item = tid + it * 256;
+        if (item < items) {
+          const int k4 = (item / og) * 4, o4 = (item - (item / og) * og) * 4;
+          const bool bias_item = k4 == 0;
+#pragma unroll 4
+          for (int r = 0; r < rows_tile; ++r) {
+            const float4 x = *reinterpret_cast<const float4*>(Xs + r * KP + k4);
+            const float4 y = *reinterpret_cast<const float4*>(Ys + r * NOP + o4);
+            const float xv[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+            for (int a = 0; a < 4; ++a) {
+              acc[it][a][0] = fmaf(xv[a], y.x, acc[it][a][0]); acc[it][a][1] = fmaf(xv[a], y.y, acc[it][a][1]);
+              acc[it][a][2] = fmaf(xv[a], y.z, acc[it][a][2]); acc[it][a][3] = fmaf(xv[a], y.w, acc[it][a][3]);
+            }
+            if (bias_item) { bacc[it][0] += y.x; bacc[it][1] += y.y; bacc[it][2] += y.z; bacc[it][3] += y.w; }
           }
         }
       }
     }
-    if (db && tid < NO) {
-      for (int r = 0; r < TR_WG_ROWS; ++r) bacc += Ys[r * NOP + tid];
+    __syncthreads();
+  }
+  if (G > 1) {
+    // partial sums of the row groups -> shared memory [group][item][20] (16 weights + 4 bias entries), then one sum per entry
+    float* red = sm;                     // the launch reserves 256 * 20 floats for this
+    if (g_row < G) {
+      float* dst = red + (g_row * items + g_item) * 20;
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) dst[a * 4 + q] = acc[0][a][q];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) dst[16 + q] = bacc[0][q];
     }
     __syncthreads();
+    for (int e = tid; e < items * 20; e += 256) {
+      const int item = e / 20, w = e - item * 20;
+      float s = 0.f;
+      for (int g = 0; g < G; ++g) s += red[(g * items + item) * 20 + w];
+      const int k4 = (item / og) * 4, o4 = (item - (item / og) * og) * 4;
+      if (w < 16) {
+        const int a = w >> 2, q = w & 3;
+        if (k4 + a < K && o4 + q < NO) atomicAdd(dW + (int64_t)(k4 + a) * ldw + o4 + q, s);
+      } else if (db && k4 == 0 && o4 + (w - 16) < NO) {
+        atomicAdd(db + o4 + (w - 16), s);
+      }
+    }
+    return;
   }
 #pragma unroll
   for (int it = 0; it < TR_WG_MAXI; ++it) {
@@ -167,9 +220,13 @@ __global__ void __launch_bounds__(256) tr_wgrad_kernel(const float* __restrict__
 #pragma unroll
         for (int q = 0; q < 4; ++q)
           if (k4 + a < K && o4 + q < NO) atomicAdd(dW + (int64_t)(k4 + a) * ldw + o4 + q, acc[it][a][q]);
+      if (db && k4 == 0) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          if (o4 + q < NO) atomicAdd(db + o4 + q, bacc[it][q]);
+      }
     }
   }
-  if (db && tid < NO) atomicAdd(db + tid, bacc);
 }
 
 // g *= ELU'(pre) with the saved post-activation h: ELU'(pre) = 1 (pre > 0) or exp(pre) = h + 1   (layers.py:150)
@@ -249,13 +306,14 @@ struct GcnBT {
 __global__ void __launch_bounds__(256) tr_gcn_bwd_kernel(GcnBT a) {
   extern __shared__ __align__(16) float sm[];
   const int c = blockIdx.x, b = blockIdx.y, N = a.N, OW = a.OW, NS = N + 1;
+  const int OS = OW | 1;          // odd row stride of the shared copies: the d A^ products walk them by rows (no bank conflicts)
   float* At = sm;                 // [N][N + 1]
   float* G = At + N * NS;         // [N][N + 1]   dA^_ij = sum_o dY_io XW_jo
   float* dv = G + N * NS;         // [N]
   float* dg = dv + N;             // [N]  degraw
   float* dd = dg + N;             // [N]  d loss / d deg
-  float* xw = dd + N;             // [N][OW]
-  float* dy = xw + N * OW;        // [N][OW]
+  float* xw = dd + N;             // [N][OS]
+  float* dy = xw + N * OS;        // [N][OS]
   const int tid = threadIdx.x;
   const float* P = a.planes + b * a.p_bs + (int64_t)c * N * N;
   const int64_t r0 = ((int64_t)c * a.B + b) * N;
@@ -268,21 +326,22 @@ __global__ void __launch_bounds__(256) tr_gcn_bwd_kernel(GcnBT a) {
     dg[i] = a.degraw[r0 + i];
   }
   for (int idx = tid; idx < N * OW; idx += 256) {
-    xw[idx] = a.XW[r0 * OW + idx];
-    dy[idx] = a.dY[r0 * OW + idx];
+    const int i = idx / OW, o = idx - i * OW;
+    xw[i * OS + o] = a.XW[r0 * OW + idx];
+    dy[i * OS + o] = a.dY[r0 * OW + idx];
   }
   __syncthreads();
   // d(xW)_j = sum_i A^_ij dY_i
   for (int idx = tid; idx < N * OW; idx += 256) {
     const int j = idx / OW, o = idx - j * OW;
     float s = 0.f;
-    for (int i = 0; i < N; ++i) s = fmaf(At[i * NS + j] * dv[i], dy[i * OW + o], s);
+    for (int i = 0; i < N; ++i) s = fmaf(At[i * NS + j] * dv[i], dy[i * OS + o], s);
     a.dXW[(r0 + j) * OW + o] = dv[j] * s;
   }
   if (a.dbias) {
     for (int o = tid; o < OW; o += 256) {
       float s = 0.f;
-      for (int i = 0; i < N; ++i) s += dy[i * OW + o];
+      for (int i = 0; i < N; ++i) s += dy[i * OS + o];
       atomicAdd(a.dbias + (int64_t)c * a.b_cs + o, s);
     }
   }
@@ -290,7 +349,7 @@ __global__ void __launch_bounds__(256) tr_gcn_bwd_kernel(GcnBT a) {
   for (int idx = tid; idx < N * N; idx += 256) {
     const int i = idx / N, j = idx - i * N;
     float s = 0.f;
-    for (int o = 0; o < OW; ++o) s = fmaf(dy[i * OW + o], xw[j * OW + o], s);
+    for (int o = 0; o < OW; ++o) s = fmaf(dy[i * OS + o], xw[j * OS + o], s);
     G[i * NS + j] = s;
   }
   __syncthreads();
@@ -317,20 +376,20 @@ __global__ void __launch_bounds__(256) tr_gcn_bwd_kernel(GcnBT a) {
 __global__ void __launch_bounds__(256) tr_maps_fwd_kernel(const float* __restrict__ Y, float* __restrict__ M, int B, int C, int N,
                                                           int OW, int attn, int heads, float scale) {
   extern __shared__ __align__(16) float sm[];
-  const int c = blockIdx.x, b = blockIdx.y, NS = N + 1;
-  float* qk = sm;                  // [N][2 attn]
-  float* T = qk + N * 2 * attn;    // [N][N + 1]
+  const int c = blockIdx.x, b = blockIdx.y, NS = N + 1, QS = 2 * attn + 1;     // odd row strides: no bank conflicts
+  float* qk = sm;                  // [N][QS]
+  float* T = qk + N * QS;          // [N][N + 1]
   const int tid = threadIdx.x, hd = attn / heads;
   const int64_t r0 = ((int64_t)c * B + b) * N;
   for (int idx = tid; idx < N * 2 * attn; idx += 256) {
     const int i = idx / (2 * attn), o = idx - i * 2 * attn;
-    qk[idx] = Y[(r0 + i) * OW + o];
+    qk[i * QS + o] = Y[(r0 + i) * OW + o];
   }
   __syncthreads();
   for (int idx = tid; idx < N * N; idx += 256) {
     const int i = idx / N, j = idx - i * N;
-    const float* q = qk + i * 2 * attn;
-    const float* k = qk + j * 2 * attn + attn;
+    const float* q = qk + i * QS;
+    const float* k = qk + j * QS + attn;
     float t = 0.f;
     for (int h = 0; h < heads; ++h) {
       float s = 0.f;
@@ -352,14 +411,14 @@ __global__ void __launch_bounds__(256) tr_maps_bwd_kernel(const float* __restric
                                                           float* __restrict__ dY, int B, int C, int N, int OW, int attn, int heads,
                                                           float scale) {
   extern __shared__ __align__(16) float sm[];
-  const int c = blockIdx.x, b = blockIdx.y, NS = N + 1;
-  float* qk = sm;                  // [N][2 attn]
-  float* dT = qk + N * 2 * attn;   // [N][N + 1]
+  const int c = blockIdx.x, b = blockIdx.y, NS = N + 1, QS = 2 * attn + 1;     // odd row strides: no bank conflicts
+  float* qk = sm;                  // [N][QS]
+  float* dT = qk + N * QS;         // [N][N + 1]
   const int tid = threadIdx.x, hd = attn / heads;
   const int64_t r0 = ((int64_t)c * B + b) * N;
   for (int idx = tid; idx < N * 2 * attn; idx += 256) {
     const int i = idx / (2 * attn), o = idx - i * 2 * attn;
-    qk[idx] = Y[(r0 + i) * OW + o];
+    qk[i * QS + o] = Y[(r0 + i) * OW + o];
   }
   const float* Mi = dM + ((int64_t)b * C + c) * N * N;
   for (int idx = tid; idx < N * N; idx += 256) {
@@ -377,8 +436,8 @@ __global__ void __launch_bounds__(256) tr_maps_bwd_kernel(const float* __restric
     for (int e = 0; e < 16; ++e) acc[e] = 0.f;
     for (int j = 0; j < N; ++j) {
       // which = 0: dQ_i += dS_ij K_j ;  which = 1: dK_i += dS_ji Q_j
-      const float* q = which == 0 ? qk + i * 2 * attn + h * hd : qk + j * 2 * attn + h * hd;
-      const float* k = which == 0 ? qk + j * 2 * attn + attn + h * hd : qk + i * 2 * attn + attn + h * hd;
+      const float* q = which == 0 ? qk + i * QS + h * hd : qk + j * QS + h * hd;
+      const float* k = which == 0 ? qk + j * QS + attn + h * hd : qk + i * QS + attn + h * hd;
       float s = 0.f;
       for (int e = 0; e < hd; ++e) s = fmaf(q[e], k[e], s);
       const float th = tanhf(s * scale);
@@ -689,11 +748,23 @@ static int wgrad(const float* X, int ldx, const float* dY, int ldy, float* dW, i
     for (int o0 = 0; o0 < NO; o0 += TR_NO_TILE) {
       const int no = NO - o0 < TR_NO_TILE ? NO - o0 : TR_NO_TILE;
       if ((int64_t)(((kt + 3) & ~3) / 4) * (((no + 3) & ~3) / 4) > 256 * TR_WG_MAXI) return GDSS_E_UNSUPPORTED;
-      const size_t smem = sizeof(float) * ((size_t)TR_WG_ROWS * ((kt + 3) & ~3) + (size_t)TR_WG_ROWS * ((no + 3) & ~3));
+      const int kp = (kt + 3) & ~3, nop = (no + 3) & ~3;
+      // rows per shared-memory tile: 32 for the wide layers, up to 256 for the narrow ones (about 32 KB per tile)
+      int rows_tile = 8192 / (kp + nop) / TR_WG_ROWS * TR_WG_ROWS;
+      if (rows_tile < TR_WG_ROWS) rows_tile = TR_WG_ROWS;
+      if (rows_tile > 256) rows_tile = 256;
+      // rows per CTA: about four CTAs per SM, whole tiles, at most TR_WG_CHUNK
+      int64_t chunk = (M / (148 * 4) + TR_WG_ROWS - 1) / TR_WG_ROWS * TR_WG_ROWS;
+      if (chunk < TR_WG_ROWS) chunk = TR_WG_ROWS;
+      if (chunk > TR_WG_CHUNK) chunk = TR_WG_CHUNK;
+      if (rows_tile > chunk) rows_tile = (int)chunk;
+      size_t smem = sizeof(float) * (size_t)rows_tile * (kp + nop);
+      if (smem < sizeof(float) * 256 * 20) smem = sizeof(float) * 256 * 20;      // the row groups' reduction buffer
       int rc = set_smem_attr((const void*)tr_wgrad_kernel, smem);
       if (rc) return rc;
-      tr_wgrad_kernel<<<(unsigned)((M + TR_WG_CHUNK - 1) / TR_WG_CHUNK), 256, smem, st>>>(
-          X + k0, ldx, dY + o0, ldy, dW + (int64_t)k0 * ldw + o0, ldw, (db && k0 == 0) ? db + o0 : nullptr, M, kt, no);
+      tr_wgrad_kernel<<<(unsigned)((M + chunk - 1) / chunk), 256, smem, st>>>(
+          X + k0, ldx, dY + o0, ldy, dW + (int64_t)k0 * ldw + o0, ldw, (db && k0 == 0) ? db + o0 : nullptr, M, kt, no, (int)chunk,
+          rows_tile);
       count_launch();
       LAUNCH_CHECK();
     }
@@ -748,8 +819,8 @@ static int mlp_bwd(const float* blob, float* gblob, const Lin* lin, int n, const
 }
 
 static size_t gcn_fwd_smem(int N, int OW) { return sizeof(float) * ((size_t)N * (N + 1) + N + (size_t)N * OW); }
-static size_t gcn_bwd_smem(int N, int OW) { return sizeof(float) * (2 * (size_t)N * (N + 1) + 3 * N + 2 * (size_t)N * OW); }
-static size_t maps_smem(int N, int attn) { return sizeof(float) * ((size_t)N * 2 * attn + (size_t)N * (N + 1)); }
+static size_t gcn_bwd_smem(int N, int OW) { return sizeof(float) * (2 * (size_t)N * (N + 1) + 3 * N + 2 * (size_t)N * (OW | 1)); }
+static size_t maps_smem(int N, int attn) { return sizeof(float) * ((size_t)N * (2 * attn + 1) + (size_t)N * (N + 1)); }
 
 // everything one network needs for forward + backward; planned twice (sizes only, then with the arena)
 struct LayerBufs {
