@@ -40,8 +40,11 @@ DEVINL float elu_exact(float v) { return v > 0.f ? v : expm1f(v); }
 // columns as one float4: 3 shared-memory loads feed 32 FMAs per k.
 __global__ void __launch_bounds__(256) tr_linear_kernel(const float* __restrict__ X, int ldx, const float* __restrict__ W, int ldw,
                                                         const float* __restrict__ bias, float* __restrict__ Y, int ldy, int64_t M,
-                                                        int K, int NO, int trans, int act, int accumulate, int TM) {
+                                                        int K, int NO, int trans, int act, int accumulate, int TM,
+                                                        const int* __restrict__ Mdev) {
   extern __shared__ __align__(16) float sm[];
+  if (Mdev) M = *Mdev;                 // compact pixel rows: the row count lives on the device (the grid covers the upper bound)
+  if ((int64_t)blockIdx.x * TM >= M) return;
   const int NOP = (NO + 3) & ~3;
   const int TMS = TM + 4;           // row stride of the transposed X tile (16-byte aligned rows); TM = rows per CTA (multiple of 8)
   float* Ws = sm;                   // [K][NOP]
@@ -110,8 +113,10 @@ __global__ void __launch_bounds__(256) tr_linear_kernel(const float* __restrict_
 // The bias gradient rides on the items of the first input group (k4 = 0).
 __global__ void __launch_bounds__(256) tr_wgrad_kernel(const float* __restrict__ X, int ldx, const float* __restrict__ dY, int ldy,
                                                        float* __restrict__ dW, int ldw, float* __restrict__ db, int64_t M, int K,
-                                                       int NO, int chunk, int rows_tile) {
+                                                       int NO, int chunk, int rows_tile, const int* __restrict__ Mdev) {
   extern __shared__ __align__(16) float sm[];
+  if (Mdev) M = *Mdev;
+  if ((int64_t)blockIdx.x * chunk >= M) return;
   const int NOP = (NO + 3) & ~3, KP = (K + 3) & ~3;
   float* Xs = sm;                        // [rows_tile][KP]
   float* Ys = Xs + rows_tile * KP;      // [ROWS][NOP]
@@ -230,7 +235,8 @@ __global__ void __launch_bounds__(256) tr_wgrad_kernel(const float* __restrict__
 }
 
 // g *= ELU'(pre) with the saved post-activation h: ELU'(pre) = 1 (pre > 0) or exp(pre) = h + 1   (layers.py:150)
-__global__ void tr_elu_bwd_kernel(float* __restrict__ g, const float* __restrict__ h, int64_t n) {
+__global__ void tr_elu_bwd_kernel(float* __restrict__ g, const float* __restrict__ h, int64_t n, int width, const int* __restrict__ Mdev) {
+  if (Mdev) n = (int64_t)*Mdev * width;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const float hv = h[i];
     g[i] *= hv > 0.f ? 1.f : hv + 1.f;
@@ -475,62 +481,128 @@ __global__ void tr_pow_kernel(const float* __restrict__ adj, float* __restrict__
   }
 }
 
-// edge-MLP input rows (attention.py:109-110): ein[(b, i, j)] = [M_0 .. M_{C-1}, P_0 .. P_{C-1}]
+// ---- compact pixel rows.  Everything per-edge is symmetric in (i, j) (attention.py:49, :113), the diagonal never reaches an
+// output (layers.py:72-74, ScoreNetwork_A.py:145) and pixels of padded nodes are masked to zero with a zero gradient, so the
+// per-edge MLPs run on ONE row per valid strict-upper-triangle pixel r = (b, i < j < neff_b) instead of the reference's N^2
+// rows per graph.  Row r stands for both (i, j) and (j, i): forward values are written to both entries; on the way back the
+// row's output gradient is the SUM of the two entries' gradients and its input gradient is split in halves between them
+// (which is what the dense formulation yields for two identical rows).  pb[r] = b, pij[r] = i << 16 | j, *Mdev = row count.
+// (32-bit indices: the host checks B N (N - 1) / 2 * 128 < 2^31; 64-bit divisions would dominate these kernels)
+#define PIX_ROWS(r, per)                                                                  \
+  const int total__ = (*Mdev) * (per);                                                   \
+  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < total__; r += gridDim.x * blockDim.x)
+
+// neff[b] = 1 + last set flag, poff = exclusive prefix sum of neff (neff - 1) / 2, poff[B] = total (one CTA)
+__global__ void __launch_bounds__(1024) tr_pix_scan_kernel(const float* __restrict__ flags, int B, int N, int* __restrict__ neff,
+                                                           int* __restrict__ poff) {
+  __shared__ int part[1024];
+  __shared__ int carry;
+  const int tid = threadIdx.x;
+  if (tid == 0) carry = 0;
+  __syncthreads();
+  for (int b0 = 0; b0 < B; b0 += 1024) {
+    const int b = b0 + tid;
+    int n = 0;
+    if (b < B) {
+      for (int i = N - 1; i >= 0; --i)
+        if (flags[(int64_t)b * N + i] != 0.f) { n = i + 1; break; }
+      neff[b] = n;
+    }
+    const int cnt = n * (n - 1) / 2;
+    part[tid] = cnt;
+    __syncthreads();
+    for (int off = 1; off < 1024; off <<= 1) {             // inclusive scan (Hillis-Steele)
+      const int v = tid >= off ? part[tid - off] : 0;
+      __syncthreads();
+      part[tid] += v;
+      __syncthreads();
+    }
+    if (b < B) poff[b] = carry + part[tid] - cnt;
+    __syncthreads();
+    if (tid == 1023) carry += part[1023];
+    __syncthreads();
+  }
+  if (tid == 0) poff[B] = carry;
+}
+
+__global__ void tr_pix_map_kernel(const int* __restrict__ neff, const int* __restrict__ poff, int* __restrict__ pb, int* __restrict__ pij) {
+  const int b = blockIdx.y, n = neff[b], base = poff[b];
+  PER_GRAPH(idx, n * n) {
+    const int i = idx / n, j = idx - i * n;
+    if (j > i) {
+      const int r = base + i * (2 * n - i - 1) / 2 + j - i - 1;
+      pb[r] = b;
+      pij[r] = (i << 16) | j;
+    }
+  }
+}
+
+// edge-MLP input rows (attention.py:109-110): ein[r] = [M_0 .. M_{C-1}, P_0 .. P_{C-1}] at (i, j)
 __global__ void tr_edge_rows_kernel(const float* __restrict__ M, const float* __restrict__ planes, int64_t p_bs,
-                                    float* __restrict__ ein, int C, int N) {
-  const int64_t b = blockIdx.y;
+                                    float* __restrict__ ein, int C, int N, const int* __restrict__ pb, const int* __restrict__ pij,
+                                    const int* __restrict__ Mdev) {
   const int NN = N * N, C2 = 2 * C;
-  const float* Mb = M + b * C * NN;
-  const float* Pb = planes + b * p_bs;
-  float* eb = ein + b * NN * C2;
-  PER_GRAPH(e, NN * C2) {
-    const int ij = e / C2, k = e - ij * C2;
-    eb[e] = k < C ? Mb[k * NN + ij] : Pb[(k - C) * NN + ij];
+  PIX_ROWS(e, C2) {
+    const int r = e / C2, k = e - r * C2;
+    const int64_t b = pb[r];
+    const int ij = (pij[r] >> 16) * N + (pij[r] & 0xffff);
+    ein[e] = k < C ? M[(b * C + k) * NN + ij] : planes[b * p_bs + (int64_t)(k - C) * NN + ij];
   }
 }
 
-// adj_out = mask_adjs(s + s^T) (attention.py:113-114) from the MLP output rows s[(b, i, j)][o]
+// adj_out = mask_adjs(s + s^T) (attention.py:113-114): both entries of the pixel get 2 s f_i f_j (entries of padded nodes and
+// the unused diagonal stay zero: the stack is cleared at the start of the forward)
 __global__ void tr_edge_out_kernel(const float* __restrict__ s, const float* __restrict__ flags, float* __restrict__ planes,
-                                   int64_t p_bs, int Co, int N) {
-  const int64_t b = blockIdx.y;
+                                   int64_t p_bs, int Co, int N, const int* __restrict__ pb, const int* __restrict__ pij,
+                                   const int* __restrict__ Mdev) {
   const int NN = N * N;
-  const float* sb = s + b * NN * Co;
-  const float* fl = flags + b * N;
-  float* Pb = planes + b * p_bs;
-  PER_GRAPH(e, Co * NN) {
-    const int o = e / NN, ij = e - o * NN;
-    const int i = ij / N, j = ij - i * N;
-    Pb[e] = (sb[ij * Co + o] + sb[(j * N + i) * Co + o]) * fl[i] * fl[j];
+  const int Mr = *Mdev;
+  PIX_ROWS(e, Co) {
+    const int o = e / Mr, r = e - o * Mr;
+    const int64_t b = pb[r];
+    const int i = pij[r] >> 16, j = pij[r] & 0xffff;
+    const float v = 2.f * s[(int64_t)r * Co + o] * flags[b * N + i] * flags[b * N + j];
+    float* P = planes + b * p_bs + (int64_t)o * NN;
+    P[i * N + j] = v;
+    P[j * N + i] = v;
   }
 }
 
-// gradient of the rows: g[(b, i, j)][o] = f_i f_j (dP_o[i][j] + dP_o[j][i])
+// gradient of the rows: g[r][o] = 2 f_i f_j (dP_o[i][j] + dP_o[j][i])
 __global__ void tr_edge_gin_kernel(const float* __restrict__ dplanes, int64_t p_bs, const float* __restrict__ flags,
-                                   float* __restrict__ g, int Co, int N) {
-  const int64_t b = blockIdx.y;
+                                   float* __restrict__ g, int Co, int N, const int* __restrict__ pb, const int* __restrict__ pij,
+                                   const int* __restrict__ Mdev) {
   const int NN = N * N;
-  const float* dPb = dplanes + b * p_bs;
-  const float* fl = flags + b * N;
-  float* gb = g + b * NN * Co;
-  PER_GRAPH(e, NN * Co) {
-    const int ij = e / Co, o = e - ij * Co;
-    const int i = ij / N, j = ij - i * N;
-    gb[e] = fl[i] * fl[j] * (dPb[o * NN + ij] + dPb[o * NN + j * N + i]);
+  const int Mr = *Mdev;
+  PIX_ROWS(e, Co) {
+    const int o = e / Mr, r = e - o * Mr;
+    const int64_t b = pb[r];
+    const int i = pij[r] >> 16, j = pij[r] & 0xffff;
+    const float* dP = dplanes + b * p_bs + (int64_t)o * NN;
+    g[(int64_t)r * Co + o] = 2.f * flags[b * N + i] * flags[b * N + j] * (dP[i * N + j] + dP[j * N + i]);
   }
 }
 
-// d ein -> dM (assign) and the input planes' gradient (+=)
+// d ein -> dM (both entries get half; dM is cleared before) and the input planes' gradient (+= half to both entries)
 __global__ void tr_edge_dein_kernel(const float* __restrict__ dein, float* __restrict__ dM, float* __restrict__ dplanes,
-                                    int64_t p_bs, int C, int N) {
-  const int64_t b = blockIdx.y;
+                                    int64_t p_bs, int C, int N, const int* __restrict__ pb, const int* __restrict__ pij,
+                                    const int* __restrict__ Mdev) {
   const int NN = N * N, C2 = 2 * C;
-  const float* db_ = dein + b * NN * C2;
-  float* dMb = dM + b * C * NN;
-  float* dPb = dplanes + b * p_bs;
-  PER_GRAPH(e, NN * C2) {
-    const int ij = e / C2, k = e - ij * C2;
-    if (k < C) dMb[k * NN + ij] = db_[e];
-    else dPb[(k - C) * NN + ij] += db_[e];
+  const int Mr = *Mdev;
+  PIX_ROWS(e, C2) {
+    const int k = e / Mr, r = e - k * Mr;
+    const int64_t b = pb[r];
+    const int i = pij[r] >> 16, j = pij[r] & 0xffff;
+    const float v = 0.5f * dein[(int64_t)r * C2 + k];
+    if (k < C) {
+      float* D = dM + (b * C + k) * NN;
+      D[i * N + j] = v;
+      D[j * N + i] = v;
+    } else {
+      float* D = dplanes + b * p_bs + (int64_t)(k - C) * NN;
+      D[i * N + j] += v;
+      D[j * N + i] += v;
+    }
   }
 }
 
@@ -583,36 +655,50 @@ __global__ void tr_node_dpre_kernel(const float* __restrict__ ga, const float* _
   }
 }
 
-// final MLP of ScoreNetworkA: input rows = the concatenated stack per pixel (ScoreNetwork_A.py:141-142)
-__global__ void tr_stack_rows_kernel(const float* __restrict__ S, int64_t s_bs, float* __restrict__ rows, int P, int N) {
-  const int64_t b = blockIdx.y;
+// final MLP of ScoreNetworkA: input rows = the concatenated stack per pixel (ScoreNetwork_A.py:141-142), compact rows
+__global__ void tr_stack_rows_kernel(const float* __restrict__ S, int64_t s_bs, float* __restrict__ rows, int P, int N,
+                                     const int* __restrict__ pb, const int* __restrict__ pij, const int* __restrict__ Mdev) {
   const int NN = N * N;
-  const float* Sb = S + b * s_bs;
-  float* rb = rows + b * NN * P;
-  PER_GRAPH(e, NN * P) {
-    const int ij = e / P, p = e - ij * P;
-    rb[e] = Sb[p * NN + ij];
+  PIX_ROWS(e, P) {
+    const int r = e / P, p = e - r * P;
+    rows[e] = S[(int64_t)pb[r] * s_bs + (int64_t)p * NN + (pij[r] >> 16) * N + (pij[r] & 0xffff)];
   }
 }
 
-__global__ void tr_stack_rows_bwd_kernel(const float* __restrict__ drows, float* __restrict__ dS, int64_t s_bs, int P, int N) {
-  const int64_t b = blockIdx.y;
+// (dS is cleared before: half of the row's gradient to each of the two entries)
+__global__ void tr_stack_rows_bwd_kernel(const float* __restrict__ drows, float* __restrict__ dS, int64_t s_bs, int P, int N,
+                                         const int* __restrict__ pb, const int* __restrict__ pij, const int* __restrict__ Mdev) {
   const int NN = N * N;
-  const float* rb = drows + b * NN * P;
-  float* Sb = dS + b * s_bs;
-  PER_GRAPH(e, P * NN) {
-    const int p = e / NN, ij = e - p * NN;
-    Sb[e] = rb[ij * P + p];
+  const int Mr = *Mdev;
+  PIX_ROWS(e, P) {
+    const int p = e / Mr, r = e - p * Mr;
+    const int i = pij[r] >> 16, j = pij[r] & 0xffff;
+    const float v = 0.5f * drows[(int64_t)r * P + p];
+    float* D = dS + (int64_t)pb[r] * s_bs + (int64_t)p * NN;
+    D[i * N + j] = v;
+    D[j * N + i] = v;
   }
 }
 
-// score_adj = mask_adjs(out) with a zero diagonal (ScoreNetwork_A.py:143-148); the same factor on the way back
-__global__ void tr_adj_mask_kernel(const float* __restrict__ in, const float* __restrict__ flags, float* __restrict__ out, int N) {
-  const int64_t b = blockIdx.y;
-  const int64_t base = b * N * N;
-  PER_GRAPH(ij, N * N) {
-    const int i = ij / N, j = ij - i * N;
-    out[base + ij] = i == j ? 0.f : in[base + ij] * flags[b * N + i] * flags[b * N + j];
+// score_adj = mask_adjs(out) with a zero diagonal (ScoreNetwork_A.py:143-148): out[r] f_i f_j to both entries (net_out cleared before)
+__global__ void tr_adj_out_kernel(const float* __restrict__ in, const float* __restrict__ flags, float* __restrict__ out, int N,
+                                  const int* __restrict__ pb, const int* __restrict__ pij, const int* __restrict__ Mdev) {
+  PIX_ROWS(r, 1) {
+    const int64_t b = pb[r];
+    const int i = pij[r] >> 16, j = pij[r] & 0xffff;
+    const float v = in[r] * flags[b * N + i] * flags[b * N + j];
+    out[b * N * N + i * N + j] = v;
+    out[b * N * N + j * N + i] = v;
+  }
+}
+
+// the same factor on the way back: g[r] = f_i f_j (dnet[i][j] + dnet[j][i])
+__global__ void tr_adj_gin_kernel(const float* __restrict__ dnet, const float* __restrict__ flags, float* __restrict__ g, int N,
+                                  const int* __restrict__ pb, const int* __restrict__ pij, const int* __restrict__ Mdev) {
+  PIX_ROWS(r, 1) {
+    const int64_t b = pb[r];
+    const int i = pij[r] >> 16, j = pij[r] & 0xffff;
+    g[r] = flags[b * N + i] * flags[b * N + j] * (dnet[b * N * N + i * N + j] + dnet[b * N * N + j * N + i]);
   }
 }
 
@@ -723,7 +809,7 @@ static int set_smem_attr(const void* fn, size_t bytes) {
 #define TR_K_TILE 128        // input rows per launch of the weight-gradient kernel
 
 static int linear(const float* X, int ldx, const float* W, int ldw, const float* bias, float* Y, int ldy, int64_t M, int K, int NO,
-                  int trans, int act, int accumulate, cudaStream_t st) {
+                  int trans, int act, int accumulate, cudaStream_t st, const int* Mdev = nullptr) {
   for (int o0 = 0; o0 < NO; o0 += TR_NO_TILE) {
     const int no = NO - o0 < TR_NO_TILE ? NO - o0 : TR_NO_TILE;
     int tm = TR_TM;                   // rows per CTA: the largest tile whose transposed copy fits next to the weights
@@ -734,7 +820,7 @@ static int linear(const float* X, int ldx, const float* W, int ldw, const float*
     // output column o of the tile = column o0 + o: W[k][o0 + o] (trans = 0) or row o0 + o of W (trans = 1)
     const float* Wt = trans ? W + (int64_t)o0 * ldw : W + o0;
     tr_linear_kernel<<<(unsigned)((M + tm - 1) / tm), 256, smem, st>>>(X, ldx, Wt, ldw, bias ? bias + o0 : nullptr, Y + o0, ldy, M, K, no,
-                                                                       trans, act, accumulate, tm);
+                                                                       trans, act, accumulate, tm, Mdev);
     count_launch();
     LAUNCH_CHECK();
   }
@@ -742,7 +828,7 @@ static int linear(const float* X, int ldx, const float* W, int ldw, const float*
 }
 
 static int wgrad(const float* X, int ldx, const float* dY, int ldy, float* dW, int ldw, float* db, int64_t M, int K, int NO,
-                 cudaStream_t st) {
+                 cudaStream_t st, const int* Mdev = nullptr) {
   for (int k0 = 0; k0 < K; k0 += TR_K_TILE) {
     const int kt = K - k0 < TR_K_TILE ? K - k0 : TR_K_TILE;
     for (int o0 = 0; o0 < NO; o0 += TR_NO_TILE) {
@@ -754,7 +840,8 @@ static int wgrad(const float* X, int ldx, const float* dY, int ldy, float* dW, i
       if (rows_tile < TR_WG_ROWS) rows_tile = TR_WG_ROWS;
       if (rows_tile > 256) rows_tile = 256;
       // rows per CTA: about four CTAs per SM, whole tiles, at most TR_WG_CHUNK
-      int64_t chunk = (M / (148 * 4) + TR_WG_ROWS - 1) / TR_WG_ROWS * TR_WG_ROWS;
+      // (M is an upper bound when the row count lives on the device: ragged batches fill about a third of it)
+      int64_t chunk = (M / (148 * (Mdev ? 8 : 4)) + TR_WG_ROWS - 1) / TR_WG_ROWS * TR_WG_ROWS;
       if (chunk < TR_WG_ROWS) chunk = TR_WG_ROWS;
       if (chunk > TR_WG_CHUNK) chunk = TR_WG_CHUNK;
       if (rows_tile > chunk) rows_tile = (int)chunk;
@@ -764,7 +851,7 @@ static int wgrad(const float* X, int ldx, const float* dY, int ldy, float* dW, i
       if (rc) return rc;
       tr_wgrad_kernel<<<(unsigned)((M + chunk - 1) / chunk), 256, smem, st>>>(
           X + k0, ldx, dY + o0, ldy, dW + (int64_t)k0 * ldw + o0, ldw, (db && k0 == 0) ? db + o0 : nullptr, M, kt, no, (int)chunk,
-          rows_tile);
+          rows_tile, Mdev);
       count_launch();
       LAUNCH_CHECK();
     }
@@ -777,14 +864,15 @@ struct Lin { int64_t woff, boff; int in, out, ld; };
 
 // forward of an MLP (layers.py:135-153) over M rows; hidden activations are saved in H[0 .. n-2]; returns through `out`
 static int mlp_fwd(const float* blob, const Lin* lin, int n, const float* X, int ldx, float* const* H, float* out, int ldo, int64_t M,
-                   cudaStream_t st) {
+                   cudaStream_t st, const int* Mdev = nullptr) {
   const float* cur = X;
   int ld = ldx;
   for (int i = 0; i < n; ++i) {
     const bool last = i == n - 1;
     float* dst = last ? out : H[i];
     const int ldd = last ? ldo : lin[i].out;
-    int rc = linear(cur, ld, blob + lin[i].woff, lin[i].ld, blob + lin[i].boff, dst, ldd, M, lin[i].in, lin[i].out, 0, last ? 0 : 1, 0, st);
+    int rc = linear(cur, ld, blob + lin[i].woff, lin[i].ld, blob + lin[i].boff, dst, ldd, M, lin[i].in, lin[i].out, 0, last ? 0 : 1, 0, st,
+                    Mdev);
     if (rc) return rc;
     cur = dst;
     ld = ldd;
@@ -795,22 +883,22 @@ static int mlp_fwd(const float* blob, const Lin* lin, int n, const float* X, int
 // reverse sweep of an MLP: g = gradient of the output rows [M][out_last] (destroyed); dX (optional) = gradient of the input rows;
 // sa / sb = two scratch row buffers of at least max width
 static int mlp_bwd(const float* blob, float* gblob, const Lin* lin, int n, const float* X, int ldx, float* const* H, float* g, int64_t M,
-                   float* dX, int lddx, float* sa, float* sb, cudaStream_t st) {
+                   float* dX, int lddx, float* sa, float* sb, cudaStream_t st, const int* Mdev = nullptr) {
   float* gcur = g;
   for (int i = n - 1; i >= 0; --i) {
     if (i < n - 1) {
-      tr_elu_bwd_kernel<<<egrid(M * lin[i].out), 256, 0, st>>>(gcur, H[i], M * lin[i].out);
+      tr_elu_bwd_kernel<<<egrid(M * lin[i].out), 256, 0, st>>>(gcur, H[i], M * lin[i].out, lin[i].out, Mdev);
       count_launch();
       LAUNCH_CHECK();
     }
     const float* Xi = i == 0 ? X : H[i - 1];
     const int ldi = i == 0 ? ldx : lin[i - 1].out;
-    int rc = wgrad(Xi, ldi, gcur, lin[i].out, gblob + lin[i].woff, lin[i].ld, gblob + lin[i].boff, M, lin[i].in, lin[i].out, st);
+    int rc = wgrad(Xi, ldi, gcur, lin[i].out, gblob + lin[i].woff, lin[i].ld, gblob + lin[i].boff, M, lin[i].in, lin[i].out, st, Mdev);
     if (rc) return rc;
     if (i > 0 || dX) {
       float* dst = i == 0 ? dX : (gcur == sa ? sb : sa);
       const int ldd = i == 0 ? lddx : lin[i].in;
-      rc = linear(gcur, lin[i].out, blob + lin[i].woff, lin[i].ld, nullptr, dst, ldd, M, lin[i].out, lin[i].in, 1, 0, 0, st);
+      rc = linear(gcur, lin[i].out, blob + lin[i].woff, lin[i].ld, nullptr, dst, ldd, M, lin[i].out, lin[i].in, 1, 0, 0, st, Mdev);
       if (rc) return rc;
       gcur = dst;
     }
@@ -941,6 +1029,8 @@ struct TrainCtx {
   const float *px, *padj, *flags;   // perturbed inputs, node flags
   int B;
   cudaStream_t st;
+  const int *pb, *pij, *mdev;       // compact pixel rows: graph / (i, j) of a row, device-side row count
+  int64_t Rmax;                     // upper bound of the row count: B N (N - 1) / 2
 };
 
 #define KCHECK()      \
@@ -952,9 +1042,11 @@ struct TrainCtx {
 // ---- AttentionLayer networks (ScoreNetworkA, ScoreNetworkX_GMH): forward with saved activations -> net output
 static int attn_forward(const NetPlan& p, const float* blob, NetBufs& nb, const TrainCtx& t, float* net_out) {
   const int B = t.B, N = p.N, F = p.F;
-  const int64_t R = (int64_t)B * N * N, Rn = (int64_t)B * N;
+  const int64_t R = t.Rmax, Rn = (int64_t)B * N;
   const bool isA = p.type == GDSS_NET_A;
   cudaStream_t st = t.st;
+  // entries no pixel row writes (padded nodes, the diagonal of the layer outputs) must read as zero
+  if (cudaMemsetAsync(nb.S, 0, sizeof(float) * (size_t)B * nb.s_bs, st) != cudaSuccess) return (int)cudaGetLastError();
   tr_pow_kernel<<<ggrid(N * N, B), 256, 0, st>>>(t.padj, nb.S, nb.s_bs, N, p.c_init);
   KCHECK();
   if (!isA) {
@@ -985,13 +1077,15 @@ static int attn_forward(const NetPlan& p, const float* blob, NetBufs& nb, const 
       tr_maps_fwd_kernel<<<dim3(L.c_in, B), 256, maps_smem(N, L.attn), st>>>(b.Y, b.M, B, L.c_in, N, L.qkvw, L.attn, p.heads,
                                                                              1.0f / sqrtf((float)L.nhid));
       KCHECK();
-      tr_edge_rows_kernel<<<ggrid((int64_t)N * N * 2 * L.c_in, B), 256, 0, st>>>(b.M, nb.S + (int64_t)cur * N * N, nb.s_bs, b.ein, L.c_in, N);
+      tr_edge_rows_kernel<<<egrid(R * 2 * L.c_in), 256, 0, st>>>(b.M, nb.S + (int64_t)cur * N * N, nb.s_bs, b.ein, L.c_in, N, t.pb, t.pij,
+                                                                 t.mdev);
       KCHECK();
       Lin lin[GDSS_MAX_LIN];
       edge_lins(L, lin);
-      rc = mlp_fwd(blob, lin, L.nlin, b.ein, 2 * L.c_in, b.H, nb.ga, L.c_out, R, st);
+      rc = mlp_fwd(blob, lin, L.nlin, b.ein, 2 * L.c_in, b.H, nb.ga, L.c_out, R, st, t.mdev);
       if (rc) return rc;
-      tr_edge_out_kernel<<<ggrid((int64_t)N * N * L.c_out, B), 256, 0, st>>>(nb.ga, t.flags, nb.S + (int64_t)(cur + L.c_in) * N * N, nb.s_bs, L.c_out, N);
+      tr_edge_out_kernel<<<egrid(R * L.c_out), 256, 0, st>>>(nb.ga, t.flags, nb.S + (int64_t)(cur + L.c_in) * N * N, nb.s_bs, L.c_out, N,
+                                                             t.pb, t.pij, t.mdev);
       KCHECK();
     }
     if (need_node) {
@@ -1017,11 +1111,12 @@ static int attn_forward(const NetPlan& p, const float* blob, NetBufs& nb, const 
   Lin fl[3];
   final_lins(p, fl);
   if (isA) {
-    tr_stack_rows_kernel<<<ggrid((int64_t)N * N * p.fdim, B), 256, 0, st>>>(nb.S, nb.s_bs, nb.cat, p.fdim, N);
+    tr_stack_rows_kernel<<<egrid(R * p.fdim), 256, 0, st>>>(nb.S, nb.s_bs, nb.cat, p.fdim, N, t.pb, t.pij, t.mdev);
     KCHECK();
-    int rc = mlp_fwd(blob, fl, 3, nb.cat, p.fdim, nb.Hf, nb.out, 1, R, st);
+    int rc = mlp_fwd(blob, fl, 3, nb.cat, p.fdim, nb.Hf, nb.out, 1, R, st, t.mdev);
     if (rc) return rc;
-    tr_adj_mask_kernel<<<ggrid(N * N, B), 256, 0, st>>>(nb.out, t.flags, net_out, N);
+    if (cudaMemsetAsync(net_out, 0, sizeof(float) * (size_t)B * N * N, st) != cudaSuccess) return (int)cudaGetLastError();
+    tr_adj_out_kernel<<<egrid(R), 256, 0, st>>>(nb.out, t.flags, net_out, N, t.pb, t.pij, t.mdev);
     KCHECK();
   } else {
     int rc = mlp_fwd(blob, fl, 3, nb.xcat, p.fdim, nb.Hf, nb.out, p.fout, Rn, st);
@@ -1035,7 +1130,7 @@ static int attn_forward(const NetPlan& p, const float* blob, NetBufs& nb, const 
 // ---- reverse sweep: dnet = d loss / d (network output) -> parameter gradients in blob layout (gblob, accumulated)
 static int attn_backward(const NetPlan& p, const float* blob, float* gblob, NetBufs& nb, const TrainCtx& t, const float* dnet) {
   const int B = t.B, N = p.N, F = p.F;
-  const int64_t R = (int64_t)B * N * N, Rn = (int64_t)B * N;
+  const int64_t R = t.Rmax, Rn = (int64_t)B * N;
   const bool isA = p.type == GDSS_NET_A;
   cudaStream_t st = t.st;
   cudaError_t e;
@@ -1045,11 +1140,13 @@ static int attn_backward(const NetPlan& p, const float* blob, float* gblob, NetB
   if (isA) {
     // ScoreNetwork_A.py:143-148: zero diagonal, mask_adjs; then the final MLP over the pixel rows; its input gradient IS the
     // gradient of every plane of the stack
-    tr_adj_mask_kernel<<<ggrid(N * N, B), 256, 0, st>>>(dnet, t.flags, nb.ga, N);
+    tr_adj_gin_kernel<<<egrid(R), 256, 0, st>>>(dnet, t.flags, nb.ga, N, t.pb, t.pij, t.mdev);
     KCHECK();
-    rc = mlp_bwd(blob, gblob, fl, 3, nb.cat, p.fdim, nb.Hf, nb.ga, R, nb.gc, p.fdim, nb.ga, nb.gb, st);
+    rc = mlp_bwd(blob, gblob, fl, 3, nb.cat, p.fdim, nb.Hf, nb.ga, R, nb.gc, p.fdim, nb.ga, nb.gb, st, t.mdev);
     if (rc) return rc;
-    tr_stack_rows_bwd_kernel<<<ggrid((int64_t)N * N * p.fdim, B), 256, 0, st>>>(nb.gc, nb.dS, nb.s_bs, p.fdim, N);
+    e = cudaMemsetAsync(nb.dS, 0, sizeof(float) * (size_t)B * nb.s_bs, st);
+    if (e != cudaSuccess) return (int)e;
+    tr_stack_rows_bwd_kernel<<<egrid(R * p.fdim), 256, 0, st>>>(nb.gc, nb.dS, nb.s_bs, p.fdim, N, t.pb, t.pij, t.mdev);
     KCHECK();
   } else {
     tr_x_mask_kernel<<<ggrid(N * F, B), 256, 0, st>>>(dnet, t.flags, nb.ga, N, F);
@@ -1088,13 +1185,17 @@ static int attn_backward(const NetPlan& p, const float* blob, float* gblob, NetB
     }
     if (need_edge) {
       // attention.py:109-114 backwards: mask_adjs, s + s^T, the per-edge MLP, split into the maps' and the planes' gradient
-      tr_edge_gin_kernel<<<ggrid((int64_t)N * N * L.c_out, B), 256, 0, st>>>(nb.dS + (int64_t)(cur + L.c_in) * N * N, nb.s_bs, t.flags, nb.ga, L.c_out, N);
+      tr_edge_gin_kernel<<<egrid(R * L.c_out), 256, 0, st>>>(nb.dS + (int64_t)(cur + L.c_in) * N * N, nb.s_bs, t.flags, nb.ga, L.c_out, N,
+                                                             t.pb, t.pij, t.mdev);
       KCHECK();
       Lin lin[GDSS_MAX_LIN];
       edge_lins(L, lin);
-      rc = mlp_bwd(blob, gblob, lin, L.nlin, b.ein, 2 * L.c_in, b.H, nb.ga, R, nb.gc, 2 * L.c_in, nb.ga, nb.gb, st);
+      rc = mlp_bwd(blob, gblob, lin, L.nlin, b.ein, 2 * L.c_in, b.H, nb.ga, R, nb.gc, 2 * L.c_in, nb.ga, nb.gb, st, t.mdev);
       if (rc) return rc;
-      tr_edge_dein_kernel<<<ggrid((int64_t)N * N * 2 * L.c_in, B), 256, 0, st>>>(nb.gc, nb.dM, nb.dS + (int64_t)cur * N * N, nb.s_bs, L.c_in, N);
+      e = cudaMemsetAsync(nb.dM, 0, sizeof(float) * (size_t)B * L.c_in * N * N, st);
+      if (e != cudaSuccess) return (int)e;
+      tr_edge_dein_kernel<<<egrid(R * 2 * L.c_in), 256, 0, st>>>(nb.gc, nb.dM, nb.dS + (int64_t)cur * N * N, nb.s_bs, L.c_in, N, t.pb, t.pij,
+                                                                 t.mdev);
       KCHECK();
       rc = set_smem_attr((const void*)tr_maps_bwd_kernel, maps_smem(N, L.attn));
       if (rc) return rc;
@@ -1204,6 +1305,7 @@ static int gcn_backward(const NetPlan& p, const float* blob, float* gblob, NetBu
 struct TrainLayout {
   NetBufs nx, na;
   float *flags, *px, *padj, *zx, *zadj, *netx, *neta, *dnetx, *dneta, *lossb;
+  int *neff, *poff, *pb, *pij;      // compact pixel rows (tr_pix_scan_kernel / tr_pix_map_kernel); poff[B] = row count
   int64_t total;
 };
 
@@ -1220,6 +1322,10 @@ static void layout_train(const gdss_ctx* ctx, int B, char* base, TrainLayout* t)
   t->neta = ar.take(B * N * N);
   t->dneta = ar.take(B * N * N);
   t->lossb = ar.take(2 * (int64_t)B);
+  t->neff = reinterpret_cast<int*>(ar.take(B));
+  t->poff = reinterpret_cast<int*>(ar.take(B + 1));
+  t->pb = reinterpret_cast<int*>(ar.take(B * N * (N - 1) / 2));
+  t->pij = reinterpret_cast<int*>(ar.take(B * N * (N - 1) / 2));
   if (ctx->has_x) plan_bufs(ctx->px, B, ar, &t->nx);
   if (ctx->has_a) plan_bufs(ctx->pa, B, ar, &t->na);
   t->total = ar.cur;
@@ -1260,7 +1366,14 @@ extern "C" int gdss_dsm_loss_backward(gdss_ctx* ctx, const float* x, const float
   // losses.py:47-58: node flags of the data, masked noise, perturbed inputs
   int rc = launch_dsm_perturb(x, adj, coef, raw_x, raw_adj, t.flags, t.px, t.padj, t.zx, t.zadj, B, N, F, st);
   if (rc) return rc;
-  TrainCtx tc{t.px, t.padj, t.flags, B, st};
+  if ((int64_t)B * N * (N - 1) / 2 >= ((int64_t)1 << 31) / 128) return GDSS_E_UNSUPPORTED;     // 32-bit row offsets
+  tr_pix_scan_kernel<<<1, 1024, 0, st>>>(t.flags, B, N, t.neff, t.poff);
+  count_launch();
+  LAUNCH_CHECK();
+  tr_pix_map_kernel<<<ggrid(N * N, B), 256, 0, st>>>(t.neff, t.poff, t.pb, t.pij);
+  count_launch();
+  LAUNCH_CHECK();
+  TrainCtx tc{t.px, t.padj, t.flags, B, st, t.pb, t.pij, t.poff + B, (int64_t)B * N * (N - 1) / 2};
   // ---- node-feature network: forward, loss (losses.py:60-67), reverse sweep
   if (ctx->px.type == GDSS_NET_X) rc = gcn_forward(ctx->px, ctx->blob_x, t.nx, tc, t.netx);
   else rc = attn_forward(ctx->px, ctx->blob_x, t.nx, tc, t.netx);
