@@ -113,8 +113,11 @@ __global__ void __launch_bounds__(256) tr_linear_kernel(const float* __restrict_
 // The bias gradient rides on the items of the first input group (k4 = 0).
 __global__ void __launch_bounds__(256) tr_wgrad_kernel(const float* __restrict__ X, int ldx, const float* __restrict__ dY, int ldy,
                                                        float* __restrict__ dW, int ldw, float* __restrict__ db, int64_t M, int K,
-                                                       int NO, int chunk, int rows_tile, const int* __restrict__ Mdev) {
+                                                       int NO, int chunk, int rows_tile, const int* __restrict__ Mdev,
+                                                       int y_cs, int64_t w_cs) {
   extern __shared__ __align__(16) float sm[];
+  dY += (int64_t)blockIdx.y * y_cs;    // blockIdx.y = slice: its NO columns of the dY rows start at column y * y_cs,
+  dW += (int64_t)blockIdx.y * w_cs;    //                     its weight block at dW + y * w_cs
   if (Mdev) M = *Mdev;
   if ((int64_t)blockIdx.x * chunk >= M) return;
   const int NOP = (NO + 3) & ~3, KP = (K + 3) & ~3;
@@ -234,6 +237,43 @@ __global__ void __launch_bounds__(256) tr_wgrad_kernel(const float* __restrict__
   }
 }
 
+// Data gradient of the C per-channel convolutions of a layer at once: dx[m][f] = sum_c sum_o dXW[m][c][o] W_c[f][o]
+// (layers.py:76 backwards, summed over the channels that share x).  Thread = (row, group of 4 input features); the weights
+// are staged transposed in shared memory, Wt[(c, o)][fin_p].
+__global__ void __launch_bounds__(256) tr_gcn_dx_kernel(const float* __restrict__ dXW, const float* __restrict__ W, int64_t w_cs, int ldw,
+                                                        float* __restrict__ dx, int lddx, int64_t M, int C, int OW, int fin) {
+  extern __shared__ __align__(16) float sm[];
+  const int finp = (fin + 3) & ~3, fg = finp >> 2, K = C * OW;
+  float* Wt = sm;                  // [K][finp]
+  const int tid = threadIdx.x;
+  for (int idx = tid; idx < K * finp; idx += 256) {
+    const int k = idx / finp, f = idx - k * finp;
+    const int c = k / OW, o = k - c * OW;
+    Wt[idx] = f < fin ? W[(int64_t)c * w_cs + (int64_t)f * ldw + o] : 0.f;
+  }
+  __syncthreads();
+  const int rows = 256 / fg;
+  const int r = tid / fg, g = tid - r * fg;
+  const int64_t m = (int64_t)blockIdx.x * rows + r;
+  if (r >= rows || m >= M) return;
+  const float* xr = dXW + m * K;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int k = 0; k < K; k += 4) {               // K = C * OW is a multiple of 4 (host-checked)
+    const float4 x = *reinterpret_cast<const float4*>(xr + k);
+    const float xv[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float4 w = *reinterpret_cast<const float4*>(Wt + (k + q) * finp + 4 * g);
+      acc.x = fmaf(xv[q], w.x, acc.x); acc.y = fmaf(xv[q], w.y, acc.y);
+      acc.z = fmaf(xv[q], w.z, acc.z); acc.w = fmaf(xv[q], w.w, acc.w);
+    }
+  }
+  const float av[4] = {acc.x, acc.y, acc.z, acc.w};
+#pragma unroll
+  for (int q = 0; q < 4; ++q)
+    if (4 * g + q < fin) dx[m * lddx + 4 * g + q] = av[q];
+}
+
 // g *= ELU'(pre) with the saved post-activation h: ELU'(pre) = 1 (pre > 0) or exp(pre) = h + 1   (layers.py:150)
 __global__ void tr_elu_bwd_kernel(float* __restrict__ g, const float* __restrict__ h, int64_t n, int width, const int* __restrict__ Mdev) {
   if (Mdev) n = (int64_t)*Mdev * width;
@@ -248,6 +288,8 @@ __global__ void tr_elu_bwd_kernel(float* __restrict__ g, const float* __restrict
 //   A~ = plane with unit diagonal, deg = rowsum A~, d = clamp(deg, 1)^-1/2, XW = x W_c, Y = d_i sum_j A~_ij d_j XW_j + b_c
 // per-channel row tensors are laid out [c][b * N + i][OW]
 // ---------------------------------------------------------------------------------------
+// Padded nodes (i >= n = neff[b]) have all-zero off-diagonal plane entries (mask_adjs) and a unit diagonal, so their rows are
+// deg = 1, d = 1, Y_i = XW_i + b: every O(N^2) loop runs over the n x n block only and the padded rows are filled in directly.
 struct GcnT {
   const float* planes; int64_t p_bs;       // plane c of graph b = planes + b * p_bs + c * N * N
   const float* x; int ldx; int fin;        // node features [B * N][ldx]
@@ -256,36 +298,50 @@ struct GcnT {
   float* degraw; float* d;                 // [C][B * N]
   float* XW; float* Y;                     // [C][B * N][OW]
   int B, N, OW;
+  const int* neff;
 };
 
 __global__ void __launch_bounds__(256) tr_gcn_fwd_kernel(GcnT a) {
   extern __shared__ __align__(16) float sm[];
-  const int c = blockIdx.x, b = blockIdx.y, N = a.N, OW = a.OW, NS = N + 1;
+  const int c = blockIdx.x, b = blockIdx.y, N = a.N, OW = a.OW, NS = N + 1, n = a.neff[b], fin = a.fin;
   float* At = sm;                 // [N][N + 1]
   float* dv = At + N * NS;        // [N]
   float* xw = dv + N;             // [N][OW]
+  float* xs = xw + N * OW;        // [N][fin]
+  float* Ws = xs + N * fin;       // [fin][OW]
   const int tid = threadIdx.x;
   const float* P = a.planes + b * a.p_bs + (int64_t)c * N * N;
-  for (int idx = tid; idx < N * N; idx += 256) {
-    const int i = idx / N, j = idx - i * N;
-    At[i * NS + j] = i == j ? 1.f : P[idx];
+  for (int idx = tid; idx < n * n; idx += 256) {
+    const int i = idx / n, j = idx - i * n;
+    At[i * NS + j] = i == j ? 1.f : P[i * N + j];
+  }
+  const float* X = a.x + (int64_t)b * N * a.ldx;
+  const float* W = a.W + (int64_t)c * a.w_cs;
+  for (int idx = tid; idx < N * fin; idx += 256) {
+    const int j = idx / fin, f = idx - j * fin;
+    xs[idx] = X[j * a.ldx + f];
+  }
+  for (int idx = tid; idx < fin * OW; idx += 256) {
+    const int f = idx / OW, o = idx - f * OW;
+    Ws[idx] = W[(int64_t)f * a.ldw + o];
   }
   __syncthreads();
   const int64_t r0 = ((int64_t)c * a.B + b) * N;
   for (int i = tid; i < N; i += 256) {
-    float s = 0.f;
-    for (int j = 0; j < N; ++j) s += At[i * NS + j];
+    float s = 1.f;
+    if (i < n) {
+      s = 0.f;
+      for (int j = 0; j < n; ++j) s += At[i * NS + j];
+    }
     const float dd = 1.0f / sqrtf(fmaxf(s, 1.0f));
     dv[i] = dd;
     a.degraw[r0 + i] = s;
     a.d[r0 + i] = dd;
   }
-  const float* X = a.x + (int64_t)b * N * a.ldx;
-  const float* W = a.W + (int64_t)c * a.w_cs;
   for (int idx = tid; idx < N * OW; idx += 256) {
     const int j = idx / OW, o = idx - j * OW;
     float s = 0.f;
-    for (int f = 0; f < a.fin; ++f) s = fmaf(X[j * a.ldx + f], W[(int64_t)f * a.ldw + o], s);
+    for (int f = 0; f < fin; ++f) s = fmaf(xs[j * fin + f], Ws[f * OW + o], s);
     xw[idx] = s;
     a.XW[(r0 + j) * OW + o] = s;
   }
@@ -293,9 +349,15 @@ __global__ void __launch_bounds__(256) tr_gcn_fwd_kernel(GcnT a) {
   const float* bias = a.bias + (int64_t)c * a.b_cs;
   for (int idx = tid; idx < N * OW; idx += 256) {
     const int i = idx / OW, o = idx - i * OW;
-    float s = 0.f;
-    for (int j = 0; j < N; ++j) s = fmaf(At[i * NS + j] * dv[j], xw[j * OW + o], s);
-    a.Y[(r0 + i) * OW + o] = dv[i] * s + bias[o];
+    float s;
+    if (i < n) {
+      s = 0.f;
+      for (int j = 0; j < n; ++j) s = fmaf(At[i * NS + j] * dv[j], xw[j * OW + o], s);
+      s *= dv[i];
+    } else {
+      s = xw[idx];
+    }
+    a.Y[(r0 + i) * OW + o] = s + bias[o];
   }
 }
 
@@ -303,15 +365,18 @@ struct GcnBT {
   const float* planes; int64_t p_bs;
   const float* degraw; const float* d;     // saved by the forward
   const float* XW; const float* dY;        // [C][B * N][OW]
-  float* dXW;                              // out: A^T dY = A^ dY  [C][B * N][OW]
+  float* dXW;                              // out: A^T dY = A^ dY  [B * N][C][OW]  (the channels of a node side by side)
   float* dplanes; int64_t dp_bs;           // in/out (+=): gradient of the adjacency channels, or null
   float* dbias; int b_cs;                  // atomics
   int B, N, OW;
+  const int* neff;
 };
 
+// (the planes' gradient is produced for the n x n block only: entries of padded nodes are multiplied by their zero mask
+//  downstream -- no pixel row reads them)
 __global__ void __launch_bounds__(256) tr_gcn_bwd_kernel(GcnBT a) {
   extern __shared__ __align__(16) float sm[];
-  const int c = blockIdx.x, b = blockIdx.y, N = a.N, OW = a.OW, NS = N + 1;
+  const int c = blockIdx.x, b = blockIdx.y, N = a.N, OW = a.OW, NS = N + 1, n = a.neff[b];
   const int OS = OW | 1;          // odd row stride of the shared copies: the d A^ products walk them by rows (no bank conflicts)
   float* At = sm;                 // [N][N + 1]
   float* G = At + N * NS;         // [N][N + 1]   dA^_ij = sum_o dY_io XW_jo
@@ -323,9 +388,9 @@ __global__ void __launch_bounds__(256) tr_gcn_bwd_kernel(GcnBT a) {
   const int tid = threadIdx.x;
   const float* P = a.planes + b * a.p_bs + (int64_t)c * N * N;
   const int64_t r0 = ((int64_t)c * a.B + b) * N;
-  for (int idx = tid; idx < N * N; idx += 256) {
-    const int i = idx / N, j = idx - i * N;
-    At[i * NS + j] = i == j ? 1.f : P[idx];
+  for (int idx = tid; idx < n * n; idx += 256) {
+    const int i = idx / n, j = idx - i * n;
+    At[i * NS + j] = i == j ? 1.f : P[i * N + j];
   }
   for (int i = tid; i < N; i += 256) {
     dv[i] = a.d[r0 + i];
@@ -340,9 +405,15 @@ __global__ void __launch_bounds__(256) tr_gcn_bwd_kernel(GcnBT a) {
   // d(xW)_j = sum_i A^_ij dY_i
   for (int idx = tid; idx < N * OW; idx += 256) {
     const int j = idx / OW, o = idx - j * OW;
-    float s = 0.f;
-    for (int i = 0; i < N; ++i) s = fmaf(At[i * NS + j] * dv[i], dy[i * OS + o], s);
-    a.dXW[(r0 + j) * OW + o] = dv[j] * s;
+    float s;
+    if (j < n) {
+      s = 0.f;
+      for (int i = 0; i < n; ++i) s = fmaf(At[i * NS + j] * dv[i], dy[i * OS + o], s);
+      s *= dv[j];
+    } else {
+      s = dy[j * OS + o];
+    }
+    a.dXW[(((int64_t)b * N + j) * gridDim.x + c) * OW + o] = s;
   }
   if (a.dbias) {
     for (int o = tid; o < OW; o += 256) {
@@ -352,48 +423,49 @@ __global__ void __launch_bounds__(256) tr_gcn_bwd_kernel(GcnBT a) {
     }
   }
   if (!a.dplanes) return;
-  for (int idx = tid; idx < N * N; idx += 256) {
-    const int i = idx / N, j = idx - i * N;
+  for (int idx = tid; idx < n * n; idx += 256) {
+    const int i = idx / n, j = idx - i * n;
     float s = 0.f;
     for (int o = 0; o < OW; ++o) s = fmaf(dy[i * OS + o], xw[j * OS + o], s);
     G[i * NS + j] = s;
   }
   __syncthreads();
   // d as the row factor + as the column factor of A^_ij = d_i A~_ij d_j; deg_i = sum_j A~_ij; d = clamp(deg, 1)^-1/2
-  for (int k = tid; k < N; k += 256) {
+  for (int k = tid; k < n; k += 256) {
     float s = 0.f;
-    for (int j = 0; j < N; ++j) s = fmaf(G[k * NS + j] * At[k * NS + j], dv[j], s);
-    for (int i = 0; i < N; ++i) s = fmaf(G[i * NS + k] * At[i * NS + k], dv[i], s);
+    for (int j = 0; j < n; ++j) s = fmaf(G[k * NS + j] * At[k * NS + j], dv[j], s);
+    for (int i = 0; i < n; ++i) s = fmaf(G[i * NS + k] * At[i * NS + k], dv[i], s);
     const float d3 = dv[k] * dv[k] * dv[k];
     dd[k] = dg[k] >= 1.f ? -0.5f * d3 * s : 0.f;
   }
   __syncthreads();
   float* dP = a.dplanes + b * a.dp_bs + (int64_t)c * N * N;
-  for (int idx = tid; idx < N * N; idx += 256) {
-    const int i = idx / N, j = idx - i * N;
+  for (int idx = tid; idx < n * n; idx += 256) {
+    const int i = idx / n, j = idx - i * n;
     if (i == j) continue;                                  // the diagonal of A~ is the constant 1
-    dP[idx] += dv[i] * G[i * NS + j] * dv[j] + dd[i];
+    dP[i * N + j] += dv[i] * G[i * NS + j] * dv[j] + dd[i];
   }
 }
 
 // ---------------------------------------------------------------------------------------
-// attention maps (attention.py:35-49): T = mean_h tanh(Q_h K_h^T / sqrt(out_dim)), M = (T + T^T) / 2
+// attention maps (attention.py:35-49): T = mean_h tanh(Q_h K_h^T / sqrt(out_dim)), M = (T + T^T) / 2; n x n block only (the
+// pixel rows read nothing else)
 // ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) tr_maps_fwd_kernel(const float* __restrict__ Y, float* __restrict__ M, int B, int C, int N,
-                                                          int OW, int attn, int heads, float scale) {
+                                                          int OW, int attn, int heads, float scale, const int* __restrict__ neff) {
   extern __shared__ __align__(16) float sm[];
-  const int c = blockIdx.x, b = blockIdx.y, NS = N + 1, QS = 2 * attn + 1;     // odd row strides: no bank conflicts
+  const int c = blockIdx.x, b = blockIdx.y, NS = N + 1, QS = 2 * attn + 1, n = neff[b];     // odd row strides: no bank conflicts
   float* qk = sm;                  // [N][QS]
   float* T = qk + N * QS;          // [N][N + 1]
   const int tid = threadIdx.x, hd = attn / heads;
   const int64_t r0 = ((int64_t)c * B + b) * N;
-  for (int idx = tid; idx < N * 2 * attn; idx += 256) {
+  for (int idx = tid; idx < n * 2 * attn; idx += 256) {
     const int i = idx / (2 * attn), o = idx - i * 2 * attn;
     qk[i * QS + o] = Y[(r0 + i) * OW + o];
   }
   __syncthreads();
-  for (int idx = tid; idx < N * N; idx += 256) {
-    const int i = idx / N, j = idx - i * N;
+  for (int idx = tid; idx < n * n; idx += 256) {
+    const int i = idx / n, j = idx - i * n;
     const float* q = qk + i * QS;
     const float* k = qk + j * QS + attn;
     float t = 0.f;
@@ -406,57 +478,64 @@ __global__ void __launch_bounds__(256) tr_maps_fwd_kernel(const float* __restric
   }
   __syncthreads();
   float* Mo = M + ((int64_t)b * C + c) * N * N;
-  for (int idx = tid; idx < N * N; idx += 256) {
-    const int i = idx / N, j = idx - i * N;
-    Mo[idx] = 0.5f * (T[i * NS + j] + T[j * NS + i]);
+  for (int idx = tid; idx < n * n; idx += 256) {
+    const int i = idx / n, j = idx - i * n;
+    Mo[i * N + j] = 0.5f * (T[i * NS + j] + T[j * NS + i]);
   }
 }
 
 // dT = (dM + dM^T) / 2; dS_h = dT / H * (1 - tanh^2) * scale; dQ_h = dS_h K_h; dK_h = dS_h^T Q_h  -> dY columns [0, 2 attn)
+// Two phases: dS_h[i][j] for every (head, i, j) of the n x n block into shared memory (one tanh per entry), then one thread per
+// (Q | K, node, column) sums over the other node index.  Rows of padded nodes get zeros.
 __global__ void __launch_bounds__(256) tr_maps_bwd_kernel(const float* __restrict__ Y, const float* __restrict__ dM,
                                                           float* __restrict__ dY, int B, int C, int N, int OW, int attn, int heads,
-                                                          float scale) {
+                                                          float scale, const int* __restrict__ neff, int hg) {
   extern __shared__ __align__(16) float sm[];
-  const int c = blockIdx.x, b = blockIdx.y, NS = N + 1, QS = 2 * attn + 1;     // odd row strides: no bank conflicts
+  const int c = blockIdx.x, b = blockIdx.y, NS = N + 1, QS = 2 * attn + 1, n = neff[b];
   float* qk = sm;                  // [N][QS]
-  float* dT = qk + N * QS;         // [N][N + 1]
+  float* dS = qk + N * QS;         // [hg][N][N + 1]
   const int tid = threadIdx.x, hd = attn / heads;
   const int64_t r0 = ((int64_t)c * B + b) * N;
-  for (int idx = tid; idx < N * 2 * attn; idx += 256) {
+  for (int idx = tid; idx < n * 2 * attn; idx += 256) {
     const int i = idx / (2 * attn), o = idx - i * 2 * attn;
     qk[i * QS + o] = Y[(r0 + i) * OW + o];
   }
-  const float* Mi = dM + ((int64_t)b * C + c) * N * N;
-  for (int idx = tid; idx < N * N; idx += 256) {
-    const int i = idx / N, j = idx - i * N;
-    dT[i * NS + j] = 0.5f * (Mi[idx] + Mi[j * N + i]);
-  }
   __syncthreads();
+  const float* Mi = dM + ((int64_t)b * C + c) * N * N;
   const float hs = scale / (float)heads;
-  // items: (node, head, q | k)
-  for (int item = tid; item < N * heads * 2; item += 256) {
-    const int which = item / (N * heads), rem = item - which * N * heads;
-    const int i = rem / heads, h = rem - i * heads;
-    float acc[16];                  // head width <= 16 (attn <= 64)
-#pragma unroll
-    for (int e = 0; e < 16; ++e) acc[e] = 0.f;
-    for (int j = 0; j < N; ++j) {
-      // which = 0: dQ_i += dS_ij K_j ;  which = 1: dK_i += dS_ji Q_j
-      const float* q = which == 0 ? qk + i * QS + h * hd : qk + j * QS + h * hd;
-      const float* k = which == 0 ? qk + j * QS + attn + h * hd : qk + i * QS + attn + h * hd;
-      float s = 0.f;
-      for (int e = 0; e < hd; ++e) s = fmaf(q[e], k[e], s);
-      const float th = tanhf(s * scale);
-      const float ds = (which == 0 ? dT[i * NS + j] : dT[j * NS + i]) * hs * (1.f - th * th);
-      const float* other = which == 0 ? k : q;
-#pragma unroll
-      for (int e = 0; e < 16; ++e)
-        if (e < hd) acc[e] = fmaf(ds, other[e], acc[e]);
+  // hg heads per pass (all of them when their dS blocks fit shared memory, else one at a time)
+  for (int h0 = 0; h0 < heads; h0 += hg) {
+    if (h0) __syncthreads();
+    for (int idx = tid; idx < n * n; idx += 256) {
+      const int i = idx / n, j = idx - i * n;
+      const float dT = 0.5f * (Mi[i * N + j] + Mi[j * N + i]) * hs;
+      const float* q = qk + i * QS;
+      const float* k = qk + j * QS + attn;
+      for (int h = h0; h < h0 + hg; ++h) {
+        float s = 0.f;
+        for (int e = 0; e < hd; ++e) s = fmaf(q[h * hd + e], k[h * hd + e], s);
+        const float th = tanhf(s * scale);
+        dS[((h - h0) * N + i) * NS + j] = dT * (1.f - th * th);
+      }
     }
-    float* dst = dY + (r0 + i) * OW + which * attn + h * hd;
-#pragma unroll
-    for (int e = 0; e < 16; ++e)
-      if (e < hd) dst[e] = acc[e];
+    __syncthreads();
+    // items: (node i, column o of Q | K): dQ_i[o] = sum_j dS_h[i][j] K_j[o];  dK_i[o] = sum_j dS_h[j][i] Q_j[o]   (h = head of o)
+    for (int item = tid; item < N * 2 * attn; item += 256) {
+      const int i = item / (2 * attn), o = item - i * 2 * attn;
+      const int oo = o < attn ? o : o - attn, h = oo / hd;
+      if (h < h0 || h >= h0 + hg) continue;
+      float s = 0.f;
+      if (i < n) {
+        if (o < attn) {
+          const float* ds = dS + ((h - h0) * N + i) * NS;
+          for (int j = 0; j < n; ++j) s = fmaf(ds[j], qk[j * QS + attn + o], s);
+        } else {
+          const float* ds = dS + (h - h0) * N * NS + i;
+          for (int j = 0; j < n; ++j) s = fmaf(ds[j * NS], qk[j * QS + oo], s);
+        }
+      }
+      dY[(r0 + i) * OW + o] = s;
+    }
   }
 }
 
@@ -828,7 +907,7 @@ static int linear(const float* X, int ldx, const float* W, int ldw, const float*
 }
 
 static int wgrad(const float* X, int ldx, const float* dY, int ldy, float* dW, int ldw, float* db, int64_t M, int K, int NO,
-                 cudaStream_t st, const int* Mdev = nullptr) {
+                 cudaStream_t st, const int* Mdev = nullptr, int slices = 1, int y_cs = 0, int64_t w_cs = 0) {
   for (int k0 = 0; k0 < K; k0 += TR_K_TILE) {
     const int kt = K - k0 < TR_K_TILE ? K - k0 : TR_K_TILE;
     for (int o0 = 0; o0 < NO; o0 += TR_NO_TILE) {
@@ -841,7 +920,7 @@ static int wgrad(const float* X, int ldx, const float* dY, int ldy, float* dW, i
       if (rows_tile > 256) rows_tile = 256;
       // rows per CTA: about four CTAs per SM, whole tiles, at most TR_WG_CHUNK
       // (M is an upper bound when the row count lives on the device: ragged batches fill about a third of it)
-      int64_t chunk = (M / (148 * (Mdev ? 8 : 4)) + TR_WG_ROWS - 1) / TR_WG_ROWS * TR_WG_ROWS;
+      int64_t chunk = (M * slices / (148 * (Mdev ? 8 : 4)) + TR_WG_ROWS - 1) / TR_WG_ROWS * TR_WG_ROWS;
       if (chunk < TR_WG_ROWS) chunk = TR_WG_ROWS;
       if (chunk > TR_WG_CHUNK) chunk = TR_WG_CHUNK;
       if (rows_tile > chunk) rows_tile = (int)chunk;
@@ -849,9 +928,9 @@ static int wgrad(const float* X, int ldx, const float* dY, int ldy, float* dW, i
       if (smem < sizeof(float) * 256 * 20) smem = sizeof(float) * 256 * 20;      // the row groups' reduction buffer
       int rc = set_smem_attr((const void*)tr_wgrad_kernel, smem);
       if (rc) return rc;
-      tr_wgrad_kernel<<<(unsigned)((M + chunk - 1) / chunk), 256, smem, st>>>(
+      tr_wgrad_kernel<<<dim3((unsigned)((M + chunk - 1) / chunk), slices), 256, smem, st>>>(
           X + k0, ldx, dY + o0, ldy, dW + (int64_t)k0 * ldw + o0, ldw, (db && k0 == 0) ? db + o0 : nullptr, M, kt, no, (int)chunk,
-          rows_tile, Mdev);
+          rows_tile, Mdev, y_cs, w_cs);
       count_launch();
       LAUNCH_CHECK();
     }
@@ -906,9 +985,9 @@ static int mlp_bwd(const float* blob, float* gblob, const Lin* lin, int n, const
   return 0;
 }
 
-static size_t gcn_fwd_smem(int N, int OW) { return sizeof(float) * ((size_t)N * (N + 1) + N + (size_t)N * OW); }
+static size_t gcn_fwd_smem(int N, int OW, int fin) { return sizeof(float) * ((size_t)N * (N + 1) + N + (size_t)N * OW + (size_t)N * fin + (size_t)fin * OW); }
 static size_t gcn_bwd_smem(int N, int OW) { return sizeof(float) * (2 * (size_t)N * (N + 1) + 3 * N + 2 * (size_t)N * (OW | 1)); }
-static size_t maps_smem(int N, int attn) { return sizeof(float) * ((size_t)N * (2 * attn + 1) + (size_t)N * (N + 1)); }
+static size_t maps_smem(int N, int attn, int heads) { return sizeof(float) * ((size_t)N * (2 * attn + 1) + (size_t)heads * N * (N + 1)); }
 
 // everything one network needs for forward + backward; planned twice (sizes only, then with the arena)
 struct LayerBufs {
@@ -1029,6 +1108,7 @@ struct TrainCtx {
   const float *px, *padj, *flags;   // perturbed inputs, node flags
   int B;
   cudaStream_t st;
+  const int *neff;                  // 1 + index of the last flagged node, per graph
   const int *pb, *pij, *mdev;       // compact pixel rows: graph / (i, j) of a row, device-side row count
   int64_t Rmax;                     // upper bound of the row count: B N (N - 1) / 2
 };
@@ -1066,16 +1146,16 @@ static int attn_forward(const NetPlan& p, const float* blob, NetBufs& nb, const 
     g.W = blob + L.wqkv; g.w_cs = (int64_t)L.f_in_p * L.qkvw; g.ldw = L.qkvw;
     g.bias = blob + L.bqkv; g.b_cs = L.qkvw;
     g.degraw = b.degraw; g.d = b.d; g.XW = b.XW; g.Y = b.Y;
-    g.B = B; g.N = N; g.OW = L.qkvw;
-    int rc = set_smem_attr((const void*)tr_gcn_fwd_kernel, gcn_fwd_smem(N, L.qkvw));
+    g.B = B; g.N = N; g.OW = L.qkvw; g.neff = t.neff;
+    int rc = set_smem_attr((const void*)tr_gcn_fwd_kernel, gcn_fwd_smem(N, L.qkvw, fin));
     if (rc) return rc;
-    tr_gcn_fwd_kernel<<<dim3(L.c_in, B), 256, gcn_fwd_smem(N, L.qkvw), st>>>(g);
+    tr_gcn_fwd_kernel<<<dim3(L.c_in, B), 256, gcn_fwd_smem(N, L.qkvw, fin), st>>>(g);
     KCHECK();
     if (need_edge) {
-      rc = set_smem_attr((const void*)tr_maps_fwd_kernel, maps_smem(N, L.attn));
+      rc = set_smem_attr((const void*)tr_maps_fwd_kernel, maps_smem(N, L.attn, 1));
       if (rc) return rc;
-      tr_maps_fwd_kernel<<<dim3(L.c_in, B), 256, maps_smem(N, L.attn), st>>>(b.Y, b.M, B, L.c_in, N, L.qkvw, L.attn, p.heads,
-                                                                             1.0f / sqrtf((float)L.nhid));
+      tr_maps_fwd_kernel<<<dim3(L.c_in, B), 256, maps_smem(N, L.attn, 1), st>>>(b.Y, b.M, B, L.c_in, N, L.qkvw, L.attn, p.heads,
+                                                                                1.0f / sqrtf((float)L.nhid), t.neff);
       KCHECK();
       tr_edge_rows_kernel<<<egrid(R * 2 * L.c_in), 256, 0, st>>>(b.M, nb.S + (int64_t)cur * N * N, nb.s_bs, b.ein, L.c_in, N, t.pb, t.pij,
                                                                  t.mdev);
@@ -1197,10 +1277,11 @@ static int attn_backward(const NetPlan& p, const float* blob, float* gblob, NetB
       tr_edge_dein_kernel<<<egrid(R * 2 * L.c_in), 256, 0, st>>>(nb.gc, nb.dM, nb.dS + (int64_t)cur * N * N, nb.s_bs, L.c_in, N, t.pb, t.pij,
                                                                  t.mdev);
       KCHECK();
-      rc = set_smem_attr((const void*)tr_maps_bwd_kernel, maps_smem(N, L.attn));
+      const int hg = maps_smem(N, L.attn, p.heads) <= 200 * 1024 ? p.heads : 1;
+      rc = set_smem_attr((const void*)tr_maps_bwd_kernel, maps_smem(N, L.attn, hg));
       if (rc) return rc;
-      tr_maps_bwd_kernel<<<dim3(L.c_in, B), 256, maps_smem(N, L.attn), st>>>(b.Y, nb.dM, nb.dY, B, L.c_in, N, L.qkvw, L.attn, p.heads,
-                                                                             1.0f / sqrtf((float)L.nhid));
+      tr_maps_bwd_kernel<<<dim3(L.c_in, B), 256, maps_smem(N, L.attn, hg), st>>>(b.Y, nb.dM, nb.dY, B, L.c_in, N, L.qkvw, L.attn, p.heads,
+                                                                                 1.0f / sqrtf((float)L.nhid), t.neff, hg);
       KCHECK();
     }
     // the three convolutions of every channel at once (they share A^ and x): layers.py:49-88 backwards
@@ -1209,21 +1290,26 @@ static int attn_backward(const NetPlan& p, const float* blob, float* gblob, NetB
     g.degraw = b.degraw; g.d = b.d; g.XW = b.XW; g.dY = nb.dY; g.dXW = nb.dXW;
     g.dplanes = nb.dS + (int64_t)cur * N * N; g.dp_bs = nb.s_bs;
     g.dbias = gblob + L.bqkv; g.b_cs = L.qkvw;
-    g.B = B; g.N = N; g.OW = L.qkvw;
+    g.B = B; g.N = N; g.OW = L.qkvw; g.neff = t.neff;
     rc = set_smem_attr((const void*)tr_gcn_bwd_kernel, gcn_bwd_smem(N, L.qkvw));
     if (rc) return rc;
     tr_gcn_bwd_kernel<<<dim3(L.c_in, B), 256, gcn_bwd_smem(N, L.qkvw), st>>>(g);
     KCHECK();
     float* dxi = nb.dx[flip];
-    for (int c = 0; c < L.c_in; ++c) {
-      const float* dxw = nb.dXW + (int64_t)c * Rn * L.qkvw;
-      rc = wgrad(xin, ldx, dxw, L.qkvw, gblob + L.wqkv + (int64_t)c * L.f_in_p * L.qkvw, L.qkvw, nullptr, Rn, fin, L.qkvw, st);
+    // weight gradients of all channels in one launch (slice c: columns [c OW, (c + 1) OW) of the dXW rows -> W_c's block)
+    rc = wgrad(xin, ldx, nb.dXW, L.c_in * L.qkvw, gblob + L.wqkv, L.qkvw, nullptr, Rn, fin, L.qkvw, st, nullptr, L.c_in, L.qkvw,
+               (int64_t)L.f_in_p * L.qkvw);
+    if (rc) return rc;
+    if (l > 0) {
+      const int finp = (fin + 3) & ~3, K = L.c_in * L.qkvw;
+      if ((K & 3) || finp > 64) return GDSS_E_UNSUPPORTED;
+      const size_t smem = sizeof(float) * (size_t)K * finp;
+      rc = set_smem_attr((const void*)tr_gcn_dx_kernel, smem);
       if (rc) return rc;
-      if (l > 0) {
-        rc = linear(dxw, L.qkvw, blob + L.wqkv + (int64_t)c * L.f_in_p * L.qkvw, L.qkvw, nullptr, dxi, fin, Rn, L.qkvw, fin, 1, 0,
-                    c > 0 ? 1 : 0, st);
-        if (rc) return rc;
-      }
+      const int rows = 256 / (finp >> 2);
+      tr_gcn_dx_kernel<<<(unsigned)((Rn + rows - 1) / rows), 256, smem, st>>>(nb.dXW, blob + L.wqkv, (int64_t)L.f_in_p * L.qkvw, L.qkvw, dxi,
+                                                                              fin, Rn, L.c_in, L.qkvw, fin);
+      KCHECK();
     }
     dxn = l > 0 ? dxi : nullptr;
     flip ^= 1;
@@ -1245,10 +1331,10 @@ static int gcn_forward(const NetPlan& p, const float* blob, NetBufs& nb, const T
     g.x = l == 0 ? nb.xcat : nb.xcat + F + (l - 1) * h; g.ldx = p.fdim; g.fin = l == 0 ? F : h;
     g.W = blob + p.gw[l]; g.w_cs = 0; g.ldw = h; g.bias = blob + p.gb[l]; g.b_cs = 0;
     g.degraw = b.degraw; g.d = b.d; g.XW = b.XW; g.Y = b.Y;
-    g.B = B; g.N = N; g.OW = h;
-    int rc = set_smem_attr((const void*)tr_gcn_fwd_kernel, gcn_fwd_smem(N, h));
+    g.B = B; g.N = N; g.OW = h; g.neff = t.neff;
+    int rc = set_smem_attr((const void*)tr_gcn_fwd_kernel, gcn_fwd_smem(N, h, g.fin));
     if (rc) return rc;
-    tr_gcn_fwd_kernel<<<dim3(1, B), 256, gcn_fwd_smem(N, h), st>>>(g);
+    tr_gcn_fwd_kernel<<<dim3(1, B), 256, gcn_fwd_smem(N, h, g.fin), st>>>(g);
     KCHECK();
     tr_tanh_rows_kernel<<<ggrid(N * h, B), 256, 0, st>>>(b.Y, nb.xcat + F + l * h, p.fdim, N, h);
     KCHECK();
@@ -1283,7 +1369,7 @@ static int gcn_backward(const NetPlan& p, const float* blob, float* gblob, NetBu
     g.degraw = b.degraw; g.d = b.d; g.XW = b.XW; g.dY = nb.dY; g.dXW = nb.dXW;
     g.dplanes = nullptr; g.dp_bs = 0;                       // the adjacency is an input here, not an activation
     g.dbias = gblob + p.gb[l]; g.b_cs = 0;
-    g.B = B; g.N = N; g.OW = h;
+    g.B = B; g.N = N; g.OW = h; g.neff = t.neff;
     rc = set_smem_attr((const void*)tr_gcn_bwd_kernel, gcn_bwd_smem(N, h));
     if (rc) return rc;
     tr_gcn_bwd_kernel<<<dim3(1, B), 256, gcn_bwd_smem(N, h), st>>>(g);
@@ -1373,16 +1459,26 @@ extern "C" int gdss_dsm_loss_backward(gdss_ctx* ctx, const float* x, const float
   tr_pix_map_kernel<<<ggrid(N * N, B), 256, 0, st>>>(t.neff, t.poff, t.pb, t.pij);
   count_launch();
   LAUNCH_CHECK();
-  TrainCtx tc{t.px, t.padj, t.flags, B, st, t.pb, t.pij, t.poff + B, (int64_t)B * N * (N - 1) / 2};
+  TrainCtx tc{t.px, t.padj, t.flags, B, st, t.neff, t.pb, t.pij, t.poff + B, (int64_t)B * N * (N - 1) / 2};
+  // The two networks are independent until the losses are averaged: the node-feature network runs on a side stream of the
+  // context (fork / join by events, also under stream capture), the adjacency network on the caller's stream.
+  cudaStream_t sx = ctx->side[0] ? ctx->side[0] : st;
+  if (sx != st) {
+    e = cudaEventRecord(ctx->ev_fork, st);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(sx, ctx->ev_fork, 0);
+    if (e != cudaSuccess) return (int)e;
+  }
   // ---- node-feature network: forward, loss (losses.py:60-67), reverse sweep
-  if (ctx->px.type == GDSS_NET_X) rc = gcn_forward(ctx->px, ctx->blob_x, t.nx, tc, t.netx);
-  else rc = attn_forward(ctx->px, ctx->blob_x, t.nx, tc, t.netx);
+  TrainCtx tx = tc;
+  tx.st = sx;
+  if (ctx->px.type == GDSS_NET_X) rc = gcn_forward(ctx->px, ctx->blob_x, t.nx, tx, t.netx);
+  else rc = attn_forward(ctx->px, ctx->blob_x, t.nx, tx, t.netx);
   if (rc) return rc;
-  tr_dsm_dnet_kernel<<<B, 256, 0, st>>>(t.netx, t.zx, coef, t.dnetx, t.lossb, N * F, 0, reduce_mean, B);
+  tr_dsm_dnet_kernel<<<B, 256, 0, sx>>>(t.netx, t.zx, coef, t.dnetx, t.lossb, N * F, 0, reduce_mean, B);
   count_launch();
   LAUNCH_CHECK();
-  if (ctx->px.type == GDSS_NET_X) rc = gcn_backward(ctx->px, ctx->blob_x, grad_blob_x, t.nx, tc, t.dnetx);
-  else rc = attn_backward(ctx->px, ctx->blob_x, grad_blob_x, t.nx, tc, t.dnetx);
+  if (ctx->px.type == GDSS_NET_X) rc = gcn_backward(ctx->px, ctx->blob_x, grad_blob_x, t.nx, tx, t.dnetx);
+  else rc = attn_backward(ctx->px, ctx->blob_x, grad_blob_x, t.nx, tx, t.dnetx);
   if (rc) return rc;
   // ---- adjacency network
   rc = attn_forward(ctx->pa, ctx->blob_a, t.na, tc, t.neta);
@@ -1392,6 +1488,11 @@ extern "C" int gdss_dsm_loss_backward(gdss_ctx* ctx, const float* x, const float
   LAUNCH_CHECK();
   rc = attn_backward(ctx->pa, ctx->blob_a, grad_blob_a, t.na, tc, t.dneta);
   if (rc) return rc;
+  if (sx != st) {
+    e = cudaEventRecord(ctx->ev_join[0], sx);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(st, ctx->ev_join[0], 0);
+    if (e != cudaSuccess) return (int)e;
+  }
   tr_mean_kernel<<<1, 1024, 0, st>>>(t.lossb, B, loss_out);
   count_launch();
   LAUNCH_CHECK();
