@@ -71,9 +71,18 @@ extern "C" gdss_ctx* gdss_ctx_create(int32_t N, int32_t F, const gdss_net_desc* 
   }
   if (c->num_sms > 0 && !(getenv("GDSS_NO_FORK") && getenv("GDSS_NO_FORK")[0] == '1')) {
     bool ok = cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming) == cudaSuccess;
-    for (int k = 0; k < 2 && ok; ++k)
-      ok = cudaStreamCreateWithFlags(&c->side[k], cudaStreamNonBlocking) == cudaSuccess &&
+    // The side streams carry the LARGER size buckets of the per-graph kernel at a higher priority than the caller's stream
+    // (which carries the smallest graphs): the block scheduler then places the big graphs first and the launch ends with the
+    // smallest ones -- a short last wave (GDSS_NO_PRIO=1: equal priorities)
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);          // numerically lower = higher priority
+    const bool noprio = getenv("GDSS_NO_PRIO") && getenv("GDSS_NO_PRIO")[0] == '1';
+    for (int k = 0; k < 2 && ok; ++k) {
+      int pr = prio_hi + k;
+      if (pr > prio_lo || noprio) pr = prio_lo;
+      ok = cudaStreamCreateWithPriority(&c->side[k], cudaStreamNonBlocking, pr) == cudaSuccess &&
            cudaEventCreateWithFlags(&c->ev_join[k], cudaEventDisableTiming) == cudaSuccess;
+    }
     if (!ok) c->side[0] = c->side[1] = nullptr;
   }
   c->fused = false;
@@ -85,8 +94,6 @@ extern "C" gdss_ctx* gdss_ctx_create(int32_t N, int32_t F, const gdss_net_desc* 
   c->use_mma = !(nmma && nmma[0] == '1');
   const char* pp = getenv("GDSS_PHASE_PROF");
   c->phase_prof = pp && pp[0] == '1';
-  const char* to = getenv("GDSS_TINY_OCC");
-  c->tiny_occ = to ? atoi(to) : 4;
   // dead sub-network elimination (gdss_pack.cu analyze_liveness): needs the weights on the host once
   const char* np = getenv("GDSS_NO_PRUNE");
   if (c->num_sms > 0 && !(np && np[0] == '1')) {

@@ -2370,7 +2370,7 @@ int launch_eval_fused(const gdss_ctx* ctx, const float* x, const float* adj, con
   }
   for (int kk = 0; kk < nbk; ++kk) {
     const int k = nbk - 1 - kk;                         // largest bucket first
-    cudaStream_t ks = (fork && kk > 0) ? ctx->side[kk - 1] : st;
+    cudaStream_t ks = (fork && kk < nbk - 1) ? ctx->side[kk] : st;     // the smallest graphs on the caller's (lowest-priority) stream
     // one launch per size bucket: B CTAs, those beyond the bucket's population exit at once (the counts live
     // on the device; no host synchronisation)
     fa.bucket = k;
@@ -2387,14 +2387,11 @@ int launch_eval_fused(const gdss_ctx* ctx, const float* x, const float* adj, con
       // and the weights of all layers stay in the then large L1 -- measured +18 % on C2
       smem = plan_smem(ctx, nb[k], &fa.sl, false);
       // (64 / 96 / 256 threads per CTA measured 20 % / 12 % / 31 % slower than 128 on C2)
-      // tiny_occ: CTAs per SM the register allocation is capped for (4: 128 registers, 5: 96, 6: 80, 8: 64)
-      void (*tk)(const FusedArgs) = ctx->tiny_occ == 8   ? fused_layers_kernel<128, false, 8>
-                                    : ctx->tiny_occ == 6 ? fused_layers_kernel<128, false, 6>
-                                    : ctx->tiny_occ == 5 ? fused_layers_kernel<128, false, 5>
-                                                         : fused_layers_kernel<256, false, 2>;
-      e = cudaFuncSetAttribute(tk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      // (register caps for 5 / 6 / 8 CTAs per SM -- 96 / 80 / 64 registers, 0.3 .. 0.7 KB of spills -- measured 1 % / 6 % / 11 %
+      //  slower than the 128-register build at 4 CTAs per SM: 10.46 k -> 10.35 k / 9.88 k / 9.27 k graphs/s on C2)
+      e = cudaFuncSetAttribute(fused_layers_kernel<256, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e != cudaSuccess) return (int)e;
-      tk<<<B, 128, smem, ks>>>(fa);
+      fused_layers_kernel<256, false, 2><<<B, 128, smem, ks>>>(fa);
     } else if (smem <= limit2) {
       e = cudaFuncSetAttribute(fused_layers_kernel<256, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e != cudaSuccess) return (int)e;
@@ -2421,14 +2418,18 @@ int launch_eval_fused(const gdss_ctx* ctx, const float* x, const float* adj, con
     count_launch();
     if (!fork) prof_tick(K_FUSED, st);
     LAUNCH_CHECK();
-    if (fork && kk > 0) {
-      cudaError_t je = cudaEventRecord(ctx->ev_join[kk - 1], ks);
-      if (je == cudaSuccess) je = cudaStreamWaitEvent(st, ctx->ev_join[kk - 1], 0);
+    if (fork && kk < nbk - 1) {
+      cudaError_t je = cudaEventRecord(ctx->ev_join[kk], ks);
       if (je != cudaSuccess) return (int)je;
     }
   }
-  if (fork) prof_tick(K_FUSED, st);                     // one interval for the parallel branches (after the join)
+  if (fork) {
+    for (int k = 0; k < nbk - 1; ++k)
+      if (cudaStreamWaitEvent(st, ctx->ev_join[k], 0) != cudaSuccess) return (int)cudaGetLastError();
+    prof_tick(K_FUSED, st);                             // one interval for the parallel branches (after the join)
+  }
   cudaError_t e;
+  bool x_side = false;
   if (xfn) {
     const NetPlan& p = ctx->px;
     FinalTriArgs ta;
@@ -2446,9 +2447,24 @@ int launch_eval_fused(const gdss_ctx* ctx, const float* x, const float* adj, con
     int grid = ctx->num_sms > 0 ? ctx->num_sms : 148;
     if ((int64_t)grid > tiles) grid = (int)tiles;
     int* errflag = reinterpret_cast<int*>(ws + w.off[R_META]) + 16;
-    xfn<<<grid, 128 * xns, xsm, st>>>(ta, errflag);
+    // The X network's final MLP and ScoreNetworkA.final are independent: the former runs on a side stream next to the latter
+    // (each is one persistent wave of at most num_sms CTAs whose prologue / tail the other fills; matters on the small shards of
+    // an 8-GPU run).  Serial under the per-kernel profiler, which times on the caller's stream.
+    x_side = fork && want_a && !prof_active();
+    cudaStream_t xs_ = st;
+    if (x_side) {
+      cudaError_t fe = cudaEventRecord(ctx->ev_fork, st);
+      if (fe == cudaSuccess) fe = cudaStreamWaitEvent(ctx->side[0], ctx->ev_fork, 0);
+      if (fe != cudaSuccess) return (int)fe;
+      xs_ = ctx->side[0];
+    }
+    xfn<<<grid, 128 * xns, xsm, xs_>>>(ta, errflag);
     launched(K_FINAL_NODE, st);
     LAUNCH_CHECK();
+    if (x_side) {
+      cudaError_t je = cudaEventRecord(ctx->ev_join[0], xs_);
+      if (je != cudaSuccess) return (int)je;
+    }
   }
   if (want_a) {
     const NetPlan& p = ctx->pa;
@@ -2475,6 +2491,7 @@ int launch_eval_fused(const gdss_ctx* ctx, const float* x, const float* adj, con
         tfn<<<grid, 128 * tns, tsm, st>>>(ta, errflag);
         launched(K_FINAL_EDGE, st);
         LAUNCH_CHECK();
+        if (x_side && cudaStreamWaitEvent(st, ctx->ev_join[0], 0) != cudaSuccess) return (int)cudaGetLastError();
         return 0;
       }
     }
@@ -2495,6 +2512,7 @@ int launch_eval_fused(const gdss_ctx* ctx, const float* x, const float* adj, con
       LAUNCH_CHECK();
     }
   }
+  if (x_side && cudaStreamWaitEvent(st, ctx->ev_join[0], 0) != cudaSuccess) return (int)cudaGetLastError();
   return 0;
 }
 

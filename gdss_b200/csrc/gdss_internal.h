@@ -82,7 +82,6 @@ struct gdss_ctx {
   bool use_mma;                 // per-graph contractions on mma.sync (3xTF32); GDSS_NO_MMA=1 selects the FFMA variants
   bool use_tc;                  // final edge MLP on tcgen05 tensor cores (3xTF32); GDSS_NO_TC=1 selects the FFMA kernel
   int pruned;                   // number of dead chains / MLPs switched off by analyze_liveness (GDSS_NO_PRUNE=1: 0)
-  int tiny_occ;                 // per-graph kernel of tiny graphs (n <= 12): CTAs per SM the registers are capped for (GDSS_TINY_OCC)
   bool phase_prof;              // GDSS_PHASE_PROF=1 (read once at creation): per-phase cycle counters in the workspace
 };
 
@@ -104,6 +103,7 @@ void count_launch(int n = 1);
 enum KernelId { K_NEFF = 0, K_POW, K_DEG, K_GCN, K_EDGE, K_NODE, K_FINAL_EDGE, K_FINAL_NODE, K_COPY, K_NORMS, K_SUMS,
                 K_UPDATE, K_MISC, K_MEMOPS, K_FUSED, K_COUNT };
 void prof_tick(int kid, cudaStream_t st);
+bool prof_active();
 inline void launched(int kid, cudaStream_t st) { count_launch(); prof_tick(kid, st); }
 
 // fused small-graph path (gdss_fused.cu)

@@ -32,6 +32,8 @@ struct ProfState {
 };
 static ProfState g_prof;
 
+bool prof_active() { return g_prof.on; }
+
 void prof_tick(int kid, cudaStream_t st) {
   if (!g_prof.on) return;
   cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
@@ -652,44 +654,46 @@ struct FinalNodeArgs {
 #define FN_ROWS 16
 
 // one linear of the MLP on a 16-row tile: inT [K][16] (k-major) -> outT [Hout][16] (ELU) or, for the last layer, global
-// rows.  Thread = (64-wide column lane, 4-row group); 4 rows x 3 columns of accumulators per pass, weights [K][ldw]
-// read through L1 / L2 (coalesced over the column lanes), inputs as one broadcast float4 per k.
+// rows.  Thread = (64-wide column lane owning 4 consecutive columns, 4-row group): 4 rows x 4 columns of accumulators per pass
+// of 256 columns; per k one broadcast float4 of inputs and one float4 of weights (rows of W are padded to 4 floats with
+// zeros, so the vector load is always in bounds) feed 16 FMAs.  Weights [K][ldw] come through L1 / L2.
 template <bool LAST>
 DEVINL void fn_linear(const float* inT, int K, const float* __restrict__ W, int ldw, const float* __restrict__ bias, int Hout,
                       float* outT, float* O, int64_t ldo, const float* fl, int rows, int tid) {
   const int cg = tid & 63, rg = tid >> 6;
-  for (int o0 = 0; o0 < Hout; o0 += 192) {
-    const int o[3] = {o0 + cg, o0 + cg + 64, o0 + cg + 128};
-    if (o[0] >= Hout) break;
-    const bool on[3] = {true, o[1] < Hout, o[2] < Hout};
-    const float* wp[3] = {W + o[0], W + (on[1] ? o[1] : o[0]), W + (on[2] ? o[2] : o[0])};
-    float acc[4][3];
+  for (int o0 = 0; o0 < Hout; o0 += 256) {
+    const int oc = o0 + 4 * cg;
+    if (oc >= Hout) break;
+    const float* wp = W + oc;
+    float acc[4][4];
 #pragma unroll
-    for (int q = 0; q < 3; ++q) {
-      const float bb = on[q] ? __ldg(bias + o[q]) : 0.f;
+    for (int q = 0; q < 4; ++q) {
+      const float bb = oc + q < Hout ? __ldg(bias + oc + q) : 0.f;
 #pragma unroll
       for (int r = 0; r < 4; ++r) acc[r][q] = bb;
     }
-#pragma unroll 8              // 24 weight loads (L1 / L2) in flight per thread: the kernel is bound by their latency
+#pragma unroll 8              // 8 weight vectors (L1 / L2) in flight per thread: the kernel is bound by their latency
     for (int k = 0; k < K; ++k) {
       const float4 xv = *reinterpret_cast<const float4*>(inT + k * FN_ROWS + 4 * rg);
-      const float w0 = __ldg(wp[0] + (int64_t)k * ldw), w1 = __ldg(wp[1] + (int64_t)k * ldw), w2 = __ldg(wp[2] + (int64_t)k * ldw);
-      acc[0][0] = fmaf(xv.x, w0, acc[0][0]); acc[1][0] = fmaf(xv.y, w0, acc[1][0]);
-      acc[2][0] = fmaf(xv.z, w0, acc[2][0]); acc[3][0] = fmaf(xv.w, w0, acc[3][0]);
-      acc[0][1] = fmaf(xv.x, w1, acc[0][1]); acc[1][1] = fmaf(xv.y, w1, acc[1][1]);
-      acc[2][1] = fmaf(xv.z, w1, acc[2][1]); acc[3][1] = fmaf(xv.w, w1, acc[3][1]);
-      acc[0][2] = fmaf(xv.x, w2, acc[0][2]); acc[1][2] = fmaf(xv.y, w2, acc[1][2]);
-      acc[2][2] = fmaf(xv.z, w2, acc[2][2]); acc[3][2] = fmaf(xv.w, w2, acc[3][2]);
+      const float4 w = __ldg(reinterpret_cast<const float4*>(wp + (int64_t)k * ldw));
+      acc[0][0] = fmaf(xv.x, w.x, acc[0][0]); acc[0][1] = fmaf(xv.x, w.y, acc[0][1]);
+      acc[0][2] = fmaf(xv.x, w.z, acc[0][2]); acc[0][3] = fmaf(xv.x, w.w, acc[0][3]);
+      acc[1][0] = fmaf(xv.y, w.x, acc[1][0]); acc[1][1] = fmaf(xv.y, w.y, acc[1][1]);
+      acc[1][2] = fmaf(xv.y, w.z, acc[1][2]); acc[1][3] = fmaf(xv.y, w.w, acc[1][3]);
+      acc[2][0] = fmaf(xv.z, w.x, acc[2][0]); acc[2][1] = fmaf(xv.z, w.y, acc[2][1]);
+      acc[2][2] = fmaf(xv.z, w.z, acc[2][2]); acc[2][3] = fmaf(xv.z, w.w, acc[2][3]);
+      acc[3][0] = fmaf(xv.w, w.x, acc[3][0]); acc[3][1] = fmaf(xv.w, w.y, acc[3][1]);
+      acc[3][2] = fmaf(xv.w, w.z, acc[3][2]); acc[3][3] = fmaf(xv.w, w.w, acc[3][3]);
     }
 #pragma unroll
-    for (int q = 0; q < 3; ++q) {
-      if (!on[q]) continue;
+    for (int q = 0; q < 4; ++q) {
+      if (oc + q >= Hout) continue;
       if (LAST) {
 #pragma unroll
         for (int r = 0; r < 4; ++r)
-          if (4 * rg + r < rows) O[(int64_t)(4 * rg + r) * ldo + o[q]] = acc[r][q] * fl[4 * rg + r];
+          if (4 * rg + r < rows) O[(int64_t)(4 * rg + r) * ldo + oc + q] = acc[r][q] * fl[4 * rg + r];
       } else {
-        *reinterpret_cast<float4*>(outT + o[q] * FN_ROWS + 4 * rg) =
+        *reinterpret_cast<float4*>(outT + (oc + q) * FN_ROWS + 4 * rg) =
             make_float4(elu_f(acc[0][q]), elu_f(acc[1][q]), elu_f(acc[2][q]), elu_f(acc[3][q]));
       }
     }
