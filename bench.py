@@ -230,8 +230,9 @@ def run_train_bench(args):
                 "frac": ach / world / peaks["bf16_tflops_sustained"], "traffic": None, "peak_source": peak_src,
                 "frac_of_fp32_ffma_peak": ach / world / fp32_peak,
                 "note": "algorithmic FLOPs = 3 x the reference's dense forward GEMM count of both networks per graph (forward + data "
-                        "gradient + weight gradient); per GPU.  This first backward is a correctness-first multi-kernel formulation on "
-                        "the FP32 pipe, not yet a fused / tensor-core one"}
+                        "gradient + weight gradient), at padded N with no credit for symmetry / flag skipping; per GPU.  HBM-staged "
+                        "multi-kernel formulation on the FP32 pipe: per-edge MLPs and their gradients on one compact row per valid "
+                        "upper-triangle pixel, per-graph kernels bounded by the node count (DESIGN 7b)"}
     cpu, torch_gpu = None, None
     if not args.no_cpu_baseline and world == 1:
         cb = args.cpu_batch or wl["cpu_B"]
