@@ -13,6 +13,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # else (the default) is the fp32-parity library.
 PRECISION = "tf32" if os.environ.get("GDSS_PRECISION", "").lower() == "tf32" else "fp32"
 LIB_PATH = os.path.join(_HERE, "csrc", "libgdss_b200_tf32.so" if PRECISION == "tf32" else "libgdss_b200.so")
+if os.environ.get("GDSS_LIB"):          # development only: A/B of two builds of the same ABI (tools/gpu_ab.sh)
+    LIB_PATH = os.environ["GDSS_LIB"]
 
 NET_X, NET_X_GMH, NET_A = 0, 1, 2
 SDE_VP, SDE_VE, SDE_SUBVP = 0, 1, 2

@@ -92,6 +92,8 @@ extern "C" gdss_ctx* gdss_ctx_create(int32_t N, int32_t F, const gdss_net_desc* 
   c->use_tc = !(ntc && ntc[0] == '1');
   const char* nmma = getenv("GDSS_NO_MMA");
   c->use_mma = !(nmma && nmma[0] == '1');
+  const char* te = getenv("GDSS_TCEDGE");          // opt-in experiment: per-edge layer MLPs on tcgen05 (slower)
+  c->use_tc_edge = te && te[0] == '1';
   const char* pp = getenv("GDSS_PHASE_PROF");
   c->phase_prof = pp && pp[0] == '1';
   // dead sub-network elimination (gdss_pack.cu analyze_liveness): needs the weights on the host once

@@ -181,6 +181,8 @@ struct FusedArgs {
   int bucket;
   int mb1;                  // every graph of the launch has at most 16 nodes (one mma row tile)
   int use_mma;              // warp-level tensor-core (mma.sync 3xTF32) variants of the per-graph contractions
+  int use_tc_edge;          // per-edge MLPs of the AttentionLayers on tcgen05 (CTAs of >= 256 threads, hidden width 16)
+  int tce_slots;            // tiles in flight per round (1 .. EDGE_SLOTS)
   unsigned long long* prof;   // optional [16] per-phase clock cycles (thread 0 of every CTA, summed), else null
   int64_t pstride;
   int N, F;
@@ -575,6 +577,86 @@ DEVINL void edge_mlp(const float* M, int MS, const float* pin, int PM, const uns
   }
 }
 
+// ---- tcgen05 / tensor-memory helpers (used by the per-edge MLP of the per-graph kernel and by final_edge_tc_kernel below)
+DEVINL uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+DEVINL float tf32_rna(float v) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+  return __uint_as_float(r);
+}
+
+DEVINL uint64_t umma_bdesc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;                 // descriptor version of sm_100; layout type 0 = no swizzle
+  return d;
+}
+
+DEVINL void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+DEVINL void tmem_st4(uint32_t taddr, float a, float b, float c, float d) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};\n" ::"r"(taddr), "r"(__float_as_uint(a)),
+               "r"(__float_as_uint(b)), "r"(__float_as_uint(c)), "r"(__float_as_uint(d))
+               : "memory");
+}
+
+DEVINL void tmem_st8(uint32_t taddr, const float* v) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};\n" ::"r"(taddr),
+               "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+               "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7]))
+               : "memory");
+}
+
+DEVINL void tmem_ld8_nowait(uint32_t taddr, uint32_t* r) {      // results are valid after tmem_ld_wait()
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+}
+DEVINL void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory"); }
+
+DEVINL void tmem_ld8(uint32_t taddr, float* v) {
+  uint32_t r[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// bounded wait (a lost arrival must not hang the GPU): returns false after ~1 s
+DEVINL bool mbar_wait(uint32_t mbar, uint32_t parity) {
+  for (int it = 0; it < (1 << 24); ++it) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}\n"
+        : "=r"(ok)
+        : "r"(mbar), "r"(parity)
+        : "memory");
+    if (ok) return true;
+  }
+  return false;
+}
+
+DEVINL void tc_sync_before_mma() {         // tcgen05.st / ld of every thread ordered before the next MMA
+  asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+}
+
+
 // ---------------------------------------------------------------------------------------
 // Warp-level tensor-core pieces: mma.sync m16n8k8 TF32 with the 3xTF32 split
 //   a*b ~= lo(a) hi(b) + hi(a) lo(b) + hi(a) hi(b)      (hi = round-to-nearest TF32, lo = TF32 of the remainder)
@@ -774,6 +856,177 @@ DEVINL void edge_mlp_mma(const float* M, int MS, const float* pin, int PM, const
       }
     }
   }
+}
+
+// ---------------------------------------------------------------------------------------
+// The same per-pixel MLP on the 5th-generation tensor cores (tcgen05), for CTAs of at least 256 threads with hidden width 16:
+// warps 0 .. 3 (128 threads), thread = pixel = tensor-memory lane, 128-pixel tiles, up to EDGE_SLOTS tiles in flight.
+//   tensor memory, 64 columns per tile slot:  [0, 16) A operand hi   [16, 32) A operand lo   [32, 48) accumulator D (N = 16)
+//   A operand of linear 1 = the pixel's 2C inputs (written by tcgen05.st straight from the channel planes in shared memory),
+//   of linear 2 / 3 = ELU(D + b) split again and stored over the consumed operand; 3xTF32: hi.hi + lo.hi + hi.lo.
+//   B operands (W^T, hi and lo copies, K-major without swizzle: [k / 4][16][k % 4]) are built per layer from the staged
+//   weights into `bop` (the Q|K rows' region, dead between the attention maps and the next layer's chain): 6 x 1 KB.
+// What it buys over the warp-level version: the three dependent linears of a 16-pixel tile were a ~3000-cycle chain per warp
+// (HMMA -> C fragment -> ELU -> split -> A fragment), 16 tiles per graph of 23 nodes on 6 warps; here a graph's <= 4 tiles
+// advance together through three MMA round trips, and there are no fragment gathers / per-warp weight fragments at all.
+// All activations live in tensor memory between the linears: nothing is held in registers across the waits.
+// pout may alias pin: a thread reads all inputs of its pixel before it writes them.
+// Returns the updated mbarrier phase bits (bit s = parity of slot s's barrier).
+// ---------------------------------------------------------------------------------------
+#define EDGE_SLOTS 4
+#define EDGE_BAR 12          // named barrier of the 128 per-edge threads
+
+DEVINL void edge_tc_sync() {               // tcgen05.st / ld of the 128 threads ordered before the next MMAs
+  asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+  asm volatile("bar.sync %0, 128;\n" ::"n"(EDGE_BAR) : "memory");
+  asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+}
+
+template <int NLIN>
+__device__ __noinline__ uint32_t edge_mlp_tc(const float* M, int MS, const float* pin, int PM, const unsigned* pix, const float* fl,
+                                             const float* wm, const FLayer& L, int P, float* pout, float* gout, int64_t gstride,
+                                             int tid, float* bop, uint32_t tb, uint64_t* mbars, uint32_t phase, int maxslots) {
+  const unsigned kmask = (L.qk_live & ((1u << L.c_in) - 1u)) | (((1u << L.c_in) - 1u) << L.c_in);
+  const int C = L.c_in, c_out = L.c_out, K1 = 2 * C, K1P = (K1 + 7) & ~7;
+  const float* W1 = wm + L.ew_o[0];                 // [2C][16]
+  const float* W2 = wm + L.ew_o[1];                 // [16][16] (NLIN == 3)
+  const float* W3 = wm + L.ew_o[NLIN - 1];          // [16][c_out]
+  const float* b1 = wm + L.eb_o[0];
+  const float* b2 = wm + L.eb_o[1];
+  const float* b3 = wm + L.eb_o[NLIN - 1];
+  // ---- B operands: [linear][hi | lo][256]
+  for (int idx = tid; idx < 256; idx += 128) {
+    const int k = idx >> 4, nn = idx & 15;
+    const int o = (k >> 2) * 64 + nn * 4 + (k & 3);
+    const Split s1 = split_tf32(k < K1 ? W1[k * 16 + nn] : 0.f);
+    bop[o] = __uint_as_float(s1.hi);
+    bop[256 + o] = __uint_as_float(s1.lo);
+    if (NLIN == 3) {
+      const Split s2 = split_tf32(W2[k * 16 + nn]);
+      bop[512 + o] = __uint_as_float(s2.hi);
+      bop[768 + o] = __uint_as_float(s2.lo);
+    }
+    const Split s3 = split_tf32(nn < c_out ? W3[k * c_out + nn] : 0.f);
+    bop[1024 + o] = __uint_as_float(s3.hi);
+    bop[1280 + o] = __uint_as_float(s3.lo);
+  }
+  asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");     // generic-proxy writes of the B operands -> async proxy (UMMA)
+  const uint32_t tl = tb + ((uint32_t)(tid & ~31) << 16);            // this warp's 32 lanes
+  constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(16 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  constexpr uint32_t LBO = 16 * 16, SBO = 128;
+  const uint32_t bbase = smem_u32(bop);
+  // one contraction (3xTF32) of every slot of the round: A = slot columns [0, 16) / [16, 32), D = [32, 48); ksteps of 8
+  auto issue = [&](int nslot, int lin, int ksteps, unsigned live) {
+    for (int s = 0; s < nslot; ++s) {
+      const uint32_t base = tb + 64 * s;
+      uint32_t acc = 0;
+#pragma unroll
+      for (int ps = 0; ps < (GDSS_SPLIT_MODE == 3 ? 1 : 3); ++ps) {
+        const uint32_t acol = base + (ps == 1 ? 16 : 0);
+        const uint32_t wb = bbase + (uint32_t)(lin * 512 + (ps == 2 ? 256 : 0)) * 4u;
+        for (int ks = 0; ks < ksteps; ++ks) {
+          if (!((live >> (8 * ks)) & 0xffu)) continue;               // a k-step of dead inputs only
+          umma_tf32_ts(base + 32, acol + ks * 8, umma_bdesc(wb + ks * 2 * LBO, LBO, SBO), idesc, acc);
+          acc = 1;
+        }
+      }
+      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(smem_u32(mbars + s))
+                   : "memory");
+    }
+  };
+  // D + bias -> ELU -> hi / lo -> the slot's A columns
+  auto elu_stage = [&](int s, const float* bias) {
+    const uint32_t base = tl + 64 * s;
+    uint32_t dr[2][8];
+    tmem_ld8_nowait(base + 32, dr[0]);
+    tmem_ld8_nowait(base + 40, dr[1]);
+    tmem_ld_wait();
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      float h[8], l[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const Split sp = split_tf32(elu_f(__uint_as_float(dr[u][q]) + bias[8 * u + q]));
+        h[q] = __uint_as_float(sp.hi);
+        l[q] = __uint_as_float(sp.lo);
+      }
+      tmem_st8(base + 8 * u, h);
+      if (GDSS_SPLIT_MODE != 3) tmem_st8(base + 16 + 8 * u, l);
+    }
+  };
+  auto wait_slot = [&](int s) {
+    mbar_wait(smem_u32(mbars + s), (phase >> s) & 1u);     // bounded: a lost arrival shows up as a wrong result, not as a hang
+    phase ^= 1u << s;
+    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+  };
+  const int ntile = (P + 127) >> 7;
+  for (int t0 = 0; t0 < ntile; t0 += maxslots) {
+    const int nslot = ntile - t0 < maxslots ? ntile - t0 : maxslots;
+    // ---- linear 1: the pixel's inputs -> A operand
+    for (int s = 0; s < nslot; ++s) {
+      const int p = (t0 + s) * 128 + tid;
+      const bool valid = p < P;
+      const int pc = valid ? p : P - 1;
+      const uint32_t base = tl + 64 * s;
+      for (int k0 = 0; k0 < K1P; k0 += 4) {
+        float h[4], l[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int k = k0 + q;
+          float v = 0.f;
+          if (valid && k < K1 && ((kmask >> k) & 1u)) v = k < C ? M[k * MS + pc] : pin[(k - C) * PM + pc];
+          const Split sp = split_tf32(v);
+          h[q] = __uint_as_float(sp.hi);
+          l[q] = __uint_as_float(sp.lo);
+        }
+        tmem_st4(base + k0, h[0], h[1], h[2], h[3]);
+        if (GDSS_SPLIT_MODE != 3) tmem_st4(base + 16 + k0, l[0], l[1], l[2], l[3]);
+      }
+    }
+    edge_tc_sync();                        // (first round: also orders the B operands' writes before the MMAs)
+    if (tid == 0) issue(nslot, 0, K1P >> 3, kmask);
+    __syncwarp();                          // warp 0 reconverges before its .sync.aligned tensor-memory loads
+    for (int s = 0; s < nslot; ++s) {
+      wait_slot(s);
+      elu_stage(s, b1);
+    }
+    if (NLIN == 3) {
+      edge_tc_sync();
+      if (tid == 0) issue(nslot, 1, 2, 0xffffu);
+      __syncwarp();                          // warp 0 reconverges before its .sync.aligned tensor-memory loads
+      for (int s = 0; s < nslot; ++s) {
+        wait_slot(s);
+        elu_stage(s, b2);
+      }
+    }
+    edge_tc_sync();
+    if (tid == 0) issue(nslot, 2, 2, 0xffffu);
+    __syncwarp();                          // warp 0 reconverges before its .sync.aligned tensor-memory loads
+    // ---- (S + S^T), mask_adjs, stores
+    for (int s = 0; s < nslot; ++s) {
+      wait_slot(s);
+      float d[8];
+      tmem_ld8(tl + 64 * s + 32, d);
+      const int p = (t0 + s) * 128 + tid;
+      if (p < P) {
+        const unsigned ij = pix[p];
+        const float fm = 2.f * fl[ij >> 8] * fl[ij & 255];
+#pragma unroll
+        for (int o = 0; o < 8; ++o) {
+          if (o < c_out) {
+            const float v = (d[o] + b3[o]) * fm;
+            if (pout) pout[o * PM + p] = v;
+            if (gout) gout[(int64_t)o * gstride + p] = v;
+          }
+        }
+      }
+    }
+    // the next round's tcgen05.st into the accumulator-free columns may start at once; its MMAs are issued after the next
+    // edge_tc_sync(), which also orders this round's tcgen05.ld before them
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+  return phase;
 }
 
 // node MLP `multi_channel` of one AttentionLayer (attention.py:90, :106-107) on the tensor cores: one warp = 16 rows,
@@ -1232,10 +1485,13 @@ DEVINL void final_node_mlp(const FNet& net, const float* xs, int XSS, int n, con
     }                                                                  \
   } while (0)
 
-template <int NT, bool WSM, int OCC>      // WSM: layer weights staged in shared memory by TMA (else read from global / L2)
+// TCE: the opt-in instantiation with the per-edge MLPs on tcgen05 (edge_mlp_tc; GDSS_TCEDGE=1).  It is a separate instantiation
+// because the mere presence of that path cost the default one 58 % (same source otherwise, measured on the same box).
+template <int NT, bool WSM, int OCC, bool TCE = false>      // WSM: layer weights staged in shared memory by TMA (else read from global / L2)
 __global__ void __launch_bounds__(NT, OCC) fused_layers_kernel(const __grid_constant__ FusedArgs A) {
   extern __shared__ __align__(16) float sm[];
-  __shared__ __align__(8) uint64_t mbar_q, mbar_m;
+  __shared__ __align__(8) uint64_t mbar_q, mbar_m, mbar_e[EDGE_SLOTS];
+  __shared__ uint32_t tmem_base_s;
   long long tprev = A.prof ? clock64() : 0;
   if ((int)blockIdx.x >= A.meta[2 + A.bucket]) return;
   const int b = A.order[A.meta[5 + A.bucket] + blockIdx.x];
@@ -1265,11 +1521,20 @@ __global__ void __launch_bounds__(NT, OCC) fused_layers_kernel(const __grid_cons
   const int64_t xrow0 = A.xst ? A.noff[b] : 0;
   const FastDiv dn(n), dP(P);
 
+  // per-edge MLPs on tcgen05: tensor memory for EDGE_SLOTS tiles (64 columns each), one mbarrier per slot
+  const bool tc_edge = TCE && A.use_mma && nt >= 256;
+  if (tc_edge && tid < 32) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(&tmem_base_s)), "n"(64 * EDGE_SLOTS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+  }
   if (tid == 0) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(sm_addr(&mbar_q)) : "memory");
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(sm_addr(&mbar_m)) : "memory");
+    for (int s = 0; s < EDGE_SLOTS; ++s) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(sm_addr(&mbar_e[s])) : "memory");
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
+  uint32_t ph_e = 0;                // parities of the slots' mbarriers (uniform over the 128 per-edge threads)
   uint32_t ph_q = 0, ph_m = 0;      // mbarrier phase parities (one completion per fetched run)
   // ---- stage the graph
   for (int i = tid; i < N; i += nt) fl[i] = A.flags[(int64_t)b * N + i];
@@ -1311,7 +1576,13 @@ __global__ void __launch_bounds__(NT, OCC) fused_layers_kernel(const __grid_cons
       R1[i * LD + j] = Ag[i * N + j];
     }
   }
+  if (tc_edge) asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
   __syncthreads();
+  uint32_t tmem_b = 0;
+  if (tc_edge) {
+    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+    tmem_b = tmem_base_s;
+  }
   // ---- power stack (graph_utils.py:133-142), c_init <= 2: plane 0 = A, plane 1 = A @ A
   int c_init = 1;
   if (A.has_a) c_init = A.a.c_init;
@@ -1505,9 +1776,11 @@ __global__ void __launch_bounds__(NT, OCC) fused_layers_kernel(const __grid_cons
       const int node_warps = (L.need_node && L.need_edge && nwarps >= 4)
                                  ? ((A.use_mma && (nwarps < 8 || n <= 16)) ? 1 : ((A.use_mma && nwarps >= 16 && n > 32) ? 3 : 2))
                                  : 0;
-      const int nt_edge = nt - 32 * node_warps;
-      if (L.need_node && (node_warps == 0 || tid >= nt_edge)) {
-        const int ltid = node_warps ? tid - nt_edge : tid, lnt = node_warps ? 32 * node_warps : nt;
+      // per-edge MLP on tcgen05 (warps 0 .. 3) when the layer has the shape the tile code is built for
+      const bool edge_tc = TCE && tc_edge && L.need_edge && !L.edge_const && (L.nlin == 2 || L.nlin == 3);     // (hidden width 16, <= 8 channels: net_fusable)
+      const int nt_edge = edge_tc ? 128 : nt - 32 * node_warps;
+      if (L.need_node && (node_warps == 0 || tid >= nt - 32 * node_warps)) {
+        const int ltid = node_warps ? tid - (nt - 32 * node_warps) : tid, lnt = node_warps ? 32 * node_warps : nt;
         if (A.use_mma) {
           node_mlp_mma(R2, LDV, C * h, wmp + L.nw0_o, wmp + L.nb0_o, wmp + L.nw1_o, wmp + L.nb1_o, n, h, fl, !isA, xb, XS, ltid >> 5,
                        lnt >> 5, lane, L.vk_live);
@@ -1518,7 +1791,7 @@ __global__ void __launch_bounds__(NT, OCC) fused_layers_kernel(const __grid_cons
           node_l2(h1, wmp + L.nw1_o, wmp + L.nb1_o, n, h, fl, !isA, xb, XS, ltid, lnt);
         }
       }
-      if (L.need_edge && (node_warps == 0 || tid < nt_edge)) {
+      if (L.need_edge && (edge_tc ? tid < 128 : (node_warps == 0 || tid < nt_edge))) {
         if (!node_warps && L.need_node) __syncthreads();       // (never both: kept for symmetry of the barrier count)
         float* gout = isA ? A.stackT + (int64_t)cbase * A.pstride + gp0 : nullptr;
         float* pout = more ? PA : nullptr;
@@ -1532,6 +1805,12 @@ __global__ void __launch_bounds__(NT, OCC) fused_layers_kernel(const __grid_cons
               if (pout) pout[o * PM + p] = v;
               if (gout) gout[(int64_t)o * A.pstride + p] = v;
             }
+          }
+        } else if (TCE && edge_tc) {
+          // B operands in the Q|K rows' region: dead between the attention maps and the next layer's chain
+          if constexpr (TCE) {
+            if (L.nlin == 3) ph_e = edge_mlp_tc<3>(R1, RS, pin, PM, pix, fl, wmp, L, P, pout, gout, A.pstride, tid, QK, tmem_b, mbar_e, ph_e, A.tce_slots);
+            else ph_e = edge_mlp_tc<2>(R1, RS, pin, PM, pix, fl, wmp, L, P, pout, gout, A.pstride, tid, QK, tmem_b, mbar_e, ph_e, A.tce_slots);
           }
         } else if (A.use_mma) {
           if (L.nlin == 3) edge_mlp_mma<3>(R1, RS, pin, PM, pix, fl, wmp, L, P, pout, gout, A.pstride, warp, nt_edge >> 5, lane);
@@ -1569,6 +1848,11 @@ __global__ void __launch_bounds__(NT, OCC) fused_layers_kernel(const __grid_cons
       final_node_mlp(net, xs, XSS, n, fl, hA, hB, A.raw_x + (int64_t)b * N * F, F);
       PHASE(6);
     }
+  }
+  if (tc_edge) {
+    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+    __syncthreads();
+    if (tid < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_b), "n"(64 * EDGE_SLOTS) : "memory");
   }
 }
 
@@ -1713,84 +1997,6 @@ __global__ void __launch_bounds__(256) final_edge_tri_kernel(FinalTriArgs a) {
 //              staged once per CTA; biases and the last layer's weight vector.
 //   256 threads: warp w works on TMEM lanes 32 (w % 4) .. +31 and on column half w / 4.
 // ---------------------------------------------------------------------------------------
-DEVINL uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-DEVINL float tf32_rna(float v) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
-  return __uint_as_float(r);
-}
-
-DEVINL uint64_t umma_bdesc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
-  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
-  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
-  d |= (uint64_t)1 << 46;                 // descriptor version of sm_100; layout type 0 = no swizzle
-  return d;
-}
-
-DEVINL void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(d_tmem),
-      "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-
-DEVINL void tmem_st4(uint32_t taddr, float a, float b, float c, float d) {
-  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};\n" ::"r"(taddr), "r"(__float_as_uint(a)),
-               "r"(__float_as_uint(b)), "r"(__float_as_uint(c)), "r"(__float_as_uint(d))
-               : "memory");
-}
-
-DEVINL void tmem_st8(uint32_t taddr, const float* v) {
-  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};\n" ::"r"(taddr),
-               "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
-               "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7]))
-               : "memory");
-}
-
-DEVINL void tmem_ld8_nowait(uint32_t taddr, uint32_t* r) {      // results are valid after tmem_ld_wait()
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
-               : "r"(taddr)
-               : "memory");
-}
-DEVINL void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory"); }
-
-DEVINL void tmem_ld8(uint32_t taddr, float* v) {
-  uint32_t r[8];
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
-               : "r"(taddr)
-               : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
-}
-
-// bounded wait (a lost arrival must not hang the GPU): returns false after ~1 s
-DEVINL bool mbar_wait(uint32_t mbar, uint32_t parity) {
-  for (int it = 0; it < (1 << 24); ++it) {
-    uint32_t ok;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}\n"
-        : "=r"(ok)
-        : "r"(mbar), "r"(parity)
-        : "memory");
-    if (ok) return true;
-  }
-  return false;
-}
-
-DEVINL void tc_sync_before_mma() {         // tcgen05.st / ld of every thread ordered before the next MMA
-  asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
-  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
-  __syncthreads();
-  asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-}
-
 // (Measured and dropped: issuing the second contraction in two K chunks so that its first half overlaps the conversion of
 // the second half of the layer-2 operand -- the extra CTA barrier per tile cost more than the overlap gained, +5 %.)
 // NODE: final MLP of an X network (FOP = padded output width), rows = nodes.  NS: column splits = warps per TMEM lane
@@ -1962,6 +2168,7 @@ __global__ void __launch_bounds__(128 * NS, 1) final_edge_tc_kernel(FinalTriArgs
       stage_a1(next);
       tc_sync_before_mma();
       if (tid == 0) issue_mma1();
+      __syncwarp();
     }
     ok = mbar_wait(mb, phase);
     phase ^= 1;
@@ -2008,6 +2215,8 @@ __global__ void __launch_bounds__(128 * NS, 1) final_edge_tc_kernel(FinalTriArgs
       asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(PIPE ? mb2 : mb) : "memory");
       if (PIPE && next < ntiles) issue_mma1();          // next tile's first contraction: overlaps the epilogue below
     }
+    __syncwarp();       // warp 0 reconverges before its .sync.aligned tensor-memory loads (lane 0 may still be issuing when the
+                        // barrier of the second contraction completes; a partial-warp tcgen05.ld was observed to return garbage)
     if (PIPE) {
       ok = ok && mbar_wait(mb2, phase2);
       phase2 ^= 1;
@@ -2354,6 +2563,9 @@ int launch_eval_fused(const gdss_ctx* ctx, const float* x, const float* adj, con
     fa.nstride = w.nstride;
   }
   fa.use_mma = ctx->use_mma ? 1 : 0;
+  fa.use_tc_edge = ctx->use_tc_edge ? 1 : 0;
+  fa.tce_slots = EDGE_SLOTS;
+  if (const char* ts = getenv("GDSS_TCE_SLOTS")) { const int v = atoi(ts); if (v >= 1 && v <= EDGE_SLOTS) fa.tce_slots = v; }
   fa.prof = ctx->phase_prof ? reinterpret_cast<unsigned long long*>(ws + w.off[R_META] + 128) : nullptr;
   fa.order = reinterpret_cast<const int*>(ws + w.off[R_ORDER]);
   fa.meta = reinterpret_cast<const int*>(ws + w.off[R_META]);
@@ -2368,6 +2580,7 @@ int launch_eval_fused(const gdss_ctx* ctx, const float* x, const float* adj, con
     for (int k = 0; k < nbk - 1 && fe == cudaSuccess; ++k) fe = cudaStreamWaitEvent(ctx->side[k], ctx->ev_fork, 0);
     if (fe != cudaSuccess) return (int)fe;
   }
+  const bool tce = ctx->use_tc_edge && ctx->use_mma;
   for (int kk = 0; kk < nbk; ++kk) {
     const int k = nbk - 1 - kk;                         // largest bucket first
     cudaStream_t ks = (fork && kk < nbk - 1) ? ctx->side[kk] : st;     // the smallest graphs on the caller's (lowest-priority) stream
@@ -2393,27 +2606,31 @@ int launch_eval_fused(const gdss_ctx* ctx, const float* x, const float* adj, con
       if (e != cudaSuccess) return (int)e;
       fused_layers_kernel<256, false, 2><<<B, 128, smem, ks>>>(fa);
     } else if (smem <= limit2) {
-      e = cudaFuncSetAttribute(fused_layers_kernel<256, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      void (*kf)(const FusedArgs) = tce ? fused_layers_kernel<256, true, 2, true> : fused_layers_kernel<256, true, 2>;
+      e = cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e != cudaSuccess) return (int)e;
-      fused_layers_kernel<256, true, 2><<<B, 256, smem, ks>>>(fa);
+      kf<<<B, 256, smem, ks>>>(fa);
     } else if (plan_smem(ctx, nb[k], &fa.sl, false) <= limit2) {   // (one CTA of 512 with staged weights measured 20 % slower here)
       smem = plan_smem(ctx, nb[k], &fa.sl, false);
-      e = cudaFuncSetAttribute(fused_layers_kernel<256, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      void (*kf)(const FusedArgs) = tce ? fused_layers_kernel<256, false, 2, true> : fused_layers_kernel<256, false, 2>;
+      e = cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e != cudaSuccess) return (int)e;
-      fused_layers_kernel<256, false, 2><<<B, 256, smem, ks>>>(fa);
+      kf<<<B, 256, smem, ks>>>(fa);
     } else if (smem > 0 && smem <= ctx->smem_optin) {
       smem = plan_smem(ctx, nb[k], &fa.sl, true);
-      e = cudaFuncSetAttribute(fused_layers_kernel<512, true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      void (*kf)(const FusedArgs) = tce ? fused_layers_kernel<512, true, 1, true> : fused_layers_kernel<512, true, 1>;
+      e = cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e != cudaSuccess) return (int)e;
-      fused_layers_kernel<512, true, 1><<<B, 512, smem, ks>>>(fa);
+      kf<<<B, 512, smem, ks>>>(fa);
     } else {
       // wide layers (nhid = adim = 32, 8 channels: community_small's 96 KB of Q|K|V weights per layer): the staged plan
       // does not fit an SM at all; one CTA of 256 per SM with the weights read through L1 / L2
       smem = plan_smem(ctx, nb[k], &fa.sl, false);
       if (smem <= 0 || smem > ctx->smem_optin) return GDSS_E_UNSUPPORTED;
-      e = cudaFuncSetAttribute(fused_layers_kernel<256, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      void (*kf)(const FusedArgs) = tce ? fused_layers_kernel<256, false, 2, true> : fused_layers_kernel<256, false, 2>;
+      e = cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e != cudaSuccess) return (int)e;
-      fused_layers_kernel<256, false, 2><<<B, 256, smem, ks>>>(fa);
+      kf<<<B, 256, smem, ks>>>(fa);
     }
     count_launch();
     if (!fork) prof_tick(K_FUSED, st);

@@ -80,6 +80,7 @@ struct gdss_ctx {
   cudaStream_t side[2];
   cudaEvent_t ev_fork, ev_join[2];
   bool use_mma;                 // per-graph contractions on mma.sync (3xTF32); GDSS_NO_MMA=1 selects the FFMA variants
+  bool use_tc_edge;             // per-edge layer MLPs of the per-graph kernel on tcgen05 (GDSS_NO_TCEDGE=1: the mma.sync version)
   bool use_tc;                  // final edge MLP on tcgen05 tensor cores (3xTF32); GDSS_NO_TC=1 selects the FFMA kernel
   int pruned;                   // number of dead chains / MLPs switched off by analyze_liveness (GDSS_NO_PRUNE=1: 0)
   bool phase_prof;              // GDSS_PHASE_PROF=1 (read once at creation): per-phase cycle counters in the workspace

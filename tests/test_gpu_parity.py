@@ -356,6 +356,27 @@ def test_tf32_variant_library_has_its_stated_tolerance():
     assert worst > 1e-5, out                    # a single-pass TF32 result cannot be as close as the 3xTF32 build
 
 
+def test_tcgen05_per_edge_mlp_variant_keeps_fp32_parity():
+    """GDSS_TCEDGE=1 selects the instantiation of the per-graph kernel whose per-edge layer MLPs run on tcgen05 (thread = pixel =
+    tensor-memory lane, 3xTF32; opt-in because it is slower than the mma.sync version): raw scores of the checkpoints
+    that run 256-thread CTAs stay within the fp32 bar of the reference fixtures.  Subprocess: the flag is read at context creation
+    but the probe also reports which library it ran."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, GDSS_TCEDGE="1", GDSS_ROOT=root)
+    env.pop("GDSS_PRECISION", None)
+    r = subprocess.run([sys.executable, "-c", TF32_PROBE], env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = [l for l in r.stdout.splitlines() if l.startswith("TF32PROBE ")][-1]
+    out = json.loads(line[len("TF32PROBE "):])
+    assert out["precision"] == "fp32" and out["lib"] == "libgdss_b200.so"
+    for name in ("zinc250k_v2", "community_small", "qm9"):         # (QM9 runs 128-thread CTAs: the flag changes nothing there)
+        ex, ea, asym = out[name]
+        assert ex <= TOL and ea <= TOL and asym == 0.0, (name, out[name])
+
+
 @pytest.mark.parametrize("name", ["zinc250k_v2", "qm9", "community_small", "enzymes"])
 def test_degenerate_graphs_follow_the_reference(name):
     """Edge cases of the flags: an empty graph (all flags 0), a single node, a pair, a full graph, and flags with holes
