@@ -963,6 +963,15 @@ static int run_attn_net(const gdss_ctx* ctx, const NetPlan& p, const float* blob
     if (rc0) return rc0;
     }
     int rc = 0;
+    // the per-edge part (maps + MLP) and the node MLP of a layer are independent once Q | K | V exist: the node MLP runs on
+    // the second side stream next to the edge kernel (both are partial waves at these batch sizes)
+    const bool node_side = need_edge && need_node && ctx->side[1] && !prof_active();
+    cudaStream_t sn = node_side ? ctx->side[1] : st;
+    if (node_side) {
+      cudaError_t fe = cudaEventRecord(ctx->ev_fork, st);
+      if (fe == cudaSuccess) fe = cudaStreamWaitEvent(sn, ctx->ev_fork, 0);
+      if (fe != cudaSuccess) return (int)fe;
+    }
     if (need_edge) {
       EdgeArgs ea;
       ea.qk_live = qk_live;
@@ -1007,10 +1016,15 @@ static int run_attn_net(const gdss_ctx* ctx, const NetPlan& p, const float* blob
       size_t smem = sizeof(float) * ((size_t)L.c_in * L.nhid * L.hid + (size_t)L.hid * L.nhid + (size_t)NODE_ROWS * L.hid);
       rc = set_smem(node_kernel, smem);
       if (rc) return rc;
-      node_kernel<<<dim3((N + NODE_ROWS - 1) / NODE_ROWS, B), 256, smem, st>>>(na);
+      node_kernel<<<dim3((N + NODE_ROWS - 1) / NODE_ROWS, B), 256, smem, sn>>>(na);
       launched(K_NODE, st);
       LAUNCH_CHECK();
       xin = na.out; x_bs = na.o_bs; ldx = na.ldo;
+      if (node_side) {
+        cudaError_t je = cudaEventRecord(ctx->ev_join[1], sn);
+        if (je == cudaSuccess) je = cudaStreamWaitEvent(st, ctx->ev_join[1], 0);
+        if (je != cudaSuccess) return (int)je;
+      }
     }
     cur += L.c_in;
   }
