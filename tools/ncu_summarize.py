@@ -14,6 +14,9 @@ CMD = (sys.argv[3] if len(sys.argv) > 3 else
        "python bench.py --steps 2 --warmup 3 --burn-in 1 --repeats 1 --no-extra --no-cpu-baseline --no-torch-baseline --no-profile")
 
 
+RX = sys.argv[4] if len(sys.argv) > 4 else "fused_layers_kernel|final_edge_tc_kernel"
+
+
 def short(name):
     name = re.sub(r"^void\s+", "", name)
     name = re.sub(r"gdss::", "", name)
@@ -37,7 +40,7 @@ for r in csv.DictReader(io.StringIO("".join(rows))):
     a[1] += v
 tot = sum(a[1] for a in agg.values())
 with open(f"profiles/{outp}_launches.csv", "w") as f:
-    f.write(f"# ncu --metrics gpu__time_duration.sum --clock-control none -c 600 : {CMD}\n")
+    f.write(f"# ncu --metrics gpu__time_duration.sum --clock-control none : {CMD}\n")
     f.write("# per-launch times are cold-cache and serialised: compare SHARES with bench.py's kernel_ms shares\n")
     f.write("kernel,launches,total_us,share\n")
     for k, a in sorted(agg.items(), key=lambda kv: -kv[1][1]):
@@ -57,7 +60,7 @@ rd = list(csv.reader(io.StringIO(raw)))
 hdr, units, data = rd[0], rd[1], rd[2:]
 col = {h: i for i, h in enumerate(hdr)}
 with open(f"profiles/{outp}_ncu_full.csv", "w") as f:
-    f.write(f"# ncu --set full --clock-control none --import-source on -k regex:fused_layers_kernel|final_edge_tc_kernel : {CMD}\n")
+    f.write(f"# ncu --set full --clock-control none --import-source on -k regex:{RX} : {CMD}\n")
     f.write("metric,unit," + ",".join('"' + short(r[col["Kernel Name"]]) + '"' for r in data) + "\n")
     for m in METRICS:
         if m in col:
