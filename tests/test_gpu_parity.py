@@ -850,6 +850,51 @@ def test_dsm_backward_matches_reference_autograd(name):
     print(name, "grad rel err", ex, ea)
 
 
+@pytest.mark.parametrize("name", ["qm9", "zinc250k_v2"])
+def test_dsm_backward_on_ragged_batches_with_holes_matches_oracle_autograd(name):
+    """The training kernels work on compact pixel rows bounded by 1 + the last flagged node (gdss_train.cu): a batch with very
+    different node counts, an isolated node IN THE MIDDLE of a graph (flag 0 between flagged nodes: losses.py:47 takes the flags
+    from the data's degrees), a single pair and an empty graph must give the losses and gradients of torch.autograd over the
+    oracle restatement (test infrastructure, itself pinned to the reference's autograd by test_oracle_golden.py)."""
+    from gdss_b200.trainer import DSMTrainStep
+    from tests.gpu_common import sde_from
+    ck = load_golden_ckpt(name)
+    N, F = int(ck["params_adj"]["max_node_num"]), int(ck["params_adj"]["max_feat_num"])
+    g = torch.Generator().manual_seed(5)
+    counts = [N, max(2, N // 2), 5, 2, 0, max(3, N - 3)]
+    B = len(counts)
+    adj = torch.zeros(B, N, N)
+    for b, c in enumerate(counts):
+        if c >= 2:
+            a = (torch.rand(c, c, generator=g) < 0.4).float().triu(1)
+            a[torch.arange(c - 1), torch.arange(1, c)] = 1.0          # a path: every node of the prefix has an edge
+            adj[b, :c, :c] = a + a.t()
+    hole = 2
+    adj[0, hole, :] = 0                                               # graph 0: node 2 isolated -> its flag is 0, nodes 3.. stay
+    adj[0, :, hole] = 0
+    adj[5, 0, :] = 0                                                  # graph 5: node 0 isolated
+    adj[5, :, 0] = 0
+    x = torch.zeros(B, N, F)
+    x[torch.arange(B)[:, None], torch.arange(N)[None, :], torch.randint(0, F, (B, N), generator=g)] = 1.0
+    x = x * (adj.abs().sum(-1) > 0).float()[:, :, None]
+    t = torch.rand(B, generator=g) * 0.9 + 0.05
+    raw_x, raw_adj = torch.randn(B, N, F, generator=g), torch.randn(B, N, N, generator=g)
+    kinds = (("VP", .1, 1.), ("VE", .2, 1.)) if name == "zinc250k_v2" else (("VE", .1, 1.), ("VE", .1, 1.))
+    sdx = {k: v.clone().float().requires_grad_(True) for k, v in ck["x_state_dict"].items()}
+    sda = {k: v.clone().float().requires_grad_(True) for k, v in ck["adj_state_dict"].items()}
+    lx, la = O.dsm_loss(O.SDESpec(*kinds[0], 1000), O.SDESpec(*kinds[1], 1000), sdx, ck["params_x"], sda, ck["params_adj"], x, adj, t,
+                        raw_x, raw_adj, reduce_mean=False)
+    gx = torch.autograd.grad(lx, list(sdx.values()), allow_unused=True)
+    ga = torch.autograd.grad(la, list(sda.values()), allow_unused=True)
+    flat = lambda gs, sd: torch.cat([(gr if gr is not None else torch.zeros_like(p)).reshape(-1) for gr, p in zip(gs, sd.values())])
+    rx, ra = flat(gx, sdx), flat(ga, sda)
+    tr = DSMTrainStep(ck["x_state_dict"], ck["adj_state_dict"], N, sde_from(kinds[0], 1000), sde_from(kinds[1], 1000),
+                      reduce_mean=False)
+    loss, cx, ca = tr.loss_and_grads(x.cuda(), adj.cuda(), t=t.cuda(), raw_x=raw_x.cuda(), raw_adj=raw_adj.cuda())
+    assert abs(float(loss[0]) - float(lx.detach())) <= TOL * abs(float(lx.detach())) and abs(float(loss[1]) - float(la.detach())) <= TOL * abs(float(la.detach()))
+    assert rel(cx, rx) <= 1e-3 and rel(ca, ra) <= 1e-3, (name, rel(cx, rx), rel(ca, ra))
+
+
 def test_two_training_iterations_match_the_reference_loop_on_gpu():
     """trainer.py:57-79 end to end (both losses, backward, per-network clip_grad_norm_, Adam with weight decay, EMA) run twice
     by DSMTrainStep on ZINC250k v2 with the shipped optimizer settings against the unmodified reference's loop (fixture by
