@@ -17,6 +17,8 @@ Produces
                                   atom) applied to the final state of the full ZINC250k v2 reference run
   tests/golden/c1_community_reference.npz  BASELINE config C1 run with the reference on the CPU (flags, thresholded
                                   samples, training graphs) for the statistical parity test
+  tests/golden/c1_mmd_reference.npz  the reference's own evaluation/stats.py (degree / cluster / orbit / spectral MMD, ORCA orbit
+                                  counts) on that run (mode `mmd`)
   tests/golden/dsm_<ckpt>_<sum|mean>.npz  loss_fn of losses.py:37-81 on a synthetic batch with recorded t / noise draws
   tests/golden/MANIFEST.json      what was generated, from which torch version
 
@@ -557,6 +559,78 @@ def make_train_steps():
     return out
 
 
+def make_mmd_reference():
+    """The reference's own evaluation (evaluation/stats.py `degree_stats`, `clustering_stats`, `orbit_stats_all`, `spectral_stats`
+    with the kernels of utils/loader.py:199-206) run UNMODIFIED on the C1 reference run: generated samples (through the
+    reference's `adjs_to_graphs` convention: isolated nodes removed) against the training graphs.  What has to be supplied from
+    outside: `np.float` (removed from numpy), `nx.from_numpy_matrix` (removed from networkx 3; `from_numpy_array` is the same
+    function), `pyemd.emd` (not installed: the exact 1-D earth mover's distance for the Toeplitz ground distance |i - j| / s,
+    checked here against the transportation LP solved by scipy on a sample of the actual histogram pairs) and the ORCA binary
+    (built from the reference's own orca.cpp by oracle/Makefile into oracle/_ref).  Stored: the four MMD values and ORCA's
+    per-node orbit counts of every graph, which pin oracle/stats.py."""
+    import subprocess
+    import networkx as nx
+    import pyemd
+    from scipy.optimize import linprog
+    np.float = float
+    subprocess.run(["make", "-C", HERE], check=True, capture_output=True)
+
+    def emd_exact_1d(x, y, dist):
+        return float(np.abs(np.cumsum(np.asarray(x, dtype=np.float64) - np.asarray(y, dtype=np.float64))).sum() * dist[0, 1])
+
+    def emd_lp(x, y, dist):
+        n = len(x)
+        a_eq = np.zeros((2 * n, n * n))
+        for i in range(n):
+            a_eq[i, i * n:(i + 1) * n] = 1
+            a_eq[n + i, i::n] = 1
+        r = linprog(dist.reshape(-1), A_eq=a_eq, b_eq=np.concatenate([x, y]), bounds=(0, None), method="highs")
+        return float(r.fun)
+
+    emd = emd_exact_1d          # (the reference evaluates the kernels in worker processes: evaluation/mmd.py:84-87)
+    pyemd.emd = emd
+    import evaluation.stats as S
+    import evaluation.mmd as M
+    S.ORCA_DIR = os.path.join(HERE, "_ref")
+    z = np.load(os.path.join(GOLD, "c1_community_reference.npz"))
+    train = [nx.from_numpy_array(z["train"][k][:n, :n].astype(np.float64)) for k, n in enumerate(z["train_counts"])]
+
+    def adjs_to_graphs(adjs):               # utils/graph_utils.py:165-176 with from_numpy_array for the removed from_numpy_matrix
+        out = []
+        for adj in adjs:
+            g = nx.from_numpy_array(adj)
+            g.remove_edges_from(nx.selfloop_edges(g))
+            g.remove_nodes_from(list(nx.isolates(g)))
+            if g.number_of_nodes() < 1:
+                g.add_node(1)
+            out.append(g)
+        return out
+
+    pred = adjs_to_graphs(z["samples"].astype(np.float64))
+    with contextlib.redirect_stdout(io.StringIO()):
+        res = {"degree": S.degree_stats(train, pred, M.gaussian_emd, is_parallel=False),
+               "cluster": S.clustering_stats(train, pred, M.gaussian_emd, is_parallel=False),
+               "orbit": S.orbit_stats_all(train, pred, M.gaussian),
+               "spectral": S.spectral_stats(train, pred, M.gaussian_emd, is_parallel=False)}
+    res = {k: round(float(v), 6) for k, v in res.items()}
+    # the closed-form EMD against the transportation LP on 40 of the actual degree-histogram pairs
+    from scipy.linalg import toeplitz
+    rs = np.random.RandomState(0)
+    lp_checks = []
+    for _ in range(40):
+        hx, hy = S.degree_worker(train[rs.randint(len(train))]), S.degree_worker(pred[rs.randint(len(pred))])
+        hx, hy = M.process_tensor(hx / hx.sum(), hy / hy.sum())
+        dist = toeplitz(range(len(hx))).astype(np.float64)
+        lp_checks.append(abs(emd_exact_1d(hx, hy, dist) - emd_lp(np.asarray(hx, dtype=np.float64), np.asarray(hy, dtype=np.float64), dist)))
+    orb = [S.orca(g) for g in train + pred]
+    sizes = np.array([o.shape[0] for o in orb], dtype=np.int32)
+    np.savez_compressed(os.path.join(GOLD, "c1_mmd_reference.npz"), degree=res["degree"], cluster=res["cluster"], orbit=res["orbit"],
+                        spectral=res["spectral"], orbit_counts=np.concatenate(orb).astype(np.int32), orbit_sizes=sizes,
+                        n_train=len(train), emd_lp_max_diff=max(lp_checks), emd_lp_checks=len(lp_checks))
+    res.update(emd_lp_checks=len(lp_checks), emd_lp_max_diff=float(max(lp_checks)))
+    return res
+
+
 def only(which):
     """python oracle/make_golden.py decode | c1 | dsm | mol | dsmgrad | train : just one of the small fixtures."""
     refimport.activate()
@@ -579,6 +653,9 @@ def only(which):
         manifest["segments"] = make_segments()
     elif which == "segs_ref":
         manifest.setdefault("segments", {}).update(make_segments_s4_ref())
+    elif which == "mmd":
+        manifest["c1_mmd"] = make_mmd_reference()
+        print(manifest["c1_mmd"])
     elif which == "traj_new":
         manifest["traj"].update(make_traj(missing_only=True))
     else:
@@ -589,4 +666,4 @@ def only(which):
 
 
 if __name__ == "__main__":
-    only(sys.argv[1]) if sys.argv[1:] in (["decode"], ["c1"], ["dsm"], ["mol"], ["dsmgrad"], ["train"], ["traj_new"], ["segs"], ["segs_ref"], ["layers"]) else main()
+    only(sys.argv[1]) if sys.argv[1:] in (["decode"], ["c1"], ["dsm"], ["mol"], ["dsmgrad"], ["train"], ["traj_new"], ["segs"], ["segs_ref"], ["layers"], ["mmd"]) else main()

@@ -17,8 +17,8 @@ def degree_histograms(adj_q, counts):
     """Per-graph degree histogram over the graph's own nodes (nx.degree_histogram, evaluation/stats.py:49): list of
     integer arrays of length max_degree + 1."""
     out = []
-    for a, n in zip(np.asarray(adj_q), counts):
-        deg = a[:n, :n].sum(axis=1).astype(int)
+    for a, n in zip(adj_q, counts):             # (a 3-D array or a list of per-graph arrays)
+        deg = np.asarray(a)[:n, :n].sum(axis=1).astype(int)
         out.append(np.bincount(deg))
     return out
 
@@ -65,8 +65,8 @@ def clustering_histograms(adj_q, counts, bins=100):
     """nx.clustering per node (triangles through the node / (deg (deg - 1) / 2), 0 when deg < 2), histogram over [0, 1] with
     `bins` bins (evaluation/stats.py:104-109)."""
     out = []
-    for a, n in zip(np.asarray(adj_q), counts):
-        a = a[:n, :n].astype(np.float64)
+    for a, n in zip(adj_q, counts):
+        a = np.asarray(a)[:n, :n].astype(np.float64)
         deg = a.sum(axis=1)
         tri = np.einsum("ij,jk,ki->i", a, a, a) / 2.0
         denom = deg * (deg - 1) / 2.0
@@ -80,10 +80,10 @@ def spectral_pmfs(adj_q, counts):
     """eigenvalues of the normalised Laplacian I - D^-1/2 A D^-1/2 (isolated nodes: zero row, as networkx builds it),
     histogram with 200 bins over (-1e-5, 2), normalised (evaluation/stats.py:61-65)."""
     out = []
-    for a, n in zip(np.asarray(adj_q), counts):
+    for a, n in zip(adj_q, counts):
         if n == 0:
             continue
-        a = a[:n, :n].astype(np.float64)
+        a = np.asarray(a)[:n, :n].astype(np.float64)
         deg = a.sum(axis=1)
         dis = np.where(deg > 0, 1.0 / np.sqrt(np.maximum(deg, 1e-30)), 0.0)
         lap = np.diag((deg > 0).astype(np.float64)) - dis[:, None] * a * dis[None, :]
@@ -109,3 +109,98 @@ def clustering_mmd(adj_ref, counts_ref, adj_pred, counts_pred, bins=100):
 def spectral_mmd(adj_ref, counts_ref, adj_pred, counts_pred):
     """evaluation/stats.py:69-101 with KERNEL = gaussian_emd (sigma = 1, distance_scaling = 1)."""
     return mmd(spectral_pmfs(adj_ref, counts_ref), spectral_pmfs(adj_pred, counts_pred), gaussian_emd)
+
+
+# ---- orbit statistics (evaluation/stats.py:172-193 `orbit_stats_all`): per-node counts of the 15 orbits of the 2- to 4-node
+# graphlets as the reference's ORCA binary reports them (`orca node 4`), restated by brute force over the induced 3- and 4-node
+# subgraphs (fine for the <= 20-node graphs of the C1 check; pinned to ORCA's own output by tests/golden/c1_mmd_reference.npz)
+_COMBOS = {}
+
+
+def _combos(n, k):
+    key = (n, k)
+    if key not in _COMBOS:
+        from itertools import combinations
+        _COMBOS[key] = np.array(list(combinations(range(n), k)), dtype=np.int64).reshape(-1, k)
+    return _COMBOS[key]
+
+
+def orbit_counts(a):
+    """a [n,n] in {0,1}, symmetric, zero diagonal -> int64 [n,15].  Orbits: 0 edge; 1 / 2 end / middle of the induced 3-path;
+    3 triangle; 4 / 5 end / inner node of the 4-path; 6 / 7 leaf / centre of the claw; 8 4-cycle; 9 / 10 / 11 pendant node /
+    degree-2 triangle nodes / degree-3 node of the tailed triangle; 12 / 13 degree-2 / degree-3 nodes of the diamond; 14 K4."""
+    a = (np.asarray(a) > 0).astype(np.int64)
+    n = a.shape[0]
+    out = np.zeros((n, 15), dtype=np.int64)
+    out[:, 0] = a.sum(axis=1)
+    if n >= 3:
+        c = _combos(n, 3)
+        sub = a[c[:, :, None], c[:, None, :]]                 # [M,3,3]
+        deg = sub.sum(axis=2)
+        edges = deg.sum(axis=1) // 2
+        for m in np.nonzero(edges == 2)[0]:
+            for q in range(3):
+                out[c[m, q], 1 if deg[m, q] == 1 else 2] += 1
+        for m in np.nonzero(edges == 3)[0]:
+            out[c[m], 3] += 1
+    if n >= 4:
+        c = _combos(n, 4)
+        sub = a[c[:, :, None], c[:, None, :]]                 # [M,4,4]
+        deg = sub.sum(axis=2)
+        edges = deg.sum(axis=1) // 2
+        conn = (deg.min(axis=1) > 0) & (edges >= 3)
+        # two disjoint edges (degrees 1,1,1,1) have 2 edges and are excluded by edges >= 3; 3 edges with every degree > 0 is a
+        # path or a claw (a triangle + isolated node has a zero degree)
+        dmax = deg.max(axis=1)
+        table = {  # (edges, max degree) -> {degree in the graphlet: orbit}
+            (3, 2): {1: 4, 2: 5}, (3, 3): {1: 6, 3: 7}, (4, 2): {2: 8}, (4, 3): {1: 9, 2: 10, 3: 11}, (5, 3): {2: 12, 3: 13},
+            (6, 3): {3: 14}}
+        for m in np.nonzero(conn)[0]:
+            orb = table[(int(edges[m]), int(dmax[m]))]
+            for q in range(4):
+                out[c[m, q], orb[int(deg[m, q])]] += 1
+    return out
+
+
+def graph_from_adj(a):
+    """utils/graph_utils.py:165-176 `adjs_to_graphs` on one thresholded adjacency: self loops and isolated nodes removed; a
+    graph left without nodes becomes one isolated node.  Returns the dense adjacency of what is left."""
+    a = (np.asarray(a) > 0).astype(np.int8)
+    np.fill_diagonal(a, 0)
+    keep = a.sum(axis=1) > 0
+    if not keep.any():
+        return np.zeros((1, 1), dtype=np.int8)
+    return a[np.ix_(keep, keep)]
+
+
+def orbit_features(adjs):
+    """per graph: orbit counts summed over the nodes / number of nodes (evaluation/stats.py:181, :190)."""
+    return [orbit_counts(a).sum(axis=0) / a.shape[0] for a in adjs]
+
+
+def gaussian_l2(x, y, sigma=1.0):
+    """evaluation/mmd.py:48-53 `gaussian` (vectors padded to equal length)."""
+    m = max(len(x), len(y))
+    x = np.pad(np.asarray(x, dtype=np.float64), (0, m - len(x)))
+    y = np.pad(np.asarray(y, dtype=np.float64), (0, m - len(y)))
+    d = np.linalg.norm(x - y, 2)
+    return np.exp(-d * d / (2 * sigma * sigma))
+
+
+def orbit_mmd(adjs_ref, adjs_pred):
+    """evaluation/stats.py:172-193 with KERNEL = gaussian: compute_mmd(..., is_hist=False, sigma=30)."""
+    s1, s2 = orbit_features(adjs_ref), orbit_features(adjs_pred)
+    k = lambda x, y: gaussian_l2(x, y, sigma=30.0)
+    return disc(s1, s1, k) + disc(s2, s2, k) - 2 * disc(s1, s2, k)
+
+
+def eval_graph_lists(adjs_ref, adjs_pred):
+    """evaluation/stats.py:218-230 `eval_graph_list` with the methods / kernels of utils/loader.py:199-206 (degree, cluster,
+    spectral: gaussian_emd; orbit: gaussian) on lists of dense adjacencies whose isolated nodes are already removed
+    (`graph_from_adj` for generated samples; training graphs as they are).  Values rounded to 6 digits as the reference does."""
+    cr, cp = [a.shape[0] for a in adjs_ref], [a.shape[0] for a in adjs_pred]
+    pad = lambda lst: lst                                   # the histogram helpers take per-graph arrays + counts
+    res = {"degree": degree_mmd(degree_histograms(pad(adjs_ref), cr), degree_histograms(pad(adjs_pred), cp)),
+           "cluster": clustering_mmd(adjs_ref, cr, adjs_pred, cp), "orbit": orbit_mmd(adjs_ref, adjs_pred),
+           "spectral": spectral_mmd(adjs_ref, cr, adjs_pred, cp)}
+    return {k: round(float(v), 6) for k, v in res.items()}

@@ -622,6 +622,15 @@ def test_c1_sample_statistics_match_the_reference_run():
           "spectral", round(s_our, 4), round(s_ref, 4))
     assert c_our < c_ref + 0.03, (c_our, c_ref)
     assert s_our < s_ref + 0.03, (s_our, s_ref)
+    # the same four numbers the reference's sampler.py prints (evaluation/stats.py eval_graph_list: degree / cluster / orbit /
+    # spectral MMD, isolated nodes of a sample removed as adjs_to_graphs does), through the restatement that reproduces the
+    # reference's own evaluation of its run to 6 digits (tests/golden/c1_mmd_reference.npz, test_oracle_golden.py)
+    g = np.load(os.path.join(GOLD, "c1_mmd_reference.npz"))
+    tr = [train[k][:n, :n] for k, n in enumerate(tc)]
+    ours = S.eval_graph_lists(tr, [S.graph_from_adj(a) for a in q[:100]])
+    print("C1 eval_graph_list (ours / reference run):", ours, {k: float(g[k]) for k in ours})
+    for k, slack in (("degree", 0.03), ("cluster", 0.03), ("orbit", 0.01), ("spectral", 0.03)):
+        assert ours[k] < float(g[k]) + slack, (k, ours[k], float(g[k]))
 
 
 @pytest.mark.parametrize("tag", ["qm9", "zinc_v2"])
