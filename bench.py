@@ -169,7 +169,7 @@ def run_train_bench(args):
     K, W, R = args.steps, max(args.warmup, 3), max(args.repeats, 1)
     tr = DSMTrainStep(sdx, sda, wl["N"], sde_from(wl["sde_x"], 1000), sde_from(wl["sde_adj"], 1000), lr=wl["lr"],
                       weight_decay=wl["weight_decay"], grad_norm=wl["grad_norm"], ema=wl["ema_decay"], reduce_mean=False, device=str(dev),
-                      shard=shard if world > 1 else None)
+                      shard=shard if world > 1 else None, use_graph=not args.train_eager)
     xd, ad = x[lo:hi].to(dev), adj[lo:hi].to(dev)
 
     def barrier():
@@ -200,6 +200,9 @@ def run_train_bench(args):
         barrier()
         times.append(mx(ev0.elapsed_time(ev1)))
     launches = (L.gdss_launch_count() - before) // R
+    used_graph = tr.use_graph
+    if used_graph:                                       # replayed launches are not counted by the library: K x the captured step
+        launches = K * tr.captured_launches
     clk = clocks.stop() if clocks is not None else {}
     ms = float(np.median(times)) / K
     value = 1000.0 / ms
@@ -253,7 +256,8 @@ def run_train_bench(args):
             "data": "synthetic ZINC-like molecules (node counts: SURVEY 8d recipe), shipped checkpoint as the initial weights",
             "config": {"workload": wl["desc"], "batch": B, "batch_per_gpu": hi - lo, "graphs_per_s": value * B,
                        "sharding": f"data parallel over {world} ranks, one NCCL all-reduce of each network's flat gradient per step" if world > 1 else "none",
-                       "l2": "activation arena >> L2 (several GB at B=1024)"},
+                       "l2": "activation arena >> L2 (several GB at B=1024)",
+                       "launch": "one CUDA graph per step, replayed" if used_graph else "eager launches"},
             "clocks": clk, "e2e": e2e, "gpu_launches": int(launches) * world, "roofline": roofline, "cpu_baseline": cpu,
             "torch_eager_same_gpu": torch_gpu, "losses_last_step": losses,
             "repeats": {"regions": R, "steps_per_region": K, "ms_per_step_min": min(times) / K, "ms_per_step_max": max(times) / K}}
@@ -460,6 +464,7 @@ def main():
     ap.add_argument("--precision", default="fp32", choices=["fp32", "tf32"],
                     help="fp32 (default, the parity build: 3xTF32 split, <= 1e-4) or tf32 (libgdss_b200_tf32.so: single-pass "
                          "TF32, <= 3e-2; a reduced-precision line, never the headline)")
+    ap.add_argument("--train-eager", action="store_true", help="zinc_train: launch every step eagerly instead of replaying one CUDA graph")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-profile", action="store_true")
     ap.add_argument("--no-torch-baseline", action="store_true")

@@ -83,6 +83,9 @@ def lib():
         "gdss_optim_scratch_floats": (i64, []),
         "gdss_adam_ema_step": (C.c_int, [fp, fp, fp, fp, fp, i64, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float,
                                           C.c_float, i32, C.c_float, i64, fp, fp, fp, vp]),
+        "gdss_adam_step_consts": (C.c_int, [C.c_float, C.c_float, C.c_float, i32, C.c_float, i64, fp]),
+        "gdss_adam_ema_step_dev": (C.c_int, [fp, fp, fp, fp, fp, i64, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float,
+                                              fp, fp, fp, fp, vp]),
         "gdss_nccl_allreduce": (C.c_int, [vp, fp, i64, vp]),
         "gdss_nccl_unique_id": (C.c_int, [vp]),
         "gdss_nccl_comm_create": (C.c_int, [vp, i32, i32, C.POINTER(vp)]),

@@ -81,6 +81,35 @@ class FusedAdamEMA:
             self.num_updates += 1
         return self.norm if self.grad_norm > 0 else None
 
+    # ---- the same step for a captured CUDA graph: the launch (`enqueue_dev`, captured once) reads the four per-step scalars from
+    # `self.consts`; `advance()` (every step, before the replay) refreshes them from the host-side step count
+    def advance(self):
+        """Bump the step count and copy {lr, bias corrections, EMA factor} of this step to the device (stream-ordered)."""
+        import ctypes as C
+        self.step_count += 1
+        if not hasattr(self, "consts"):
+            self.consts = torch.zeros(4, device=self.p.device)
+            self._consts_host = torch.zeros(4).pin_memory()
+        check(self.L.gdss_adam_step_consts(self.lr, self.betas[0], self.betas[1], self.step_count,
+                                           float(self.ema_decay if self.ema_decay is not None else 0.0), self.num_updates,
+                                           self._consts_host.data_ptr()), "gdss_adam_step_consts")
+        self.consts.copy_(self._consts_host, non_blocking=True)
+        if self.shadow is not None:
+            self.num_updates += 1
+
+    def enqueue_dev(self, flat_grads, grad_scale=1.0):
+        if not hasattr(self, "consts"):
+            self.consts = torch.zeros(4, device=self.p.device)
+            self._consts_host = torch.zeros(4).pin_memory()
+        st = torch.cuda.current_stream(self.p.device).cuda_stream
+        with torch.cuda.device(self.p.device):
+            check(self.L.gdss_adam_ema_step_dev(self.p.data_ptr(), flat_grads.data_ptr(), self.m.data_ptr(), self.v.data_ptr(),
+                                                self.shadow.data_ptr() if self.shadow is not None else None, self.p.numel(),
+                                                self.betas[0], self.betas[1], self.eps, self.wd, self.grad_norm, float(grad_scale),
+                                                self.consts.data_ptr(), self.active.data_ptr() if self.active is not None else None,
+                                                self.scratch.data_ptr(), self.norm.data_ptr(), st), "gdss_adam_ema_step_dev")
+        return self.norm if self.grad_norm > 0 else None
+
 
 def allreduce_grads(shard, flat_grads):
     """In-place NCCL sum of the flat gradient over the ranks of a ShardInfo (gdss_b200.dist); no-op for one rank."""

@@ -73,6 +73,8 @@ class _Net:
         self.perm = perm.to(dev)
         self.valid = self.perm >= 0
         self.src = self.perm.clamp_min(0)
+        self.valid_idx = torch.nonzero(self.valid).flatten()        # blob positions that hold a parameter ...
+        self.dst_idx = self.perm[self.valid_idx]                    # ... and the flat index each of them maps to
         self.blob = torch.zeros(self.perm.numel(), device=dev)
         self.gblob = torch.zeros_like(self.blob)
         self.grad = torch.zeros_like(self.flat)
@@ -84,8 +86,9 @@ class _Net:
         self.blob.copy_(torch.where(self.valid, self.flat[self.src], torch.zeros((), device=self.flat.device)))
 
     def collect_grad(self):
+        # (index tensors precomputed: no data-dependent shapes, so the step can be captured into a CUDA graph)
         self.grad.zero_()
-        self.grad[self.perm[self.valid]] = self.gblob[self.valid]
+        self.grad.index_copy_(0, self.dst_idx, self.gblob.index_select(0, self.valid_idx))
         return self.grad
 
     def state_dict(self, ema=False):
@@ -98,7 +101,7 @@ class DSMTrainStep:
     or state_dicts; hyper-parameters as config.train (utils/loader.py:51-64): lr, weight_decay, grad_norm, ema."""
 
     def __init__(self, model_x, model_adj, n_nodes, sde_x, sde_adj, lr=1e-3, weight_decay=0.0, grad_norm=1.0, ema=0.999,
-                 reduce_mean=False, eps=1e-5, device="cuda", shard=None):
+                 reduce_mean=False, eps=1e-5, device="cuda", shard=None, use_graph=False):
         require_cuda()
         self.L = lib()
         self.dev = torch.device(device if device != "cuda" else f"cuda:{torch.cuda.current_device()}")
@@ -118,6 +121,13 @@ class DSMTrainStep:
             raise _lib.GdssError("gdss_ctx_create failed (unsupported network configuration)")
         self._ws = None
         self.loss = torch.zeros(2, device=self.dev)
+        # use_graph: the whole step (marginals, gdss_dsm_loss_backward, gradient gather, NCCL all-reduce, clip / Adam / EMA, blob
+        # refresh) is captured once per batch shape into a CUDA graph and replayed; inputs go through static buffers and the
+        # optimizer's per-step scalars through device memory (gdss_adam_ema_step_dev).  What it buys: the ~330 launches of a
+        # step are launch-bound on small per-GPU batches (data-parallel training of B = 1024 on 8 GPUs)
+        self.use_graph = bool(use_graph)
+        self._graphs = {}
+        self.captured_launches = 0
 
     def __del__(self):
         try:
@@ -163,9 +173,7 @@ class DSMTrainStep:
                                                 torch.cuda.current_stream(dev).cuda_stream), "gdss_dsm_loss_backward")
             return self.loss, self.x.collect_grad(), self.a.collect_grad()
 
-    def step(self, x, adj, t=None, raw_x=None, raw_adj=None):
-        """trainer.py:57-79 for one batch -> (loss_x, loss_adj, grad_norm_x, grad_norm_adj) as device scalars (this rank's
-        losses; the gradient norms are those of the global, batch-mean gradient)."""
+    def _eager_step(self, x, adj, t=None, raw_x=None, raw_adj=None):
         loss, gx, ga = self.loss_and_grads(x, adj, t, raw_x, raw_adj)
         world = 1 if self.shard is None else self.shard.world
         with torch.no_grad(), torch.cuda.device(self.dev):
@@ -176,6 +184,60 @@ class DSMTrainStep:
                 net.refresh_blob()
         lx, la = loss[0].clone(), loss[1].clone()
         return lx, la, norms[0], norms[1]
+
+    def _graph_step(self, x, adj, t, raw_x, raw_adj):
+        dev = self.dev
+        B = x.shape[0]
+        key = (B, t is None, raw_x is None, raw_adj is None)
+        world = 1 if self.shard is None else self.shard.world
+        g = self._graphs.get(key)
+        if g is None:
+            g = {"x": torch.empty(B, self.N, self.F, device=dev), "adj": torch.empty(B, self.N, self.N, device=dev),
+                 "t": None if t is None else torch.empty(B, device=dev),
+                 "rx": None if raw_x is None else torch.empty(B, self.N, self.F, device=dev),
+                 "ra": None if raw_adj is None else torch.empty(B, self.N, self.N, device=dev),
+                 "out": torch.zeros(4, device=dev)}
+            self._workspace(B)
+            for net in (self.x, self.a):
+                if not hasattr(net.opt, "consts"):
+                    net.opt.consts = torch.zeros(4, device=dev)
+                    net.opt._consts_host = torch.zeros(4).pin_memory()
+            torch.cuda.synchronize(dev)
+            graph = torch.cuda.CUDAGraph()
+            before = self.L.gdss_launch_count()
+            with torch.cuda.graph(graph):
+                loss, gx, ga = self.loss_and_grads(g["x"], g["adj"], g["t"], g["rx"], g["ra"])
+                norms = []
+                for net, gr in ((self.x, gx), (self.a, ga)):
+                    allreduce_grads(self.shard, gr)
+                    norms.append(net.opt.enqueue_dev(gr, grad_scale=1.0 / world))
+                    net.refresh_blob()
+                g["out"][:2].copy_(loss)
+                for k, nrm in enumerate(norms):
+                    if nrm is not None:
+                        g["out"][2 + k:3 + k].copy_(nrm)
+            g["graph"] = graph
+            self.captured_launches = int(self.L.gdss_launch_count() - before)
+            self._graphs[key] = g
+        with torch.no_grad(), torch.cuda.device(dev):
+            g["x"].copy_(x, non_blocking=True)
+            g["adj"].copy_(adj, non_blocking=True)
+            for name, src in (("t", t), ("rx", raw_x), ("ra", raw_adj)):
+                if src is not None:
+                    g[name].copy_(src, non_blocking=True)
+            for net in (self.x, self.a):
+                net.opt.advance()
+            g["graph"].replay()
+            out = g["out"].clone()
+        clip = self.x.opt.grad_norm > 0
+        return out[0], out[1], (out[2] if clip else None), (out[3] if self.a.opt.grad_norm > 0 else None)
+
+    def step(self, x, adj, t=None, raw_x=None, raw_adj=None):
+        """trainer.py:57-79 for one batch -> (loss_x, loss_adj, grad_norm_x, grad_norm_adj) as device scalars (this rank's
+        losses; the gradient norms are those of the global, batch-mean gradient)."""
+        if self.use_graph:
+            return self._graph_step(x, adj, t, raw_x, raw_adj)
+        return self._eager_step(x, adj, t, raw_x, raw_adj)
 
     def state_dicts(self, ema=False):
         return self.x.state_dict(ema), self.a.state_dict(ema)

@@ -218,6 +218,15 @@ int gdss_adam_ema_step(float* params, const float* grads, float* exp_avg, float*
                        float lr, float beta1, float beta2, float eps, float weight_decay, float grad_clip, float grad_scale,
                        int32_t step, float ema_decay, int64_t ema_num_updates, const unsigned char* active_or_null,
                        float* scratch, float* grad_norm_out, void* stream);
+/* The per-step scalars of that update -- out4 = {lr, 1 - beta1^step, sqrt(1 - beta2^step), 1 - EMA decay of this update} (host,
+ * double arithmetic as torch's) -- and the same step reading them from DEVICE memory: the launch no longer depends on the step
+ * count, so a whole training step (gdss_dsm_loss_backward + gdss_nccl_allreduce + this) can be captured into one CUDA graph and
+ * replayed; the caller copies the four floats to the device before each replay. */
+int gdss_adam_step_consts(float lr, float beta1, float beta2, int32_t step, float ema_decay, int64_t ema_num_updates, float* out4);
+int gdss_adam_ema_step_dev(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, float* ema_shadow, int64_t n,
+                           float beta1, float beta2, float eps, float weight_decay, float grad_clip, float grad_scale,
+                           const float* step_consts_dev, const unsigned char* active_or_null, float* scratch,
+                           float* grad_norm_out, void* stream);
 
 /* ---- tensor helpers -----------------------------------------------------------------
  * Replace utils/graph_utils.py: mask_x :8-12, mask_adjs :16-29 (3-D or 4-D via C channels),

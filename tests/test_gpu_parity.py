@@ -937,6 +937,39 @@ def test_two_training_iterations_match_the_reference_loop_on_gpu():
     assert list(sda.keys()) == list(ck["adj_state_dict"].keys())
 
 
+def test_training_step_replayed_from_a_cuda_graph_equals_eager_launches():
+    """DSMTrainStep(use_graph=True) captures the whole step (marginals, gdss_dsm_loss_backward, gradient gather, clip / Adam / EMA
+    with the per-step scalars in device memory, blob refresh) once and replays it: three iterations with injected draws give the
+    losses, gradient norms, parameters and EMA shadows of the eagerly launched step (weight-gradient atomics make both runs
+    non-deterministic at the 1e-6 level, hence a tolerance instead of bit equality)."""
+    import json
+    from gdss_b200.trainer import DSMTrainStep
+    from tests.gpu_common import sde_from
+    name = "zinc250k_v2"
+    z = np.load(os.path.join(GOLD, f"dsm_{name}_sum.npz"))
+    ck = load_golden_ckpt(name)
+    sx_, sa_ = json.loads(str(z["sde"]))
+    mk = lambda g: DSMTrainStep(ck["x_state_dict"], ck["adj_state_dict"], 38, sde_from(sx_, 1000), sde_from(sa_, 1000), lr=0.005,
+                                weight_decay=0.0001, grad_norm=1.0, ema=0.999, reduce_mean=False, use_graph=g)
+    eager, graph = mk(False), mk(True)
+    c = lambda k: torch.from_numpy(z[k]).cuda()
+    for it in range(2):
+        oe = eager.step(c("x"), c("adj"), t=c("t"), raw_x=c("raw_x"), raw_adj=c("raw_adj"))
+        og = graph.step(c("x"), c("adj"), t=c("t"), raw_x=c("raw_x"), raw_adj=c("raw_adj"))
+        # (Adam's first steps turn 1e-7 gradient noise near eps into lr-sized parameter differences: the tolerances of the second
+        #  iteration are those of the reference-loop test above)
+        tol_o, tol_p = (1e-4, 1e-5) if it == 0 else (3e-3, 2e-3)
+        for a, b in zip(oe, og):
+            assert abs(float(a) - float(b)) <= tol_o * abs(float(a)), (it, float(a), float(b))
+        assert rel(graph.x.flat, eager.x.flat) <= tol_p and rel(graph.a.flat, eager.a.flat) <= tol_p, it
+        assert rel(graph.a.opt.shadow, eager.a.opt.shadow) <= tol_p
+    assert graph.captured_launches > 100 and graph.x.opt.step_count == 2
+    # without injected draws the graph draws t / noise itself (torch's graph-safe generator): losses stay finite and differ per step
+    l1 = graph.step(c("x"), c("adj"))
+    l2 = graph.step(c("x"), c("adj"))
+    assert np.isfinite(float(l1[0])) and np.isfinite(float(l2[1])) and float(l1[0]) != float(l2[0])
+
+
 @pytest.mark.parametrize("name", ["qm9", "zinc250k_v2", "community_small"])
 @pytest.mark.parametrize("path", ["general", "fused"])
 def test_op_level_outputs_match_reference_modules(name, path):
