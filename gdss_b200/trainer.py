@@ -125,7 +125,9 @@ class DSMTrainStep:
         # refresh) is captured once per batch shape into a CUDA graph and replayed; inputs go through static buffers and the
         # optimizer's per-step scalars through device memory (gdss_adam_ema_step_dev).  What it buys: the ~330 launches of a
         # step are launch-bound on small per-GPU batches (data-parallel training of B = 1024 on 8 GPUs)
-        self.use_graph = bool(use_graph)
+        # Single-process only: with the NCCL all-reduce inside torch's (global-mode) capture the first 8-rank attempt hung --
+        # NCCL sets its connections up lazily on the first collective -- and data-parallel runs therefore launch eagerly
+        self.use_graph = bool(use_graph) and (shard is None or shard.world == 1)
         self._graphs = {}
         self.captured_launches = 0
 
