@@ -2,7 +2,9 @@
 // networks (BASELINE config C5; losses.py:37-81 + trainer.py:57-65: loss_x.backward(), loss_adj.backward()).
 //
 // This is the HBM-staged, multi-kernel formulation (one launch per tensor operation of the reference's graph, activations
-// kept in a caller-provided arena): dense [B, N, N] / [B, N, F] layouts, every node evaluated (no neff shortcut), fp32 FFMA.
+// kept in a caller-provided arena), fp32 FFMA.  Node tensors are dense [B, N, .]; everything per-edge runs on ONE compact row
+// per valid strict-upper-triangle pixel (i < j < neff_b, see "compact pixel rows" below; row count on the device), and the
+// per-graph kernels (tr_gcn_*, tr_maps_*) work on the neff_b x neff_b block only (padded rows are filled in directly).
 // Each kernel is the gradient of the forward restatement of the same name in the oracle (oracle/gdss_backward.py, test
 // infrastructure) and cites the reference lines it differentiates.  Parameter gradients are accumulated in the layout of
 // the packed weight blob (gdss_pack.cu): the host mirror maps them back to state_dict order.

@@ -188,8 +188,10 @@ int gdss_dsm_loss(gdss_ctx* ctx, const float* x, const float* adj, const float* 
  * ScoreNetwork_X.py:32-46, :75-89).  x / adj / coef / raw_x / raw_adj / reduce_mean as in gdss_dsm_loss.
  * grad_blob_x / grad_blob_a (device, gdss_packed_floats floats each, overwritten): d loss_x / d theta_x and
  * d loss_adj / d theta_adj in the LAYOUT OF THE PACKED BLOBS (padding entries stay 0); parameters a loss never reaches get 0.
- * The context's blobs are read as the current weights (update them in place between steps).  Every node is evaluated (dense
- * layouts, no dead-chain elimination); N <= 128.  loss_out[0..1] on the device.  No host synchronisation. */
+ * The context's blobs are read as the current weights (update them in place between steps).  No dead-chain elimination (every
+ * parameter gets its gradient); padded nodes and the symmetric half of every per-edge quantity are skipped exactly (their
+ * gradient contributions are zero / identical); N <= 128.  loss_out[0..1] on the device.  No host synchronisation.  The node-
+ * feature network runs on a side stream of the context next to the adjacency network (fork / join by events on `stream`). */
 int64_t gdss_train_workspace_bytes(const gdss_ctx* ctx, int32_t B);
 int gdss_dsm_loss_backward(gdss_ctx* ctx, const float* x, const float* adj, const float* coef, const float* raw_x,
                            const float* raw_adj, int32_t B, int32_t reduce_mean, float* grad_blob_x, float* grad_blob_a,
