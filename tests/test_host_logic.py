@@ -389,3 +389,26 @@ def test_probability_flow_and_n_steps_in_the_schedule():
         fn({}, {}, torch.ones(2, 9))
     with pytest.raises(ValueError):
         get_pc_sampler(sx, sa, (2, 9, 4), (2, 9, 9), predictor="Reverse", corrector="Langevin", n_steps=0)
+
+
+def test_adam_step_constants_follow_torch_and_the_reference_ema():
+    """gdss_adam_step_consts (host code; what a graph-replayed training step copies to the device before every replay): lr, the
+    two Adam bias corrections as torch.optim.Adam computes them from the python step count, and the EMA factor of
+    utils/ema.py:26-28 (num_updates += 1; decay = min(decay, (1 + num_updates) / (10 + num_updates)))."""
+    import ctypes as C
+    import math
+    from gdss_b200 import _lib
+    L = _lib.lib()
+    out = (C.c_float * 4)()
+    for step, nu in ((1, 0), (2, 1), (10, 9), (1000, 999), (200000, 5)):
+        rc = L.gdss_adam_step_consts(0.005, 0.9, 0.999, step, 0.999, nu, C.cast(out, C.c_void_p))
+        assert rc == 0
+        n1 = nu + 1
+        decay = min(0.999, (1 + n1) / (10 + n1))
+        b1, b2 = float(np.float32(0.9)), float(np.float32(0.999))       # the ABI takes the betas as C floats
+        want = [0.005, 1 - b1 ** step, math.sqrt(1 - b2 ** step), 1 - decay]
+        for a, b in zip(out, want):
+            assert abs(a - b) <= 2e-7 * max(1.0, abs(b)), (step, nu, list(out), want)
+    rc = L.gdss_adam_step_consts(0.005, 0.9, 0.999, 3, 0.5, -1, C.cast(out, C.c_void_p))      # -1: the decay as it is
+    assert rc == 0 and abs(out[3] - 0.5) < 1e-7
+    assert L.gdss_adam_step_consts(0.005, 0.9, 0.999, 0, 0.999, 0, C.cast(out, C.c_void_p)) < 0       # step is 1-based
