@@ -2602,25 +2602,21 @@ int launch_eval_fused(const gdss_ctx* ctx, const float* x, const float* adj, con
       // (64 / 96 / 256 threads per CTA measured 20 % / 12 % / 31 % slower than 128 on C2)
       // (register caps for 5 / 6 / 8 CTAs per SM -- 96 / 80 / 64 registers, 0.3 .. 0.7 KB of spills -- measured 1 % / 6 % / 11 %
       //  slower than the 128-register build at 4 CTAs per SM: 10.46 k -> 10.35 k / 9.88 k / 9.27 k graphs/s on C2)
-      e = cudaFuncSetAttribute(fused_layers_kernel<256, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      if (e != cudaSuccess) return (int)e;
+      if (int rc_ = ensure_smem((const void*)fused_layers_kernel<256, false, 2>, smem)) return rc_;
       fused_layers_kernel<256, false, 2><<<B, 128, smem, ks>>>(fa);
     } else if (smem <= limit2) {
       void (*kf)(const FusedArgs) = tce ? fused_layers_kernel<256, true, 2, true> : fused_layers_kernel<256, true, 2>;
-      e = cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      if (e != cudaSuccess) return (int)e;
+      if (int rc_ = ensure_smem((const void*)kf, smem)) return rc_;
       kf<<<B, 256, smem, ks>>>(fa);
     } else if (plan_smem(ctx, nb[k], &fa.sl, false) <= limit2) {   // (one CTA of 512 with staged weights measured 20 % slower here)
       smem = plan_smem(ctx, nb[k], &fa.sl, false);
       void (*kf)(const FusedArgs) = tce ? fused_layers_kernel<256, false, 2, true> : fused_layers_kernel<256, false, 2>;
-      e = cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      if (e != cudaSuccess) return (int)e;
+      if (int rc_ = ensure_smem((const void*)kf, smem)) return rc_;
       kf<<<B, 256, smem, ks>>>(fa);
     } else if (smem > 0 && smem <= ctx->smem_optin) {
       smem = plan_smem(ctx, nb[k], &fa.sl, true);
       void (*kf)(const FusedArgs) = tce ? fused_layers_kernel<512, true, 1, true> : fused_layers_kernel<512, true, 1>;
-      e = cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      if (e != cudaSuccess) return (int)e;
+      if (int rc_ = ensure_smem((const void*)kf, smem)) return rc_;
       kf<<<B, 512, smem, ks>>>(fa);
     } else {
       // wide layers (nhid = adim = 32, 8 channels: community_small's 96 KB of Q|K|V weights per layer): the staged plan
@@ -2628,8 +2624,7 @@ int launch_eval_fused(const gdss_ctx* ctx, const float* x, const float* adj, con
       smem = plan_smem(ctx, nb[k], &fa.sl, false);
       if (smem <= 0 || smem > ctx->smem_optin) return GDSS_E_UNSUPPORTED;
       void (*kf)(const FusedArgs) = tce ? fused_layers_kernel<256, false, 2, true> : fused_layers_kernel<256, false, 2>;
-      e = cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      if (e != cudaSuccess) return (int)e;
+      if (int rc_ = ensure_smem((const void*)kf, smem)) return rc_;
       kf<<<B, 256, smem, ks>>>(fa);
     }
     count_launch();
@@ -2658,8 +2653,7 @@ int launch_eval_fused(const gdss_ctx* ctx, const float* x, const float* adj, con
     ta.out = score_x; ta.flags = flags; ta.N = N; ta.fdim = p.fdim; ta.H = 2 * p.fdim; ta.Hs = p.Hp;
     ta.neff = neff; ta.B = B; ta.F = ctx->F; ta.foutp = p.foutp;
     ta.nmap = reinterpret_cast<const int*>(ws + w.off[R_NMAP]);
-    e = cudaFuncSetAttribute(xfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xsm);
-    if (e != cudaSuccess) return (int)e;
+    if (int rc_ = ensure_smem((const void*)xfn, xsm)) return rc_;
     const int64_t tiles = ((int64_t)B * N + 127) / 128;
     int grid = ctx->num_sms > 0 ? ctx->num_sms : 148;
     if ((int64_t)grid > tiles) grid = (int)tiles;
@@ -2700,8 +2694,7 @@ int launch_eval_fused(const gdss_ctx* ctx, const float* x, const float* adj, con
     if (tfn && max_tiles > 0) {
       const size_t tsm = sizeof(float) * (2 * (size_t)(k1p * np + np * np) + 3 * np + 128 * (size_t)(tns - 1)) + 256;
       if ((int)tsm <= ctx->smem_optin) {
-        e = cudaFuncSetAttribute(tfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsm);
-        if (e != cudaSuccess) return (int)e;
+        if (int rc_ = ensure_smem((const void*)tfn, tsm)) return rc_;
         int grid = ctx->num_sms > 0 ? ctx->num_sms : 148;
         if ((int64_t)grid > max_tiles) grid = (int)max_tiles;
         int* errflag = reinterpret_cast<int*>(ws + w.off[R_META]) + 16;
@@ -2720,8 +2713,7 @@ int launch_eval_fused(const gdss_ctx* ctx, const float* x, const float* adj, con
     const size_t fsm = sizeof(float) * (sizeA + (size_t)HP * 128 + 3 * HP);
     if ((int)fsm > ctx->smem_optin) return GDSS_E_UNSUPPORTED;
     if (fsm > 48 * 1024) {
-      e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsm);
-      if (e != cudaSuccess) return (int)e;
+      if (int rc_ = ensure_smem((const void*)fn, fsm)) return rc_;
     }
     if (max_tiles > 0) {
       fn<<<(unsigned)max_tiles, 256, fsm, st>>>(ta);
@@ -2762,8 +2754,7 @@ int launch_final_tc_dense(const gdss_ctx* ctx, const float* stack, int64_t s_bs,
   final_tc_fn tfn = pick_final_tc(p.fdim, &np, &k1p, &tns);
   if (!tfn) return GDSS_E_UNSUPPORTED;
   const size_t tsm = final_tc_smem(np, k1p, tns);
-  cudaError_t e = cudaFuncSetAttribute(tfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsm);
-  if (e != cudaSuccess) return (int)e;
+  if (int rc_ = ensure_smem((const void*)tfn, tsm)) return rc_;
   const int64_t max_tiles = ((int64_t)B * (N * (N - 1) / 2) + 127) / 128;
   if (max_tiles <= 0) return 0;
   int grid = ctx->num_sms > 0 ? ctx->num_sms : 148;

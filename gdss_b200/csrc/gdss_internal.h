@@ -105,6 +105,8 @@ enum KernelId { K_NEFF = 0, K_POW, K_DEG, K_GCN, K_EDGE, K_NODE, K_FINAL_EDGE, K
                 K_UPDATE, K_MISC, K_MEMOPS, K_FUSED, K_COUNT };
 void prof_tick(int kid, cudaStream_t st);
 bool prof_active();
+// raise a kernel's dynamic shared-memory limit if (and only if) `bytes` exceeds what it was granted before on this device
+int ensure_smem(const void* fn, size_t bytes);
 inline void launched(int kid, cudaStream_t st) { count_launch(); prof_tick(kid, st); }
 
 // fused small-graph path (gdss_fused.cu)

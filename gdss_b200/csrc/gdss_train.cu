@@ -878,13 +878,7 @@ struct Arena {
   }
 };
 
-static int set_smem_attr(const void* fn, size_t bytes) {
-  if (bytes > 48 * 1024) {
-    cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
-    if (e != cudaSuccess) return (int)e;
-  }
-  return 0;
-}
+static int set_smem_attr(const void* fn, size_t bytes) { return ensure_smem(fn, bytes); }
 
 #define TR_NO_TILE 96        // output columns per launch of the linear kernel (wide layers are tiled over their outputs)
 #define TR_K_TILE 128        // input rows per launch of the weight-gradient kernel
