@@ -11,6 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # GDSS_PRECISION=tf32 (read once, at the first call) selects the reduced-precision build of the same sources: single-pass
 # TF32 contractions instead of the 3xTF32 split, raw scores within 3e-2 rel-L2 of the reference instead of 1e-4.  Anything
 # else (the default) is the fp32-parity library.
+PHASE_CORRECTOR, PHASE_PREDICTOR = 1, 2          # include/gdss_b200.h: GDSS_PHASE_*
 PRECISION = "tf32" if os.environ.get("GDSS_PRECISION", "").lower() == "tf32" else "fp32"
 LIB_PATH = os.path.join(_HERE, "csrc", "libgdss_b200_tf32.so" if PRECISION == "tf32" else "libgdss_b200.so")
 if os.environ.get("GDSS_LIB"):          # development only: A/B of two builds of the same ABI (tools/gpu_ab.sh)
@@ -76,6 +77,8 @@ def lib():
         "gdss_score_forward": (C.c_int, [vp, fp, fp, fp, fp, fp, i32, i32, vp, i64, vp]),
         "gdss_sample": (C.c_int, [vp, C.POINTER(SamplerDesc), fp, i32, i32, fp, fp, fp, fp, fp, i32, i32, u64, i64, i64,
                                    fp, fp, fp, vp, i32, vp, i64, vp]),
+        "gdss_solver_phase": (C.c_int, [vp, C.POINTER(SamplerDesc), fp, i32, i32, fp, fp, fp, fp, fp, i32, u64, i64, i64, fp, fp, fp,
+                                         vp, vp, i64, vp]),
         "gdss_dsm_scratch_floats": (i64, [vp, i32]),
         "gdss_dsm_loss": (C.c_int, [vp, fp, fp, fp, fp, fp, i32, i32, fp, i64, fp, vp, i64, vp]),
         "gdss_train_workspace_bytes": (i64, [vp, i32]),

@@ -329,6 +329,7 @@ struct StepPlan {
   void* comm;
   int n_steps;           // Langevin iterations per step (solver.py:126, :138)
   float* x0; float* a0;  // n_steps > 1: the state the corrector phase started from
+  int phases;            // GDSS_PHASE_CORRECTOR | GDSS_PHASE_PREDICTOR (gdss_solver_phase; gdss_sample runs both)
 };
 
 static int enqueue_step(const StepPlan& p, cudaStream_t st) {
@@ -364,7 +365,7 @@ static int enqueue_step(const StepPlan& p, cudaStream_t st) {
     launched(K_UPDATE, st);
     LAUNCH_CHECK();
   } else {
-    if (p.langevin) {
+    if (p.langevin && (p.phases & GDSS_PHASE_CORRECTOR)) {
       const int K = p.n_steps;
       if (K > 1) {
         // solver.py:187-189: the x corrector iterates on (x_k, adj_0), the adjacency corrector on (x_0, adj_k)
@@ -390,11 +391,13 @@ static int enqueue_step(const StepPlan& p, cudaStream_t st) {
         LAUNCH_CHECK();
       }
     }
-    rc = launch_eval(p.ctx, u.x, u.adj, u.flags, u.neff, raw_x, raw_a, B, p.ws, p.w, st, !p.ctx->fused);
-    if (rc) return rc;
-    update_kernel<MODE_PRED><<<ugrid, 256, 0, st>>>(u);
-    launched(K_UPDATE, st);
-    LAUNCH_CHECK();
+    if (p.phases & GDSS_PHASE_PREDICTOR) {
+      rc = launch_eval(p.ctx, u.x, u.adj, u.flags, u.neff, raw_x, raw_a, B, p.ws, p.w, st, !p.ctx->fused);
+      if (rc) return rc;
+      update_kernel<MODE_PRED><<<ugrid, 256, 0, st>>>(u);
+      launched(K_UPDATE, st);
+      LAUNCH_CHECK();
+    }
   }
   advance_kernel<<<1, 1, 0, st>>>(p.step_ptr);
   launched(K_MISC, st);
@@ -406,11 +409,12 @@ static int enqueue_step(const StepPlan& p, cudaStream_t st) {
 
 using namespace gdss;
 
-extern "C" int gdss_sample(gdss_ctx* ctx, const gdss_sampler_desc* s, const gdss_step_coef* table, int32_t first_step,
-                           int32_t n_iters, float* x, float* adj, const float* flags, float* x_mean, float* adj_mean,
-                           int32_t B, int32_t init_prior, uint64_t seed, int64_t graph_offset, int64_t global_B,
-                           const float* inj_x, const float* inj_adj, float* trace, void* nccl_comm, int32_t use_graph,
-                           void* workspace, int64_t workspace_bytes, void* stream) {
+// phases / single_row / sums_out: gdss_solver_phase (one phase of ONE step: `table` then points at that step's row alone)
+static int sample_impl(gdss_ctx* ctx, const gdss_sampler_desc* s, const gdss_step_coef* table, int32_t first_step,
+                       int32_t n_iters, float* x, float* adj, const float* flags, float* x_mean, float* adj_mean,
+                       int32_t B, int32_t init_prior, uint64_t seed, int64_t graph_offset, int64_t global_B,
+                       const float* inj_x, const float* inj_adj, float* trace, void* nccl_comm, int32_t use_graph,
+                       void* workspace, int64_t workspace_bytes, void* stream, int phases, bool single_row, float* sums_out) {
   if (!ctx || !s || !table || !x || !adj || !flags || !x_mean || !adj_mean || !workspace) return GDSS_E_BADARG;
   if (B <= 0 || n_iters < 0 || first_step < 0 || first_step + n_iters > GDSS_MAX_STEPS) return GDSS_E_BADARG;
   if (!ctx->has_x || !ctx->has_a) return GDSS_E_BADARG;
@@ -443,6 +447,8 @@ extern "C" int gdss_sample(gdss_ctx* ctx, const gdss_sampler_desc* s, const gdss
   p.n_steps = langevin ? s->n_steps : 1;
   p.x0 = reinterpret_cast<float*>(ws + w.off[R_X0]);
   p.a0 = reinterpret_cast<float*>(ws + w.off[R_A0]);
+  p.phases = phases;
+  if (s4 && phases != (GDSS_PHASE_CORRECTOR | GDSS_PHASE_PREDICTOR)) return GDSS_E_BADARG;    // an S4 step is one unit (solver.py:229-278)
   int* neff = reinterpret_cast<int*>(ws + w.off[R_NEFF]);
   gdss_step_coef* dtable = reinterpret_cast<gdss_step_coef*>(ws + w.off[R_TABLE]);
   UpdateArgs& u = p.ua;
@@ -467,7 +473,8 @@ extern "C" int gdss_sample(gdss_ctx* ctx, const gdss_sampler_desc* s, const gdss
   u.corr_draw = 0;
 
   cudaError_t e;
-  e = cudaMemcpyAsync(dtable, table, sizeof(gdss_step_coef) * (size_t)(first_step + n_iters), cudaMemcpyHostToDevice, st);
+  if (single_row) e = cudaMemcpyAsync(dtable + first_step, table, sizeof(gdss_step_coef), cudaMemcpyHostToDevice, st);
+  else e = cudaMemcpyAsync(dtable, table, sizeof(gdss_step_coef) * (size_t)(first_step + n_iters), cudaMemcpyHostToDevice, st);
   if (e != cudaSuccess) return (int)e;
   set_step_kernel<<<1, 1, 0, st>>>(p.step_ptr, first_step);
   launched(K_MISC, st);
@@ -500,6 +507,10 @@ extern "C" int gdss_sample(gdss_ctx* ctx, const gdss_sampler_desc* s, const gdss
   // one captured graph -- the step index is read from device memory, so every replay is identical.
   rc = enqueue_step(p, st);
   if (rc) return rc;
+  if (sums_out) {                            // the four batch sums of the corrector's norms (solver.py:130-132), device to device
+    e = cudaMemcpyAsync(sums_out, p.sums, 4 * sizeof(float), cudaMemcpyDeviceToDevice, st);
+    if (e != cudaSuccess) return (int)e;
+  }
   if (n_iters == 1) return GDSS_OK;
   if (!use_graph) {
     for (int it = 1; it < n_iters; ++it) {
@@ -549,4 +560,23 @@ extern "C" int gdss_sample(gdss_ctx* ctx, const gdss_sampler_desc* s, const gdss
   if (graph) cudaGraphDestroy(graph);
   if (own_stream) cudaStreamDestroy(cs);
   return rc;
+}
+
+extern "C" int gdss_sample(gdss_ctx* ctx, const gdss_sampler_desc* s, const gdss_step_coef* table, int32_t first_step,
+                           int32_t n_iters, float* x, float* adj, const float* flags, float* x_mean, float* adj_mean,
+                           int32_t B, int32_t init_prior, uint64_t seed, int64_t graph_offset, int64_t global_B,
+                           const float* inj_x, const float* inj_adj, float* trace, void* nccl_comm, int32_t use_graph,
+                           void* workspace, int64_t workspace_bytes, void* stream) {
+  return sample_impl(ctx, s, table, first_step, n_iters, x, adj, flags, x_mean, adj_mean, B, init_prior, seed, graph_offset, global_B,
+                     inj_x, inj_adj, trace, nccl_comm, use_graph, workspace, workspace_bytes, stream,
+                     GDSS_PHASE_CORRECTOR | GDSS_PHASE_PREDICTOR, false, nullptr);
+}
+
+extern "C" int gdss_solver_phase(gdss_ctx* ctx, const gdss_sampler_desc* s, const gdss_step_coef* row, int32_t step, int32_t phases,
+                                 float* x, float* adj, const float* flags, float* x_mean, float* adj_mean, int32_t B,
+                                 uint64_t seed, int64_t graph_offset, int64_t global_B, const float* inj_x, const float* inj_adj,
+                                 float* sums4_out, void* nccl_comm, void* workspace, int64_t workspace_bytes, void* stream) {
+  if (phases < 1 || phases > (GDSS_PHASE_CORRECTOR | GDSS_PHASE_PREDICTOR) || step < 0 || step >= GDSS_MAX_STEPS) return GDSS_E_BADARG;
+  return sample_impl(ctx, s, row, step, 1, x, adj, flags, x_mean, adj_mean, B, 0, seed, graph_offset, global_B, inj_x, inj_adj, nullptr,
+                     nccl_comm, 0, workspace, workspace_bytes, stream, phases, true, sums4_out);
 }

@@ -223,6 +223,34 @@ class Engine:
         return (x, adj, xm, am, tr) if trace else (x, adj, xm, am)
 
 
+    def solver_phase(self, sdesc, table, step, phases, x, adj, flags, seed=0, graph_offset=0, global_B=None, inj_x=None,
+                     inj_adj=None, comm=None):
+        """ONE phase of solver step `step` (gdss_solver_phase): phases = _lib.PHASE_CORRECTOR, _lib.PHASE_PREDICTOR or both.
+        x / adj are updated in place (float32, contiguous, on the engine's device); inj_x / inj_adj = this step's draws
+        [draws, B, N, F|N].  -> (x_mean, adj_mean, sums4) with sums4 = the batch sums of the corrector's four norms."""
+        flags = flags.to(self.device, torch.float32).contiguous()
+        B = flags.shape[0]
+        row = np.ascontiguousarray(table[step:step + 1], dtype=np.float32)
+        if not (x.is_cuda and adj.is_cuda) or x.dtype != torch.float32 or adj.dtype != torch.float32 or not x.is_contiguous() \
+                or not adj.is_contiguous():
+            raise ValueError("solver_phase updates x / adj in place: pass contiguous fp32 tensors on the engine's device")
+        with torch.cuda.device(self.device):
+            xm, am = torch.empty_like(x), torch.empty_like(adj)
+            sums = torch.zeros(4, device=self.device)
+            if inj_x is not None:
+                inj_x = inj_x.to(self.device, torch.float32).contiguous()
+                inj_adj = inj_adj.to(self.device, torch.float32).contiguous()
+            ws, need = self.workspace(B)
+            rc = self.L.gdss_solver_phase(self.ctx, C.byref(sdesc), row.ctypes.data, int(step), int(phases), x.data_ptr(),
+                                          adj.data_ptr(), flags.data_ptr(), xm.data_ptr(), am.data_ptr(), B,
+                                          int(seed) & (2 ** 64 - 1), int(graph_offset), int(global_B if global_B is not None else B),
+                                          inj_x.data_ptr() if inj_x is not None else None,
+                                          inj_adj.data_ptr() if inj_adj is not None else None, sums.data_ptr(), comm,
+                                          ws.data_ptr(), need, self._stream())
+            check(rc, "gdss_solver_phase")
+        return xm, am, sums
+
+
 def make_sampler_desc(sde_x, sde_adj, predictor, corrector, snr, scale_eps, eps, n_steps, probability_flow, denoise):
     from .sde import sde_params
     d = SamplerDesc()

@@ -167,6 +167,20 @@ int gdss_sample(gdss_ctx* ctx, const gdss_sampler_desc* s, const gdss_step_coef*
                 const float* inj_x, const float* inj_adj, float* trace, void* nccl_comm, int32_t use_graph,
                 void* workspace, int64_t workspace_bytes, void* stream);
 
+/* gdss_solver_phase: ONE phase of ONE solver step -- the corrector's update_fn pair (LangevinCorrector.update_fn, solver.py:113-149,
+ * as pc_sampler calls it at :183-189) or the predictor's (ReverseDiffusionPredictor / EulerMaruyamaPredictor.update_fn,
+ * solver.py:45-89, called at :190-193), or both (= what gdss_sample runs per step).  `row` = the coefficient row of step
+ * `step` (host); x / adj are updated in place, x_mean / adj_mean are written by the predictor phase (initialised to the state);
+ * the noise draws are those of gdss_sample for that step (Philox keyed by seed / graph / step / draw, or inj_x / inj_adj =
+ * [draws][B][N][F|N] of this step).  sums4_out (device, optional): the batch sums of the four corrector norms.  S4 steps are one
+ * unit (phases must be CORRECTOR | PREDICTOR).  Enqueues on `stream`, no host synchronisation. */
+#define GDSS_PHASE_CORRECTOR 1
+#define GDSS_PHASE_PREDICTOR 2
+int gdss_solver_phase(gdss_ctx* ctx, const gdss_sampler_desc* s, const gdss_step_coef* row, int32_t step, int32_t phases,
+                      float* x, float* adj, const float* flags, float* x_mean, float* adj_mean, int32_t B, uint64_t seed,
+                      int64_t graph_offset, int64_t global_B, const float* inj_x, const float* inj_adj, float* sums4_out,
+                      void* nccl_comm, void* workspace, int64_t workspace_bytes, void* stream);
+
 /* ---- denoising-score-matching loss, forward only -----------------------------------------------
  * Replaces loss_fn of losses.py:37-81 (likelihood_weighting = False) as the trainer's evaluation loop calls it under
  * torch.no_grad() (trainer.py:84-99): flags = node_flags(adj), z = gen_noise from the supplied raw N(0,1) draws

@@ -149,6 +149,43 @@ def test_full_1000_step_runs_match_reference(name):
     assert torch.equal((xm > 0.5).cpu(), gx > 0.5), name
 
 
+@pytest.mark.parametrize("name", ["zinc250k_v2", "community_small"])
+def test_solver_phase_by_phase_equals_the_whole_step(name):
+    """gdss_solver_phase: the corrector phase followed by the predictor phase of a step, each through its own call,
+    leaves exactly the state, the means and the batch sums that one whole step of gdss_sample leaves (same Philox draws: they are
+    keyed by seed / graph / step / draw) -- and a phase alone differs from the whole step."""
+    from gdss_b200 import _lib
+    from gdss_b200.engine import Engine, make_sampler_desc
+    from gdss_b200.schedule import build_table
+    from gdss_b200.sde import VPSDE, VESDE
+    ck = load_golden_ckpt(name)
+    N, F = int(ck["params_adj"]["max_node_num"]), int(ck["params_adj"]["max_feat_num"])
+    if name == "zinc250k_v2":
+        sx, sa, pred, snr, seps = VPSDE(.1, 1., 1000), VESDE(.2, 1., 1000), "Reverse", .2, .8
+    else:
+        sx, sa, pred, snr, seps = VPSDE(.1, 1., 1000), VPSDE(.1, 1., 1000), "Euler", .05, .7
+    table = build_table(sx, sa, pred, "Langevin", snr, seps, 1e-4)
+    sdesc = make_sampler_desc(sx, sa, pred, "Langevin", snr, seps, 1e-4, 1, False, True)
+    B = 6
+    g = torch.Generator().manual_seed(3)
+    counts = torch.tensor([N, N - 1, max(2, N // 2), 5, 2, max(3, 2 * N // 3)])
+    flags = (torch.arange(N)[None, :] < counts[:, None]).float()
+    x0 = torch.randn(B, N, F, generator=g) * flags[:, :, None]
+    a0 = torch.randn(B, N, N, generator=g).triu(1)
+    a0 = (a0 + a0.transpose(1, 2)) * flags[:, :, None] * flags[:, None, :]
+    eng = Engine(ck["x_state_dict"], ck["adj_state_dict"], N, "cuda")
+    step, seed = 417, 99
+    wx, wa, wxm, wam = eng.sample(sdesc, table, flags, x=x0, adj=a0, first_step=step, n_iters=1, seed=seed, use_graph=False)
+    x, a = x0.cuda().clone(), a0.cuda().clone()
+    _, _, sums = eng.solver_phase(sdesc, table, step, _lib.PHASE_CORRECTOR, x, a, flags, seed=seed)
+    assert float(sums.min()) > 0 and not torch.equal(x, wx)                     # the corrector alone is not the whole step
+    xm, am, _ = eng.solver_phase(sdesc, table, step, _lib.PHASE_PREDICTOR, x, a, flags, seed=seed)
+    assert torch.equal(x, wx) and torch.equal(a, wa) and torch.equal(xm, wxm) and torch.equal(am, wam)
+    x2, a2 = x0.cuda().clone(), a0.cuda().clone()
+    xm2, am2, _ = eng.solver_phase(sdesc, table, step, _lib.PHASE_CORRECTOR | _lib.PHASE_PREDICTOR, x2, a2, flags, seed=seed)
+    assert torch.equal(x2, wx) and torch.equal(am2, wam)
+
+
 def test_tensor_helpers_match_oracle():
     from gdss_b200 import graph_utils as G
     g = torch.Generator().manual_seed(3)
