@@ -2,13 +2,13 @@
 # tcgen05 per-edge MLP of the per-graph kernel: smoke first (small batch, bounded waits), then parity tests, then the A/B bench
 set -u
 out=gpurun_out; mkdir -p $out
-timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $out/tce_smoke.log 2>&1; rc=$?
+GDSS_TCEDGE=1 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $out/tce_smoke.log 2>&1; rc=$?
 tail -3 $out/tce_smoke.log; echo "smoke rc=$rc"
 if [ $rc -ne 0 ]; then
-  GDSS_NO_TCEDGE=1 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
+  timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
   exit 0
 fi
-(timeout 1200 python -m pytest tests -m gpu -q -x --timeout 900 > $out/tests.log 2>&1; echo "pytest rc=$?" >> $out/tests.log)
+(GDSS_TCEDGE=1 timeout 1200 python -m pytest tests -m gpu -q -x --timeout 900 > $out/tests.log 2>&1; echo "pytest rc=$?" >> $out/tests.log)
 tail -6 $out/tests.log
 Q="--no-extra --no-cpu-baseline --no-torch-baseline"
 show() { python - "$1" <<'PY'
@@ -20,6 +20,6 @@ try:
 except Exception as e: print(sys.argv[1], "failed", e)
 PY
 }
-timeout 600 python bench.py $Q > $out/tce_on.json 2> $out/tce_on.err; show $out/tce_on.json
-GDSS_NO_TCEDGE=1 timeout 600 python bench.py $Q > $out/tce_off.json 2> $out/tce_off.err; show $out/tce_off.json
-timeout 300 python tools/phase_prof.py zinc250k_v2 2960 > $out/phase_zinc_tce.txt 2>&1; cat $out/phase_zinc_tce.txt
+GDSS_TCEDGE=1 timeout 600 python bench.py $Q > $out/tce_on.json 2> $out/tce_on.err; show $out/tce_on.json
+timeout 600 python bench.py $Q > $out/tce_off.json 2> $out/tce_off.err; show $out/tce_off.json
+GDSS_TCEDGE=1 timeout 300 python tools/phase_prof.py zinc250k_v2 2960 > $out/phase_zinc_tce.txt 2>&1; cat $out/phase_zinc_tce.txt
