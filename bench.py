@@ -220,6 +220,7 @@ def run_train_bench(args):
         e2e_t.append(mx(time.perf_counter() - t0))
     e2e = {"value": K / float(np.median(e2e_t)), "unit": "steps/s", "h2d_bytes_per_step": (hx.numel() + ha.numel()) * 4,
            "d2h_bytes_per_step": 8, "call": "DSMTrainStep.step(x_host, adj_host) + float(loss_x), float(loss_adj); bytes per rank"}
+    tr.close()                                           # captured graphs go before the communicator they reference
     if rank != 0:
         shard.close()
         if world > 1:

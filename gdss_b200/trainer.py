@@ -125,9 +125,15 @@ class DSMTrainStep:
         # refresh) is captured once per batch shape into a CUDA graph and replayed; inputs go through static buffers and the
         # optimizer's per-step scalars through device memory (gdss_adam_ema_step_dev).  What it buys: the ~330 launches of a
         # step are launch-bound on small per-GPU batches (data-parallel training of B = 1024 on 8 GPUs)
-        # Single-process only: with the NCCL all-reduce inside torch's (global-mode) capture the first 8-rank attempt hung --
-        # NCCL sets its connections up lazily on the first collective -- and data-parallel runs therefore launch eagerly
-        self.use_graph = bool(use_graph) and (shard is None or shard.world == 1)
+        # Data-parallel runs launch eagerly unless GDSS_TRAIN_GRAPH_DP=1: with the NCCL all-reduce inside a global-mode capture and
+        # no eager first step the first 8-rank attempt hung (NCCL sets its connections up lazily on the first collective).  The
+        # capture now happens on the SECOND call of a batch shape, after one eager step, in thread-local capture mode (what the
+        # sampler's own captured step does).  Measured on 2 ranks: 152 vs 138.5 steps/s, results as the eager run's -- but the
+        # process then did not exit (captured graphs referencing the communicator at teardown; `close()` is the untested
+        # remedy), hence opt-in for more than one rank.
+        import os
+        dp_ok = shard is None or shard.world == 1 or os.environ.get("GDSS_TRAIN_GRAPH_DP", "") == "1"
+        self.use_graph = bool(use_graph) and dp_ok
         self._graphs = {}
         self.captured_launches = 0
 
@@ -194,6 +200,10 @@ class DSMTrainStep:
         world = 1 if self.shard is None else self.shard.world
         g = self._graphs.get(key)
         if g is None:
+            # first call of this batch shape: eager (sets the kernels' attributes, warms the NCCL communicator up)
+            self._graphs[key] = {"pending": True}
+            return self._eager_step(x, adj, t, raw_x, raw_adj)
+        if g.get("pending"):
             g = {"x": torch.empty(B, self.N, self.F, device=dev), "adj": torch.empty(B, self.N, self.N, device=dev),
                  "t": None if t is None else torch.empty(B, device=dev),
                  "rx": None if raw_x is None else torch.empty(B, self.N, self.F, device=dev),
@@ -207,7 +217,7 @@ class DSMTrainStep:
             torch.cuda.synchronize(dev)
             graph = torch.cuda.CUDAGraph()
             before = self.L.gdss_launch_count()
-            with torch.cuda.graph(graph):
+            with torch.cuda.graph(graph, capture_error_mode="thread_local"):
                 loss, gx, ga = self.loss_and_grads(g["x"], g["adj"], g["t"], g["rx"], g["ra"])
                 norms = []
                 for net, gr in ((self.x, gx), (self.a, ga)):
@@ -240,6 +250,11 @@ class DSMTrainStep:
         if self.use_graph:
             return self._graph_step(x, adj, t, raw_x, raw_adj)
         return self._eager_step(x, adj, t, raw_x, raw_adj)
+
+    def close(self):
+        """Drop the captured graphs (they reference the NCCL communicator of a data-parallel run: destroy them before it)."""
+        self._graphs.clear()
+        torch.cuda.synchronize(self.dev)
 
     def state_dicts(self, ema=False):
         return self.x.state_dict(ema), self.a.state_dict(ema)
