@@ -8,8 +8,9 @@ and the forward half of a training step.  The time draw and the two Gaussian dra
 in the same order, as the reference (``torch.rand`` for t, ``torch.randn_like`` for z_x then z_adj), so under the same
 seed on the same device the closure sees the reference's own random numbers; everything after that (node flags, noise
 masking / symmetrisation, perturbation, both score networks, the per-graph reduction and the batch mean) runs in the
-CUDA library (``gdss_dsm_loss``).  The returned tensors carry no autograd graph: the backward pass / optimizer step of
-trainer.py:57-79 is not built yet and ``loss.backward()`` raises.
+CUDA library (``gdss_dsm_loss``).  The returned tensors carry no autograd graph (this is the loss the trainer evaluates under
+``no_grad``, trainer.py:84-99); the loop body trainer.py:57-79 -- both losses WITH their parameter gradients, clip, Adam, EMA -- is
+``gdss_b200.trainer.DSMTrainStep``.
 """
 import torch
 

@@ -3,8 +3,8 @@ format (models/ScoreNetwork_X.py, models/ScoreNetwork_A.py, models/attention.py,
 whose forward pass is ONE call into the CUDA library -- these modules only hold parameters.
 
 ``state_dict()`` keys are identical to the reference's (``layers.{l}.attn.{c}.gnn_q.weight`` ...),
-so ``load_state_dict`` accepts the shipped ``.pth`` checkpoints unchanged.  Inference only: the
-forward is not differentiable (the DSM training step is SURVEY.md 8f, not built yet)."""
+so ``load_state_dict`` accepts the shipped ``.pth`` checkpoints unchanged.  The forward carries no
+autograd graph: training goes through ``gdss_b200.trainer.DSMTrainStep`` (hand-written backward)."""
 import math
 
 import torch

@@ -7,7 +7,8 @@ parameter vector per network:
 as two CUDA launches (gdss_adam_ema_step).  Data parallel: ``allreduce_grads`` sums the flat gradient over the ranks with
 NCCL first (the clip must see the global gradient); ``grad_scale = 1 / world`` turns the sum into the batch mean.
 
-The backward pass that fills ``grad`` is not built yet: this module is the verified tail of the step.
+The gradients come from ``gdss_dsm_loss_backward`` (``gdss_b200.trainer.DSMTrainStep`` wires the three calls together) or from
+the reference's own autograd; ``advance`` / ``enqueue_dev`` are the same step for a CUDA-graph replay (per-step scalars on the device).
 """
 import ctypes as C
 
