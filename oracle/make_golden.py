@@ -19,6 +19,8 @@ Produces
                                   samples, training graphs) for the statistical parity test
   tests/golden/c1_mmd_reference.npz  the reference's own evaluation/stats.py (degree / cluster / orbit / spectral MMD, ORCA orbit
                                   counts) on that run (mode `mmd`)
+  tests/golden/nspdk_reference.npz  the reference's own NSPDK MMD (evaluation/mmd.py compute_nspdk_mmd over evaluation/eden.py) on the
+                                  molecule graphs of the C2 / C3 reference runs (mode `nspdk`)
   tests/golden/dsm_<ckpt>_<sum|mean>.npz  loss_fn of losses.py:37-81 on a synthetic batch with recorded t / noise draws
   tests/golden/MANIFEST.json      what was generated, from which torch version
 
@@ -631,6 +633,66 @@ def make_mmd_reference():
     return res
 
 
+def _mol_nx(graphs, symbols):
+    """utils/mol_utils.py:161-183 `mols_to_nx` on (atomic numbers, bond orders): node label = the atom's symbol as sampler.py
+    has it (symbols=True) or its atomic number (an integer label: Python's hash of it does not depend on PYTHONHASHSEED)."""
+    import networkx as nx
+    sym = {6: "C", 7: "N", 8: "O", 9: "F", 15: "P", 16: "S", 17: "Cl", 35: "Br", 53: "I"}
+    out = []
+    for lab, b in graphs:
+        g = nx.Graph()
+        for i, z in enumerate(lab):
+            g.add_node(i, label=sym[int(z)] if symbols else int(z))
+        for i in range(len(lab)):
+            for j in range(i + 1, len(lab)):
+                if b[i, j]:
+                    g.add_edge(i, j, label=int(b[i, j]))
+        out.append(g)
+    return out
+
+
+def _nspdk_halves(tag):
+    from oracle import stats as OS
+    z = np.load(os.path.join(GOLD, f"stats_{tag}_reference.npz"))
+    gs = [g for g in OS.mol_graphs(z["atoms"], z["bonds"], OS.QM9_ATOMS if tag == "qm9" else OS.ZINC_ATOMS) if len(g[0]) > 0]
+    return gs[:len(gs) // 2], gs[len(gs) // 2:]
+
+
+def nspdk_symbol_run(tag):
+    """one process = one PYTHONHASHSEED: the reference's NSPDK MMD with atom-symbol labels, as sampler.py:151 evaluates it."""
+    import evaluation.mmd as M
+    a, b = _nspdk_halves(tag)
+    print(repr(float(M.compute_nspdk_mmd(_mol_nx(a, True), _mol_nx(b, True), metric="nspdk", is_hist=False, n_jobs=1))))
+
+
+def make_nspdk_reference():
+    """The reference's own NSPDK MMD (evaluation/mmd.py:115-127 `compute_nspdk_mmd` over evaluation/eden.py `vectorize`, run
+    UNMODIFIED) on the molecule graphs of the C2 / C3 reference runs (tests/golden/stats_*_reference.npz, decoded as
+    utils/mol_utils.py `construct_mol` reads them, first half of the run against the second half):
+      * with integer node labels (atomic numbers): value + the feature vectors of the first graphs -> pins oracle/stats.py exactly;
+      * with the atom-symbol labels sampler.py uses, in three processes with PYTHONHASHSEED 0 / 1 / 2: the label -> code map and
+        with it the 16-bit feature collisions change from process to process; the spread is the reference's own noise floor."""
+    import subprocess
+    import evaluation.mmd as M
+    from evaluation.eden import vectorize
+    out, arrays = {}, {}
+    for tag in ("qm9", "zinc_v2"):
+        a, b = _nspdk_halves(tag)
+        val = float(M.compute_nspdk_mmd(_mol_nx(a, False), _mol_nx(b, False), metric="nspdk", is_hist=False, n_jobs=1))
+        feats = vectorize(_mol_nx(a[:6], False), complexity=4, discrete=True).tocsr()
+        sym = []
+        for seed in ("0", "1", "2"):
+            r = subprocess.run([sys.executable, os.path.abspath(__file__), "nspdk_symbols", tag], capture_output=True, text=True,
+                               check=True, env=dict(os.environ, PYTHONHASHSEED=seed))
+            sym.append(float(r.stdout.strip().splitlines()[-1]))
+        arrays.update({f"{tag}_mmd_int": val, f"{tag}_mmd_symbols": np.array(sym), f"{tag}_n": np.array([len(a), len(b)]),
+                       f"{tag}_feat_indptr": feats.indptr.astype(np.int32), f"{tag}_feat_indices": feats.indices.astype(np.int32),
+                       f"{tag}_feat_data": feats.data})
+        out[tag] = {"mmd_int_labels": val, "mmd_symbol_labels_hashseed_0_1_2": sym, "graphs": [len(a), len(b)]}
+    np.savez_compressed(os.path.join(GOLD, "nspdk_reference.npz"), **arrays)
+    return out
+
+
 def only(which):
     """python oracle/make_golden.py decode | c1 | dsm | mol | dsmgrad | train : just one of the small fixtures."""
     refimport.activate()
@@ -656,6 +718,11 @@ def only(which):
     elif which == "mmd":
         manifest["c1_mmd"] = make_mmd_reference()
         print(manifest["c1_mmd"])
+    elif which == "nspdk":
+        manifest["nspdk"] = make_nspdk_reference()
+        print(manifest["nspdk"])
+    elif which == "nspdk_symbols":
+        return nspdk_symbol_run(sys.argv[2])
     elif which == "traj_new":
         manifest["traj"].update(make_traj(missing_only=True))
     else:
@@ -666,4 +733,4 @@ def only(which):
 
 
 if __name__ == "__main__":
-    only(sys.argv[1]) if sys.argv[1:] in (["decode"], ["c1"], ["dsm"], ["mol"], ["dsmgrad"], ["train"], ["traj_new"], ["segs"], ["segs_ref"], ["layers"], ["mmd"]) else main()
+    only(sys.argv[1]) if sys.argv[1:2] in (["decode"], ["c1"], ["dsm"], ["mol"], ["dsmgrad"], ["train"], ["traj_new"], ["segs"], ["segs_ref"], ["layers"], ["mmd"], ["nspdk"], ["nspdk_symbols"]) else main()

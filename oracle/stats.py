@@ -4,7 +4,8 @@ Restatement of the degree MMD of the reference's evaluation (evaluation/stats.py
 evaluation/mmd.py:16-29 `emd`, :37-45 `gaussian_emd`, :73-100 `disc` / `compute_mmd`) on thresholded dense adjacency
 tensors instead of networkx graphs.  The reference computes the earth mover's distance with `pyemd` (not installed
 here) on a Toeplitz ground distance |i - j|; for 1-D histograms with that ground distance the EMD is the L1 distance of
-the two CDFs, which is what `emd1d` computes (unit-mass pmfs of equal length)."""
+the two CDFs, which is what `emd1d` computes (unit-mass pmfs of equal length).  Further down: clustering / spectral / orbit
+MMD (pinned by tests/golden/c1_mmd_reference.npz) and the NSPDK MMD of molecule graphs (tests/golden/nspdk_reference.npz)."""
 import numpy as np
 
 
@@ -204,3 +205,147 @@ def eval_graph_lists(adjs_ref, adjs_pred):
            "cluster": clustering_mmd(adjs_ref, cr, adjs_pred, cp), "orbit": orbit_mmd(adjs_ref, adjs_pred),
            "spectral": spectral_mmd(adjs_ref, cr, adjs_pred, cp)}
     return {k: round(float(v), 6) for k, v in res.items()}
+
+
+# ---- NSPDK MMD (evaluation/stats.py:231-241 `nspdk_stats`, evaluation/mmd.py:115-127 `compute_nspdk_mmd`, evaluation/eden.py
+# `vectorize(graphs, complexity=4, discrete=True)`): the neighbourhood-subgraph pairwise-distance kernel of EDeN as the
+# reference vendors it, restated on (labels [n], bond orders [n,n]) arrays instead of networkx graphs.  The reference hashes
+# with Python's builtin `hash` of int tuples (deterministic) and of the LABEL itself (evaluation/eden.py:943-948).  sampler.py
+# labels atoms with their symbol string (utils/mol_utils.py:161-183), whose hash changes from process to process; here a label
+# is an integer (the atomic number; bond order for an edge), for which hash(v) = v.  The kernel value of two graphs does not
+# depend on the label -> code map except through collisions in the 2^16-entry feature space, so the restatement is pinned
+# EXACTLY against the reference run on integer-labelled graphs and to the collision noise against the string-labelled run
+# (tests/golden/nspdk_reference.npz).
+_NSPDK_BITS = 16                                     # Vectorizer(nbits=16): evaluation/eden.py:160, :245-246
+_NSPDK_MASK = (1 << _NSPDK_BITS) - 1                 # labels and feature ids
+_NSPDK_MASK32 = 4294967295                           # evaluation/eden.py:22: the default mask of the neighbourhood hashes
+
+
+def _h(mask, *items):
+    """fast_hash_2 / _3 / _4 / fast_hash (evaluation/eden.py:57-70)."""
+    return int(hash(tuple(items)) & mask) + 1
+
+
+def _expanded(labels, bonds):
+    """evaluation/eden.py:951-977 `_edge_to_vertex_transform` + :943-948 `_label_preprocessing`: one extra vertex per edge
+    (self loops dropped), joined to its two endpoints.  -> (hashed label per vertex, neighbour lists, number of atom vertices)."""
+    labels = [int(v) for v in labels]
+    b = np.asarray(bonds)
+    n = len(labels)
+    hlabel = [int(hash(v) & _NSPDK_MASK) + 1 for v in labels]
+    nbr = [[] for _ in range(n)]
+    for u in range(n):
+        for v in range(u + 1, n):
+            if b[u, v] != 0:
+                w = len(nbr)
+                nbr.append([u, v])
+                nbr[u].append(w)
+                nbr[v].append(w)
+                hlabel.append(int(hash(int(b[u, v])) & _NSPDK_MASK) + 1)
+    return hlabel, nbr, n
+
+
+def _levels(nbr, root, max_depth):
+    """evaluation/eden.py:730-763: breadth-first levels of the expanded graph around `root`, up to `max_depth`."""
+    seen = {root}
+    levels = [[root]]
+    while len(levels) <= max_depth:
+        nxt = []
+        for u in levels[-1]:
+            for v in nbr[u]:
+                if v not in seen:
+                    seen.add(v)
+                    nxt.append(v)
+        if not nxt:
+            break
+        levels.append(nxt)
+    return levels
+
+
+def nspdk_features(labels, bonds, complexity=4):
+    """One graph -> {feature id: value}, both normalisations on (evaluation/eden.py:421-430 `_transform`, :438-453, :547-616,
+    :618-650).  Vertices of the expanded graph alternate atom / bond, so distance and radius step by 2."""
+    hlabel, nbr, n = _expanded(labels, bonds)
+    if n == 0:
+        raise ValueError("empty graph (evaluation/eden.py:368-370)")
+    r = d = complexity
+    levels, nhash = [], []
+    for root in range(n):
+        lv = _levels(nbr, root, 2 * max(r, d))
+        levels.append(lv)
+        # evaluation/eden.py:658-689: per level the sorted multiset of hash(label, degree), hashed; then the running hash of
+        # the level sequence (fast_hash_vec :73-79) -> one code per radius
+        codes, run = [], 0xAAAAAAAA
+        for k, level in enumerate(lv):
+            item = _h(_NSPDK_MASK32, *sorted(_h(_NSPDK_MASK32, hlabel[v], len(nbr[v])) for v in level))
+            run ^= hash((run, item, k))
+            codes.append(int(run & _NSPDK_MASK32) + 1)
+        nhash.append(codes)
+    blocks = {}                                          # (radius / 2, distance / 2) -> {feature: count}, in first-use order
+    for v in range(n):
+        for dist in range(0, 2 * (d + 1), 2):
+            if dist >= len(levels[v]):
+                continue
+            for u in levels[v][dist]:
+                for rad in range(0, 2 * (r + 1), 2):
+                    if rad < len(nhash[v]) and rad < len(nhash[u]):
+                        hv, hu = nhash[v][rad], nhash[u][rad]
+                        blk = blocks.setdefault((rad // 2, dist // 2), {})
+                        full = _h(_NSPDK_MASK, min(hv, hu), max(hv, hu), rad, dist)
+                        blk[full] = blk.get(full, 0.0) + 1.0
+                        half = _h(_NSPDK_MASK, hu, rad, dist)                    # the context feature that ignores the centre vertex
+                        blk[half] = blk.get(half, 0.0) + 1.0
+    vec = {}
+    for blk in blocks.values():                          # a feature id met again in a later block REPLACES the earlier value
+        norm = np.sqrt(sum(c * c for c in blk.values()))
+        for f, c in blk.items():
+            vec[f] = float(c) / norm
+    total = np.sqrt(sum(v * v for v in vec.values()))
+    return {f: v / total for f, v in vec.items()}
+
+
+def nspdk_matrix(graphs, complexity=4):
+    """graphs: list of (labels [n], bonds [n,n]) -> sparse [G, 2^16 + 1] feature matrix (evaluation/eden.py:372-390)."""
+    from scipy.sparse import csr_matrix
+    data, row, col = [], [], []
+    for i, (labels, bonds) in enumerate(graphs):
+        for f, v in nspdk_features(labels, bonds, complexity).items():
+            row.append(i)
+            col.append(f)
+            data.append(v)
+    return csr_matrix((data, (row, col)), shape=(len(graphs), _NSPDK_MASK + 2), dtype=np.float64)
+
+
+def nspdk_mmd(graphs_ref, graphs_pred, with_unbiased=False):
+    """evaluation/mmd.py:115-127 with the linear kernel on the NSPDK vectors; graphs without nodes are dropped from the
+    generated list as evaluation/stats.py:232 does.  The reference's number averages the kernel matrices WITH their diagonals
+    (every vector has unit norm), so two lists drawn from one distribution still give about (1 / m + 1 / n) (1 - mean kernel).
+    with_unbiased: also return the same statistic without the diagonals, which is 0 in expectation for one distribution --
+    what a sample-against-sample parity check can put a threshold on."""
+    x = nspdk_matrix(graphs_ref)
+    y = nspdk_matrix([g for g in graphs_pred if len(g[0]) > 0])
+    kxx, kyy, kxy = (x @ x.T).toarray(), (y @ y.T).toarray(), (x @ y.T).toarray()
+    val = float(np.mean(kxx) + np.mean(kyy) - 2 * np.mean(kxy))
+    if not with_unbiased:
+        return val
+    m, n = kxx.shape[0], kyy.shape[0]
+    ub = (kxx.sum() - np.trace(kxx)) / (m * (m - 1)) + (kyy.sum() - np.trace(kyy)) / (n * (n - 1)) - 2 * np.mean(kxy)
+    return val, float(ub)
+
+
+QM9_ATOMS = (6, 7, 8, 9)                                 # utils/mol_utils.py:56 / :58 without the virtual-atom entry
+ZINC_ATOMS = (6, 7, 8, 9, 15, 16, 17, 35, 53)
+
+
+def mol_graphs(atoms, bonds, atomic_numbers):
+    """atoms [B,N,F] in {0,1} (x > 0.5), bonds [B,N,N] bond orders 0..3 (quantize_mol) -> list of (atomic numbers [n], bond
+    orders [n,n]) the way utils/mol_utils.py:72-90 `construct_mol` reads them: atom type = argmax over [x, 1 - sum x] (the last
+    entry = no atom: dropped), bonds among the atoms that exist.  RDKit's valency correction / largest-fragment step that
+    follows in gen_mol is NOT applied (RDKit is absent here)."""
+    atoms, bonds = np.asarray(atoms).astype(np.int64), np.asarray(bonds).astype(np.int64)
+    out = []
+    for a, b in zip(atoms, bonds):
+        t = np.argmax(np.concatenate([a, 1 - a.sum(axis=1, keepdims=True)], axis=1), axis=1)
+        keep = t != a.shape[1]
+        out.append((np.asarray(atomic_numbers)[t[keep]], b[np.ix_(keep, keep)]))
+    return out
