@@ -33,6 +33,9 @@ def ema_weights(sd, ema):
     shadow = ema["shadow_params"]
     if len(shadow) != len(sd):
         raise ValueError("EMA shadow parameters do not match the state_dict")
+    for k, s in zip(sd.keys(), shadow):
+        if tuple(s.shape) != tuple(sd[k].shape):
+            raise ValueError(f"EMA shadow parameter of {k} has shape {tuple(s.shape)}, the state_dict has {tuple(sd[k].shape)}")
     return {k: s.detach().to(torch.float32) for k, s in zip(sd.keys(), shadow)}
 
 

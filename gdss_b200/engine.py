@@ -27,6 +27,14 @@ def model_state(model):
     return _strip(model.state_dict())
 
 
+def resolve_device(device):
+    """'cuda' / 'cuda:1' / torch.device -> a torch.device with an explicit index (the current device for a bare 'cuda')."""
+    dev = torch.device(device)
+    if dev.type == "cuda" and dev.index is None:
+        dev = torch.device("cuda", torch.cuda.current_device())
+    return dev
+
+
 def describe_network(sd, n_nodes):
     """Infer the constructor arguments (utils/loader.py:150-165 params dict) from the tensor shapes
     of a state_dict (key grammar: SURVEY.md 8b).  -> NetDesc"""
@@ -99,7 +107,8 @@ def pack_network(sd, n_nodes, desc=None, model=None):
         raise _lib.GdssError(f"num_heads={heads} is not supported (the kernels are built for num_heads=4)")
     keys = state_keys(desc)
     missing = [k for k in keys if k not in sd]
-    extra = [k for k in sd if k not in set(keys)]
+    known = set(keys)
+    extra = [k for k in sd if k not in known]
     if missing or extra:
         raise _lib.GdssError(f"state_dict does not match the network description: missing {missing[:3]}, unexpected {extra[:3]}")
     tensors = [sd[k].detach().to("cpu", torch.float32).contiguous() for k in keys]

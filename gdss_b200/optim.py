@@ -85,23 +85,24 @@ class FusedAdamEMA:
     # ---- the same step for a captured CUDA graph: the launch (`enqueue_dev`, captured once) reads the four per-step scalars from
     # `self.consts`; `advance()` (every step, before the replay) refreshes them from the host-side step count
     def advance(self):
-        """Bump the step count and copy {lr, bias corrections, EMA factor} of this step to the device (stream-ordered)."""
-        import ctypes as C
+        """Bump the step count and copy {lr, bias corrections, EMA factor} of this step to the device (stream-ordered).
+        Every step stages its scalars in its OWN pinned block: the host runs ahead of the device when steps are replayed
+        back to back, and a single reused staging buffer would be overwritten with a later step's scalars before the queued
+        copy of this step has read it.  (torch's pinned-memory cache recycles a block only after the copies that read it.)"""
         self.step_count += 1
         if not hasattr(self, "consts"):
             self.consts = torch.zeros(4, device=self.p.device)
-            self._consts_host = torch.zeros(4).pin_memory()
+        host = torch.zeros(4, dtype=torch.float32).pin_memory()
         check(self.L.gdss_adam_step_consts(self.lr, self.betas[0], self.betas[1], self.step_count,
                                            float(self.ema_decay if self.ema_decay is not None else 0.0), self.num_updates,
-                                           self._consts_host.data_ptr()), "gdss_adam_step_consts")
-        self.consts.copy_(self._consts_host, non_blocking=True)
+                                           host.data_ptr()), "gdss_adam_step_consts")
+        self.consts.copy_(host, non_blocking=True)
         if self.shadow is not None:
             self.num_updates += 1
 
     def enqueue_dev(self, flat_grads, grad_scale=1.0):
         if not hasattr(self, "consts"):
             self.consts = torch.zeros(4, device=self.p.device)
-            self._consts_host = torch.zeros(4).pin_memory()
         st = torch.cuda.current_stream(self.p.device).cuda_stream
         with torch.cuda.device(self.p.device):
             check(self.L.gdss_adam_ema_step_dev(self.p.data_ptr(), flat_grads.data_ptr(), self.m.data_ptr(), self.v.data_ptr(),

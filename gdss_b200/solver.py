@@ -17,7 +17,7 @@ takes the mean over the WHOLE batch) and the result is gathered on every rank.
 """
 import torch
 
-from .engine import Engine, make_sampler_desc, model_state
+from .engine import Engine, make_sampler_desc, model_state, resolve_device
 from .schedule import build_table
 
 _ENGINES = []          # [(model_x, model_adj, N, device, fingerprint, Engine)], most recent last
@@ -92,7 +92,7 @@ def _make(sde_x, sde_adj, shape_x, shape_adj, predictor, corrector, snr, scale_e
             # the reference fails here too: RSDE.sde returns the float 0. as the diffusion (sde.py:91) and
             # EulerMaruyamaPredictor.update_fn indexes it (solver.py:52)
             raise TypeError("'float' object is not subscriptable")
-        dev = torch.device(device if device != "cuda" else f"cuda:{torch.cuda.current_device()}")
+        dev = resolve_device(device)
         eng = _engine_for(model_x, model_adj, N, dev)
         flags = init_flags.to(dev, torch.float32)
         seed = fresh_seed()

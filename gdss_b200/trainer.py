@@ -19,7 +19,7 @@ import torch
 
 from . import _lib
 from ._lib import check, lib, require_cuda
-from .engine import describe_network, model_state, pack_network, state_keys
+from .engine import describe_network, model_state, pack_network, resolve_device, state_keys
 from .losses import _marginal
 from .optim import FusedAdamEMA, allreduce_grads, flatten_state, unflatten_state
 from .sde import sde_kind
@@ -104,7 +104,7 @@ class DSMTrainStep:
                  reduce_mean=False, eps=1e-5, device="cuda", shard=None, use_graph=False):
         require_cuda()
         self.L = lib()
-        self.dev = torch.device(device if device != "cuda" else f"cuda:{torch.cuda.current_device()}")
+        self.dev = resolve_device(device)
         self.N = int(n_nodes)
         self.sde_x, self.sde_adj, self.eps, self.reduce_mean = sde_x, sde_adj, eps, bool(reduce_mean)
         self.kx, self.ka = sde_kind(sde_x), sde_kind(sde_adj)
@@ -213,7 +213,6 @@ class DSMTrainStep:
             for net in (self.x, self.a):
                 if not hasattr(net.opt, "consts"):
                     net.opt.consts = torch.zeros(4, device=dev)
-                    net.opt._consts_host = torch.zeros(4).pin_memory()
             torch.cuda.synchronize(dev)
             graph = torch.cuda.CUDAGraph()
             before = self.L.gdss_launch_count()
