@@ -438,7 +438,8 @@ def run_reference_arm(args, wl, weights):
 def workload_config(args, wl, B):
     world = max(1, int(os.environ.get("WORLD_SIZE", "1")))
     return {"workload": wl["desc"], "batch": B, "batch_per_gpu": B // world if args.impl != "reference" else B,
-            "sharding": f"{world} contiguous shards of independent graphs, one 4-float all-reduce per solver phase" if world > 1 else "none",
+            "sharding": "none (CPU arm: rank 0 alone runs it)" if args.impl == "reference" else
+                        f"{world} contiguous shards of independent graphs, one 4-float all-reduce per solver phase" if world > 1 else "none",
             "flags": args.flags, "solver_steps_per_sample": 1000,
             "step": "one reverse-diffusion solver step over the whole batch", "l2": "inputs larger than L2 (per-step working "
             "set = edge-channel stacks >> 126 MB at B=10000)" if B * wl["N"] ** 2 * 46 * 4 > 126e6 else "working set fits L2",
