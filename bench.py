@@ -36,21 +36,23 @@ WORKLOADS = {
     "zinc250k_v2": dict(ckpt="zinc250k_v2", N=38, F=9, B=10000, sde_x=("VP", .1, 1.), sde_adj=("VE", .2, 1.),
                         predictor="Reverse", corrector="Langevin", snr=.2, scale_eps=.8, evals=2,
                         flop_eval=6.504e6 + 5.849e7, flop_final=2 * 1444 * (46 * 92 + 92 * 92 + 92), flop_final_x=2 * 38 * (41 * 82 + 82 * 82 + 82 * 9), cpu_B=32, cpu_steps=4,
+                        transcendentals=(306e3, 646e3),
                         desc="C3 ZINC250k v2 (N=38, F=9, ScoreNetworkX_GMH + ScoreNetworkA) Reverse+Langevin snr .2 scale_eps .8"),
     "qm9_s4": dict(ckpt="qm9", N=9, F=4, B=10000, sde_x=("VE", .1, 1.), sde_adj=("VE", .1, 1.), predictor="S4",
-                   corrector="None", snr=.2, scale_eps=.7, evals=1, flop_eval=1.561e5 + 1.260e6,
+                   corrector="None", snr=.2, scale_eps=.7, evals=1, flop_eval=1.561e5 + 1.260e6, transcendentals=(6.55e3, 16.6e3),
                    flop_final=2 * 81 * (22 * 44 + 44 * 44 + 44), flop_final_x=2 * 9 * (36 * 72 + 72 * 72 + 72 * 4), cpu_B=1000, cpu_steps=8,
                    desc="C2 QM9 (N=9, F=4, ScoreNetworkX + ScoreNetworkA) S4 snr .2 scale_eps .7"),
     "community_small": dict(ckpt="community_small", N=20, F=10, B=100, sde_x=("VP", .1, 1.), sde_adj=("VP", .1, 1.),
                             predictor="Euler", corrector="Langevin", snr=.05, scale_eps=.7, evals=2,
                             flop_eval=2.953e6 + 1.663e7, flop_final=2 * 400 * (38 * 76 + 76 * 76 + 76), cpu_B=100,
+                            transcendentals=(59.5e3, 102.9e3),
                             cpu_steps=8, desc="C1 community_small (N=20) Euler+Langevin"),
     "enzymes": dict(ckpt="enzymes", N=125, F=10, B=64, sde_x=("VP", .1, 1.), sde_adj=("VE", .2, 1.), predictor="S4",
-                    corrector="None", snr=.15, scale_eps=.7, evals=1, flop_eval=5.030e7 + 8.747e8,
+                    corrector="None", snr=.15, scale_eps=.7, evals=1, flop_eval=5.030e7 + 8.747e8, transcendentals=(3.17e6, 5.22e6),
                     flop_final=2 * 15625 * (54 * 108 + 108 * 108 + 108), cpu_B=8, cpu_steps=3, ema=True,
                     desc="C4 ENZYMES (N=125) S4"),
     "grid": dict(ckpt="grid", N=361, F=5, B=8, sde_x=("VP", .1, 1.), sde_adj=("VP", .2, .8), predictor="Reverse",
-                 corrector="Langevin", snr=.1, scale_eps=.7, evals=2, flop_eval=1.639e8 + 7.113e9,
+                 corrector="Langevin", snr=.1, scale_eps=.7, evals=2, flop_eval=1.639e8 + 7.113e9, transcendentals=(26.2e6, 43.0e6),
                  flop_final=2 * 130321 * (54 * 108 + 108 * 108 + 108), cpu_B=1, cpu_steps=2, ema=True,
                  desc="C4 grid (N=361) Reverse+Langevin"),
 }
@@ -360,6 +362,20 @@ def measured_peaks():
         d = json.load(open(p))
         return d, "measured (MEASURED_PEAKS.json)"
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "sm_max_mhz": 1965.0}, "fallback"
+
+
+def mufu_ceiling(wl, graphs_per_s, sm_mhz, n_gpus=1, sms=148):
+    """BASELINE.md 3's secondary ceiling: the tanh / ELU elements of the reference's dense formulation (per joint evaluation
+    and graph, at padded N) against the special-function pipe, 16 results per clock and SM.  One element is counted as ONE
+    MUFU operation, as BASELINE.md counts them (the kernels spend ex2 + rcp on a tanh, and skip padded nodes and the
+    symmetric half, so this is a dense-equivalent rate like `roofline.achieved`)."""
+    tanh, elu = wl["transcendentals"]
+    per_graph = (tanh + elu) * wl["evals"] * 1000.0                     # per sampled graph (1000 solver steps)
+    peak = sms * 16 * float(sm_mhz) * 1e6 * n_gpus
+    return {"pipe": "MUFU (16 / clk / SM)", "elements_per_graph_step": (tanh + elu) * wl["evals"], "peak_elements_per_s": peak,
+            "ceiling_graphs_per_s": peak / per_graph, "achieved_elements_per_s": graphs_per_s * per_graph,
+            "frac": graphs_per_s * per_graph / peak,
+            "note": "dense-equivalent element count of the reference formulation (BASELINE.md 3), one MUFU operation per element"}
 
 
 def measured_traffic(workload):
@@ -673,6 +689,11 @@ def main():
                               peak_tc / 6.0, "tcgen05 tf32 / 3 (3xTF32), from the measured bf16 peak")
         if roofline is None:
             roofline = roofline_final
+        if roofline is not None:
+            try:                                          # additive key; never allowed to cost the line
+                roofline["mufu_ceiling"] = mufu_ceiling(wl, value, clk.get("sm_mhz") or peaks["sm_max_mhz"], world)
+            except Exception as exc:
+                roofline["mufu_ceiling"] = {"unavailable": repr(exc)[:120]}
     # ---- extra lines (one GPU): worst-case flags, the network evaluated without dead-chain elimination, the other BASELINE
     # configurations -- each `min(R, 3)` regions of K steps, median
     extras = None

@@ -412,3 +412,16 @@ def test_adam_step_constants_follow_torch_and_the_reference_ema():
     rc = L.gdss_adam_step_consts(0.005, 0.9, 0.999, 3, 0.5, -1, C.cast(out, C.c_void_p))      # -1: the decay as it is
     assert rc == 0 and abs(out[3] - 0.5) < 1e-7
     assert L.gdss_adam_step_consts(0.005, 0.9, 0.999, 0, 0.999, 0, C.cast(out, C.c_void_p)) < 0       # step is 1-based
+
+
+def test_bench_secondary_ceiling_follows_baseline_md():
+    """the MUFU ceiling of C3 is ~2.4 k graphs/s per GPU (306 k tanh + 646 k ELU elements per joint
+    evaluation, two evaluations per step, 148 SMs x 16 results per clock at 1965 MHz); the reported fraction is the achieved
+    dense-equivalent element rate against it and scales with the number of GPUs."""
+    import bench
+    c = bench.mufu_ceiling(bench.WORKLOADS["zinc250k_v2"], 1214.07, 1965.0)
+    assert abs(c["ceiling_graphs_per_s"] - 2443.9) < 1 and abs(c["frac"] - 1214.07 / c["ceiling_graphs_per_s"]) < 1e-12
+    c8 = bench.mufu_ceiling(bench.WORKLOADS["zinc250k_v2"], 8000.0, 1965.0, n_gpus=8)
+    assert abs(c8["ceiling_graphs_per_s"] - 8 * c["ceiling_graphs_per_s"]) < 1e-6
+    for wl in bench.WORKLOADS.values():
+        assert len(wl["transcendentals"]) == 2
