@@ -425,3 +425,61 @@ def test_bench_secondary_ceiling_follows_baseline_md():
     assert abs(c8["ceiling_graphs_per_s"] - 8 * c["ceiling_graphs_per_s"]) < 1e-6
     for wl in bench.WORKLOADS.values():
         assert len(wl["transcendentals"]) == 2
+
+
+def test_load_sampling_fn_forwards_the_reference_configs(monkeypatch):
+    """utils/loader.py:121-147: the sampler closure is built from (config_train, config.sampler, config.sample, device) -- here
+    the checkpoint's own `model_config` (plain dict or attribute objects, as the reference's EasyDict gives them) and the
+    sampler / sample blocks of config/sample_zinc250k.yaml and config/sample_qm9.yaml: 10 000-graph shapes for the molecule sets,
+    the data batch size otherwise, S4_solver for predictor 'S4', `cuda:<first id>` for a device list."""
+    from types import SimpleNamespace
+    from gdss_b200 import solver
+    from gdss_b200.ckpt import load_ckpt
+    seen = []
+    monkeypatch.setattr(solver, "_make", lambda *a, **k: seen.append((a, k)) or "closure")
+
+    def ns(d):
+        return SimpleNamespace(**{k: ns(v) if isinstance(v, dict) else v for k, v in d.items()})
+
+    sample = dict(use_ema=False, noise_removal=True, probability_flow=False, eps=1e-4, seed=42)
+    zinc = load_ckpt("zinc250k_v2")["model_config"]
+    module = dict(predictor="Reverse", corrector="Langevin", snr=0.2, scale_eps=0.9, n_steps=1)
+    for cfg, mod, smp in ((zinc, module, sample), (ns(zinc), ns(module), ns(sample))):
+        assert solver.load_sampling_fn(cfg, mod, smp, [3, 4]) == "closure"
+        a, k = seen.pop()
+        sde_x, sde_adj, shape_x, shape_adj, pred, corr, snr, seps, n_steps, pf, cont, denoise, eps, dev, s4 = a
+        assert (sde_x.kind, sde_x.beta_0, sde_x.beta_1, sde_x.N) == ("VP", 0.1, 1.0, 1000)
+        assert (sde_adj.kind, sde_adj.sigma_min, sde_adj.sigma_max, sde_adj.N) == ("VE", 0.2, 1.0, 1000)
+        assert shape_x == (10000, 38, 9) and shape_adj == (10000, 38, 38)
+        assert (pred, corr, snr, seps, n_steps, pf, cont, denoise, eps, dev, s4) == \
+            ("Reverse", "Langevin", 0.2, 0.9, 1, False, True, True, 1e-4, "cuda:3", False)
+    qm9 = load_ckpt("qm9")["model_config"]
+    assert solver.load_sampling_fn(qm9, dict(predictor="S4", corrector="None", snr=0.2, scale_eps=0.7, n_steps=1), sample, "cuda:0")
+    a, _ = seen.pop()
+    assert a[2] == (10000, 9, 4) and a[-1] is True and a[-2] == "cuda:0"
+    com = load_ckpt("community_small")["model_config"]
+    assert solver.load_sampling_fn(com, dict(predictor="Euler", corrector="Langevin", snr=0.05, scale_eps=0.7, n_steps=1), sample, "cuda")
+    a, _ = seen.pop()
+    assert a[2] == (com["data"]["batch_size"], 20, 10) and a[3] == (com["data"]["batch_size"], 20, 20) and a[-1] is False
+
+
+def test_sampling_weights_apply_the_ema_shadow_like_the_reference_sampler():
+    """sampler.py:47-52 / utils/ema.py:37-47: with `sample.use_ema` the i-th parameter is overwritten by the i-th shadow
+    parameter (ENZYMES, grid ship EMA and ask for it; QM9 has none); a shadow list that does not fit the state_dict is refused."""
+    from gdss_b200.ckpt import ema_weights, load_ckpt, sampling_weights
+    ck = load_ckpt("enzymes")
+    sdx, px, sda, pa = sampling_weights(ck)                       # the checkpoint's own config asks for EMA
+    raw_x, _, raw_a, _ = sampling_weights(ck, use_ema=False)
+    assert list(sdx) == list(raw_x) and list(sda) == list(raw_a) and px["model_type"] == "ScoreNetworkX"
+    for sd, raw, ema in ((sdx, raw_x, ck["ema_x"]), (sda, raw_a, ck["ema_adj"])):
+        for (k, v), s in zip(sd.items(), ema["shadow_params"]):
+            assert torch.equal(v, s.float()) and v.shape == raw[k].shape
+        assert max(float((sd[k] - raw[k]).abs().max()) for k in sd) > 0          # the shadow differs from the raw weights
+    q = load_ckpt("qm9")
+    assert all(torch.equal(a, b) for a, b in zip(sampling_weights(q)[0].values(), q["x_state_dict"].values()))
+    with pytest.raises(ValueError):
+        ema_weights(raw_x, {"shadow_params": ck["ema_x"]["shadow_params"][:-1]})
+    bad = list(ck["ema_x"]["shadow_params"])
+    bad[0] = bad[0].reshape(-1)
+    with pytest.raises(ValueError):
+        ema_weights(raw_x, {"shadow_params": bad})
